@@ -1,0 +1,267 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+TEST INFRASTRUCTURE ONLY.  Usage:  python oracle/gen_golden.py [--check-only]
+
+Produces
+  * the six RNG-free known-answer traces of SURVEY.md Appendix C (KAT A-F) and checks
+    their totals and SHA-256 prefixes against the table there,
+  * seeded random-policy traces for every reward variant over several domains,
+  * the hard-coded-agent trace of BASELINE config 1 (seed 1),
+  * a semi-aggregated observation-layout trace,
+  * torch actor forward / Categorical log-prob vectors and PPO return vectors
+    (src/PPOmodules.py:53-63, 128-137).
+The fixtures are small (int16/int32 arrays, compressed) and are committed; the GPU box
+never sees /root/reference.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as H  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+DOMS = {
+    "A": dict(N=2, C=3, L=2, prios=[5], lens=[4], probs=[1], fix=[3], mult=2, newJobs=1),
+    "B": dict(N=4, C=4, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7], mult=1,
+              newJobs=1),
+    "C": dict(N=2, C=3, L=3, prios=[2, 4, 8], lens=[5, 5, 5], probs=[1 / 3] * 3, fix=[1], mult=1,
+              newJobs=1),
+    "E": dict(N=2, C=2, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7], mult=1,
+              newJobs=1),
+    "F": dict(N=8, C=8, L=4, prios=[3, 10, 6], lens=[6, 3, 2], probs=[0.5, 0.2, 0.3],
+              fix=[2, 7, 4], mult=1, newJobs=2),
+    # extra domains for random traces
+    "G": dict(N=3, C=5, L=2, prios=[1, 7, 4, 9], lens=[1, 2, 7, 3], probs=[0.1, 0.4, 0.3, 0.2],
+              fix=[1, 5, 2, 6], mult=3, newJobs=1),
+    "H": dict(N=5, C=2, L=4, prios=[6, 2], lens=[2, 9], probs=[0.5, 0.5], fix=[4, 1], mult=1,
+              newJobs=3),
+    "S": dict(N=1, C=1, L=1, prios=[3], lens=[2], probs=[1], fix=[2], mult=1, newJobs=1),
+}
+
+# SURVEY.md Appendix C table
+KAT_EXPECT = {
+    "A": dict(mode="fix", steps=200, ag=[371, 314], auc=305, acc=105, term=99, off=525.0,
+              price=0.0, draws=102, sha="3b70e5b44bfe06e4"),
+    "B": dict(mode="fix", steps=200, ag=[41, 20, 7, 32], auc=464, acc=162, term=132, off=703.0,
+              price=0.0, draws=144, sha="3d1f2b32aaf7b658"),
+    "C": dict(mode="free_comm", steps=200, ag=[-223, -212], auc=435, acc=137, term=90, off=628.0,
+              price=98.5, draws=96, sha="7e87c7df7e172bd2"),
+    "D": dict(mode="free_ncomm", steps=200, ag=[-223, -212], auc=435, acc=137, term=90,
+              off=628.0, price=318.0, draws=96, sha="7e87c7df7e172bd2"),
+    "E": dict(mode="agg", steps=200, ag=[99, 7], auc=189, acc=102, term=68, off=397.0, price=0.0,
+              draws=74, sha="071a520f139e5e1e"),
+    "F": dict(mode="fix", steps=100, ag=[23, 34, 43, 21, 21, -16, 9, 28], auc=626, acc=179,
+              term=147, off=928.0, price=0.0, draws=176, sha="c74447fe2bfc3bd1"),
+}
+
+
+def kat_sha(tr, mode):
+    """Re-serialise a recorded trace exactly as the SURVEY App. C generator hashed it."""
+    h = hashlib.sha256()
+    T = tr["done"].shape[0]
+    N, L = tr["slot_prio"].shape[1:]
+    for s in range(T):
+        offers = []
+        for i in range(N):
+            for q in range(L):
+                if tr["off_core"][s, i, q] > 0:
+                    offers.append((int(tr["off_id"][s, i, q]), i + 1, int(tr["off_recip"][s, i, q]),
+                                   int(tr["off_core"][s, i, q]), q, int(tr["off_price"][s, i, q]),
+                                   int(tr["off_time"][s, i, q])))
+        offers.sort()
+        na, nt = int(tr["n_accepted"][s]), int(tr["n_term"][s])
+        accR = tr["r_acceptor"][s]
+        if mode != "agg":
+            accR = accR.reshape(accR.shape[0], accR.shape[1], 1)
+        state = dict(
+            s=s, owners=tr["core_owner"][s].tolist(), cprio=tr["core_prio"][s].tolist(),
+            crem=tr["core_rem"][s].tolist(), cjob=tr["core_jobid"][s].tolist(),
+            slots=[[(int(tr["slot_prio"][s, i, q]), int(tr["slot_rem"][s, i, q]),
+                     int(tr["slot_jobid"][s, i, q]), int(tr["slot_kind"][s, i, q]),
+                     int(tr["slot_wait"][s, i, q])) for q in range(L)] for i in range(N)],
+            offers=offers,
+            accepted=[tuple(int(x) for x in tr["accepted"][s, k]) for k in range(na)],
+            term=[tuple(int(x) for x in tr["term"][s, k]) for k in range(nt)],
+            aa=tr["in_auc"][s].tolist(), accR=accR.astype(int).tolist(),
+            aucR=tr["r_auctioneer"][s].tolist(), agR=tr["r_agent"][s].tolist(),
+            done=bool(tr["done"][s]))
+        h.update(json.dumps(state, sort_keys=True).encode())
+    return h.hexdigest()[:16]
+
+
+def pack(tr, dom, mode, agent_kind="divided"):
+    """Shrink dtypes and attach the domain description."""
+    out = {}
+    for k, v in tr.items():
+        v = np.asarray(v)
+        if v.dtype == np.int32 and v.size and np.abs(v).max() < 32000 and k not in (
+                "core_jobid", "slot_jobid", "core_birth", "slot_birth", "round"):
+            v = v.astype(np.int16)
+        out[k] = v
+    meta = dict(dom)
+    meta["mode"] = mode
+    meta["agent_kind"] = agent_kind
+    meta.setdefault("episodeLength", 100)
+    meta.setdefault("netZero", 0.5)
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    return out
+
+
+def save(name, tr):
+    os.makedirs(GOLDEN, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **tr)
+
+
+def gen_kats():
+    ok = True
+    for name, exp in KAT_EXPECT.items():
+        dom = DOMS["C" if name == "D" else name]
+        mode = exp["mode"]
+        free = mode.startswith("free")
+        tr = H.record_trace(dom, mode, exp["steps"], H.kat_policy(dom, free),
+                            u_source=H.kat_u_source())
+        got = dict(
+            ag=tr["r_agent"].sum(0).tolist(), auc=int(tr["r_auctioneer"].sum()),
+            acc=int(tr["n_accepted"].sum()), term=int(tr["n_term"].sum()),
+            off=float(tr["r_offer"].sum()), price=float(tr["r_price"].sum()),
+            draws=int(tr["total_draws"]), sha=kat_sha(tr, mode))
+        for k, v in got.items():
+            if exp[k] != v:
+                ok = False
+                print(f"KAT {name}: MISMATCH {k}: survey {exp[k]} vs harness {v}")
+        assert int(tr["last_jobid"]) == got["draws"]
+        print(f"KAT {name}: {got}")
+        save("kat_" + name, pack(tr, dom, mode))
+    return ok
+
+
+RANDOM_TRACES = [
+    # name, dom, mode, steps, seed
+    ("rand_fix_B", "B", "fix", 400, 11),
+    ("rand_fix_A", "A", "fix", 300, 12),
+    ("rand_fix_G", "G", "fix", 300, 13),
+    ("rand_fix_H", "H", "fix", 300, 14),
+    ("rand_fix_S", "S", "fix", 120, 15),
+    ("rand_freec_C", "C", "free_comm", 400, 21),
+    ("rand_freen_C", "C", "free_ncomm", 400, 22),
+    ("rand_freec_G", "G", "free_comm", 300, 23),
+    ("rand_freen_F", "F", "free_ncomm", 150, 24),
+    ("rand_agg_E", "E", "agg", 400, 31),
+    ("rand_agg_B", "B", "agg", 300, 32),
+    ("rand_fix_F", "F", "fix", 150, 33),
+]
+
+
+def gen_random():
+    for name, dk, mode, steps, seed in RANDOM_TRACES:
+        dom = DOMS[dk]
+        free = mode.startswith("free")
+        rng = np.random.default_rng(seed)
+        tr = H.record_trace(dom, mode, steps, H.random_policy(dom, free, rng), seed=seed)
+        print(f"{name}: accepted={int(tr['n_accepted'].sum())} term={int(tr['n_term'].sum())} "
+              f"maxchain={int(tr['chain_len'].max())} draws={int(tr['total_draws'])}")
+        save(name, pack(tr, dom, mode))
+
+
+def gen_hardcoded():
+    dom = DOMS["A"]
+    tr = H.record_trace(dom, "fix", 2000, H.hardcoded_policy(), agent_kind="hardcoded", seed=1)
+    tot = tr["r_agent"].sum(0).tolist()
+    print("hardcoded cfg1 seed1: sum agentReward", tot, "maxchain", int(tr["chain_len"].max()))
+    assert tot == [4018, 3941], tot  # SURVEY App. C seeded trace
+    # keep the first 400 steps (the rest only checks the survey total above)
+    keep = {k: (v[:400] if (isinstance(v, np.ndarray) and v.ndim and v.shape[0] == 2000) else v)
+            for k, v in tr.items()}
+    save("hardcoded_A", pack(keep, dom, "fix", "hardcoded"))
+
+
+def gen_aggregated_obs():
+    dom = DOMS["E"]
+    rng = np.random.default_rng(41)
+    tr = H.record_trace(dom, "agg", 120, H.random_policy(dom, False, rng, auctioneer="first"),
+                        agent_kind="aggregated", seed=41)
+    save("aggobs_E", pack(tr, dom, "agg", "aggregated"))
+
+
+def gen_torch_vectors():
+    """Actor forward / log-prob / returns vectors from the reference's torch code."""
+    import torch
+    m = H.import_reference()
+    P = m.P
+    torch.manual_seed(7)
+    out = {}
+    # (in, A, h) of the divided units at cfg2 / cfg3 and one aggregated head
+    for tag, (nin, A, h) in dict(acc_cfg3=(15, 7, 16), off_cfg3=(8, 4, 16), price_cfg3=(4, 9, 16),
+                                 acc_cfg2=(27, 13, 16), off_cfg2=(10, 5, 16),
+                                 aggoff=(12, 64, 32)).items():
+        net = P.ActorCritic(nin, A, h)
+        x = torch.randint(-2, 11, (64, nin)).float()
+        with torch.no_grad():
+            probs = net.actor(x)
+            dist = P.Categorical(probs)
+            act = dist.sample()
+            lp = dist.log_prob(act)
+            val = net.critic(x).squeeze(-1)
+            ent = dist.entropy()
+        sd = net.state_dict()
+        for k, v in sd.items():
+            out[f"{tag}.{k}"] = v.numpy()
+        out[f"{tag}.x"] = x.numpy()
+        out[f"{tag}.probs"] = probs.numpy()
+        out[f"{tag}.action"] = act.numpy().astype(np.int32)
+        out[f"{tag}.logprob"] = lp.numpy()
+        out[f"{tag}.value"] = val.numpy()
+        out[f"{tag}.entropy"] = ent.numpy()
+    # returns (src/PPOmodules.py:128-137) through the reference's own update() prologue
+    from collections import deque
+    rng = np.random.default_rng(5)
+    for tag, (T, gamma) in dict(ret_a=(200, 0.5), ret_b=(200, 0.8733333333333333),
+                                ret_c=(3, 0.5), ret_d=(57, 0.95)).items():
+        r = rng.integers(-6, 12, T).astype(np.float64)
+        if tag == "ret_c":
+            r = np.array([1.0, 0.0, 2.0])
+        if tag == "ret_d":
+            r = r + 0.5 * rng.integers(0, 2, T)
+        rewards = deque([])
+        disc = 0
+        for reward in reversed(r.tolist()):
+            disc = reward + (gamma * disc)
+            rewards.appendleft(disc)
+        raw = np.array(rewards, np.float64)
+        t = torch.tensor(rewards, dtype=torch.float32)
+        t = (t - t.mean()) / (t.std() + 1e-7)
+        out[f"{tag}.r"] = r
+        out[f"{tag}.gamma"] = np.float64(gamma)
+        out[f"{tag}.raw"] = raw
+        out[f"{tag}.norm"] = t.numpy()
+    os.makedirs(GOLDEN, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN, "torch_vectors.npz"), **out)
+    print("torch vectors:", len(out), "arrays")
+
+
+def main():
+    if not os.path.isdir(H.REFERENCE_SRC):
+        raise SystemExit("reference not present; golden fixtures can only be regenerated in "
+                         "the build container")
+    ok = gen_kats()
+    gen_random()
+    gen_hardcoded()
+    gen_aggregated_obs()
+    gen_torch_vectors()
+    print("KAT table check:", "OK" if ok else "MISMATCH")
+    sz = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
+    print("golden size: %.1f KiB" % (sz / 1024))
+    if not ok:
+        raise SystemExit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,230 @@
+"""ctypes wrapper around oracle/libmsched_oracle.so (CPU checker; TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libmsched_oracle.so")
+
+MAX_KINDS = 16
+MODES = {"fix": 0, "free_comm": 1, "free_ncomm": 2, "agg": 3}
+TIE_FIRST, TIE_PHILOX = 0, 1
+
+
+class MsorConfig(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("N", C.c_int32), ("C", C.c_int32), ("L", C.c_int32), ("J", C.c_int32),
+        ("newJobs", C.c_int32), ("rewardMultiplier", C.c_int32), ("episodeLength", C.c_int32),
+        ("freePrices", C.c_int32), ("rewardMode", C.c_int32), ("chainCap", C.c_int32),
+        ("tieMode", C.c_int32),
+        ("prio", C.c_int32 * MAX_KINDS), ("len", C.c_int32 * MAX_KINDS),
+        ("fix", C.c_int32 * MAX_KINDS),
+        ("cumProb", C.c_double * MAX_KINDS),
+        ("netZeroOfferReward", C.c_double),
+        ("seed", C.c_uint64),
+        ("envOffset", C.c_int64),
+    ]
+
+
+def build(force=False):
+    src = os.path.join(HERE, "msched_oracle.c")
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", HERE, "-s"])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(LIB)
+        _lib.msor_create.restype = C.c_void_p
+        _lib.msor_create.argtypes = [C.POINTER(MsorConfig)]
+        _lib.msor_destroy.argtypes = [C.c_void_p]
+        _lib.msor_reset.argtypes = [C.c_void_p]
+        _lib.msor_step_range.argtypes = [C.c_void_p, C.c_int, C.c_int] + [C.c_void_p] * 18
+        _lib.msor_observe.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        _lib.msor_export.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 9
+        _lib.msor_returns.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]
+        _lib.msor_mlp_forward.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
+                                          + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 4)
+        _lib.msor_philox.argtypes = [C.c_void_p] * 3
+    return _lib
+
+
+def cum_prob(probabilities):
+    """World.accProbabilities (src/world.py:220-222): Python float prefix sums."""
+    return [sum(probabilities[: i + 1]) for i in range(len(probabilities))]
+
+
+def make_config(B, dom, mode, chain_cap=32, tie_mode=TIE_FIRST, seed=0, env_offset=0):
+    cfg = MsorConfig()
+    J = len(dom["prios"])
+    cfg.B, cfg.N, cfg.C, cfg.L, cfg.J = B, dom["N"], dom["C"], dom["L"], J
+    cfg.newJobs = dom.get("newJobs", 1)
+    cfg.rewardMultiplier = dom.get("mult", 1)
+    cfg.episodeLength = dom.get("episodeLength", 100)
+    cfg.freePrices = int(mode.startswith("free"))
+    cfg.rewardMode = MODES[mode]
+    cfg.chainCap = chain_cap
+    cfg.tieMode = tie_mode
+    fix = list(dom.get("fix", [0] * J))
+    fix = (fix + [0] * J)[:J]
+    cp = cum_prob(list(dom["probs"]))
+    for k in range(J):
+        cfg.prio[k] = dom["prios"][k]
+        cfg.len[k] = dom["lens"][k]
+        cfg.fix[k] = fix[k]
+        cfg.cumProb[k] = cp[k]
+    cfg.netZeroOfferReward = dom.get("netZero", 0.5)
+    cfg.seed = seed
+    cfg.envOffset = env_offset
+    return cfg
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Oracle:
+    """B independent reference worlds advanced in lock-step on the CPU."""
+
+    def __init__(self, B, dom, mode, chain_cap=32, tie_mode=TIE_FIRST, seed=0, env_offset=0):
+        self.cfg = make_config(B, dom, mode, chain_cap, tie_mode, seed, env_offset)
+        self.B, self.N, self.C, self.L = B, dom["N"], dom["C"], dom["L"]
+        self.NL = self.N * self.L
+        self.nj = self.cfg.newJobs
+        self.K = chain_cap
+        self.agg = mode == "agg"
+        self.RL = 1 if self.agg else self.L
+        self.RC = 1 if self.agg else self.C
+        self.h = lib().msor_create(C.byref(self.cfg))
+        if not self.h:
+            raise ValueError("bad oracle config")
+        lib().msor_reset(self.h)
+        B, N, Cc = self.B, self.N, self.C
+        self.r_offer = np.zeros((B, N, self.RL), np.float64)
+        self.r_price = np.zeros((B, N, self.RL), np.float64)
+        self.r_acceptor = np.zeros((B, N, self.RC), np.int64)
+        self.r_auctioneer = np.zeros((B, Cc), np.int64)
+        self.r_agent = np.zeros((B, N), np.int64)
+        self.quality_sum = np.zeros(B, np.float64)
+        self.quality_cnt = np.zeros(B, np.int32)
+        self.done = np.zeros(B, np.uint8)
+        self.auc_out = np.zeros((B, Cc), np.int32)
+        self.n_accepted = np.zeros(B, np.int32)
+        self.n_term = np.zeros(B, np.int32)
+        self.flags = np.zeros(B, np.uint32)
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().msor_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def reset(self):
+        lib().msor_reset(self.h)
+
+    def step(self, offc, acc, auc=None, offp=None, spawn_u=None, spawn_kind=None, b0=0, b1=None):
+        """Argument order mirrors SchedulingEnv.step(offerActions, acceptorActions, auctioneer)."""
+        B = self.B
+        b1 = B if b1 is None else b1
+        offc = np.ascontiguousarray(offc, np.int32).reshape(B, self.N, self.L)
+        acc = np.ascontiguousarray(acc, np.int32).reshape(B, self.N, self.C)
+        auc = None if auc is None else np.ascontiguousarray(auc, np.int32).reshape(B, self.C)
+        offp = None if offp is None else np.ascontiguousarray(offp, np.int32).reshape(B, self.N, self.L)
+        if self.cfg.freePrices and offp is None:
+            raise ValueError("free prices need offp")
+        spawn_u = None if spawn_u is None else np.ascontiguousarray(spawn_u, np.float64).reshape(
+            B, self.N, self.nj)
+        spawn_kind = None if spawn_kind is None else np.ascontiguousarray(
+            spawn_kind, np.uint8).reshape(B, self.N, self.nj)
+        self._keep = (offc, acc, auc, offp, spawn_u, spawn_kind)
+        lib().msor_step_range(self.h, b0, b1, _p(offc), _p(offp), _p(acc), _p(auc), _p(spawn_u),
+                              _p(spawn_kind), _p(self.r_offer), _p(self.r_price),
+                              _p(self.r_acceptor), _p(self.r_auctioneer), _p(self.r_agent),
+                              _p(self.quality_sum), _p(self.quality_cnt), _p(self.done),
+                              _p(self.auc_out), _p(self.n_accepted), _p(self.n_term),
+                              _p(self.flags))
+
+    def observe(self, b):
+        N, Cc, L, NL = self.N, self.C, self.L, self.NL
+        W = 3 + 2 * NL
+        o = dict(obs_acc=np.zeros((N, Cc, W), np.int32), obs_off=np.zeros((N, L, 2 * Cc + 2), np.int32),
+                 obs_auc=np.zeros((Cc, W), np.int32), ids=np.zeros((N, Cc, NL), np.int32),
+                 auc_ids=np.zeros((Cc, NL), np.int32))
+        lib().msor_observe(self.h, b, _p(o["obs_acc"]), _p(o["obs_off"]), _p(o["obs_auc"]),
+                           _p(o["ids"]), _p(o["auc_ids"]))
+        return o
+
+    def export(self, b):
+        N, Cc, L, NL, K = self.N, self.C, self.L, self.NL, self.K
+        core = np.zeros((Cc, 7), np.int32)
+        slot = np.zeros((NL, 7), np.int32)
+        off = np.zeros((NL, 5), np.int32)
+        chain = np.zeros((Cc, K, 5), np.int32)
+        clen = np.zeros(Cc, np.int32)
+        accepted = np.zeros((Cc, 5), np.int32)
+        term = np.zeros((Cc, 8), np.int32)
+        tnorm = np.zeros(Cc, np.float64)
+        misc = np.zeros(6, np.int32)
+        lib().msor_export(self.h, b, _p(core), _p(slot), _p(off), _p(chain), _p(clen),
+                          _p(accepted), _p(term), _p(tnorm), _p(misc))
+        s = slot.reshape(N, L, 7)
+        f = off.reshape(N, L, 5)
+        return dict(
+            core_owner=core[:, 0], core_prio=core[:, 1], core_rem=core[:, 2], core_jobid=core[:, 3],
+            core_kind=core[:, 4], core_birth=core[:, 5], core_init=core[:, 6],
+            slot_prio=s[..., 0], slot_rem=s[..., 1], slot_jobid=s[..., 2], slot_kind=s[..., 3],
+            slot_wait=s[..., 4], slot_birth=s[..., 5], slot_init=s[..., 6],
+            off_core=f[..., 0], off_recip=f[..., 1], off_price=f[..., 2], off_time=f[..., 3],
+            off_id=f[..., 4], chain=chain, chain_len=clen, accepted=accepted, term=term,
+            term_norm=tnorm, round=int(misc[0]), job_counter=int(misc[1]),
+            n_accepted=int(misc[2]), n_term=int(misc[3]), flags=int(misc[4]),
+            term_revenue=int(misc[5]))
+
+
+def returns(rewards, gamma, normalise=True):
+    r = np.ascontiguousarray(rewards, np.float64)
+    T, M = r.shape
+    out = np.zeros((T, M), np.float32)
+    lib().msor_returns(_p(r), T, M, float(gamma), int(normalise), _p(out))
+    return out
+
+
+def mlp_forward(x, W1, b1, W2, b2, W3, b3, softmax=True, u=None):
+    x = np.ascontiguousarray(x, np.float32)
+    M, nin = x.shape
+    h = W1.shape[0]
+    A = W3.shape[0]
+    ws = [np.ascontiguousarray(w, np.float32) for w in (W1, b1, W2, b2, W3, b3)]
+    out = np.zeros((M, A), np.float32)
+    act = lp = None
+    if u is not None:
+        u = np.ascontiguousarray(u, np.float32)
+        act = np.zeros(M, np.int32)
+        lp = np.zeros(M, np.float32)
+    lib().msor_mlp_forward(_p(x), M, nin, h, A, *[_p(w) for w in ws], int(softmax), _p(out),
+                           _p(u), _p(act), _p(lp))
+    return out, act, lp
+
+
+def philox(ctr, key):
+    c = np.ascontiguousarray(ctr, np.uint32)
+    k = np.ascontiguousarray(key, np.uint32)
+    o = np.zeros(4, np.uint32)
+    lib().msor_philox(_p(c), _p(k), _p(o))
+    return o

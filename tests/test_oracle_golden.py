@@ -1,0 +1,123 @@
+"""CPU: the C restatement (oracle/) replayed against traces of the unmodified reference.
+
+The golden traces were produced by oracle/gen_golden.py from /root/reference;
+this is what pins the oracle.  Everything integer is compared bit-exactly; float rewards exactly
+(they are small dyadic rationals); the acception-quality mean within 1e-12 relative."""
+import numpy as np
+import pytest
+
+from helpers import assert_state_equal, golden_names, load_golden
+from oracle import oracle as O
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_replays_reference_trace(name):
+    tr, meta = load_golden(name)
+    T = tr["done"].shape[0]
+    free = meta["mode"].startswith("free")
+    orc = O.Oracle(1, meta, meta["mode"], chain_cap=32)
+    assert_state_equal(orc.export(0), tr, None, prefix=name)
+    obs = orc.observe(0)
+    for k in ("obs_acc", "obs_off", "obs_auc", "ids", "auc_ids"):
+        assert np.array_equal(obs[k], tr["init_" + k].astype(np.int32)), (name, "init", k)
+    for t in range(T):
+        orc.step(tr["in_offc"][t][None], tr["in_acc"][t][None], tr["in_auc"][t][None],
+                 offp=tr["in_offp"][t][None] if free else None, spawn_u=tr["in_spawn_u"][t][None])
+        e = orc.export(0)
+        assert e["flags"] == 0, (name, t, e["flags"])
+        assert_state_equal(e, tr, t, prefix=name)
+        assert e["round"] == int(tr["round"][t])
+        assert orc.n_accepted[0] == tr["n_accepted"][t] and orc.n_term[0] == tr["n_term"][t]
+        na, nt = int(tr["n_accepted"][t]), int(tr["n_term"][t])
+        assert np.array_equal(e["accepted"][:na], tr["accepted"][t][:na])
+        assert np.array_equal(e["term"][:nt, :5], tr["term"][t][:nt])
+        assert np.array_equal(orc.r_offer[0], tr["r_offer"][t]), (name, t, "r_offer")
+        assert np.array_equal(orc.r_price[0], tr["r_price"][t]), (name, t, "r_price")
+        assert np.array_equal(orc.r_acceptor[0], tr["r_acceptor"][t]), (name, t, "r_acceptor")
+        assert np.array_equal(orc.r_auctioneer[0], tr["r_auctioneer"][t]), (name, t)
+        assert np.array_equal(orc.r_agent[0], tr["r_agent"][t]), (name, t, "r_agent")
+        assert orc.done[0] == tr["done"][t]
+        assert orc.quality_cnt[0] == tr["quality_cnt"][t]
+        if tr["quality_cnt"][t] > 0:
+            mean = orc.quality_sum[0] / orc.quality_cnt[0]
+            assert mean == pytest.approx(float(tr["quality"][t]), rel=1e-12, abs=1e-12)
+        obs = orc.observe(0)
+        if meta["agent_kind"] != "aggregated":
+            for k in ("obs_acc", "obs_off"):
+                assert np.array_equal(obs[k], tr[k][t].astype(np.int32)), (name, t, k)
+        for k in ("obs_auc", "ids", "auc_ids"):
+            assert np.array_equal(obs[k], tr[k][t].astype(np.int32)), (name, t, k)
+    if "term_revenue" in tr and meta["mode"] == "fix":
+        assert e["term_revenue"] == int(tr["term_revenue"][-1])
+
+
+def test_oracle_semi_aggregated_observation_layout():
+    """AggregatedAgent layouts (src/Agent.py:82-140) are concatenations of the divided blocks."""
+    tr, meta = load_golden("aggobs_E")
+    N, C, L = meta["N"], meta["C"], meta["L"]
+    orc = O.Oracle(1, meta, meta["mode"])
+    for t in range(tr["done"].shape[0]):
+        orc.step(tr["in_offc"][t][None], tr["in_acc"][t][None], tr["in_auc"][t][None],
+                 spawn_u=tr["in_spawn_u"][t][None])
+        obs = orc.observe(0)
+        acc = obs["obs_acc"].reshape(N, -1).astype(np.float32)
+        assert np.array_equal(acc, tr["obs_acc"][t])
+        cores = obs["obs_off"][:, 0, : 2 * C]
+        slots = obs["obs_off"][:, :, 2 * C:].reshape(N, 2 * L)
+        assert np.array_equal(np.concatenate([cores, slots], 1), tr["obs_off"][t].astype(np.int32))
+
+
+def test_oracle_hardcoded_auctioneer_matches_reference_choice_when_unique():
+    """With in-oracle auction (auc=None, first-arg-max) the choice equals the recorded reference
+    auctioneer action whenever the arg-max is unique (ties are random in the reference)."""
+    tr, meta = load_golden("kat_B")  # KAT protocol = first arg-max: must match always
+    orc = O.Oracle(1, meta, meta["mode"])
+    for t in range(tr["done"].shape[0]):
+        orc.step(tr["in_offc"][t][None], tr["in_acc"][t][None], None,
+                 spawn_u=tr["in_spawn_u"][t][None])
+        assert np.array_equal(orc.auc_out[0], tr["in_auc"][t]), t
+        assert_state_equal(orc.export(0), tr, t)
+
+
+def test_oracle_returns_and_mlp_match_torch_vectors():
+    z = np.load(__import__("os").path.join(__import__("helpers").GOLDEN, "torch_vectors.npz"))
+    for tag in ("ret_a", "ret_b", "ret_c", "ret_d"):
+        r = z[tag + ".r"]
+        raw = O.returns(r[:, None], float(z[tag + ".gamma"]), normalise=False)[:, 0]
+        assert np.array_equal(raw, z[tag + ".raw"].astype(np.float32))
+        nrm = O.returns(r[:, None], float(z[tag + ".gamma"]), normalise=True)[:, 0]
+        np.testing.assert_allclose(nrm, z[tag + ".norm"], rtol=1e-5, atol=1e-6)
+    # SURVEY App. C arithmetic vector
+    nrm = O.returns(np.array([[1.0], [0.0], [2.0]]), 0.5)[:, 0]
+    np.testing.assert_allclose(nrm, [0.0, -0.9999998, 0.9999998], atol=1e-6)
+    for tag in ("acc_cfg3", "off_cfg3", "price_cfg3", "acc_cfg2", "off_cfg2", "aggoff"):
+        w = [z[f"{tag}.actor.{i}.{p}"] for i in (0, 2, 4) for p in ("weight", "bias")]
+        probs, _, _ = O.mlp_forward(z[tag + ".x"], *w)
+        np.testing.assert_allclose(probs, z[tag + ".probs"], rtol=2e-5, atol=1e-7)
+        wc = [z[f"{tag}.critic.{i}.{p}"] for i in (0, 2, 4) for p in ("weight", "bias")]
+        val, _, _ = O.mlp_forward(z[tag + ".x"], *wc, softmax=False)
+        np.testing.assert_allclose(val[:, 0], z[tag + ".value"], rtol=2e-5, atol=2e-6)
+        # log-prob of the torch-sampled action via Categorical semantics
+        p = probs[np.arange(len(probs)), z[tag + ".action"]] / probs.sum(1)
+        np.testing.assert_allclose(np.log(p), z[tag + ".logprob"], rtol=1e-4, atol=1e-5)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+        ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+        ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]),
+    ]
+    for ctr, key, exp in kat:
+        assert O.philox(ctr, key).tolist() == exp
+
+
+def test_arithmetic_vectors():
+    """round-half-even on float64 products."""
+    import math
+    for p, t, d, exp in [(3, 6, 1, 0), (3, 6, 3, 2), (10, 3, 2, 7), (7, 3, 3, 7)]:
+        assert round(p / t * d) == exp
+    assert [round(0.5), round(1.5), round(2.5)] == [0, 2, 2]
+    assert sum([1 / 6] * 6) == 1.0 or math.isclose(sum([1 / 6] * 6), 1.0)
