@@ -1,0 +1,200 @@
+/*
+ * msched.h -- C-ABI of the B200-native batched marl-scheduling rollout path.
+ *
+ * The reference (lr40/marl-scheduling) has no FFI layer: the path sits behind plain Python
+ * classes (SchedulingEnv.step/reset, World, Auctioneer, the PPO units).  This header is the
+ * boundary a maintainer would bind with ctypes from those classes; every entry point names
+ * the reference interface it replaces (file:line relative to the reference repo).  The
+ * Python binding shipped here is marl_scheduling_b200/_lib.py; INTEGRATION.md shows the
+ * reference-side stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are CALLER-OWNED DEVICE buffers unless
+ *     the name ends in _host; nothing is allocated after msched_create;
+ *   - every launch takes a cudaStream_t (passed as void*), is asynchronous and returns an int
+ *     status: 0 ok, <0 MSCHED_E_* (argument / shape / CUDA error, see msched_last_error);
+ *   - per-environment runtime faults are reported through the sticky uint32 flags word of the
+ *     result record (MSCHED_FLAG_*), never by aborting;
+ *   - one process per GPU, one handle per env shard; envs never communicate.
+ *
+ * Record streams (all env-major, one fixed-size record per environment, sizes from
+ * msched_get_layout; buffers must hold msched_padded_envs(B) records):
+ *   state   uint32[state_words]   opaque persistent state (cores, job slots, pending offers)
+ *   action  int16 [action_halfs]  acceptor idx [N][C] | offer core [N][L] | offer price [N][L]
+ *                                 | auctioneer idx [C] | spawn kind [N][newJobs]
+ *   result  uint32[result_words]  offer reward f32 [N][RL] | price reward f32 [N][RL]
+ *                                 | acceptor reward i32 [N][RC] | auctioneer reward i32 [C]
+ *                                 | agent reward i32 [N] | quality_sum f64 (lo,hi words)
+ *                                 | counts (quality_cnt | n_accepted<<8 | n_terminated<<16
+ *                                 | done<<24) | flags | auctioneer idx used, 2 x i16 per word
+ *   obs     int16 [obs_halfs]     dense reference-layout observations (Appendix B of SURVEY.md)
+ *   chain   uint32[C][chainCap][2] liability chains (src/world.py:238,285-289), touched
+ *                                 only on acceptance / termination
+ */
+#ifndef MSCHED_H
+#define MSCHED_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSCHED_ABI_VERSION 1
+#define MSCHED_MAX_KINDS 16
+#define MSCHED_TILE_ENVS 128 /* record buffers are padded to a multiple of this */
+
+/* status codes */
+#define MSCHED_OK 0
+#define MSCHED_E_ARG (-1)      /* bad argument / unsupported shape */
+#define MSCHED_E_CUDA (-2)     /* CUDA runtime error, see msched_last_error */
+#define MSCHED_E_NODEVICE (-3) /* no CUDA device: there is NO CPU fallback */
+#define MSCHED_E_STATE (-4)    /* state / chain buffer not bound */
+
+/* per-env fault flags (sticky, result record + state record) */
+#define MSCHED_FLAG_CHAIN_OVERFLOW 1u  /* liability chain longer than chainCap (entry dropped) */
+#define MSCHED_FLAG_COLLECTION_FULL 2u /* reference: raise in JobCollection.insertJob, src/world.py:133 */
+#define MSCHED_FLAG_ACTION_RANGE 4u    /* reference: assert in src/world.py:389,404 */
+#define MSCHED_FLAG_SPAWN_RANGE 8u     /* reference: UnboundLocalError in src/Agent.py:52-57 (Q13) */
+
+/* reward variants: src/Reward.py:146-212, :6-89 (commercial / non-commercial), :92-143 */
+enum {
+    MSCHED_REWARD_DIVIDED_FIXED = 0,
+    MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL = 1,
+    MSCHED_REWARD_DIVIDED_FREE_NONCOMMERCIAL = 2,
+    MSCHED_REWARD_AGGREGATED_FIXED = 3
+};
+
+/* who supplies the auctioneer's acceptor action (src/Auctioneer.py:95-102) */
+enum {
+    MSCHED_AUCTION_EXTERNAL = 0,     /* action record carries auctioneer idx [C] (parity mode) */
+    MSCHED_AUCTION_FIRST_MAX = 1,    /* in-kernel HardcodedAuctioneerAcceptor, first arg-max */
+    MSCHED_AUCTION_RANDOM_MAX = 2    /* in-kernel, uniformly random arg-max (Philox) */
+};
+
+/* where spawn draws come from (src/Agent.py:50-70) */
+enum {
+    MSCHED_SPAWN_PHILOX = 0, /* device Philox4x32-10, counter (global env, round, agent, k) */
+    MSCHED_SPAWN_KINDS = 1,  /* action record carries the job kind per (agent, k) */
+    MSCHED_SPAWN_U64 = 2     /* float64 draws u in [0,1) per (agent, k): recorded random.random() */
+};
+
+/* World(params) + SchedulingEnv(world, params): src/world.py:210-254,
+ * src/SchedulingEnvironment.py:22-30,253-259 */
+typedef struct MschedConfig {
+    int32_t abi_version;   /* MSCHED_ABI_VERSION */
+    int32_t B;             /* environments in this shard */
+    int32_t N, C, L, J;    /* numberOfAgents, numberOfCores, collectionLength, #job kinds */
+    int32_t newJobsPerRound, rewardMultiplier, episodeLength;
+    int32_t freePrices;    /* 0/1 */
+    int32_t rewardVariant; /* MSCHED_REWARD_* */
+    int32_t chainCapacity; /* liability-chain entries kept per core (default 32) */
+    int32_t auctionMode;   /* MSCHED_AUCTION_* */
+    int32_t spawnMode;     /* MSCHED_SPAWN_* */
+    int32_t prio[MSCHED_MAX_KINDS];     /* possibleJobPriorities */
+    int32_t len[MSCHED_MAX_KINDS];      /* possibleJobLengths (1..255) */
+    int32_t fixPrice[MSCHED_MAX_KINDS]; /* fixPricesList (fixed prices only) */
+    double cumProb[MSCHED_MAX_KINDS];   /* World.accProbabilities: float64 prefix sums */
+    double netZeroOfferReward;          /* src/Reward.py:29-33 */
+    uint64_t seed;                      /* Philox key */
+    int64_t envOffset;                  /* global index of env 0 of this shard (multi-GPU) */
+} MschedConfig;
+
+/* record geometry; element offsets inside each record (-1 = absent) */
+typedef struct MschedLayout {
+    int32_t padded_envs;
+    int32_t state_words;  /* uint32 per env */
+    int32_t action_halfs; /* int16 per env (even; action_halfs/2 is odd) */
+    int32_t result_words; /* uint32 per env (odd) */
+    int32_t obs_halfs;    /* int16 per env; 0 if the dense layout is infeasible (>32 KB/env) */
+    int32_t chain_words;  /* uint32 per env = C*chainCapacity*2 */
+    /* action record, int16 element offsets */
+    int32_t a_acceptor, a_offer_core, a_offer_price, a_auctioneer, a_spawn_kind;
+    /* result record, word offsets */
+    int32_t r_offer, r_price, r_acceptor, r_auctioneer, r_agent, r_quality, r_counts, r_flags,
+        r_auctioneer_idx;
+    int32_t RL, RC; /* reward row lengths: L,C (divided) or 1,1 (aggregated) */
+    /* obs record, int16 element offsets: acceptor [N][C][3+2NL], offer [N][L][2C+2],
+     * auctioneer [C][3+2NL], offer-ID tables [N][C][NL] and [C][NL] */
+    int32_t o_acceptor, o_offer, o_auctioneer, o_ids, o_auctioneer_ids;
+} MschedLayout;
+
+int msched_abi_version(void);
+const char *msched_last_error(void);
+int msched_padded_envs(int B);
+int msched_get_layout(const MschedConfig *cfg, MschedLayout *out);
+
+/* World.__init__ / SchedulingEnv.__init__ (src/world.py:210-254) */
+int msched_create(const MschedConfig *cfg, int device, void **handle);
+int msched_destroy(void *handle);
+
+/* bind the caller-owned persistent buffers (state: padded_envs*state_words uint32,
+ * chain: padded_envs*chain_words uint32) */
+int msched_bind_state(void *handle, void *state_dev, void *chain_dev);
+
+/* fresh worlds: all cores auctioneer-owned, collections empty, round 0, jobIDs from 1
+ * (World.__init__; note SchedulingEnv.reset itself resets nothing, src/SchedulingEnvironment.py:85-109) */
+int msched_reset(void *handle, void *stream);
+int msched_get_round(void *handle, int64_t *round);
+int msched_set_round(void *handle, int64_t round);
+
+/* One SchedulingEnv.step for every env (src/SchedulingEnvironment.py:32-83 =
+ * World.step1 src/world.py:295-334 + acception quality :174-192 + Reward.py + done),
+ * i.e. acceptance application, auction + core allocation, job progress/completion, offer
+ * creation, spawn refill, rewards.  spawn_u_dev: float64 [B][N][newJobs] for MSCHED_SPAWN_U64,
+ * else NULL. */
+int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_dev,
+                uint32_t *result_dev, void *stream);
+
+/* same call with HOST buffers (pinned recommended): H2D of the action records, the step, D2H of
+ * the result records, then stream synchronise.  staging buffers are owned by the handle. */
+int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_host,
+                     void *stream);
+
+/* Agent.gatherObservations + gatherDividedAuctioneerObservation (src/Agent.py:148-300,
+ * src/Auctioneer.py:20-77): dense reference-layout observations and offer-ID tables */
+int msched_observe_dense(void *handle, int16_t *obs_dev, void *stream);
+
+/* debug / parity: reference-shaped int32 dump of envs [env0, env0+count):
+ * core [C][7] owner,prio,rem,jobid,kind,birth,init ; slot [N*L][7] prio,rem,jobid,kind,wait,
+ * birth,init ; offer [N*L][5] core(0 none),recipient,price,time,offerID ;
+ * chain [C][chainCap][5] offerer,recipient,price,time,round (newest first, -1 pad) ;
+ * chain_len [C] ; misc [4] jobCounter, flags, 0, 0.  Device pointers, any may be NULL. */
+int msched_export_state(void *handle, int env0, int count, int32_t *core, int32_t *slot,
+                        int32_t *offer, int32_t *chain, int32_t *chain_len, int32_t *misc,
+                        void *stream);
+
+/* ---- policy side ----
+ * ActorCritic.act (src/PPOmodules.py:53-63) for a group of identically shaped nets:
+ * Linear(in,h)-Tanh-Linear(h,h)-Tanh-Linear(h,A)-Softmax, inverse-CDF categorical sample,
+ * Categorical.log_prob.  weights: float32, torch layout, per net
+ * [W1 h*in | b1 h | W2 h*h | b2 h | W3 A*h | b3 A]. */
+typedef struct MschedMlpGroup {
+    int32_t n_in, n_hidden, n_actions, n_nets;
+    const float *weights; /* device, n_nets * msched_mlp_param_count() floats */
+} MschedMlpGroup;
+
+int msched_mlp_param_count(int n_in, int n_hidden, int n_actions);
+
+/* x: int16 observations.  Unit u of env b is the row at x + b*env_stride + u*x_stride (int16
+ * elements; env_stride 0 means units*x_stride, i.e. a dense [M][x_stride] matrix) and is evaluated
+ * by net (u % n_nets).  M = n_envs*units rows, row index r = b*units + u.  seed/step select the
+ * Philox stream (counter = (row_offset + r, step)); u_override float32 [M] replaces the draws
+ * (parity tests).  action int32 [M], logprob float32 [M] (either may be NULL); probs float32
+ * [M][A] optional (NULL in production). */
+int msched_actor_forward(const MschedMlpGroup *nets, const int16_t *x, int x_stride,
+                         int64_t env_stride, int units, int M, uint64_t seed, uint64_t step,
+                         int64_t row_offset, const float *u_override, int32_t *action,
+                         float *logprob, float *probs, void *stream);
+
+/* PPO.update returns prologue (src/PPOmodules.py:128-137): G_t = r_t + gamma*G_{t+1} over
+ * the whole buffer in float64, cast to float32, optional (G-mean)/(std_unbiased+1e-7) per
+ * unit.  rewards/out: float32 [T][M] time-major. */
+int msched_returns(const float *rewards, int T, int M, double gamma, int normalise, float *out,
+                   void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSCHED_H */

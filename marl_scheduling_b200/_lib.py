@@ -1,0 +1,163 @@
+"""ctypes binding of include/msched.h (libmsched.so, built in-tree by marl_scheduling_b200/csrc).
+
+There is no CPU fallback: if the shared library is missing this module raises at import of the
+symbol table, and every launch fails with MSCHED_E_NODEVICE when no CUDA device is present.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmsched.so")
+CSRC = os.path.join(HERE, "csrc")
+
+ABI_VERSION = 1
+MAX_KINDS = 16
+TILE_ENVS = 128
+
+OK, E_ARG, E_CUDA, E_NODEVICE, E_STATE = 0, -1, -2, -3, -4
+FLAG_CHAIN_OVERFLOW, FLAG_COLLECTION_FULL, FLAG_ACTION_RANGE, FLAG_SPAWN_RANGE = 1, 2, 4, 8
+
+REWARD = {"fix": 0, "divided_fixed": 0, "free_comm": 1, "divided_free_commercial": 1,
+          "free_ncomm": 2, "divided_free_noncommercial": 2, "agg": 3, "aggregated_fixed": 3}
+AUCTION = {"external": 0, "first": 1, "first_max": 1, "random": 2, "random_max": 2}
+SPAWN = {"philox": 0, "kinds": 1, "u64": 2}
+
+
+class MschedConfig(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("B", C.c_int32),
+        ("N", C.c_int32), ("C", C.c_int32), ("L", C.c_int32), ("J", C.c_int32),
+        ("newJobsPerRound", C.c_int32), ("rewardMultiplier", C.c_int32),
+        ("episodeLength", C.c_int32), ("freePrices", C.c_int32), ("rewardVariant", C.c_int32),
+        ("chainCapacity", C.c_int32), ("auctionMode", C.c_int32), ("spawnMode", C.c_int32),
+        ("prio", C.c_int32 * MAX_KINDS), ("len", C.c_int32 * MAX_KINDS),
+        ("fixPrice", C.c_int32 * MAX_KINDS), ("cumProb", C.c_double * MAX_KINDS),
+        ("netZeroOfferReward", C.c_double), ("seed", C.c_uint64), ("envOffset", C.c_int64),
+    ]
+
+
+class MschedLayout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "padded_envs", "state_words", "action_halfs", "result_words", "obs_halfs", "chain_words",
+        "a_acceptor", "a_offer_core", "a_offer_price", "a_auctioneer", "a_spawn_kind",
+        "r_offer", "r_price", "r_acceptor", "r_auctioneer", "r_agent", "r_quality", "r_counts",
+        "r_flags", "r_auctioneer_idx", "RL", "RC",
+        "o_acceptor", "o_offer", "o_auctioneer", "o_ids", "o_auctioneer_ids")]
+
+
+class MschedMlpGroup(C.Structure):
+    _fields_ = [("n_in", C.c_int32), ("n_hidden", C.c_int32), ("n_actions", C.c_int32),
+                ("n_nets", C.c_int32), ("weights", C.c_void_p)]
+
+
+# every symbol include/msched.h declares: name -> (restype, argtypes)
+P = C.c_void_p
+SYMBOLS = {
+    "msched_abi_version": (C.c_int, []),
+    "msched_last_error": (C.c_char_p, []),
+    "msched_padded_envs": (C.c_int, [C.c_int]),
+    "msched_get_layout": (C.c_int, [C.POINTER(MschedConfig), C.POINTER(MschedLayout)]),
+    "msched_create": (C.c_int, [C.POINTER(MschedConfig), C.c_int, C.POINTER(P)]),
+    "msched_destroy": (C.c_int, [P]),
+    "msched_bind_state": (C.c_int, [P, P, P]),
+    "msched_reset": (C.c_int, [P, P]),
+    "msched_get_round": (C.c_int, [P, C.POINTER(C.c_int64)]),
+    "msched_set_round": (C.c_int, [P, C.c_int64]),
+    "msched_step": (C.c_int, [P, P, P, P, P]),
+    "msched_step_host": (C.c_int, [P, P, P, P]),
+    "msched_observe_dense": (C.c_int, [P, P, P]),
+    "msched_export_state": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, P]),
+    "msched_mlp_param_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "msched_actor_forward": (C.c_int, [C.POINTER(MschedMlpGroup), P, C.c_int, C.c_int64, C.c_int,
+                                       C.c_int, C.c_uint64, C.c_uint64, C.c_int64, P, P, P, P, P]),
+    "msched_returns": (C.c_int, [P, C.c_int, C.c_int, C.c_double, C.c_int, P, P]),
+}
+
+
+class MschedError(RuntimeError):
+    pass
+
+
+def build(verbose=False):
+    """Compile libmsched.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-C", CSRC] + ([] if verbose else ["-s"]))
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; raises (never falls back) if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise MschedError(
+                f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the ABI and the header disagree
+            fn.restype = res
+            fn.argtypes = args
+        if L.msched_abi_version() != ABI_VERSION:
+            raise MschedError("libmsched.so ABI version mismatch")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != OK:
+        msg = lib().msched_last_error().decode(errors="replace")
+        raise MschedError(f"msched error {rc}: {msg}")
+
+
+def cum_prob(probabilities):
+    """World.accProbabilities (src/world.py:220-222): Python float prefix sums."""
+    probabilities = list(probabilities)
+    return [sum(probabilities[: i + 1]) for i in range(len(probabilities))]
+
+
+def make_config(B, world_params, reward="fix", auction="external", spawn="philox",
+                chain_capacity=32, seed=0, env_offset=0, net_zero_offer_reward=0.5):
+    """world_params uses the reference's World(params) keys (src/world.py:211-246)."""
+    wp = world_params
+    prios = list(wp["possibleJobPriorities"])
+    lens = list(wp["possibleJobLengths"])
+    J = len(prios)
+    if len(lens) != J or len(wp["probabilities"]) != J or J > MAX_KINDS:
+        raise ValueError("possibleJobPriorities/Lengths/probabilities must have equal length <= 16")
+    cfg = MschedConfig()
+    cfg.abi_version = ABI_VERSION
+    cfg.B = int(B)
+    cfg.N, cfg.C, cfg.L, cfg.J = (int(wp["numberOfAgents"]), int(wp["numberOfCores"]),
+                                  int(wp["collectionLength"]), J)
+    cfg.newJobsPerRound = int(wp["newJobsPerRoundPerAgent"])
+    cfg.rewardMultiplier = int(wp["rewardMultiplier"])
+    cfg.episodeLength = int(wp["episodeLength"])
+    cfg.freePrices = int(bool(wp["freePrices"]))
+    cfg.rewardVariant = REWARD[reward]
+    cfg.chainCapacity = int(chain_capacity)
+    cfg.auctionMode = AUCTION[auction]
+    cfg.spawnMode = SPAWN[spawn]
+    fix = list(wp.get("fixPricesList") or [])
+    if not cfg.freePrices and len(fix) < J:
+        raise ValueError("fixPricesList needs one price per job kind")
+    cp = cum_prob(wp["probabilities"])
+    for k in range(J):
+        cfg.prio[k], cfg.len[k] = int(prios[k]), int(lens[k])
+        cfg.fixPrice[k] = int(fix[k]) if k < len(fix) else 0
+        cfg.cumProb[k] = float(cp[k])
+    cfg.netZeroOfferReward = float(net_zero_offer_reward)
+    cfg.seed = int(seed)
+    cfg.envOffset = int(env_offset)
+    return cfg
+
+
+def get_layout(cfg):
+    lay = MschedLayout()
+    check(lib().msched_get_layout(C.byref(cfg), C.byref(lay)))
+    return lay

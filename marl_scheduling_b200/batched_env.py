@@ -1,0 +1,221 @@
+"""BatchedSchedulingEnv: B independent reference worlds advanced by one CUDA launch per step.
+
+This is the device-resident core that the drop-in classes in SchedulingEnvironment.py wrap.
+torch is used for device memory and streams only; all compute goes through the C-ABI
+(include/msched.h) into the sm_100a kernels.  Argument order and meaning of `step` mirror
+SchedulingEnv.step(offerActions, acceptorActions, auctioneer_action)
+(reference src/SchedulingEnvironment.py:32-83) with a leading env dimension.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def world_params_from_dom(dom, free):
+    """Small helper for tests/bench: compact domain dict -> reference World(params) keys."""
+    return dict(
+        freePrices=bool(free), fixPricesList=list(dom.get("fix", [])),
+        numberOfAgents=dom["N"], numberOfCores=dom["C"], collectionLength=dom["L"],
+        possibleJobPriorities=list(dom["prios"]), possibleJobLengths=list(dom["lens"]),
+        probabilities=list(dom["probs"]), newJobsPerRoundPerAgent=dom.get("newJobs", 1),
+        rewardMultiplier=dom.get("mult", 1), episodeLength=dom.get("episodeLength", 100),
+        maxVisibleOffers=4)
+
+
+class BatchedSchedulingEnv:
+    def __init__(self, B, world_params, reward="fix", auction="external", spawn="philox",
+                 chain_capacity=32, seed=0, env_offset=0, net_zero_offer_reward=0.5, device=0):
+        if not torch.cuda.is_available():
+            raise L.MschedError("no CUDA device: marl_scheduling_b200 has no CPU fallback")
+        self.lib = L.lib()
+        self.cfg = L.make_config(B, world_params, reward, auction, spawn, chain_capacity, seed,
+                                 env_offset, net_zero_offer_reward)
+        self.layout = lay = L.get_layout(self.cfg)
+        self.B, self.N, self.C, self.Lc = B, self.cfg.N, self.cfg.C, self.cfg.L
+        self.NL = self.N * self.Lc
+        self.newJobs = self.cfg.newJobsPerRound
+        self.free = bool(self.cfg.freePrices)
+        self.agg = self.cfg.rewardVariant == 3
+        self.device = torch.device("cuda", device)
+        self.handle = C.c_void_p()
+        L.check(self.lib.msched_create(C.byref(self.cfg), device, C.byref(self.handle)))
+        Bp = lay.padded_envs
+        dev = self.device
+        self.state = torch.zeros((Bp, lay.state_words), dtype=torch.int32, device=dev)
+        self.chain = torch.zeros((Bp, lay.chain_words), dtype=torch.int32, device=dev)
+        self.action = torch.zeros((Bp, lay.action_halfs), dtype=torch.int16, device=dev)
+        self.result = torch.zeros((Bp, lay.result_words), dtype=torch.int32, device=dev)
+        self._obs = None
+        L.check(self.lib.msched_bind_state(self.handle, self.state.data_ptr(), self.chain.data_ptr()))
+        self.reset()
+
+    # ------------------------------------------------------------------ lifecycle
+    def close(self):
+        if getattr(self, "handle", None) and self.handle.value:
+            self.lib.msched_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def round(self):
+        r = C.c_int64()
+        L.check(self.lib.msched_get_round(self.handle, C.byref(r)))
+        return int(r.value)
+
+    def reset(self):
+        """Fresh worlds (World.__init__, reference src/world.py:210-254)."""
+        L.check(self.lib.msched_reset(self.handle, self._stream()))
+
+    # ------------------------------------------------------------------ action record views
+    def _aview(self, off, n, shape):
+        return self.action[: self.B, off: off + n].view(self.B, *shape) if off >= 0 else None
+
+    @property
+    def acceptor_actions(self):  # [B,N,C] int16 view into the action record
+        return self._aview(self.layout.a_acceptor, self.N * self.C, (self.N, self.C))
+
+    @property
+    def offer_core_actions(self):  # [B,N,L]
+        return self._aview(self.layout.a_offer_core, self.NL, (self.N, self.Lc))
+
+    @property
+    def offer_price_actions(self):  # [B,N,L] (free prices) or None
+        return self._aview(self.layout.a_offer_price, self.NL, (self.N, self.Lc))
+
+    @property
+    def auctioneer_actions(self):  # [B,C] (external auctioneer) or None
+        return self._aview(self.layout.a_auctioneer, self.C, (self.C,))
+
+    @property
+    def spawn_kinds(self):  # [B,N,newJobs] (spawn='kinds') or None
+        return self._aview(self.layout.a_spawn_kind, self.N * self.newJobs, (self.N, self.newJobs))
+
+    def set_actions(self, offer_core, acceptor, auctioneer=None, offer_price=None, spawn_kind=None):
+        """Copy per-field action tensors (any integer dtype, device or host) into the record."""
+        def put(view, src, name):
+            if view is None:
+                if src is not None:
+                    raise ValueError(f"{name} not part of this configuration's action record")
+                return
+            if src is None:
+                raise ValueError(f"{name} required")
+            src = torch.as_tensor(src)
+            view.copy_(src.to(self.device, non_blocking=True).reshape(view.shape))
+        put(self.offer_core_actions, offer_core, "offer_core")
+        put(self.acceptor_actions, acceptor, "acceptor")
+        put(self.auctioneer_actions, auctioneer, "auctioneer")
+        put(self.offer_price_actions, offer_price, "offer_price")
+        put(self.spawn_kinds, spawn_kind, "spawn_kind")
+
+    # ------------------------------------------------------------------ the hot path
+    def step_records(self, action=None, result=None, spawn_u=None):
+        """One step on caller-provided (or the env's own) device records.  Asynchronous."""
+        action = self.action if action is None else action
+        result = self.result if result is None else result
+        su = None
+        if spawn_u is not None:
+            su = torch.as_tensor(spawn_u, dtype=torch.float64).to(self.device).contiguous()
+            self._keep_su = su
+        L.check(self.lib.msched_step(self.handle, action.data_ptr(),
+                                     None if su is None else su.data_ptr(), result.data_ptr(),
+                                     self._stream()))
+        return result
+
+    def step(self, offer_core, acceptor, auctioneer=None, offer_price=None, spawn_kind=None,
+             spawn_u=None):
+        """SchedulingEnv.step(offerActions, acceptorActions, auctioneer_action) over B envs."""
+        self.set_actions(offer_core, acceptor, auctioneer, offer_price, spawn_kind)
+        self.step_records(spawn_u=spawn_u)
+        return self.rewards()
+
+    def step_host(self, action_host, result_host):
+        """The C-ABI call with HOST buffers (pinned int16 / int32 tensors): H2D, step, D2H, sync."""
+        L.check(self.lib.msched_step_host(self.handle, action_host.data_ptr(),
+                                          result_host.data_ptr(), self._stream()))
+        return result_host
+
+    # ------------------------------------------------------------------ result record views
+    def rewards(self, result=None):
+        lay, B, N = self.layout, self.B, self.N
+        r = (self.result if result is None else result)[:B]
+        f = r.view(torch.float32)
+        out = {}
+        out["offer"] = f[:, lay.r_offer: lay.r_offer + N * lay.RL].view(B, N, lay.RL)
+        out["price"] = (f[:, lay.r_price: lay.r_price + N * lay.RL].view(B, N, lay.RL)
+                        if lay.r_price >= 0 else None)
+        out["acceptor"] = r[:, lay.r_acceptor: lay.r_acceptor + N * lay.RC].view(B, N, lay.RC)
+        out["auctioneer"] = r[:, lay.r_auctioneer: lay.r_auctioneer + self.C]
+        out["agent"] = r[:, lay.r_agent: lay.r_agent + N]
+        q = r[:, lay.r_quality: lay.r_quality + 2].contiguous().view(torch.float64).view(B)
+        counts = r[:, lay.r_counts]
+        out["quality_sum"] = q
+        out["quality_cnt"] = counts & 0xFF
+        out["n_accepted"] = (counts >> 8) & 0xFF
+        out["n_terminated"] = (counts >> 16) & 0xFF
+        out["done"] = (counts >> 24) & 0x1
+        out["flags"] = r[:, lay.r_flags]
+        nw = (self.C + 1) // 2
+        ai = r[:, lay.r_auctioneer_idx: lay.r_auctioneer_idx + nw].contiguous().view(torch.int16)
+        out["auctioneer_idx"] = ai[:, : self.C]
+        return out
+
+    # ------------------------------------------------------------------ observations
+    def observe(self):
+        """Dense reference-layout observations (reference src/Agent.py:148-300,
+        src/Auctioneer.py:20-77) as int16 views: acceptor [B,N,C,3+2NL], offer [B,N,L,2C+2],
+        auctioneer [B,C,3+2NL], ids [B,N,C,NL], auctioneer_ids [B,C,NL]."""
+        lay = self.layout
+        if self._obs is None:
+            self._obs = torch.zeros((lay.padded_envs, lay.obs_halfs), dtype=torch.int16,
+                                    device=self.device)
+        L.check(self.lib.msched_observe_dense(self.handle, self._obs.data_ptr(), self._stream()))
+        B, N, Cc, Lc, NL = self.B, self.N, self.C, self.Lc, self.NL
+        Wd = 3 + 2 * NL
+        o = self._obs[:B]
+        return dict(
+            acceptor=o[:, lay.o_acceptor: lay.o_acceptor + N * Cc * Wd].view(B, N, Cc, Wd),
+            offer=o[:, lay.o_offer: lay.o_offer + NL * (2 * Cc + 2)].view(B, N, Lc, 2 * Cc + 2),
+            auctioneer=o[:, lay.o_auctioneer: lay.o_auctioneer + Cc * Wd].view(B, Cc, Wd),
+            ids=o[:, lay.o_ids: lay.o_ids + N * Cc * NL].view(B, N, Cc, NL),
+            auctioneer_ids=o[:, lay.o_auctioneer_ids: lay.o_auctioneer_ids + Cc * NL].view(B, Cc, NL))
+
+    # ------------------------------------------------------------------ debug / parity
+    def export_state(self, env0=0, count=None):
+        """Reference-shaped dump (numpy) of envs [env0, env0+count), see include/msched.h."""
+        count = self.B - env0 if count is None else count
+        N, Cc, Lc, NL, K = self.N, self.C, self.Lc, self.NL, self.cfg.chainCapacity
+        dev = self.device
+        core = torch.empty((count, Cc, 7), dtype=torch.int32, device=dev)
+        slot = torch.empty((count, NL, 7), dtype=torch.int32, device=dev)
+        off = torch.empty((count, NL, 5), dtype=torch.int32, device=dev)
+        chain = torch.empty((count, Cc, K, 5), dtype=torch.int32, device=dev)
+        clen = torch.empty((count, Cc), dtype=torch.int32, device=dev)
+        misc = torch.empty((count, 4), dtype=torch.int32, device=dev)
+        L.check(self.lib.msched_export_state(self.handle, env0, count, core.data_ptr(),
+                                             slot.data_ptr(), off.data_ptr(), chain.data_ptr(),
+                                             clen.data_ptr(), misc.data_ptr(), self._stream()))
+        core, slot, off, chain, clen, misc = (t.cpu().numpy() for t in (core, slot, off, chain, clen, misc))
+        s = slot.reshape(count, N, Lc, 7)
+        f = off.reshape(count, N, Lc, 5)
+        return dict(
+            core_owner=core[..., 0], core_prio=core[..., 1], core_rem=core[..., 2],
+            core_jobid=core[..., 3], core_kind=core[..., 4], core_birth=core[..., 5],
+            core_init=core[..., 6],
+            slot_prio=s[..., 0], slot_rem=s[..., 1], slot_jobid=s[..., 2], slot_kind=s[..., 3],
+            slot_wait=s[..., 4], slot_birth=s[..., 5], slot_init=s[..., 6],
+            off_core=f[..., 0], off_recip=f[..., 1], off_price=f[..., 2], off_time=f[..., 3],
+            off_id=f[..., 4], chain=chain, chain_len=clen, job_counter=misc[:, 0],
+            flags=misc[:, 1].astype(np.uint32))

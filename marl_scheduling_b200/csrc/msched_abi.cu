@@ -1,0 +1,385 @@
+// msched_abi.cu -- the C-ABI (include/msched.h) over the sm_100a kernels.
+// There is no CPU fallback anywhere in this library: without a CUDA device every launch entry
+// point returns MSCHED_E_NODEVICE.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "msched_common.cuh"
+#include "observe_kernel.cuh"
+#include "policy_kernels.cuh"
+#include "step_kernel.cuh"
+
+using namespace msched;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return fail(MSCHED_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));    \
+    } while (0)
+
+int even_odd_half(int halfs)
+{  // even count of int16 whose word count is odd (bank-conflict-free lane stride)
+    if (halfs & 1) ++halfs;
+    if (((halfs / 2) & 1) == 0) halfs += 2;
+    return halfs;
+}
+
+int compute_layout(const MschedConfig *c, MschedLayout *o)
+{
+    if (!c || !o) return fail(MSCHED_E_ARG, "null config/layout");
+    if (c->abi_version != MSCHED_ABI_VERSION) return fail(MSCHED_E_ARG, "abi_version mismatch");
+    if (c->B < 1) return fail(MSCHED_E_ARG, "B must be >= 1");
+    if (c->N < 1 || c->N > 250) return fail(MSCHED_E_ARG, "numberOfAgents must be in 1..250");
+    if (c->C < 1 || c->C > 64) return fail(MSCHED_E_ARG, "numberOfCores must be in 1..64");
+    if (c->L < 1 || (long long)c->N * c->L > 4096) return fail(MSCHED_E_ARG, "N*L must be in 1..4096");
+    if (c->J < 1 || c->J > MSCHED_MAX_KINDS) return fail(MSCHED_E_ARG, "job kinds must be in 1..16");
+    if (c->newJobsPerRound < 0 || c->newJobsPerRound > c->L)
+        return fail(MSCHED_E_ARG, "newJobsPerRoundPerAgent must be in 0..collectionLength");
+    if (c->episodeLength < 1) return fail(MSCHED_E_ARG, "episodeLength must be >= 1");
+    if (c->chainCapacity < 1 || c->chainCapacity > 255)
+        return fail(MSCHED_E_ARG, "chainCapacity must be in 1..255");
+    if (c->rewardVariant < 0 || c->rewardVariant > 3) return fail(MSCHED_E_ARG, "bad rewardVariant");
+    if (c->auctionMode < 0 || c->auctionMode > 2) return fail(MSCHED_E_ARG, "bad auctionMode");
+    if (c->spawnMode < 0 || c->spawnMode > 2) return fail(MSCHED_E_ARG, "bad spawnMode");
+    const bool freeVar = c->rewardVariant == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL ||
+                         c->rewardVariant == MSCHED_REWARD_DIVIDED_FREE_NONCOMMERCIAL;
+    if (freeVar != (c->freePrices != 0))
+        return fail(MSCHED_E_ARG, "freePrices must match the reward variant");
+    for (int k = 0; k < c->J; ++k) {
+        if (c->len[k] < 1 || c->len[k] > 255) return fail(MSCHED_E_ARG, "job lengths must be in 1..255");
+        if (c->prio[k] < -32000 || c->prio[k] > 32000) return fail(MSCHED_E_ARG, "priority out of int16 range");
+        if (c->fixPrice[k] < -32000 || c->fixPrice[k] > 32000) return fail(MSCHED_E_ARG, "price out of int16 range");
+    }
+    const int N = c->N, C = c->C, L = c->L, NL = N * L;
+    const bool agg = c->rewardVariant == MSCHED_REWARD_AGGREGATED_FIXED;
+    memset(o, 0, sizeof(*o));
+    o->padded_envs = msched_padded_envs(c->B);
+    o->state_words = make_odd(2 + 3 * C + (C + 3) / 4 + 4 * NL);
+    int h = 0;
+    o->a_acceptor = h; h += N * C;
+    o->a_offer_core = h; h += NL;
+    o->a_offer_price = -1;
+    if (c->freePrices) { o->a_offer_price = h; h += NL; }
+    o->a_auctioneer = -1;
+    if (c->auctionMode == MSCHED_AUCTION_EXTERNAL) { o->a_auctioneer = h; h += C; }
+    o->a_spawn_kind = -1;
+    if (c->spawnMode == MSCHED_SPAWN_KINDS) { o->a_spawn_kind = h; h += N * c->newJobsPerRound; }
+    o->action_halfs = even_odd_half(h);
+    o->RL = agg ? 1 : L;
+    o->RC = agg ? 1 : C;
+    int w = 0;
+    o->r_offer = w; w += N * o->RL;
+    o->r_price = -1;
+    if (c->freePrices) { o->r_price = w; w += N * o->RL; }
+    o->r_acceptor = w; w += N * o->RC;
+    o->r_auctioneer = w; w += C;
+    o->r_agent = w; w += N;
+    o->r_quality = w; w += 2;
+    o->r_counts = w; w += 1;
+    o->r_flags = w; w += 1;
+    o->r_auctioneer_idx = w; w += (C + 1) / 2;
+    o->result_words = make_odd(w);
+    const int Wd = 3 + 2 * NL;
+    long long oh = 0;
+    o->o_acceptor = (int)oh; oh += (long long)N * C * Wd;
+    o->o_offer = (int)oh; oh += (long long)NL * (2 * C + 2);
+    o->o_auctioneer = (int)oh; oh += (long long)C * Wd;
+    o->o_ids = (int)oh; oh += (long long)N * C * NL;
+    o->o_auctioneer_ids = (int)oh; oh += (long long)C * NL;
+    if (oh > (1ll << 28)) return fail(MSCHED_E_ARG, "observation record too large");
+    o->obs_halfs = even_odd_half((int)oh);
+    o->chain_words = C * c->chainCapacity * 2;
+    return MSCHED_OK;
+}
+
+typedef void (*StepKernel)(const DevParams);
+
+struct Handle {
+    MschedConfig cfg;
+    MschedLayout lay;
+    DevParams p;
+    int device;
+    long long round;
+    int smemOptin;
+    int stepTile, obsTile;  // envs per CTA (0 = unsupported / direct)
+    StepKernel stepFn;
+    int16_t *stageAction;
+    uint32_t *stageResult;
+};
+
+StepKernel pick_step_kernel(int N, int C, int L)
+{
+    if (N == 2 && C == 3 && L == 3) return step_kernel<2, 3, 3>;  // BASELINE cfg3 (Exp 4-2)
+    if (N == 4 && C == 4 && L == 3) return step_kernel<4, 4, 3>;  // BASELINE cfg2 / cfg4
+    if (N == 2 && C == 3 && L == 2) return step_kernel<2, 3, 2>;  // BASELINE cfg1 (trainHC)
+    if (N == 2 && C == 2 && L == 3) return step_kernel<2, 2, 3>;  // README 2-agent domain
+    return step_kernel<0, 0, 0>;
+}
+
+void fill_params(Handle *h)
+{
+    const MschedConfig &c = h->cfg;
+    const MschedLayout &l = h->lay;
+    DevParams &p = h->p;
+    memset(&p, 0, sizeof(p));
+    p.B = c.B; p.Bpad = l.padded_envs; p.N = c.N; p.C = c.C; p.L = c.L; p.NL = c.N * c.L; p.J = c.J;
+    p.newJobs = c.newJobsPerRound; p.mult = c.rewardMultiplier; p.episodeLength = c.episodeLength;
+    p.freePrices = c.freePrices; p.mode = c.rewardVariant; p.chainCap = c.chainCapacity;
+    p.auctionMode = c.auctionMode; p.spawnMode = c.spawnMode;
+    p.W = l.state_words; p.AH = l.action_halfs; p.RW = l.result_words; p.OH = l.obs_halfs;
+    p.sChlen = 2 + 3 * c.C; p.sSlot = p.sChlen + (c.C + 3) / 4;
+    p.aAcc = l.a_acceptor; p.aOffc = l.a_offer_core; p.aOffp = l.a_offer_price; p.aAuc = l.a_auctioneer;
+    p.aSpawn = l.a_spawn_kind;
+    p.rOffer = l.r_offer; p.rPrice = l.r_price; p.rAcc = l.r_acceptor; p.rAuc = l.r_auctioneer;
+    p.rAgent = l.r_agent; p.rQual = l.r_quality; p.rCounts = l.r_counts; p.rFlags = l.r_flags;
+    p.rAucIdx = l.r_auctioneer_idx; p.RL = l.RL; p.RC = l.RC;
+    p.oAcc = l.o_acceptor; p.oOff = l.o_offer; p.oAuc = l.o_auctioneer; p.oIds = l.o_ids;
+    p.oAucIds = l.o_auctioneer_ids;
+    for (int k = 0; k < MSCHED_MAX_KINDS; ++k) {
+        p.prio[k] = c.prio[k]; p.len[k] = c.len[k]; p.fix[k] = c.fixPrice[k]; p.cum[k] = c.cumProb[k];
+    }
+    p.netZero = (float)c.netZeroOfferReward;
+    p.seed = c.seed;
+    p.envOffset = c.envOffset;
+}
+
+int pick_tile(size_t bytesPerEnv, int smemOptin, const char *envName)
+{
+    if (const char *e = getenv(envName)) {
+        const int t = atoi(e);
+        if ((t == 32 || t == 64 || t == 128) && (size_t)t * bytesPerEnv + 64 <= (size_t)smemOptin) return t;
+    }
+    // prefer 64-env tiles with >= 2 CTAs per SM, then 32, then 128 never needed
+    if (64 * bytesPerEnv <= 100 * 1024) return 64;
+    if (32 * bytesPerEnv + 64 <= (size_t)smemOptin) return 32;
+    return 0;
+}
+
+bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int msched_abi_version(void) { return MSCHED_ABI_VERSION; }
+const char *msched_last_error(void) { return g_err.c_str(); }
+int msched_padded_envs(int B)
+{
+    return ((B + MSCHED_TILE_ENVS - 1) / MSCHED_TILE_ENVS) * MSCHED_TILE_ENVS;
+}
+int msched_get_layout(const MschedConfig *cfg, MschedLayout *out) { return compute_layout(cfg, out); }
+
+int msched_create(const MschedConfig *cfg, int device, void **handle)
+{
+    if (!handle) return fail(MSCHED_E_ARG, "null handle pointer");
+    *handle = nullptr;
+    MschedLayout lay;
+    int rc = compute_layout(cfg, &lay);
+    if (rc) return rc;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(MSCHED_E_NODEVICE, "no CUDA device (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(MSCHED_E_ARG, "bad device index");
+    CUDA_TRY(cudaSetDevice(device));
+    Handle *h = new Handle();
+    memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->lay = lay;
+    h->device = device;
+    fill_params(h);
+    CUDA_TRY(cudaDeviceGetAttribute(&h->smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    const size_t stepBytes = (size_t)lay.state_words * 4 + (size_t)lay.action_halfs * 2 + (size_t)lay.result_words * 4;
+    h->stepTile = pick_tile(stepBytes, h->smemOptin, "MSCHED_STEP_TILE");
+    if (h->stepTile == 0) {
+        delete h;
+        return fail(MSCHED_E_ARG, "domain too large for the lane-per-env step kernel (state+action+result of "
+                                  "32 envs must fit in shared memory)");
+    }
+    h->stepFn = pick_step_kernel(cfg->N, cfg->C, cfg->L);
+    CUDA_TRY(cudaFuncSetAttribute(h->stepFn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)(h->stepTile * stepBytes)));
+    const size_t obsBytes = (size_t)lay.state_words * 4 + (size_t)lay.obs_halfs * 2;
+    h->obsTile = pick_tile(obsBytes, h->smemOptin, "MSCHED_OBS_TILE");
+    if (h->obsTile)
+        CUDA_TRY(cudaFuncSetAttribute(observe_kernel_staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(h->obsTile * obsBytes)));
+    CUDA_TRY(cudaMalloc(&h->stageAction, (size_t)lay.padded_envs * lay.action_halfs * 2));
+    CUDA_TRY(cudaMalloc(&h->stageResult, (size_t)lay.padded_envs * lay.result_words * 4));
+    CUDA_TRY(cudaMemset(h->stageAction, 0, (size_t)lay.padded_envs * lay.action_halfs * 2));
+    *handle = h;
+    return MSCHED_OK;
+}
+
+int msched_destroy(void *handle)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return MSCHED_OK;
+    cudaSetDevice(h->device);
+    cudaFree(h->stageAction);
+    cudaFree(h->stageResult);
+    delete h;
+    return MSCHED_OK;
+}
+
+int msched_bind_state(void *handle, void *state_dev, void *chain_dev)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !state_dev || !chain_dev) return fail(MSCHED_E_ARG, "null handle/state/chain");
+    if (!aligned16(state_dev) || !aligned16(chain_dev)) return fail(MSCHED_E_ARG, "buffers must be 16-byte aligned");
+    h->p.state = static_cast<uint32_t *>(state_dev);
+    h->p.chain = static_cast<uint32_t *>(chain_dev);
+    return MSCHED_OK;
+}
+
+int msched_reset(void *handle, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(MSCHED_E_ARG, "null handle");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    CUDA_TRY(cudaSetDevice(h->device));
+    h->round = 0;
+    h->p.round = 0;
+    reset_kernel<<<(h->p.Bpad + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->p);
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+int msched_get_round(void *handle, int64_t *round)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !round) return fail(MSCHED_E_ARG, "null handle/round");
+    *round = h->round;
+    return MSCHED_OK;
+}
+
+int msched_set_round(void *handle, int64_t round)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || round < 0 || round > 0x7fffffff) return fail(MSCHED_E_ARG, "bad handle/round");
+    h->round = round;
+    return MSCHED_OK;
+}
+
+int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_dev, uint32_t *result_dev,
+                void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !action_dev || !result_dev) return fail(MSCHED_E_ARG, "null handle/action/result");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    if (!aligned16(action_dev) || !aligned16(result_dev)) return fail(MSCHED_E_ARG, "buffers must be 16-byte aligned");
+    if (h->cfg.spawnMode == MSCHED_SPAWN_U64 && !spawn_u_dev) return fail(MSCHED_E_ARG, "spawn_u required");
+    DevParams p = h->p;
+    p.action = action_dev;
+    p.spawnU = spawn_u_dev;
+    p.result = result_dev;
+    p.round = (int)h->round;
+    const int T = h->stepTile;
+    const size_t smem = (size_t)T * ((size_t)p.W * 4 + (size_t)p.AH * 2 + (size_t)p.RW * 4);
+    h->stepFn<<<p.Bpad / T, T, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    h->round += 1;
+    return MSCHED_OK;
+}
+
+int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_host, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !action_host || !result_host) return fail(MSCHED_E_ARG, "null handle/action/result");
+    if (h->cfg.spawnMode == MSCHED_SPAWN_U64) return fail(MSCHED_E_ARG, "step_host does not take recorded draws");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaMemcpyAsync(h->stageAction, action_host, (size_t)h->cfg.B * h->lay.action_halfs * 2,
+                             cudaMemcpyHostToDevice, s));
+    int rc = msched_step(handle, h->stageAction, nullptr, h->stageResult, stream);
+    if (rc) return rc;
+    CUDA_TRY(cudaMemcpyAsync(result_host, h->stageResult, (size_t)h->cfg.B * h->lay.result_words * 4,
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MSCHED_OK;
+}
+
+int msched_observe_dense(void *handle, int16_t *obs_dev, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !obs_dev) return fail(MSCHED_E_ARG, "null handle/obs");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    if (!aligned16(obs_dev)) return fail(MSCHED_E_ARG, "buffers must be 16-byte aligned");
+    DevParams p = h->p;
+    p.obs = obs_dev;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (h->obsTile) {
+        const int T = h->obsTile;
+        const size_t smem = (size_t)T * ((size_t)p.W * 4 + (size_t)p.OH * 2);
+        observe_kernel_staged<<<p.Bpad / T, T, smem, s>>>(p);
+    } else {
+        observe_kernel_direct<<<(p.Bpad + 63) / 64, 64, 0, s>>>(p);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+int msched_export_state(void *handle, int env0, int count, int32_t *core, int32_t *slot, int32_t *offer,
+                        int32_t *chain, int32_t *chain_len, int32_t *misc, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(MSCHED_E_ARG, "null handle");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    if (env0 < 0 || count < 0 || env0 + count > h->cfg.B) return fail(MSCHED_E_ARG, "env range out of bounds");
+    if (count == 0) return MSCHED_OK;
+    ExportArgs a{env0, count, core, slot, offer, chain, chain_len, misc};
+    export_kernel<<<(count + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(h->p, a);
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+int msched_mlp_param_count(int n_in, int n_hidden, int n_actions)
+{
+    return n_hidden * n_in + n_hidden + n_hidden * n_hidden + n_hidden + n_actions * n_hidden + n_actions;
+}
+
+int msched_actor_forward(const MschedMlpGroup *nets, const int16_t *x, int x_stride, int64_t env_stride,
+                         int units, int M,
+                         uint64_t seed, uint64_t step, int64_t row_offset, const float *u_override,
+                         int32_t *action, float *logprob, float *probs, void *stream)
+{
+    if (!nets || !x || !nets->weights) return fail(MSCHED_E_ARG, "null nets/x/weights");
+    if (M < 0 || units < 1 || nets->n_nets < 1 || x_stride < nets->n_in)
+        return fail(MSCHED_E_ARG, "bad M/units/n_nets/x_stride");
+    if (nets->n_in < 1 || nets->n_in > 128 || nets->n_hidden < 8 || nets->n_hidden > 64 ||
+        (nets->n_hidden % 8) != 0 || nets->n_actions < 1)
+        return fail(MSCHED_E_ARG, "unsupported MLP shape (in 1..128, hidden 8..64 multiple of 8)");
+    if (M == 0) return MSCHED_OK;
+    int rc = launch_actor_forward(*nets, x, x_stride, env_stride, units, M, seed, step, row_offset, u_override, action,
+                                  logprob, probs, static_cast<cudaStream_t>(stream));
+    if (rc == -1) return fail(MSCHED_E_ARG, "unsupported MLP shape for the actor kernel");
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+int msched_returns(const float *rewards, int T, int M, double gamma, int normalise, float *out, void *stream)
+{
+    if (!rewards || !out || T < 1 || M < 0) return fail(MSCHED_E_ARG, "bad rewards/out/T/M");
+    if (normalise && T < 2) return fail(MSCHED_E_ARG, "normalisation needs T >= 2");
+    if (M == 0) return MSCHED_OK;
+    returns_kernel<<<(M + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(rewards, T, M, gamma,
+                                                                                   normalise, out);
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+}  // extern "C"

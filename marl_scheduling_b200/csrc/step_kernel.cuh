@@ -1,0 +1,388 @@
+// step_kernel.cuh -- one SchedulingEnv.step for a tile of environments, one lane per env.
+//
+// Reference semantics restated (file:line relative to the reference):
+//   src/SchedulingEnvironment.py:32-83   SchedulingEnv.step
+//   src/world.py:295-334                 World.step1 (order of phases)
+//   src/world.py:391-404, 378-389        executeAgentAcceptions1 / executeAuctioneerAcceptions
+//   src/world.py:261-293                 executeAnOffer
+//   src/HardcodedModules.py:48-78        HardcodedAuctioneerAcceptor.selectAction (the auction)
+//   src/world.py:336-367                 processOneTimestepAndUpdateOwnership
+//   src/world.py:406-478                 create{Fix,Free}PriceOfferObjectsFromActions
+//   src/world.py:369-376, src/Agent.py:50-70  spawn refill
+//   src/Reward.py:6-212                  the three reward functions
+//   src/SchedulingEnvironment.py:174-192 acception quality
+//
+// Mapping: a CTA owns a tile of blockDim.x consecutive environments.  The tile's state records
+// and action records are each ONE contiguous HBM chunk; thread 0 moves them into shared memory
+// with cp.async.bulk (TMA) and every lane then advances its own environment entirely out of
+// shared memory (record strides are odd, so any field index is bank-conflict free).  Results
+// are built in a shared-memory result tile and written back with two bulk stores.  The only
+// scattered HBM traffic is the liability chain: one 8-byte append per acceptance, one short
+// walk per job completion.
+#pragma once
+#include "msched_common.cuh"
+
+namespace msched {
+
+template <int TN, int TC, int TL>
+struct Dims {
+    const int N, C, L, NL;
+    __device__ __forceinline__ explicit Dims(const DevParams &p)
+        : N(TN ? TN : p.N), C(TC ? TC : p.C), L(TL ? TL : p.L), NL((TN ? TN : p.N) * (TL ? TL : p.L))
+    {
+    }
+};
+
+// Python round(): round-half-even of the float64 product, no FMA contraction (Q7)
+__device__ __forceinline__ int traded_reward(int price, int time, int dt)
+{
+    const double ratio = __ddiv_rn((double)price, (double)time);
+    return (int)rint(__dmul_rn(ratio, (double)dt));
+}
+
+template <int TN, int TC, int TL>
+__device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restrict__ st,
+                                         const int16_t *__restrict__ act, uint32_t *__restrict__ res,
+                                         int env)
+{
+    const Dims<TN, TC, TL> d(p);
+    const int N = d.N, C = d.C, L = d.L, NL = d.NL;
+    const int mode = p.mode;
+    const bool agg = mode == MSCHED_REWARD_AGGREGATED_FIXED;
+    const bool freeM = mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL ||
+                       mode == MSCHED_REWARD_DIVIDED_FREE_NONCOMMERCIAL;
+    const int round = p.round;
+    uint32_t *core = st + 2;
+    uint32_t *chl = st + p.sChlen;
+    uint32_t *slot = st + p.sSlot;
+    float *resf = reinterpret_cast<float *>(res);
+    int *resi = reinterpret_cast<int *>(res);
+    uint32_t flags = st[1];
+
+    for (int k = 0; k < p.RW; ++k) res[k] = 0u;
+
+    // ---- range check of every acceptor action (assert in src/world.py:389,404) ----
+    for (int k = 0; k < N * C; ++k) {
+        const int a = act[p.aAcc + k];
+        if (a < 0 || a > NL) flags |= MSCHED_FLAG_ACTION_RANGE;
+    }
+
+    double qualSum = 0.0;
+    int qualCnt = 0, nAcc = 0, nTerm = 0;
+
+    // auctioneer index per core as the reference's Auctioneer.getAuctioneerAction reports it:
+    // reject (NL) for cores it does not own; echo of the input in external mode
+    for (int j = 0; j < C; ++j) {
+        const int k = (p.auctionMode == MSCHED_AUCTION_EXTERNAL) ? (int)act[p.aAuc + j] : NL;
+        res[p.rAucIdx + (j >> 1)] |= ((uint32_t)(k & 0xffff)) << ((j & 1) * 16);
+    }
+
+    // ---- acceptances in reference order: agents ascending (core ascending), then auctioneer ----
+    unsigned long long handled = 0ull;
+    for (int ord = 1; ord <= N + 1; ++ord) {
+        const int who = (ord <= N) ? ord : 0;
+        for (int j = 0; j < C; ++j) {
+            if ((handled >> j) & 1ull) continue;
+            const uint32_t cw0 = core[3 * j];
+            if (core_owner(cw0) != who) continue;
+            handled |= 1ull << j;
+            const uint32_t key = (uint32_t)(j + 1) | ((uint32_t)who << 8);
+            int k;         // index into the (recipient, core) offer table
+            bool haveK = true;
+            if (who > 0) {
+                k = act[p.aAcc + (who - 1) * C + j];
+            } else if (p.auctionMode == MSCHED_AUCTION_EXTERNAL) {
+                k = act[p.aAuc + j];
+                if (k < 0 || k > NL) flags |= MSCHED_FLAG_ACTION_RANGE;
+            } else {
+                // the auction: best offeredReward/necessaryTime among offers to this idle core,
+                // compared exactly by cross-multiplication (ratios of int16 operands are distinct
+                // floats iff distinct rationals); -1/-2 operands rate -1 (calculateRewardRatio)
+                int bn = -1, bd = 1, ncand = 0;
+                for (int s = 0; s < NL; ++s) {
+                    const uint32_t w3 = slot[4 * s + 3];
+                    if ((w3 & 0xffffu) != key) continue;
+                    int pn = off_price(w3), pd = job_rem(slot[4 * s]);
+                    if (pn == -1 || pn == -2 || pd == -1 || pd == -2) { pn = -1; pd = 1; }
+                    const int lhs = pn * bd, rhs = bn * pd;
+                    if (lhs > rhs) { bn = pn; bd = pd; ncand = 1; }
+                    else if (lhs == rhs) ++ncand;
+                }
+                k = NL;  // reject unless max ratio > -1
+                if (bn > -bd) {
+                    int pick = 0;
+                    if (p.auctionMode == MSCHED_AUCTION_RANDOM_MAX && ncand > 1) {
+                        uint32_t x[4];
+                        env_draw(p, env, kStreamTie, (uint32_t)j, 0u, x);
+                        pick = (int)__umulhi(x[0], (uint32_t)ncand);
+                    }
+                    int idx = 0;
+                    for (int s = 0; s < NL; ++s) {
+                        const uint32_t w3 = slot[4 * s + 3];
+                        if ((w3 & 0xffffu) != key) continue;
+                        int pn = off_price(w3), pd = job_rem(slot[4 * s]);
+                        if (pn == -1 || pn == -2 || pd == -1 || pd == -2) { pn = -1; pd = 1; }
+                        if (pn * bd == bn * pd) {
+                            if (pick == 0) { k = idx; break; }
+                            --pick;
+                        }
+                        ++idx;
+                    }
+                }
+            }
+            if (who == 0) {  // record the auctioneer index actually used
+                uint32_t *w = res + p.rAucIdx + (j >> 1);
+                const int sh = (j & 1) * 16;
+                *w = (*w & ~(0xffffu << sh)) | (((uint32_t)(k & 0xffff)) << sh);
+            }
+            if (k < 0 || k >= NL) haveK = false;
+            if (!haveK) continue;
+            // k-th pending offer addressed to (who, core j) in creation order
+            int sel = -1, selA = 0, selQ = 0, cnt = 0;
+            for (int a = 0, s = 0; a < N; ++a)
+                for (int q = 0; q < L; ++q, ++s) {
+                    if ((slot[4 * s + 3] & 0xffffu) != key) continue;
+                    if (cnt == k) { sel = s; selA = a; selQ = q; }
+                    ++cnt;
+                }
+            if (sel < 0) continue;  // table entry was padding (-2)
+
+            // ---- executeAnOffer ----
+            const uint32_t sw0 = slot[4 * sel], sw1 = slot[4 * sel + 1], sw2 = slot[4 * sel + 2];
+            const uint32_t sw3 = slot[4 * sel + 3];
+            const int kind = job_kind(sw0), time = job_rem(sw0), price = off_price(sw3);
+            const int offerer = selA + 1;
+            const int prio1 = p.prio[kind];
+            const uint32_t cw1 = core[3 * j + 1], cw2 = core[3 * j + 2];
+            slot[4 * sel] = kEmptyJobW0; slot[4 * sel + 1] = kEmptyId; slot[4 * sel + 2] = kEmptyId;
+            slot[4 * sel + 3] = 0u;
+            core[3 * j] = pack_core(offerer, kind, time);
+            core[3 * j + 1] = sw1;
+            core[3 * j + 2] = sw2;
+            if (who > 0) {
+                // old job back into the recipient's first empty slot
+                const int base = (who - 1) * L;
+                int q = -1;
+                for (int t = 0; t < L; ++t)
+                    if (job_kind(slot[4 * (base + t)]) < 0) { q = t; break; }
+                if (q >= 0) {
+                    slot[4 * (base + q)] = cw0 & 0xffffff00u;
+                    slot[4 * (base + q) + 1] = cw1;
+                    slot[4 * (base + q) + 2] = cw2;
+                    slot[4 * (base + q) + 3] = 0u;
+                } else {
+                    flags |= MSCHED_FLAG_COLLECTION_FULL;
+                }
+                // acception quality, src/SchedulingEnvironment.py:174-192 (former = core before)
+                double qv = __ddiv_rn((double)price, (double)time);
+                const int fk = job_kind(cw0);
+                if (fk >= 0) qv = __dsub_rn(qv, __ddiv_rn((double)p.prio[fk], (double)job_rem(cw0)));
+                qualSum = __dadd_rn(qualSum, __dmul_rn(qv, 10.0));
+                ++qualCnt;
+            }
+            // liability chain append (stored oldest first)
+            {
+                const uint32_t cw = chl[j >> 2];
+                const int len = (int)((cw >> ((j & 3) * 8)) & 0xffu);
+                if (len < p.chainCap) {
+                    uint32_t *ce = p.chain + (((size_t)env * C + j) * p.chainCap + len) * 2;
+                    ce[0] = (uint32_t)round;
+                    ce[1] = pack_chain(price, time, offerer);
+                    chl[j >> 2] = cw + (1u << ((j & 3) * 8));
+                } else {
+                    flags |= MSCHED_FLAG_CHAIN_OVERFLOW;
+                }
+            }
+            // offer-side rewards
+            if (agg) {
+                resf[p.rOffer + selA] += (float)prio1;
+            } else {
+                resf[p.rOffer + selA * L + selQ] = (float)prio1;
+                if (freeM) {
+                    const int df = prio1 - price;
+                    float pr;
+                    if (mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL)
+                        pr = (df == 0) ? p.netZero : (float)df;
+                    else
+                        pr = (df >= 0) ? (float)prio1 : (float)df;
+                    resf[p.rPrice + selA * L + selQ] = pr;
+                }
+            }
+            ++nAcc;
+        }
+    }
+
+    // ---- job progress / completion + termination rewards ----
+    for (int j = 0; j < C; ++j) {
+        const uint32_t cw0 = core[3 * j];
+        const int kind = job_kind(cw0);
+        if (kind < 0) continue;
+        const int rem = job_rem(cw0) - 1;
+        const int owner = core_owner(cw0);
+        if (rem != 0) {
+            core[3 * j] = pack_core(owner, kind, rem);
+            continue;
+        }
+        const int R = p.mult * p.prio[kind];
+        const int o = owner - 1;
+        if (agg) {
+            resi[p.rAcc + o] += R;
+            resi[p.rAgent + o] += R;
+        } else {
+            resi[p.rAcc + o * C + j] = R;
+            if (!freeM) resi[p.rAgent + o] += R;
+        }
+        const uint32_t cw = chl[j >> 2];
+        const int len = (int)((cw >> ((j & 3) * 8)) & 0xffu);
+        const uint2 *ce = reinterpret_cast<const uint2 *>(p.chain + ((size_t)env * C + j) * p.chainCap * 2);
+        int recip = 0;  // the oldest entry was accepted by the auctioneer
+        for (int e = 0; e < len; ++e) {
+            const uint2 en = ce[e];
+            const int price = (int)(int16_t)(en.y & 0xffffu);
+            const int time = (int)((en.y >> 16) & 0xffu);
+            const int offerer = (int)(en.y >> 24);
+            const int traded = traded_reward(price, time, (round + 1) - (int)en.x);
+            resi[p.rAgent + offerer - 1] -= traded;
+            if (agg) {
+                resi[p.rAcc + offerer - 1] -= traded;
+                if (recip > 0) resi[p.rAgent + recip - 1] += traded;
+            } else {
+                resi[p.rAcc + (offerer - 1) * C + j] -= traded;
+                if (recip > 0) {
+                    resi[p.rAcc + (recip - 1) * C + j] += traded;
+                    resi[p.rAgent + recip - 1] += traded;
+                }
+            }
+            if (recip == 0) resi[p.rAuc + j] = traded;
+            recip = offerer;
+        }
+        chl[j >> 2] = cw & ~(0xffu << ((j & 3) * 8));
+        core[3 * j] = kEmptyJobW0;
+        core[3 * j + 1] = kEmptyId;
+        core[3 * j + 2] = kEmptyId;
+        ++nTerm;
+    }
+
+    // ---- offer creation ----
+    for (int s = 0; s < NL; ++s) {
+        const int a = act[p.aOffc + s];
+        const uint32_t w0 = slot[4 * s];
+        const int kind = job_kind(w0);
+        const bool waitOld = (slot[4 * s + 3] & 0xffu) != 0u;
+        uint32_t w3 = 0u;
+        if (a >= 0 && a < C && kind >= 0 && !waitOld) {
+            const int price = p.freePrices ? (int)act[p.aOffp + s] : p.fix[kind];
+            w3 = pack_offer(a + 1, core_owner(core[3 * a]), price);
+        }
+        slot[4 * s + 3] = w3;
+    }
+
+    // ---- spawn refill ----
+    uint32_t jobctr = st[0];
+    for (int a = 0; a < N; ++a) {
+        int owned = 0, nfree = 0;
+        for (int j = 0; j < C; ++j) owned += (core_owner(core[3 * j]) == a + 1);
+        for (int q = 0; q < L; ++q) nfree += (job_kind(slot[4 * (a * L + q)]) < 0);
+        if (owned + p.newJobs > nfree) continue;
+        for (int k = 0; k < p.newJobs; ++k) {
+            int kind = -1;
+            if (p.spawnMode == MSCHED_SPAWN_KINDS) {
+                kind = act[p.aSpawn + a * p.newJobs + k];
+            } else {
+                double u;
+                if (p.spawnMode == MSCHED_SPAWN_U64) {
+                    u = p.spawnU[((size_t)env * N + a) * p.newJobs + k];
+                } else {
+                    uint32_t x[4];
+                    env_draw(p, env, kStreamSpawn, (uint32_t)a, (uint32_t)k, x);
+                    u = u53(x);
+                }
+                for (int q = 0; q < p.J; ++q)
+                    if (u < p.cum[q]) { kind = q; break; }
+            }
+            if (kind < 0 || kind >= p.J) { flags |= MSCHED_FLAG_SPAWN_RANGE; kind = p.J - 1; }
+            int q = -1;
+            for (int t = 0; t < L; ++t)
+                if (job_kind(slot[4 * (a * L + t)]) < 0) { q = t; break; }
+            const int s = a * L + q;  // q >= 0 is guaranteed by the guard above
+            slot[4 * s] = pack_slot(kind, p.len[kind]);
+            slot[4 * s + 1] = jobctr++;
+            slot[4 * s + 2] = (uint32_t)round;
+            slot[4 * s + 3] = 0u;
+        }
+    }
+    st[0] = jobctr;
+    st[1] = flags;
+
+    // ---- scalar outputs ----
+    const unsigned long long qb = (unsigned long long)__double_as_longlong(qualSum);
+    res[p.rQual] = (uint32_t)qb;
+    res[p.rQual + 1] = (uint32_t)(qb >> 32);
+    const uint32_t done = (((long long)round + 1) % p.episodeLength) == 0 ? 1u : 0u;
+    res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nAcc << 8) | ((uint32_t)nTerm << 16) | (done << 24);
+    res[p.rFlags] = flags;
+}
+
+// grid = Bpad / blockDim.x tiles; dynamic smem = blockDim.x * (W*4 + AH*2 + RW*4) bytes
+template <int TN, int TC, int TL>
+__global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevParams p)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const int T = blockDim.x;
+    const int lane = threadIdx.x;
+    const int env0 = blockIdx.x * T;
+    const uint32_t stBytes = (uint32_t)T * p.W * 4u, acBytes = (uint32_t)T * p.AH * 2u,
+                   rsBytes = (uint32_t)T * p.RW * 4u;
+    uint32_t *sState = reinterpret_cast<uint32_t *>(smem);
+    int16_t *sAct = reinterpret_cast<int16_t *>(smem + stBytes);
+    uint32_t *sRes = reinterpret_cast<uint32_t *>(smem + stBytes + acBytes);
+
+    if (lane == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, stBytes + acBytes);
+        bulk_g2s(sState, p.state + (size_t)env0 * p.W, stBytes, &bar);
+        bulk_g2s(sAct, p.action + (size_t)env0 * p.AH, acBytes, &bar);
+    }
+    __syncthreads();  // barrier init visible before anyone polls it
+    mbar_wait(&bar, 0);
+
+    const int env = env0 + lane;
+    if (env < p.B)
+        step_env<TN, TC, TL>(p, sState + (size_t)lane * p.W, sAct + (size_t)lane * p.AH,
+                             sRes + (size_t)lane * p.RW, env);
+    else
+        for (int k = 0; k < p.RW; ++k) sRes[(size_t)lane * p.RW + k] = 0u;
+
+    fence_async_smem();
+    __syncthreads();
+    if (lane == 0) {
+        bulk_s2g(p.state + (size_t)env0 * p.W, sState, stBytes);
+        bulk_s2g(p.result + (size_t)env0 * p.RW, sRes, rsBytes);
+        bulk_commit();
+        bulk_wait_all();
+    }
+}
+
+// World.__init__ (src/world.py:210-254): every core idle and auctioneer-owned, every slot empty
+__global__ void reset_kernel(const __grid_constant__ DevParams p)
+{
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.Bpad) return;
+    uint32_t *st = p.state + (size_t)env * p.W;
+    for (int k = 0; k < p.W; ++k) st[k] = 0u;
+    st[0] = 1u;
+    for (int j = 0; j < p.C; ++j) {
+        st[2 + 3 * j] = kEmptyJobW0;
+        st[2 + 3 * j + 1] = kEmptyId;
+        st[2 + 3 * j + 2] = kEmptyId;
+    }
+    for (int s = 0; s < p.NL; ++s) {
+        st[p.sSlot + 4 * s] = kEmptyJobW0;
+        st[p.sSlot + 4 * s + 1] = kEmptyId;
+        st[p.sSlot + 4 * s + 2] = kEmptyId;
+        st[p.sSlot + 4 * s + 3] = 0u;
+    }
+}
+
+}  // namespace msched

@@ -1,0 +1,123 @@
+"""Batched PPO rollout pieces over the C-ABI: actor forward (+ categorical sample / log-prob)
+and discounted returns.  Mirrors reference src/PPOmodules.py:25-72 (ActorCritic.act),
+:114-125 (PPO.selectAction) and :128-137 (returns prologue of PPO.update)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def param_count(n_in, n_hidden, n_actions):
+    return L.lib().msched_mlp_param_count(n_in, n_hidden, n_actions)
+
+
+def pack_actor(state_dict, prefix="actor."):
+    """Flatten an ActorCritic.actor state dict (Linear at indices 0, 2, 4) into the ABI's
+    per-net layout [W1 | b1 | W2 | b2 | W3 | b3] (float32, torch [out][in] order)."""
+    parts = []
+    for i in (0, 2, 4):
+        parts.append(torch.as_tensor(state_dict[f"{prefix}{i}.weight"]).float().reshape(-1))
+        parts.append(torch.as_tensor(state_dict[f"{prefix}{i}.bias"]).float().reshape(-1))
+    return torch.cat(parts)
+
+
+class MlpGroup:
+    """n_nets identically shaped actor MLPs with their weights resident on the device."""
+
+    def __init__(self, n_in, n_hidden, n_actions, weights, device):
+        self.n_in, self.n_hidden, self.n_actions = n_in, n_hidden, n_actions
+        w = torch.as_tensor(weights, dtype=torch.float32)
+        pc = param_count(n_in, n_hidden, n_actions)
+        w = w.reshape(-1, pc)
+        self.n_nets = w.shape[0]
+        self.weights = w.to(device).contiguous()
+        self.desc = L.MschedMlpGroup(n_in, n_hidden, n_actions, self.n_nets,
+                                     self.weights.data_ptr())
+
+    @classmethod
+    def from_state_dicts(cls, n_in, n_hidden, n_actions, state_dicts, device, prefix="actor."):
+        return cls(n_in, n_hidden, n_actions,
+                   torch.stack([pack_actor(sd, prefix) for sd in state_dicts]), device)
+
+    @classmethod
+    def random(cls, n_in, n_hidden, n_actions, n_nets, device, seed=0):
+        """torch.nn.Linear default initialisation (what the reference's ActorCritic gets)."""
+        g = torch.Generator().manual_seed(seed)
+        nets = []
+        for _ in range(n_nets):
+            parts = []
+            for fan_in, fan_out in ((n_in, n_hidden), (n_hidden, n_hidden), (n_hidden, n_actions)):
+                bound = 1.0 / (fan_in ** 0.5)
+                parts.append((torch.rand(fan_out * fan_in, generator=g) * 2 - 1) * bound)
+                parts.append((torch.rand(fan_out, generator=g) * 2 - 1) * bound)
+            nets.append(torch.cat(parts))
+        return cls(n_in, n_hidden, n_actions, torch.stack(nets), device)
+
+
+def _stream(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def actor_forward(group, x, x_stride, units, n_envs, env_stride=0, seed=0, step=0, row_offset=0,
+                  u=None, want_probs=False, action=None, logprob=None):
+    """x: int16 device tensor; unit u of env b is the row at x[b*env_stride + u*x_stride : +n_in].
+    Returns (action int32 [n_envs*units], logprob float32, probs or None)."""
+    dev = x.device
+    M = n_envs * units
+    if action is None:
+        action = torch.empty(M, dtype=torch.int32, device=dev)
+    if logprob is None:
+        logprob = torch.empty(M, dtype=torch.float32, device=dev)
+    probs = torch.empty((M, group.n_actions), dtype=torch.float32, device=dev) if want_probs else None
+    if u is not None:
+        u = torch.as_tensor(u, dtype=torch.float32).to(dev).contiguous()
+    L.check(L.lib().msched_actor_forward(
+        C.byref(group.desc), x.data_ptr(), x_stride, env_stride, units, M, seed, step, row_offset,
+        None if u is None else u.data_ptr(), action.data_ptr(), logprob.data_ptr(),
+        None if probs is None else probs.data_ptr(), _stream(dev)))
+    return action, logprob, probs
+
+
+def returns(rewards, gamma, normalise=True, out=None):
+    """rewards float32 [T][M] on the device -> (normalised) Monte-Carlo returns, same shape."""
+    r = rewards.contiguous()
+    T, M = r.shape
+    if out is None:
+        out = torch.empty_like(r)
+    L.check(L.lib().msched_returns(r.data_ptr(), T, M, float(gamma), int(normalise), out.data_ptr(),
+                                   _stream(r.device)))
+    return out
+
+
+def smoke_check(env, obs):
+    """One actor forward on the env's acceptor observations and one returns launch, checked
+    against the CPU oracle (used by __graft_entry__.smoke)."""
+    import numpy as np
+    from oracle import oracle as O
+    N, Cc, NL = env.N, env.C, env.NL
+    Wd = 3 + 2 * NL
+    grp = MlpGroup.random(Wd, 16, NL + 1, N * Cc, env.device, seed=1)
+    x = obs["acceptor"]  # [B,N,C,Wd] view into the obs record
+    B = x.shape[0]
+    uu = torch.rand(B * N * Cc, generator=torch.Generator().manual_seed(2))
+    act, lp, pr = actor_forward(grp, x, Wd, N * Cc, B, env_stride=env.layout.obs_halfs, u=uu,
+                                want_probs=True)
+    xs = x.cpu().numpy().reshape(B, N * Cc, Wd).astype(np.float32)
+    w = grp.weights.cpu().numpy()
+    H, A = 16, NL + 1
+    pr = pr.cpu().numpy().reshape(B, N * Cc, A)
+    for n in range(N * Cc):
+        o = 0
+        ws = []
+        for sz in (H * Wd, H, H * H, H, A * H, A):
+            ws.append(w[n, o:o + sz]); o += sz
+        p, _, _ = O.mlp_forward(xs[:, n], ws[0].reshape(H, Wd), ws[1], ws[2].reshape(H, H), ws[3],
+                                ws[4].reshape(A, H), ws[5])
+        np.testing.assert_allclose(pr[:, n], p, rtol=2e-5, atol=1e-6)
+    r = torch.randint(-5, 12, (50, 64)).float().to(env.device)
+    g = returns(r, 0.8733, True).cpu().numpy()
+    go = O.returns(r.cpu().numpy().astype(np.float64), 0.8733, True)
+    np.testing.assert_allclose(g, go, rtol=1e-5, atol=1e-5)

@@ -1,0 +1,102 @@
+"""GPU: actor forward / categorical log-prob / returns kernels against the reference's torch
+outputs (tests/golden/torch_vectors.npz) and the CPU oracle.  Floating point: 1e-5 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN
+
+pytestmark = pytest.mark.gpu
+TAGS = dict(acc_cfg3=(15, 7, 16), off_cfg3=(8, 4, 16), price_cfg3=(4, 9, 16), acc_cfg2=(27, 13, 16),
+            off_cfg2=(10, 5, 16), aggoff=(12, 64, 32))
+
+
+def test_actor_forward_matches_torch_reference():
+    import torch
+    from marl_scheduling_b200 import policy
+    z = np.load(os.path.join(GOLDEN, "torch_vectors.npz"))
+    dev = torch.device("cuda", 0)
+    for tag, (nin, A, h) in TAGS.items():
+        sd = {k[len(tag) + 1:]: z[k] for k in z.files if k.startswith(tag + ".actor")}
+        grp = policy.MlpGroup.from_state_dicts(nin, h, A, [sd], dev)
+        x = torch.as_tensor(z[tag + ".x"]).to(torch.int16).to(dev)
+        M = x.shape[0]
+        # u chosen so that the inverse CDF lands on the torch-sampled action
+        probs_ref = z[tag + ".probs"]
+        cdf = np.cumsum(probs_ref, 1)
+        a_ref = z[tag + ".action"]
+        lo = np.where(a_ref > 0, cdf[np.arange(M), a_ref - 1], 0.0)
+        hi = cdf[np.arange(M), a_ref]
+        u = ((lo + hi) / 2 / cdf[:, -1]).astype(np.float32)
+        act, lp, pr = policy.actor_forward(grp, x, nin, 1, M, u=u, want_probs=True)
+        np.testing.assert_allclose(pr.cpu().numpy(), probs_ref, rtol=2e-5, atol=1e-7)
+        sure = (hi - lo) > 1e-4
+        assert np.array_equal(act.cpu().numpy()[sure], a_ref[sure])
+        np.testing.assert_allclose(lp.cpu().numpy()[sure], z[tag + ".logprob"][sure], rtol=1e-4, atol=2e-5)
+
+
+def test_actor_forward_grouped_nets_and_strides_match_oracle():
+    import torch
+    from marl_scheduling_b200 import policy
+    from oracle import oracle as O
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(3)
+    n_envs, units, nin, h, A, stride, env_stride = 777, 6, 15, 16, 7, 15, 119
+    grp = policy.MlpGroup.random(nin, h, A, units, dev, seed=4)
+    xs = rng.integers(-2, 12, (n_envs, env_stride)).astype(np.int16)
+    u = rng.random(n_envs * units).astype(np.float32)
+    act, lp, pr = policy.actor_forward(grp, torch.as_tensor(xs).to(dev), stride, units, n_envs,
+                                       env_stride=env_stride, u=u, want_probs=True)
+    act, lp, pr = act.cpu().numpy(), lp.cpu().numpy(), pr.cpu().numpy()
+    w = grp.weights.cpu().numpy()
+    for n in range(units):
+        o, ws = 0, []
+        for sz in (h * nin, h, h * h, h, A * h, A):
+            ws.append(w[n, o:o + sz]); o += sz
+        x = xs[:, n * stride: n * stride + nin].astype(np.float32)
+        p, a, l = O.mlp_forward(x, ws[0].reshape(h, nin), ws[1], ws[2].reshape(h, h), ws[3],
+                                ws[4].reshape(A, h), ws[5], u=u[n::units])
+        np.testing.assert_allclose(pr[n::units], p, rtol=2e-5, atol=1e-7)
+        cdf = np.cumsum(p, 1)
+        thr = (u[n::units] * p.sum(1))[:, None]
+        margin = np.abs(cdf - thr).min(1)
+        sure = margin > 1e-5
+        assert np.array_equal(act[n::units][sure], a[sure])
+        np.testing.assert_allclose(lp[n::units][sure], l[sure], rtol=1e-4, atol=2e-5)
+
+
+def test_actor_sampling_is_distributionally_correct():
+    import torch
+    from marl_scheduling_b200 import policy
+    dev = torch.device("cuda", 0)
+    grp = policy.MlpGroup.random(8, 16, 4, 1, dev, seed=5)
+    x = torch.zeros((200000, 8), dtype=torch.int16, device=dev)
+    act, lp, pr = policy.actor_forward(grp, x, 8, 1, 200000, seed=11, step=3, want_probs=True)
+    p = pr[0].cpu().numpy()
+    freq = np.bincount(act.cpu().numpy(), minlength=4) / 200000
+    assert np.abs(freq - p).max() < 5e-3
+    act2, _, _ = policy.actor_forward(grp, x, 8, 1, 200000, seed=11, step=4)
+    assert (act2 != act).any()
+
+
+def test_returns_match_reference_and_oracle():
+    import torch
+    from marl_scheduling_b200 import policy
+    from oracle import oracle as O
+    dev = torch.device("cuda", 0)
+    z = np.load(os.path.join(GOLDEN, "torch_vectors.npz"))
+    for tag in ("ret_a", "ret_b", "ret_c", "ret_d"):
+        r = torch.as_tensor(z[tag + ".r"], dtype=torch.float32)[:, None].to(dev)
+        g = float(z[tag + ".gamma"])
+        raw = policy.returns(r, g, normalise=False).cpu().numpy()[:, 0]
+        assert np.array_equal(raw, z[tag + ".raw"].astype(np.float32))
+        nrm = policy.returns(r, g, normalise=True).cpu().numpy()[:, 0]
+        np.testing.assert_allclose(nrm, z[tag + ".norm"], rtol=1e-5, atol=1e-6)
+    rng = np.random.default_rng(1)
+    r = rng.integers(-9, 15, (200, 5000)).astype(np.float32)
+    out = policy.returns(torch.as_tensor(r).to(dev), 0.8733333333333333).cpu().numpy()
+    np.testing.assert_allclose(out, O.returns(r.astype(np.float64), 0.8733333333333333), rtol=1e-5, atol=1e-5)
+    # scan property: raw returns satisfy G_t - gamma*G_{t+1} = r_t
+    raw = policy.returns(torch.as_tensor(r).to(dev), 0.5, normalise=False).cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(raw[:-1] - 0.5 * raw[1:], r[:-1], rtol=0, atol=2e-5)

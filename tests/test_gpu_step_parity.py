@@ -1,0 +1,179 @@
+"""GPU: the CUDA step / observe path (through the C-ABI) against the reference traces and the
+CPU oracle.  Integer state, rewards and observations are compared bit-exactly."""
+import numpy as np
+import pytest
+
+from helpers import STATE_KEYS, assert_state_equal, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(B, meta, **kw):
+    from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
+    free = meta["mode"].startswith("free")
+    return BatchedSchedulingEnv(B, world_params_from_dom(meta, free), reward=meta["mode"],
+                                net_zero_offer_reward=meta.get("netZero", 0.5), **kw)
+
+
+def _one(exp, b):
+    return {k: (v[b] if isinstance(v, np.ndarray) else v) for k, v in exp.items()}
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_replays_reference_trace(name):
+    """Recorded reference trace, replicated into B envs that straddle two tiles."""
+    tr, meta = load_golden(name)
+    T = tr["done"].shape[0]
+    free = meta["mode"].startswith("free")
+    agg = meta["mode"] == "agg"
+    B = 130
+    env = _env(B, meta, auction="external", spawn="u64")
+    e0 = env.export_state()
+    for b in (0, 1, 129):
+        assert_state_equal(_one(e0, b), tr, None, prefix=name)
+    rep = lambda a: np.broadcast_to(np.asarray(a)[None], (B,) + np.asarray(a).shape).copy()
+    for t in range(T):
+        r = env.step(rep(tr["in_offc"][t]), rep(tr["in_acc"][t]), rep(tr["in_auc"][t]),
+                     offer_price=rep(tr["in_offp"][t]) if free else None,
+                     spawn_u=rep(tr["in_spawn_u"][t]))
+        e = env.export_state()
+        assert (e["flags"] == 0).all(), (name, t)
+        for b in (0, 64, 129):
+            assert_state_equal(_one(e, b), tr, t, prefix=f"{name}[env {b}]")
+        r = {k: (v.cpu().numpy() if v is not None else None) for k, v in r.items()}
+        for b in (0, 63, 64, 129):
+            assert np.array_equal(r["offer"][b].astype(np.float64), tr["r_offer"][t]), (name, t)
+            if free:
+                assert np.array_equal(r["price"][b].astype(np.float64), tr["r_price"][t]), (name, t)
+            assert np.array_equal(r["acceptor"][b], tr["r_acceptor"][t]), (name, t, "acceptor")
+            assert np.array_equal(r["auctioneer"][b], tr["r_auctioneer"][t]), (name, t)
+            assert np.array_equal(r["agent"][b], tr["r_agent"][t]), (name, t, "agent")
+            assert r["done"][b] == tr["done"][t]
+            assert r["n_accepted"][b] == tr["n_accepted"][t]
+            assert r["n_terminated"][b] == tr["n_term"][t]
+            assert r["quality_cnt"][b] == tr["quality_cnt"][t]
+            if tr["quality_cnt"][t] > 0:
+                assert r["quality_sum"][b] / r["quality_cnt"][b] == pytest.approx(
+                    float(tr["quality"][t]), rel=1e-12, abs=1e-12)
+        if t % 7 == 0 or t == T - 1:
+            o = {k: v.cpu().numpy() for k, v in env.observe().items()}
+            for b in (0, 129):
+                if meta["agent_kind"] != "aggregated":
+                    assert np.array_equal(o["acceptor"][b], tr["obs_acc"][t]), (name, t)
+                    assert np.array_equal(o["offer"][b], tr["obs_off"][t]), (name, t)
+                assert np.array_equal(o["auctioneer"][b], tr["obs_auc"][t]), (name, t)
+                assert np.array_equal(o["ids"][b], tr["ids"][t]), (name, t)
+                assert np.array_equal(o["auctioneer_ids"][b], tr["auc_ids"][t]), (name, t)
+    env.close()
+
+
+DOMS = {
+    "cfg3": (dict(N=2, C=3, L=3, prios=[2, 4, 8], lens=[5, 5, 5], probs=[1 / 3] * 3, fix=[1]), "free_comm"),
+    "cfg2": (dict(N=4, C=4, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7]), "fix"),
+    "cfg1": (dict(N=2, C=3, L=2, prios=[5], lens=[4], probs=[1], fix=[3], mult=2), "fix"),
+    "agg": (dict(N=2, C=2, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7]), "agg"),
+    "F": (dict(N=8, C=8, L=4, prios=[3, 10, 6], lens=[6, 3, 2], probs=[0.5, 0.2, 0.3], fix=[2, 7, 4],
+               newJobs=2), "free_ncomm"),
+    "odd": (dict(N=3, C=5, L=2, prios=[1, 7, 4, 9], lens=[1, 2, 7, 3], probs=[0.1, 0.4, 0.3, 0.2],
+                 fix=[1, 5, 2, 6], mult=3), "fix"),
+}
+
+
+def random_actions(rng, B, dom, free, p_valid_hint=None):
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    NL = N * L
+    P = max(dom["prios"])
+    acc = rng.integers(0, NL + 1, (B, N, C))
+    # bias towards low indices so that real offers get accepted often
+    low = rng.random((B, N, C)) < 0.6
+    acc = np.where(low, rng.integers(0, 2, (B, N, C)), acc)
+    offc = rng.integers(0, C + 1, (B, N, L))
+    offp = rng.integers(0, P + 1, (B, N, L)) if free else None
+    return offc, acc, offp
+
+
+@pytest.mark.parametrize("key", list(DOMS))
+@pytest.mark.parametrize("auction", ["first", "random"])
+def test_cuda_matches_oracle_random_batch(key, auction):
+    """Thousands of envs, device Philox spawn + in-kernel auction, vs the CPU oracle."""
+    from oracle import oracle as O
+    dom, mode = DOMS[key]
+    free = mode.startswith("free")
+    B, T = (1000, 40) if key == "F" else (3000, 60)
+    seed = 1234
+    env = _env(B, dict(dom, mode=mode), auction=auction, spawn="philox", seed=seed, env_offset=77)
+    orc = O.Oracle(B, dom, mode, tie_mode=O.TIE_PHILOX if auction == "random" else O.TIE_FIRST,
+                   seed=seed, env_offset=77)
+    rng = np.random.default_rng(5)
+    for t in range(T):
+        offc, acc, offp = random_actions(rng, B, dom, free)
+        r = env.step(offc, acc, None, offer_price=offp)
+        orc.step(offc, acc, None, offp=offp)
+        r = {k: (v.cpu().numpy() if v is not None else None) for k, v in r.items()}
+        assert np.array_equal(r["auctioneer_idx"], orc.auc_out), (key, t, "auction winners")
+        assert np.array_equal(r["offer"].astype(np.float64), orc.r_offer), (key, t)
+        if free:
+            assert np.array_equal(r["price"].astype(np.float64), orc.r_price), (key, t)
+        assert np.array_equal(r["acceptor"], orc.r_acceptor), (key, t)
+        assert np.array_equal(r["auctioneer"], orc.r_auctioneer), (key, t)
+        assert np.array_equal(r["agent"], orc.r_agent), (key, t)
+        assert np.array_equal(r["n_accepted"], orc.n_accepted), (key, t)
+        assert np.array_equal(r["n_terminated"], orc.n_term), (key, t)
+        assert np.array_equal(r["flags"].astype(np.uint32), orc.flags), (key, t)
+        np.testing.assert_allclose(r["quality_sum"], orc.quality_sum, rtol=1e-12, atol=1e-12)
+        if t % 10 == 9 or t == T - 1:
+            e = env.export_state()
+            for b in rng.integers(0, B, 25):
+                ob = orc.export(int(b))
+                for k in STATE_KEYS:
+                    assert np.array_equal(np.asarray(e[k][b]), np.asarray(ob[k])), (key, t, b, k)
+                assert np.array_equal(e["chain"][b], ob["chain"]), (key, t, b, "chain")
+                assert e["job_counter"][b] == ob["job_counter"]
+            o = {k: v.cpu().numpy() for k, v in env.observe().items()}
+            for b in rng.integers(0, B, 10):
+                oo = orc.observe(int(b))
+                assert np.array_equal(o["acceptor"][b], oo["obs_acc"])
+                assert np.array_equal(o["offer"][b], oo["obs_off"])
+                assert np.array_equal(o["auctioneer"][b], oo["obs_auc"])
+                assert np.array_equal(o["ids"][b], oo["ids"])
+                assert np.array_equal(o["auctioneer_ids"][b], oo["auc_ids"])
+    assert int(orc.n_accepted.sum()) >= 0
+    env.close()
+
+
+def test_fault_flags():
+    """Out-of-range acceptor index -> ACTION_RANGE flag (reference: AssertionError);
+    chain capacity 1 -> CHAIN_OVERFLOW flag."""
+    dom, mode = DOMS["cfg2"]
+    env = _env(4, dict(dom, mode=mode), auction="first", spawn="philox", chain_capacity=1)
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    acc = np.zeros((4, N, C), np.int64)
+    acc[1, 0, 0] = N * L + 1
+    acc[2, 1, 2] = -1
+    r = env.step(np.zeros((4, N, L), np.int64), acc, None)
+    f = r["flags"].cpu().numpy()
+    assert f[0] == 0 and f[1] & 4 and f[2] & 4 and f[3] == 0
+    for t in range(40):
+        r = env.step(np.zeros((4, N, L), np.int64), np.zeros((4, N, C), np.int64), None)
+    assert (r["flags"].cpu().numpy()[0] & 1) == 1
+    env.close()
+
+
+def test_step_host_matches_device_step():
+    import torch
+    dom, mode = DOMS["cfg3"]
+    B = 500
+    a = _env(B, dict(dom, mode=mode), auction="first", spawn="philox", seed=3)
+    b = _env(B, dict(dom, mode=mode), auction="first", spawn="philox", seed=3)
+    rng = np.random.default_rng(0)
+    lay = a.layout
+    ah = torch.zeros((B, lay.action_halfs), dtype=torch.int16).pin_memory()
+    rh = torch.zeros((B, lay.result_words), dtype=torch.int32).pin_memory()
+    for t in range(20):
+        offc, acc, offp = random_actions(rng, B, dom, True)
+        a.step(offc, acc, None, offer_price=offp)
+        ah.copy_(a.action[:B].cpu())
+        b.step_host(ah, rh)
+        assert torch.equal(rh, a.result[:B].cpu())
+    assert a.round == b.round == 20
+    a.close(); b.close()
