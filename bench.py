@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark: agent-steps/sec of the batched env step + auction.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3|cfg2]
+
+One "step" = one pass of the hot path over one batch of environments: the step kernel
+(acceptances, in-kernel auction + core allocation, progress/completion, offer creation, Philox
+spawn, rewards) followed by the dense observation kernel, i.e. one SchedulingEnv.step for every
+environment.  Workload at N=1: BASELINE.json configs[2] ("cfg3": N=2 C=3 L=3, three job kinds,
+free prices, commercial reward, hard-coded auctioneer) at 65,536 environments -- the
+configuration the metric is quoted on.  Each extra GPU adds its own 65,536-env shard (weak
+scaling, no data-path collective).
+
+Timing: every step is bracketed by CUDA events on the launching stream; the L2 (126 MB) is
+flushed before every timed step by overwriting a 256 MiB buffer, so the state/action records are
+read from HBM.  `value` = units processed / sum of the per-step device times (max over ranks).
+`e2e` goes through msched_step_host: pinned host action records -> H2D -> step -> D2H of the
+result records -> sync, wall-clock timed.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # BASELINE.json configs[2]; reference src/trainPPOExperiment4-2.py:42-56,103
+    "cfg3": dict(dom=dict(N=2, C=3, L=3, prios=[2, 4, 8], lens=[5, 5, 5], probs=[1 / 3] * 3, fix=[1],
+                          mult=1, newJobs=1, episodeLength=100, netZero=0.5),
+                 mode="free_comm", envs=65536,
+                 desc="N2 C3 L3, 3 job kinds, free prices, commercial reward, hard-coded auctioneer"),
+    # BASELINE.json configs[1]; reference README.md:49-61, src/trainPPOCopy.py:41-54
+    "cfg2": dict(dom=dict(N=4, C=4, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7],
+                          mult=1, newJobs=1, episodeLength=100),
+                 mode="fix", envs=4096,
+                 desc="N4 C4 L3, 2 job kinds, fixed prices, divided reward, hard-coded auctioneer"),
+    "cfg4": dict(dom=dict(N=4, C=4, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7],
+                          mult=1, newJobs=1, episodeLength=100),
+                 mode="fix", envs=65536,
+                 desc="N4 C4 L3 (cfg2 domain) at 65,536 envs per GPU"),
+}
+
+
+def algorithmic_bytes(dom, mode):
+    """canonical bytes per env-step (state read+write, actions, rewards)
+    and of the dense observation record."""
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    NL = N * L
+    free = mode.startswith("free")
+    nj = dom.get("newJobs", 1)
+    S = 16 * C + 20 * NL + 4 * C + 8
+    w = 1 if NL + 1 <= 255 else 2
+    a = N * C * w + NL * (2 if free else 1) + C * w + N * nj
+    r = 4 * N * C + 4 * NL * (2 if free else 1) + 4 * C + 4 * N
+    o = 2 * (N * C * (3 + 2 * NL) + NL * (2 * C + 2) + C * (3 + 2 * NL))
+    return dict(step=2 * S + a + r, obs=o, state=S)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def traffic_from_profile(cfg_name):
+    """dram bytes per step-kernel launch from the committed `ncu --set full` capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(cfg_name, {}).get("step_kernel_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index, period=0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    NAMES = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap",
+             0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+             0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def sample(self):
+        nv = self.nv
+        mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.samples.append(mhz)
+        for bit, name in self.NAMES.items():
+            if mask & bit and name != "gpu_idle":
+                self.reasons.add(name)
+
+    def run(self):
+        if not self.ok:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.sample()
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.ok and not self.samples:
+            try:
+                self.sample()
+            except Exception:
+                pass
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def make_actions(torch, env, ring, seed):
+    """Uniform random action records: acceptor idx ~ U{0..NL}, offer core ~ U{0..C},
+    price ~ U{0..maxPrio}; a ring of distinct records so consecutive steps differ."""
+    lay, B = env.layout, env.B
+    g = torch.Generator(device=env.device).manual_seed(seed)
+    recs = []
+    P = max(env.cfg.prio[k] for k in range(env.cfg.J))
+    for _ in range(ring):
+        rec = torch.zeros((lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=env.device)
+        rec[:B, lay.a_acceptor: lay.a_acceptor + env.N * env.C] = torch.randint(
+            0, env.NL + 1, (B, env.N * env.C), generator=g, device=env.device, dtype=torch.int16)
+        rec[:B, lay.a_offer_core: lay.a_offer_core + env.NL] = torch.randint(
+            0, env.C + 1, (B, env.NL), generator=g, device=env.device, dtype=torch.int16)
+        if lay.a_offer_price >= 0:
+            rec[:B, lay.a_offer_price: lay.a_offer_price + env.NL] = torch.randint(
+                0, P + 1, (B, env.NL), generator=g, device=env.device, dtype=torch.int16)
+        recs.append(rec)
+    return recs
+
+
+def cpu_baseline_sample(cfg, seconds=12.0, threads=1, envs=2048):
+    """Times the CPU port (oracle/) on a bounded sample of the same workload.  Checker code used
+    as the reported baseline only; see DESIGN.md section "CPU baseline"."""
+    import numpy as np
+    from oracle import oracle as O
+    dom, mode = cfg["dom"], cfg["mode"]
+    free = mode.startswith("free")
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    NL, P = N * L, max(dom["prios"])
+    B = envs * threads
+    orc = O.Oracle(B, dom, mode, tie_mode=O.TIE_PHILOX, seed=0)
+    rng = np.random.default_rng(0)
+    ring = [(rng.integers(0, C + 1, (B, N, L)).astype(np.int32),
+             rng.integers(0, NL + 1, (B, N, C)).astype(np.int32),
+             rng.integers(0, P + 1, (B, N, L)).astype(np.int32) if free else None) for _ in range(4)]
+
+    def run(steps):
+        if threads == 1:
+            for s in range(steps):
+                offc, acc, offp = ring[s % 4]
+                orc.step(offc, acc, None, offp=offp)
+            return
+        bounds = [(t * envs, (t + 1) * envs) for t in range(threads)]
+
+        def work(b0, b1):
+            for s in range(steps):
+                offc, acc, offp = ring[s % 4]
+                orc.step(offc, acc, None, offp=offp, b0=b0, b1=b1)
+        ths = [threading.Thread(target=work, args=b) for b in bounds]
+        [t.start() for t in ths]
+        [t.join() for t in ths]
+
+    run(100)  # warm: steady-state occupancy
+    steps_done, t0 = 0, time.perf_counter()
+    chunk = 50
+    while True:
+        run(chunk)
+        steps_done += chunk
+        el = time.perf_counter() - t0
+        if el >= seconds:
+            break
+    return dict(value=B * N * steps_done / el, env_steps=B * steps_done, seconds=el, envs=B,
+                steps=steps_done)
+
+
+def run_reference(args, cfg):
+    """--impl reference: the CPU port of the reference's path on all host cores (the Python
+    reference itself cannot travel to the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    K = max(1, args.steps)
+    res = cpu_baseline_sample(cfg, seconds=min(60.0, max(5.0, 0.01 * K)), threads=threads, envs=1024)
+    dom = cfg["dom"]
+    line = {
+        "impl": "reference", "metric": "agent-steps/sec, batched env step+auction",
+        "value": res["value"], "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / res["steps"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+        "data": "synthetic",
+        "config": {"workload": args.config, "domain": cfg["desc"], "envs_per_step": res["envs"],
+                   "note": "CPU port (oracle/msched_oracle.c) of the reference path; each step is a "
+                           "bounded sample of the 65,536-env workload"},
+        "cpu_baseline": {"value": res["value"], "unit": "agent-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"{res['envs']} envs x {res['steps']} steps, {threads} threads"},
+        "e2e": {"value": res["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg3", choices=list(CONFIGS))
+    ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
+    ap.add_argument("--obs", default="dense", choices=["dense", "none"])
+    ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (diagnostic)")
+    ap.add_argument("--state-warm", type=int, default=1000, help="untimed steps to reach steady state")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        return run_reference(args, cfg)
+
+    import torch
+    import torch.distributed as dist
+    from marl_scheduling_b200 import _lib as L
+    from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    dom, mode = cfg["dom"], cfg["mode"]
+    B = args.envs or cfg["envs"]
+    N = dom["N"]
+    env = BatchedSchedulingEnv(B, world_params_from_dom(dom, mode.startswith("free")), reward=mode,
+                               auction="random", spawn="philox", seed=0, env_offset=rank * B,
+                               net_zero_offer_reward=dom.get("netZero", 0.5), device=local)
+    lay = env.layout
+    ring = make_actions(torch, env, 8, seed=1 + rank)
+    results = [torch.zeros_like(env.result) for _ in range(2)]
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    dense = args.obs == "dense"
+
+    def one_step(i):
+        env.step_records(ring[i % len(ring)], results[i & 1])
+        if dense:
+            env.observe()
+
+    for i in range(args.state_warm):
+        one_step(i)
+    torch.cuda.synchronize()
+    flags = int(results[(args.state_warm - 1) & 1][:B, lay.r_flags].max().item()) if args.state_warm else 0
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    for i in range(args.warmup):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        one_step(i)
+    K = args.steps
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        if flush is not None:
+            flush.fill_(i & 0xFF)
+        ev[i][0].record()
+        env.step_records(ring[i % len(ring)], results[i & 1])
+        ev[i][1].record()
+        if dense:
+            env.observe()
+        ev[i][2].record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.finish()
+    step_ms = [e[0].elapsed_time(e[1]) for e in ev]
+    obs_ms = [e[1].elapsed_time(e[2]) for e in ev]
+    tot_ms = sum(step_ms) + sum(obs_ms)
+    t = torch.tensor([tot_ms, sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tot_ms, stepk_ms = float(t[0]), float(t[1])
+    value = world * B * N * K / (tot_ms * 1e-3)
+
+    # ---- e2e: host records in, host records out, through msched_step_host ----
+    e2e = None
+    nE = min(args.e2e_steps, K) if K > 0 else 0
+    if nE > 0:
+        ah = [r[:B].cpu().pin_memory() for r in ring[:4]]
+        rh = torch.zeros((B, lay.result_words), dtype=torch.int32).pin_memory()
+        for i in range(5):
+            env.step_host(ah[i % 4], rh)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(nE):
+            env.step_host(ah[i % 4], rh)
+            if dense:
+                env.observe()  # observations stay on the device for the policy kernels
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * N * nE / float(te[0]), "unit": "agent-steps/s",
+               "h2d_bytes_per_step": B * lay.action_halfs * 2, "d2h_bytes_per_step": B * lay.result_words * 4,
+               "steps": nE, "api": "msched_step_host (pinned action records -> result records)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ab = algorithmic_bytes(dom, mode)
+    peak, peak_src = measured_peak()
+    step_launch_s = stepk_ms * 1e-3 / K
+    achieved = ab["step"] * B / step_launch_s / 1e9
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        c = cpu_baseline_sample(cfg, seconds=args.cpu_seconds, threads=1, envs=2048)
+        cpu = {"value": c["value"], "unit": "agent-steps/s", "cores": 1, "kind": "port",
+               "sample": f"{c['envs']} envs x {c['steps']} steps of the same workload, 1 thread of "
+                         f"{os.cpu_count()} host cores, oracle/msched_oracle.c"}
+    line = {
+        "metric": "agent-steps/sec, batched env step+auction @65,536 envs",
+        "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic",
+        "config": {"workload": args.config, "domain": cfg["desc"], "envs_per_gpu": B,
+                   "observations": args.obs, "auctioneer": "in-kernel, random arg-max (Philox)",
+                   "spawn": "device Philox", "actions": "uniform random, ring of 8 records",
+                   "l2": "warm (no flush)" if args.no_flush else "flushed before every timed step (256 MiB write)",
+                   "state_warm_steps": args.state_warm, "step_tile": os.environ.get("MSCHED_STEP_TILE", "auto")},
+        "clocks": clocks,
+        "e2e": e2e,
+        "gpu_launches": K * (2 if dense else 1),
+        "roofline": {"bound": "hbm", "kernel": "step_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile(args.config),
+                     "peak_source": peak_src, "algorithmic_bytes_per_env_step": ab["step"],
+                     "units_per_launch": B, "launch_us": step_launch_s * 1e6},
+        "kernels": {"step_us": 1e3 * sum(step_ms) / K, "observe_us": 1e3 * sum(obs_ms) / K,
+                    "observe_algorithmic_bytes_per_env": ab["obs"] + ab["state"]},
+        "cpu_baseline": cpu,
+        "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
+        "sticky_flags_after_warm": flags,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
