@@ -27,7 +27,9 @@
  *                                 | agent reward i32 [N] | quality_sum f64 (lo,hi words)
  *                                 | counts (quality_cnt | n_accepted<<8 | n_terminated<<16
  *                                 | done<<24) | flags | auctioneer idx used, 2 x i16 per word
- *   obs     int16 [obs_halfs]     dense reference-layout observations (Appendix B of SURVEY.md)
+ *   obs     int16 [obs_halfs]     dense reference-layout observations (Appendix B of SURVEY.md),
+ *                                 rows padded to aligned 32-bit (value, value) pairs
+ *   ids     int16 [ids_halfs]     offer-ID tables [N][C][NL] | [C][NL] (drop-in API / parity only)
  *   chain   uint32[C][chainCap][2] liability chains (src/world.py:238,285-289), touched
  *                                 only on acceptance / termination
  */
@@ -107,7 +109,8 @@ typedef struct MschedLayout {
     int32_t state_words;  /* uint32 per env */
     int32_t action_halfs; /* int16 per env (even; action_halfs/2 is odd) */
     int32_t result_words; /* uint32 per env (odd) */
-    int32_t obs_halfs;    /* int16 per env; 0 if the dense layout is infeasible (>32 KB/env) */
+    int32_t obs_halfs;    /* int16 per env (even; obs_halfs/2 is odd) */
+    int32_t ids_halfs;    /* int16 per env = (N*C + C) * N*L */
     int32_t chain_words;  /* uint32 per env = C*chainCapacity*2 */
     /* action record, int16 element offsets */
     int32_t a_acceptor, a_offer_core, a_offer_price, a_auctioneer, a_spawn_kind;
@@ -115,9 +118,11 @@ typedef struct MschedLayout {
     int32_t r_offer, r_price, r_acceptor, r_auctioneer, r_agent, r_quality, r_counts, r_flags,
         r_auctioneer_idx;
     int32_t RL, RC; /* reward row lengths: L,C (divided) or 1,1 (aggregated) */
-    /* obs record, int16 element offsets: acceptor [N][C][3+2NL], offer [N][L][2C+2],
-     * auctioneer [C][3+2NL], offer-ID tables [N][C][NL] and [C][NL] */
-    int32_t o_acceptor, o_offer, o_auctioneer, o_ids, o_auctioneer_ids;
+    /* obs record, int16 element offsets of the first logical element of each block and the row
+     * strides: acceptor [N][C] rows of 3+2NL values, stride o_acc_row (o_acceptor is odd: the
+     * rows carry one leading pad so that (price,time) pairs are aligned words); auctioneer [C]
+     * rows, same stride; offer [N][L] rows of 2C+2 values, stride o_off_row */
+    int32_t o_acceptor, o_offer, o_auctioneer, o_acc_row, o_off_row;
 } MschedLayout;
 
 int msched_abi_version(void);
@@ -153,8 +158,10 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
                      void *stream);
 
 /* Agent.gatherObservations + gatherDividedAuctioneerObservation (src/Agent.py:148-300,
- * src/Auctioneer.py:20-77): dense reference-layout observations and offer-ID tables */
-int msched_observe_dense(void *handle, int16_t *obs_dev, void *stream);
+ * src/Auctioneer.py:20-77): dense reference-layout observations; ids_dev (optional, may be
+ * NULL) receives the offer-ID tables env.correspondingOfferIDs /
+ * auctioneer_correspondingOfferIDs (src/SchedulingEnvironment.py:26-29, B*ids_halfs int16) */
+int msched_observe_dense(void *handle, int16_t *obs_dev, int16_t *ids_dev, void *stream);
 
 /* debug / parity: reference-shaped int32 dump of envs [env0, env0+count):
  * core [C][7] owner,prio,rem,jobid,kind,birth,init ; slot [N*L][7] prio,rem,jobid,kind,wait,

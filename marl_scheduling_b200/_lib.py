@@ -41,11 +41,12 @@ class MschedConfig(C.Structure):
 
 class MschedLayout(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
-        "padded_envs", "state_words", "action_halfs", "result_words", "obs_halfs", "chain_words",
+        "padded_envs", "state_words", "action_halfs", "result_words", "obs_halfs", "ids_halfs",
+        "chain_words",
         "a_acceptor", "a_offer_core", "a_offer_price", "a_auctioneer", "a_spawn_kind",
         "r_offer", "r_price", "r_acceptor", "r_auctioneer", "r_agent", "r_quality", "r_counts",
         "r_flags", "r_auctioneer_idx", "RL", "RC",
-        "o_acceptor", "o_offer", "o_auctioneer", "o_ids", "o_auctioneer_ids")]
+        "o_acceptor", "o_offer", "o_auctioneer", "o_acc_row", "o_off_row")]
 
 
 class MschedMlpGroup(C.Structure):
@@ -68,7 +69,7 @@ SYMBOLS = {
     "msched_set_round": (C.c_int, [P, C.c_int64]),
     "msched_step": (C.c_int, [P, P, P, P, P]),
     "msched_step_host": (C.c_int, [P, P, P, P]),
-    "msched_observe_dense": (C.c_int, [P, P, P]),
+    "msched_observe_dense": (C.c_int, [P, P, P, P]),
     "msched_export_state": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, P]),
     "msched_mlp_param_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "msched_actor_forward": (C.c_int, [C.POINTER(MschedMlpGroup), P, C.c_int, C.c_int64, C.c_int,

@@ -51,6 +51,7 @@ class BatchedSchedulingEnv:
         self.action = torch.zeros((Bp, lay.action_halfs), dtype=torch.int16, device=dev)
         self.result = torch.zeros((Bp, lay.result_words), dtype=torch.int32, device=dev)
         self._obs = None
+        self._ids = None
         L.check(self.lib.msched_bind_state(self.handle, self.state.data_ptr(), self.chain.data_ptr()))
         self.reset()
 
@@ -173,24 +174,33 @@ class BatchedSchedulingEnv:
         return out
 
     # ------------------------------------------------------------------ observations
-    def observe(self):
+    def observe(self, with_ids=False):
         """Dense reference-layout observations (reference src/Agent.py:148-300,
-        src/Auctioneer.py:20-77) as int16 views: acceptor [B,N,C,3+2NL], offer [B,N,L,2C+2],
-        auctioneer [B,C,3+2NL], ids [B,N,C,NL], auctioneer_ids [B,C,NL]."""
+        src/Auctioneer.py:20-77) as int16 strided views into the obs record: acceptor
+        [B,N,C,3+2NL], offer [B,N,L,2C+2], auctioneer [B,C,3+2NL]; with_ids adds the offer-ID
+        tables ids [B,N,C,NL], auctioneer_ids [B,C,NL] (env.correspondingOfferIDs)."""
         lay = self.layout
         if self._obs is None:
             self._obs = torch.zeros((lay.padded_envs, lay.obs_halfs), dtype=torch.int16,
                                     device=self.device)
-        L.check(self.lib.msched_observe_dense(self.handle, self._obs.data_ptr(), self._stream()))
+        ids = None
+        if with_ids:
+            if self._ids is None:
+                self._ids = torch.zeros((self.B, lay.ids_halfs), dtype=torch.int16, device=self.device)
+            ids = self._ids
+        L.check(self.lib.msched_observe_dense(self.handle, self._obs.data_ptr(),
+                                              None if ids is None else ids.data_ptr(), self._stream()))
         B, N, Cc, Lc, NL = self.B, self.N, self.C, self.Lc, self.NL
-        Wd = 3 + 2 * NL
-        o = self._obs[:B]
-        return dict(
-            acceptor=o[:, lay.o_acceptor: lay.o_acceptor + N * Cc * Wd].view(B, N, Cc, Wd),
-            offer=o[:, lay.o_offer: lay.o_offer + NL * (2 * Cc + 2)].view(B, N, Lc, 2 * Cc + 2),
-            auctioneer=o[:, lay.o_auctioneer: lay.o_auctioneer + Cc * Wd].view(B, Cc, Wd),
-            ids=o[:, lay.o_ids: lay.o_ids + N * Cc * NL].view(B, N, Cc, NL),
-            auctioneer_ids=o[:, lay.o_auctioneer_ids: lay.o_auctioneer_ids + Cc * NL].view(B, Cc, NL))
+        Wd, OH, RA, RO = 3 + 2 * NL, lay.obs_halfs, lay.o_acc_row, lay.o_off_row
+        o = self._obs
+        out = dict(
+            acceptor=o.as_strided((B, N, Cc, Wd), (OH, Cc * RA, RA, 1), lay.o_acceptor),
+            offer=o.as_strided((B, N, Lc, 2 * Cc + 2), (OH, Lc * RO, RO, 1), lay.o_offer),
+            auctioneer=o.as_strided((B, Cc, Wd), (OH, RA, 1), lay.o_auctioneer))
+        if with_ids:
+            out["ids"] = ids[:, : N * Cc * NL].view(B, N, Cc, NL)
+            out["auctioneer_ids"] = ids[:, N * Cc * NL:].view(B, Cc, NL)
+        return out
 
     # ------------------------------------------------------------------ debug / parity
     def export_state(self, env0=0, count=None):

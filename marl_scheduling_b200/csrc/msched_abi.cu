@@ -46,7 +46,7 @@ int compute_layout(const MschedConfig *c, MschedLayout *o)
     if (c->B < 1) return fail(MSCHED_E_ARG, "B must be >= 1");
     if (c->N < 1 || c->N > 250) return fail(MSCHED_E_ARG, "numberOfAgents must be in 1..250");
     if (c->C < 1 || c->C > 64) return fail(MSCHED_E_ARG, "numberOfCores must be in 1..64");
-    if (c->L < 1 || (long long)c->N * c->L > 4096) return fail(MSCHED_E_ARG, "N*L must be in 1..4096");
+    if (c->L < 1 || (long long)c->N * c->L > 254) return fail(MSCHED_E_ARG, "N*L must be in 1..254");
     if (c->J < 1 || c->J > MSCHED_MAX_KINDS) return fail(MSCHED_E_ARG, "job kinds must be in 1..16");
     if (c->newJobsPerRound < 0 || c->newJobsPerRound > c->L)
         return fail(MSCHED_E_ARG, "newJobsPerRoundPerAgent must be in 0..collectionLength");
@@ -94,20 +94,22 @@ int compute_layout(const MschedConfig *c, MschedLayout *o)
     o->r_flags = w; w += 1;
     o->r_auctioneer_idx = w; w += (C + 1) / 2;
     o->result_words = make_odd(w);
-    const int Wd = 3 + 2 * NL;
-    long long oh = 0;
-    o->o_acceptor = (int)oh; oh += (long long)N * C * Wd;
-    o->o_offer = (int)oh; oh += (long long)NL * (2 * C + 2);
-    o->o_auctioneer = (int)oh; oh += (long long)C * Wd;
-    o->o_ids = (int)oh; oh += (long long)N * C * NL;
-    o->o_auctioneer_ids = (int)oh; oh += (long long)C * NL;
+    const int RA = 3 + 2 * NL + 1, RO = 2 * C + 2;
+    const long long oh = (long long)(N * C + C) * RA + (long long)NL * RO;
     if (oh > (1ll << 28)) return fail(MSCHED_E_ARG, "observation record too large");
+    o->o_acceptor = 1;
+    o->o_auctioneer = N * C * RA + 1;
+    o->o_offer = (N * C + C) * RA;
+    o->o_acc_row = RA;
+    o->o_off_row = RO;
     o->obs_halfs = even_odd_half((int)oh);
+    o->ids_halfs = (N * C + C) * NL;
     o->chain_words = C * c->chainCapacity * 2;
     return MSCHED_OK;
 }
 
 typedef void (*StepKernel)(const DevParams);
+typedef void (*ObsKernel)(const DevParams);
 
 struct Handle {
     MschedConfig cfg;
@@ -116,8 +118,9 @@ struct Handle {
     int device;
     long long round;
     int smemOptin;
-    int stepTile, obsTile;  // envs per CTA (0 = unsupported / direct)
+    int stepTile;  // envs per CTA of the step kernel
     StepKernel stepFn;
+    ObsKernel obsFn;  // compile-time-domain observation kernel, or null -> direct kernel
     int16_t *stageAction;
     uint32_t *stageResult;
 };
@@ -129,6 +132,15 @@ StepKernel pick_step_kernel(int N, int C, int L)
     if (N == 2 && C == 3 && L == 2) return step_kernel<2, 3, 2>;  // BASELINE cfg1 (trainHC)
     if (N == 2 && C == 2 && L == 3) return step_kernel<2, 2, 3>;  // README 2-agent domain
     return step_kernel<0, 0, 0>;
+}
+
+ObsKernel pick_obs_kernel(int N, int C, int L)
+{
+    if (N == 2 && C == 3 && L == 3) return observe_kernel_t<2, 3, 3>;
+    if (N == 4 && C == 4 && L == 3) return observe_kernel_t<4, 4, 3>;
+    if (N == 2 && C == 3 && L == 2) return observe_kernel_t<2, 3, 2>;
+    if (N == 2 && C == 2 && L == 3) return observe_kernel_t<2, 2, 3>;
+    return nullptr;
 }
 
 void fill_params(Handle *h)
@@ -148,8 +160,6 @@ void fill_params(Handle *h)
     p.rOffer = l.r_offer; p.rPrice = l.r_price; p.rAcc = l.r_acceptor; p.rAuc = l.r_auctioneer;
     p.rAgent = l.r_agent; p.rQual = l.r_quality; p.rCounts = l.r_counts; p.rFlags = l.r_flags;
     p.rAucIdx = l.r_auctioneer_idx; p.RL = l.RL; p.RC = l.RC;
-    p.oAcc = l.o_acceptor; p.oOff = l.o_offer; p.oAuc = l.o_auctioneer; p.oIds = l.o_ids;
-    p.oAucIds = l.o_auctioneer_ids;
     for (int k = 0; k < MSCHED_MAX_KINDS; ++k) {
         p.prio[k] = c.prio[k]; p.len[k] = c.len[k]; p.fix[k] = c.fixPrice[k]; p.cum[k] = c.cumProb[k];
     }
@@ -196,6 +206,18 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
         return fail(MSCHED_E_NODEVICE, "no CUDA device (this library has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(MSCHED_E_ARG, "bad device index");
     CUDA_TRY(cudaSetDevice(device));
+    {
+        double rcp[256];
+        unsigned char odd[256];
+        for (int t = 0; t < 256; ++t) {
+            rcp[t] = t ? 1.0 / (double)t : 0.0;
+            int o = t ? t : 1;
+            while ((o & 1) == 0) o >>= 1;
+            odd[t] = (unsigned char)o;
+        }
+        CUDA_TRY(cudaMemcpyToSymbol(c_rcp, rcp, sizeof(rcp)));
+        CUDA_TRY(cudaMemcpyToSymbol(c_oddpart, odd, sizeof(odd)));
+    }
     Handle *h = new Handle();
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
@@ -203,7 +225,8 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     h->device = device;
     fill_params(h);
     CUDA_TRY(cudaDeviceGetAttribute(&h->smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    const size_t stepBytes = (size_t)lay.state_words * 4 + (size_t)lay.action_halfs * 2 + (size_t)lay.result_words * 4;
+    const size_t stepBytes = (size_t)lay.state_words * 4 + (size_t)lay.action_halfs * 2 + (size_t)lay.result_words * 4 +
+                             (size_t)scratch_words(cfg->C) * 4;
     h->stepTile = pick_tile(stepBytes, h->smemOptin, "MSCHED_STEP_TILE");
     if (h->stepTile == 0) {
         delete h;
@@ -213,11 +236,12 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     h->stepFn = pick_step_kernel(cfg->N, cfg->C, cfg->L);
     CUDA_TRY(cudaFuncSetAttribute(h->stepFn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(h->stepTile * stepBytes)));
-    const size_t obsBytes = (size_t)lay.state_words * 4 + (size_t)lay.obs_halfs * 2;
-    h->obsTile = pick_tile(obsBytes, h->smemOptin, "MSCHED_OBS_TILE");
-    if (h->obsTile)
-        CUDA_TRY(cudaFuncSetAttribute(observe_kernel_staged, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(h->obsTile * obsBytes)));
+    h->obsFn = pick_obs_kernel(cfg->N, cfg->C, cfg->L);
+    if (h->obsFn && (lay.state_words * 4 > lay.obs_halfs * 2 || 32 * lay.obs_halfs * 2 + 64 > h->smemOptin))
+        h->obsFn = nullptr;
+    if (h->obsFn)
+        CUDA_TRY(cudaFuncSetAttribute(h->obsFn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      32 * lay.obs_halfs * 2));
     CUDA_TRY(cudaMalloc(&h->stageAction, (size_t)lay.padded_envs * lay.action_halfs * 2));
     CUDA_TRY(cudaMalloc(&h->stageResult, (size_t)lay.padded_envs * lay.result_words * 4));
     CUDA_TRY(cudaMemset(h->stageAction, 0, (size_t)lay.padded_envs * lay.action_halfs * 2));
@@ -288,8 +312,9 @@ int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_d
     p.spawnU = spawn_u_dev;
     p.result = result_dev;
     p.round = (int)h->round;
+    p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     const int T = h->stepTile;
-    const size_t smem = (size_t)T * ((size_t)p.W * 4 + (size_t)p.AH * 2 + (size_t)p.RW * 4);
+    const size_t smem = (size_t)T * ((size_t)p.W * 4 + (size_t)p.AH * 2 + (size_t)p.RW * 4 + (size_t)scratch_words(p.C) * 4);
     h->stepFn<<<p.Bpad / T, T, smem, static_cast<cudaStream_t>(stream)>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->round += 1;
@@ -313,7 +338,7 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
     return MSCHED_OK;
 }
 
-int msched_observe_dense(void *handle, int16_t *obs_dev, void *stream)
+int msched_observe_dense(void *handle, int16_t *obs_dev, int16_t *ids_dev, void *stream)
 {
     Handle *h = static_cast<Handle *>(handle);
     if (!h || !obs_dev) return fail(MSCHED_E_ARG, "null handle/obs");
@@ -322,14 +347,15 @@ int msched_observe_dense(void *handle, int16_t *obs_dev, void *stream)
     DevParams p = h->p;
     p.obs = obs_dev;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (h->obsTile) {
-        const int T = h->obsTile;
-        const size_t smem = (size_t)T * ((size_t)p.W * 4 + (size_t)p.OH * 2);
-        observe_kernel_staged<<<p.Bpad / T, T, smem, s>>>(p);
-    } else {
+    if (h->obsFn)
+        h->obsFn<<<p.Bpad / 32, 32, (size_t)32 * p.OH * 2, s>>>(p);
+    else
         observe_kernel_direct<<<(p.Bpad + 63) / 64, 64, 0, s>>>(p);
-    }
     CUDA_TRY(cudaGetLastError());
+    if (ids_dev) {
+        ids_kernel<<<(p.B + 63) / 64, 64, 0, s>>>(p, ids_dev);
+        CUDA_TRY(cudaGetLastError());
+    }
     return MSCHED_OK;
 }
 

@@ -39,13 +39,13 @@ struct DevParams {
     int sChlen, sSlot;
     int aAcc, aOffc, aOffp, aAuc, aSpawn;
     int rOffer, rPrice, rAcc, rAuc, rAgent, rQual, rCounts, rFlags, rAucIdx, RL, RC;
-    int oAcc, oOff, oAuc, oIds, oAucIds;
     // per-kind tables
     int prio[kMaxKinds], len[kMaxKinds], fix[kMaxKinds];
     double cum[kMaxKinds];
     float netZero;
     // dynamic
     int round;
+    int doneFlag;  // (round + 1) % episodeLength == 0, src/SchedulingEnvironment.py:64-67
     unsigned long long seed;
     long long envOffset;
     // buffers
@@ -164,6 +164,9 @@ __device__ __forceinline__ void bulk_s2g(void *dst_gmem, const void *src_smem, u
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// wait only until the bulk stores have READ their shared-memory source (enough before CTA exit)
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // make this thread's generic-proxy shared-memory writes visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

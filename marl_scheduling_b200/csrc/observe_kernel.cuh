@@ -4,110 +4,168 @@
 //   src/Agent.py:271-300    getOfferNetObservationTensor
 //   src/Auctioneer.py:20-77 gatherDividedAuctioneerObservation
 //
-// Observation record (int16 per env, layout from msched_get_layout):
-//   acceptor [N][C][3+2NL] : own?1:0, own?prio:-1, own?rem:-1, (price,time) of the offers addressed
-//                            to (agent, core) in creation order, (-2,-2) padding
-//   offer    [N][L][2C+2]  : (prio, rem) of every core, then of the slot (empty = -1)
-//   auctioneer [C][3+2NL]  : as acceptor with owner 0
-//   ids      [N][C][NL], auctioneer ids [C][NL] : offerIDs of those offers, -2 padding
+// Observation record (int16 per env, offsets from msched_get_layout).  Row CONTENTS are the
+// reference's; rows are padded so that every (value, value) pair is one aligned 32-bit word:
+//   acceptor rows   [N*C] x RA halfs, RA = 3+2NL+1: [pad, own?1:0, own?prio:-1, own?rem:-1,
+//                   (price,time) of the offers addressed to (agent, core) in creation order,
+//                   (-2,-2) padding]; the logical row starts at +1 (o_acceptor is odd)
+//   auctioneer rows [C] x RA, same with owner 0
+//   offer rows      [N*L] x RO halfs, RO = 2C+2: (prio, rem) of every core, then of the slot
 // The semi-/fully-aggregated layouts (src/Agent.py:82-140, 399-461) are concatenations of these
-// blocks and are assembled as views on the host side.
+// rows and are assembled as views on the host side.  Offer-ID tables (only the drop-in API and
+// the parity tests need them) are a separate record written by ids_kernel.
 #pragma once
 #include "msched_common.cuh"
 
 namespace msched {
 
-// one acceptor-style row for `who` (agentID, or 0 = auctioneer) and core j
-__device__ __forceinline__ void acceptor_row(const DevParams &p, const uint32_t *st, int who, int j,
-                                             int16_t *row, int16_t *ids)
+__device__ __forceinline__ uint32_t pair16(int lo, int hi)
 {
-    const int NL = p.NL;
-    const uint32_t *slot = st + p.sSlot;
-    const uint32_t cw0 = st[2 + 3 * j];
-    const bool own = core_owner(cw0) == who;
-    const int kind = job_kind(cw0);
-    row[0] = own ? 1 : 0;
-    row[1] = (int16_t)((own && kind >= 0) ? p.prio[kind] : -1);
-    row[2] = (int16_t)(own ? job_rem(cw0) : -1);
-    int n = 0;
-    if (own) {  // every pending offer to core j is addressed to its owner
-        const uint32_t key = (uint32_t)(j + 1) | ((uint32_t)who << 8);
-        int id = 0;
-        for (int s = 0; s < NL; ++s) {
-            const uint32_t w3 = slot[4 * s + 3];
-            if ((w3 & 0xffu) == 0u) continue;
-            ++id;  // Offer.offerID restarts at 1 every step, src/world.py:324-325
-            if ((w3 & 0xffffu) != key) continue;
-            row[3 + 2 * n] = (int16_t)off_price(w3);
-            row[4 + 2 * n] = (int16_t)job_rem(slot[4 * s]);
-            ids[n] = (int16_t)id;
-            ++n;
-        }
-    }
-    for (; n < NL; ++n) {
-        row[3 + 2 * n] = -2;
-        row[4 + 2 * n] = -2;
-        ids[n] = -2;
-    }
+    return (uint32_t)(lo & 0xffff) | ((uint32_t)(hi & 0xffff) << 16);
+}
+__device__ __forceinline__ uint32_t job_pair(const DevParams &p, uint32_t w0)
+{  // (priority, remainingLength) of a core/slot job word; empty -> (-1, -1)
+    const int kind = job_kind(w0);
+    return kind >= 0 ? pair16(p.prio[kind], job_rem(w0)) : 0xffffffffu;
 }
 
-__device__ __forceinline__ void observe_env(const DevParams &p, const uint32_t *st, int16_t *ob)
+// ---- fast path: compile-time domain, one warp per 32-env tile --------------------------------
+// The state tile lands (TMA) in the front of the staging buffer, every lane lifts its record into
+// registers, and the same buffer is then overwritten with the observation tile that one bulk
+// store writes back: shared memory per env = the observation record only.
+template <int N, int C, int L>
+__global__ void __launch_bounds__(32) observe_kernel_t(const __grid_constant__ DevParams p)
 {
-    const int N = p.N, C = p.C, L = p.L, NL = p.NL, Wd = 3 + 2 * NL, Wo = 2 * C + 2;
-    const uint32_t *slot = st + p.sSlot;
-    for (int a = 0; a < N; ++a)
-        for (int j = 0; j < C; ++j)
-            acceptor_row(p, st, a + 1, j, ob + p.oAcc + (a * C + j) * Wd, ob + p.oIds + (a * C + j) * NL);
-    for (int j = 0; j < C; ++j)
-        acceptor_row(p, st, 0, j, ob + p.oAuc + j * Wd, ob + p.oAucIds + j * NL);
-    for (int s = 0; s < NL; ++s) {
-        int16_t *row = ob + p.oOff + s * Wo;
-        for (int j = 0; j < C; ++j) {
-            const uint32_t cw0 = st[2 + 3 * j];
-            const int kind = job_kind(cw0);
-            row[2 * j] = (int16_t)(kind >= 0 ? p.prio[kind] : -1);
-            row[2 * j + 1] = (int16_t)job_rem(cw0);
-        }
-        const uint32_t w0 = slot[4 * s];
-        const int kind = job_kind(w0);
-        row[2 * C] = (int16_t)(kind >= 0 ? p.prio[kind] : -1);
-        row[2 * C + 1] = (int16_t)job_rem(w0);
-    }
-}
-
-// staged variant: state tile in by TMA, observation tile out by TMA.
-// dynamic smem = blockDim.x * (W*4 + OH*2)
-__global__ void __launch_bounds__(128) observe_kernel_staged(const __grid_constant__ DevParams p)
-{
-    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NL = N * L;
+    constexpr int W = (2 + 3 * C + (C + 3) / 4 + 4 * NL) | 1;
+    constexpr int SSLOT = 2 + 3 * C + (C + 3) / 4;
+    constexpr int RAw = NL + 2, ROw = C + 1;
+    static_assert(C <= 8, "packed per-core counters");
+    extern __shared__ __align__(128) uint32_t sm[];
     __shared__ __align__(8) uint64_t bar;
-    const int T = blockDim.x, lane = threadIdx.x, env0 = blockIdx.x * T;
-    const uint32_t stBytes = (uint32_t)T * p.W * 4u, obBytes = (uint32_t)T * p.OH * 2u;
-    uint32_t *sState = reinterpret_cast<uint32_t *>(smem);
-    int16_t *sObs = reinterpret_cast<int16_t *>(smem + stBytes);
+    const int lane = threadIdx.x, env0 = blockIdx.x * 32;
+    const int OW = p.OH >> 1;
     if (lane == 0) {
         mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, stBytes);
-        bulk_g2s(sState, p.state + (size_t)env0 * p.W, stBytes, &bar);
+        mbar_expect_tx(&bar, 32u * W * 4u);
+        bulk_g2s(sm, p.state + (size_t)env0 * W, 32u * W * 4u, &bar);
     }
-    __syncthreads();
+    __syncwarp();
     mbar_wait(&bar, 0);
-    observe_env(p, sState + (size_t)lane * p.W, sObs + (size_t)lane * p.OH);
+    uint32_t st[W];
+#pragma unroll
+    for (int k = 0; k < W; ++k) st[k] = sm[lane * W + k];
+    __syncwarp();
+
+    uint32_t *ob = sm + (size_t)lane * OW;
+    // background: nobody owns, no offers
+#pragma unroll
+    for (int r = 0; r < N * C + C; ++r) {
+        ob[r * RAw] = 0u;
+        ob[r * RAw + 1] = 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < NL; ++k) ob[r * RAw + 2 + k] = 0xfffefffeu;
+    }
+    uint32_t cp[C];
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        cp[j] = job_pair(p, st[2 + 3 * j]);
+        const int o = core_owner(st[2 + 3 * j]);
+        const int row = o > 0 ? (o - 1) * C + j : N * C + j;
+        ob[row * RAw] = 0x00010000u;  // [pad, own = 1]
+        ob[row * RAw + 1] = cp[j];
+    }
+    unsigned long long cnt = 0ull;
+#pragma unroll
+    for (int s = 0; s < NL; ++s) {
+        const uint32_t w3 = st[SSLOT + 4 * s + 3];
+        const int c = (int)(w3 & 0xffu);
+        if (c != 0) {
+            const int j = c - 1, r = off_recip(w3);
+            const int row = r > 0 ? (r - 1) * C + j : N * C + j;
+            const int n = (int)((cnt >> (8 * j)) & 0xffull);
+            cnt += 1ull << (8 * j);
+            ob[row * RAw + 2 + n] = pair16(off_price(w3), job_rem(st[SSLOT + 4 * s]));
+        }
+    }
+    uint32_t *oo = ob + (N * C + C) * RAw;
+#pragma unroll
+    for (int s = 0; s < NL; ++s) {
+#pragma unroll
+        for (int j = 0; j < C; ++j) oo[s * ROw + j] = cp[j];
+        oo[s * ROw + C] = job_pair(p, st[SSLOT + 4 * s]);
+    }
+    // tail padding words of the record are never read; zero them once so the store is clean
+    for (int k = (N * C + C) * RAw + NL * ROw; k < OW; ++k) ob[k] = 0u;
+
     fence_async_smem();
-    __syncthreads();
+    __syncwarp();
     if (lane == 0) {
-        bulk_s2g(p.obs + (size_t)env0 * p.OH, sObs, obBytes);
+        bulk_s2g(reinterpret_cast<uint32_t *>(p.obs) + (size_t)env0 * OW, sm, 32u * (uint32_t)OW * 4u);
         bulk_commit();
-        bulk_wait_all();
+        bulk_wait_read();
     }
 }
 
-// direct variant for domains whose observation tile does not fit in shared memory
+// ---- generic path: any domain, one thread per env, straight to global memory ----------------
 __global__ void observe_kernel_direct(const __grid_constant__ DevParams p)
 {
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
     if (env >= p.Bpad) return;
-    observe_env(p, p.state + (size_t)env * p.W, p.obs + (size_t)env * p.OH);
+    const int N = p.N, C = p.C, NL = p.NL, RAw = NL + 2, ROw = C + 1;
+    const uint32_t *st = p.state + (size_t)env * p.W;
+    const uint32_t *slot = st + p.sSlot;
+    uint32_t *ob = reinterpret_cast<uint32_t *>(p.obs) + (size_t)env * (p.OH >> 1);
+    for (int r = 0; r < N * C + C; ++r) {
+        ob[r * RAw] = 0u;
+        ob[r * RAw + 1] = 0xffffffffu;
+        for (int k = 0; k < NL; ++k) ob[r * RAw + 2 + k] = 0xfffefffeu;
+    }
+    for (int j = 0; j < C; ++j) {
+        const int o = core_owner(st[2 + 3 * j]);
+        const int row = o > 0 ? (o - 1) * C + j : N * C + j;
+        ob[row * RAw] = 0x00010000u;
+        ob[row * RAw + 1] = job_pair(p, st[2 + 3 * j]);
+    }
+    unsigned char cnt[64];
+    for (int j = 0; j < C; ++j) cnt[j] = 0;
+    for (int s = 0; s < NL; ++s) {
+        const uint32_t w3 = slot[4 * s + 3];
+        const int c = (int)(w3 & 0xffu);
+        if (c == 0) continue;
+        const int j = c - 1, r = off_recip(w3);
+        const int row = r > 0 ? (r - 1) * C + j : N * C + j;
+        ob[row * RAw + 2 + cnt[j]++] = pair16(off_price(w3), job_rem(slot[4 * s]));
+    }
+    uint32_t *oo = ob + (N * C + C) * RAw;
+    for (int s = 0; s < NL; ++s) {
+        for (int j = 0; j < C; ++j) oo[s * ROw + j] = job_pair(p, st[2 + 3 * j]);
+        oo[s * ROw + C] = job_pair(p, slot[4 * s]);
+    }
+}
+
+// offer-ID tables: ids [N][C][NL] then auctioneer ids [C][NL] (int16), -2 padding.
+// env.correspondingOfferIDs / auctioneer_correspondingOfferIDs, src/SchedulingEnvironment.py:26-29
+__global__ void ids_kernel(const __grid_constant__ DevParams p, int16_t *__restrict__ ids)
+{
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.B) return;
+    const int N = p.N, C = p.C, NL = p.NL;
+    const uint32_t *slot = p.state + (size_t)env * p.W + p.sSlot;
+    int16_t *o = ids + (size_t)env * (N * C + C) * NL;
+    for (int k = 0; k < (N * C + C) * NL; ++k) o[k] = -2;
+    unsigned char cnt[64];
+    for (int j = 0; j < C; ++j) cnt[j] = 0;
+    int id = 0;
+    for (int s = 0; s < NL; ++s) {
+        const uint32_t w3 = slot[4 * s + 3];
+        const int c = (int)(w3 & 0xffu);
+        if (c == 0) continue;
+        ++id;  // Offer.offerID restarts at 1 every step, src/world.py:324-325
+        const int j = c - 1, r = off_recip(w3);
+        const int row = r > 0 ? (r - 1) * C + j : N * C + j;
+        o[row * NL + cnt[j]++] = (int16_t)id;
+    }
 }
 
 // reference-shaped dump (debug / parity), see msched_export_state in include/msched.h

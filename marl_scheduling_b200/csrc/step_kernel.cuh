@@ -33,17 +33,47 @@ struct Dims {
     }
 };
 
-// Python round(): round-half-even of the float64 product, no FMA contraction (Q7)
-__device__ __forceinline__ int traded_reward(int price, int time, int dt)
+// 1/t and the odd part of t for t in 0..255 (job lengths are 1..255), filled at library load
+__constant__ double c_rcp[256];
+__constant__ unsigned char c_oddpart[256];
+
+// tradedReward = round(offeredReward / necessaryTime * timeMeasure), src/Reward.py:70-71: float64
+// divide, float64 multiply, Python round() = round-half-even (Q7).  Fast path: the exact rational
+// price*dt/time is at least 1/(2*time) away from a rounding boundary unless it is an exact tie, and
+// the float64 evaluation is within 2^-20 of it, so the nearest integer is the answer.  Exact ties
+// are decided like the float64 code does when price/time is exactly representable (tie -> even);
+// everything else takes the literal float64 path.
+__device__ __noinline__ int traded_reward_slow(int price, int time, int dt)
 {
     const double ratio = __ddiv_rn((double)price, (double)time);
     return (int)rint(__dmul_rn(ratio, (double)dt));
 }
+__device__ __forceinline__ int traded_reward(int price, int time, int dt)
+{
+    if ((unsigned)dt < 32768u) {
+        const int num = price * dt;  // |num| < 2^30
+        const int m = __double2int_rn(__dmul_rn((double)num, c_rcp[time]));
+        const int d2 = 2 * (num - m * time);
+        const int ad = d2 < 0 ? -d2 : d2;
+        if (ad < time) return m;
+        if (ad == time && (price % (int)c_oddpart[time]) == 0) {
+            const int lo = d2 > 0 ? m : m - 1;  // exact value is lo + 0.5
+            return (lo & 1) ? lo + 1 : lo;
+        }
+    }
+    return traded_reward_slow(price, time, dt);
+}
+
+// per-lane scratch (shared memory, 3 words per core, record stride odd):
+//   w0 = selected slot (0xff none) | offers seen << 8 | acceptor index (0xff none) << 16 | owner << 24
+//   w1 = best price i16 | best time u8 << 16 | #candidates << 24      (in-kernel auction)
+//   w2 = rank of the selected offer inside the core's offer table
+__host__ __device__ inline int scratch_words(int C) { return make_odd(3 * C); }
 
 template <int TN, int TC, int TL>
 __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restrict__ st,
                                          const int16_t *__restrict__ act, uint32_t *__restrict__ res,
-                                         int env)
+                                         uint32_t *__restrict__ scr, int env)
 {
     const Dims<TN, TC, TL> d(p);
     const int N = d.N, C = d.C, L = d.L, NL = d.NL;
@@ -51,6 +81,7 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
     const bool agg = mode == MSCHED_REWARD_AGGREGATED_FIXED;
     const bool freeM = mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL ||
                        mode == MSCHED_REWARD_DIVIDED_FREE_NONCOMMERCIAL;
+    const bool external = p.auctionMode == MSCHED_AUCTION_EXTERNAL;
     const int round = p.round;
     uint32_t *core = st + 2;
     uint32_t *chl = st + p.sChlen;
@@ -59,172 +90,220 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
     int *resi = reinterpret_cast<int *>(res);
     uint32_t flags = st[1];
 
+    // liability chains of cores whose job completes this step are walked further down: start
+    // pulling their first line out of HBM now (one 128 B line holds 16 entries)
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const uint32_t cw0 = core[3 * j];
+        if (job_kind(cw0) >= 0 && job_rem(cw0) == 1)
+            prefetch_l1(reinterpret_cast<const uint2 *>(p.chain) + ((size_t)env * C + j) * p.chainCap);
+    }
+
+#pragma unroll 4
     for (int k = 0; k < p.RW; ++k) res[k] = 0u;
 
     // ---- range check of every acceptor action (assert in src/world.py:389,404) ----
-    for (int k = 0; k < N * C; ++k) {
-        const int a = act[p.aAcc + k];
-        if (a < 0 || a > NL) flags |= MSCHED_FLAG_ACTION_RANGE;
+    {
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < N * C; ++k) {
+            const int a = act[p.aAcc + k];
+            bad |= (a < 0) | (a > NL);
+        }
+        if (external) {
+#pragma unroll
+            for (int j = 0; j < C; ++j) {
+                const int a = act[p.aAuc + j];
+                bad |= (a < 0) | (a > NL);
+            }
+        }
+        if (bad) flags |= MSCHED_FLAG_ACTION_RANGE;
+    }
+
+    // ---- pass A: per core, who acts on it and with which table index ----
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        const int o = core_owner(core[3 * j]);
+        int k = -1;
+        if (o > 0) k = act[p.aAcc + (o - 1) * C + j];
+        else if (external) k = act[p.aAuc + j];
+        const uint32_t kk = (k >= 0 && k < NL) ? (uint32_t)k : 0xffu;
+        scr[3 * j] = 0xffu | (kk << 16) | ((uint32_t)o << 24);
+        scr[3 * j + 1] = 0x0001ffffu;  // best = -1/1, no candidates
+        scr[3 * j + 2] = 0u;
+    }
+
+    // ---- pass B: one sweep over the pending offers in creation order (agent asc, slot asc):
+    // rank inside the (recipient, core) table -> selection by the acceptor index, or, for idle
+    // cores in in-kernel auction mode, the running arg-max of offeredReward/necessaryTime compared
+    // exactly by cross-multiplication; -1/-2 operands rate -1 (HardcodedModules.calculateRewardRatio)
+#pragma unroll
+    for (int s = 0; s < NL; ++s) {
+        const uint32_t w3 = slot[4 * s + 3];
+        const int c = (int)(w3 & 0xffu);
+        if (c == 0) continue;
+        const int j = c - 1;
+        const int r = off_recip(w3);
+        uint32_t x0 = scr[3 * j];
+        if (r != (int)(x0 >> 24)) continue;  // not addressed to the core's owner: in nobody's table
+        const uint32_t rank = (x0 >> 8) & 0xffu;
+        x0 += 0x100u;
+        if (r > 0 || external) {
+            if (rank == ((x0 >> 16) & 0xffu)) { x0 = (x0 & ~0xffu) | (uint32_t)s; scr[3 * j + 2] = rank; }
+        } else {
+            int pn = off_price(w3), pd = job_rem(slot[4 * s]);
+            if (pn == -1 || pn == -2 || pd == -1 || pd == -2) { pn = -1; pd = 1; }
+            uint32_t x1 = scr[3 * j + 1];
+            const int bn = (int)(int16_t)(x1 & 0xffffu), bd = (int)((x1 >> 16) & 0xffu);
+            const int lhs = pn * bd, rhs = bn * pd;
+            if (lhs > rhs) {
+                x1 = (uint32_t)(pn & 0xffff) | ((uint32_t)pd << 16) | (1u << 24);
+                x0 = (x0 & ~0xffu) | (uint32_t)s;
+                scr[3 * j + 2] = rank;
+            } else if (lhs == rhs) {
+                x1 += 1u << 24;
+            }
+            scr[3 * j + 1] = x1;
+        }
+        scr[3 * j] = x0;
+    }
+
+    // ---- auction epilogue: uniformly random arg-max (random.sample in the reference), and the
+    // auctioneer index per core as Auctioneer.getAuctioneerAction reports it ----
+#pragma unroll
+    for (int j = 0; j < C; ++j) {
+        uint32_t x0 = scr[3 * j];
+        int kUsed = NL;
+        if (external) {
+            kUsed = act[p.aAuc + j];
+        } else if ((x0 >> 24) == 0u && (x0 & 0xffu) != 0xffu) {
+            const uint32_t x1 = scr[3 * j + 1];
+            const int ncand = (int)(x1 >> 24);
+            if (p.auctionMode == MSCHED_AUCTION_RANDOM_MAX && ncand > 1) {
+                uint32_t x[4];
+                env_draw(p, env, kStreamTie, (uint32_t)j, 0u, x);
+                int pick = (int)__umulhi(x[0], (uint32_t)ncand);
+                if (pick > 0) {
+                    const int bn = (int)(int16_t)(x1 & 0xffffu), bd = (int)((x1 >> 16) & 0xffu);
+                    int rank = 0;
+                    for (int s = 0; s < NL; ++s) {
+                        const uint32_t w3 = slot[4 * s + 3];
+                        if ((w3 & 0xffffu) != (uint32_t)(j + 1)) continue;
+                        int pn = off_price(w3), pd = job_rem(slot[4 * s]);
+                        if (pn == -1 || pn == -2 || pd == -1 || pd == -2) { pn = -1; pd = 1; }
+                        if (pn * bd == bn * pd) {
+                            if (pick == 0) {
+                                x0 = (x0 & ~0xffu) | (uint32_t)s;
+                                scr[3 * j] = x0;
+                                scr[3 * j + 2] = (uint32_t)rank;
+                                break;
+                            }
+                            --pick;
+                        }
+                        ++rank;
+                    }
+                }
+            }
+            kUsed = (int)scr[3 * j + 2];
+        }
+        res[p.rAucIdx + (j >> 1)] |= ((uint32_t)(kUsed & 0xffff)) << ((j & 1) * 16);
     }
 
     double qualSum = 0.0;
     int qualCnt = 0, nAcc = 0, nTerm = 0;
 
-    // auctioneer index per core as the reference's Auctioneer.getAuctioneerAction reports it:
-    // reject (NL) for cores it does not own; echo of the input in external mode
-    for (int j = 0; j < C; ++j) {
-        const int k = (p.auctionMode == MSCHED_AUCTION_EXTERNAL) ? (int)act[p.aAuc + j] : NL;
-        res[p.rAucIdx + (j >> 1)] |= ((uint32_t)(k & 0xffff)) << ((j & 1) * 16);
-    }
-
-    // ---- acceptances in reference order: agents ascending (core ascending), then auctioneer ----
-    unsigned long long handled = 0ull;
-    for (int ord = 1; ord <= N + 1; ++ord) {
-        const int who = (ord <= N) ? ord : 0;
-        for (int j = 0; j < C; ++j) {
-            if ((handled >> j) & 1ull) continue;
-            const uint32_t cw0 = core[3 * j];
-            if (core_owner(cw0) != who) continue;
-            handled |= 1ull << j;
-            const uint32_t key = (uint32_t)(j + 1) | ((uint32_t)who << 8);
-            int k;         // index into the (recipient, core) offer table
-            bool haveK = true;
-            if (who > 0) {
-                k = act[p.aAcc + (who - 1) * C + j];
-            } else if (p.auctionMode == MSCHED_AUCTION_EXTERNAL) {
-                k = act[p.aAuc + j];
-                if (k < 0 || k > NL) flags |= MSCHED_FLAG_ACTION_RANGE;
-            } else {
-                // the auction: best offeredReward/necessaryTime among offers to this idle core,
-                // compared exactly by cross-multiplication (ratios of int16 operands are distinct
-                // floats iff distinct rationals); -1/-2 operands rate -1 (calculateRewardRatio)
-                int bn = -1, bd = 1, ncand = 0;
-                for (int s = 0; s < NL; ++s) {
-                    const uint32_t w3 = slot[4 * s + 3];
-                    if ((w3 & 0xffffu) != key) continue;
-                    int pn = off_price(w3), pd = job_rem(slot[4 * s]);
-                    if (pn == -1 || pn == -2 || pd == -1 || pd == -2) { pn = -1; pd = 1; }
-                    const int lhs = pn * bd, rhs = bn * pd;
-                    if (lhs > rhs) { bn = pn; bd = pd; ncand = 1; }
-                    else if (lhs == rhs) ++ncand;
-                }
-                k = NL;  // reject unless max ratio > -1
-                if (bn > -bd) {
-                    int pick = 0;
-                    if (p.auctionMode == MSCHED_AUCTION_RANDOM_MAX && ncand > 1) {
-                        uint32_t x[4];
-                        env_draw(p, env, kStreamTie, (uint32_t)j, 0u, x);
-                        pick = (int)__umulhi(x[0], (uint32_t)ncand);
-                    }
-                    int idx = 0;
-                    for (int s = 0; s < NL; ++s) {
-                        const uint32_t w3 = slot[4 * s + 3];
-                        if ((w3 & 0xffffu) != key) continue;
-                        int pn = off_price(w3), pd = job_rem(slot[4 * s]);
-                        if (pn == -1 || pn == -2 || pd == -1 || pd == -2) { pn = -1; pd = 1; }
-                        if (pn * bd == bn * pd) {
-                            if (pick == 0) { k = idx; break; }
-                            --pick;
-                        }
-                        ++idx;
-                    }
-                }
-            }
-            if (who == 0) {  // record the auctioneer index actually used
-                uint32_t *w = res + p.rAucIdx + (j >> 1);
-                const int sh = (j & 1) * 16;
-                *w = (*w & ~(0xffffu << sh)) | (((uint32_t)(k & 0xffff)) << sh);
-            }
-            if (k < 0 || k >= NL) haveK = false;
-            if (!haveK) continue;
-            // k-th pending offer addressed to (who, core j) in creation order
-            int sel = -1, selA = 0, selQ = 0, cnt = 0;
-            for (int a = 0, s = 0; a < N; ++a)
-                for (int q = 0; q < L; ++q, ++s) {
-                    if ((slot[4 * s + 3] & 0xffffu) != key) continue;
-                    if (cnt == k) { sel = s; selA = a; selQ = q; }
-                    ++cnt;
-                }
-            if (sel < 0) continue;  // table entry was padding (-2)
-
-            // ---- executeAnOffer ----
-            const uint32_t sw0 = slot[4 * sel], sw1 = slot[4 * sel + 1], sw2 = slot[4 * sel + 2];
-            const uint32_t sw3 = slot[4 * sel + 3];
-            const int kind = job_kind(sw0), time = job_rem(sw0), price = off_price(sw3);
-            const int offerer = selA + 1;
-            const int prio1 = p.prio[kind];
-            const uint32_t cw1 = core[3 * j + 1], cw2 = core[3 * j + 2];
-            slot[4 * sel] = kEmptyJobW0; slot[4 * sel + 1] = kEmptyId; slot[4 * sel + 2] = kEmptyId;
-            slot[4 * sel + 3] = 0u;
-            core[3 * j] = pack_core(offerer, kind, time);
-            core[3 * j + 1] = sw1;
-            core[3 * j + 2] = sw2;
-            if (who > 0) {
-                // old job back into the recipient's first empty slot
-                const int base = (who - 1) * L;
-                int q = -1;
-                for (int t = 0; t < L; ++t)
-                    if (job_kind(slot[4 * (base + t)]) < 0) { q = t; break; }
-                if (q >= 0) {
-                    slot[4 * (base + q)] = cw0 & 0xffffff00u;
-                    slot[4 * (base + q) + 1] = cw1;
-                    slot[4 * (base + q) + 2] = cw2;
-                    slot[4 * (base + q) + 3] = 0u;
-                } else {
-                    flags |= MSCHED_FLAG_COLLECTION_FULL;
-                }
-                // acception quality, src/SchedulingEnvironment.py:174-192 (former = core before)
-                double qv = __ddiv_rn((double)price, (double)time);
-                const int fk = job_kind(cw0);
-                if (fk >= 0) qv = __dsub_rn(qv, __ddiv_rn((double)p.prio[fk], (double)job_rem(cw0)));
-                qualSum = __dadd_rn(qualSum, __dmul_rn(qv, 10.0));
-                ++qualCnt;
-            }
-            // liability chain append (stored oldest first)
-            {
-                const uint32_t cw = chl[j >> 2];
-                const int len = (int)((cw >> ((j & 3) * 8)) & 0xffu);
-                if (len < p.chainCap) {
-                    uint32_t *ce = p.chain + (((size_t)env * C + j) * p.chainCap + len) * 2;
-                    ce[0] = (uint32_t)round;
-                    ce[1] = pack_chain(price, time, offerer);
-                    chl[j >> 2] = cw + (1u << ((j & 3) * 8));
-                } else {
-                    flags |= MSCHED_FLAG_CHAIN_OVERFLOW;
-                }
-            }
-            // offer-side rewards
-            if (agg) {
-                resf[p.rOffer + selA] += (float)prio1;
-            } else {
-                resf[p.rOffer + selA * L + selQ] = (float)prio1;
-                if (freeM) {
-                    const int df = prio1 - price;
-                    float pr;
-                    if (mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL)
-                        pr = (df == 0) ? p.netZero : (float)df;
-                    else
-                        pr = (df >= 0) ? (float)prio1 : (float)df;
-                    resf[p.rPrice + selA * L + selQ] = pr;
-                }
-            }
-            ++nAcc;
+    // ---- executeAnOffer in reference order: agents ascending, cores ascending, auctioneer last
+    // (at most one acceptance per core, invariant I2) ----
+    int lastKey = -1;
+    for (int e = 0; e < C; ++e) {
+        int best = 0x7fffffff, j = -1;
+#pragma unroll
+        for (int jj = 0; jj < C; ++jj) {
+            const uint32_t x0 = scr[3 * jj];
+            const int o = (int)(x0 >> 24);
+            const int key = (((o == 0) ? (N + 1) : o) << 8) | jj;
+            if ((x0 & 0xffu) != 0xffu && key > lastKey && key < best) { best = key; j = jj; }
         }
+        if (j < 0) break;
+        lastKey = best;
+        const int sel = (int)(scr[3 * j] & 0xffu);
+        const int who = (int)(scr[3 * j] >> 24);
+        const int selA = sel / L, selQ = sel - selA * L;
+        const uint32_t cw0 = core[3 * j], cw1 = core[3 * j + 1], cw2 = core[3 * j + 2];
+        const uint32_t sw0 = slot[4 * sel], sw1 = slot[4 * sel + 1], sw2 = slot[4 * sel + 2];
+        const uint32_t sw3 = slot[4 * sel + 3];
+        const int kind = job_kind(sw0), time = job_rem(sw0), price = off_price(sw3);
+        const int offerer = selA + 1;
+        const int prio1 = p.prio[kind];
+        slot[4 * sel] = kEmptyJobW0; slot[4 * sel + 1] = kEmptyId; slot[4 * sel + 2] = kEmptyId;
+        slot[4 * sel + 3] = 0u;
+        core[3 * j] = pack_core(offerer, kind, time);
+        core[3 * j + 1] = sw1;
+        core[3 * j + 2] = sw2;
+        if (who > 0) {
+            // old job back into the recipient's first empty slot
+            const int base = (who - 1) * L;
+            int q = -1;
+#pragma unroll
+            for (int t = L - 1; t >= 0; --t)
+                if (job_kind(slot[4 * (base + t)]) < 0) q = t;
+            if (q >= 0) {
+                slot[4 * (base + q)] = cw0 & 0xffffff00u;
+                slot[4 * (base + q) + 1] = cw1;
+                slot[4 * (base + q) + 2] = cw2;
+                slot[4 * (base + q) + 3] = 0u;
+            } else {
+                flags |= MSCHED_FLAG_COLLECTION_FULL;
+            }
+            // acception quality, src/SchedulingEnvironment.py:174-192 (former = core before)
+            double qv = __dmul_rn((double)price, c_rcp[time]);
+            const int fk = job_kind(cw0);
+            if (fk >= 0) qv = __dsub_rn(qv, __dmul_rn((double)p.prio[fk], c_rcp[job_rem(cw0) & 0xff]));
+            qualSum = __dadd_rn(qualSum, __dmul_rn(qv, 10.0));
+            ++qualCnt;
+        }
+        {  // liability chain append (stored oldest first)
+            const uint32_t cw = chl[j >> 2];
+            const int len = (int)((cw >> ((j & 3) * 8)) & 0xffu);
+            if (len < p.chainCap) {
+                uint2 *ce = reinterpret_cast<uint2 *>(p.chain) + ((size_t)env * C + j) * p.chainCap + len;
+                *ce = make_uint2((uint32_t)round, pack_chain(price, time, offerer));
+                chl[j >> 2] = cw + (1u << ((j & 3) * 8));
+            } else {
+                flags |= MSCHED_FLAG_CHAIN_OVERFLOW;
+            }
+        }
+        if (agg) {
+            resf[p.rOffer + selA] += (float)prio1;
+        } else {
+            resf[p.rOffer + sel] = (float)prio1;
+            if (freeM) {
+                const int df = prio1 - price;
+                float pr;
+                if (mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL)
+                    pr = (df == 0) ? p.netZero : (float)df;
+                else
+                    pr = (df >= 0) ? (float)prio1 : (float)df;
+                resf[p.rPrice + sel] = pr;
+            }
+        }
+        (void)selQ;
+        ++nAcc;
     }
 
     // ---- job progress / completion + termination rewards ----
+#pragma unroll
     for (int j = 0; j < C; ++j) {
         const uint32_t cw0 = core[3 * j];
         const int kind = job_kind(cw0);
         if (kind < 0) continue;
         const int rem = job_rem(cw0) - 1;
-        const int owner = core_owner(cw0);
         if (rem != 0) {
-            core[3 * j] = pack_core(owner, kind, rem);
+            core[3 * j] = (cw0 & 0x0000ffffu) | ((uint32_t)rem << 16);
             continue;
         }
         const int R = p.mult * p.prio[kind];
-        const int o = owner - 1;
+        const int o = core_owner(cw0) - 1;
         if (agg) {
             resi[p.rAcc + o] += R;
             resi[p.rAgent + o] += R;
@@ -234,7 +313,7 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
         }
         const uint32_t cw = chl[j >> 2];
         const int len = (int)((cw >> ((j & 3) * 8)) & 0xffu);
-        const uint2 *ce = reinterpret_cast<const uint2 *>(p.chain + ((size_t)env * C + j) * p.chainCap * 2);
+        const uint2 *ce = reinterpret_cast<const uint2 *>(p.chain) + ((size_t)env * C + j) * p.chainCap;
         int recip = 0;  // the oldest entry was accepted by the auctioneer
         for (int e = 0; e < len; ++e) {
             const uint2 en = ce[e];
@@ -264,6 +343,7 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
     }
 
     // ---- offer creation ----
+#pragma unroll
     for (int s = 0; s < NL; ++s) {
         const int a = act[p.aOffc + s];
         const uint32_t w0 = slot[4 * s];
@@ -279,9 +359,14 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
 
     // ---- spawn refill ----
     uint32_t jobctr = st[0];
+    uint32_t rnd[4] = {0u, 0u, 0u, 0u};
+    int rndCall = -1;
+#pragma unroll
     for (int a = 0; a < N; ++a) {
         int owned = 0, nfree = 0;
+#pragma unroll
         for (int j = 0; j < C; ++j) owned += (core_owner(core[3 * j]) == a + 1);
+#pragma unroll
         for (int q = 0; q < L; ++q) nfree += (job_kind(slot[4 * (a * L + q)]) < 0);
         if (owned + p.newJobs > nfree) continue;
         for (int k = 0; k < p.newJobs; ++k) {
@@ -293,18 +378,23 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
                 if (p.spawnMode == MSCHED_SPAWN_U64) {
                     u = p.spawnU[((size_t)env * N + a) * p.newJobs + k];
                 } else {
-                    uint32_t x[4];
-                    env_draw(p, env, kStreamSpawn, (uint32_t)a, (uint32_t)k, x);
-                    u = u53(x);
+                    const int dnum = a * p.newJobs + k;  // draw d uses word d%4 of Philox call d/4
+                    if ((dnum >> 2) != rndCall) {
+                        rndCall = dnum >> 2;
+                        env_draw(p, env, kStreamSpawn, (uint32_t)rndCall, 0u, rnd);
+                    }
+                    const uint32_t xr = (dnum & 3) == 0 ? rnd[0] : (dnum & 3) == 1 ? rnd[1] : (dnum & 3) == 2 ? rnd[2] : rnd[3];
+                    u = (double)xr * (1.0 / 4294967296.0);
                 }
                 for (int q = 0; q < p.J; ++q)
                     if (u < p.cum[q]) { kind = q; break; }
             }
             if (kind < 0 || kind >= p.J) { flags |= MSCHED_FLAG_SPAWN_RANGE; kind = p.J - 1; }
-            int q = -1;
-            for (int t = 0; t < L; ++t)
-                if (job_kind(slot[4 * (a * L + t)]) < 0) { q = t; break; }
-            const int s = a * L + q;  // q >= 0 is guaranteed by the guard above
+            int q = 0;
+#pragma unroll
+            for (int t = L - 1; t >= 0; --t)
+                if (job_kind(slot[4 * (a * L + t)]) < 0) q = t;
+            const int s = a * L + q;  // an empty slot exists by the guard above
             slot[4 * s] = pack_slot(kind, p.len[kind]);
             slot[4 * s + 1] = jobctr++;
             slot[4 * s + 2] = (uint32_t)round;
@@ -318,12 +408,11 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
     const unsigned long long qb = (unsigned long long)__double_as_longlong(qualSum);
     res[p.rQual] = (uint32_t)qb;
     res[p.rQual + 1] = (uint32_t)(qb >> 32);
-    const uint32_t done = (((long long)round + 1) % p.episodeLength) == 0 ? 1u : 0u;
-    res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nAcc << 8) | ((uint32_t)nTerm << 16) | (done << 24);
+    res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nAcc << 8) | ((uint32_t)nTerm << 16) | ((uint32_t)p.doneFlag << 24);
     res[p.rFlags] = flags;
 }
 
-// grid = Bpad / blockDim.x tiles; dynamic smem = blockDim.x * (W*4 + AH*2 + RW*4) bytes
+// grid = Bpad / blockDim.x tiles; dynamic smem = blockDim.x * (W*4 + AH*2 + RW*4 + SCR*4) bytes
 template <int TN, int TC, int TL>
 __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevParams p)
 {
@@ -337,6 +426,8 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevPa
     uint32_t *sState = reinterpret_cast<uint32_t *>(smem);
     int16_t *sAct = reinterpret_cast<int16_t *>(smem + stBytes);
     uint32_t *sRes = reinterpret_cast<uint32_t *>(smem + stBytes + acBytes);
+    const int SCR = scratch_words(p.C);
+    uint32_t *sScr = reinterpret_cast<uint32_t *>(smem + stBytes + acBytes + rsBytes);
 
     if (lane == 0) {
         mbar_init(&bar, 1);
@@ -350,7 +441,7 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevPa
     const int env = env0 + lane;
     if (env < p.B)
         step_env<TN, TC, TL>(p, sState + (size_t)lane * p.W, sAct + (size_t)lane * p.AH,
-                             sRes + (size_t)lane * p.RW, env);
+                             sRes + (size_t)lane * p.RW, sScr + (size_t)lane * SCR, env);
     else
         for (int k = 0; k < p.RW; ++k) sRes[(size_t)lane * p.RW + k] = 0u;
 
@@ -360,7 +451,7 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevPa
         bulk_s2g(p.state + (size_t)env0 * p.W, sState, stBytes);
         bulk_s2g(p.result + (size_t)env0 * p.RW, sRes, rsBytes);
         bulk_commit();
-        bulk_wait_all();
+        bulk_wait_read();
     }
 }
 

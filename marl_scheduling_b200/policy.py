@@ -103,8 +103,8 @@ def smoke_check(env, obs):
     x = obs["acceptor"]  # [B,N,C,Wd] view into the obs record
     B = x.shape[0]
     uu = torch.rand(B * N * Cc, generator=torch.Generator().manual_seed(2))
-    act, lp, pr = actor_forward(grp, x, Wd, N * Cc, B, env_stride=env.layout.obs_halfs, u=uu,
-                                want_probs=True)
+    act, lp, pr = actor_forward(grp, x, env.layout.o_acc_row, N * Cc, B,
+                                env_stride=env.layout.obs_halfs, u=uu, want_probs=True)
     xs = x.cpu().numpy().reshape(B, N * Cc, Wd).astype(np.float32)
     w = grp.weights.cpu().numpy()
     H, A = 16, NL + 1

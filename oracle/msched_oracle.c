@@ -129,11 +129,6 @@ static void draw(const MsorConfig *cfg, int64_t env, uint32_t round, uint32_t st
     philox4x32_10(ctr, key, out);
 }
 
-static double u53(const uint32_t x[4])
-{
-    uint64_t v = ((uint64_t)x[1] << 32) | x[0];
-    return (double)(v >> 11) * (1.0 / 9007199254740992.0);
-}
 
 /* ------------------------------------------------------------------ world objects */
 static Job emptyJob(void) /* Job(0,0,0,True,None,None), src/world.py:83-93 */
@@ -332,9 +327,11 @@ static void fillQueuesWithNewRandomJobs(const MsorConfig *cfg, World *w, int64_t
                     if (spawnU) {
                         u = spawnU[i * cfg->newJobs + k];
                     } else {
+                        /* draw d = agent*newJobs + k uses word d%4 of Philox call d/4 */
+                        const int d = i * cfg->newJobs + k;
                         uint32_t x[4];
-                        draw(cfg, env, (uint32_t)w->round, STREAM_SPAWN, (uint32_t)i, (uint32_t)k, x);
-                        u = u53(x);
+                        draw(cfg, env, (uint32_t)w->round, STREAM_SPAWN, (uint32_t)(d >> 2), 0u, x);
+                        u = (double)x[d & 3] * (1.0 / 4294967296.0);
                     }
                     for (int q = 0; q < cfg->J; ++q)
                         if (u < cfg->cumProb[q]) { kind = q; break; }

@@ -56,7 +56,7 @@ def test_cuda_replays_reference_trace(name):
                 assert r["quality_sum"][b] / r["quality_cnt"][b] == pytest.approx(
                     float(tr["quality"][t]), rel=1e-12, abs=1e-12)
         if t % 7 == 0 or t == T - 1:
-            o = {k: v.cpu().numpy() for k, v in env.observe().items()}
+            o = {k: v.cpu().numpy() for k, v in env.observe(with_ids=True).items()}
             for b in (0, 129):
                 if meta["agent_kind"] != "aggregated":
                     assert np.array_equal(o["acceptor"][b], tr["obs_acc"][t]), (name, t)
@@ -129,7 +129,7 @@ def test_cuda_matches_oracle_random_batch(key, auction):
                     assert np.array_equal(np.asarray(e[k][b]), np.asarray(ob[k])), (key, t, b, k)
                 assert np.array_equal(e["chain"][b], ob["chain"]), (key, t, b, "chain")
                 assert e["job_counter"][b] == ob["job_counter"]
-            o = {k: v.cpu().numpy() for k, v in env.observe().items()}
+            o = {k: v.cpu().numpy() for k, v in env.observe(with_ids=True).items()}
             for b in rng.integers(0, B, 10):
                 oo = orc.observe(int(b))
                 assert np.array_equal(o["acceptor"][b], oo["obs_acc"])
