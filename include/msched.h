@@ -163,6 +163,15 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
  * auctioneer_correspondingOfferIDs (src/SchedulingEnvironment.py:26-29, B*ids_halfs int16) */
 int msched_observe_dense(void *handle, int16_t *obs_dev, int16_t *ids_dev, void *stream);
 
+/* Auctioneer.getAuctioneerAction (src/Auctioneer.py:95-102) = HardcodedAuctioneerAcceptor
+ * .selectAction per core (src/HardcodedModules.py:48-78) on the CURRENT state: the table index of
+ * the best offeredReward/necessaryTime offer to each idle core (N*L = reject, also for cores the
+ * auctioneer does not own).  random_ties != 0 picks uniformly among equal maxima (Philox, same
+ * draw the step kernel would use this round), else the first.  out: int16 [B][C].  The step
+ * kernel runs the same rule in-kernel when auctionMode != EXTERNAL; this entry point exists for
+ * callers that want to see / override the auctioneer's action like the reference scripts do. */
+int msched_auctioneer_action(void *handle, int random_ties, int16_t *out_dev, void *stream);
+
 /* debug / parity: reference-shaped int32 dump of envs [env0, env0+count):
  * core [C][7] owner,prio,rem,jobid,kind,birth,init ; slot [N*L][7] prio,rem,jobid,kind,wait,
  * birth,init ; offer [N*L][5] core(0 none),recipient,price,time,offerID ;
@@ -179,6 +188,10 @@ int msched_export_state(void *handle, int env0, int count, int32_t *core, int32_
  * [W1 h*in | b1 h | W2 h*h | b2 h | W3 A*h | b3 A]. */
 typedef struct MschedMlpGroup {
     int32_t n_in, n_hidden, n_actions, n_nets;
+    int32_t unit_div; /* unit u is served by net (u / unit_div) % n_nets: 1 = one net per unit
+                         (divided) or one net for all (n_nets = 1, globally shared); C or L = one
+                         net per agent (locally shared) */
+    int32_t reserved;
     const float *weights; /* device, n_nets * msched_mlp_param_count() floats */
 } MschedMlpGroup;
 
@@ -186,7 +199,7 @@ int msched_mlp_param_count(int n_in, int n_hidden, int n_actions);
 
 /* x: int16 observations.  Unit u of env b is the row at x + b*env_stride + u*x_stride (int16
  * elements; env_stride 0 means units*x_stride, i.e. a dense [M][x_stride] matrix) and is evaluated
- * by net (u % n_nets).  M = n_envs*units rows, row index r = b*units + u.  seed/step select the
+ * by net (u / unit_div) % n_nets.  M = n_envs*units rows, row index r = b*units + u.  seed/step select the
  * Philox stream (counter = (row_offset + r, step)); u_override float32 [M] replaces the draws
  * (parity tests).  action int32 [M], logprob float32 [M] (either may be NULL); probs float32
  * [M][A] optional (NULL in production). */

@@ -51,7 +51,8 @@ class MschedLayout(C.Structure):
 
 class MschedMlpGroup(C.Structure):
     _fields_ = [("n_in", C.c_int32), ("n_hidden", C.c_int32), ("n_actions", C.c_int32),
-                ("n_nets", C.c_int32), ("weights", C.c_void_p)]
+                ("n_nets", C.c_int32), ("unit_div", C.c_int32), ("reserved", C.c_int32),
+                ("weights", C.c_void_p)]
 
 
 # every symbol include/msched.h declares: name -> (restype, argtypes)
@@ -70,6 +71,7 @@ SYMBOLS = {
     "msched_step": (C.c_int, [P, P, P, P, P]),
     "msched_step_host": (C.c_int, [P, P, P, P]),
     "msched_observe_dense": (C.c_int, [P, P, P, P]),
+    "msched_auctioneer_action": (C.c_int, [P, C.c_int, P, P]),
     "msched_export_state": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, P]),
     "msched_mlp_param_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "msched_actor_forward": (C.c_int, [C.POINTER(MschedMlpGroup), P, C.c_int, C.c_int64, C.c_int,
@@ -123,7 +125,7 @@ def cum_prob(probabilities):
 
 
 def make_config(B, world_params, reward="fix", auction="external", spawn="philox",
-                chain_capacity=32, seed=0, env_offset=0, net_zero_offer_reward=0.5):
+                chain_capacity=64, seed=0, env_offset=0, net_zero_offer_reward=0.5):
     """world_params uses the reference's World(params) keys (src/world.py:211-246)."""
     wp = world_params
     prios = list(wp["possibleJobPriorities"])

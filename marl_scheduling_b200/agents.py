@@ -1,0 +1,233 @@
+"""Batched PPO agents: the reference's per-unit PPO objects (src/PPOmodules.py:75-174, :273-332,
+:335-449, :490-597 and the agents' getActions/saveRewards/updateParts in src/Agent.py:495-619,
+:669-735) with a leading environment dimension.
+
+Rollout (the hot path): actor forward + categorical sample + log-prob run in the CUDA actor kernel
+(msched_actor_forward) straight on the observation record; rewards are routed into device
+buffers; returns use msched_returns.  The PPO update itself (clipped surrogate, 0.5*MSE,
+-0.01*entropy, two-LR Adam, K epochs, policy_old sync) is SURVEY.md section 8(f) row N1 and is
+implemented here with PyTorch autograd over the batched buffers.
+"""
+from __future__ import annotations
+
+import random
+
+import torch
+
+from . import policy as P
+from .distributed import allreduce_gradients
+
+UPDATE_CHUNK = 1 << 20  # samples per autograd chunk (gradient accumulation bounds memory)
+
+
+class BatchedPPO:
+    """n_nets ActorCritic pairs of one shape (src/PPOmodules.py:25-72), parameters stacked.
+
+    unit u of an environment is served by net (u // unit_div) % n_nets."""
+
+    def __init__(self, n_in, n_actions, n_hidden, n_nets, units, unit_div, lr_actor, lr_critic, gamma,
+                 eps_clip, k_epochs, device, seed=0):
+        self.n_in, self.A, self.H = n_in, n_actions, n_hidden
+        self.n_nets, self.units, self.unit_div = n_nets, units, unit_div
+        self.gamma, self.eps_clip, self.K_epochs = gamma, eps_clip, k_epochs
+        self.device = device
+        init = P.MlpGroup.random(n_in, n_hidden, n_actions, n_nets, device, seed=seed)
+        crit = P.MlpGroup.random(n_in, n_hidden, 1, n_nets, device, seed=seed + 7919)
+        self.actor = torch.nn.Parameter(init.weights.clone())      # [n_nets, pc_actor]
+        self.critic = torch.nn.Parameter(crit.weights.clone())     # [n_nets, pc_critic]
+        self.optimizer = torch.optim.Adam([{"params": [self.actor], "lr": lr_actor},
+                                           {"params": [self.critic], "lr": lr_critic}])
+        self.policy_old = P.MlpGroup(n_in, n_hidden, n_actions, self.actor.detach().clone(), device,
+                                     unit_div=unit_div)
+        self.buf_x, self.buf_a, self.buf_lp, self.buf_r = [], [], [], []
+        self.step_no = 0
+
+    # -- rollout ---------------------------------------------------------------------------------
+    def selectAction(self, x, x_stride, env_stride, n_envs, seed):
+        """PPO.selectAction for every (env, unit): x is an int16 view whose rows are the units'
+        observations.  Returns actions int32 [n_envs, units]; stores state/action/logprob."""
+        act, lp, _ = P.actor_forward(self.policy_old, x, x_stride, self.units, n_envs,
+                                     env_stride=env_stride, seed=seed, step=self.step_no)
+        self.step_no += 1
+        # the PPO buffer keeps the observation like buffer.states
+        self.buf_x.append(x.reshape(n_envs, self.units, self.n_in).clone())
+        self.buf_a.append(act.view(n_envs, self.units))
+        self.buf_lp.append(lp.view(n_envs, self.units))
+        return act.view(n_envs, self.units)
+
+    def saveReward(self, r):
+        self.buf_r.append(r.reshape(r.shape[0], self.units).float())
+
+    # -- update (N1) -------------------------------------------------------------------------------
+    def _forward(self, flat, x, A):
+        """flat [n, pc], x [n, M, in] -> [n, M, A] (Linear-Tanh-Linear-Tanh-Linear)."""
+        n, H, nin = flat.shape[0], self.H, self.n_in
+        o = 0
+        W1 = flat[:, o:o + H * nin].view(n, H, nin); o += H * nin
+        b1 = flat[:, o:o + H]; o += H
+        W2 = flat[:, o:o + H * H].view(n, H, H); o += H * H
+        b2 = flat[:, o:o + H]; o += H
+        W3 = flat[:, o:o + A * H].view(n, A, H); o += A * H
+        b3 = flat[:, o:o + A]
+        h = torch.tanh(torch.baddbmm(b1.unsqueeze(1), x, W1.transpose(1, 2)))
+        h = torch.tanh(torch.baddbmm(b2.unsqueeze(1), h, W2.transpose(1, 2)))
+        return torch.baddbmm(b3.unsqueeze(1), h, W3.transpose(1, 2))
+
+    def update(self, unit_subset=None):
+        """PPO.update (src/PPOmodules.py:127-174) for all nets at once.  Returns are normalised per
+        (env, unit) over the buffer like one reference world would; every net then takes K full-
+        batch epochs over the samples of the units it serves (unit_subset restricts them, for the
+        shared-parameter sampling rule)."""
+        T = len(self.buf_r)
+        if T < 2:
+            return
+        B = self.buf_r[0].shape[0]
+        U = self.units
+        r = torch.stack(self.buf_r).reshape(T, B * U)
+        G = P.returns(r, self.gamma, normalise=True).view(T, B, U)
+        X = torch.stack(self.buf_x).float()                       # [T,B,U,in]
+        Aold = torch.stack(self.buf_a).long()
+        LPold = torch.stack(self.buf_lp)
+        units = list(range(U)) if unit_subset is None else list(unit_subset)
+        nets = sorted({(u // self.unit_div) % self.n_nets for u in units})
+        per_net = {n: [u for u in units if (u // self.unit_div) % self.n_nets == n] for n in nets}
+        m = max(len(v) for v in per_net.values())
+        if any(len(v) != m for v in per_net.values()):
+            raise ValueError("unit subset must give every net the same number of units")
+        idx = torch.tensor([per_net[n] for n in nets], device=self.device)      # [n, m]
+        def gather(t):  # [T,B,U,...] -> [n, T*B*m, ...]
+            g = t[:, :, idx]                                          # [T,B,n,m,...]
+            g = g.permute(2, 0, 1, 3, *range(4, g.dim())).contiguous()
+            return g.view(len(nets), T * B * m, *g.shape[4:])
+        Xn, An, LPn, Gn = gather(X), gather(Aold), gather(LPold), gather(G)
+        M = Xn.shape[1]
+        sel = torch.tensor(nets, device=self.device)
+        for _ in range(self.K_epochs):
+            self.optimizer.zero_grad()
+            # MSELoss is a mean over the whole batch of a net: first pass for the values
+            with torch.no_grad():
+                mse = torch.zeros(len(nets), device=self.device)
+                for c0 in range(0, M, UPDATE_CHUNK):
+                    v = self._forward(self.critic[sel], Xn[:, c0:c0 + UPDATE_CHUNK], 1).squeeze(-1)
+                    mse += ((v - Gn[:, c0:c0 + UPDATE_CHUNK]) ** 2).sum(1)
+                mse /= M
+            for c0 in range(0, M, UPDATE_CHUNK):
+                xs = Xn[:, c0:c0 + UPDATE_CHUNK]
+                logits = self._forward(self.actor[sel], xs, self.A)
+                logp_all = torch.log_softmax(logits, -1)
+                logp = logp_all.gather(-1, An[:, c0:c0 + UPDATE_CHUNK].unsqueeze(-1)).squeeze(-1)
+                ent = -(logp_all.exp() * logp_all).sum(-1)
+                v = self._forward(self.critic[sel], xs, 1).squeeze(-1)
+                g = Gn[:, c0:c0 + UPDATE_CHUNK]
+                ratios = torch.exp(logp - LPn[:, c0:c0 + UPDATE_CHUNK])
+                adv = g - v.detach()
+                surr = torch.min(ratios * adv, torch.clamp(ratios, 1 - self.eps_clip, 1 + self.eps_clip) * adv)
+                # d/dtheta of mean(-surr + 0.5*MSE - 0.01*H): the MSE term is a batch mean added
+                # to every element, so its gradient is that of 0.5*mean((v-g)^2)
+                loss = (-surr - 0.01 * ent).sum(1) / M + 0.5 * ((v - g) ** 2).sum(1) / M
+                loss.sum().backward()
+            # data-parallel env shards: one flat-bucket all-reduce per epoch (NCCL over NVLink)
+            allreduce_gradients([self.actor, self.critic])
+            self.optimizer.step()
+        return float(mse.mean())
+
+    def sync_old_and_clear(self):
+        self.policy_old.weights.copy_(self.actor.detach())
+        self.buf_x, self.buf_a, self.buf_lp, self.buf_r = [], [], [], []
+
+
+class DividedFixedPricePPOAgents:
+    """All N agents of src/Agent.py:495-536 (divided), :539-576 (globally shared) or :669-735
+    (locally shared) at once: N*C acceptor units and N*L offer units."""
+
+    def __init__(self, world, env, sharing=None):
+        self.world, self.env, self.sharing = world, env, sharing
+        N, C, L = world.numberOfAgents, world.numberOfCores, world.collectionLength
+        NL = N * L
+        dev = env.core.device
+        if sharing == "global":
+            na, no, da, do = 1, 1, 1, 1
+        elif sharing == "local":
+            na, no, da, do = N, N, C, L
+        else:
+            na, no, da, do = N * C, N * L, 1, 1
+        self.acceptor = BatchedPPO(3 + 2 * NL, NL + 1, 16, na, N * C, da, env.LR_ACTOR, env.LR_CRITIC,
+                                   env.ACCEPTOR_GAMMA, env.EPS_CLIP, env.ACCEPTOR_K_EPOCHS, dev, seed=1)
+        self.offer = BatchedPPO(2 * C + 2, C + 1, 16, no, N * L, do, env.LR_ACTOR, env.LR_CRITIC,
+                                env.OFFER_GAMMA, env.EPS_CLIP, env.OFFER_K_EPOCHS, dev, seed=2)
+        self.CENTRALISATION_SAMPLE = env.CENTRALISATION_SAMPLE
+
+    def getActions(self, offerObs, acceptorObs):
+        c, lay = self.env.core, self.env.core.layout
+        B, N, C, L = c.B, c.N, c.C, c.Lc
+        seed = self.world.seed
+        off = self.offer.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 2 + 1)
+        acc = self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 2)
+        # SchedulingEnv.getActionForAllAgents returns (acceptorActions, offerActions)
+        return acc.view(B, N, C), off.view(B, N, L)
+
+    def saveRewards(self, offerRewards, acceptorRewards, agentReward):
+        self.offer.saveReward(offerRewards)
+        self.acceptor.saveReward(acceptorRewards)
+
+    def updateParts(self):
+        for ppo, sub in ((self.acceptor, self.world.numberOfCores), (self.offer, self.world.collectionLength)):
+            if self.sharing is None:
+                ppo.update()
+            elif self.sharing == "global":   # src/SchedulingEnvironment.py:314-329
+                for _ in range(self.CENTRALISATION_SAMPLE):
+                    ppo.update([random.randint(0, ppo.units - 1)])
+            else:                            # src/Agent.py:708-728
+                N = self.world.numberOfAgents
+                for _ in range(self.CENTRALISATION_SAMPLE):
+                    j = random.randint(0, sub - 1)
+                    ppo.update([a * sub + j for a in range(N)])
+            ppo.sync_old_and_clear()
+
+
+class DividedFreePricePPOAgents:
+    """src/Agent.py:579-619 + FreePriceOfferPPO (src/PPOmodules.py:273-332): acceptor units as
+    above; every offer unit is a core chooser followed by a price chooser whose input is
+    [core prio, core rem, slot prio, slot rem] of the chosen core (quirk Q1: action 0 means "no
+    offer" to the chooser, a dummy [-5]*4 input is pushed through the price net and price -5 is
+    reported, while the world still maps action 0 to core 1)."""
+
+    def __init__(self, world, env):
+        self.world, self.env = world, env
+        N, C, L = world.numberOfAgents, world.numberOfCores, world.collectionLength
+        NL = N * L
+        dev = env.core.device
+        a = dict(lr_actor=env.LR_ACTOR, lr_critic=env.LR_CRITIC, eps_clip=env.EPS_CLIP, device=dev)
+        self.acceptor = BatchedPPO(3 + 2 * NL, NL + 1, 16, N * C, N * C, 1, gamma=env.ACCEPTOR_GAMMA,
+                                   k_epochs=env.ACCEPTOR_K_EPOCHS, seed=1, **a)
+        self.core = BatchedPPO(2 * C + 2, C + 1, 16, NL, NL, 1, gamma=env.OFFER_GAMMA,
+                               k_epochs=env.RAW_K_EPOCHS, seed=2, **a)
+        self.price = BatchedPPO(4, world.maxSumToOffer + 1, 16, NL, NL, 1, gamma=env.OFFER_GAMMA,
+                                k_epochs=env.RAW_K_EPOCHS, seed=3, **a)
+
+    def getActions(self, offerObs, acceptorObs):
+        c, lay = self.env.core, self.env.core.layout
+        B, N, C, L = c.B, c.N, c.C, c.Lc
+        seed = self.world.seed
+        core = self.core.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 3 + 1).view(B, N, L)
+        a = core.long().clamp(max=C)            # for a == C the slice [2C:2C+2] is the slot pair
+        idx = torch.stack([2 * a, 2 * a + 1], -1)
+        chosen = torch.gather(offerObs, 3, idx)                      # [B,N,L,2]
+        own = offerObs[..., 2 * C: 2 * C + 2]
+        xin = torch.cat([chosen, own], -1)
+        xin = torch.where((core == 0)[..., None], torch.full_like(xin, -5), xin).contiguous()
+        price = self.price.selectAction(xin.view(B * N * L, 4), 4, 0, B, seed * 3 + 2).view(B, N, L)
+        price = torch.where(core == 0, torch.full_like(price, -5), price)
+        acc = self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 3)
+        return acc.view(B, N, C), (core, price)
+
+    def saveRewards(self, offerRewards, acceptorRewards, agentReward):
+        coreChooser, priceChooser = offerRewards
+        self.core.saveReward(coreChooser)
+        self.price.saveReward(priceChooser)
+        self.acceptor.saveReward(acceptorRewards)
+
+    def updateParts(self):
+        for ppo in (self.acceptor, self.core, self.price):
+            ppo.update()
+            ppo.sync_old_and_clear()

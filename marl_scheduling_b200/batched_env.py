@@ -29,7 +29,7 @@ def world_params_from_dom(dom, free):
 
 class BatchedSchedulingEnv:
     def __init__(self, B, world_params, reward="fix", auction="external", spawn="philox",
-                 chain_capacity=32, seed=0, env_offset=0, net_zero_offer_reward=0.5, device=0):
+                 chain_capacity=64, seed=0, env_offset=0, net_zero_offer_reward=0.5, device=0):
         if not torch.cuda.is_available():
             raise L.MschedError("no CUDA device: marl_scheduling_b200 has no CPU fallback")
         self.lib = L.lib()
@@ -200,6 +200,14 @@ class BatchedSchedulingEnv:
         if with_ids:
             out["ids"] = ids[:, : N * Cc * NL].view(B, N, Cc, NL)
             out["auctioneer_ids"] = ids[:, N * Cc * NL:].view(B, Cc, NL)
+        return out
+
+    def auctioneer_action(self, random_ties=True):
+        """Auctioneer.getAuctioneerAction (reference src/Auctioneer.py:95-102) on the current
+        state: int16 [B,C] table indices (N*L = reject)."""
+        out = torch.empty((self.B, self.C), dtype=torch.int16, device=self.device)
+        L.check(self.lib.msched_auctioneer_action(self.handle, int(random_ties), out.data_ptr(),
+                                                  self._stream()))
         return out
 
     # ------------------------------------------------------------------ debug / parity

@@ -359,6 +359,18 @@ int msched_observe_dense(void *handle, int16_t *obs_dev, int16_t *ids_dev, void 
     return MSCHED_OK;
 }
 
+int msched_auctioneer_action(void *handle, int random_ties, int16_t *out_dev, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !out_dev) return fail(MSCHED_E_ARG, "null handle/out");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    DevParams p = h->p;
+    p.round = (int)h->round;
+    auctioneer_kernel<<<(p.B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p, random_ties, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
 int msched_export_state(void *handle, int env0, int count, int32_t *core, int32_t *slot, int32_t *offer,
                         int32_t *chain, int32_t *chain_len, int32_t *misc, void *stream)
 {

@@ -168,6 +168,54 @@ __global__ void ids_kernel(const __grid_constant__ DevParams p, int16_t *__restr
     }
 }
 
+// Auctioneer.getAuctioneerAction on the current state (src/Auctioneer.py:95-102,
+// src/HardcodedModules.py:48-78); same rule and same tie draw as the step kernel's in-kernel auction
+__global__ void auctioneer_kernel(const __grid_constant__ DevParams p, int randomTies, int16_t *__restrict__ out)
+{
+    const int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= p.B) return;
+    const int C = p.C, NL = p.NL;
+    const uint32_t *st = p.state + (size_t)env * p.W;
+    const uint32_t *slot = st + p.sSlot;
+    for (int j = 0; j < C; ++j) {
+        int k = NL;
+        if (core_owner(st[2 + 3 * j]) == 0) {
+            int bn = -1, bd = 1, ncand = 0, first = -1, rank = 0;
+            for (int s = 0; s < NL; ++s) {
+                const uint32_t w3 = slot[4 * s + 3];
+                if ((w3 & 0xffffu) != (uint32_t)(j + 1)) continue;
+                int pn = off_price(w3), pd = job_rem(slot[4 * s]);
+                if (pn == -1 || pn == -2 || pd == -1 || pd == -2) { pn = -1; pd = 1; }
+                const int lhs = pn * bd, rhs = bn * pd;
+                if (lhs > rhs) { bn = pn; bd = pd; ncand = 1; first = rank; }
+                else if (lhs == rhs) ++ncand;
+                ++rank;
+            }
+            if (first >= 0) {
+                k = first;
+                if (randomTies && ncand > 1) {
+                    uint32_t x[4];
+                    env_draw(p, env, kStreamTie, (uint32_t)j, 0u, x);
+                    int pick = (int)__umulhi(x[0], (uint32_t)ncand);
+                    rank = 0;
+                    for (int s = 0; s < NL && pick >= 0; ++s) {
+                        const uint32_t w3 = slot[4 * s + 3];
+                        if ((w3 & 0xffffu) != (uint32_t)(j + 1)) continue;
+                        int pn = off_price(w3), pd = job_rem(slot[4 * s]);
+                        if (pn == -1 || pn == -2 || pd == -1 || pd == -2) { pn = -1; pd = 1; }
+                        if (pn * bd == bn * pd) {
+                            if (pick == 0) k = rank;
+                            --pick;
+                        }
+                        ++rank;
+                    }
+                }
+            }
+        }
+        out[(size_t)env * C + j] = (int16_t)k;
+    }
+}
+
 // reference-shaped dump (debug / parity), see msched_export_state in include/msched.h
 struct ExportArgs {
     int env0, count;

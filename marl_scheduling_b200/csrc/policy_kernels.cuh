@@ -50,7 +50,7 @@ struct ActorArgs {
     const float *weights;  // n_nets * param_count floats, torch layout per net
     const int16_t *x;
     long long envStride, unitStride;  // in int16 elements
-    int nIn, nHidden, nActions, nNets, units, nEnvs;
+    int nIn, nHidden, nActions, nNets, unitDiv, units, nEnvs;
     unsigned long long seed, step;
     long long rowOffset;
     const float *uOverride;  // [M] or null
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
     extern __shared__ __align__(16) float sw[];
     const int nIn = a.nIn, A = a.nActions;
     const int unit = blockIdx.y;
-    const int net = unit % a.nNets;
+    const int net = (unit / a.unitDiv) % a.nNets;
     const int pc = H * nIn + H + H * H + H + A * H + A;
     const float *w = a.weights + (size_t)net * pc;
     // smem layout: W1t [nIn][H] | b1 [H] | W2t [H][H] | b2 [H] | W3t [H][Apad] | b3 [Apad]
@@ -203,6 +203,7 @@ inline int launch_actor_forward(const MschedMlpGroup &g, const int16_t *x, int x
     a.weights = g.weights; a.x = x;
     a.envStride = env_stride ? env_stride : (long long)x_stride * units; a.unitStride = x_stride;
     a.nIn = g.n_in; a.nHidden = g.n_hidden; a.nActions = g.n_actions; a.nNets = g.n_nets;
+    a.unitDiv = g.unit_div > 0 ? g.unit_div : 1;
     a.units = units; a.nEnvs = M / units;
     a.seed = seed; a.step = step; a.rowOffset = row_offset; a.uOverride = u_override;
     a.action = action; a.logprob = logprob; a.probs = probs;

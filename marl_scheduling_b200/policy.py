@@ -27,14 +27,15 @@ def pack_actor(state_dict, prefix="actor."):
 class MlpGroup:
     """n_nets identically shaped actor MLPs with their weights resident on the device."""
 
-    def __init__(self, n_in, n_hidden, n_actions, weights, device):
+    def __init__(self, n_in, n_hidden, n_actions, weights, device, unit_div=1):
         self.n_in, self.n_hidden, self.n_actions = n_in, n_hidden, n_actions
         w = torch.as_tensor(weights, dtype=torch.float32)
         pc = param_count(n_in, n_hidden, n_actions)
         w = w.reshape(-1, pc)
         self.n_nets = w.shape[0]
         self.weights = w.to(device).contiguous()
-        self.desc = L.MschedMlpGroup(n_in, n_hidden, n_actions, self.n_nets,
+        self.unit_div = unit_div
+        self.desc = L.MschedMlpGroup(n_in, n_hidden, n_actions, self.n_nets, unit_div, 0,
                                      self.weights.data_ptr())
 
     @classmethod

@@ -1,0 +1,143 @@
+"""GPU: the drop-in classes (World / SchedulingEnv / Auctioneer / PPO envs) keep the reference's
+call shapes and agree with the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+WP = dict(freePrices=False, fixPricesList=[2, 7], numberOfAgents=4, numberOfCores=4, collectionLength=3,
+          possibleJobPriorities=[3, 10], possibleJobLengths=[6, 3], probabilities=[0.8, 0.2],
+          newJobsPerRoundPerAgent=1, rewardMultiplier=1, episodeLength=10, maxVisibleOffers=4)
+RL = dict(netZeroOfferReward=0.5, LR_ACTOR=0.003, LR_CRITIC=0.01, OFFER_GAMMA=0.5, ACCEPTOR_GAMMA=0.8733,
+          EPS_CLIP=0.2, RAW_K_EPOCHS=2, ACCEPTOR_K_EPOCHS=2, OFFER_K_EPOCHS=2, CENTRALISATION_SAMPLE=2)
+DOM = dict(N=4, C=4, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7], episodeLength=10)
+
+
+def test_hardcoded_env_loop_matches_oracle():
+    """trainHC-shaped loop: auctioneer action from world.auctioneer, 9-tuple from env.step."""
+    import torch
+    from marl_scheduling_b200.SchedulingEnvironment import HardcodedFixPriceEnvironment
+    from marl_scheduling_b200.world import World
+    from oracle import oracle as O
+    B = 300
+    world = World(dict(WP, numberOfEnvironments=B, seed=5, chainCapacity=32))
+    env = HardcodedFixPriceEnvironment(world, dict(netZeroOfferReward=0.5))
+    orc = O.Oracle(B, DOM, "fix", tie_mode=O.TIE_PHILOX, seed=5)
+    accO, offO, aucO = env.reset()
+    assert accO.shape == (B, 4, 4, 27) and offO.shape == (B, 4, 3, 10) and aucO.shape == (B, 4, 27)
+    rng = np.random.default_rng(0)
+    for t in range(25):
+        offc = rng.integers(0, 5, (B, 4, 3))
+        acc = rng.integers(0, 3, (B, 4, 4))
+        aa = world.auctioneer.getAuctioneerAction(aucO)
+        out = env.step(torch.as_tensor(offc), torch.as_tensor(acc), aa)
+        assert len(out) == 9
+        accO, offO, aucO, offR, accR, aucR, agR, (qm, qn), done = out
+        orc.step(offc, acc, None)
+        assert np.array_equal(aa.cpu().numpy(), orc.auc_out), t
+        assert offR.shape == (B, 4, 3, 1) and accR.shape == (B, 4, 4, 1)
+        assert np.array_equal(offR[..., 0].cpu().numpy().astype(np.float64), orc.r_offer)
+        assert np.array_equal(accR[..., 0].cpu().numpy(), orc.r_acceptor)
+        assert np.array_equal(aucR.cpu().numpy(), orc.r_auctioneer)
+        assert np.array_equal(agR.cpu().numpy(), orc.r_agent)
+        assert done == bool(orc.done[0]) == ((t + 1) % 10 == 0)
+        assert world.round == t + 1
+        o = orc.observe(7)
+        assert np.array_equal(accO[7].cpu().numpy(), o["obs_acc"])
+        assert np.array_equal(aucO[7].cpu().numpy(), o["obs_auc"])
+        qn_ = qn.cpu().numpy()
+        assert np.array_equal(qn_, orc.quality_cnt)
+        assert np.isnan(qm.cpu().numpy()[qn_ == 0]).all()
+    env.close()
+
+
+@pytest.mark.parametrize("cls", ["divided", "global", "local"])
+def test_ppo_fixed_price_env_rollout_and_update(cls):
+    import torch
+    from marl_scheduling_b200 import SchedulingEnvironment as SE
+    from marl_scheduling_b200.world import World
+    B = 64
+    world = World(dict(WP, numberOfEnvironments=B, seed=1))
+    env = {"divided": SE.PPODividedFixedPriceEnv, "global": SE.GloballySharedParamsDividedFixedPriceEnv,
+           "local": SE.LocallySharedParamsDividedFixedPriceEnv}[cls](world, RL)
+    accO, offO, aucO = env.reset()
+    for t in range(12):
+        acceptorActions, offerActions = env.getActionForAllAgents(accO, offO)
+        assert acceptorActions.shape == (B, 4, 4) and offerActions.shape == (B, 4, 3)
+        assert int(acceptorActions.max()) <= 12 and int(offerActions.max()) <= 4
+        aa = world.auctioneer.getAuctioneerAction(aucO)
+        accO, offO, aucO, offR, accR, aucR, agR, q, done = env.step(offerActions, acceptorActions, aa)
+        env.saveRewards(offR, accR, agR)
+    ag = env.agents
+    # log-probs stored by the CUDA actor kernel == torch forward of policy_old on the stored obs
+    ppo = ag.acceptor
+    X = torch.stack(ppo.buf_x).float()
+    T = X.shape[0]
+    nets = torch.tensor([(u // ppo.unit_div) % ppo.n_nets for u in range(ppo.units)], device=X.device)
+    flat = ppo.policy_old.weights[nets]
+    logits = ppo._forward(flat, X.permute(2, 0, 1, 3).reshape(ppo.units, T * B, -1), ppo.A)
+    lp = torch.log_softmax(logits, -1).gather(-1, torch.stack(ppo.buf_a).long().permute(2, 0, 1).reshape(
+        ppo.units, T * B, 1)).squeeze(-1)
+    lp_k = torch.stack(ppo.buf_lp).permute(2, 0, 1).reshape(ppo.units, T * B)
+    assert torch.allclose(lp, lp_k, rtol=1e-4, atol=1e-4)
+    before = ppo.actor.detach().clone()
+    env.updateAgents()
+    assert not torch.equal(before, ppo.actor.detach())
+    assert torch.equal(ppo.policy_old.weights, ppo.actor.detach())
+    assert ppo.buf_r == [] and torch.isfinite(ppo.actor).all()
+    env.close()
+
+
+def test_ppo_free_price_env_rollout_and_update():
+    import torch
+    from marl_scheduling_b200 import SchedulingEnvironment as SE
+    from marl_scheduling_b200.world import World
+    B = 48
+    wp = dict(WP, freePrices=True, numberOfAgents=2, numberOfCores=3, collectionLength=3,
+              possibleJobPriorities=[2, 4, 8], possibleJobLengths=[5, 5, 5], probabilities=[1 / 3] * 3,
+              numberOfEnvironments=B)
+    world = World(wp)
+    env = SE.PPODividedFreePriceEnv(world, RL, True)
+    accO, offO, aucO = env.reset()
+    for t in range(8):
+        acceptorActions, offerActions = env.getActionForAllAgents(accO, offO)
+        core, price = offerActions
+        assert core.shape == (B, 2, 3) and price.shape == (B, 2, 3)
+        assert bool(((price == -5) == (core == 0)).all())  # quirk Q1
+        assert int(price.max()) <= 8
+        accO, offO, aucO, offR, accR, aucR, agR, q, done = env.step(offerActions, acceptorActions, None)
+        assert isinstance(offR, tuple) and offR[0].shape == (B, 2, 3, 1) and offR[1].shape == (B, 2, 3, 1)
+        env.saveRewards(offR, accR, agR)
+    env.updateAgents()
+    assert torch.isfinite(env.agents.price.actor).all()
+    env.close()
+
+
+def test_aggregated_env_views_match_oracle():
+    import torch
+    from marl_scheduling_b200 import SchedulingEnvironment as SE
+    from marl_scheduling_b200.world import World
+    from oracle import oracle as O
+    B = 40
+    dom = dict(N=2, C=2, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7])
+    wp = dict(WP, numberOfAgents=2, numberOfCores=2, numberOfEnvironments=B, seed=3)
+    world = World(wp)
+    env = SE.PPOFullyAggregatedFixPriceEnv(world, RL)
+    orc = O.Oracle(B, dom, "agg", tie_mode=O.TIE_PHILOX, seed=3)
+    rng = np.random.default_rng(1)
+    for t in range(15):
+        offc, acc = rng.integers(0, 3, (B, 2, 3)), rng.integers(0, 3, (B, 2, 2))
+        out = env.step(torch.as_tensor(offc), torch.as_tensor(acc), None)
+        orc.step(offc, acc, None)
+        assert out[3].shape == (B, 2, 1) and out[4].shape == (B, 2, 1)
+        assert np.array_equal(out[4][..., 0].cpu().numpy(), orc.r_acceptor[..., 0])
+        assert np.array_equal(out[3][..., 0].cpu().numpy().astype(np.float64), orc.r_offer[..., 0])
+    accA, offA = env.aggregatedObservations()
+    full = env.fullyAggregatedObservations()
+    o = orc.observe(5)
+    assert np.array_equal(accA[5].cpu().numpy(), o["obs_acc"].reshape(2, -1).astype(np.float32))
+    cores = o["obs_off"][:, 0, :4]
+    slots = o["obs_off"][:, :, 4:].reshape(2, 6)
+    assert np.array_equal(offA[5].cpu().numpy(), np.concatenate([cores, slots], 1))
+    assert full.shape == (B, 2, 10 + 2 * 15)
+    env.close()
