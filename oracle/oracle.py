@@ -68,7 +68,7 @@ def cum_prob(probabilities):
     return [sum(probabilities[: i + 1]) for i in range(len(probabilities))]
 
 
-def make_config(B, dom, mode, chain_cap=32, tie_mode=TIE_FIRST, seed=0, env_offset=0):
+def make_config(B, dom, mode, chain_cap=64, tie_mode=TIE_FIRST, seed=0, env_offset=0):
     cfg = MsorConfig()
     J = len(dom["prios"])
     cfg.B, cfg.N, cfg.C, cfg.L, cfg.J = B, dom["N"], dom["C"], dom["L"], J
@@ -100,7 +100,7 @@ def _p(a):
 class Oracle:
     """B independent reference worlds advanced in lock-step on the CPU."""
 
-    def __init__(self, B, dom, mode, chain_cap=32, tie_mode=TIE_FIRST, seed=0, env_offset=0):
+    def __init__(self, B, dom, mode, chain_cap=64, tie_mode=TIE_FIRST, seed=0, env_offset=0):
         self.cfg = make_config(B, dom, mode, chain_cap, tie_mode, seed, env_offset)
         self.B, self.N, self.C, self.L = B, dom["N"], dom["C"], dom["L"]
         self.NL = self.N * self.L
