@@ -44,6 +44,11 @@ CONFIGS = {
                           mult=1, newJobs=1, episodeLength=100),
                  mode="fix", envs=65536,
                  desc="N4 C4 L3 (cfg2 domain) at 65,536 envs per GPU"),
+    # BASELINE.json configs[4]: large domain, cooperative kernel (one warp per env), no dense obs
+    "cfg5": dict(dom=dict(N=32, C=64, L=8, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7],
+                          mult=1, newJobs=1, episodeLength=100),
+                 mode="fix", envs=262144, obs="none", ring=2,
+                 desc="N32 C64 L8, 2 job kinds, fixed prices, 262,144 envs, compact observations (state record)"),
 }
 
 
@@ -141,24 +146,27 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def make_actions(torch, env, ring, seed):
-    """Uniform random action records: acceptor idx ~ U{0..NL}, offer core ~ U{0..C},
-    price ~ U{0..maxPrio}; a ring of distinct records so consecutive steps differ."""
+def refresh_actions(env, rec, gen):
+    """Uniform random action record: acceptor idx ~ U{0..NL}, offer core ~ U{0..C},
+    price ~ U{0..maxPrio}.  Fresh draws every step: a short periodic ring of records lets some
+    environments fall into resonant cycles whose liability chains grow without bound."""
     lay, B = env.layout, env.B
-    g = torch.Generator(device=env.device).manual_seed(seed)
-    recs = []
     P = max(env.cfg.prio[k] for k in range(env.cfg.J))
+    rec[:B, lay.a_acceptor: lay.a_acceptor + env.N * env.C].random_(0, env.NL + 1, generator=gen)
+    rec[:B, lay.a_offer_core: lay.a_offer_core + env.NL].random_(0, env.C + 1, generator=gen)
+    if lay.a_offer_price >= 0:
+        rec[:B, lay.a_offer_price: lay.a_offer_price + env.NL].random_(0, P + 1, generator=gen)
+
+
+def make_actions(torch, env, ring, seed):
+    gen = torch.Generator(device=env.device).manual_seed(seed)
+    recs = []
     for _ in range(ring):
-        rec = torch.zeros((lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=env.device)
-        rec[:B, lay.a_acceptor: lay.a_acceptor + env.N * env.C] = torch.randint(
-            0, env.NL + 1, (B, env.N * env.C), generator=g, device=env.device, dtype=torch.int16)
-        rec[:B, lay.a_offer_core: lay.a_offer_core + env.NL] = torch.randint(
-            0, env.C + 1, (B, env.NL), generator=g, device=env.device, dtype=torch.int16)
-        if lay.a_offer_price >= 0:
-            rec[:B, lay.a_offer_price: lay.a_offer_price + env.NL] = torch.randint(
-                0, P + 1, (B, env.NL), generator=g, device=env.device, dtype=torch.int16)
+        rec = torch.zeros((env.layout.padded_envs, env.layout.action_halfs), dtype=torch.int16,
+                          device=env.device)
+        refresh_actions(env, rec, gen)
         recs.append(rec)
-    return recs
+    return recs, gen
 
 
 def cpu_baseline_sample(cfg, seconds=12.0, threads=1, envs=2048):
@@ -275,12 +283,15 @@ def main():
                                auction="random", spawn="philox", seed=0, env_offset=rank * B,
                                net_zero_offer_reward=dom.get("netZero", 0.5), device=local)
     lay = env.layout
-    ring = make_actions(torch, env, 8, seed=1 + rank)
+    ring, gen = make_actions(torch, env, cfg.get("ring", 8), seed=1 + rank)
     results = [torch.zeros_like(env.result) for _ in range(2)]
     flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    if cfg.get("obs") == "none":
+        args.obs = "none"
     dense = args.obs == "dense"
 
     def one_step(i):
+        refresh_actions(env, ring[i % len(ring)], gen)
         env.step_records(ring[i % len(ring)], results[i & 1])
         if dense:
             env.observe()
@@ -303,6 +314,7 @@ def main():
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
     for i in range(K):
+        refresh_actions(env, ring[i % len(ring)], gen)
         if flush is not None:
             flush.fill_(i & 0xFF)
         ev[i][0].record()
@@ -329,16 +341,19 @@ def main():
     e2e = None
     nE = min(args.e2e_steps, K) if K > 0 else 0
     if nE > 0:
-        ah = [r[:B].cpu().pin_memory() for r in ring[:4]]
+        ah = []
+        for _ in range(16):
+            refresh_actions(env, ring[0], gen)
+            ah.append(ring[0][:B].cpu().pin_memory())
         rh = torch.zeros((B, lay.result_words), dtype=torch.int32).pin_memory()
         for i in range(5):
-            env.step_host(ah[i % 4], rh)
+            env.step_host(ah[i % 16], rh)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(nE):
-            env.step_host(ah[i % 4], rh)
+            env.step_host(ah[i % 16], rh)
             if dense:
                 env.observe()  # observations stay on the device for the policy kernels
         torch.cuda.synchronize()
@@ -371,7 +386,7 @@ def main():
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": args.config, "domain": cfg["desc"], "envs_per_gpu": B,
                    "observations": args.obs, "auctioneer": "in-kernel, random arg-max (Philox)",
-                   "spawn": "device Philox", "actions": "uniform random, ring of 8 records",
+                   "spawn": "device Philox", "actions": "uniform random, fresh draws every step (untimed)",
                    "l2": "warm (no flush)" if args.no_flush else "flushed before every timed step (256 MiB write)",
                    "state_warm_steps": args.state_warm, "step_tile": os.environ.get("MSCHED_STEP_TILE", "auto")},
         "clocks": clocks,

@@ -12,6 +12,7 @@
 #include "observe_kernel.cuh"
 #include "policy_kernels.cuh"
 #include "step_kernel.cuh"
+#include "coop_step_kernel.cuh"
 
 using namespace msched;
 
@@ -46,7 +47,7 @@ int compute_layout(const MschedConfig *c, MschedLayout *o)
     if (c->B < 1) return fail(MSCHED_E_ARG, "B must be >= 1");
     if (c->N < 1 || c->N > 250) return fail(MSCHED_E_ARG, "numberOfAgents must be in 1..250");
     if (c->C < 1 || c->C > 64) return fail(MSCHED_E_ARG, "numberOfCores must be in 1..64");
-    if (c->L < 1 || (long long)c->N * c->L > 254) return fail(MSCHED_E_ARG, "N*L must be in 1..254");
+    if (c->L < 1 || (long long)c->N * c->L > 4096) return fail(MSCHED_E_ARG, "N*L must be in 1..4096");
     if (c->J < 1 || c->J > MSCHED_MAX_KINDS) return fail(MSCHED_E_ARG, "job kinds must be in 1..16");
     if (c->newJobsPerRound < 0 || c->newJobsPerRound > c->L)
         return fail(MSCHED_E_ARG, "newJobsPerRoundPerAgent must be in 0..collectionLength");
@@ -118,8 +119,12 @@ struct Handle {
     int device;
     long long round;
     int smemOptin;
-    int stepTile;  // envs per CTA of the step kernel
+    int stepTile;  // envs per CTA of the lane-per-env step kernel (0 = not available)
     StepKernel stepFn;
+    StepKernel coopFn;  // cooperative kernel (G lanes per env), null = not available
+    int coopG, coopThreads;
+    size_t coopSmem;
+    bool useCoop;
     ObsKernel obsFn;  // compile-time-domain observation kernel, or null -> direct kernel
     int16_t *stageAction;
     uint32_t *stageResult;
@@ -227,15 +232,43 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     CUDA_TRY(cudaDeviceGetAttribute(&h->smemOptin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     const size_t stepBytes = (size_t)lay.state_words * 4 + (size_t)lay.action_halfs * 2 + (size_t)lay.result_words * 4 +
                              (size_t)scratch_words(cfg->C) * 4;
-    h->stepTile = pick_tile(stepBytes, h->smemOptin, "MSCHED_STEP_TILE");
-    if (h->stepTile == 0) {
-        delete h;
-        return fail(MSCHED_E_ARG, "domain too large for the lane-per-env step kernel (state+action+result of "
-                                  "32 envs must fit in shared memory)");
+    // lane-per-env kernel (needs N*L <= 254 and 32 envs of records in shared memory)
+    h->stepTile = (cfg->N * cfg->L <= 254) ? pick_tile(stepBytes, h->smemOptin, "MSCHED_STEP_TILE") : 0;
+    if (h->stepTile) {
+        h->stepFn = pick_step_kernel(cfg->N, cfg->C, cfg->L);
+        CUDA_TRY(cudaFuncSetAttribute(h->stepFn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(h->stepTile * stepBytes)));
     }
-    h->stepFn = pick_step_kernel(cfg->N, cfg->C, cfg->L);
-    CUDA_TRY(cudaFuncSetAttribute(h->stepFn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)(h->stepTile * stepBytes)));
+    // cooperative kernel: G lanes per env, G = next power of two >= max(C, N), clamped to 4..32
+    {
+        int G = 4;
+        while (G < 32 && G < (cfg->C > cfg->N ? cfg->C : cfg->N)) G <<= 1;
+        if (const char *e = getenv("MSCHED_COOP_G")) {
+            const int g = atoi(e);
+            if (g == 4 || g == 8 || g == 16 || g == 32) G = g;
+        }
+        const size_t coopBytes = (size_t)lay.state_words * 4 + (size_t)lay.action_halfs * 2 +
+                                 (size_t)lay.result_words * 4 + (size_t)coop_scratch_words(cfg->C) * 4;
+        int T = 128;
+        while (T > 4 * G && (size_t)(T / G) * coopBytes + 64 > (size_t)h->smemOptin) T >>= 1;
+        if ((size_t)(T / G) * coopBytes + 64 <= (size_t)h->smemOptin) {
+            h->coopG = G;
+            h->coopThreads = T;
+            h->coopSmem = (size_t)(T / G) * coopBytes;
+            h->coopFn = G == 4 ? coop_step_kernel<4> : G == 8 ? coop_step_kernel<8>
+                      : G == 16 ? coop_step_kernel<16> : coop_step_kernel<32>;
+            CUDA_TRY(cudaFuncSetAttribute(h->coopFn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->coopSmem));
+        }
+    }
+    if (!h->stepTile && !h->coopFn) {
+        delete h;
+        return fail(MSCHED_E_ARG, "domain too large: the records of 4 environments must fit in shared memory");
+    }
+    h->useCoop = h->coopFn && !h->stepTile;
+    if (const char *e = getenv("MSCHED_STEP_IMPL")) {
+        if (!strcmp(e, "coop") && h->coopFn) h->useCoop = true;
+        if (!strcmp(e, "lane") && h->stepTile) h->useCoop = false;
+    }
     h->obsFn = pick_obs_kernel(cfg->N, cfg->C, cfg->L);
     if (h->obsFn && (lay.state_words * 4 > lay.obs_halfs * 2 || 32 * lay.obs_halfs * 2 + 64 > h->smemOptin))
         h->obsFn = nullptr;
@@ -313,9 +346,14 @@ int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_d
     p.result = result_dev;
     p.round = (int)h->round;
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
-    const int T = h->stepTile;
-    const size_t smem = (size_t)T * ((size_t)p.W * 4 + (size_t)p.AH * 2 + (size_t)p.RW * 4 + (size_t)scratch_words(p.C) * 4);
-    h->stepFn<<<p.Bpad / T, T, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    if (h->useCoop) {
+        const int E = h->coopThreads / h->coopG;
+        h->coopFn<<<p.Bpad / E, h->coopThreads, h->coopSmem, static_cast<cudaStream_t>(stream)>>>(p);
+    } else {
+        const int T = h->stepTile;
+        const size_t smem = (size_t)T * ((size_t)p.W * 4 + (size_t)p.AH * 2 + (size_t)p.RW * 4 + (size_t)scratch_words(p.C) * 4);
+        h->stepFn<<<p.Bpad / T, T, smem, static_cast<cudaStream_t>(stream)>>>(p);
+    }
     CUDA_TRY(cudaGetLastError());
     h->round += 1;
     return MSCHED_OK;

@@ -90,13 +90,27 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
     int *resi = reinterpret_cast<int *>(res);
     uint32_t flags = st[1];
 
-    // liability chains of cores whose job completes this step are walked further down: start
-    // pulling their first line out of HBM now (one 128 B line holds 16 entries)
+    // liability chains of cores whose job completes this step are walked further down; their
+    // loads are cold, dependent HBM accesses, so issue them NOW: with a compile-time domain the
+    // first two entries (16 B) of every candidate core go straight into registers, otherwise the
+    // line is prefetched
+    constexpr int PC = TC > 0 ? TC : 1;
+    uint4 pre[PC];
+    bool preOk[PC];
+#pragma unroll
+    for (int j = 0; j < PC; ++j) { pre[j] = make_uint4(0u, 0u, 0u, 0u); preOk[j] = false; }
 #pragma unroll
     for (int j = 0; j < C; ++j) {
         const uint32_t cw0 = core[3 * j];
-        if (job_kind(cw0) >= 0 && job_rem(cw0) == 1)
-            prefetch_l1(reinterpret_cast<const uint2 *>(p.chain) + ((size_t)env * C + j) * p.chainCap);
+        if (job_kind(cw0) >= 0 && job_rem(cw0) == 1) {
+            const uint2 *cb = reinterpret_cast<const uint2 *>(p.chain) + ((size_t)env * C + j) * p.chainCap;
+            if (TC > 0 && (p.chainCap & 1) == 0) {
+                pre[TC > 0 ? j : 0] = *reinterpret_cast<const uint4 *>(cb);
+                preOk[TC > 0 ? j : 0] = true;
+            } else {
+                prefetch_l1(cb);
+            }
+        }
     }
 
 #pragma unroll 4
@@ -269,6 +283,9 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
                 uint2 *ce = reinterpret_cast<uint2 *>(p.chain) + ((size_t)env * C + j) * p.chainCap + len;
                 *ce = make_uint2((uint32_t)round, pack_chain(price, time, offerer));
                 chl[j >> 2] = cw + (1u << ((j & 3) * 8));
+#pragma unroll
+                for (int jj = 0; jj < PC; ++jj)
+                    if (jj == j) preOk[jj] = false;  // the preloaded copy is stale now
             } else {
                 flags |= MSCHED_FLAG_CHAIN_OVERFLOW;
             }
@@ -316,7 +333,13 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
         const uint2 *ce = reinterpret_cast<const uint2 *>(p.chain) + ((size_t)env * C + j) * p.chainCap;
         int recip = 0;  // the oldest entry was accepted by the auctioneer
         for (int e = 0; e < len; ++e) {
-            const uint2 en = ce[e];
+            uint2 en;
+            if (TC > 0 && e < 2 && preOk[TC > 0 ? j : 0]) {
+                const uint4 q4 = pre[TC > 0 ? j : 0];
+                en = e == 0 ? make_uint2(q4.x, q4.y) : make_uint2(q4.z, q4.w);
+            } else {
+                en = ce[e];
+            }
             const int price = (int)(int16_t)(en.y & 0xffffu);
             const int time = (int)((en.y >> 16) & 0xffu);
             const int offerer = (int)(en.y >> 24);
