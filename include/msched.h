@@ -197,16 +197,32 @@ typedef struct MschedMlpGroup {
 
 int msched_mlp_param_count(int n_in, int n_hidden, int n_actions);
 
-/* x: int16 observations.  Unit u of env b is the row at x + b*env_stride + u*x_stride (int16
- * elements; env_stride 0 means units*x_stride, i.e. a dense [M][x_stride] matrix) and is evaluated
- * by net (u / unit_div) % n_nets.  M = n_envs*units rows, row index r = b*units + u.  seed/step select the
- * Philox stream (counter = (row_offset + r, step)); u_override float32 [M] replaces the draws
- * (parity tests).  action int32 [M], logprob float32 [M] (either may be NULL); probs float32
- * [M][A] optional (NULL in production). */
-int msched_actor_forward(const MschedMlpGroup *nets, const int16_t *x, int x_stride,
-                         int64_t env_stride, int units, int M, uint64_t seed, uint64_t step,
-                         int64_t row_offset, const float *u_override, int32_t *action,
-                         float *logprob, float *probs, void *stream);
+/* Inputs/outputs of one actor launch over n_envs * units rows (row index r = b*units + u).
+ * Unit u of env b reads its observation at x + b*env_stride + u*x_stride (int16 elements;
+ * env_stride 0 means units*x_stride, i.e. a dense [M][x_stride] matrix) and is evaluated by net
+ * (u / unit_div) % n_nets.  seed/step select the Philox stream (counter = (row_offset + r, step));
+ * u_override float32 [M] replaces the draws (parity tests).  Any output may be NULL. */
+typedef struct MschedActorIO {
+    const int16_t *x;
+    int32_t x_stride, units, n_envs, n_cores;
+    int64_t env_stride, row_offset;
+    uint64_t seed, step;
+    const float *u_override;
+    int32_t *action;         /* int32 [M] */
+    float *logprob;          /* float32 [M] */
+    float *probs;            /* float32 [M][A], tests only */
+    int16_t *action_rec;     /* action of (b,u) also stored at action_rec[b*action_rec_stride + u]:
+                                lets the kernel write straight into the env's action record */
+    int64_t action_rec_stride;
+    /* FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): when gather_core != NULL the row
+     * at x is the unit's OFFER observation [2C+2] and the net's 4 inputs are gathered from it by the
+     * core chooser's action a = gather_core[r]: [row[2a], row[2a+1], row[2C], row[2C+1]], or
+     * [-5,-5,-5,-5] for a == 0, in which case the reported action is -5 (quirk Q1). */
+    const int32_t *gather_core;
+    int16_t *x_used;         /* optional int16 [M][n_in]: the input actually fed (PPO buffer.states) */
+} MschedActorIO;
+
+int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, void *stream);
 
 /* PPO.update returns prologue (src/PPOmodules.py:128-137): G_t = r_t + gamma*G_{t+1} over
  * the whole buffer in float64, cast to float32, optional (G-mean)/(std_unbiased+1e-7) per

@@ -55,6 +55,15 @@ class MschedMlpGroup(C.Structure):
                 ("weights", C.c_void_p)]
 
 
+class MschedActorIO(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("x_stride", C.c_int32), ("units", C.c_int32),
+                ("n_envs", C.c_int32), ("n_cores", C.c_int32), ("env_stride", C.c_int64),
+                ("row_offset", C.c_int64), ("seed", C.c_uint64), ("step", C.c_uint64),
+                ("u_override", C.c_void_p), ("action", C.c_void_p), ("logprob", C.c_void_p),
+                ("probs", C.c_void_p), ("action_rec", C.c_void_p), ("action_rec_stride", C.c_int64),
+                ("gather_core", C.c_void_p), ("x_used", C.c_void_p)]
+
+
 # every symbol include/msched.h declares: name -> (restype, argtypes)
 P = C.c_void_p
 SYMBOLS = {
@@ -74,8 +83,7 @@ SYMBOLS = {
     "msched_auctioneer_action": (C.c_int, [P, C.c_int, P, P]),
     "msched_export_state": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, P]),
     "msched_mlp_param_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
-    "msched_actor_forward": (C.c_int, [C.POINTER(MschedMlpGroup), P, C.c_int, C.c_int64, C.c_int,
-                                       C.c_int, C.c_uint64, C.c_uint64, C.c_int64, P, P, P, P, P]),
+    "msched_actor_forward": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),
     "msched_returns": (C.c_int, [P, C.c_int, C.c_int, C.c_double, C.c_int, P, P]),
 }
 

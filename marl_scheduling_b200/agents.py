@@ -43,14 +43,22 @@ class BatchedPPO:
         self.step_no = 0
 
     # -- rollout ---------------------------------------------------------------------------------
-    def selectAction(self, x, x_stride, env_stride, n_envs, seed):
+    def selectAction(self, x, x_stride, env_stride, n_envs, seed, action_rec=None, action_rec_stride=0,
+                     gather_core=None, n_cores=0):
         """PPO.selectAction for every (env, unit): x is an int16 view whose rows are the units'
-        observations.  Returns actions int32 [n_envs, units]; stores state/action/logprob."""
+        observations.  Returns actions int32 [n_envs, units]; stores state/action/logprob.
+        action_rec: int16 view into the environment's action record that the kernel fills
+        directly; gather_core: core chooser actions (price chooser launch, see policy.actor_forward)."""
+        x_used = None
+        if gather_core is not None:
+            x_used = torch.empty((n_envs, self.units, self.n_in), dtype=torch.int16, device=x.device)
         act, lp, _ = P.actor_forward(self.policy_old, x, x_stride, self.units, n_envs,
-                                     env_stride=env_stride, seed=seed, step=self.step_no)
+                                     env_stride=env_stride, seed=seed, step=self.step_no,
+                                     action_rec=action_rec, action_rec_stride=action_rec_stride,
+                                     gather_core=gather_core, n_cores=n_cores, x_used=x_used)
         self.step_no += 1
         # the PPO buffer keeps the observation like buffer.states
-        self.buf_x.append(x.reshape(n_envs, self.units, self.n_in).clone())
+        self.buf_x.append(x_used if x_used is not None else x.reshape(n_envs, self.units, self.n_in).clone())
         self.buf_a.append(act.view(n_envs, self.units))
         self.buf_lp.append(lp.view(n_envs, self.units))
         return act.view(n_envs, self.units)
@@ -161,10 +169,13 @@ class DividedFixedPricePPOAgents:
         c, lay = self.env.core, self.env.core.layout
         B, N, C, L = c.B, c.N, c.C, c.Lc
         seed = self.world.seed
-        off = self.offer.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 2 + 1)
-        acc = self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 2)
+        # the kernels write the chosen actions straight into the env's action record
+        self.offer.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 2 + 1,
+                                action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs)
+        self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 2,
+                                   action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs)
         # SchedulingEnv.getActionForAllAgents returns (acceptorActions, offerActions)
-        return acc.view(B, N, C), off.view(B, N, L)
+        return c.acceptor_actions, c.offer_core_actions
 
     def saveRewards(self, offerRewards, acceptorRewards, agentReward):
         self.offer.saveReward(offerRewards)
@@ -209,17 +220,16 @@ class DividedFreePricePPOAgents:
         c, lay = self.env.core, self.env.core.layout
         B, N, C, L = c.B, c.N, c.C, c.Lc
         seed = self.world.seed
-        core = self.core.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 3 + 1).view(B, N, L)
-        a = core.long().clamp(max=C)            # for a == C the slice [2C:2C+2] is the slot pair
-        idx = torch.stack([2 * a, 2 * a + 1], -1)
-        chosen = torch.gather(offerObs, 3, idx)                      # [B,N,L,2]
-        own = offerObs[..., 2 * C: 2 * C + 2]
-        xin = torch.cat([chosen, own], -1)
-        xin = torch.where((core == 0)[..., None], torch.full_like(xin, -5), xin).contiguous()
-        price = self.price.selectAction(xin.view(B * N * L, 4), 4, 0, B, seed * 3 + 2).view(B, N, L)
-        price = torch.where(core == 0, torch.full_like(price, -5), price)
-        acc = self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 3)
-        return acc.view(B, N, C), (core, price)
+        core = self.core.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 3 + 1,
+                                      action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs)
+        # price chooser: the kernel slices [core prio, core rem, slot prio, slot rem] of the chosen
+        # core out of the offer observation row ([-5]*4 and reported price -5 for core action 0)
+        self.price.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 3 + 2,
+                                action_rec=c.offer_price_actions, action_rec_stride=lay.action_halfs,
+                                gather_core=core.reshape(-1), n_cores=C)
+        self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 3,
+                                   action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs)
+        return c.acceptor_actions, (c.offer_core_actions, c.offer_price_actions)
 
     def saveRewards(self, offerRewards, acceptorRewards, agentReward):
         coreChooser, priceChooser = offerRewards

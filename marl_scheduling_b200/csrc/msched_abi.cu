@@ -128,6 +128,8 @@ struct Handle {
     ObsKernel obsFn;  // compile-time-domain observation kernel, or null -> direct kernel
     int16_t *stageAction;
     uint32_t *stageResult;
+    cudaStream_t hostStream[2];  // msched_step_host pipelines its chunks over these
+    cudaEvent_t evStart, evDone[2];
 };
 
 StepKernel pick_step_kernel(int N, int C, int L)
@@ -186,6 +188,19 @@ int pick_tile(size_t bytesPerEnv, int smemOptin, const char *envName)
 }
 
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// launch the step kernel for the env range described by p (p.Bpad padded envs starting at p.state)
+void launch_step(const Handle *h, const DevParams &p, cudaStream_t s)
+{
+    if (h->useCoop) {
+        const int E = h->coopThreads / h->coopG;
+        h->coopFn<<<p.Bpad / E, h->coopThreads, h->coopSmem, s>>>(p);
+    } else {
+        const int T = h->stepTile;
+        const size_t smem = (size_t)T * ((size_t)p.W * 4 + (size_t)p.AH * 2 + (size_t)p.RW * 4 + (size_t)scratch_words(p.C) * 4);
+        h->stepFn<<<p.Bpad / T, T, smem, s>>>(p);
+    }
+}
 
 }  // namespace
 
@@ -264,7 +279,10 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
         delete h;
         return fail(MSCHED_E_ARG, "domain too large: the records of 4 environments must fit in shared memory");
     }
-    h->useCoop = h->coopFn && !h->stepTile;
+    // small batches are latency-bound: the cooperative kernel's shorter per-env critical path wins
+    // (cfg2 at 4,096 envs: 17.6 us vs 22.8 us); large batches of small domains are issue-bound and
+    // the lane-per-env kernel executes a third of the instructions (cfg3 at 65,536: 20.7 vs 37 us)
+    h->useCoop = h->coopFn && (!h->stepTile || cfg->B <= 8192);
     if (const char *e = getenv("MSCHED_STEP_IMPL")) {
         if (!strcmp(e, "coop") && h->coopFn) h->useCoop = true;
         if (!strcmp(e, "lane") && h->stepTile) h->useCoop = false;
@@ -278,6 +296,11 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     CUDA_TRY(cudaMalloc(&h->stageAction, (size_t)lay.padded_envs * lay.action_halfs * 2));
     CUDA_TRY(cudaMalloc(&h->stageResult, (size_t)lay.padded_envs * lay.result_words * 4));
     CUDA_TRY(cudaMemset(h->stageAction, 0, (size_t)lay.padded_envs * lay.action_halfs * 2));
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->hostStream[k], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->evDone[k], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&h->evStart, cudaEventDisableTiming));
     *handle = h;
     return MSCHED_OK;
 }
@@ -289,6 +312,11 @@ int msched_destroy(void *handle)
     cudaSetDevice(h->device);
     cudaFree(h->stageAction);
     cudaFree(h->stageResult);
+    for (int k = 0; k < 2; ++k) {
+        if (h->hostStream[k]) cudaStreamDestroy(h->hostStream[k]);
+        if (h->evDone[k]) cudaEventDestroy(h->evDone[k]);
+    }
+    if (h->evStart) cudaEventDestroy(h->evStart);
     delete h;
     return MSCHED_OK;
 }
@@ -346,14 +374,7 @@ int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_d
     p.result = result_dev;
     p.round = (int)h->round;
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
-    if (h->useCoop) {
-        const int E = h->coopThreads / h->coopG;
-        h->coopFn<<<p.Bpad / E, h->coopThreads, h->coopSmem, static_cast<cudaStream_t>(stream)>>>(p);
-    } else {
-        const int T = h->stepTile;
-        const size_t smem = (size_t)T * ((size_t)p.W * 4 + (size_t)p.AH * 2 + (size_t)p.RW * 4 + (size_t)scratch_words(p.C) * 4);
-        h->stepFn<<<p.Bpad / T, T, smem, static_cast<cudaStream_t>(stream)>>>(p);
-    }
+    launch_step(h, p, static_cast<cudaStream_t>(stream));
     CUDA_TRY(cudaGetLastError());
     h->round += 1;
     return MSCHED_OK;
@@ -364,14 +385,45 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
     Handle *h = static_cast<Handle *>(handle);
     if (!h || !action_host || !result_host) return fail(MSCHED_E_ARG, "null handle/action/result");
     if (h->cfg.spawnMode == MSCHED_SPAWN_U64) return fail(MSCHED_E_ARG, "step_host does not take recorded draws");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(h->device));
-    CUDA_TRY(cudaMemcpyAsync(h->stageAction, action_host, (size_t)h->cfg.B * h->lay.action_halfs * 2,
-                             cudaMemcpyHostToDevice, s));
-    int rc = msched_step(handle, h->stageAction, nullptr, h->stageResult, stream);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(result_host, h->stageResult, (size_t)h->cfg.B * h->lay.result_words * 4,
-                             cudaMemcpyDeviceToHost, s));
+    // The batch is cut into chunks (multiples of the 128-env padding unit) that alternate between
+    // two internal streams, so the H2D copy of one chunk, the kernel of another and the D2H copy of
+    // a third overlap (PCIe is full duplex); environments are independent, so any split is exact.
+    const int B = h->cfg.B, AH = h->lay.action_halfs, RW = h->lay.result_words;
+    int nChunks = 2;
+    if (const char *e = getenv("MSCHED_HOST_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 64) nChunks = v; }
+    int chunk = ((B + nChunks - 1) / nChunks + MSCHED_TILE_ENVS - 1) / MSCHED_TILE_ENVS * MSCHED_TILE_ENVS;
+    CUDA_TRY(cudaEventRecord(h->evStart, s));
+    for (int k = 0; k < 2; ++k) CUDA_TRY(cudaStreamWaitEvent(h->hostStream[k], h->evStart, 0));
+    int c = 0;
+    for (int e0 = 0; e0 < B; e0 += chunk, ++c) {
+        const int n = (B - e0 < chunk) ? (B - e0) : chunk;
+        cudaStream_t cs = h->hostStream[c & 1];
+        CUDA_TRY(cudaMemcpyAsync(h->stageAction + (size_t)e0 * AH, action_host + (size_t)e0 * AH, (size_t)n * AH * 2,
+                                 cudaMemcpyHostToDevice, cs));
+        DevParams p = h->p;
+        p.B = n;
+        p.Bpad = msched_padded_envs(n);
+        p.state = h->p.state + (size_t)e0 * p.W;
+        p.chain = h->p.chain + (size_t)e0 * h->lay.chain_words;
+        p.action = h->stageAction + (size_t)e0 * AH;
+        p.result = h->stageResult + (size_t)e0 * RW;
+        p.spawnU = nullptr;
+        p.envOffset = h->p.envOffset + e0;
+        p.round = (int)h->round;
+        p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
+        launch_step(h, p, cs);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(result_host + (size_t)e0 * RW, h->stageResult + (size_t)e0 * RW, (size_t)n * RW * 4,
+                                 cudaMemcpyDeviceToHost, cs));
+    }
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(cudaEventRecord(h->evDone[k], h->hostStream[k]));
+        CUDA_TRY(cudaStreamWaitEvent(s, h->evDone[k], 0));
+    }
+    h->round += 1;
     CUDA_TRY(cudaStreamSynchronize(s));
     return MSCHED_OK;
 }
@@ -428,20 +480,24 @@ int msched_mlp_param_count(int n_in, int n_hidden, int n_actions)
     return n_hidden * n_in + n_hidden + n_hidden * n_hidden + n_hidden + n_actions * n_hidden + n_actions;
 }
 
-int msched_actor_forward(const MschedMlpGroup *nets, const int16_t *x, int x_stride, int64_t env_stride,
-                         int units, int M,
-                         uint64_t seed, uint64_t step, int64_t row_offset, const float *u_override,
-                         int32_t *action, float *logprob, float *probs, void *stream)
+int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, void *stream)
 {
-    if (!nets || !x || !nets->weights) return fail(MSCHED_E_ARG, "null nets/x/weights");
-    if (M < 0 || units < 1 || nets->n_nets < 1 || x_stride < nets->n_in)
-        return fail(MSCHED_E_ARG, "bad M/units/n_nets/x_stride");
+    if (!nets || !io || !io->x || !nets->weights) return fail(MSCHED_E_ARG, "null nets/io/x/weights");
+    if (io->n_envs < 0 || io->units < 1 || nets->n_nets < 1)
+        return fail(MSCHED_E_ARG, "bad n_envs/units/n_nets");
     if (nets->n_in < 1 || nets->n_in > 128 || nets->n_hidden < 8 || nets->n_hidden > 64 ||
         (nets->n_hidden % 8) != 0 || nets->n_actions < 1)
         return fail(MSCHED_E_ARG, "unsupported MLP shape (in 1..128, hidden 8..64 multiple of 8)");
-    if (M == 0) return MSCHED_OK;
-    int rc = launch_actor_forward(*nets, x, x_stride, env_stride, units, M, seed, step, row_offset, u_override, action,
-                                  logprob, probs, static_cast<cudaStream_t>(stream));
+    if (io->gather_core) {
+        if (nets->n_in != 4 || io->n_cores < 1 || io->x_stride < 2 * io->n_cores + 2)
+            return fail(MSCHED_E_ARG, "gather_core needs n_in == 4 and offer observation rows of 2*n_cores+2");
+    } else if (io->x_stride < nets->n_in) {
+        return fail(MSCHED_E_ARG, "x_stride smaller than n_in");
+    }
+    if (io->action_rec && io->action_rec_stride < io->units)
+        return fail(MSCHED_E_ARG, "action_rec_stride smaller than units");
+    if (io->n_envs == 0) return MSCHED_OK;
+    int rc = launch_actor_forward(*nets, *io, static_cast<cudaStream_t>(stream));
     if (rc == -1) return fail(MSCHED_E_ARG, "unsupported MLP shape for the actor kernel");
     CUDA_TRY(cudaGetLastError());
     return MSCHED_OK;

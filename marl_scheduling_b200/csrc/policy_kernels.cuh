@@ -57,6 +57,11 @@ struct ActorArgs {
     int32_t *action;         // [M] or null
     float *logprob;          // [M] or null
     float *probs;            // [M][A] or null
+    int16_t *actionRec;      // reported action also stored at actionRec[env*actionRecStride + unit]
+    long long actionRecStride;
+    const int32_t *gatherCore;  // FreePriceOfferPPO price chooser: gather the 4 inputs by this action
+    int16_t *xUsed;             // [M][nIn] input actually fed, or null
+    int nCores;
 };
 
 constexpr int kActorMaxActions = 64;
@@ -91,11 +96,28 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
     const int16_t *xr = a.x + (size_t)env * a.envStride + (size_t)unit * a.unitStride;
     const long long row = (long long)env * a.units + unit;
 
+    // FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): the price chooser's input is
+    // [core prio, core rem, slot prio, slot rem] of the core the core chooser picked, sliced out
+    // of the offer observation row; core action 0 feeds the dummy [-5,-5,-5,-5] (quirk Q1)
+    int gsel = -1;
+    int16_t g4[4] = {0, 0, 0, 0};
+    if (a.gatherCore) {
+        gsel = a.gatherCore[row];
+        const int c2 = 2 * a.nCores;
+        if (gsel <= 0 || gsel > a.nCores) {
+            g4[0] = g4[1] = g4[2] = g4[3] = (int16_t)-5;
+        } else {
+            g4[0] = xr[2 * gsel]; g4[1] = xr[2 * gsel + 1]; g4[2] = xr[c2]; g4[3] = xr[c2 + 1];
+        }
+    }
+    if (a.xUsed)
+        for (int k = 0; k < nIn; ++k) a.xUsed[(size_t)row * nIn + k] = a.gatherCore ? g4[k & 3] : xr[k];
+
     float h1[H], h2[H];
 #pragma unroll
     for (int o = 0; o < H; ++o) h1[o] = b1[o];
     for (int k = 0; k < nIn; ++k) {
-        const float xv = (float)xr[k];
+        const float xv = a.gatherCore ? (float)g4[k & 3] : (float)xr[k];
         const float4 *wr = reinterpret_cast<const float4 *>(W1t + k * H);
 #pragma unroll
         for (int o4 = 0; o4 < H / 4; ++o4) {
@@ -156,7 +178,7 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
         if (o < A) { lg[o] = lg[o] / sum; tot += lg[o]; }
     if (a.probs)
         for (int o = 0; o < A; ++o) a.probs[(size_t)row * A + o] = lg[o];
-    if (!a.action && !a.logprob) return;
+    if (!a.action && !a.logprob && !a.actionRec) return;
     float u;
     if (a.uOverride) {
         u = a.uOverride[row];
@@ -183,7 +205,9 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
         for (int o = 0; o < kActorMaxActions; ++o)
             if (o == A - 1) pa = lg[o];
     }
-    if (a.action) a.action[row] = act;
+    if (a.action) a.action[row] = act;  // what PPO.selectAction stores in buffer.actions
+    if (a.actionRec)                    // what the world is handed (price -5 next to core action 0)
+        a.actionRec[(size_t)env * a.actionRecStride + unit] = (int16_t)((a.gatherCore && gsel == 0) ? -5 : act);
     if (a.logprob) {
         const float eps = 1.1920928955078125e-07f;
         float pn = pa / tot;
@@ -192,24 +216,22 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
     }
 }
 
-inline int launch_actor_forward(const MschedMlpGroup &g, const int16_t *x, int x_stride, long long env_stride,
-                                int units, int M,
-                                uint64_t seed, uint64_t step, int64_t row_offset, const float *u_override,
-                                int32_t *action, float *logprob, float *probs, cudaStream_t s)
+inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io, cudaStream_t s)
 {
     if (g.n_actions > kActorMaxActions) return -1;
-    if (M % units) return -1;
     ActorArgs a;
-    a.weights = g.weights; a.x = x;
-    a.envStride = env_stride ? env_stride : (long long)x_stride * units; a.unitStride = x_stride;
+    a.weights = g.weights; a.x = io.x;
+    a.envStride = io.env_stride ? io.env_stride : (long long)io.x_stride * io.units; a.unitStride = io.x_stride;
     a.nIn = g.n_in; a.nHidden = g.n_hidden; a.nActions = g.n_actions; a.nNets = g.n_nets;
     a.unitDiv = g.unit_div > 0 ? g.unit_div : 1;
-    a.units = units; a.nEnvs = M / units;
-    a.seed = seed; a.step = step; a.rowOffset = row_offset; a.uOverride = u_override;
-    a.action = action; a.logprob = logprob; a.probs = probs;
+    a.units = io.units; a.nEnvs = io.n_envs;
+    a.seed = io.seed; a.step = io.step; a.rowOffset = io.row_offset; a.uOverride = io.u_override;
+    a.action = io.action; a.logprob = io.logprob; a.probs = io.probs;
+    a.actionRec = io.action_rec; a.actionRecStride = io.action_rec_stride;
+    a.gatherCore = io.gather_core; a.xUsed = io.x_used; a.nCores = io.n_cores;
     const int H = g.n_hidden, Apad = (g.n_actions + 3) & ~3;
     const size_t smem = sizeof(float) * ((size_t)g.n_in * H + H + (size_t)H * H + H + (size_t)H * Apad + Apad);
-    dim3 grid((a.nEnvs + 127) / 128, units);
+    dim3 grid((a.nEnvs + 127) / 128, io.units);
     if (H == 16) actor_forward_simt<16><<<grid, 128, smem, s>>>(a);
     else if (H == 32) actor_forward_simt<32><<<grid, 128, smem, s>>>(a);
     else if (H == 64) actor_forward_simt<64><<<grid, 128, smem, s>>>(a);

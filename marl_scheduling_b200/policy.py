@@ -63,8 +63,13 @@ def _stream(device):
 
 
 def actor_forward(group, x, x_stride, units, n_envs, env_stride=0, seed=0, step=0, row_offset=0,
-                  u=None, want_probs=False, action=None, logprob=None):
+                  u=None, want_probs=False, action=None, logprob=None, action_rec=None,
+                  action_rec_stride=0, gather_core=None, n_cores=0, x_used=None):
     """x: int16 device tensor; unit u of env b is the row at x[b*env_stride + u*x_stride : +n_in].
+    action_rec (int16 view into the env's action record) additionally receives the action the
+    world is handed; gather_core (int32 [n_envs*units]) turns the launch into the free-price price
+    chooser (its 4 inputs are sliced out of the offer observation row, src/PPOmodules.py:312-332);
+    x_used (int16 [n_envs*units, n_in]) receives the inputs actually fed (PPO buffer.states).
     Returns (action int32 [n_envs*units], logprob float32, probs or None)."""
     dev = x.device
     M = n_envs * units
@@ -75,10 +80,17 @@ def actor_forward(group, x, x_stride, units, n_envs, env_stride=0, seed=0, step=
     probs = torch.empty((M, group.n_actions), dtype=torch.float32, device=dev) if want_probs else None
     if u is not None:
         u = torch.as_tensor(u, dtype=torch.float32).to(dev).contiguous()
-    L.check(L.lib().msched_actor_forward(
-        C.byref(group.desc), x.data_ptr(), x_stride, env_stride, units, M, seed, step, row_offset,
-        None if u is None else u.data_ptr(), action.data_ptr(), logprob.data_ptr(),
-        None if probs is None else probs.data_ptr(), _stream(dev)))
+    io = L.MschedActorIO()
+    io.x, io.x_stride, io.units, io.n_envs, io.n_cores = x.data_ptr(), x_stride, units, n_envs, n_cores
+    io.env_stride, io.row_offset, io.seed, io.step = env_stride, row_offset, seed, step
+    io.u_override = None if u is None else u.data_ptr()
+    io.action, io.logprob = action.data_ptr(), logprob.data_ptr()
+    io.probs = None if probs is None else probs.data_ptr()
+    io.action_rec = None if action_rec is None else action_rec.data_ptr()
+    io.action_rec_stride = action_rec_stride
+    io.gather_core = None if gather_core is None else gather_core.data_ptr()
+    io.x_used = None if x_used is None else x_used.data_ptr()
+    L.check(L.lib().msched_actor_forward(C.byref(group.desc), C.byref(io), _stream(dev)))
     return action, logprob, probs
 
 

@@ -100,3 +100,46 @@ def test_returns_match_reference_and_oracle():
     # scan property: raw returns satisfy G_t - gamma*G_{t+1} = r_t
     raw = policy.returns(torch.as_tensor(r).to(dev), 0.5, normalise=False).cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(raw[:-1] - 0.5 * raw[1:], r[:-1], rtol=0, atol=2e-5)
+
+
+def test_price_chooser_gather_and_action_record():
+    """FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): the price chooser sees
+    [obs[2a], obs[2a+1], obs[-2], obs[-1]] of the core chooser's action a, the dummy [-5]*4 and a
+    reported price of -5 for a == 0; the kernel also writes the reported action into the action
+    record."""
+    import torch
+    from marl_scheduling_b200 import policy
+    from oracle import oracle as O
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(8)
+    n_envs, units, C, A, h = 333, 6, 3, 9, 16
+    row = 2 * C + 2
+    env_stride = units * row + 5
+    xs = rng.integers(-1, 9, (n_envs, env_stride)).astype(np.int16)
+    core = rng.integers(0, C + 1, (n_envs, units)).astype(np.int32)
+    u = rng.random(n_envs * units).astype(np.float32)
+    grp = policy.MlpGroup.random(4, h, A, units, dev, seed=12)
+    rec = torch.full((n_envs, 32), 77, dtype=torch.int16, device=dev)
+    x_used = torch.zeros((n_envs * units, 4), dtype=torch.int16, device=dev)
+    act, lp, pr = policy.actor_forward(grp, torch.as_tensor(xs).to(dev), row, units, n_envs,
+                                       env_stride=env_stride, u=u, want_probs=True,
+                                       action_rec=rec[:, 10:], action_rec_stride=32,
+                                       gather_core=torch.as_tensor(core.reshape(-1)).to(dev), n_cores=C,
+                                       x_used=x_used)
+    rows = xs[:, : units * row].reshape(n_envs, units, row)
+    a = core[..., None]
+    exp = np.concatenate([np.take_along_axis(rows, np.concatenate([2 * a, 2 * a + 1], -1), 2), rows[..., -2:]], -1)
+    exp = np.where(a == 0, -5, exp).astype(np.int16)
+    assert np.array_equal(x_used.cpu().numpy().reshape(n_envs, units, 4), exp)
+    act, pr = act.cpu().numpy().reshape(n_envs, units), pr.cpu().numpy().reshape(n_envs, units, A)
+    w = grp.weights.cpu().numpy()
+    for n in range(units):
+        o, ws = 0, []
+        for sz in (h * 4, h, h * h, h, A * h, A):
+            ws.append(w[n, o:o + sz]); o += sz
+        p, _, _ = O.mlp_forward(exp[:, n].astype(np.float32), ws[0].reshape(h, 4), ws[1], ws[2].reshape(h, h),
+                                ws[3], ws[4].reshape(A, h), ws[5])
+        np.testing.assert_allclose(pr[:, n], p, rtol=2e-5, atol=1e-7)
+    r = rec.cpu().numpy()
+    assert (r[:, :10] == 77).all() and (r[:, 10 + units:] == 77).all()
+    assert np.array_equal(r[:, 10:10 + units], np.where(core == 0, -5, act))
