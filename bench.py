@@ -76,12 +76,13 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_from_profile(cfg_name):
-    """dram bytes per step-kernel launch from the committed `ncu --set full` capture, or None."""
+def traffic_from_profile(cfg_name, kernel="step_kernel"):
+    """dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture,
+    or None if that kernel has not been captured."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(p) as f:
-            return json.load(f).get(cfg_name, {}).get("step_kernel_dram_bytes_per_launch")
+            return json.load(f).get(cfg_name, {}).get(kernel + "_dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -292,9 +293,10 @@ def main():
 
     def one_step(i):
         refresh_actions(env, ring[i % len(ring)], gen)
-        env.step_records(ring[i % len(ring)], results[i & 1])
         if dense:
-            env.observe()
+            env.step_observe_records(ring[i % len(ring)], results[i & 1])
+        else:
+            env.step_records(ring[i % len(ring)], results[i & 1])
 
     for i in range(args.state_warm):
         one_step(i)
@@ -313,15 +315,21 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t_wall0 = time.perf_counter()
+    info = env.info()
+    fused = dense and info["fuses_observations"]
     for i in range(K):
         refresh_actions(env, ring[i % len(ring)], gen)
         if flush is not None:
             flush.fill_(i & 0xFF)
         ev[i][0].record()
-        env.step_records(ring[i % len(ring)], results[i & 1])
-        ev[i][1].record()
-        if dense:
-            env.observe()
+        if fused:      # ONE launch: transition + observations of the new state
+            env.step_observe_records(ring[i % len(ring)], results[i & 1])
+            ev[i][1].record()
+        else:
+            env.step_records(ring[i % len(ring)], results[i & 1])
+            ev[i][1].record()
+            if dense:
+                env.observe()
         ev[i][2].record()
     if world > 1:
         dist.barrier()
@@ -372,7 +380,10 @@ def main():
     ab = algorithmic_bytes(dom, mode)
     peak, peak_src = measured_peak()
     step_launch_s = stepk_ms * 1e-3 / K
-    achieved = ab["step"] * B / step_launch_s / 1e9
+    kname = {"lane": "step_kernel", "coop": "coop_step_kernel", "fused": "fused_step_kernel"}[info["step_impl"]]
+    # the fused launch also writes the dense observation record: SURVEY 8(d) bytes = 2S + a + r + o
+    alg_bytes = ab["step"] + (ab["obs"] if fused else 0)
+    achieved = alg_bytes * B / step_launch_s / 1e9
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         c = cpu_baseline_sample(cfg, seconds=args.cpu_seconds, threads=1, envs=2048)
@@ -388,15 +399,19 @@ def main():
                    "observations": args.obs, "auctioneer": "in-kernel, random arg-max (Philox)",
                    "spawn": "device Philox", "actions": "uniform random, fresh draws every step (untimed)",
                    "l2": "warm (no flush)" if args.no_flush else "flushed before every timed step (256 MiB write)",
-                   "state_warm_steps": args.state_warm, "step_tile": os.environ.get("MSCHED_STEP_TILE", "auto")},
+                   "state_warm_steps": args.state_warm, "step_impl": info["step_impl"],
+                   "observations_fused_into_step_launch": bool(fused),
+                   "envs_per_cta": info["envs_per_cta"], "smem_bytes_per_cta": info["smem_bytes_per_cta"]},
         "clocks": clocks,
         "e2e": e2e,
-        "gpu_launches": K * (2 if dense else 1),
-        "roofline": {"bound": "hbm", "kernel": "step_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile(args.config),
-                     "peak_source": peak_src, "algorithmic_bytes_per_env_step": ab["step"],
+        "gpu_launches": K * (2 if (dense and not fused) else 1),
+        "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile(args.config, kname),
+                     "peak_source": peak_src, "algorithmic_bytes_per_env_step": alg_bytes,
+                     "algorithmic_bytes_formula": "2S+a+r" + ("+o (dense observations)" if fused else ""),
                      "units_per_launch": B, "launch_us": step_launch_s * 1e6},
-        "kernels": {"step_us": 1e3 * sum(step_ms) / K, "observe_us": 1e3 * sum(obs_ms) / K,
+        "kernels": {"step_us": 1e3 * sum(step_ms) / K,
+                    "observe_us": None if (fused or not dense) else 1e3 * sum(obs_ms) / K,
                     "observe_algorithmic_bytes_per_env": ab["obs"] + ab["state"]},
         "cpu_baseline": cpu,
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,

@@ -134,6 +134,23 @@ int msched_get_layout(const MschedConfig *cfg, MschedLayout *out);
 int msched_create(const MschedConfig *cfg, int device, void **handle);
 int msched_destroy(void *handle);
 
+/* which kernels this handle launches (diagnostics; bench.py reports it) */
+typedef struct MschedInfo {
+    int32_t step_impl;        /* 0 one lane per env (any domain), 1 cooperative G lanes per env,
+                                 2 register-resident compile-time-domain kernel */
+    int32_t fuses_observations; /* msched_step_observe is ONE launch */
+    int32_t envs_per_cta, threads_per_cta;
+    int32_t smem_bytes_per_cta; /* dynamic shared memory of the step launch (with observations if fused) */
+    int32_t reserved[3];
+} MschedInfo;
+int msched_get_info(void *handle, MschedInfo *out);
+
+/* diagnostics: when timeline_dev != NULL the compile-time-domain step kernel records, per CTA,
+ * 8 x uint64: SM id, %globaltimer at start, clock64 at start / after the pre-work / after the tile
+ * arrived / before the bulk stores / after they have read shared memory, %globaltimer at the end.
+ * Buffer: padded_envs/32 * 8 uint64.  NULL switches it off (default). */
+int msched_debug_timeline(void *handle, uint64_t *timeline_dev);
+
 /* bind the caller-owned persistent buffers (state: padded_envs*state_words uint32,
  * chain: padded_envs*chain_words uint32) */
 int msched_bind_state(void *handle, void *state_dev, void *chain_dev);
@@ -151,6 +168,14 @@ int msched_set_round(void *handle, int64_t round);
  * else NULL. */
 int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_dev,
                 uint32_t *result_dev, void *stream);
+
+/* SchedulingEnv.step INCLUDING the observations it returns (src/SchedulingEnvironment.py:32-83:
+ * world.step1, then every agent's gatherObservations and the auctioneer's observation of the NEW
+ * state, src/SchedulingEnvironment.py:44-58): msched_step followed by msched_observe_dense, fused
+ * into ONE launch when the domain has a compile-time kernel and the observation tile fits in
+ * shared memory next to the state tile (two launches otherwise; same results either way). */
+int msched_step_observe(void *handle, const int16_t *action_dev, const double *spawn_u_dev,
+                        uint32_t *result_dev, int16_t *obs_dev, void *stream);
 
 /* same call with HOST buffers (pinned recommended): H2D of the action records, the step, D2H of
  * the result records, then stream synchronise.  staging buffers are owned by the handle. */

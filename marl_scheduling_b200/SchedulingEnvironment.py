@@ -68,9 +68,10 @@ class SchedulingEnv(object):
                 auctioneer_action = c.auctioneer_action(self.world.randomAuctioneerTies)
         elif auctioneer_action is not None:
             raise ValueError("this environment runs the auction in-kernel; pass None")
-        r = c.step(offerActions, acceptorActions, auctioneer_action, offer_price=price)
+        # one C-ABI call: the transition and the observations of the new state (fused launch)
+        r = c.step(offerActions, acceptorActions, auctioneer_action, offer_price=price, observe=True)
         self._last = r
-        o = c.observe()
+        o = c.obs_views()
         offerRewards, acceptorRewards, auctioneerReward, agentReward = self.getRewards()
         cnt = r["quality_cnt"]
         mean = torch.where(cnt > 0, r["quality_sum"] / cnt.clamp(min=1).double(),

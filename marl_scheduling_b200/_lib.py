@@ -49,6 +49,12 @@ class MschedLayout(C.Structure):
         "o_acceptor", "o_offer", "o_auctioneer", "o_acc_row", "o_off_row")]
 
 
+class MschedInfo(C.Structure):
+    _fields_ = [("step_impl", C.c_int32), ("fuses_observations", C.c_int32), ("envs_per_cta", C.c_int32),
+                ("threads_per_cta", C.c_int32), ("smem_bytes_per_cta", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
+
+
 class MschedMlpGroup(C.Structure):
     _fields_ = [("n_in", C.c_int32), ("n_hidden", C.c_int32), ("n_actions", C.c_int32),
                 ("n_nets", C.c_int32), ("unit_div", C.c_int32), ("reserved", C.c_int32),
@@ -73,11 +79,14 @@ SYMBOLS = {
     "msched_get_layout": (C.c_int, [C.POINTER(MschedConfig), C.POINTER(MschedLayout)]),
     "msched_create": (C.c_int, [C.POINTER(MschedConfig), C.c_int, C.POINTER(P)]),
     "msched_destroy": (C.c_int, [P]),
+    "msched_get_info": (C.c_int, [P, C.POINTER(MschedInfo)]),
+    "msched_debug_timeline": (C.c_int, [P, P]),
     "msched_bind_state": (C.c_int, [P, P, P]),
     "msched_reset": (C.c_int, [P, P]),
     "msched_get_round": (C.c_int, [P, C.POINTER(C.c_int64)]),
     "msched_set_round": (C.c_int, [P, C.c_int64]),
     "msched_step": (C.c_int, [P, P, P, P, P]),
+    "msched_step_observe": (C.c_int, [P, P, P, P, P, P]),
     "msched_step_host": (C.c_int, [P, P, P, P]),
     "msched_observe_dense": (C.c_int, [P, P, P, P]),
     "msched_auctioneer_action": (C.c_int, [P, C.c_int, P, P]),

@@ -70,6 +70,14 @@ class BatchedSchedulingEnv:
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
+    def info(self):
+        """Which kernels the handle launches: dict(step_impl, fuses_observations, ...)."""
+        i = L.MschedInfo()
+        L.check(self.lib.msched_get_info(self.handle, C.byref(i)))
+        return dict(step_impl=("lane", "coop", "fused")[i.step_impl],
+                    fuses_observations=bool(i.fuses_observations), envs_per_cta=i.envs_per_cta,
+                    threads_per_cta=i.threads_per_cta, smem_bytes_per_cta=i.smem_bytes_per_cta)
+
     @property
     def round(self):
         r = C.c_int64()
@@ -138,11 +146,30 @@ class BatchedSchedulingEnv:
                                      self._stream()))
         return result
 
+    def step_observe_records(self, action=None, result=None, spawn_u=None, obs=None):
+        """step_records + the dense observations of the new state in one C-ABI call
+        (msched_step_observe: ONE fused launch for the compile-time domains).  Asynchronous."""
+        action = self.action if action is None else action
+        result = self.result if result is None else result
+        obs = self._obs_buffer() if obs is None else obs
+        su = None
+        if spawn_u is not None:
+            su = torch.as_tensor(spawn_u, dtype=torch.float64).to(self.device).contiguous()
+            self._keep_su = su
+        L.check(self.lib.msched_step_observe(self.handle, action.data_ptr(),
+                                             None if su is None else su.data_ptr(), result.data_ptr(),
+                                             obs.data_ptr(), self._stream()))
+        return result, obs
+
     def step(self, offer_core, acceptor, auctioneer=None, offer_price=None, spawn_kind=None,
-             spawn_u=None):
-        """SchedulingEnv.step(offerActions, acceptorActions, auctioneer_action) over B envs."""
+             spawn_u=None, observe=False):
+        """SchedulingEnv.step(offerActions, acceptorActions, auctioneer_action) over B envs.
+        observe=True also refreshes the observation record (see obs_views)."""
         self.set_actions(offer_core, acceptor, auctioneer, offer_price, spawn_kind)
-        self.step_records(spawn_u=spawn_u)
+        if observe:
+            self.step_observe_records(spawn_u=spawn_u)
+        else:
+            self.step_records(spawn_u=spawn_u)
         return self.rewards()
 
     def step_host(self, action_host, result_host):
@@ -177,29 +204,40 @@ class BatchedSchedulingEnv:
         return out
 
     # ------------------------------------------------------------------ observations
+    def _obs_buffer(self):
+        if self._obs is None:
+            self._obs = torch.zeros((self.layout.padded_envs, self.layout.obs_halfs), dtype=torch.int16,
+                                    device=self.device)
+        return self._obs
+
+    def obs_views(self, obs=None):
+        """int16 strided views into an observation record buffer (default: the env's own, as last
+        written by observe() or step(..., observe=True))."""
+        lay = self.layout
+        B, N, Cc, Lc, NL = self.B, self.N, self.C, self.Lc, self.NL
+        Wd, OH, RA, RO = 3 + 2 * NL, lay.obs_halfs, lay.o_acc_row, lay.o_off_row
+        o = self._obs_buffer() if obs is None else obs
+        return dict(
+            acceptor=o.as_strided((B, N, Cc, Wd), (OH, Cc * RA, RA, 1), lay.o_acceptor),
+            offer=o.as_strided((B, N, Lc, 2 * Cc + 2), (OH, Lc * RO, RO, 1), lay.o_offer),
+            auctioneer=o.as_strided((B, Cc, Wd), (OH, RA, 1), lay.o_auctioneer))
+
     def observe(self, with_ids=False):
         """Dense reference-layout observations (reference src/Agent.py:148-300,
         src/Auctioneer.py:20-77) as int16 strided views into the obs record: acceptor
         [B,N,C,3+2NL], offer [B,N,L,2C+2], auctioneer [B,C,3+2NL]; with_ids adds the offer-ID
         tables ids [B,N,C,NL], auctioneer_ids [B,C,NL] (env.correspondingOfferIDs)."""
         lay = self.layout
-        if self._obs is None:
-            self._obs = torch.zeros((lay.padded_envs, lay.obs_halfs), dtype=torch.int16,
-                                    device=self.device)
+        B, N, Cc, NL = self.B, self.N, self.C, self.NL
+        obs = self._obs_buffer()
         ids = None
         if with_ids:
             if self._ids is None:
                 self._ids = torch.zeros((self.B, lay.ids_halfs), dtype=torch.int16, device=self.device)
             ids = self._ids
-        L.check(self.lib.msched_observe_dense(self.handle, self._obs.data_ptr(),
+        L.check(self.lib.msched_observe_dense(self.handle, obs.data_ptr(),
                                               None if ids is None else ids.data_ptr(), self._stream()))
-        B, N, Cc, Lc, NL = self.B, self.N, self.C, self.Lc, self.NL
-        Wd, OH, RA, RO = 3 + 2 * NL, lay.obs_halfs, lay.o_acc_row, lay.o_off_row
-        o = self._obs
-        out = dict(
-            acceptor=o.as_strided((B, N, Cc, Wd), (OH, Cc * RA, RA, 1), lay.o_acceptor),
-            offer=o.as_strided((B, N, Lc, 2 * Cc + 2), (OH, Lc * RO, RO, 1), lay.o_offer),
-            auctioneer=o.as_strided((B, Cc, Wd), (OH, RA, 1), lay.o_auctioneer))
+        out = self.obs_views()
         if with_ids:
             out["ids"] = ids[:, : N * Cc * NL].view(B, N, Cc, NL)
             out["auctioneer_ids"] = ids[:, N * Cc * NL:].view(B, Cc, NL)

@@ -13,6 +13,7 @@
 #include "policy_kernels.cuh"
 #include "step_kernel.cuh"
 #include "coop_step_kernel.cuh"
+#include "fused_step_kernel.cuh"
 
 using namespace msched;
 
@@ -125,6 +126,10 @@ struct Handle {
     int coopG, coopThreads;
     size_t coopSmem;
     bool useCoop;
+    StepKernel fusedFn;  // compile-time-domain register-resident kernel (step + observations), or null
+    size_t fusedSmem, fusedSmemObs;  // dynamic shared memory without / with the observation tile
+    int fusedRoles;                  // warps per 32-env tile
+    bool useFused, fuseObs;
     ObsKernel obsFn;  // compile-time-domain observation kernel, or null -> direct kernel
     int16_t *stageAction;
     uint32_t *stageResult;
@@ -139,6 +144,22 @@ StepKernel pick_step_kernel(int N, int C, int L)
     if (N == 2 && C == 3 && L == 2) return step_kernel<2, 3, 2>;  // BASELINE cfg1 (trainHC)
     if (N == 2 && C == 2 && L == 3) return step_kernel<2, 2, 3>;  // README 2-agent domain
     return step_kernel<0, 0, 0>;
+}
+
+template <int R>
+StepKernel pick_fused_kernel_r(int N, int C, int L)
+{
+    if (N == 2 && C == 3 && L == 3) return fused_step_kernel<2, 3, 3, R>;  // BASELINE cfg3 (Exp 4-2)
+    if (N == 4 && C == 4 && L == 3) return fused_step_kernel<4, 4, 3, R>;  // BASELINE cfg2 / cfg4
+    if (N == 2 && C == 3 && L == 2) return fused_step_kernel<2, 3, 2, R>;  // BASELINE cfg1 (trainHC)
+    if (N == 2 && C == 2 && L == 3) return fused_step_kernel<2, 2, 3, R>;  // README 2-agent domain
+    return nullptr;
+}
+
+StepKernel pick_fused_kernel(int N, int C, int L, int roles)
+{
+    return roles == 1 ? pick_fused_kernel_r<1>(N, C, L) : roles == 2 ? pick_fused_kernel_r<2>(N, C, L)
+                                                                     : pick_fused_kernel_r<4>(N, C, L);
 }
 
 ObsKernel pick_obs_kernel(int N, int C, int L)
@@ -192,7 +213,9 @@ bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 // launch the step kernel for the env range described by p (p.Bpad padded envs starting at p.state)
 void launch_step(const Handle *h, const DevParams &p, cudaStream_t s)
 {
-    if (h->useCoop) {
+    if (h->useFused) {
+        h->fusedFn<<<p.Bpad / 32, 32 * h->fusedRoles, p.obs ? h->fusedSmemObs : h->fusedSmem, s>>>(p);
+    } else if (h->useCoop) {
         const int E = h->coopThreads / h->coopG;
         h->coopFn<<<p.Bpad / E, h->coopThreads, h->coopSmem, s>>>(p);
     } else {
@@ -283,9 +306,42 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     // (cfg2 at 4,096 envs: 17.6 us vs 22.8 us); large batches of small domains are issue-bound and
     // the lane-per-env kernel executes a third of the instructions (cfg3 at 65,536: 20.7 vs 37 us)
     h->useCoop = h->coopFn && (!h->stepTile || cfg->B <= 8192);
+    // register-resident kernel for the compile-time domains; it also emits the observations when
+    // the observation tile leaves room for enough resident warps (cfg3: 22 KB per 32-env tile)
+    // roles (warps) per 32-env tile: big batches of a small domain fill every SM with one-warp
+    // tiles in a single wave (cfg3 at 65,536 envs: 22.9 us vs 24.6 us with 4 roles); small batches
+    // and bigger domains are bound by one tile's critical path, which 4 roles cut (cfg2 domain at
+    // 65,536 envs: 24.6 us vs 41.8 us)
+    {
+        const size_t obsTile = (size_t)32 * lay.obs_halfs * 2;
+        h->fusedRoles = (cfg->B >= 32768 && obsTile <= 28 * 1024) ? 1 : 4;
+    }
+    if (const char *e = getenv("MSCHED_ROLES")) { const int r = atoi(e); if (r == 1 || r == 2 || r == 4) h->fusedRoles = r; }
+    h->fusedFn = pick_fused_kernel(cfg->N, cfg->C, cfg->L, h->fusedRoles);
+    if (h->fusedFn) {
+        h->fusedSmem = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, 0, cfg->C);
+        h->fusedSmemObs = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, lay.obs_halfs, cfg->C);
+        h->fuseObs = h->fusedSmemObs <= 48 * 1024;  // cfg2 domain: 43.6 KB tile, still one launch fewer
+        if (const char *e = getenv("MSCHED_FUSE_OBS"))
+            h->fuseObs = atoi(e) != 0 && h->fusedSmemObs + 2048 <= (size_t)h->smemOptin;
+        if (h->fusedSmem + 64 > (size_t)h->smemOptin) h->fusedFn = nullptr;
+    }
+    if (h->fusedFn) {
+        CUDA_TRY(cudaFuncSetAttribute(h->fusedFn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(h->fuseObs ? h->fusedSmemObs : h->fusedSmem)));
+        h->useFused = true;
+    }
+    // MSCHED_STEP_IMPL=fused|lane|coop forces one implementation (tests run all of them)
     if (const char *e = getenv("MSCHED_STEP_IMPL")) {
-        if (!strcmp(e, "coop") && h->coopFn) h->useCoop = true;
-        if (!strcmp(e, "lane") && h->stepTile) h->useCoop = false;
+        const bool wantFused = !strcmp(e, "fused"), wantCoop = !strcmp(e, "coop"), wantLane = !strcmp(e, "lane");
+        if ((wantFused && !h->fusedFn) || (wantCoop && !h->coopFn) || (wantLane && !h->stepTile)) {
+            delete h;
+            return fail(MSCHED_E_ARG, "MSCHED_STEP_IMPL: that kernel is not available for this domain");
+        }
+        if (wantFused || wantCoop || wantLane) {
+            h->useFused = wantFused;
+            h->useCoop = wantCoop;
+        }
     }
     h->obsFn = pick_obs_kernel(cfg->N, cfg->C, cfg->L);
     if (h->obsFn && (lay.state_words * 4 > lay.obs_halfs * 2 || 32 * lay.obs_halfs * 2 + 64 > h->smemOptin))
@@ -318,6 +374,39 @@ int msched_destroy(void *handle)
     }
     if (h->evStart) cudaEventDestroy(h->evStart);
     delete h;
+    return MSCHED_OK;
+}
+
+int msched_get_info(void *handle, MschedInfo *out)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !out) return fail(MSCHED_E_ARG, "null handle/out");
+    memset(out, 0, sizeof(*out));
+    if (h->useFused) {
+        out->step_impl = 2;
+        out->fuses_observations = h->fuseObs ? 1 : 0;
+        out->envs_per_cta = 32;
+        out->threads_per_cta = 32 * h->fusedRoles;
+        out->smem_bytes_per_cta = (int)(h->fuseObs ? h->fusedSmemObs : h->fusedSmem);
+    } else if (h->useCoop) {
+        out->step_impl = 1;
+        out->envs_per_cta = h->coopThreads / h->coopG;
+        out->threads_per_cta = h->coopThreads;
+        out->smem_bytes_per_cta = (int)h->coopSmem;
+    } else {
+        out->step_impl = 0;
+        out->envs_per_cta = out->threads_per_cta = h->stepTile;
+        out->smem_bytes_per_cta = (int)((size_t)h->stepTile * ((size_t)h->p.W * 4 + (size_t)h->p.AH * 2 +
+                                                                (size_t)h->p.RW * 4 + (size_t)scratch_words(h->p.C) * 4));
+    }
+    return MSCHED_OK;
+}
+
+int msched_debug_timeline(void *handle, uint64_t *timeline_dev)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(MSCHED_E_ARG, "null handle");
+    h->p.timeline = reinterpret_cast<unsigned long long *>(timeline_dev);
     return MSCHED_OK;
 }
 
@@ -372,6 +461,35 @@ int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_d
     p.action = action_dev;
     p.spawnU = spawn_u_dev;
     p.result = result_dev;
+    p.obs = nullptr;
+    p.round = (int)h->round;
+    p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
+    launch_step(h, p, static_cast<cudaStream_t>(stream));
+    CUDA_TRY(cudaGetLastError());
+    h->round += 1;
+    return MSCHED_OK;
+}
+
+int msched_step_observe(void *handle, const int16_t *action_dev, const double *spawn_u_dev, uint32_t *result_dev,
+                        int16_t *obs_dev, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !obs_dev) return fail(MSCHED_E_ARG, "null handle/obs");
+    if (!aligned16(obs_dev)) return fail(MSCHED_E_ARG, "buffers must be 16-byte aligned");
+    if (!(h->useFused && h->fuseObs)) {
+        int rc = msched_step(handle, action_dev, spawn_u_dev, result_dev, stream);
+        if (rc) return rc;
+        return msched_observe_dense(handle, obs_dev, nullptr, stream);
+    }
+    if (!action_dev || !result_dev) return fail(MSCHED_E_ARG, "null action/result");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    if (!aligned16(action_dev) || !aligned16(result_dev)) return fail(MSCHED_E_ARG, "buffers must be 16-byte aligned");
+    if (h->cfg.spawnMode == MSCHED_SPAWN_U64 && !spawn_u_dev) return fail(MSCHED_E_ARG, "spawn_u required");
+    DevParams p = h->p;
+    p.action = action_dev;
+    p.spawnU = spawn_u_dev;
+    p.result = result_dev;
+    p.obs = obs_dev;
     p.round = (int)h->round;
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     launch_step(h, p, static_cast<cudaStream_t>(stream));
@@ -411,6 +529,7 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
         p.action = h->stageAction + (size_t)e0 * AH;
         p.result = h->stageResult + (size_t)e0 * RW;
         p.spawnU = nullptr;
+        p.obs = nullptr;
         p.envOffset = h->p.envOffset + e0;
         p.round = (int)h->round;
         p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;

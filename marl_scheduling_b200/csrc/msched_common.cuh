@@ -55,6 +55,7 @@ struct DevParams {
     const double *spawnU;
     uint32_t *result;
     int16_t *obs;
+    unsigned long long *timeline;  // diagnostics: 8 x u64 per CTA (smid, clock64 at phase ends), or null
 };
 
 // ---- host+device layout arithmetic ------------------------------------------------------
@@ -167,6 +168,18 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // wait only until the bulk stores have READ their shared-memory source (enough before CTA exit)
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ unsigned smid()
+{
+    unsigned r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned long long globaltimer()
+{
+    unsigned long long r;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(r));
+    return r;
+}
 // make this thread's generic-proxy shared-memory writes visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -195,8 +195,9 @@ __global__ void auctioneer_kernel(const __grid_constant__ DevParams p, int rando
                 k = first;
                 if (randomTies && ncand > 1) {
                     uint32_t x[4];
-                    env_draw(p, env, kStreamTie, (uint32_t)j, 0u, x);
-                    int pick = (int)__umulhi(x[0], (uint32_t)ncand);
+                    env_draw(p, env, kStreamTie, (uint32_t)(j >> 2), 0u, x);  // word j%4 of call j/4
+                    const uint32_t xw = (j & 3) == 0 ? x[0] : (j & 3) == 1 ? x[1] : (j & 3) == 2 ? x[2] : x[3];
+                int pick = (int)__umulhi(xw, (uint32_t)ncand);
                     rank = 0;
                     for (int s = 0; s < NL && pick >= 0; ++s) {
                         const uint32_t w3 = slot[4 * s + 3];

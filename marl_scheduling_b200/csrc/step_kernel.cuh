@@ -195,8 +195,9 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
             const int ncand = (int)(x1 >> 24);
             if (p.auctionMode == MSCHED_AUCTION_RANDOM_MAX && ncand > 1) {
                 uint32_t x[4];
-                env_draw(p, env, kStreamTie, (uint32_t)j, 0u, x);
-                int pick = (int)__umulhi(x[0], (uint32_t)ncand);
+                env_draw(p, env, kStreamTie, (uint32_t)(j >> 2), 0u, x);  // word j%4 of call j/4
+                const uint32_t xw = (j & 3) == 0 ? x[0] : (j & 3) == 1 ? x[1] : (j & 3) == 2 ? x[2] : x[3];
+                int pick = (int)__umulhi(xw, (uint32_t)ncand);
                 if (pick > 0) {
                     const int bn = (int)(int16_t)(x1 & 0xffffu), bd = (int)((x1 >> 16) & 0xffu);
                     int rank = 0;

@@ -427,8 +427,9 @@ static int auctioneerSelectAction(const MsorConfig *cfg, const World *w, int64_t
     int pick = 0;
     if (cfg->tieMode == TIE_PHILOX && ncand > 1) {
         uint32_t x[4];
-        draw(cfg, env, (uint32_t)w->round, STREAM_TIE, (uint32_t)coreIdx, 0, x);
-        pick = (int)(((uint64_t)x[0] * (uint64_t)ncand) >> 32);
+        /* core j uses word j%4 of Philox call j/4 of the tie stream */
+        draw(cfg, env, (uint32_t)w->round, STREAM_TIE, (uint32_t)(coreIdx >> 2), 0, x);
+        pick = (int)(((uint64_t)x[coreIdx & 3] * (uint64_t)ncand) >> 32);
     }
     for (int k = 0; k < NL; ++k)
         if (calculateRewardRatio(obs[3 + 2 * k], obs[4 + 2 * k]) == best) {

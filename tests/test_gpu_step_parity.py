@@ -9,31 +9,51 @@ pytestmark = pytest.mark.gpu
 
 
 def _env(B, meta, impl=None, **kw):
-    """impl: None (library default), "lane" (one lane per env) or "coop" (G lanes per env)."""
+    """impl: None (library default), "lane" (one lane per env), "coop" (G lanes per env) or
+    "fusedR" (compile-time-domain kernel with R = 1, 2 or 4 role warps per 32-env tile)."""
     import os
     from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
     free = meta["mode"].startswith("free")
-    old = os.environ.pop("MSCHED_STEP_IMPL", None)
-    if impl:
+    old = {k: os.environ.pop(k, None) for k in ("MSCHED_STEP_IMPL", "MSCHED_ROLES")}
+    if impl and impl.startswith("fused"):
+        os.environ["MSCHED_STEP_IMPL"] = "fused"
+        os.environ["MSCHED_ROLES"] = impl[5:]
+    elif impl:
         os.environ["MSCHED_STEP_IMPL"] = impl
     try:
-        return BatchedSchedulingEnv(B, world_params_from_dom(meta, free), reward=meta["mode"],
-                                    net_zero_offer_reward=meta.get("netZero", 0.5), **kw)
+        env = BatchedSchedulingEnv(B, world_params_from_dom(meta, free), reward=meta["mode"],
+                                   net_zero_offer_reward=meta.get("netZero", 0.5), **kw)
+        if impl:
+            info = env.info()
+            assert info["step_impl"] == impl[:5].rstrip("124") and (
+                not impl.startswith("fused") or info["threads_per_cta"] == 32 * int(impl[5:])), info
+        return env
     finally:
-        os.environ.pop("MSCHED_STEP_IMPL", None)
-        if old is not None:
-            os.environ["MSCHED_STEP_IMPL"] = old
+        for k, v in old.items():
+            os.environ.pop(k, None)
+            if v is not None:
+                os.environ[k] = v
+
+
+FUSED_DOMAINS = {(2, 3, 3), (4, 4, 3), (2, 3, 2), (2, 2, 3)}  # compile-time kernels in msched_abi.cu
+
+
+def _has_fused(dom):
+    return (dom["N"], dom["C"], dom["L"]) in FUSED_DOMAINS
 
 
 def _one(exp, b):
     return {k: (v[b] if isinstance(v, np.ndarray) else v) for k, v in exp.items()}
 
 
-@pytest.mark.parametrize("impl", ["lane", "coop"])
+@pytest.mark.parametrize("impl", ["lane", "coop", "fused1", "fused2", "fused4"])
 @pytest.mark.parametrize("name", golden_names())
 def test_cuda_replays_reference_trace(name, impl):
     """Recorded reference trace, replicated into B envs that straddle two tiles."""
     tr, meta = load_golden(name)
+    if impl.startswith("fused") and not _has_fused(meta):
+        pytest.skip("no compile-time kernel for this domain")
+    fused = impl.startswith("fused")
     T = tr["done"].shape[0]
     free = meta["mode"].startswith("free")
     agg = meta["mode"] == "agg"
@@ -46,7 +66,7 @@ def test_cuda_replays_reference_trace(name, impl):
     for t in range(T):
         r = env.step(rep(tr["in_offc"][t]), rep(tr["in_acc"][t]), rep(tr["in_auc"][t]),
                      offer_price=rep(tr["in_offp"][t]) if free else None,
-                     spawn_u=rep(tr["in_spawn_u"][t]))
+                     spawn_u=rep(tr["in_spawn_u"][t]), observe=fused)
         e = env.export_state()
         assert (e["flags"] == 0).all(), (name, t)
         for b in (0, 64, 129):
@@ -67,7 +87,11 @@ def test_cuda_replays_reference_trace(name, impl):
                 assert r["quality_sum"][b] / r["quality_cnt"][b] == pytest.approx(
                     float(tr["quality"][t]), rel=1e-12, abs=1e-12)
         if t % 7 == 0 or t == T - 1:
+            of = {k: v.cpu().numpy() for k, v in env.obs_views().items()} if fused else None
             o = {k: v.cpu().numpy() for k, v in env.observe(with_ids=True).items()}
+            if fused:  # the observations the step launch wrote == the stand-alone observe kernel's
+                for k in of:
+                    assert np.array_equal(of[k], o[k]), (name, t, k)
             for b in (0, 129):
                 if meta["agent_kind"] != "aggregated":
                     assert np.array_equal(o["acceptor"][b], tr["obs_acc"][t]), (name, t)
@@ -106,13 +130,16 @@ def random_actions(rng, B, dom, free, p_valid_hint=None):
 DOMS["cfg5"] = (dict(N=32, C=64, L=8, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7]), "fix")
 
 
-@pytest.mark.parametrize("impl", ["lane", "coop"])
+@pytest.mark.parametrize("impl", ["lane", "coop", "fused1", "fused2", "fused4"])
 @pytest.mark.parametrize("key", list(DOMS))
 @pytest.mark.parametrize("auction", ["first", "random"])
 def test_cuda_matches_oracle_random_batch(key, auction, impl):
     """Thousands of envs, device Philox spawn + in-kernel auction, vs the CPU oracle."""
     from oracle import oracle as O
     dom, mode = DOMS[key]
+    if impl.startswith("fused") and not _has_fused(dom):
+        pytest.skip("no compile-time kernel for this domain")
+    fused = impl.startswith("fused")
     free = mode.startswith("free")
     B, T = (1000, 40) if key == "F" else (3000, 60)
     if key == "cfg5":
@@ -126,7 +153,7 @@ def test_cuda_matches_oracle_random_batch(key, auction, impl):
     rng = np.random.default_rng(5)
     for t in range(T):
         offc, acc, offp = random_actions(rng, B, dom, free)
-        r = env.step(offc, acc, None, offer_price=offp)
+        r = env.step(offc, acc, None, offer_price=offp, observe=fused)
         orc.step(offc, acc, None, offp=offp)
         r = {k: (v.cpu().numpy() if v is not None else None) for k, v in r.items()}
         assert np.array_equal(r["auctioneer_idx"], orc.auc_out), (key, t, "auction winners")
@@ -150,7 +177,11 @@ def test_cuda_matches_oracle_random_batch(key, auction, impl):
                 assert e["job_counter"][b] == ob["job_counter"]
             if key == "cfg5":
                 continue  # dense observations are 2.2 MB per env there; the state record is the compact form
+            of = {k: v.cpu().numpy() for k, v in env.obs_views().items()} if fused else None
             o = {k: v.cpu().numpy() for k, v in env.observe(with_ids=True).items()}
+            if fused:
+                for k in of:
+                    assert np.array_equal(of[k], o[k]), (key, t, k)
             for b in rng.integers(0, B, 10):
                 oo = orc.observe(int(b))
                 assert np.array_equal(o["acceptor"][b], oo["obs_acc"])
