@@ -252,6 +252,10 @@ def main():
     ap.add_argument("--config", default="cfg3", choices=list(CONFIGS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
     ap.add_argument("--obs", default="dense", choices=["dense", "none"])
+    ap.add_argument("--l2", default="auto", choices=["auto", "rotate", "flush"],
+                    help="rotate: shards larger than L2 visited round-robin, back-to-back launches; "
+                         "flush: 256 MiB write before every step, per-launch events")
+    ap.add_argument("--sets", type=int, default=0, help="shards for --l2 rotate (default: >= 200 MB in flight)")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (diagnostic)")
     ap.add_argument("--state-warm", type=int, default=1000, help="untimed steps to reach steady state")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -280,69 +284,139 @@ def main():
     dom, mode = cfg["dom"], cfg["mode"]
     B = args.envs or cfg["envs"]
     N = dom["N"]
-    env = BatchedSchedulingEnv(B, world_params_from_dom(dom, mode.startswith("free")), reward=mode,
-                               auction="random", spawn="philox", seed=0, env_offset=rank * B,
-                               net_zero_offer_reward=dom.get("netZero", 0.5), device=local)
-    lay = env.layout
-    ring, gen = make_actions(torch, env, cfg.get("ring", 8), seed=1 + rank)
-    results = [torch.zeros_like(env.result) for _ in range(2)]
-    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     if cfg.get("obs") == "none":
         args.obs = "none"
     dense = args.obs == "dense"
 
-    def one_step(i):
-        refresh_actions(env, ring[i % len(ring)], gen)
-        if dense:
-            env.step_observe_records(ring[i % len(ring)], results[i & 1])
-        else:
-            env.step_records(ring[i % len(ring)], results[i & 1])
+    def make_env(k):
+        return BatchedSchedulingEnv(B, world_params_from_dom(dom, mode.startswith("free")), reward=mode,
+                                    auction="random", spawn="philox", seed=0,
+                                    env_offset=(rank * 64 + k) * B,
+                                    net_zero_offer_reward=dom.get("netZero", 0.5), device=local)
 
-    for i in range(args.state_warm):
-        one_step(i)
-    torch.cuda.synchronize()
-    flags = int(results[(args.state_warm - 1) & 1][:B, lay.r_flags].max().item()) if args.state_warm else 0
-
-    sampler = ClockSampler(local)
-    sampler.start()
-    for i in range(args.warmup):
-        if flush is not None:
-            flush.fill_(i & 0xFF)
-        one_step(i)
-    K = args.steps
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall0 = time.perf_counter()
+    env = make_env(0)
+    lay = env.layout
     info = env.info()
     fused = dense and info["fuses_observations"]
-    for i in range(K):
-        refresh_actions(env, ring[i % len(ring)], gen)
-        if flush is not None:
-            flush.fill_(i & 0xFF)
-        ev[i][0].record()
-        if fused:      # ONE launch: transition + observations of the new state
-            env.step_observe_records(ring[i % len(ring)], results[i & 1])
-            ev[i][1].record()
+    l2 = args.l2
+    if l2 == "auto":  # one launch per step: time back-to-back launches over rotating shards
+        l2 = "rotate" if (fused or not dense) else "flush"
+    if args.no_flush:
+        l2 = "warm"
+    K = args.steps
+    sampler = ClockSampler(local)
+
+    def step_on(e, action, result):
+        if dense:
+            e.step_observe_records(action, result)
         else:
-            env.step_records(ring[i % len(ring)], results[i & 1])
-            ev[i][1].record()
-            if dense:
+            e.step_records(action, result)
+
+    if l2 == "rotate":
+        # ---- inputs larger than L2: S independent shards of B envs each, visited round-robin, so a
+        # shard's records were last touched (S-1) launches ago and (S-1) x its working set has gone
+        # through the 126 MB L2 since.  Launches are back to back on one stream; each timed block
+        # of S*G launches has its own freshly drawn action records (drawn untimed between blocks).
+        per_set = B * (lay.state_words * 4 + lay.action_halfs * 2 + lay.result_words * 4 +
+                       (lay.obs_halfs * 2 if dense else 0))
+        S = args.sets or max(3, -(-200_000_000 // per_set) + 1)
+        G = 4
+        envs = [env] + [make_env(k) for k in range(1, S)]
+        gen = torch.Generator(device=dev).manual_seed(1 + rank)
+        recs = [torch.zeros((lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=dev)
+                for _ in range(S * G)]
+        results = [torch.zeros_like(env.result) for _ in range(S)]
+
+        def run_block(n, timed):
+            for r in recs[:n]:
+                refresh_actions(env, r, gen)
+            if timed is not None:
+                timed[0].record()
+            for i in range(n):
+                step_on(envs[i % S], recs[i], results[i % S])
+            if timed is not None:
+                timed[1].record()
+
+        for _ in range(-(-args.state_warm * S // (S * G))):
+            run_block(S * G, None)
+        torch.cuda.synchronize()
+        flags = max(int(r[:B, lay.r_flags].max().item()) for r in results) if args.state_warm else 0
+        sampler.start()
+        for _ in range(-(-max(args.warmup, 3) // (S * G))):
+            run_block(S * G, None)
+        blocks = [min(S * G, K - b0) for b0 in range(0, K, S * G)]
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in blocks]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_wall0 = time.perf_counter()
+        for n, e in zip(blocks, ev):
+            run_block(n, e)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.finish()
+        tot_ms = sum(e[0].elapsed_time(e[1]) for e in ev)
+        t = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms = stepk_ms = float(t[0])
+        obs_us = None
+        l2_note = (f"inputs larger than L2: {S} shards x {per_set / 1e6:.0f} MB visited round-robin, launches "
+                   f"back to back in blocks of {S * G}")
+        n_launch = K
+    else:
+        ring, gen = make_actions(torch, env, cfg.get("ring", 8), seed=1 + rank)
+        results = [torch.zeros_like(env.result) for _ in range(2)]
+        flush = None if l2 == "warm" else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def one_step(i):
+            refresh_actions(env, ring[i % len(ring)], gen)
+            step_on(env, ring[i % len(ring)], results[i & 1])
+
+        for i in range(args.state_warm):
+            one_step(i)
+        torch.cuda.synchronize()
+        flags = int(results[(args.state_warm - 1) & 1][:B, lay.r_flags].max().item()) if args.state_warm else 0
+        sampler.start()
+        for i in range(max(args.warmup, 3)):
+            if flush is not None:
+                flush.fill_(i & 0xFF)
+            one_step(i)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_wall0 = time.perf_counter()
+        for i in range(K):
+            refresh_actions(env, ring[i % len(ring)], gen)
+            if flush is not None:
+                flush.fill_(i & 0xFF)
+            ev[i][0].record()
+            if fused or not dense:      # ONE launch: transition (+ observations of the new state)
+                step_on(env, ring[i % len(ring)], results[i & 1])
+                ev[i][1].record()
+            else:
+                env.step_records(ring[i % len(ring)], results[i & 1])
+                ev[i][1].record()
                 env.observe()
-        ev[i][2].record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.finish()
-    step_ms = [e[0].elapsed_time(e[1]) for e in ev]
-    obs_ms = [e[1].elapsed_time(e[2]) for e in ev]
-    tot_ms = sum(step_ms) + sum(obs_ms)
-    t = torch.tensor([tot_ms, sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    tot_ms, stepk_ms = float(t[0]), float(t[1])
+            ev[i][2].record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_wall = time.perf_counter() - t_wall0
+        clocks = sampler.finish()
+        step_ms = [e[0].elapsed_time(e[1]) for e in ev]
+        obs_ms = [e[1].elapsed_time(e[2]) for e in ev]
+        tot_ms = sum(step_ms) + sum(obs_ms)
+        t = torch.tensor([tot_ms, sum(step_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        tot_ms, stepk_ms = float(t[0]), float(t[1])
+        obs_us = None if (fused or not dense) else 1e3 * sum(obs_ms) / K
+        l2_note = "warm (no flush)" if l2 == "warm" else "flushed before every timed step (256 MiB write), per-launch events"
+        n_launch = K * (2 if (dense and not fused) else 1)
     value = world * B * N * K / (tot_ms * 1e-3)
 
     # ---- e2e: host records in, host records out, through msched_step_host ----
@@ -351,8 +425,9 @@ def main():
     if nE > 0:
         ah = []
         for _ in range(16):
-            refresh_actions(env, ring[0], gen)
-            ah.append(ring[0][:B].cpu().pin_memory())
+            tmp = torch.zeros((lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=dev)
+            refresh_actions(env, tmp, gen)
+            ah.append(tmp[:B].cpu().pin_memory())
         rh = torch.zeros((B, lay.result_words), dtype=torch.int32).pin_memory()
         for i in range(5):
             env.step_host(ah[i % 16], rh)
@@ -398,20 +473,19 @@ def main():
         "config": {"workload": args.config, "domain": cfg["desc"], "envs_per_gpu": B,
                    "observations": args.obs, "auctioneer": "in-kernel, random arg-max (Philox)",
                    "spawn": "device Philox", "actions": "uniform random, fresh draws every step (untimed)",
-                   "l2": "warm (no flush)" if args.no_flush else "flushed before every timed step (256 MiB write)",
+                   "l2": l2_note,
                    "state_warm_steps": args.state_warm, "step_impl": info["step_impl"],
                    "observations_fused_into_step_launch": bool(fused),
                    "envs_per_cta": info["envs_per_cta"], "smem_bytes_per_cta": info["smem_bytes_per_cta"]},
         "clocks": clocks,
         "e2e": e2e,
-        "gpu_launches": K * (2 if (dense and not fused) else 1),
+        "gpu_launches": n_launch,
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile(args.config, kname),
                      "peak_source": peak_src, "algorithmic_bytes_per_env_step": alg_bytes,
                      "algorithmic_bytes_formula": "2S+a+r" + ("+o (dense observations)" if fused else ""),
                      "units_per_launch": B, "launch_us": step_launch_s * 1e6},
-        "kernels": {"step_us": 1e3 * sum(step_ms) / K,
-                    "observe_us": None if (fused or not dense) else 1e3 * sum(obs_ms) / K,
+        "kernels": {"step_us": 1e3 * stepk_ms / K, "observe_us": obs_us,
                     "observe_algorithmic_bytes_per_env": ab["obs"] + ab["state"]},
         "cpu_baseline": cpu,
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,

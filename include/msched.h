@@ -245,6 +245,8 @@ typedef struct MschedActorIO {
      * [-5,-5,-5,-5] for a == 0, in which case the reported action is -5 (quirk Q1). */
     const int32_t *gather_core;
     int16_t *x_used;         /* optional int16 [M][n_in]: the input actually fed (PPO buffer.states) */
+    uint64_t *timeline;      /* diagnostics (NULL in production): the tensor-core kernel records 8 x uint64
+                                clock64 stamps per CTA for its first tile */
 } MschedActorIO;
 
 int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, void *stream);

@@ -8,31 +8,18 @@
 #include <cstring>
 #include <string>
 
+#include "abi_common.h"
 #include "msched_common.cuh"
 #include "observe_kernel.cuh"
-#include "policy_kernels.cuh"
 #include "step_kernel.cuh"
 #include "coop_step_kernel.cuh"
 #include "fused_step_kernel.cuh"
 
 using namespace msched;
 
+thread_local std::string msched_g_err;
+
 namespace {
-
-thread_local std::string g_err;
-
-int fail(int code, const std::string &msg)
-{
-    g_err = msg;
-    return code;
-}
-
-#define CUDA_TRY(expr)                                                                          \
-    do {                                                                                        \
-        cudaError_t e__ = (expr);                                                               \
-        if (e__ != cudaSuccess)                                                                 \
-            return fail(MSCHED_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));    \
-    } while (0)
 
 int even_odd_half(int halfs)
 {  // even count of int16 whose word count is odd (bank-conflict-free lane stride)
@@ -230,7 +217,7 @@ void launch_step(const Handle *h, const DevParams &p, cudaStream_t s)
 extern "C" {
 
 int msched_abi_version(void) { return MSCHED_ABI_VERSION; }
-const char *msched_last_error(void) { return g_err.c_str(); }
+const char *msched_last_error(void) { return msched_g_err.c_str(); }
 int msched_padded_envs(int B)
 {
     return ((B + MSCHED_TILE_ENVS - 1) / MSCHED_TILE_ENVS) * MSCHED_TILE_ENVS;
@@ -590,45 +577,6 @@ int msched_export_state(void *handle, int env0, int count, int32_t *core, int32_
     if (count == 0) return MSCHED_OK;
     ExportArgs a{env0, count, core, slot, offer, chain, chain_len, misc};
     export_kernel<<<(count + 63) / 64, 64, 0, static_cast<cudaStream_t>(stream)>>>(h->p, a);
-    CUDA_TRY(cudaGetLastError());
-    return MSCHED_OK;
-}
-
-int msched_mlp_param_count(int n_in, int n_hidden, int n_actions)
-{
-    return n_hidden * n_in + n_hidden + n_hidden * n_hidden + n_hidden + n_actions * n_hidden + n_actions;
-}
-
-int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, void *stream)
-{
-    if (!nets || !io || !io->x || !nets->weights) return fail(MSCHED_E_ARG, "null nets/io/x/weights");
-    if (io->n_envs < 0 || io->units < 1 || nets->n_nets < 1)
-        return fail(MSCHED_E_ARG, "bad n_envs/units/n_nets");
-    if (nets->n_in < 1 || nets->n_in > 128 || nets->n_hidden < 8 || nets->n_hidden > 64 ||
-        (nets->n_hidden % 8) != 0 || nets->n_actions < 1)
-        return fail(MSCHED_E_ARG, "unsupported MLP shape (in 1..128, hidden 8..64 multiple of 8)");
-    if (io->gather_core) {
-        if (nets->n_in != 4 || io->n_cores < 1 || io->x_stride < 2 * io->n_cores + 2)
-            return fail(MSCHED_E_ARG, "gather_core needs n_in == 4 and offer observation rows of 2*n_cores+2");
-    } else if (io->x_stride < nets->n_in) {
-        return fail(MSCHED_E_ARG, "x_stride smaller than n_in");
-    }
-    if (io->action_rec && io->action_rec_stride < io->units)
-        return fail(MSCHED_E_ARG, "action_rec_stride smaller than units");
-    if (io->n_envs == 0) return MSCHED_OK;
-    int rc = launch_actor_forward(*nets, *io, static_cast<cudaStream_t>(stream));
-    if (rc == -1) return fail(MSCHED_E_ARG, "unsupported MLP shape for the actor kernel");
-    CUDA_TRY(cudaGetLastError());
-    return MSCHED_OK;
-}
-
-int msched_returns(const float *rewards, int T, int M, double gamma, int normalise, float *out, void *stream)
-{
-    if (!rewards || !out || T < 1 || M < 0) return fail(MSCHED_E_ARG, "bad rewards/out/T/M");
-    if (normalise && T < 2) return fail(MSCHED_E_ARG, "normalisation needs T >= 2");
-    if (M == 0) return MSCHED_OK;
-    returns_kernel<<<(M + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(rewards, T, M, gamma,
-                                                                                   normalise, out);
     CUDA_TRY(cudaGetLastError());
     return MSCHED_OK;
 }

@@ -1,0 +1,62 @@
+// msched_policy.cu -- the policy side of the C-ABI (include/msched.h): actor forward on the tensor
+// cores (or the fp32 SIMT kernel) and the discounted-returns kernel.  No CPU fallback.
+#include <cstdlib>
+#include <cstring>
+
+#include "abi_common.h"
+#include "msched_common.cuh"
+#include "policy_kernels.cuh"
+#include "actor_tc_kernel.cuh"
+#include "actor_tc_wide_kernel.cuh"
+
+using namespace msched;
+
+extern "C" {
+
+int msched_mlp_param_count(int n_in, int n_hidden, int n_actions)
+{
+    return n_hidden * n_in + n_hidden + n_hidden * n_hidden + n_hidden + n_actions * n_hidden + n_actions;
+}
+
+int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, void *stream)
+{
+    if (!nets || !io || !io->x || !nets->weights) return fail(MSCHED_E_ARG, "null nets/io/x/weights");
+    if (io->n_envs < 0 || io->units < 1 || nets->n_nets < 1)
+        return fail(MSCHED_E_ARG, "bad n_envs/units/n_nets");
+    if (nets->n_in < 1 || nets->n_in > 128 || nets->n_hidden < 8 || nets->n_hidden > 64 ||
+        (nets->n_hidden % 8) != 0 || nets->n_actions < 1)
+        return fail(MSCHED_E_ARG, "unsupported MLP shape (in 1..128, hidden 8..64 multiple of 8)");
+    if (io->gather_core) {
+        if (nets->n_in != 4 || io->n_cores < 1 || io->x_stride < 2 * io->n_cores + 2)
+            return fail(MSCHED_E_ARG, "gather_core needs n_in == 4 and offer observation rows of 2*n_cores+2");
+    } else if (io->x_stride < nets->n_in) {
+        return fail(MSCHED_E_ARG, "x_stride smaller than n_in");
+    }
+    if (io->action_rec && io->action_rec_stride < io->units)
+        return fail(MSCHED_E_ARG, "action_rec_stride smaller than units");
+    if (io->n_envs == 0) return MSCHED_OK;
+    // Tensor cores (tcgen05, 3xTF32) where the contraction is wide enough to pay for the operand
+    // staging and the three MMA round trips per tile: hidden width >= 32 or more than 16 actions
+    // (measured on B200, 65,536 envs: 12->32->32->64 net 33.9 us vs 56.8 us SIMT; 15->16->16->7 net
+    // 41 us vs 35 us SIMT).  MSCHED_ACTOR_IMPL=tc|simt forces one.
+    int impl = (nets->n_hidden >= 32 || nets->n_actions > 16) ? 0 : 1;
+    if (const char *e = getenv("MSCHED_ACTOR_IMPL")) impl = !strcmp(e, "simt") ? 1 : (!strcmp(e, "tc") ? 0 : impl);
+    int rc = launch_actor_forward(*nets, *io, impl, static_cast<cudaStream_t>(stream));
+    if (rc == -1) return fail(MSCHED_E_ARG, "unsupported MLP shape for the actor kernel");
+    if (rc == -2) return fail(MSCHED_E_CUDA, "actor kernel: shared-memory attribute rejected");
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+int msched_returns(const float *rewards, int T, int M, double gamma, int normalise, float *out, void *stream)
+{
+    if (!rewards || !out || T < 1 || M < 0) return fail(MSCHED_E_ARG, "bad rewards/out/T/M");
+    if (normalise && T < 2) return fail(MSCHED_E_ARG, "normalisation needs T >= 2");
+    if (M == 0) return MSCHED_OK;
+    returns_kernel<<<(M + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(rewards, T, M, gamma,
+                                                                                   normalise, out);
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+}  // extern "C"

@@ -62,11 +62,85 @@ struct ActorArgs {
     const int32_t *gatherCore;  // FreePriceOfferPPO price chooser: gather the 4 inputs by this action
     int16_t *xUsed;             // [M][nIn] input actually fed, or null
     int nCores;
+    unsigned long long *timeline;  // diagnostics, or null
 };
 
 constexpr int kActorMaxActions = 64;
 
-template <int H>
+// Softmax -> Categorical(probs): sample by inverse CDF, log_prob with torch's renormalisation and
+// clamp to [eps, 1-eps] (src/PPOmodules.py:53-63); one row per thread, logits in registers
+// tanh with 2 MUFU ops: 1 - 2/(e^{2x}+1).  Absolute error < 3e-7 on the whole range (what matters
+// downstream: the activations feed a Linear layer), exact limits for |x| -> inf, tanh(0) = 0
+__device__ __forceinline__ float fast_tanh(float x)
+{
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));  // e^{2x}
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
+    return fmaf(-2.f, r, 1.f);
+}
+
+// lg[o] must be -inf for o >= A (the callers pad the last layer's bias with -inf), so every sweep
+// runs unpredicated over the AP registers
+template <int AP>
+__device__ __forceinline__ void actor_epilogue(const ActorArgs &a, float (&lg)[AP], int A, long long row, int env,
+                                               int unit, int gsel)
+{
+    float mx = lg[0];
+#pragma unroll
+    for (int o = 1; o < AP; ++o) mx = fmaxf(mx, lg[o]);
+    float sum = 0.f;
+#pragma unroll
+    for (int o = 0; o < AP; ++o) { lg[o] = __expf(lg[o] - mx); sum += lg[o]; }
+    const float inv = 1.f / sum;
+    float tot = 0.f;  // Categorical(probs) renormalises by the sum of the softmax output
+#pragma unroll
+    for (int o = 0; o < AP; ++o) { lg[o] *= inv; tot += lg[o]; }
+    if (a.probs) {
+#pragma unroll
+        for (int o = 0; o < AP; ++o)
+            if (o < A) a.probs[(size_t)row * A + o] = lg[o];
+    }
+    if (!a.action && !a.logprob && !a.actionRec) return;
+    float u;
+    if (a.uOverride) {
+        u = a.uOverride[row];
+    } else {
+        const unsigned long long g = (unsigned long long)(a.rowOffset + row);
+        uint32_t x4[4];
+        philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)a.step,
+                      (kStreamPolicy << 28) | (uint32_t)((a.step >> 32) & 0x0fffffffu), (uint32_t)a.seed,
+                      (uint32_t)(a.seed >> 32), x4);
+        u = (float)(x4[0] >> 8) * (1.0f / 16777216.0f);
+    }
+    // inverse CDF: the first action whose cumulative probability exceeds u * total; padded entries
+    // add 0 and can never be the first to exceed
+    const float thr = u * tot;
+    float cdf = 0.f, pa = 0.f;
+    int act = -1;
+#pragma unroll
+    for (int o = 0; o < AP; ++o) {
+        cdf += lg[o];
+        const bool hit = act < 0 && cdf > thr;
+        act = hit ? o : act;
+        pa = hit ? lg[o] : pa;
+    }
+    if (act < 0) {  // u * total rounded up to the total: the last action
+        act = A - 1;
+#pragma unroll
+        for (int o = 0; o < AP; ++o) pa = (o == A - 1) ? lg[o] : pa;
+    }
+    if (a.action) a.action[row] = act;  // what PPO.selectAction stores in buffer.actions
+    if (a.actionRec)                    // what the world is handed (price -5 next to core action 0)
+        a.actionRec[(size_t)env * a.actionRecStride + unit] = (int16_t)((a.gatherCore && gsel == 0) ? -5 : act);
+    if (a.logprob) {
+        const float eps = 1.1920928955078125e-07f;
+        float pn = pa / tot;
+        pn = fminf(fmaxf(pn, eps), 1.f - eps);
+        a.logprob[row] = logf(pn);
+    }
+}
+
+template <int H, int AP>
 __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
 {
     extern __shared__ __align__(16) float sw[];
@@ -88,7 +162,7 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
     for (int i = threadIdx.x; i < H * Apad; i += blockDim.x) W3t[i] = 0.f;
     __syncthreads();
     for (int i = threadIdx.x; i < A * H; i += blockDim.x) W3t[(i % H) * Apad + i / H] = w3[i];
-    for (int i = threadIdx.x; i < Apad; i += blockDim.x) b3[i] = i < A ? w3[A * H + i] : 0.f;
+    for (int i = threadIdx.x; i < Apad; i += blockDim.x) b3[i] = i < A ? w3[A * H + i] : -INFINITY;
     __syncthreads();
 
     const int env = blockIdx.x * blockDim.x + threadIdx.x;
@@ -116,20 +190,33 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
     float h1[H], h2[H];
 #pragma unroll
     for (int o = 0; o < H; ++o) h1[o] = b1[o];
-    for (int k = 0; k < nIn; ++k) {
-        const float xv = a.gatherCore ? (float)g4[k & 3] : (float)xr[k];
-        const float4 *wr = reinterpret_cast<const float4 *>(W1t + k * H);
+    // inputs in batches of 16: the loads of a batch are issued together (one memory round trip
+    // per 16 inputs instead of one per input)
+    for (int k0 = 0; k0 < nIn; k0 += 16) {
+        float xb[16];
 #pragma unroll
-        for (int o4 = 0; o4 < H / 4; ++o4) {
-            const float4 wv = wr[o4];
-            h1[4 * o4 + 0] = fmaf(wv.x, xv, h1[4 * o4 + 0]);
-            h1[4 * o4 + 1] = fmaf(wv.y, xv, h1[4 * o4 + 1]);
-            h1[4 * o4 + 2] = fmaf(wv.z, xv, h1[4 * o4 + 2]);
-            h1[4 * o4 + 3] = fmaf(wv.w, xv, h1[4 * o4 + 3]);
+        for (int q = 0; q < 16; ++q) {
+            const int k = k0 + q;
+            xb[q] = k < nIn ? (a.gatherCore ? (float)g4[k & 3] : (float)xr[k]) : 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            if (k0 + q < nIn) {
+                const float xv = xb[q];
+                const float4 *wr = reinterpret_cast<const float4 *>(W1t + (k0 + q) * H);
+#pragma unroll
+                for (int o4 = 0; o4 < H / 4; ++o4) {
+                    const float4 wv = wr[o4];
+                    h1[4 * o4 + 0] = fmaf(wv.x, xv, h1[4 * o4 + 0]);
+                    h1[4 * o4 + 1] = fmaf(wv.y, xv, h1[4 * o4 + 1]);
+                    h1[4 * o4 + 2] = fmaf(wv.z, xv, h1[4 * o4 + 2]);
+                    h1[4 * o4 + 3] = fmaf(wv.w, xv, h1[4 * o4 + 3]);
+                }
+            }
         }
     }
 #pragma unroll
-    for (int o = 0; o < H; ++o) { h1[o] = tanhf(h1[o]); h2[o] = b2[o]; }
+    for (int o = 0; o < H; ++o) { h1[o] = fast_tanh(h1[o]); h2[o] = b2[o]; }
 #pragma unroll
     for (int k = 0; k < H; ++k) {
         const float xv = h1[k];
@@ -144,14 +231,13 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
         }
     }
 #pragma unroll
-    for (int o = 0; o < H; ++o) h2[o] = tanhf(h2[o]);
+    for (int o = 0; o < H; ++o) h2[o] = fast_tanh(h2[o]);
 
-    float lg[kActorMaxActions];
+    float lg[AP];
 #pragma unroll
-    for (int o = 0; o < kActorMaxActions; ++o) lg[o] = 0.f;
-    float mx = -INFINITY;
+    for (int o = 0; o < AP; ++o) lg[o] = -INFINITY;
 #pragma unroll
-    for (int o4 = 0; o4 < kActorMaxActions / 4; ++o4) {
+    for (int o4 = 0; o4 < AP / 4; ++o4) {
         if (4 * o4 < A) {
             float4 acc = *reinterpret_cast<const float4 *>(b3 + 4 * o4);
 #pragma unroll
@@ -165,78 +251,7 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
             lg[4 * o4 + 0] = acc.x; lg[4 * o4 + 1] = acc.y; lg[4 * o4 + 2] = acc.z; lg[4 * o4 + 3] = acc.w;
         }
     }
-#pragma unroll
-    for (int o = 0; o < kActorMaxActions; ++o)
-        if (o < A) mx = fmaxf(mx, lg[o]);
-    float sum = 0.f;
-#pragma unroll
-    for (int o = 0; o < kActorMaxActions; ++o)
-        if (o < A) { lg[o] = expf(lg[o] - mx); sum += lg[o]; }
-    float tot = 0.f;  // Categorical(probs) renormalises by the sum of the softmax output
-#pragma unroll
-    for (int o = 0; o < kActorMaxActions; ++o)
-        if (o < A) { lg[o] = lg[o] / sum; tot += lg[o]; }
-    if (a.probs)
-        for (int o = 0; o < A; ++o) a.probs[(size_t)row * A + o] = lg[o];
-    if (!a.action && !a.logprob && !a.actionRec) return;
-    float u;
-    if (a.uOverride) {
-        u = a.uOverride[row];
-    } else {
-        const unsigned long long g = (unsigned long long)(a.rowOffset + row);
-        uint32_t x4[4];
-        philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)a.step,
-                      (kStreamPolicy << 28) | (uint32_t)((a.step >> 32) & 0x0fffffffu), (uint32_t)a.seed,
-                      (uint32_t)(a.seed >> 32), x4);
-        u = (float)(x4[0] >> 8) * (1.0f / 16777216.0f);
-    }
-    const float thr = u * tot;
-    float cdf = 0.f, pa = 0.f;
-    int act = A - 1;
-    bool found = false;
-#pragma unroll
-    for (int o = 0; o < kActorMaxActions; ++o)
-        if (o < A) {
-            cdf += lg[o];
-            if (!found && cdf > thr) { act = o; pa = lg[o]; found = true; }
-        }
-    if (!found) {
-#pragma unroll
-        for (int o = 0; o < kActorMaxActions; ++o)
-            if (o == A - 1) pa = lg[o];
-    }
-    if (a.action) a.action[row] = act;  // what PPO.selectAction stores in buffer.actions
-    if (a.actionRec)                    // what the world is handed (price -5 next to core action 0)
-        a.actionRec[(size_t)env * a.actionRecStride + unit] = (int16_t)((a.gatherCore && gsel == 0) ? -5 : act);
-    if (a.logprob) {
-        const float eps = 1.1920928955078125e-07f;
-        float pn = pa / tot;
-        pn = fminf(fmaxf(pn, eps), 1.f - eps);
-        a.logprob[row] = logf(pn);
-    }
-}
-
-inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io, cudaStream_t s)
-{
-    if (g.n_actions > kActorMaxActions) return -1;
-    ActorArgs a;
-    a.weights = g.weights; a.x = io.x;
-    a.envStride = io.env_stride ? io.env_stride : (long long)io.x_stride * io.units; a.unitStride = io.x_stride;
-    a.nIn = g.n_in; a.nHidden = g.n_hidden; a.nActions = g.n_actions; a.nNets = g.n_nets;
-    a.unitDiv = g.unit_div > 0 ? g.unit_div : 1;
-    a.units = io.units; a.nEnvs = io.n_envs;
-    a.seed = io.seed; a.step = io.step; a.rowOffset = io.row_offset; a.uOverride = io.u_override;
-    a.action = io.action; a.logprob = io.logprob; a.probs = io.probs;
-    a.actionRec = io.action_rec; a.actionRecStride = io.action_rec_stride;
-    a.gatherCore = io.gather_core; a.xUsed = io.x_used; a.nCores = io.n_cores;
-    const int H = g.n_hidden, Apad = (g.n_actions + 3) & ~3;
-    const size_t smem = sizeof(float) * ((size_t)g.n_in * H + H + (size_t)H * H + H + (size_t)H * Apad + Apad);
-    dim3 grid((a.nEnvs + 127) / 128, io.units);
-    if (H == 16) actor_forward_simt<16><<<grid, 128, smem, s>>>(a);
-    else if (H == 32) actor_forward_simt<32><<<grid, 128, smem, s>>>(a);
-    else if (H == 64) actor_forward_simt<64><<<grid, 128, smem, s>>>(a);
-    else return -1;
-    return 0;
+    actor_epilogue(a, lg, A, row, env, unit, gsel);
 }
 
 }  // namespace msched

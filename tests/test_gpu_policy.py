@@ -8,11 +8,19 @@ import pytest
 from helpers import GOLDEN
 
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(params=["tc", "simt"])
+def actor_impl(request, monkeypatch):
+    """Both actor kernels: tcgen05 tensor cores (3xTF32) and fp32 SIMT."""
+    monkeypatch.setenv("MSCHED_ACTOR_IMPL", request.param)
+    return request.param
+
 TAGS = dict(acc_cfg3=(15, 7, 16), off_cfg3=(8, 4, 16), price_cfg3=(4, 9, 16), acc_cfg2=(27, 13, 16),
             off_cfg2=(10, 5, 16), aggoff=(12, 64, 32))
 
 
-def test_actor_forward_matches_torch_reference():
+def test_actor_forward_matches_torch_reference(actor_impl):
     import torch
     from marl_scheduling_b200 import policy
     z = np.load(os.path.join(GOLDEN, "torch_vectors.npz"))
@@ -36,7 +44,7 @@ def test_actor_forward_matches_torch_reference():
         np.testing.assert_allclose(lp.cpu().numpy()[sure], z[tag + ".logprob"][sure], rtol=1e-4, atol=2e-5)
 
 
-def test_actor_forward_grouped_nets_and_strides_match_oracle():
+def test_actor_forward_grouped_nets_and_strides_match_oracle(actor_impl):
     import torch
     from marl_scheduling_b200 import policy
     from oracle import oracle as O
@@ -66,7 +74,7 @@ def test_actor_forward_grouped_nets_and_strides_match_oracle():
         np.testing.assert_allclose(lp[n::units][sure], l[sure], rtol=1e-4, atol=2e-5)
 
 
-def test_actor_sampling_is_distributionally_correct():
+def test_actor_sampling_is_distributionally_correct(actor_impl):
     import torch
     from marl_scheduling_b200 import policy
     dev = torch.device("cuda", 0)
@@ -102,7 +110,7 @@ def test_returns_match_reference_and_oracle():
     np.testing.assert_allclose(raw[:-1] - 0.5 * raw[1:], r[:-1], rtol=0, atol=2e-5)
 
 
-def test_price_chooser_gather_and_action_record():
+def test_price_chooser_gather_and_action_record(actor_impl):
     """FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): the price chooser sees
     [obs[2a], obs[2a+1], obs[-2], obs[-1]] of the core chooser's action a, the dummy [-5]*4 and a
     reported price of -5 for a == 0; the kernel also writes the reported action into the action
@@ -143,3 +151,53 @@ def test_price_chooser_gather_and_action_record():
     r = rec.cpu().numpy()
     assert (r[:, :10] == 77).all() and (r[:, 10 + units:] == 77).all()
     assert np.array_equal(r[:, 10:10 + units], np.where(core == 0, -5, act))
+
+
+@pytest.mark.parametrize("shape", [(45, 32, 343, 2), (12, 32, 64, 2), (40, 64, 1323, 1), (30, 16, 130, 3)])
+def test_aggregated_head_matches_fp32_reference(shape):
+    """Aggregated action heads (src/PPOmodules.py:177-232): the tensor-core kernel tiles the last
+    layer over the actions and never materialises the logits; probabilities, the inverse-CDF
+    sample and the log-prob are compared with a float64 evaluation of the same net."""
+    import torch
+    from marl_scheduling_b200 import policy
+    nin, h, A, units = shape
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(21)
+    n_envs = 333
+    grp = policy.MlpGroup.random(nin, h, A, units, dev, seed=31)
+    xs = rng.integers(-2, 12, (n_envs, units * nin)).astype(np.int16)
+    u = rng.random(n_envs * units).astype(np.float32)
+    act, lp, pr = policy.actor_forward(grp, torch.as_tensor(xs).to(dev), nin, units, n_envs, u=u, want_probs=True)
+    act, lp, pr = act.cpu().numpy(), lp.cpu().numpy(), pr.cpu().numpy()
+    w = grp.weights.cpu().numpy().astype(np.float64)
+    for n in range(units):
+        o, ws = 0, []
+        for sz in (h * nin, h, h * h, h, A * h, A):
+            ws.append(w[n, o:o + sz]); o += sz
+        x = xs[:, n * nin:(n + 1) * nin].astype(np.float64)
+        h1 = np.tanh(x @ ws[0].reshape(h, nin).T + ws[1])
+        h2 = np.tanh(h1 @ ws[2].reshape(h, h).T + ws[3])
+        lg = h2 @ ws[4].reshape(A, h).T + ws[5]
+        p = np.exp(lg - lg.max(1, keepdims=True)); p /= p.sum(1, keepdims=True)
+        np.testing.assert_allclose(pr[n::units], p, rtol=5e-5, atol=1e-9)
+        cdf = np.cumsum(p, 1)
+        thr = u[n::units].astype(np.float64)[:, None]
+        a_ref = (cdf > thr).argmax(1)
+        margin = np.abs(cdf - thr).min(1)
+        sure = margin > 1e-5
+        assert sure.mean() > 0.9
+        assert np.array_equal(act[n::units][sure], a_ref[sure])
+        np.testing.assert_allclose(lp[n::units][sure], np.log(p[np.arange(n_envs), a_ref])[sure], rtol=1e-4, atol=5e-5)
+
+
+def test_aggregated_head_sampling_distribution():
+    import torch
+    from marl_scheduling_b200 import policy
+    dev = torch.device("cuda", 0)
+    grp = policy.MlpGroup.random(12, 32, 200, 1, dev, seed=5)
+    x = torch.ones((100000, 12), dtype=torch.int16, device=dev)
+    act, lp, pr = policy.actor_forward(grp, x, 12, 1, 100000, seed=3, step=1, want_probs=True)
+    p = pr[0].cpu().numpy()
+    freq = np.bincount(act.cpu().numpy(), minlength=200) / 100000
+    assert np.abs(freq - p).max() < 5e-3
+    assert abs(float(lp.exp().mean().cpu()) - float((p * p).sum())) < 2e-3   # E[p(a)] = sum p^2
