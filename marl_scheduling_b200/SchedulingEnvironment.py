@@ -48,11 +48,14 @@ class SchedulingEnv(object):
         self._last = None
 
     # -- reference API -------------------------------------------------------------------------
+    def _format_obs(self, o):
+        """(acceptorObs, offerObs, auctioneerObs) as the agents of this environment consume them."""
+        return o["acceptor"], o["offer"], o["auctioneer"]
+
     def reset(self):
         """Like the reference (src/SchedulingEnvironment.py:85-109) this resets NOTHING: it only
         re-gathers the observations of the current state."""
-        o = self.core.observe()
-        return o["acceptor"], o["offer"], o["auctioneer"]
+        return self._format_obs(self.core.observe())
 
     def step(self, offerActions, acceptorActions, auctioneer_action=None):
         c = self.core
@@ -79,7 +82,7 @@ class SchedulingEnv(object):
         done = (c.round % self.world.episodeLength) == 0
         if self.reward == "fix":  # src/Reward.py:193
             self.terminationRevenues = self.terminationRevenues + self._termination_revenue(r)
-        return (o["acceptor"], o["offer"], o["auctioneer"], offerRewards, acceptorRewards,
+        return (*self._format_obs(o), offerRewards, acceptorRewards,
                 auctioneerReward, agentReward, (mean, cnt), done)
 
     def getRewards(self):
@@ -195,23 +198,42 @@ class LocallySharedParamsDividedFixedPriceEnv(PPOSchedulingEnv):
 
 
 class PPOAggregatedFixPriceEnv(PPOSchedulingEnv):
-    """src/SchedulingEnvironment.py:213-228 (getAggregatedFixedPricesReward).  The environment
-    side (step, rewards, semi-aggregated observation views) is complete; the aggregated action
-    heads ((NL+1)^C-way softmax) are not built yet -- see DESIGN.md "out of scope this round"."""
+    """src/SchedulingEnvironment.py:213-228 (getAggregatedFixedPricesReward): semi-aggregated agents.
+    reset/step return the aggregated observations of src/Agent.py:82-140: acceptor int16
+    [B,N,C*(3+2NL)] (float32 in the reference), offer int16 [B,N,2C+2L], auctioneer [B,C,3+2NL]."""
     REWARD = "agg"
 
-    def aggregatedObservations(self):
-        """src/Agent.py:82-140: acceptor float32 [B,N,C*(3+2NL)], offer int16 [B,N,2C+2L]."""
-        o = self.core.observe()
+    def __init__(self, world, params, agents=True):
+        super().__init__(world, params)
+        if agents:
+            from .agents import AggregatedFixPricePPOAgents
+            self._attach(AggregatedFixPricePPOAgents(world, self))
+
+    def _aggregate(self, o):
         B, N, C, L = self.core.B, self.core.N, self.core.C, self.core.Lc
-        acc = o["acceptor"].reshape(B, N, -1).float()
+        acc = o["acceptor"].reshape(B, N, -1)
         cores = o["offer"][:, :, 0, : 2 * C]
         slots = o["offer"][:, :, :, 2 * C:].reshape(B, N, 2 * L)
         return acc, torch.cat([cores, slots], dim=2)
 
+    def _format_obs(self, o):
+        acc, off = self._aggregate(o)
+        return acc, off, o["auctioneer"]
+
+    def aggregatedObservations(self):
+        """(acceptor float32 [B,N,C*(3+2NL)], offer int16 [B,N,2C+2L]) of the current state."""
+        acc, off = self._aggregate(self.core.observe())
+        return acc.float(), off
+
 
 class PPOFullyAggregatedFixPriceEnv(PPOAggregatedFixPriceEnv):
     """src/SchedulingEnvironment.py:231-250."""
+
+    def __init__(self, world, params, agents=True):
+        super().__init__(world, params, agents=False)
+        if agents:
+            from .agents import FullyAggregatedFixPricePPOAgents
+            self._attach(FullyAggregatedFixPricePPOAgents(world, self))
 
     def fullyAggregatedObservations(self):
         acc, off = self.aggregatedObservations()

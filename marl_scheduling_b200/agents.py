@@ -241,3 +241,84 @@ class DividedFreePricePPOAgents:
         for ppo in (self.acceptor, self.core, self.price):
             ppo.update()
             ppo.sync_old_and_clear()
+
+
+def _digits(number, base, dimensionality):
+    """numberToNDimensionalAction (src/Agent.py:644-666) for tensors: digit k = (n // base**k) % base,
+    index 0 = least significant."""
+    return torch.stack([(number // (base ** k)) % base for k in range(dimensionality)], dim=-1)
+
+
+class AggregatedFixPricePPOAgents:
+    """All N agents of src/Agent.py:359-390 (semi-aggregated): per agent one AggregatedAcceptorPPO
+    (in C(3+2NL), (NL+1)^C actions, 32 neurons) and one AggregatedOfferPPO (in 2C+2L, (C+1)^L actions)
+    (src/PPOmodules.py:177-211).  The heads run on the tensor cores (msched_actor_forward tiles the last
+    layer over the actions); the aggregated action number is decoded into the per-core / per-slot
+    actions the world consumes."""
+
+    def __init__(self, world, env):
+        self.world, self.env = world, env
+        N, C, L = world.numberOfAgents, world.numberOfCores, world.collectionLength
+        NL = N * L
+        dev = env.core.device
+        if (NL + 1) ** C > 32767 or (C + 1) ** L > 32767:
+            raise ValueError("aggregated action space too large (more than 32,767 actions per unit)")
+        a = dict(lr_actor=env.LR_ACTOR, lr_critic=env.LR_CRITIC, eps_clip=env.EPS_CLIP, device=dev)
+        self.acceptor = BatchedPPO(C * (3 + 2 * NL), (NL + 1) ** C, 32, N, N, 1, gamma=env.ACCEPTOR_GAMMA,
+                                   k_epochs=env.ACCEPTOR_K_EPOCHS, seed=1, **a)
+        self.offer = BatchedPPO(2 * C + 2 * L, (C + 1) ** L, 32, N, N, 1, gamma=env.OFFER_GAMMA,
+                                k_epochs=env.OFFER_K_EPOCHS, seed=2, **a)
+
+    def getActions(self, offerObs, acceptorObs):
+        """offerObs int16 [B,N,2C+2L], acceptorObs int16 [B,N,C(3+2NL)] (env.aggregatedObservations)."""
+        c = self.env.core
+        B, N, C, L = c.B, c.N, c.C, c.Lc
+        seed = self.world.seed
+        acc = self.acceptor.selectAction(acceptorObs.contiguous(), acceptorObs.shape[-1], 0, B, seed * 2)
+        off = self.offer.selectAction(offerObs.contiguous(), offerObs.shape[-1], 0, B, seed * 2 + 1)
+        nd_acc = _digits(acc.long(), c.NL + 1, C)      # [B,N,C]
+        nd_off = _digits(off.long(), C + 1, L)         # [B,N,L]
+        return nd_acc, nd_off
+
+    def saveRewards(self, offerUnitRewards, acceptorUnitRewards, agentReward):
+        # src/SchedulingEnvironment.py:223-225, src/Agent.py:388-390
+        self.acceptor.saveReward(agentReward)
+        self.offer.saveReward(offerUnitRewards[..., 0])
+
+    def updateParts(self):
+        for ppo in (self.acceptor, self.offer):
+            ppo.update()
+            ppo.sync_old_and_clear()
+
+
+class FullyAggregatedFixPricePPOAgents:
+    """src/Agent.py:393-492: one FullyAggregatedPPO per agent (64 neurons) on
+    cat(offerObs, acceptorObs); action = acceptor number * (C+1)^L + offer number."""
+
+    def __init__(self, world, env):
+        self.world, self.env = world, env
+        N, C, L = world.numberOfAgents, world.numberOfCores, world.collectionLength
+        NL = N * L
+        self.divisor = (C + 1) ** L
+        n_actions = ((NL + 1) ** C) * self.divisor
+        if n_actions > 32767:
+            raise ValueError("fully aggregated action space too large (more than 32,767 actions)")
+        self.unit = BatchedPPO(C * (3 + 2 * NL) + 2 * C + 2 * L, n_actions, 64, N, N, 1, env.LR_ACTOR,
+                               env.LR_CRITIC, env.ACCEPTOR_GAMMA, env.EPS_CLIP, env.ACCEPTOR_K_EPOCHS,
+                               env.core.device, seed=1)
+
+    def getActions(self, offerObs, acceptorObs):
+        c = self.env.core
+        x = torch.cat([offerObs, acceptorObs], dim=-1).contiguous()   # src/Agent.py:463-467
+        n = self.unit.selectAction(x, x.shape[-1], 0, c.B, self.world.seed).long()
+        nd_acc = _digits(n // self.divisor, c.NL + 1, c.C)
+        nd_off = _digits(n % self.divisor, c.C + 1, c.Lc)
+        return nd_acc, nd_off
+
+    def saveRewards(self, offerUnitRewards, acceptorUnitRewards, agentReward):
+        # src/SchedulingEnvironment.py:243-247: agentReward[i] + offerUnitRewards[i][0]
+        self.unit.saveReward(agentReward.float() + offerUnitRewards[..., 0].float())
+
+    def updateParts(self):
+        self.unit.update()
+        self.unit.sync_old_and_clear()

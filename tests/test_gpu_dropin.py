@@ -122,7 +122,7 @@ def test_aggregated_env_views_match_oracle():
     dom = dict(N=2, C=2, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7])
     wp = dict(WP, numberOfAgents=2, numberOfCores=2, numberOfEnvironments=B, seed=3)
     world = World(wp)
-    env = SE.PPOFullyAggregatedFixPriceEnv(world, RL)
+    env = SE.PPOFullyAggregatedFixPriceEnv(world, RL, agents=False)
     orc = O.Oracle(B, dom, "agg", tie_mode=O.TIE_PHILOX, seed=3)
     rng = np.random.default_rng(1)
     for t in range(15):
@@ -140,4 +140,41 @@ def test_aggregated_env_views_match_oracle():
     slots = o["obs_off"][:, :, 4:].reshape(2, 6)
     assert np.array_equal(offA[5].cpu().numpy(), np.concatenate([cores, slots], 1))
     assert full.shape == (B, 2, 10 + 2 * 15)
+    env.close()
+
+
+@pytest.mark.parametrize("kind", ["semi", "fully"])
+def test_aggregated_ppo_env_rollout_and_update(kind):
+    """Semi- / fully-aggregated agents (src/Agent.py:359-492) on the README 2-agent domain: the
+    aggregated heads (49 / 27 / 1,323 actions) run in the tensor-core actor kernel, the action
+    number decodes to per-core / per-slot actions, the log-probs match a torch forward."""
+    import torch
+    from marl_scheduling_b200 import SchedulingEnvironment as SE
+    from marl_scheduling_b200.world import World
+    B = 40
+    wp = dict(WP, numberOfAgents=2, numberOfCores=2, numberOfEnvironments=B, seed=4)
+    world = World(wp)
+    env = (SE.PPOAggregatedFixPriceEnv if kind == "semi" else SE.PPOFullyAggregatedFixPriceEnv)(world, RL)
+    accO, offO, aucO = env.reset()
+    assert accO.shape == (B, 2, 2 * 15) and offO.shape == (B, 2, 4 + 6) and aucO.shape == (B, 2, 15)
+    for t in range(10):
+        acceptorActions, offerActions = env.getActionForAllAgents(accO, offO)
+        assert acceptorActions.shape == (B, 2, 2) and offerActions.shape == (B, 2, 3)
+        assert int(acceptorActions.max()) <= 6 and int(offerActions.max()) <= 2
+        aa = world.auctioneer.getAuctioneerAction(aucO)
+        accO, offO, aucO, offR, accR, aucR, agR, q, done = env.step(offerActions, acceptorActions, aa)
+        assert offR.shape == (B, 2, 1) and accR.shape == (B, 2, 1)
+        env.saveRewards(offR, accR, agR)
+        assert int(q[1].max()) >= 0
+    ppo = env.agents.acceptor if kind == "semi" else env.agents.unit
+    X = torch.stack(ppo.buf_x).float()
+    T = X.shape[0]
+    logits = ppo._forward(ppo.policy_old.weights, X.permute(2, 0, 1, 3).reshape(ppo.units, T * B, -1), ppo.A)
+    lp = torch.log_softmax(logits, -1).gather(-1, torch.stack(ppo.buf_a).long().permute(2, 0, 1).reshape(
+        ppo.units, T * B, 1)).squeeze(-1)
+    lp_k = torch.stack(ppo.buf_lp).permute(2, 0, 1).reshape(ppo.units, T * B)
+    assert torch.allclose(lp, lp_k, rtol=1e-4, atol=1e-4)
+    before = ppo.actor.detach().clone()
+    env.updateAgents()
+    assert not torch.equal(before, ppo.actor.detach()) and torch.isfinite(ppo.actor).all()
     env.close()
