@@ -261,6 +261,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--rollout-steps", type=int, default=200,
+                    help="steps of the secondary metric (env step + actor forward); 0 = skip")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -430,22 +432,81 @@ def main():
             ah.append(tmp[:B].cpu().pin_memory())
         rh = torch.zeros((B, lay.result_words), dtype=torch.int32).pin_memory()
         for i in range(5):
-            env.step_host(ah[i % 16], rh)
+            env.step_host(ah[i % 16], rh, observe=dense)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(nE):
-            env.step_host(ah[i % 16], rh)
-            if dense:
-                env.observe()  # observations stay on the device for the policy kernels
+            env.step_host(ah[i % 16], rh, observe=dense)  # observations stay on the device for the policy kernels
         torch.cuda.synchronize()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": world * B * N * nE / float(te[0]), "unit": "agent-steps/s",
                "h2d_bytes_per_step": B * lay.action_halfs * 2, "d2h_bytes_per_step": B * lay.result_words * 4,
-               "steps": nE, "api": "msched_step_host (pinned action records -> result records)"}
+               "steps": nE, "api": "msched_step_host (pinned action records -> result records; observations stay on the device)"}
+
+    # ---- secondary metric: the same step INCLUDING the batched actor forward of the
+    # divided PPO agents (one net per unit, src/Agent.py:495-619) and, separately, the return scan ----
+    rollout = None
+    if args.rollout_steps > 0 and dense and world == 1:
+        from marl_scheduling_b200 import policy
+        free = mode.startswith("free")
+        Cc, Lc, NL = dom["C"], dom["L"], N * dom["L"]
+        P = max(dom["prios"])
+        acc_net = policy.MlpGroup.random(3 + 2 * NL, 16, NL + 1, N * Cc, dev, seed=1)
+        off_net = policy.MlpGroup.random(2 * Cc + 2, 16, Cc + 1, NL, dev, seed=2)
+        price_net = policy.MlpGroup.random(4, 16, P + 1, NL, dev, seed=3) if free else None
+        ov = env.obs_views()
+        a_act = torch.empty(B * N * Cc, dtype=torch.int32, device=dev)
+        a_lp = torch.empty(B * N * Cc, dtype=torch.float32, device=dev)
+        o_act = torch.empty(B * NL, dtype=torch.int32, device=dev)
+        o_lp = torch.empty(B * NL, dtype=torch.float32, device=dev)
+        p_act, p_lp = torch.empty_like(o_act), torch.empty_like(o_lp)
+        res_r = torch.zeros_like(env.result)
+
+        def rollout_step(i):
+            policy.actor_forward(off_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=2, step=i,
+                                 action=o_act, logprob=o_lp, action_rec=env.offer_core_actions,
+                                 action_rec_stride=lay.action_halfs)
+            if free:
+                policy.actor_forward(price_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=3,
+                                     step=i, action=p_act, logprob=p_lp, action_rec=env.offer_price_actions,
+                                     action_rec_stride=lay.action_halfs, gather_core=o_act, n_cores=Cc)
+            policy.actor_forward(acc_net, ov["acceptor"], lay.o_acc_row, N * Cc, B, env_stride=lay.obs_halfs, seed=1,
+                                 step=i, action=a_act, logprob=a_lp, action_rec=env.acceptor_actions,
+                                 action_rec_stride=lay.action_halfs)
+            env.step_observe_records(env.action, res_r)
+
+        for i in range(20):
+            rollout_step(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.rollout_steps):
+            rollout_step(20 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        r_ms = e0.elapsed_time(e1) / args.rollout_steps
+        T = 200
+        rew = torch.randn(T, B * N * Cc, device=dev)
+        for _ in range(2):
+            policy.returns(rew, 0.8733, True)
+        e0.record()
+        for _ in range(5):
+            policy.returns(rew, 0.8733, True)
+        e1.record()
+        torch.cuda.synchronize()
+        ret_us = e0.elapsed_time(e1) * 1e3 / 5
+        rollout = {"value": B * N / (r_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": r_ms,
+                   "steps": args.rollout_steps, "launches_per_step": 4 if free else 3,
+                   "what": "actor forward of every divided PPO unit (offer/core chooser"
+                           + (", price chooser" if free else "") + ", acceptor: sample + log-prob, actions "
+                           "written into the action record) + fused env step + observations, one shard, L2 warm",
+                   "returns_kernel": {"T": T, "units": B * N * Cc, "us": ret_us,
+                                      "gbs": 12.0 * rew.numel() / ret_us / 1e3,
+                                      "algorithmic_bytes_per_element": 12}}
 
     if rank != 0:
         if world > 1:
@@ -488,6 +549,7 @@ def main():
         "kernels": {"step_us": 1e3 * stepk_ms / K, "observe_us": obs_us,
                     "observe_algorithmic_bytes_per_env": ab["obs"] + ab["state"]},
         "cpu_baseline": cpu,
+        "rollout_with_policy": rollout,
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
         "sticky_flags_after_warm": flags,
     }

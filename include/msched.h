@@ -178,9 +178,12 @@ int msched_step_observe(void *handle, const int16_t *action_dev, const double *s
                         uint32_t *result_dev, int16_t *obs_dev, void *stream);
 
 /* same call with HOST buffers (pinned recommended): H2D of the action records, the step, D2H of
- * the result records, then stream synchronise.  staging buffers are owned by the handle. */
+ * the result records, then stream synchronise.  The batch is cut into chunks that alternate between
+ * two internal streams so the copies of one chunk overlap the kernel of another.  obs_dev (DEVICE,
+ * optional): the dense observations of the new state stay on the device for the policy kernels
+ * (written by the same launch when the domain fuses them).  Staging buffers are owned by the handle. */
 int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_host,
-                     void *stream);
+                     int16_t *obs_dev, void *stream);
 
 /* Agent.gatherObservations + gatherDividedAuctioneerObservation (src/Agent.py:148-300,
  * src/Auctioneer.py:20-77): dense reference-layout observations; ids_dev (optional, may be

@@ -87,7 +87,7 @@ SYMBOLS = {
     "msched_set_round": (C.c_int, [P, C.c_int64]),
     "msched_step": (C.c_int, [P, P, P, P, P]),
     "msched_step_observe": (C.c_int, [P, P, P, P, P, P]),
-    "msched_step_host": (C.c_int, [P, P, P, P]),
+    "msched_step_host": (C.c_int, [P, P, P, P, P]),
     "msched_observe_dense": (C.c_int, [P, P, P, P]),
     "msched_auctioneer_action": (C.c_int, [P, C.c_int, P, P]),
     "msched_export_state": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, P]),

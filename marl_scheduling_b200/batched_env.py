@@ -172,10 +172,11 @@ class BatchedSchedulingEnv:
             self.step_records(spawn_u=spawn_u)
         return self.rewards()
 
-    def step_host(self, action_host, result_host):
-        """The C-ABI call with HOST buffers (pinned int16 / int32 tensors): H2D, step, D2H, sync."""
-        L.check(self.lib.msched_step_host(self.handle, action_host.data_ptr(),
-                                          result_host.data_ptr(), self._stream()))
+    def step_host(self, action_host, result_host, observe=False):
+        """The C-ABI call with HOST buffers (pinned int16 / int32 tensors): H2D, step, D2H, sync.
+        observe=True also refreshes the device-resident observation record (see obs_views)."""
+        L.check(self.lib.msched_step_host(self.handle, action_host.data_ptr(), result_host.data_ptr(),
+                                          self._obs_buffer().data_ptr() if observe else None, self._stream()))
         return result_host
 
     # ------------------------------------------------------------------ result record views

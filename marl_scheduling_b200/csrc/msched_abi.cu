@@ -485,14 +485,16 @@ int msched_step_observe(void *handle, const int16_t *action_dev, const double *s
     return MSCHED_OK;
 }
 
-int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_host, void *stream)
+int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_host, int16_t *obs_dev, void *stream)
 {
     Handle *h = static_cast<Handle *>(handle);
     if (!h || !action_host || !result_host) return fail(MSCHED_E_ARG, "null handle/action/result");
     if (h->cfg.spawnMode == MSCHED_SPAWN_U64) return fail(MSCHED_E_ARG, "step_host does not take recorded draws");
     if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    if (obs_dev && !aligned16(obs_dev)) return fail(MSCHED_E_ARG, "buffers must be 16-byte aligned");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(h->device));
+    const bool fuse = obs_dev && h->useFused && h->fuseObs;
     // The batch is cut into chunks (multiples of the 128-env padding unit) that alternate between
     // two internal streams, so the H2D copy of one chunk, the kernel of another and the D2H copy of
     // a third overlap (PCIe is full duplex); environments are independent, so any split is exact.
@@ -516,7 +518,7 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
         p.action = h->stageAction + (size_t)e0 * AH;
         p.result = h->stageResult + (size_t)e0 * RW;
         p.spawnU = nullptr;
-        p.obs = nullptr;
+        p.obs = fuse ? obs_dev + (size_t)e0 * h->lay.obs_halfs : nullptr;
         p.envOffset = h->p.envOffset + e0;
         p.round = (int)h->round;
         p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
@@ -530,6 +532,10 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
         CUDA_TRY(cudaStreamWaitEvent(s, h->evDone[k], 0));
     }
     h->round += 1;
+    if (obs_dev && !fuse) {  // two-launch domains: the observation kernel follows on the caller's stream
+        int rc = msched_observe_dense(handle, obs_dev, nullptr, stream);
+        if (rc) return rc;
+    }
     CUDA_TRY(cudaStreamSynchronize(s));
     return MSCHED_OK;
 }

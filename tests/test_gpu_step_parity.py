@@ -225,7 +225,11 @@ def test_step_host_matches_device_step():
         offc, acc, offp = random_actions(rng, B, dom, True)
         a.step(offc, acc, None, offer_price=offp)
         ah.copy_(a.action[:B].cpu())
-        b.step_host(ah, rh)
+        b.step_host(ah, rh, observe=(t % 2 == 0))
         assert torch.equal(rh, a.result[:B].cpu())
+        if t % 2 == 0:
+            oa, ob = a.observe(), b.obs_views()
+            for k in oa:
+                assert torch.equal(oa[k], ob[k]), (t, k)
     assert a.round == b.round == 20
     a.close(); b.close()
