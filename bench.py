@@ -3,19 +3,20 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg3|cfg2]
 
-One "step" = one pass of the hot path over one batch of environments: the step kernel
-(acceptances, in-kernel auction + core allocation, progress/completion, offer creation, Philox
-spawn, rewards) followed by the dense observation kernel, i.e. one SchedulingEnv.step for every
-environment.  Workload at N=1: BASELINE.json configs[2] ("cfg3": N=2 C=3 L=3, three job kinds,
+One "step" = one pass of the hot path over one batch of environments: ONE launch of the fused
+kernel (acceptances, in-kernel auction + core allocation, progress/completion, offer creation,
+Philox spawn, rewards, dense observations of the new state), i.e. one SchedulingEnv.step for
+every environment.  Workload at N=1: BASELINE.json configs[2] ("cfg3": N=2 C=3 L=3, three job kinds,
 free prices, commercial reward, hard-coded auctioneer) at 65,536 environments -- the
 configuration the metric is quoted on.  Each extra GPU adds its own 65,536-env shard (weak
 scaling, no data-path collective).
 
-Timing: every step is bracketed by CUDA events on the launching stream; the L2 (126 MB) is
-flushed before every timed step by overwriting a 256 MiB buffer, so the state/action records are
-read from HBM.  `value` = units processed / sum of the per-step device times (max over ranks).
-`e2e` goes through msched_step_host: pinned host action records -> H2D -> step -> D2H of the
-result records -> sync, wall-clock timed.
+Timing: inputs larger than L2 -- several independent 65,536-env shards are visited round-robin, so
+a shard's records come from HBM; launches are back to back on the launching stream, timed with
+CUDA events in blocks (fresh action records are drawn, untimed, between blocks).  `--l2 flush` is
+the per-launch protocol (256 MiB write before every step).  `value` = units processed / sum of
+the block times (max over ranks).  `e2e` goes through msched_step_host: pinned host action
+records -> H2D -> step -> D2H of the result records -> sync, wall-clock timed.
 """
 from __future__ import annotations
 
@@ -226,7 +227,7 @@ def run_reference(args, cfg):
     res = cpu_baseline_sample(cfg, seconds=min(60.0, max(5.0, 0.01 * K)), threads=threads, envs=1024)
     dom = cfg["dom"]
     line = {
-        "impl": "reference", "metric": "agent-steps/sec, batched env step+auction",
+        "impl": "reference", "metric": "agent-steps/sec, batched env step+auction @65,536 envs",
         "value": res["value"], "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / res["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
