@@ -257,6 +257,8 @@ def main():
                     help="rotate: shards larger than L2 visited round-robin, back-to-back launches; "
                          "flush: 256 MiB write before every step, per-launch events")
     ap.add_argument("--sets", type=int, default=0, help="shards for --l2 rotate (default: >= 200 MB in flight)")
+    ap.add_argument("--streams", type=int, default=3,
+                    help="streams the independent shards alternate between in --l2 rotate (1 = strictly serial launches)")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (diagnostic)")
     ap.add_argument("--state-warm", type=int, default=1000, help="untimed steps to reach steady state")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -323,22 +325,38 @@ def main():
         per_set = B * (lay.state_words * 4 + lay.action_halfs * 2 + lay.result_words * 4 +
                        (lay.obs_halfs * 2 if dense else 0))
         S = args.sets or max(3, -(-200_000_000 // per_set) + 1)
-        G = 4
+        G = 8
         envs = [env] + [make_env(k) for k in range(1, S)]
         gen = torch.Generator(device=dev).manual_seed(1 + rank)
         recs = [torch.zeros((lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=dev)
                 for _ in range(S * G)]
         results = [torch.zeros_like(env.result) for _ in range(S)]
 
+        # independent shards alternate between two streams (shard k always on stream k % 2, so a
+        # shard's launches stay ordered): the first CTAs of one launch fill the SMs that the tail
+        # of the previous launch has already left.  A block is timed on the default stream, which
+        # the two streams fork from and join back into.
+        streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)]
+        main = torch.cuda.current_stream(dev)
+
         def run_block(n, timed):
             for r in recs[:n]:
                 refresh_actions(env, r, gen)
             if timed is not None:
-                timed[0].record()
+                timed[0].record(main)
+            fork = torch.cuda.Event()
+            fork.record(main)
+            for st in streams:
+                st.wait_event(fork)
             for i in range(n):
-                step_on(envs[i % S], recs[i], results[i % S])
+                with torch.cuda.stream(streams[(i % S) % len(streams)]):
+                    step_on(envs[i % S], recs[i], results[i % S])
+            for st in streams:
+                join = torch.cuda.Event()
+                join.record(st)
+                main.wait_event(join)
             if timed is not None:
-                timed[1].record()
+                timed[1].record(main)
 
         for _ in range(-(-args.state_warm * S // (S * G))):
             run_block(S * G, None)
@@ -367,7 +385,7 @@ def main():
         tot_ms = stepk_ms = float(t[0])
         obs_us = None
         l2_note = (f"inputs larger than L2: {S} shards x {per_set / 1e6:.0f} MB visited round-robin, launches "
-                   f"back to back in blocks of {S * G}")
+                   f"back to back in blocks of {S * G} on {len(streams)} stream(s)")
         n_launch = K
     else:
         ring, gen = make_actions(torch, env, cfg.get("ring", 8), seed=1 + rank)

@@ -60,6 +60,27 @@ inline size_t fused_smem_bytes(int stateWords, int actionHalfs, int resultWords,
     return (size_t)32 * 4 * (work > obs ? work : obs);  // the observation tile overlays the work tiles
 }
 
+// integer accumulation into the tile: several role warps may touch one word (exact, order-free
+// atomics); a one-warp tile owns its words
+template <int R>
+__device__ __forceinline__ void acc_add(int *p, int v)
+{
+    if (R == 1) *p += v;
+    else atomicAdd(p, v);
+}
+template <int R>
+__device__ __forceinline__ void acc_or(uint32_t *p, uint32_t v)
+{
+    if (R == 1) *p |= v;
+    else atomicOr(p, v);
+}
+template <int R>
+__device__ __forceinline__ void acc_and(uint32_t *p, uint32_t v)
+{
+    if (R == 1) *p &= v;
+    else atomicAnd(p, v);
+}
+
 template <int N, int C, int L, int R>
 __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constant__ DevParams p)
 {
@@ -69,7 +90,8 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
     static_assert(C <= 8 && NL <= 64, "packed per-core counters / unrolled sweeps");
     extern __shared__ __align__(128) uint32_t sm[];
     __shared__ __align__(8) uint64_t bar;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int w = R == 1 ? 0 : (int)(threadIdx.x >> 5);  // compile-time for the one-warp tile: every role test folds
     const int env0 = blockIdx.x * 32, env = env0 + lane;
     const int AW = p.AH >> 1, RW = p.RW;
     const bool withObs = p.obs != nullptr;
@@ -162,7 +184,7 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
 #pragma unroll
             for (int a = 0; a < N; ++a) bad |= (unsigned)(int)act[p.aAcc + a * C + j] > (unsigned)NL;
             if (external) bad |= (unsigned)(int)act[p.aAuc + j] > (unsigned)NL;
-            if (bad) atomicOr(&st[1], MSCHED_FLAG_ACTION_RANGE);
+            if (bad) acc_or<R>(&st[1], MSCHED_FLAG_ACTION_RANGE);
 
             int k = -1;
             if (o > 0) k = act[p.aAcc + (o - 1) * C + j];
@@ -301,7 +323,7 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
             }
             ++nAcc;
         }
-        if (flags) atomicOr(&st[1], flags);
+        if (flags) acc_or<R>(&st[1], flags);
     }
     __syncthreads();
 
@@ -321,11 +343,11 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
                     const int R_ = p.mult * p.prio[kind];
                     const int o = core_owner(c0) - 1;
                     if (agg) {
-                        atomicAdd(&resi[p.rAcc + o], R_);
-                        atomicAdd(&resi[p.rAgent + o], R_);
+                        acc_add<R>(&resi[p.rAcc + o], R_);
+                        acc_add<R>(&resi[p.rAgent + o], R_);
                     } else {
-                        atomicAdd(&resi[p.rAcc + o * C + j], R_);  // the only "=" into this word
-                        if (!freeM) atomicAdd(&resi[p.rAgent + o], R_);
+                        acc_add<R>(&resi[p.rAcc + o * C + j], R_);  // the only "=" into this word
+                        if (!freeM) acc_add<R>(&resi[p.rAgent + o], R_);
                     }
                     const uint32_t cw = chlS[j >> 2];
                     const int len = (int)((cw >> ((j & 3) * 8)) & 0xffu);
@@ -344,21 +366,21 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
                         const int time = (int)((en.y >> 16) & 0xffu);
                         const int offerer = (int)(en.y >> 24);
                         const int traded = traded_reward(price, time, (round + 1) - (int)en.x);
-                        atomicSub(&resi[p.rAgent + offerer - 1], traded);
+                        acc_add<R>(&resi[p.rAgent + offerer - 1], -traded);
                         if (agg) {
-                            atomicSub(&resi[p.rAcc + offerer - 1], traded);
-                            if (recip > 0) atomicAdd(&resi[p.rAgent + recip - 1], traded);
+                            acc_add<R>(&resi[p.rAcc + offerer - 1], -traded);
+                            if (recip > 0) acc_add<R>(&resi[p.rAgent + recip - 1], traded);
                         } else {
-                            atomicSub(&resi[p.rAcc + (offerer - 1) * C + j], traded);
+                            acc_add<R>(&resi[p.rAcc + (offerer - 1) * C + j], -traded);
                             if (recip > 0) {
-                                atomicAdd(&resi[p.rAcc + (recip - 1) * C + j], traded);
-                                atomicAdd(&resi[p.rAgent + recip - 1], traded);
+                                acc_add<R>(&resi[p.rAcc + (recip - 1) * C + j], traded);
+                                acc_add<R>(&resi[p.rAgent + recip - 1], traded);
                             }
                         }
                         if (recip == 0) resi[p.rAuc + j] = traded;
                         recip = offerer;
                     }
-                    atomicAnd(&chlS[j >> 2], ~(0xffu << ((j & 3) * 8)));
+                    acc_and<R>(&chlS[j >> 2], ~(0xffu << ((j & 3) * 8)));
                     core[3 * j] = kEmptyJobW0;
                     core[3 * j + 1] = kEmptyId;
                     core[3 * j + 2] = kEmptyId;
@@ -417,7 +439,7 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
             }
             if (!mine) continue;
             uint32_t jobctr = st[0] + before;
-            atomicAdd(&scr[D::X_NSPAWN], (uint32_t)p.newJobs);
+            acc_add<R>(reinterpret_cast<int *>(&scr[D::X_NSPAWN]), p.newJobs);
             uint32_t rnd[4] = {scr[D::X_SPAWN], scr[D::X_SPAWN + 1], scr[D::X_SPAWN + 2], scr[D::X_SPAWN + 3]};
             int rndCall = 0;
             for (int k = 0; k < p.newJobs; ++k) {
@@ -425,9 +447,10 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
                 if (p.spawnMode == MSCHED_SPAWN_KINDS) {
                     kind = act[p.aSpawn + a * p.newJobs + k];
                 } else {
-                    double u;
                     if (p.spawnMode == MSCHED_SPAWN_U64) {
-                        u = p.spawnU[((size_t)env * N + a) * p.newJobs + k];
+                        const double u = p.spawnU[((size_t)env * N + a) * p.newJobs + k];
+                        for (int q = 0; q < p.J; ++q)
+                            if (u < p.cum[q]) { kind = q; break; }
                     } else {
                         const int dnum = a * p.newJobs + k;  // draw d uses word d%4 of Philox call d/4
                         if ((dnum >> 2) != rndCall) {
@@ -435,12 +458,13 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
                             env_draw(p, env, kStreamSpawn, (uint32_t)rndCall, 0u, rnd);
                         }
                         const uint32_t xr = (dnum & 3) == 0 ? rnd[0] : (dnum & 3) == 1 ? rnd[1] : (dnum & 3) == 2 ? rnd[2] : rnd[3];
-                        u = (double)xr * (1.0 / 4294967296.0);
+                        // first kind with u = xr * 2^-32 < cum[kind], decided exactly in integers
+                        int cnt = 0;
+                        for (int q = 0; q < p.J; ++q) cnt += ((unsigned long long)xr >= p.cumThr[q]) ? 1 : 0;
+                        kind = cnt < p.J ? cnt : -1;
                     }
-                    for (int q = 0; q < p.J; ++q)
-                        if (u < p.cum[q]) { kind = q; break; }
                 }
-                if (kind < 0 || kind >= p.J) { atomicOr(&st[1], MSCHED_FLAG_SPAWN_RANGE); kind = p.J - 1; }
+                if (kind < 0 || kind >= p.J) { acc_or<R>(&st[1], MSCHED_FLAG_SPAWN_RANGE); kind = p.J - 1; }
                 int q = 0;
 #pragma unroll
                 for (int t = L - 1; t >= 0; --t)

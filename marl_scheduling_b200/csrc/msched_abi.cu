@@ -3,6 +3,7 @@
 // point returns MSCHED_E_NODEVICE.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -177,6 +178,12 @@ void fill_params(Handle *h)
     p.rAucIdx = l.r_auctioneer_idx; p.RL = l.RL; p.RC = l.RC;
     for (int k = 0; k < MSCHED_MAX_KINDS; ++k) {
         p.prio[k] = c.prio[k]; p.len[k] = c.len[k]; p.fix[k] = c.fixPrice[k]; p.cum[k] = c.cumProb[k];
+        {
+            double t = ceil(c.cumProb[k] * 4294967296.0);
+            if (!(t > 0.0)) t = 0.0;
+            if (t > 4294967296.0) t = 4294967296.0;
+            p.cumThr[k] = (unsigned long long)t;
+        }
     }
     p.netZero = (float)c.netZeroOfferReward;
     p.seed = c.seed;

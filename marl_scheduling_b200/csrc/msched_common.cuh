@@ -42,6 +42,7 @@ struct DevParams {
     // per-kind tables
     int prio[kMaxKinds], len[kMaxKinds], fix[kMaxKinds];
     double cum[kMaxKinds];
+    unsigned long long cumThr[kMaxKinds];  // ceil(cum * 2^32): u = x * 2^-32 < cum  <=>  x < cumThr (exact)
     float netZero;
     // dynamic
     int round;
