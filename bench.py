@@ -485,29 +485,64 @@ def main():
         p_act, p_lp = torch.empty_like(o_act), torch.empty_like(o_lp)
         res_r = torch.zeros_like(env.result)
 
-        def rollout_step(i):
-            policy.actor_forward(off_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=2, step=i,
-                                 action=o_act, logprob=o_lp, action_rec=env.offer_core_actions,
-                                 action_rec_stride=lay.action_halfs)
-            if free:
-                policy.actor_forward(price_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=3,
-                                     step=i, action=p_act, logprob=p_lp, action_rec=env.offer_price_actions,
-                                     action_rec_stride=lay.action_halfs, gather_core=o_act, n_cores=Cc)
-            policy.actor_forward(acc_net, ov["acceptor"], lay.o_acc_row, N * Cc, B, env_stride=lay.obs_halfs, seed=1,
-                                 step=i, action=a_act, logprob=a_lp, action_rec=env.acceptor_actions,
-                                 action_rec_stride=lay.action_halfs)
-            env.step_observe_records(env.action, res_r)
+        # the acceptor units and the offer units are independent: they run on two side streams and
+        # join before the env step (the price chooser follows the core chooser on its stream).  The
+        # whole step is captured ONCE in a CUDA graph and replayed: world.round and the policy's
+        # Philox step live in device counters (msched_set_round_mode, MschedActorIO.step_dev)
+        side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        step_t = torch.zeros(1, dtype=torch.int64, device=dev)
+        env.set_device_round(True)
 
+        def rollout_step():
+            cur = torch.cuda.current_stream(dev)
+            fork = torch.cuda.Event()
+            fork.record(cur)
+            with torch.cuda.stream(side[0]):
+                side[0].wait_event(fork)
+                policy.actor_forward(off_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=2,
+                                     step_dev=step_t, action=o_act, logprob=o_lp, action_rec=env.offer_core_actions,
+                                     action_rec_stride=lay.action_halfs)
+                if free:
+                    policy.actor_forward(price_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs,
+                                         seed=3, step_dev=step_t, action=p_act, logprob=p_lp,
+                                         action_rec=env.offer_price_actions, action_rec_stride=lay.action_halfs,
+                                         gather_core=o_act, n_cores=Cc)
+                j0 = torch.cuda.Event()
+                j0.record(side[0])
+            with torch.cuda.stream(side[1]):
+                side[1].wait_event(fork)
+                policy.actor_forward(acc_net, ov["acceptor"], lay.o_acc_row, N * Cc, B, env_stride=lay.obs_halfs,
+                                     seed=1, step_dev=step_t, action=a_act, logprob=a_lp,
+                                     action_rec=env.acceptor_actions, action_rec_stride=lay.action_halfs)
+                j1 = torch.cuda.Event()
+                j1.record(side[1])
+            cur.wait_event(j0)
+            cur.wait_event(j1)
+            env.step_observe_records(env.action, res_r)
+            step_t.add_(1)
+
+        for i in range(5):
+            rollout_step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(graph, stream=cap):
+                rollout_step()
+        torch.cuda.current_stream(dev).wait_stream(cap)
         for i in range(20):
-            rollout_step(i)
+            graph.replay()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(args.rollout_steps):
-            rollout_step(20 + i)
+            graph.replay()
         e1.record()
         torch.cuda.synchronize()
         r_ms = e0.elapsed_time(e1) / args.rollout_steps
+        rflags = int(res_r[:B, lay.r_flags].max().item())
+        env.set_device_round(False)
         T = 200
         rew = torch.randn(T, B * N * Cc, device=dev)
         for _ in range(2):
@@ -522,7 +557,8 @@ def main():
                    "steps": args.rollout_steps, "launches_per_step": 4 if free else 3,
                    "what": "actor forward of every divided PPO unit (offer/core chooser"
                            + (", price chooser" if free else "") + ", acceptor: sample + log-prob, actions "
-                           "written into the action record) + fused env step + observations, one shard, L2 warm",
+                           "written into the action record; acceptor and offer units on two streams) + fused env step + observations; one shard, L2 warm, the step captured in a CUDA graph and replayed",
+                   "sticky_flags": rflags,
                    "returns_kernel": {"T": T, "units": B * N * Cc, "us": ret_us,
                                       "gbs": 12.0 * rew.numel() / ret_us / 1e3,
                                       "algorithmic_bytes_per_element": 12}}

@@ -160,6 +160,10 @@ int msched_bind_state(void *handle, void *state_dev, void *chain_dev);
 int msched_reset(void *handle, void *stream);
 int msched_get_round(void *handle, int64_t *round);
 int msched_set_round(void *handle, int64_t round);
+/* CUDA-graph support: with device_side != 0 world.round lives in a device counter that every step
+ * launch reads and a one-thread kernel advances, so a captured step can be replayed (the kernel
+ * arguments no longer change from step to step).  msched_get_round then synchronises the device. */
+int msched_set_round_mode(void *handle, int device_side, void *stream);
 
 /* One SchedulingEnv.step for every env (src/SchedulingEnvironment.py:32-83 =
  * World.step1 src/world.py:295-334 + acception quality :174-192 + Reward.py + done),
@@ -250,6 +254,8 @@ typedef struct MschedActorIO {
     int16_t *x_used;         /* optional int16 [M][n_in]: the input actually fed (PPO buffer.states) */
     uint64_t *timeline;      /* diagnostics (NULL in production): the tensor-core kernel records 8 x uint64
                                 clock64 stamps per CTA for its first tile */
+    const uint64_t *step_dev; /* optional DEVICE step counter read instead of `step` (the caller advances
+                                it, e.g. inside a CUDA graph that replays the rollout step) */
 } MschedActorIO;
 
 int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, void *stream);

@@ -67,7 +67,7 @@ class MschedActorIO(C.Structure):
                 ("row_offset", C.c_int64), ("seed", C.c_uint64), ("step", C.c_uint64),
                 ("u_override", C.c_void_p), ("action", C.c_void_p), ("logprob", C.c_void_p),
                 ("probs", C.c_void_p), ("action_rec", C.c_void_p), ("action_rec_stride", C.c_int64),
-                ("gather_core", C.c_void_p), ("x_used", C.c_void_p), ("timeline", C.c_void_p)]
+                ("gather_core", C.c_void_p), ("x_used", C.c_void_p), ("timeline", C.c_void_p), ("step_dev", C.c_void_p)]
 
 
 # every symbol include/msched.h declares: name -> (restype, argtypes)
@@ -85,6 +85,7 @@ SYMBOLS = {
     "msched_reset": (C.c_int, [P, P]),
     "msched_get_round": (C.c_int, [P, C.POINTER(C.c_int64)]),
     "msched_set_round": (C.c_int, [P, C.c_int64]),
+    "msched_set_round_mode": (C.c_int, [P, C.c_int, P]),
     "msched_step": (C.c_int, [P, P, P, P, P]),
     "msched_step_observe": (C.c_int, [P, P, P, P, P, P]),
     "msched_step_host": (C.c_int, [P, P, P, P, P]),

@@ -84,6 +84,11 @@ class BatchedSchedulingEnv:
         L.check(self.lib.msched_get_round(self.handle, C.byref(r)))
         return int(r.value)
 
+    def set_device_round(self, enable=True):
+        """world.round in a device counter (advanced by a one-thread kernel after every step), so
+        that a captured step can be replayed from a CUDA graph."""
+        L.check(self.lib.msched_set_round_mode(self.handle, int(bool(enable)), self._stream()))
+
     def reset(self):
         """Fresh worlds (World.__init__, reference src/world.py:210-254)."""
         L.check(self.lib.msched_reset(self.handle, self._stream()))

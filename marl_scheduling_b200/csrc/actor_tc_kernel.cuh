@@ -98,13 +98,13 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 
 // stage an [n_real][k_real] torch weight matrix as hi / lo B operands ([Npad][Kpad], zero padded)
 __device__ __forceinline__ void stage_weight(const float *__restrict__ w, int n_real, int k_real, int Npad, int Kpad,
-                                             unsigned char *dstHi, unsigned char *dstLo)
+                                             unsigned char *dstHi, unsigned char *dstLo, float scale = 1.f)
 {
     const int panel = Npad * 16;  // bytes of one K chunk (4 floats) of all rows
 #pragma unroll 4
     for (int i = threadIdx.x; i < Npad * Kpad; i += blockDim.x) {
         const int n = i / Kpad, k = i - n * Kpad;
-        const float v = (n < n_real && k < k_real) ? w[n * k_real + k] : 0.f;
+        const float v = (n < n_real && k < k_real) ? w[n * k_real + k] * scale : 0.f;
         const float hi = tf32_hi(v);
         const int off = (k >> 2) * panel + n * 16 + (k & 3) * 4;
         *reinterpret_cast<float *>(dstHi + off) = hi;
@@ -266,9 +266,9 @@ __global__ void __launch_bounds__(128) actor_forward_tc(const ActorArgs a)
     const float *w2 = w + H * nIn + H, *w3 = w2 + H * H + H;
     stage_weight(w, H, nIn, H, L.Kc1 * 4, smc + L.w1, smc + L.w1 + L.Kc1 * H * 16);
     stage_weight(w2, H, H, H, H, smc + L.w2, smc + L.w2 + L.Kc * H * 16);
-    stage_weight(w3, A, H, Apad, H, smc + L.w3, smc + L.w3 + L.Kc * Apad * 16);
+    stage_weight(w3, A, H, Apad, H, smc + L.w3, smc + L.w3 + L.Kc * Apad * 16, kLog2e);  // base-2 logits
     for (int i = tid; i < H; i += 128) { bia[i] = w[H * nIn + i]; bia[H + i] = w2[H * H + i]; }
-    for (int i = tid; i < Apad; i += 128) bia[2 * H + i] = i < A ? w3[A * H + i] : -INFINITY;  // padded logits
+    for (int i = tid; i < Apad; i += 128) bia[2 * H + i] = i < A ? w3[A * H + i] * kLog2e : -INFINITY;  // padded logits
 
     fence_async_smem();
     tc_fence_before();

@@ -15,6 +15,8 @@
 // are conflict-free across the warp.  The global loads of tile t+2 are issued before the epilogue
 // of tile t and consumed after it.
 #pragma once
+#include <cstdio>
+#include <cstdlib>
 #include "actor_tc_kernel.cuh"
 
 namespace msched {
@@ -120,7 +122,10 @@ __global__ void __launch_bounds__(128) actor_forward_tc_wide(const ActorArgs a)
 #pragma unroll
                 for (int c = 0; c < Kc; ++c) wr[c] = make_float4(src[4 * c], src[4 * c + 1], src[4 * c + 2], src[4 * c + 3]);
             }
-            br = b3[n];
+            // the last layer works in base 2: logits * log2(e), so that the softmax needs ex2 only
+#pragma unroll
+            for (int c = 0; c < Kc; ++c) { wr[c].x *= kLog2e; wr[c].y *= kLog2e; wr[c].z *= kLog2e; wr[c].w *= kLog2e; }
+            br = b3[n] * kLog2e;
         } else {
 #pragma unroll
             for (int c = 0; c < Kc; ++c) wr[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -195,8 +200,9 @@ __global__ void __launch_bounds__(128) actor_forward_tc_wide(const ActorArgs a)
             } else {
                 const unsigned long long g = (unsigned long long)(a.rowOffset + row);
                 uint32_t x4[4];
-                philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)a.step,
-                              (kStreamPolicy << 28) | (uint32_t)((a.step >> 32) & 0x0fffffffu), (uint32_t)a.seed,
+                const unsigned long long stp = a.stepDev ? *a.stepDev : a.step;
+                philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)stp,
+                              (kStreamPolicy << 28) | (uint32_t)((stp >> 32) & 0x0fffffffu), (uint32_t)a.seed,
                               (uint32_t)(a.seed >> 32), x4);
                 u = (float)(x4[0] >> 8) * (1.0f / 16777216.0f);
             }
@@ -246,22 +252,35 @@ __global__ void __launch_bounds__(128) actor_forward_tc_wide(const ActorArgs a)
                         v[i] += b4.x; v[i + 1] += b4.y; v[i + 2] += b4.z; v[i + 3] += b4.w;
                     }
                     if (pass == 0) {
+                        // online softmax in base 2: running max m, running sum s of 2^(l - m)
                         float cm = v[0];
 #pragma unroll
                         for (int i = 1; i < 16; ++i) cm = fmaxf(cm, v[i]);
-                        if (cm > m) { s *= __expf(m - cm); m = cm; }  // (exp(-inf) = 0 on the first chunk)
+                        if (cm > m) { s *= ex2_approx(m - cm); m = cm; }  // (2^-inf = 0 on the first chunk)
+                        float cs = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) s += __expf(v[i] - m);
+                        for (int i = 0; i < 16; ++i) cs += ex2_approx(v[i] - m);
+                        s += cs;
                     } else {
                         const int col0 = t * NT + c * 16;
+                        float e[16], cs = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const float e = __expf(v[i] - m);
-                            cdf += e;
-                            const bool hit = act < 0 && cdf > thr && col0 + i < A;
-                            act = hit ? col0 + i : act;
-                            lact = hit ? v[i] : lact;
-                            if (a.probs && live && col0 + i < A) a.probs[(size_t)row * A + col0 + i] = e * invs;
+                        for (int i = 0; i < 16; ++i) { e[i] = ex2_approx(v[i] - m); cs += e[i]; }
+                        if (act < 0 && cdf + cs > thr) {  // the sample lies in this chunk (once per row)
+                            float cc = cdf;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                cc += e[i];
+                                const bool hit = act < 0 && cc > thr && col0 + i < A;
+                                act = hit ? col0 + i : act;
+                                lact = hit ? v[i] : lact;
+                            }
+                        }
+                        cdf += cs;
+                        if (a.probs && live) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (col0 + i < A) a.probs[(size_t)row * A + col0 + i] = e[i] * invs;
                         }
                     }
                 }
@@ -290,7 +309,7 @@ __global__ void __launch_bounds__(128) actor_forward_tc_wide(const ActorArgs a)
             if (a.logprob) {
                 // Categorical.log_prob clamps the probability to [eps, 1-eps] before the log
                 const float lo = -15.942385152878742f, hi = -1.1920929665620916e-07f;
-                float lp = lact - m - logf(s);
+                float lp = (lact - m) * kLn2 - logf(s);  // the logits are in base 2
                 lp = fminf(fmaxf(lp, lo), hi);
                 a.logprob[row] = lp;
             }
@@ -301,25 +320,48 @@ __global__ void __launch_bounds__(128) actor_forward_tc_wide(const ActorArgs a)
     if (warp == 0) tmem_dealloc(tbase, kCols);
 }
 
+// 128-thread CTAs resident per SM: registers, shared memory and tensor-memory columns (the runtime's
+// occupancy calculator reports 1 for kernels that allocate tensor memory, so it is derived here)
+inline int resident_ctas(const void *fn, size_t dynSmem, int tmemCols)
+{
+    cudaFuncAttributes fa;
+    if (cudaFuncGetAttributes(&fa, fn) != cudaSuccess) return 1;
+    const int regsPerThread = (fa.numRegs + 7) / 8 * 8;
+    int byRegs = 65536 / (regsPerThread * 128);
+    int bySmem = (int)((227 * 1024) / (dynSmem + fa.sharedSizeBytes + 1024));
+    int byTmem = 512 / tmemCols;
+    int r = byRegs < bySmem ? byRegs : bySmem;
+    r = r < byTmem ? r : byTmem;
+    return r < 1 ? 1 : r;
+}
+
 template <int H, int AP>
 inline int launch_actor_shape(const ActorArgs &a, const MschedMlpGroup &g, dim3 grid, int impl, cudaStream_t s)
 {
     if (impl == 0) {  // tensor cores (tcgen05, 3xTF32)
         const size_t smem = (size_t)actor_tc_smem(g.n_in, H, g.n_actions).total;
         if (smem > 200 * 1024) return -1;
-        if (cudaFuncSetAttribute(actor_forward_tc<H, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-            return -2;
-        // persistent CTAs: one wave of (SMs x resident CTAs) shared by the units, each CTA loops
-        // over its unit's tiles (weights staged and tensor memory allocated once per CTA)
-        static int nSm = 0;
-        if (!nSm) {
+        static size_t attrSmem = 0;
+        if (smem > attrSmem) {
+            if (cudaFuncSetAttribute(actor_forward_tc<H, AP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+                return -2;
+            attrSmem = smem;
+        }
+        // persistent CTAs: exactly one resident wave (SMs x occupancy) shared by the units, each CTA
+        // loops over its unit's tiles (weights staged and tensor memory allocated once per CTA)
+        // (host queries cached per kernel instantiation and shared-memory size: a launch must stay
+        // cheaper on the host than on the device)
+        static int nSm = 0, perSm = 0;
+        static size_t cachedSmem = 0;
+        if (!nSm || cachedSmem != smem) {
             int dev = 0;
             cudaGetDevice(&dev);
             cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev);
+            perSm = resident_ctas(reinterpret_cast<const void *>(actor_forward_tc<H, AP>), smem, (H > 32 || AP > 32) ? 64 : 32);
+            if (getenv("MSCHED_DEBUG")) fprintf(stderr, "actor_forward_tc<%d,%d>: smem %zu resident CTAs/SM %d SMs %d\n", H, AP, smem, perSm, nSm);
+            cachedSmem = smem;
         }
-        int perSm = (int)((220 * 1024) / (smem + 1024));
-        perSm = perSm > 12 ? 12 : (perSm < 1 ? 1 : perSm);
-        int gx = (nSm * perSm + (int)grid.y - 1) / (int)grid.y;
+        int gx = (nSm * perSm) / (int)grid.y;
         if (gx > (int)grid.x) gx = (int)grid.x;
         if (gx < 1) gx = 1;
         actor_forward_tc<H, AP><<<dim3(gx, grid.y), 128, smem, s>>>(a);
@@ -328,7 +370,19 @@ inline int launch_actor_shape(const ActorArgs &a, const MschedMlpGroup &g, dim3 
     const int Apad = (g.n_actions + 3) & ~3;
     const size_t smem = sizeof(float) * ((size_t)g.n_in * H + H + (size_t)H * H + H + (size_t)H * Apad + Apad);
     constexpr int APS = AP <= 16 ? 16 : 64;  // the SIMT kernel is built for two action buckets only
-    actor_forward_simt<H, APS><<<grid, 128, smem, s>>>(a);
+    static int nSm = 0, perSm = 0;
+    static size_t cachedSmem = ~(size_t)0;
+    if (!nSm || cachedSmem != smem) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev);
+        perSm = resident_ctas(reinterpret_cast<const void *>(actor_forward_simt<H, APS>), smem, 1);
+        cachedSmem = smem;
+    }
+    int gx = (nSm * perSm) / (int)grid.y;  // persistent: one resident wave, weights staged once per CTA
+    if (gx > (int)grid.x) gx = (int)grid.x;
+    if (gx < 1) gx = 1;
+    actor_forward_simt<H, APS><<<dim3(gx, grid.y), 128, smem, s>>>(a);
     return 0;
 }
 
@@ -349,13 +403,21 @@ inline int launch_actor_wide(const ActorArgs &a, const MschedMlpGroup &g, dim3 g
 {
     const size_t smem = (size_t)actor_wide_smem(g.n_in, H).total;
     if (smem > 220 * 1024) return -1;
-    if (cudaFuncSetAttribute(actor_forward_tc_wide<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-        return -2;
-    int nSm = 0, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev);
-    const int perSm = (smem + 1024) * 2 <= 227 * 1024 ? 2 : 1;  // tensor memory: 2 x 256 columns
-    int gx = (nSm * perSm + (int)grid.y - 1) / (int)grid.y;
+    static size_t attrSmem = 0, cachedSmem = 0;
+    static int nSm = 0, perSm = 0;
+    if (smem > attrSmem) {
+        if (cudaFuncSetAttribute(actor_forward_tc_wide<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return -2;
+        attrSmem = smem;
+    }
+    if (!nSm || cachedSmem != smem) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev);
+        perSm = resident_ctas(reinterpret_cast<const void *>(actor_forward_tc_wide<H>), smem, 256);
+        cachedSmem = smem;
+    }
+    int gx = (nSm * perSm) / (int)grid.y;
     if (gx > (int)grid.x) gx = (int)grid.x;
     if (gx < 1) gx = 1;
     actor_forward_tc_wide<H><<<dim3(gx, grid.y), 128, smem, s>>>(a);
@@ -377,6 +439,7 @@ inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io
     a.actionRec = io.action_rec; a.actionRecStride = io.action_rec_stride;
     a.gatherCore = io.gather_core; a.xUsed = io.x_used; a.nCores = io.n_cores;
     a.timeline = reinterpret_cast<unsigned long long *>(io.timeline);
+    a.stepDev = reinterpret_cast<const unsigned long long *>(io.step_dev);
     dim3 grid((a.nEnvs + 127) / 128, io.units);
     if (g.n_actions > kActorMaxActions) {
         if (a.gatherCore) return -1;

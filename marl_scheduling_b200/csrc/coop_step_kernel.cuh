@@ -49,7 +49,7 @@ __device__ __forceinline__ void coop_step_env(const DevParams &p, uint32_t *st, 
     const bool freeM = mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL ||
                        mode == MSCHED_REWARD_DIVIDED_FREE_NONCOMMERCIAL;
     const bool external = p.auctionMode == MSCHED_AUCTION_EXTERNAL;
-    const int round = p.round;
+    const int round = cur_round(p);
     uint32_t *core = st + 2;
     unsigned char *chl = reinterpret_cast<unsigned char *>(st + p.sChlen);
     uint32_t *slot = st + p.sSlot;
@@ -365,7 +365,7 @@ __device__ __forceinline__ void coop_step_env(const DevParams &p, uint32_t *st, 
         res[p.rQual] = (uint32_t)qb;
         res[p.rQual + 1] = (uint32_t)(qb >> 32);
         res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nExec << 8) | ((uint32_t)nTerm << 16) |
-                         ((uint32_t)p.doneFlag << 24);
+                         ((uint32_t)cur_done(p, round) << 24);
         res[p.rFlags] = flags;
     }
 }

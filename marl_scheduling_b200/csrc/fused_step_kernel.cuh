@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
     const int mode = p.mode;
     const bool agg = mode == MSCHED_REWARD_AGGREGATED_FIXED;
     const bool freeM = mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL || mode == MSCHED_REWARD_DIVIDED_FREE_NONCOMMERCIAL;
-    const int round = p.round;
+    const int round = cur_round(p);
     const bool live = env < p.B;
 
     uint32_t *st = sState + (size_t)lane * W;
@@ -491,7 +491,7 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
             const unsigned long long qb = (unsigned long long)__double_as_longlong(qualSum);
             res[p.rQual] = (uint32_t)qb;
             res[p.rQual + 1] = (uint32_t)(qb >> 32);
-            res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nAcc << 8) | ((uint32_t)nTerm << 16) | ((uint32_t)p.doneFlag << 24);
+            res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nAcc << 8) | ((uint32_t)nTerm << 16) | ((uint32_t)cur_done(p, round) << 24);
             res[p.rFlags] = flags;
         }
     }

@@ -121,6 +121,8 @@ struct Handle {
     ObsKernel obsFn;  // compile-time-domain observation kernel, or null -> direct kernel
     int16_t *stageAction;
     uint32_t *stageResult;
+    int *roundDev;       // device-side round counter (msched_set_round_mode)
+    bool deviceRound;
     cudaStream_t hostStream[2];  // msched_step_host pipelines its chunks over these
     cudaEvent_t evStart, evDone[2];
 };
@@ -205,8 +207,10 @@ int pick_tile(size_t bytesPerEnv, int smemOptin, const char *envName)
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // launch the step kernel for the env range described by p (p.Bpad padded envs starting at p.state)
-void launch_step(const Handle *h, const DevParams &p, cudaStream_t s)
+void launch_step(const Handle *h, const DevParams &p0, cudaStream_t s)
 {
+    DevParams p = p0;
+    p.roundDev = h->deviceRound ? h->roundDev : nullptr;
     if (h->useFused) {
         h->fusedFn<<<p.Bpad / 32, 32 * h->fusedRoles, p.obs ? h->fusedSmemObs : h->fusedSmem, s>>>(p);
     } else if (h->useCoop) {
@@ -346,6 +350,8 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     CUDA_TRY(cudaMalloc(&h->stageAction, (size_t)lay.padded_envs * lay.action_halfs * 2));
     CUDA_TRY(cudaMalloc(&h->stageResult, (size_t)lay.padded_envs * lay.result_words * 4));
     CUDA_TRY(cudaMemset(h->stageAction, 0, (size_t)lay.padded_envs * lay.action_halfs * 2));
+    CUDA_TRY(cudaMalloc(&h->roundDev, sizeof(int)));
+    CUDA_TRY(cudaMemset(h->roundDev, 0, sizeof(int)));
     for (int k = 0; k < 2; ++k) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->hostStream[k], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&h->evDone[k], cudaEventDisableTiming));
@@ -362,6 +368,7 @@ int msched_destroy(void *handle)
     cudaSetDevice(h->device);
     cudaFree(h->stageAction);
     cudaFree(h->stageResult);
+    cudaFree(h->roundDev);
     for (int k = 0; k < 2; ++k) {
         if (h->hostStream[k]) cudaStreamDestroy(h->hostStream[k]);
         if (h->evDone[k]) cudaEventDestroy(h->evDone[k]);
@@ -422,6 +429,7 @@ int msched_reset(void *handle, void *stream)
     CUDA_TRY(cudaSetDevice(h->device));
     h->round = 0;
     h->p.round = 0;
+    CUDA_TRY(cudaMemsetAsync(h->roundDev, 0, sizeof(int), static_cast<cudaStream_t>(stream)));
     reset_kernel<<<(h->p.Bpad + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(h->p);
     CUDA_TRY(cudaGetLastError());
     return MSCHED_OK;
@@ -431,7 +439,34 @@ int msched_get_round(void *handle, int64_t *round)
 {
     Handle *h = static_cast<Handle *>(handle);
     if (!h || !round) return fail(MSCHED_E_ARG, "null handle/round");
+    if (h->deviceRound) {  // graph replays advance the device counter only
+        int r = 0;
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(&r, h->roundDev, sizeof(int), cudaMemcpyDeviceToHost));
+        h->round = r;
+    }
     *round = h->round;
+    return MSCHED_OK;
+}
+
+int msched_set_round_mode(void *handle, int device_side, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(MSCHED_E_ARG, "null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (device_side) {
+        const int r = (int)h->round;
+        CUDA_TRY(cudaMemcpyAsync(h->roundDev, &r, sizeof(int), cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        h->deviceRound = true;
+    } else if (h->deviceRound) {
+        int64_t r = 0;
+        int rc = msched_get_round(handle, &r);
+        if (rc) return rc;
+        h->deviceRound = false;
+    }
     return MSCHED_OK;
 }
 
@@ -440,6 +475,11 @@ int msched_set_round(void *handle, int64_t round)
     Handle *h = static_cast<Handle *>(handle);
     if (!h || round < 0 || round > 0x7fffffff) return fail(MSCHED_E_ARG, "bad handle/round");
     h->round = round;
+    if (h->deviceRound) {
+        const int r = (int)round;
+        CUDA_TRY(cudaSetDevice(h->device));
+        CUDA_TRY(cudaMemcpy(h->roundDev, &r, sizeof(int), cudaMemcpyHostToDevice));
+    }
     return MSCHED_OK;
 }
 
@@ -459,6 +499,7 @@ int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_d
     p.round = (int)h->round;
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     launch_step(h, p, static_cast<cudaStream_t>(stream));
+    if (h->deviceRound) bump_round_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(h->roundDev);
     CUDA_TRY(cudaGetLastError());
     h->round += 1;
     return MSCHED_OK;
@@ -487,6 +528,7 @@ int msched_step_observe(void *handle, const int16_t *action_dev, const double *s
     p.round = (int)h->round;
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     launch_step(h, p, static_cast<cudaStream_t>(stream));
+    if (h->deviceRound) bump_round_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(h->roundDev);
     CUDA_TRY(cudaGetLastError());
     h->round += 1;
     return MSCHED_OK;
@@ -538,6 +580,7 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
         CUDA_TRY(cudaEventRecord(h->evDone[k], h->hostStream[k]));
         CUDA_TRY(cudaStreamWaitEvent(s, h->evDone[k], 0));
     }
+    if (h->deviceRound) bump_round_kernel<<<1, 1, 0, s>>>(h->roundDev);
     h->round += 1;
     if (obs_dev && !fuse) {  // two-launch domains: the observation kernel follows on the caller's stream
         int rc = msched_observe_dense(handle, obs_dev, nullptr, stream);
@@ -575,6 +618,7 @@ int msched_auctioneer_action(void *handle, int random_ties, int16_t *out_dev, vo
     if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
     DevParams p = h->p;
     p.round = (int)h->round;
+    p.roundDev = h->deviceRound ? h->roundDev : nullptr;
     auctioneer_kernel<<<(p.B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p, random_ties, out_dev);
     CUDA_TRY(cudaGetLastError());
     return MSCHED_OK;

@@ -57,6 +57,7 @@ struct DevParams {
     uint32_t *result;
     int16_t *obs;
     unsigned long long *timeline;  // diagnostics: 8 x u64 per CTA (smid, clock64 at phase ends), or null
+    const int *roundDev;           // device-side round counter (CUDA-graph replays), or null -> `round`
 };
 
 // ---- host+device layout arithmetic ------------------------------------------------------
@@ -107,11 +108,19 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 constexpr uint32_t kStreamSpawn = 0, kStreamTie = 1, kStreamPolicy = 2;
 
+// world.round of this step: a kernel argument, or (graph-replay mode) a device counter that a
+// one-thread kernel advances after every step
+__device__ __forceinline__ int cur_round(const DevParams &p) { return p.roundDev ? *p.roundDev : p.round; }
+__device__ __forceinline__ int cur_done(const DevParams &p, int round)
+{   // done = (world.round % episodeLength == 0) after the step, src/SchedulingEnvironment.py:64-67
+    return p.roundDev ? (((round + 1) % p.episodeLength) == 0 ? 1 : 0) : p.doneFlag;
+}
+
 __device__ __forceinline__ void env_draw(const DevParams &p, int env, uint32_t stream, uint32_t a,
                                          uint32_t b, uint32_t out[4])
 {
     const unsigned long long g = (unsigned long long)(p.envOffset + env);
-    philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)p.round, (stream << 28) | (a << 12) | b,
+    philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)cur_round(p), (stream << 28) | (a << 12) | b,
                   (uint32_t)p.seed, (uint32_t)(p.seed >> 32), out);
 }
 __device__ __forceinline__ double u53(const uint32_t x[4])

@@ -63,6 +63,7 @@ struct ActorArgs {
     int16_t *xUsed;             // [M][nIn] input actually fed, or null
     int nCores;
     unsigned long long *timeline;  // diagnostics, or null
+    const unsigned long long *stepDev;  // device-side step counter (CUDA-graph replays), or null -> `step`
 };
 
 constexpr int kActorMaxActions = 64;
@@ -71,6 +72,13 @@ constexpr int kActorMaxActions = 64;
 // clamp to [eps, 1-eps] (src/PPOmodules.py:53-63); one row per thread, logits in registers
 // tanh with 2 MUFU ops: 1 - 2/(e^{2x}+1).  Absolute error < 3e-7 on the whole range (what matters
 // downstream: the activations feed a Linear layer), exact limits for |x| -> inf, tanh(0) = 0
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float fast_tanh(float x)
 {
     float e, r;
@@ -79,8 +87,9 @@ __device__ __forceinline__ float fast_tanh(float x)
     return fmaf(-2.f, r, 1.f);
 }
 
-// lg[o] must be -inf for o >= A (the callers pad the last layer's bias with -inf), so every sweep
-// runs unpredicated over the AP registers
+// lg[] are BASE-2 logits (the callers fold log2(e) into the last layer's weights and bias when they
+// stage them), so the softmax needs one ex2 per action; lg[o] must be -inf for o >= A (padded
+// bias), so every sweep runs unpredicated over the AP registers
 template <int AP>
 __device__ __forceinline__ void actor_epilogue(const ActorArgs &a, float (&lg)[AP], int A, long long row, int env,
                                                int unit, int gsel)
@@ -90,7 +99,7 @@ __device__ __forceinline__ void actor_epilogue(const ActorArgs &a, float (&lg)[A
     for (int o = 1; o < AP; ++o) mx = fmaxf(mx, lg[o]);
     float sum = 0.f;
 #pragma unroll
-    for (int o = 0; o < AP; ++o) { lg[o] = __expf(lg[o] - mx); sum += lg[o]; }
+    for (int o = 0; o < AP; ++o) { lg[o] = ex2_approx(lg[o] - mx); sum += lg[o]; }
     const float inv = 1.f / sum;
     float tot = 0.f;  // Categorical(probs) renormalises by the sum of the softmax output
 #pragma unroll
@@ -107,8 +116,9 @@ __device__ __forceinline__ void actor_epilogue(const ActorArgs &a, float (&lg)[A
     } else {
         const unsigned long long g = (unsigned long long)(a.rowOffset + row);
         uint32_t x4[4];
-        philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)a.step,
-                      (kStreamPolicy << 28) | (uint32_t)((a.step >> 32) & 0x0fffffffu), (uint32_t)a.seed,
+        const unsigned long long stp = a.stepDev ? *a.stepDev : a.step;
+        philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)stp,
+                      (kStreamPolicy << 28) | (uint32_t)((stp >> 32) & 0x0fffffffu), (uint32_t)a.seed,
                       (uint32_t)(a.seed >> 32), x4);
         u = (float)(x4[0] >> 8) * (1.0f / 16777216.0f);
     }
@@ -153,20 +163,27 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
     const int Apad = (A + 3) & ~3;
     float *W1t = sw, *b1 = W1t + nIn * H, *W2t = b1 + H, *b2 = W2t + H * H, *W3t = b2 + H,
           *b3 = W3t + H * Apad;
-    for (int i = threadIdx.x; i < H * nIn; i += blockDim.x) W1t[(i % nIn) * H + i / nIn] = w[i];
-    for (int i = threadIdx.x; i < H; i += blockDim.x) b1[i] = w[H * nIn + i];
-    const float *w2 = w + H * nIn + H;
-    for (int i = threadIdx.x; i < H * H; i += blockDim.x) W2t[(i % H) * H + i / H] = w2[i];
-    for (int i = threadIdx.x; i < H; i += blockDim.x) b2[i] = w2[H * H + i];
-    const float *w3 = w2 + H * H + H;
+    // stage the weights transposed ([in][out]); a warp reads one weight row (contiguous) at a time.
+    // The last layer is scaled by log2(e): base-2 logits for the epilogue
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *w2 = w + H * nIn + H, *w3 = w2 + H * H + H;
+    for (int o = warp; o < H; o += 4)
+        for (int k = lane; k < nIn; k += 32) W1t[k * H + o] = w[o * nIn + k];
+    for (int o = warp; o < H; o += 4)
+        for (int k = lane; k < H; k += 32) W2t[k * H + o] = w2[o * H + k];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) { b1[i] = w[H * nIn + i]; b2[i] = w2[H * H + i]; }
     for (int i = threadIdx.x; i < H * Apad; i += blockDim.x) W3t[i] = 0.f;
     __syncthreads();
-    for (int i = threadIdx.x; i < A * H; i += blockDim.x) W3t[(i % H) * Apad + i / H] = w3[i];
-    for (int i = threadIdx.x; i < Apad; i += blockDim.x) b3[i] = i < A ? w3[A * H + i] : -INFINITY;
+    for (int o = warp; o < A; o += 4)
+        for (int k = lane; k < H; k += 32) W3t[k * Apad + o] = w3[o * H + k] * kLog2e;
+    for (int i = threadIdx.x; i < Apad; i += blockDim.x) b3[i] = i < A ? w3[A * H + i] * kLog2e : -INFINITY;
     __syncthreads();
 
-    const int env = blockIdx.x * blockDim.x + threadIdx.x;
-    if (env >= a.nEnvs) return;
+    // persistent: this CTA's share of the unit's 128-environment tiles
+    const int nTiles = (a.nEnvs + 127) / 128;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+    const int env = tile * 128 + threadIdx.x;
+    if (env >= a.nEnvs) continue;
     const int16_t *xr = a.x + (size_t)env * a.envStride + (size_t)unit * a.unitStride;
     const long long row = (long long)env * a.units + unit;
 
@@ -252,6 +269,7 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
         }
     }
     actor_epilogue(a, lg, A, row, env, unit, gsel);
+    }
 }
 
 }  // namespace msched

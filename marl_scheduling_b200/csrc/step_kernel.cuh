@@ -82,7 +82,7 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
     const bool freeM = mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL ||
                        mode == MSCHED_REWARD_DIVIDED_FREE_NONCOMMERCIAL;
     const bool external = p.auctionMode == MSCHED_AUCTION_EXTERNAL;
-    const int round = p.round;
+    const int round = cur_round(p);
     uint32_t *core = st + 2;
     uint32_t *chl = st + p.sChlen;
     uint32_t *slot = st + p.sSlot;
@@ -432,7 +432,7 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
     const unsigned long long qb = (unsigned long long)__double_as_longlong(qualSum);
     res[p.rQual] = (uint32_t)qb;
     res[p.rQual + 1] = (uint32_t)(qb >> 32);
-    res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nAcc << 8) | ((uint32_t)nTerm << 16) | ((uint32_t)p.doneFlag << 24);
+    res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nAcc << 8) | ((uint32_t)nTerm << 16) | ((uint32_t)cur_done(p, round) << 24);
     res[p.rFlags] = flags;
 }
 
@@ -478,6 +478,8 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevPa
         bulk_wait_read();
     }
 }
+
+__global__ void bump_round_kernel(int *roundDev) { *roundDev += 1; }
 
 // World.__init__ (src/world.py:210-254): every core idle and auctioneer-owned, every slot empty
 __global__ void reset_kernel(const __grid_constant__ DevParams p)

@@ -64,7 +64,7 @@ def _stream(device):
 
 def actor_forward(group, x, x_stride, units, n_envs, env_stride=0, seed=0, step=0, row_offset=0,
                   u=None, want_probs=False, action=None, logprob=None, action_rec=None,
-                  action_rec_stride=0, gather_core=None, n_cores=0, x_used=None, timeline=None):
+                  action_rec_stride=0, gather_core=None, n_cores=0, x_used=None, timeline=None, step_dev=None):
     """x: int16 device tensor; unit u of env b is the row at x[b*env_stride + u*x_stride : +n_in].
     action_rec (int16 view into the env's action record) additionally receives the action the
     world is handed; gather_core (int32 [n_envs*units]) turns the launch into the free-price price
@@ -91,6 +91,7 @@ def actor_forward(group, x, x_stride, units, n_envs, env_stride=0, seed=0, step=
     io.gather_core = None if gather_core is None else gather_core.data_ptr()
     io.x_used = None if x_used is None else x_used.data_ptr()
     io.timeline = None if timeline is None else timeline.data_ptr()
+    io.step_dev = None if step_dev is None else step_dev.data_ptr()  # int64 device counter (graph replays)
     L.check(L.lib().msched_actor_forward(C.byref(group.desc), C.byref(io), _stream(dev)))
     return action, logprob, probs
 

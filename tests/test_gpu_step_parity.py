@@ -233,3 +233,44 @@ def test_step_host_matches_device_step():
                 assert torch.equal(oa[k], ob[k]), (t, k)
     assert a.round == b.round == 20
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("impl", ["fused1", "fused4", "lane"])
+def test_cuda_graph_replay_matches_eager_steps(impl):
+    """Device-side round counter (msched_set_round_mode): a captured step + observations can be
+    replayed from a CUDA graph and walks through the same states as eager launches (the round feeds
+    the Philox spawn draws, birth dates, chain rounds and the done flag)."""
+    import torch
+    dom, mode = DOMS["cfg3"]
+    B, T = 700, 45
+    a = _env(B, dict(dom, mode=mode), impl=impl, auction="random", spawn="philox", seed=11)
+    b = _env(B, dict(dom, mode=mode), impl=impl, auction="random", spawn="philox", seed=11)
+    b.set_device_round(True)
+    rng = np.random.default_rng(2)
+    offc, acc, offp = random_actions(rng, B, dom, True)
+    for e in (a, b):
+        e.set_actions(offc, acc, None, offer_price=offp)
+    # warm-up launch outside the capture, mirrored eagerly
+    a.step_observe_records()
+    b.step_observe_records()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            b.step_observe_records()
+    torch.cuda.current_stream().wait_stream(s)
+    a.step_observe_records()          # the capture itself did not run anything: replay once for step 2
+    g.replay()
+    for t in range(T):
+        a.step_observe_records()
+        g.replay()
+        if t % 11 == 0 or t == T - 1:
+            torch.cuda.synchronize()
+            assert torch.equal(a.state[:B], b.state[:B]), (impl, t)
+            assert torch.equal(a.result[:B], b.result[:B]), (impl, t)
+            assert torch.equal(a._obs[:B], b._obs[:B]), (impl, t)
+    assert a.round == b.round == T + 2
+    done = (b.result[:B, b.layout.r_counts] >> 24) & 1
+    assert int(done.max()) == int(((T + 2) % 100) == 0)
+    a.close(); b.close()
