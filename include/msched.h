@@ -155,6 +155,23 @@ int msched_debug_timeline(void *handle, uint64_t *timeline_dev);
  * chain: padded_envs*chain_words uint32) */
 int msched_bind_state(void *handle, void *state_dev, void *chain_dev);
 
+/* ---- episode aggregates (src/trainPPO.py:172-227: what the train scripts accumulate per step and
+ * average per episode) ----
+ * msched_bind_stats: caller-owned int32 [padded_envs][J][4] (zero it at episode start); every step
+ *   launch then adds, per env and job kind, [sum of the accepted offers' prices, #accepted offers,
+ *   sum of (dwell time - 1) of the terminated jobs, #terminated jobs] -- the raw material of the
+ *   per-kind mean price and mean normalised dwell time ((dwell-1)/length, src/world.py:350-357).
+ *   NULL switches it off (default).
+ * msched_stats_sums: adds the column sums over the environments to out_dev int64 [J][4].
+ * msched_result_sums: adds the sums over the environments of one step's result records to out_dev
+ *   float64 [result_words + 6]: out[k] = sum of record word k (float fields as float, integer fields
+ *   as integer, out[r_quality] = sum of quality_sum); tail: +0 sum quality_cnt, +1 sum n_accepted,
+ *   +2 sum n_terminated, +3 sum done, +4 sum of the per-env mean acception quality over envs with
+ *   quality_cnt > 0, +5 number of such envs. */
+int msched_bind_stats(void *handle, int32_t *stats_dev);
+int msched_stats_sums(void *handle, int64_t *out_dev, void *stream);
+int msched_result_sums(void *handle, const uint32_t *result_dev, double *out_dev, void *stream);
+
 /* fresh worlds: all cores auctioneer-owned, collections empty, round 0, jobIDs from 1
  * (World.__init__; note SchedulingEnv.reset itself resets nothing, src/SchedulingEnvironment.py:85-109) */
 int msched_reset(void *handle, void *stream);

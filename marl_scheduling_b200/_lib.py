@@ -82,6 +82,9 @@ SYMBOLS = {
     "msched_get_info": (C.c_int, [P, C.POINTER(MschedInfo)]),
     "msched_debug_timeline": (C.c_int, [P, P]),
     "msched_bind_state": (C.c_int, [P, P, P]),
+    "msched_bind_stats": (C.c_int, [P, P]),
+    "msched_stats_sums": (C.c_int, [P, P, P]),
+    "msched_result_sums": (C.c_int, [P, P, P, P]),
     "msched_reset": (C.c_int, [P, P]),
     "msched_get_round": (C.c_int, [P, C.POINTER(C.c_int64)]),
     "msched_set_round": (C.c_int, [P, C.c_int64]),

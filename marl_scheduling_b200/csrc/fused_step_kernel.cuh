@@ -270,6 +270,7 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
             const int kind = job_kind(s0), time = job_rem(s0), price = off_price(s3);
             const int offerer = selA + 1;
             const int prio1 = p.prio[kind];
+            stat_accept(p, env, kind, price);
             slot[4 * se] = kEmptyJobW0; slot[4 * se + 1] = kEmptyId; slot[4 * se + 2] = kEmptyId; slot[4 * se + 3] = 0u;
             core[3 * j] = pack_core(offerer, kind, time);
             core[3 * j + 1] = s1;
@@ -342,6 +343,7 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
                 } else {
                     const int R_ = p.mult * p.prio[kind];
                     const int o = core_owner(c0) - 1;
+                    stat_terminate(p, env, kind, round, core[3 * j + 2]);
                     if (agg) {
                         acc_add<R>(&resi[p.rAcc + o], R_);
                         acc_add<R>(&resi[p.rAgent + o], R_);

@@ -421,6 +421,40 @@ int msched_bind_state(void *handle, void *state_dev, void *chain_dev)
     return MSCHED_OK;
 }
 
+int msched_bind_stats(void *handle, int32_t *stats_dev)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h) return fail(MSCHED_E_ARG, "null handle");
+    h->p.stats = stats_dev;  // NULL switches the statistics off
+    return MSCHED_OK;
+}
+
+int msched_result_sums(void *handle, const uint32_t *result_dev, double *out_dev, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !result_dev || !out_dev) return fail(MSCHED_E_ARG, "null handle/result/out");
+    const int nOut = h->lay.result_words + 6;
+    int blocks = (h->cfg.B + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    result_sums_kernel<<<blocks, 256, nOut * sizeof(double), static_cast<cudaStream_t>(stream)>>>(h->p, result_dev, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+int msched_stats_sums(void *handle, int64_t *out_dev, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !out_dev) return fail(MSCHED_E_ARG, "null handle/out");
+    if (!h->p.stats) return fail(MSCHED_E_STATE, "statistics buffer not bound");
+    const int cols = 4 * h->cfg.J;
+    dim3 block(32, 4), grid((h->cfg.B + 32 * 64 - 1) / (32 * 64), (cols + 3) / 4);
+    if (grid.x < 1) grid.x = 1;
+    stats_sums_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(h->p.stats, h->cfg.B, cols,
+                                                                           reinterpret_cast<unsigned long long *>(out_dev));
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
 int msched_reset(void *handle, void *stream)
 {
     Handle *h = static_cast<Handle *>(handle);

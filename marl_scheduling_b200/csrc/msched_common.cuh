@@ -58,6 +58,7 @@ struct DevParams {
     int16_t *obs;
     unsigned long long *timeline;  // diagnostics: 8 x u64 per CTA (smid, clock64 at phase ends), or null
     const int *roundDev;           // device-side round counter (CUDA-graph replays), or null -> `round`
+    int *stats;                    // episode statistics int32 [Bpad][J][4], or null (msched_bind_stats)
 };
 
 // ---- host+device layout arithmetic ------------------------------------------------------
@@ -189,6 +190,26 @@ __device__ __forceinline__ unsigned long long globaltimer()
     unsigned long long r;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(r));
     return r;
+}
+// Episode statistics the train scripts derive from world.acceptedOffers / world.verweilzeiten
+// (src/trainPPO.py:172-227, src/world.py:350-357): per env and job kind
+// [sum of accepted prices, #accepted, sum of (dwell - 1), #terminated].  Rare events (about one per
+// env-step): fire-and-forget reductions straight to HBM.
+__device__ __forceinline__ void stat_accept(const DevParams &p, int env, int kind, int price)
+{
+    if (p.stats && kind >= 0) {
+        int *sp = p.stats + ((size_t)env * p.J + kind) * 4;
+        atomicAdd(sp, price);
+        atomicAdd(sp + 1, 1);
+    }
+}
+__device__ __forceinline__ void stat_terminate(const DevParams &p, int env, int kind, int round, uint32_t birth)
+{
+    if (p.stats && kind >= 0) {
+        int *sp = p.stats + ((size_t)env * p.J + kind) * 4;
+        atomicAdd(sp + 2, round - (int)birth - 1);
+        atomicAdd(sp + 3, 1);
+    }
 }
 // make this thread's generic-proxy shared-memory writes visible to the async (TMA) proxy
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

@@ -295,4 +295,53 @@ __global__ void export_kernel(const __grid_constant__ DevParams p, const ExportA
     }
 }
 
+// ---- episode aggregates: sums over the environments of one step's result records ----------------
+// The reference's train loop accumulates every reward array per step and averages per episode
+// (src/trainPPO.py:172-227).  Batched, the per-step arrays are reduced over the env dimension on
+// the device and ACCUMULATED into `out` (float64 [result_words + 6]): word k of the record lands
+// in out[k] (float fields as float, integer fields as integer; the two quality words hold the sum
+// of quality_sum in the first), the packed counts in the six tail entries
+//   +0 sum quality_cnt, +1 sum n_accepted, +2 sum n_terminated, +3 sum done,
+//   +4 sum over envs with quality_cnt > 0 of the step's mean quality, +5 number of such envs.
+__global__ void result_sums_kernel(const __grid_constant__ DevParams p, const uint32_t *__restrict__ result,
+                                   double *__restrict__ out)
+{
+    extern __shared__ double sacc[];  // [RW + 6]
+    const int RW = p.RW, nOut = RW + 6;
+    for (int k = threadIdx.x; k < nOut; k += blockDim.x) sacc[k] = 0.0;
+    __syncthreads();
+    const int nFloat = p.rAcc;  // offer (and price) rewards are float32 and come first in the record
+    for (int env = blockIdx.x * blockDim.x + threadIdx.x; env < p.B; env += gridDim.x * blockDim.x) {
+        const uint32_t *r = result + (size_t)env * RW;
+        for (int k = 0; k < p.rQual; ++k) {
+            const uint32_t w = r[k];
+            if (w != 0u) atomicAdd(&sacc[k], k < nFloat ? (double)__uint_as_float(w) : (double)(int)w);
+        }
+        const double q = __longlong_as_double(((long long)r[p.rQual + 1] << 32) | (long long)r[p.rQual]);
+        const uint32_t cw = r[p.rCounts];
+        const int qc = (int)(cw & 0xffu), na = (int)((cw >> 8) & 0xffu), nt = (int)((cw >> 16) & 0xffu);
+        if (q != 0.0) atomicAdd(&sacc[p.rQual], q);
+        if (qc) { atomicAdd(&sacc[RW + 0], (double)qc); atomicAdd(&sacc[RW + 4], q / (double)qc); atomicAdd(&sacc[RW + 5], 1.0); }
+        if (na) atomicAdd(&sacc[RW + 1], (double)na);
+        if (nt) atomicAdd(&sacc[RW + 2], (double)nt);
+        if ((cw >> 24) & 1u) atomicAdd(&sacc[RW + 3], 1.0);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nOut; k += blockDim.x)
+        if (sacc[k] != 0.0) atomicAdd(&out[k], sacc[k]);
+}
+
+// column sums of the episode statistics: int32 [B][cols] -> int64 [cols] (accumulated into out)
+__global__ void stats_sums_kernel(const int *__restrict__ stats, int rows, int cols, unsigned long long *__restrict__ out)
+{
+    const int c = blockIdx.y * blockDim.y + threadIdx.y;
+    if (c >= cols) return;
+    long long acc = 0;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += gridDim.x * blockDim.x)
+        acc += stats[(size_t)r * cols + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0 && acc != 0) atomicAdd(&out[c], (unsigned long long)acc);
+}
+
 }  // namespace msched

@@ -250,6 +250,7 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
         const int kind = job_kind(sw0), time = job_rem(sw0), price = off_price(sw3);
         const int offerer = selA + 1;
         const int prio1 = p.prio[kind];
+        stat_accept(p, env, kind, price);
         slot[4 * sel] = kEmptyJobW0; slot[4 * sel + 1] = kEmptyId; slot[4 * sel + 2] = kEmptyId;
         slot[4 * sel + 3] = 0u;
         core[3 * j] = pack_core(offerer, kind, time);
@@ -322,6 +323,7 @@ __device__ __forceinline__ void step_env(const DevParams &p, uint32_t *__restric
         }
         const int R = p.mult * p.prio[kind];
         const int o = core_owner(cw0) - 1;
+        stat_terminate(p, env, kind, round, core[3 * j + 2]);
         if (agg) {
             resi[p.rAcc + o] += R;
             resi[p.rAgent + o] += R;

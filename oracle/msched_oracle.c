@@ -84,6 +84,10 @@ typedef struct {
     int offerIDCounter;    /* Offer.offerID */
     uint32_t flags;
     int64_t terminationRevenues;
+    /* episode statistics the train scripts derive from world.acceptedOffers / world.verweilzeiten
+     * (src/trainPPO.py:172-227): per job kind [sum of accepted prices, #accepted,
+     * sum of (dwell - 1), #terminated] */
+    int32_t stats[4 * MSOR_MAX_KINDS];
 } World;
 
 typedef struct {
@@ -213,6 +217,10 @@ static void executeAnOffer(const MsorConfig *cfg, World *w, int offerID)
             w->flags |= FLAG_CHAIN_OVERFLOW; /* build-defined capacity, see DESIGN.md */
         }
         w->accepted[w->nAccepted++] = *offer; /* :293 */
+        if (offer->jobKind >= 0) { /* prices.append((offer.offeredReward, offer.jobKind)), src/trainPPO.py:172-174 */
+            w->stats[4 * offer->jobKind + 0] += offer->offeredReward;
+            w->stats[4 * offer->jobKind + 1] += 1;
+        }
     }
 }
 
@@ -268,6 +276,10 @@ static void processOneTimestepAndUpdateOwnership(const MsorConfig *cfg, World *w
                 t->dwell = w->round - core->job.birthDate;
                 t->dwellNorm = (double)(w->round - core->job.birthDate - 1) /
                                (double)core->job.initialLength;
+                if (core->job.jobKind >= 0) { /* Verweilzeit record by (priority, length) = job kind */
+                    w->stats[4 * core->job.jobKind + 2] += w->round - core->job.birthDate - 1;
+                    w->stats[4 * core->job.jobKind + 3] += 1;
+                }
                 core->job = emptyJob(); /* assignCoreToAuctioneer, :57-59 */
                 core->ownerID = 0;
             }
@@ -603,6 +615,7 @@ void msor_reset(void *hv)
         w->nOffers = 0; w->nTerm = 0; w->nAccepted = 0;
         w->round = 0; w->jobIDCounter = 1; w->offerIDCounter = 1;
         w->flags = 0; w->terminationRevenues = 0;
+        memset(w->stats, 0, sizeof(w->stats));
         gatherAllObservations(cfg, w);
     }
 }
@@ -845,4 +858,13 @@ void msor_mlp_forward(const float *x, int M, int nin, int h, int A, const float 
     }
     free(h1);
     free(h2);
+}
+
+/* episode statistics of every env: out [B][J][4] int32 (see World.stats) */
+void msor_stats(void *handle, int32_t *out)
+{
+    Msor *h = (Msor *)handle;
+    const int J = h->cfg.J;
+    for (int b = 0; b < h->cfg.B; ++b)
+        memcpy(out + (size_t)b * 4 * J, h->w[b].stats, sizeof(int32_t) * 4 * (size_t)J);
 }

@@ -60,6 +60,7 @@ def lib():
         _lib.msor_mlp_forward.argtypes = ([C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int]
                                           + [C.c_void_p] * 6 + [C.c_int] + [C.c_void_p] * 4)
         _lib.msor_philox.argtypes = [C.c_void_p] * 3
+        _lib.msor_stats.argtypes = [C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -169,6 +170,13 @@ class Oracle:
         lib().msor_observe(self.h, b, _p(o["obs_acc"]), _p(o["obs_off"]), _p(o["obs_auc"]),
                            _p(o["ids"]), _p(o["auc_ids"]))
         return o
+
+    def stats(self):
+        """Episode statistics [B][J][4]: per job kind (sum of accepted prices, #accepted, sum of
+        (dwell - 1), #terminated) since the last reset."""
+        out = np.zeros((self.cfg.B, self.cfg.J, 4), np.int32)
+        lib().msor_stats(self.h, _p(out))
+        return out
 
     def export(self, b):
         N, Cc, L, NL, K = self.N, self.C, self.L, self.NL, self.K

@@ -121,3 +121,37 @@ def test_arithmetic_vectors():
         assert round(p / t * d) == exp
     assert [round(0.5), round(1.5), round(2.5)] == [0, 2, 2]
     assert sum([1 / 6] * 6) == 1.0 or math.isclose(sum([1 / 6] * 6), 1.0)
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_episode_statistics_match_reference_records(name):
+    """The per-kind episode statistics (accepted prices, dwell times) against what the train scripts
+    read off the reference's world.acceptedOffers and world.verweilzeiten (src/trainPPO.py:172-227)."""
+    tr, meta = load_golden(name)
+    T = tr["done"].shape[0]
+    free = meta["mode"].startswith("free")
+    prios, lens = list(meta["prios"]), list(meta["lens"])
+    J = len(prios)
+    orc = O.Oracle(1, meta, meta["mode"], chain_cap=32)
+    exp = np.zeros((J, 4), np.int64)
+    kind_before = tr["init_slot_kind"]
+    for t in range(T):
+        for k in range(int(tr["n_accepted"][t])):
+            offerer, _, _, slot, price = (int(v) for v in tr["accepted"][t][k])
+            kind = int(kind_before[offerer - 1][slot])   # offer.jobKind: the offered job sat in that slot
+            exp[kind, 0] += price
+            exp[kind, 1] += 1
+        kind_before = tr["slot_kind"][t]
+        orc.step(tr["in_offc"][t][None], tr["in_acc"][t][None], tr["in_auc"][t][None],
+                 offp=tr["in_offp"][t][None] if free else None, spawn_u=tr["in_spawn_u"][t][None])
+    if len(set(zip(prios, lens))) == J:   # a Verweilzeit record names its kind by (priority, length)
+        n_rec = int(tr["n_term"].sum())   # (a trace may record fewer steps than the reference ran)
+        for (prio, ln, dwell), norm in zip(tr["dwell"][:n_rec], tr["dwell_norm"][:n_rec]):
+            kind = list(zip(prios, lens)).index((int(prio), int(ln)))
+            exp[kind, 2] += int(dwell) - 1
+            exp[kind, 3] += 1
+            assert norm == (int(dwell) - 1) / int(ln)
+        assert np.array_equal(orc.stats()[0].astype(np.int64), exp), name
+    else:
+        assert np.array_equal(orc.stats()[0][:, :2].astype(np.int64), exp[:, :2]), name
+    assert int(orc.stats()[0][:, 3].sum()) == int(tr["n_term"].sum())
