@@ -178,3 +178,30 @@ def test_aggregated_ppo_env_rollout_and_update(kind):
     env.updateAgents()
     assert not torch.equal(before, ppo.actor.detach()) and torch.isfinite(ppo.actor).all()
     env.close()
+
+
+def test_ppo_checkpoint_roundtrip(tmp_path):
+    import torch
+    from marl_scheduling_b200 import SchedulingEnvironment as SE
+    from marl_scheduling_b200.results import load_checkpoint, save_checkpoint
+    from marl_scheduling_b200.world import World
+    B = 16
+    world = World(dict(WP, numberOfEnvironments=B, seed=1))
+    env = SE.PPODividedFixedPriceEnv(world, RL)
+    accO, offO, aucO = env.reset()
+    for t in range(6):
+        a, o = env.getActionForAllAgents(accO, offO)
+        accO, offO, aucO, offR, accR, aucR, agR, q, done = env.step(o, a, None) if False else env.step(
+            o, a, world.auctioneer.getAuctioneerAction(aucO))
+        env.saveRewards(offR, accR, agR)
+    env.updateAgents()
+    path = str(tmp_path / "ckpt.pt")
+    save_checkpoint(path, world)
+    saved = world.agents.acceptor.actor.detach().clone()
+    with torch.no_grad():
+        world.agents.acceptor.actor.add_(1.0)
+        world.agents.acceptor.policy_old.weights.zero_()
+    load_checkpoint(path, world)
+    assert torch.equal(world.agents.acceptor.actor.detach(), saved)
+    assert torch.equal(world.agents.acceptor.policy_old.weights, saved)
+    env.close()
