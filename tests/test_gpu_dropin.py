@@ -191,7 +191,7 @@ def test_ppo_checkpoint_roundtrip(tmp_path):
     accO, offO, aucO = env.reset()
     for t in range(6):
         a, o = env.getActionForAllAgents(accO, offO)
-        accO, offO, aucO, offR, accR, aucR, agR, q, done = env.step(o, a, None) if False else env.step(
+        accO, offO, aucO, offR, accR, aucR, agR, q, done = env.step(
             o, a, world.auctioneer.getAuctioneerAction(aucO))
         env.saveRewards(offR, accR, agR)
     env.updateAgents()
