@@ -132,6 +132,21 @@ def smoke_check(env, obs):
         p, _, _ = O.mlp_forward(xs[:, n], ws[0].reshape(H, Wd), ws[1], ws[2].reshape(H, H), ws[3],
                                 ws[4].reshape(A, H), ws[5])
         np.testing.assert_allclose(pr[:, n], p, rtol=2e-5, atol=1e-6)
+    # tensor-core kernels: a 32-wide net (tcgen05, 3xTF32) and an aggregated head (200 actions, tiled)
+    for A2 in (40, 200):
+        g2 = MlpGroup.random(Wd, 32, A2, 2, env.device, seed=3)
+        x2 = x[:, 0, :2].contiguous()  # [B,2,Wd]: two units per env
+        _, lp2, pr2 = actor_forward(g2, x2, Wd, 2, B, u=uu[: 2 * B], want_probs=True)
+        w2 = g2.weights.cpu().numpy()
+        xs2 = x2.cpu().numpy().astype(np.float32)
+        pr2 = pr2.cpu().numpy().reshape(B, 2, A2)
+        for n in range(2):
+            o, ws = 0, []
+            for sz in (32 * Wd, 32, 32 * 32, 32, A2 * 32, A2):
+                ws.append(w2[n, o:o + sz]); o += sz
+            p2, _, _ = O.mlp_forward(xs2[:, n], ws[0].reshape(32, Wd), ws[1], ws[2].reshape(32, 32), ws[3],
+                                     ws[4].reshape(A2, 32), ws[5])
+            np.testing.assert_allclose(pr2[:, n], p2, rtol=5e-5, atol=1e-7)
     r = torch.randint(-5, 12, (50, 64)).float().to(env.device)
     g = returns(r, 0.8733, True).cpu().numpy()
     go = O.returns(r.cpu().numpy().astype(np.float64), 0.8733, True)
