@@ -257,6 +257,8 @@ def main():
                     help="rotate: shards larger than L2 visited round-robin, back-to-back launches; "
                          "flush: 256 MiB write before every step, per-launch events")
     ap.add_argument("--sets", type=int, default=0, help="shards for --l2 rotate (default: >= 200 MB in flight)")
+    ap.add_argument("--graph", type=int, default=1, help="--l2 rotate: replay each block from a CUDA graph")
+    ap.add_argument("--device-round", action="store_true", help="device-side round counter without graphs")
     ap.add_argument("--streams", type=int, default=3,
                     help="streams the independent shards alternate between in --l2 rotate (1 = strictly serial launches)")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (diagnostic)")
@@ -337,15 +339,15 @@ def main():
         # of the previous launch has already left.  A block is timed on the default stream, which
         # the two streams fork from and join back into.
         streams = [torch.cuda.Stream(device=dev) for _ in range(args.streams)]
-        main = torch.cuda.current_stream(dev)
+        use_graph = args.graph == 1
+        if use_graph or args.device_round:
+            for e in envs:
+                e.set_device_round(True)  # world.round in a device counter: a block can be replayed from a graph
 
-        def run_block(n, timed):
-            for r in recs[:n]:
-                refresh_actions(env, r, gen)
-            if timed is not None:
-                timed[0].record(main)
+        def launch_block(n):
+            cur = torch.cuda.current_stream(dev)
             fork = torch.cuda.Event()
-            fork.record(main)
+            fork.record(cur)
             for st in streams:
                 st.wait_event(fork)
             for i in range(n):
@@ -354,9 +356,38 @@ def main():
             for st in streams:
                 join = torch.cuda.Event()
                 join.record(st)
-                main.wait_event(join)
+                cur.wait_event(join)
+
+        # the Python launch loop costs ~15 us per launch, as much as the kernel: a block of launches is
+        # captured ONCE in a CUDA graph (its action records are refreshed in place between replays)
+        graphs = {}
+
+        def block_graph(n):
+            if n not in graphs:
+                launch_block(n)  # warm-up outside the capture
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                cap = torch.cuda.Stream(device=dev)
+                cap.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(cap):
+                    with torch.cuda.graph(g, stream=cap):
+                        launch_block(n)
+                torch.cuda.current_stream(dev).wait_stream(cap)
+                graphs[n] = g
+            return graphs[n]
+
+        def run_block(n, timed):
+            g = block_graph(n) if use_graph else None
+            for r in recs[:n]:
+                refresh_actions(env, r, gen)
             if timed is not None:
-                timed[1].record(main)
+                timed[0].record()
+            if g is not None:
+                g.replay()
+            else:
+                launch_block(n)
+            if timed is not None:
+                timed[1].record()
 
         for _ in range(-(-args.state_warm * S // (S * G))):
             run_block(S * G, None)
@@ -385,7 +416,7 @@ def main():
         tot_ms = stepk_ms = float(t[0])
         obs_us = None
         l2_note = (f"inputs larger than L2: {S} shards x {per_set / 1e6:.0f} MB visited round-robin, launches "
-                   f"back to back in blocks of {S * G} on {len(streams)} stream(s)")
+                   f"in blocks of {S * G} on {len(streams)} stream(s)" + (", each block one CUDA-graph replay" if use_graph else ""))
         n_launch = K
     else:
         ring, gen = make_actions(torch, env, cfg.get("ring", 8), seed=1 + rank)

@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(128) coop_step_kernel(const __grid_constant__ 
         bulk_s2g(p.result + (size_t)env0 * p.RW, sRes, rsBytes);
         bulk_commit();
         bulk_wait_read();
+        finish_round(p);
     }
 }
 

@@ -51,6 +51,10 @@ struct FusedDims {
     static constexpr int X_SEL = 0, X_KEY = C, X_TERM = 2 * C, X_TIE = 3 * C, X_SPAWN = 3 * C + 4 * NCH;
     static constexpr int X_NSPAWN = X_SPAWN + 4, X_OCC = X_NSPAWN + 1;
     static constexpr int XW = (X_OCC + 2) | 1;
+    // observation tile of 32 envs (bytes): small domains keep every tile of a big launch resident,
+    // which needs 16 CTAs of <= 64 threads (8 of 128) per SM, i.e. at most 64 registers per thread
+    static constexpr int OBS_TILE = 64 * ((N * C + C) * (2 * NL + 4) + NL * (2 * C + 2));
+    static constexpr bool SMALL = OBS_TILE <= 14 * 1024;
 };
 
 inline size_t fused_smem_bytes(int stateWords, int actionHalfs, int resultWords, int obsHalfs, int C)
@@ -82,7 +86,8 @@ __device__ __forceinline__ void acc_and(uint32_t *p, uint32_t v)
 }
 
 template <int N, int C, int L, int R>
-__global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constant__ DevParams p)
+__global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 16 : 8) : 1)
+    fused_step_kernel(const __grid_constant__ DevParams p)
 {
     using D = FusedDims<N, C, L>;
     constexpr int NL = D::NL, NCH = D::NCH, W = D::W, SCH = D::SCH, SSLOT = D::SSLOT, XW = D::XW;
@@ -517,7 +522,10 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
         bulk_wait_read();
     }
     if (!withObs) {
-        if (tl && threadIdx.x == 0) { tl[6] = clock64(); tl[7] = globaltimer(); }
+        if (threadIdx.x == 0) {
+            if (tl) { tl[6] = clock64(); tl[7] = globaltimer(); }
+            finish_round(p);
+        }
         return;
     }
     __syncthreads();  // the bulk stores have read the work tiles: the memory is free
@@ -580,6 +588,7 @@ __global__ void __launch_bounds__(32 * R) fused_step_kernel(const __grid_constan
         bulk_commit();
         bulk_wait_read();
         if (tl) { tl[6] = clock64(); tl[7] = globaltimer(); }
+        finish_round(p);
     }
 }
 

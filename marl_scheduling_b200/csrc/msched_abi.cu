@@ -121,7 +121,7 @@ struct Handle {
     ObsKernel obsFn;  // compile-time-domain observation kernel, or null -> direct kernel
     int16_t *stageAction;
     uint32_t *stageResult;
-    int *roundDev;       // device-side round counter (msched_set_round_mode)
+    int *roundDev;       // device-side round counter + CTA ticket word (msched_set_round_mode)
     bool deviceRound;
     cudaStream_t hostStream[2];  // msched_step_host pipelines its chunks over these
     cudaEvent_t evStart, evDone[2];
@@ -207,10 +207,12 @@ int pick_tile(size_t bytesPerEnv, int smemOptin, const char *envName)
 bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // launch the step kernel for the env range described by p (p.Bpad padded envs starting at p.state)
-void launch_step(const Handle *h, const DevParams &p0, cudaStream_t s)
+// selfAdvance: the launch covers the whole step, so its last CTA advances the device-side round
+void launch_step(const Handle *h, const DevParams &p0, cudaStream_t s, bool selfAdvance = true)
 {
     DevParams p = p0;
     p.roundDev = h->deviceRound ? h->roundDev : nullptr;
+    p.roundTicket = (h->deviceRound && selfAdvance) ? reinterpret_cast<unsigned *>(h->roundDev + 1) : nullptr;
     if (h->useFused) {
         h->fusedFn<<<p.Bpad / 32, 32 * h->fusedRoles, p.obs ? h->fusedSmemObs : h->fusedSmem, s>>>(p);
     } else if (h->useCoop) {
@@ -306,13 +308,15 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     h->useCoop = h->coopFn && (!h->stepTile || cfg->B <= 8192);
     // register-resident kernel for the compile-time domains; it also emits the observations when
     // the observation tile leaves room for enough resident warps (cfg3: 22 KB per 32-env tile)
-    // roles (warps) per 32-env tile: big batches of a small domain fill every SM with one-warp
-    // tiles in a single wave (cfg3 at 65,536 envs: 22.9 us vs 24.6 us with 4 roles); small batches
-    // and bigger domains are bound by one tile's critical path, which 4 roles cut (cfg2 domain at
-    // 65,536 envs: 24.6 us vs 41.8 us)
+    // roles (warps) per 32-env tile.  Big batches of a small domain: every tile of a launch is resident
+    // at once (12.4 KB of shared memory per tile), two roles give the schedulers twice the warps to
+    // hide the serial latency of an environment (cfg3 at 65,536 envs, launches from independent shards
+    // overlapping on 3 streams: 15.1 / 14.4 / 14.6 us per launch with 1 / 2 / 4 roles; strictly
+    // serial launches: 21.9 / 23.8 / 24.6 us).  Small batches and bigger domains are bound by one
+    // tile's critical path, which 4 roles cut (cfg2 domain at 65,536 envs: 24.6 us vs 41.8 us)
     {
         const size_t obsTile = (size_t)32 * lay.obs_halfs * 2;
-        h->fusedRoles = (cfg->B >= 32768 && obsTile <= 28 * 1024) ? 1 : 4;
+        h->fusedRoles = (cfg->B >= 32768 && obsTile <= 28 * 1024) ? 2 : 4;
     }
     if (const char *e = getenv("MSCHED_ROLES")) { const int r = atoi(e); if (r == 1 || r == 2 || r == 4) h->fusedRoles = r; }
     h->fusedFn = pick_fused_kernel(cfg->N, cfg->C, cfg->L, h->fusedRoles);
@@ -350,8 +354,8 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     CUDA_TRY(cudaMalloc(&h->stageAction, (size_t)lay.padded_envs * lay.action_halfs * 2));
     CUDA_TRY(cudaMalloc(&h->stageResult, (size_t)lay.padded_envs * lay.result_words * 4));
     CUDA_TRY(cudaMemset(h->stageAction, 0, (size_t)lay.padded_envs * lay.action_halfs * 2));
-    CUDA_TRY(cudaMalloc(&h->roundDev, sizeof(int)));
-    CUDA_TRY(cudaMemset(h->roundDev, 0, sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->roundDev, 2 * sizeof(int)));
+    CUDA_TRY(cudaMemset(h->roundDev, 0, 2 * sizeof(int)));
     for (int k = 0; k < 2; ++k) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->hostStream[k], cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&h->evDone[k], cudaEventDisableTiming));
@@ -533,7 +537,6 @@ int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_d
     p.round = (int)h->round;
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     launch_step(h, p, static_cast<cudaStream_t>(stream));
-    if (h->deviceRound) bump_round_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(h->roundDev);
     CUDA_TRY(cudaGetLastError());
     h->round += 1;
     return MSCHED_OK;
@@ -562,7 +565,6 @@ int msched_step_observe(void *handle, const int16_t *action_dev, const double *s
     p.round = (int)h->round;
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     launch_step(h, p, static_cast<cudaStream_t>(stream));
-    if (h->deviceRound) bump_round_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(h->roundDev);
     CUDA_TRY(cudaGetLastError());
     h->round += 1;
     return MSCHED_OK;
@@ -605,7 +607,7 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
         p.envOffset = h->p.envOffset + e0;
         p.round = (int)h->round;
         p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
-        launch_step(h, p, cs);
+        launch_step(h, p, cs, false);  // several launches per step: the round advances once, below
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(result_host + (size_t)e0 * RW, h->stageResult + (size_t)e0 * RW, (size_t)n * RW * 4,
                                  cudaMemcpyDeviceToHost, cs));

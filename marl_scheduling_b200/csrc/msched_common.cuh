@@ -57,7 +57,8 @@ struct DevParams {
     uint32_t *result;
     int16_t *obs;
     unsigned long long *timeline;  // diagnostics: 8 x u64 per CTA (smid, clock64 at phase ends), or null
-    const int *roundDev;           // device-side round counter (CUDA-graph replays), or null -> `round`
+    int *roundDev;                 // device-side round counter (CUDA-graph replays), or null -> `round`
+    unsigned *roundTicket;         // CTA exit tickets: the last CTA of a launch advances roundDev (or null)
     int *stats;                    // episode statistics int32 [Bpad][J][4], or null (msched_bind_stats)
 };
 
@@ -191,6 +192,22 @@ __device__ __forceinline__ unsigned long long globaltimer()
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(r));
     return r;
 }
+// Called by one thread of every CTA after its last use of the round: the CTA that draws the last
+// ticket knows that every other CTA of the launch is past its reads and advances the counter, so a
+// step needs no separate "round += 1" launch (graph-replay mode only)
+__device__ __forceinline__ void finish_round(const DevParams &p)
+{
+    if (p.roundTicket) {
+        __threadfence();
+        const unsigned t = atomicAdd(p.roundTicket, 1u);
+        if (t == gridDim.x - 1) {
+            *p.roundTicket = 0u;
+            *p.roundDev += 1;
+            __threadfence();
+        }
+    }
+}
+
 // Episode statistics the train scripts derive from world.acceptedOffers / world.verweilzeiten
 // (src/trainPPO.py:172-227, src/world.py:350-357): per env and job kind
 // [sum of accepted prices, #accepted, sum of (dwell - 1), #terminated].  Rare events (about one per

@@ -478,6 +478,7 @@ __global__ void __launch_bounds__(128) step_kernel(const __grid_constant__ DevPa
         bulk_s2g(p.result + (size_t)env0 * p.RW, sRes, rsBytes);
         bulk_commit();
         bulk_wait_read();
+        finish_round(p);
     }
 }
 
