@@ -78,6 +78,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 // bounded mbarrier wait: a lost completion traps instead of hanging the device
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity)
 {
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 24); ++it) {
         uint32_t done;
         asm volatile(
