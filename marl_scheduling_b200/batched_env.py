@@ -196,7 +196,7 @@ class BatchedSchedulingEnv:
         out["acceptor"] = r[:, lay.r_acceptor: lay.r_acceptor + N * lay.RC].view(B, N, lay.RC)
         out["auctioneer"] = r[:, lay.r_auctioneer: lay.r_auctioneer + self.C]
         out["agent"] = r[:, lay.r_agent: lay.r_agent + N]
-        q = r[:, lay.r_quality: lay.r_quality + 2].contiguous().view(torch.float64).view(B)
+        q = r[:, lay.r_quality: lay.r_quality + 2].reshape(-1).clone().view(torch.float64).view(B)
         counts = r[:, lay.r_counts]
         out["quality_sum"] = q
         out["quality_cnt"] = counts & 0xFF
@@ -205,7 +205,7 @@ class BatchedSchedulingEnv:
         out["done"] = (counts >> 24) & 0x1
         out["flags"] = r[:, lay.r_flags]
         nw = (self.C + 1) // 2
-        ai = r[:, lay.r_auctioneer_idx: lay.r_auctioneer_idx + nw].contiguous().view(torch.int16)
+        ai = r[:, lay.r_auctioneer_idx: lay.r_auctioneer_idx + nw].reshape(-1).clone().view(torch.int16).view(B, 2 * nw)
         out["auctioneer_idx"] = ai[:, : self.C]
         return out
 

@@ -274,3 +274,70 @@ def test_cuda_graph_replay_matches_eager_steps(impl):
     done = (b.result[:B, b.layout.r_counts] >> 24) & 1
     assert int(done.max()) == int(((T + 2) % 100) == 0)
     a.close(); b.close()
+
+
+EDGE = {
+    # one environment, one agent, one core, one slot
+    "tiny": (dict(N=1, C=1, L=1, prios=[3], lens=[2], probs=[1], fix=[2]), "fix", 1),
+    # 16 job kinds (the maximum), every agent refills its whole collection per round
+    "kinds16": (dict(N=2, C=3, L=3, prios=list(range(1, 17)), lens=[1 + (k % 7) for k in range(16)],
+                     probs=[1 / 16] * 16, fix=list(range(16)), newJobs=3), "fix", 257),
+    # N*L = 254: the largest offer table of the lane-per-env kernels; job length 255; price -2 / -1 sentinels
+    "wide": (dict(N=127, C=2, L=2, prios=[5, 9], lens=[255, 1], probs=[0.5, 0.5], fix=[-2, -1]), "fix", 40),
+    # 64 cores (the maximum), cooperative kernel only
+    "cores64": (dict(N=3, C=64, L=4, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7], mult=2), "agg", 70),
+    # free prices incl. the -5 of quirk Q1 and negative prices (payments flip direction, Q2)
+    "negprice": (dict(N=2, C=3, L=3, prios=[2, 4, 8], lens=[5, 5, 5], probs=[1 / 3] * 3, fix=[1]), "free_ncomm", 300),
+}
+
+
+@pytest.mark.parametrize("key", list(EDGE))
+def test_edge_domains_match_oracle(key):
+    """Edge cases: single env, maximum kinds / table width / core count, sentinel and negative prices,
+    batches that are not a multiple of the 32-env tile."""
+    from oracle import oracle as O
+    dom, mode, B = EDGE[key]
+    free = mode.startswith("free")
+    impls = ["coop"] if key == "cores64" else (["lane", "coop"] + (["fused1", "fused2"] if _has_fused(dom) else []))
+    from marl_scheduling_b200 import MschedError
+    ran = 0
+    for impl in impls:
+        try:
+            env = _env(B, dict(dom, mode=mode), impl=impl, auction="random", spawn="philox", seed=77, chain_capacity=255)
+        except MschedError as e:   # e.g. 32 records of the widest domain exceed the lane kernel's shared memory
+            assert "not available for this domain" in str(e), e
+            continue
+        ran += 1
+        orc = O.Oracle(B, dom, mode, chain_cap=255, tie_mode=O.TIE_PHILOX, seed=77)
+        rng = np.random.default_rng(3)
+        N, C, L = dom["N"], dom["C"], dom["L"]
+        for t in range(30):
+            offc, acc, offp = random_actions(rng, B, dom, free)
+            if key == "negprice":
+                offp = rng.integers(-6, 9, (B, N, L))
+            if key == "wide":   # make acceptances likely despite the 255-entry tables
+                acc = rng.integers(0, 3, (B, N, C))
+            r = env.step(offc, acc, None, offer_price=offp)
+            orc.step(offc, acc, None, offp=offp)
+            r = {k: (v.cpu().numpy() if v is not None else None) for k, v in r.items()}
+            assert np.array_equal(r["auctioneer_idx"], orc.auc_out), (key, impl, t)
+            assert np.array_equal(r["offer"].astype(np.float64), orc.r_offer), (key, impl, t)
+            assert np.array_equal(r["acceptor"], orc.r_acceptor), (key, impl, t)
+            assert np.array_equal(r["auctioneer"], orc.r_auctioneer), (key, impl, t)
+            assert np.array_equal(r["agent"], orc.r_agent), (key, impl, t)
+            assert np.array_equal(r["flags"].astype(np.uint32), orc.flags), (key, impl, t)
+            if free:
+                assert np.array_equal(r["price"].astype(np.float64), orc.r_price), (key, impl, t)
+        e = env.export_state()
+        for b in sorted({0, B // 2, B - 1}):
+            ob = orc.export(b)
+            for k in STATE_KEYS:
+                assert np.array_equal(np.asarray(e[k][b]), np.asarray(ob[k])), (key, impl, b, k)
+            assert np.array_equal(e["chain"][b], ob["chain"]), (key, impl, b)
+        if key != "cores64" and key != "wide":
+            o = {k: v.cpu().numpy() for k, v in env.observe().items()}
+            oo = orc.observe(B - 1)
+            assert np.array_equal(o["acceptor"][B - 1], oo["obs_acc"])
+            assert np.array_equal(o["offer"][B - 1], oo["obs_off"])
+        env.close()
+    assert ran >= 1
