@@ -277,6 +277,16 @@ typedef struct MschedActorIO {
 
 int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, void *stream);
 
+/* DQNEntity.selectAction (src/DQNmodules.py:34-76) for a group of Q-nets Linear(in,16)-Tanh-Linear(16,A)
+ * (weights per net [W1 16*in | b1 16 | W2 A*16 | b2 A], torch layout): epsilon-greedy action per
+ * (environment, unit) row -- a uniformly random action with probability epsilon (the caller evaluates the
+ * schedule RUN_END + (RUN_START-RUN_END)*exp(-round/RUN_DECAY)), else the first arg-max of Q.  Uses the
+ * x / stride / units / n_envs / seed / step / action / action_rec fields of io; u_override, if set, is
+ * float32 [M][2] (exploration draw, random-action draw).  q_out: optional float32 [M][A]. */
+int msched_dqn_param_count(int n_in, int n_actions);
+int msched_dqn_select(const MschedMlpGroup *nets, const MschedActorIO *io, float epsilon, float *q_out,
+                      void *stream);
+
 /* PPO.update returns prologue (src/PPOmodules.py:128-137): G_t = r_t + gamma*G_{t+1} over
  * the whole buffer in float64, cast to float32, optional (G-mean)/(std_unbiased+1e-7) per
  * unit.  rewards/out: float32 [T][M] time-major. */

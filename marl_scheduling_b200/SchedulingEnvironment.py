@@ -240,6 +240,50 @@ class PPOFullyAggregatedFixPriceEnv(PPOAggregatedFixPriceEnv):
         return torch.cat([off.float(), acc], dim=2)  # src/Agent.py:463-467
 
 
+class DQNSchedulingEnv(SchedulingEnv):
+    """src/SchedulingEnvironment.py:351-425: carries the DQN hyper-parameters and the
+    update*MemoriesAndOptimize methods (push one transition per environment and unit, then one
+    optimize_model step per unit)."""
+    REWARD = "fix"
+
+    def __init__(self, world, params):
+        super().__init__(world, params)
+        self.RUN_END = params["RUN_END"]
+        self.RUN_START = params["RUN_START"]
+        self.RUN_DECAY = params["RUN_DECAY"]
+        self.BATCH_SIZE = params["BATCH_SIZE"]
+        self.OFFER_GAMMA = params["OFFER_GAMMA"]
+        self.ACCEPTOR_GAMMA = params["ACCEPTOR_GAMMA"]
+        self.REPLAY_MEMORY_SIZE = params["REPLAY_MEMORY_SIZE"]
+        self.agents = None
+
+    def getActionForAllAgents(self, acceptorObs, offerObs):
+        return self.agents.getActions(offerObs, acceptorObs)
+
+    def _push_and_optimize(self, dqn, old_obs, actions, new_obs, rewards):
+        B = self.core.B
+        dqn.memory.push(old_obs.reshape(B, dqn.units, dqn.n_in), actions.reshape(B, dqn.units),
+                        new_obs.reshape(B, dqn.units, dqn.n_in), rewards.reshape(B, dqn.units))
+        return dqn.optimize_model(self.BATCH_SIZE)
+
+    def updateOfferMemoriesAndOptimize(self, oldOfferObs, offerActions, newOfferObs, offerNetRewards):
+        return self._push_and_optimize(self.agents.offer, oldOfferObs, offerActions, newOfferObs, offerNetRewards)
+
+    def updateAcceptorMemoriesAndOptimize(self, oldAcceptorObs, acceptorActions, newAcceptorObs, acceptorNetRewards):
+        return self._push_and_optimize(self.agents.acceptor, oldAcceptorObs, acceptorActions, newAcceptorObs,
+                                       acceptorNetRewards)
+
+
+class DQNDividedFixedPricesEnv(DQNSchedulingEnv):
+    """src/SchedulingEnvironment.py:428-436."""
+
+    def __init__(self, world, params):
+        super().__init__(world, params)
+        from .dqn import DividedFixPriceDQNAgents
+        self.agents = DividedFixPriceDQNAgents(world, self)
+        self.world.agents = self.agents
+
+
 def numberToNDimensionalAction(number, base, dimensionality):
     """src/Agent.py:644-666 for tensors: digit k = (number // base**k) % base, index 0 = least
     significant.  Raises ValueError("Illegal Argument") like the reference."""

@@ -59,4 +59,41 @@ int msched_returns(const float *rewards, int T, int M, double gamma, int normali
     return MSCHED_OK;
 }
 
+int msched_dqn_param_count(int n_in, int n_actions) { return 16 * n_in + 16 + n_actions * 16 + n_actions; }
+
+int msched_dqn_select(const MschedMlpGroup *nets, const MschedActorIO *io, float epsilon, float *q_out, void *stream)
+{
+    if (!nets || !io || !io->x || !nets->weights) return fail(MSCHED_E_ARG, "null nets/io/x/weights");
+    if (nets->n_hidden != 16) return fail(MSCHED_E_ARG, "the DQN nets have 16 hidden neurons (src/DQNmodules.py:41-46)");
+    if (io->n_envs < 0 || io->units < 1 || nets->n_nets < 1 || nets->n_in < 1 || nets->n_in > 512 ||
+        nets->n_actions < 1 || nets->n_actions > 1024 || io->x_stride < nets->n_in)
+        return fail(MSCHED_E_ARG, "bad n_envs/units/n_nets/n_in/n_actions/x_stride");
+    if (io->gather_core) return fail(MSCHED_E_ARG, "gather_core is a PPO free-price feature");
+    if (io->action_rec && io->action_rec_stride < io->units) return fail(MSCHED_E_ARG, "action_rec_stride smaller than units");
+    if (io->n_envs == 0) return MSCHED_OK;
+    QArgs q;
+    memset(&q, 0, sizeof(q));
+    ActorArgs &a = q.a;
+    a.weights = nets->weights; a.x = io->x;
+    a.envStride = io->env_stride ? io->env_stride : (long long)io->x_stride * io->units; a.unitStride = io->x_stride;
+    a.nIn = nets->n_in; a.nHidden = 16; a.nActions = nets->n_actions; a.nNets = nets->n_nets;
+    a.unitDiv = nets->unit_div > 0 ? nets->unit_div : 1;
+    a.units = io->units; a.nEnvs = io->n_envs;
+    a.seed = io->seed; a.step = io->step; a.rowOffset = io->row_offset; a.uOverride = io->u_override;
+    a.action = io->action; a.actionRec = io->action_rec; a.actionRecStride = io->action_rec_stride;
+    a.stepDev = reinterpret_cast<const unsigned long long *>(io->step_dev);
+    q.epsilon = epsilon;
+    q.qOut = q_out;
+    const size_t smem = sizeof(float) * ((size_t)16 * a.nIn + 16 + (size_t)a.nActions * 16 + a.nActions);
+    int tiles = (a.nEnvs + 127) / 128;
+    int gx = (148 * 8 + io->units - 1) / io->units;
+    if (gx > tiles) gx = tiles;
+    if (gx < 1) gx = 1;
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(dqn_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dqn_select_kernel<<<dim3(gx, io->units), 128, smem, static_cast<cudaStream_t>(stream)>>>(q);
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
 }  // extern "C"

@@ -272,4 +272,94 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
     }
 }
 
+// ---- DQNEntity.selectAction (src/DQNmodules.py:34-76), batched ------------------------------------
+// Q-net Linear(in,16)-Tanh-Linear(16,A); epsilon-greedy: with probability epsilon (the caller's
+// RUN_END + (RUN_START-RUN_END)*exp(-round/RUN_DECAY)) a uniformly random action, else arg-max Q
+// (first maximum, like torch.max).  Weights per net: [W1 16*in | b1 16 | W2 A*16 | b2 A], torch layout.
+// One thread per (environment, unit) row, the unit's weights staged in shared memory.
+struct QArgs {
+    ActorArgs a;     // x / strides / units / nets / seed / step / uOverride ([M][2]) / action / actionRec
+    float epsilon;
+    float *qOut;     // [M][A] or null
+};
+
+__global__ void __launch_bounds__(128) dqn_select_kernel(const QArgs q)
+{
+    constexpr int H = 16;
+    extern __shared__ __align__(16) float sq[];
+    const ActorArgs &a = q.a;
+    const int nIn = a.nIn, A = a.nActions;
+    const int unit = blockIdx.y;
+    const int net = (unit / a.unitDiv) % a.nNets;
+    const int pc = H * nIn + H + A * H + A;
+    const float *w = a.weights + (size_t)net * pc;
+    float *W1t = sq, *b1 = W1t + nIn * H, *W2 = b1 + H, *b2 = W2 + A * H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int o = warp; o < H; o += 4)
+        for (int k = lane; k < nIn; k += 32) W1t[k * H + o] = w[o * nIn + k];
+    for (int i = threadIdx.x; i < H; i += blockDim.x) b1[i] = w[H * nIn + i];
+    const float *w2 = w + H * nIn + H;
+    for (int i = threadIdx.x; i < A * H; i += blockDim.x) W2[i] = w2[i];
+    for (int i = threadIdx.x; i < A; i += blockDim.x) b2[i] = w2[A * H + i];
+    __syncthreads();
+    const int nTiles = (a.nEnvs + 127) / 128;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int env = tile * 128 + threadIdx.x;
+        if (env >= a.nEnvs) continue;
+        const int16_t *xr = a.x + (size_t)env * a.envStride + (size_t)unit * a.unitStride;
+        const long long row = (long long)env * a.units + unit;
+        float h[H];
+#pragma unroll
+        for (int o = 0; o < H; ++o) h[o] = b1[o];
+        for (int k = 0; k < nIn; ++k) {
+            const float xv = (float)xr[k];
+            const float4 *wr = reinterpret_cast<const float4 *>(W1t + k * H);
+#pragma unroll
+            for (int o4 = 0; o4 < H / 4; ++o4) {
+                const float4 wv = wr[o4];
+                h[4 * o4] = fmaf(wv.x, xv, h[4 * o4]); h[4 * o4 + 1] = fmaf(wv.y, xv, h[4 * o4 + 1]);
+                h[4 * o4 + 2] = fmaf(wv.z, xv, h[4 * o4 + 2]); h[4 * o4 + 3] = fmaf(wv.w, xv, h[4 * o4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < H; ++o) h[o] = tanhf(h[o]);
+        float best = -INFINITY;
+        int arg = 0;
+        for (int o = 0; o < A; ++o) {
+            float acc = b2[o];
+            const float4 *wr = reinterpret_cast<const float4 *>(W2 + o * H);
+#pragma unroll
+            for (int k4 = 0; k4 < H / 4; ++k4) {
+                const float4 wv = wr[k4];
+                acc = fmaf(wv.x, h[4 * k4], acc); acc = fmaf(wv.y, h[4 * k4 + 1], acc);
+                acc = fmaf(wv.z, h[4 * k4 + 2], acc); acc = fmaf(wv.w, h[4 * k4 + 3], acc);
+            }
+            if (q.qOut) q.qOut[(size_t)row * A + o] = acc;
+            if (acc > best) { best = acc; arg = o; }
+        }
+        float u0, u1;
+        if (a.uOverride) {
+            u0 = a.uOverride[2 * row];
+            u1 = a.uOverride[2 * row + 1];
+        } else {
+            const unsigned long long g = (unsigned long long)(a.rowOffset + row);
+            const unsigned long long stp = a.stepDev ? *a.stepDev : a.step;
+            uint32_t x4[4];
+            philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)stp,
+                          (kStreamPolicy << 28) | (uint32_t)((stp >> 32) & 0x0fffffffu), (uint32_t)a.seed,
+                          (uint32_t)(a.seed >> 32), x4);
+            u0 = (float)(x4[0] >> 8) * (1.0f / 16777216.0f);
+            u1 = (float)(x4[1] >> 8) * (1.0f / 16777216.0f);
+        }
+        // `sample > eps_treshold` exploits, otherwise random.randrange(numberOfActions)
+        int act = arg;
+        if (!(u0 > q.epsilon)) {
+            act = (int)(u1 * (float)A);
+            act = act >= A ? A - 1 : act;
+        }
+        if (a.action) a.action[row] = act;
+        if (a.actionRec) a.actionRec[(size_t)env * a.actionRecStride + unit] = (int16_t)act;
+    }
+}
+
 }  // namespace msched
