@@ -530,14 +530,22 @@ def main():
             fork.record(cur)
             with torch.cuda.stream(side[0]):
                 side[0].wait_event(fork)
-                policy.actor_forward(off_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=2,
-                                     step_dev=step_t, action=o_act, logprob=o_lp, action_rec=env.offer_core_actions,
-                                     action_rec_stride=lay.action_halfs)
-                if free:
-                    policy.actor_forward(price_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs,
-                                         seed=3, step_dev=step_t, action=p_act, logprob=p_lp,
-                                         action_rec=env.offer_price_actions, action_rec_stride=lay.action_halfs,
-                                         gather_core=o_act, n_cores=Cc)
+                if free and policy.offer_unit_fusable(off_net, price_net):
+                    # core chooser + price chooser of every offer unit in ONE launch
+                    policy.offer_unit_forward(off_net, price_net, ov["offer"], lay.o_off_row, NL, B, Cc,
+                                              env_stride=lay.obs_halfs, seeds=(2, 3), step_dev=step_t,
+                                              core_out=(o_act, o_lp), price_out=(p_act, p_lp),
+                                              core_rec=env.offer_core_actions, price_rec=env.offer_price_actions,
+                                              action_rec_stride=lay.action_halfs)
+                else:
+                    policy.actor_forward(off_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=2,
+                                         step_dev=step_t, action=o_act, logprob=o_lp, action_rec=env.offer_core_actions,
+                                         action_rec_stride=lay.action_halfs)
+                    if free:
+                        policy.actor_forward(price_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs,
+                                             seed=3, step_dev=step_t, action=p_act, logprob=p_lp,
+                                             action_rec=env.offer_price_actions, action_rec_stride=lay.action_halfs,
+                                             gather_core=o_act, n_cores=Cc)
                 j0 = torch.cuda.Event()
                 j0.record(side[0])
             with torch.cuda.stream(side[1]):
@@ -585,7 +593,7 @@ def main():
         torch.cuda.synchronize()
         ret_us = e0.elapsed_time(e1) * 1e3 / 5
         rollout = {"value": B * N / (r_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": r_ms,
-                   "steps": args.rollout_steps, "launches_per_step": 4 if free else 3,
+                   "steps": args.rollout_steps, "launches_per_step": 3 if (free and policy.offer_unit_fusable(off_net, price_net)) or not free else 4,
                    "what": "actor forward of every divided PPO unit (offer/core chooser"
                            + (", price chooser" if free else "") + ", acceptor: sample + log-prob, actions "
                            "written into the action record; acceptor and offer units on two streams) + fused env step + observations; one shard, L2 warm, the step captured in a CUDA graph and replayed",

@@ -277,6 +277,18 @@ typedef struct MschedActorIO {
 
 int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, void *stream);
 
+/* FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332) for every offer unit in ONE launch: the
+ * core chooser samples a core from the unit's offer observation row (core_io->x, n_cores set), then the
+ * same thread feeds [core prio, core rem, slot prio, slot rem] of that core to the price chooser
+ * ([-5]*4 and a reported price of -5 for core action 0, quirk Q1).  Equivalent to msched_actor_forward
+ * (core_nets, core_io) followed by msched_actor_forward(price_nets, price_io with gather_core =
+ * core_io->action), without re-reading the row and without the second launch.  price_io's x / strides /
+ * gather_core are ignored; its seed / step / u_override / outputs are the price chooser's own.  16-wide
+ * nets with at most 16 actions each (the divided free-price agents); other shapes: MSCHED_E_ARG, use
+ * the two-call form. */
+int msched_offer_unit_forward(const MschedMlpGroup *core_nets, const MschedActorIO *core_io,
+                              const MschedMlpGroup *price_nets, const MschedActorIO *price_io, void *stream);
+
 /* DQNEntity.selectAction (src/DQNmodules.py:34-76) for a group of Q-nets Linear(in,16)-Tanh-Linear(16,A)
  * (weights per net [W1 16*in | b1 16 | W2 A*16 | b2 A], torch layout): epsilon-greedy action per
  * (environment, unit) row -- a uniformly random action with probability epsilon (the caller evaluates the

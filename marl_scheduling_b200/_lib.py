@@ -97,6 +97,8 @@ SYMBOLS = {
     "msched_export_state": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, P]),
     "msched_mlp_param_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "msched_actor_forward": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),
+    "msched_offer_unit_forward": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO),
+                                            C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),
     "msched_dqn_param_count": (C.c_int, [C.c_int, C.c_int]),
     "msched_dqn_select": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), C.c_float, P, P]),
     "msched_returns": (C.c_int, [P, C.c_int, C.c_int, C.c_double, C.c_int, P, P]),

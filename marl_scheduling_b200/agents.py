@@ -220,6 +220,24 @@ class DividedFreePricePPOAgents:
         c, lay = self.env.core, self.env.core.layout
         B, N, C, L = c.B, c.N, c.C, c.Lc
         seed = self.world.seed
+        if P.offer_unit_fusable(self.core.policy_old, self.price.policy_old) and self.core.step_no == self.price.step_no:
+            # both choosers of every offer unit in one launch (msched_offer_unit_forward)
+            NL = N * L
+            x_used = torch.empty((B, NL, 4), dtype=torch.int16, device=offerObs.device)
+            (ca, clp), (pa, plp) = P.offer_unit_forward(
+                self.core.policy_old, self.price.policy_old, offerObs, lay.o_off_row, NL, B, C,
+                env_stride=lay.obs_halfs, seeds=(seed * 3 + 1, seed * 3 + 2), step=self.core.step_no,
+                core_rec=c.offer_core_actions, price_rec=c.offer_price_actions,
+                action_rec_stride=lay.action_halfs, x_used=x_used)
+            for ppo, xs, a_, lp_ in ((self.core, offerObs.reshape(B, NL, 2 * C + 2).clone(), ca, clp),
+                                     (self.price, x_used, pa, plp)):
+                ppo.step_no += 1
+                ppo.buf_x.append(xs)
+                ppo.buf_a.append(a_.view(B, NL))
+                ppo.buf_lp.append(lp_.view(B, NL))
+            self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 3,
+                                       action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs)
+            return c.acceptor_actions, (c.offer_core_actions, c.offer_price_actions)
         core = self.core.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 3 + 1,
                                       action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs)
         # price chooser: the kernel slices [core prio, core rem, slot prio, slot rem] of the chosen

@@ -424,10 +424,8 @@ inline int launch_actor_wide(const ActorArgs &a, const MschedMlpGroup &g, dim3 g
     return 0;
 }
 
-// impl: 0 = tensor cores (tcgen05), 1 = fp32 SIMT
-inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io, int impl, cudaStream_t s)
+inline ActorArgs make_actor_args(const MschedMlpGroup &g, const MschedActorIO &io)
 {
-    if (g.n_actions > 32767) return -1;  // actions are reported as int16 in the action record
     ActorArgs a;
     a.weights = g.weights; a.x = io.x;
     a.envStride = io.env_stride ? io.env_stride : (long long)io.x_stride * io.units; a.unitStride = io.x_stride;
@@ -440,6 +438,42 @@ inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io
     a.gatherCore = io.gather_core; a.xUsed = io.x_used; a.nCores = io.n_cores;
     a.timeline = reinterpret_cast<unsigned long long *>(io.timeline);
     a.stepDev = reinterpret_cast<const unsigned long long *>(io.step_dev);
+    return a;
+}
+
+// FreePriceOfferPPO.selectAction in one launch (fp32 SIMT, 16-wide nets, <= 16 actions each): the
+// core chooser and the price chooser of every offer unit
+inline int launch_offer_unit(const MschedMlpGroup &gc, const MschedActorIO &ioc, const MschedMlpGroup &gp,
+                             const MschedActorIO &iop, cudaStream_t s)
+{
+    OfferUnitArgs q;
+    q.core = make_actor_args(gc, ioc);
+    q.price = make_actor_args(gp, iop);
+    q.price.nCores = ioc.n_cores;
+    auto fl = [](int nIn, int A) { const int Ap = (A + 3) & ~3; return nIn * 16 + 16 + 256 + 16 + 16 * Ap + Ap; };
+    const size_t smem = sizeof(float) * (size_t)(((fl(gc.n_in, gc.n_actions) + 3) & ~3) + fl(gp.n_in, gp.n_actions));
+    static int nSm = 0, perSm = 0;
+    static size_t cachedSmem = ~(size_t)0;
+    if (!nSm || cachedSmem != smem) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev);
+        perSm = resident_ctas(reinterpret_cast<const void *>(offer_unit_forward_simt<16, 16, 16>), smem, 1);
+        cachedSmem = smem;
+    }
+    const int tiles = (ioc.n_envs + 127) / 128;
+    int gx = (nSm * perSm) / ioc.units;
+    if (gx > tiles) gx = tiles;
+    if (gx < 1) gx = 1;
+    offer_unit_forward_simt<16, 16, 16><<<dim3(gx, ioc.units), 128, smem, s>>>(q);
+    return 0;
+}
+
+// impl: 0 = tensor cores (tcgen05), 1 = fp32 SIMT
+inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io, int impl, cudaStream_t s)
+{
+    if (g.n_actions > 32767) return -1;  // actions are reported as int16 in the action record
+    ActorArgs a = make_actor_args(g, io);
     dim3 grid((a.nEnvs + 127) / 128, io.units);
     if (g.n_actions > kActorMaxActions) {
         if (a.gatherCore) return -1;

@@ -48,6 +48,32 @@ int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, vo
     return MSCHED_OK;
 }
 
+int msched_offer_unit_forward(const MschedMlpGroup *core_nets, const MschedActorIO *core_io,
+                              const MschedMlpGroup *price_nets, const MschedActorIO *price_io, void *stream)
+{
+    if (!core_nets || !core_io || !price_nets || !price_io || !core_io->x || !core_nets->weights || !price_nets->weights)
+        return fail(MSCHED_E_ARG, "null nets/io/x/weights");
+    if (core_io->n_envs < 0 || core_io->units < 1 || core_nets->n_nets < 1 || price_nets->n_nets < 1)
+        return fail(MSCHED_E_ARG, "bad n_envs/units/n_nets");
+    if (price_io->units != core_io->units || price_io->n_envs != core_io->n_envs)
+        return fail(MSCHED_E_ARG, "the price chooser serves the core chooser's rows (same units and n_envs)");
+    const int nc = core_io->n_cores;
+    if (nc < 1 || core_nets->n_in != 2 * nc + 2 || core_io->x_stride < 2 * nc + 2 || core_nets->n_actions != nc + 1)
+        return fail(MSCHED_E_ARG, "core chooser: n_in == 2*n_cores+2 offer rows and n_cores+1 actions");
+    if (price_nets->n_in != 4) return fail(MSCHED_E_ARG, "price chooser: n_in == 4");
+    if (core_nets->n_hidden != 16 || price_nets->n_hidden != 16 || core_nets->n_actions > 16 || price_nets->n_actions > 16 ||
+        price_nets->n_actions < 1)
+        return fail(MSCHED_E_ARG, "fused offer unit: 16-wide nets with at most 16 actions (use two msched_actor_forward calls)");
+    if ((core_io->action_rec && core_io->action_rec_stride < core_io->units) ||
+        (price_io->action_rec && price_io->action_rec_stride < price_io->units))
+        return fail(MSCHED_E_ARG, "action_rec_stride smaller than units");
+    if (core_io->probs || price_io->probs) return fail(MSCHED_E_ARG, "probs output: use msched_actor_forward");
+    if (core_io->n_envs == 0) return MSCHED_OK;
+    launch_offer_unit(*core_nets, *core_io, *price_nets, *price_io, static_cast<cudaStream_t>(stream));
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
 int msched_returns(const float *rewards, int T, int M, double gamma, int normalise, float *out, void *stream)
 {
     if (!rewards || !out || T < 1 || M < 0) return fail(MSCHED_E_ARG, "bad rewards/out/T/M");

@@ -91,8 +91,8 @@ __device__ __forceinline__ float fast_tanh(float x)
 // stage them), so the softmax needs one ex2 per action; lg[o] must be -inf for o >= A (padded
 // bias), so every sweep runs unpredicated over the AP registers
 template <int AP>
-__device__ __forceinline__ void actor_epilogue(const ActorArgs &a, float (&lg)[AP], int A, long long row, int env,
-                                               int unit, int gsel)
+__device__ __forceinline__ int actor_epilogue(const ActorArgs &a, float (&lg)[AP], int A, long long row, int env,
+                                              int unit, int gsel)
 {
     float mx = lg[0];
 #pragma unroll
@@ -109,7 +109,7 @@ __device__ __forceinline__ void actor_epilogue(const ActorArgs &a, float (&lg)[A
         for (int o = 0; o < AP; ++o)
             if (o < A) a.probs[(size_t)row * A + o] = lg[o];
     }
-    if (!a.action && !a.logprob && !a.actionRec) return;
+    if (!a.action && !a.logprob && !a.actionRec) return -1;
     float u;
     if (a.uOverride) {
         u = a.uOverride[row];
@@ -141,14 +141,109 @@ __device__ __forceinline__ void actor_epilogue(const ActorArgs &a, float (&lg)[A
     }
     if (a.action) a.action[row] = act;  // what PPO.selectAction stores in buffer.actions
     if (a.actionRec)                    // what the world is handed (price -5 next to core action 0)
-        a.actionRec[(size_t)env * a.actionRecStride + unit] = (int16_t)((a.gatherCore && gsel == 0) ? -5 : act);
+        a.actionRec[(size_t)env * a.actionRecStride + unit] = (int16_t)(gsel == 0 ? -5 : act);  // gsel is -1 without a gather
     if (a.logprob) {
         const float eps = 1.1920928955078125e-07f;
         float pn = pa / tot;
         pn = fminf(fmaxf(pn, eps), 1.f - eps);
         a.logprob[row] = logf(pn);
     }
+    return act;
 }
+
+// shared-memory image of one actor net for the SIMT kernels: W1t [nIn][H] | b1 [H] | W2t [H][H] |
+// b2 [H] | W3t [H][Apad] | b3 [Apad]; weights transposed ([in][out]), the last layer scaled by log2(e)
+// (base-2 logits for the epilogue), padded actions get bias -inf
+template <int H>
+struct SimtNet {
+    float *W1t, *b1, *W2t, *b2, *W3t, *b3;
+    int nIn, A, Apad;
+    __device__ __forceinline__ static int floats(int nIn, int A) { const int Ap = (A + 3) & ~3; return nIn * H + H + H * H + H + H * Ap + Ap; }
+    __device__ __forceinline__ void carve(float *base, int nIn_, int A_)
+    {
+        nIn = nIn_; A = A_; Apad = (A_ + 3) & ~3;
+        W1t = base; b1 = W1t + nIn * H; W2t = b1 + H; b2 = W2t + H * H; W3t = b2 + H; b3 = W3t + H * Apad;
+    }
+    // called by all 128 threads; a warp reads one weight row (contiguous) at a time.  Needs a
+    // __syncthreads() between zero_pad() and stage(), and one after stage()
+    __device__ __forceinline__ void zero_pad() { for (int i = threadIdx.x; i < H * Apad; i += blockDim.x) W3t[i] = 0.f; }
+    __device__ __forceinline__ void stage(const float *w)
+    {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const float *w2 = w + H * nIn + H, *w3 = w2 + H * H + H;
+        for (int o = warp; o < H; o += 4)
+            for (int k = lane; k < nIn; k += 32) W1t[k * H + o] = w[o * nIn + k];
+        for (int o = warp; o < H; o += 4)
+            for (int k = lane; k < H; k += 32) W2t[k * H + o] = w2[o * H + k];
+        for (int i = threadIdx.x; i < H; i += blockDim.x) { b1[i] = w[H * nIn + i]; b2[i] = w2[H * H + i]; }
+        for (int o = warp; o < A; o += 4)
+            for (int k = lane; k < H; k += 32) W3t[k * Apad + o] = w3[o * H + k] * kLog2e;
+        for (int i = threadIdx.x; i < Apad; i += blockDim.x) b3[i] = i < A ? w3[A * H + i] * kLog2e : -INFINITY;
+    }
+    // one row: xf(k) is input k; the inputs are fetched in batches of 16 (one memory round trip
+    // per 16 inputs instead of one per input)
+    template <int AP, class XF>
+    __device__ __forceinline__ void forward(XF xf, float (&lg)[AP]) const
+    {
+        float h1[H], h2[H];
+#pragma unroll
+        for (int o = 0; o < H; ++o) h1[o] = b1[o];
+        for (int k0 = 0; k0 < nIn; k0 += 16) {
+            float xb[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) xb[q] = k0 + q < nIn ? xf(k0 + q) : 0.f;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (k0 + q < nIn) {
+                    const float xv = xb[q];
+                    const float4 *wr = reinterpret_cast<const float4 *>(W1t + (k0 + q) * H);
+#pragma unroll
+                    for (int o4 = 0; o4 < H / 4; ++o4) {
+                        const float4 wv = wr[o4];
+                        h1[4 * o4 + 0] = fmaf(wv.x, xv, h1[4 * o4 + 0]);
+                        h1[4 * o4 + 1] = fmaf(wv.y, xv, h1[4 * o4 + 1]);
+                        h1[4 * o4 + 2] = fmaf(wv.z, xv, h1[4 * o4 + 2]);
+                        h1[4 * o4 + 3] = fmaf(wv.w, xv, h1[4 * o4 + 3]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < H; ++o) { h1[o] = fast_tanh(h1[o]); h2[o] = b2[o]; }
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+            const float xv = h1[k];
+            const float4 *wr = reinterpret_cast<const float4 *>(W2t + k * H);
+#pragma unroll
+            for (int o4 = 0; o4 < H / 4; ++o4) {
+                const float4 wv = wr[o4];
+                h2[4 * o4 + 0] = fmaf(wv.x, xv, h2[4 * o4 + 0]);
+                h2[4 * o4 + 1] = fmaf(wv.y, xv, h2[4 * o4 + 1]);
+                h2[4 * o4 + 2] = fmaf(wv.z, xv, h2[4 * o4 + 2]);
+                h2[4 * o4 + 3] = fmaf(wv.w, xv, h2[4 * o4 + 3]);
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < H; ++o) h2[o] = fast_tanh(h2[o]);
+#pragma unroll
+        for (int o = 0; o < AP; ++o) lg[o] = -INFINITY;
+#pragma unroll
+        for (int o4 = 0; o4 < AP / 4; ++o4) {
+            if (4 * o4 < A) {
+                float4 acc = *reinterpret_cast<const float4 *>(b3 + 4 * o4);
+#pragma unroll
+                for (int k = 0; k < H; ++k) {
+                    const float4 wv = *reinterpret_cast<const float4 *>(W3t + k * Apad + 4 * o4);
+                    acc.x = fmaf(wv.x, h2[k], acc.x);
+                    acc.y = fmaf(wv.y, h2[k], acc.y);
+                    acc.z = fmaf(wv.z, h2[k], acc.z);
+                    acc.w = fmaf(wv.w, h2[k], acc.w);
+                }
+                lg[4 * o4 + 0] = acc.x; lg[4 * o4 + 1] = acc.y; lg[4 * o4 + 2] = acc.z; lg[4 * o4 + 3] = acc.w;
+            }
+        }
+    }
+};
 
 template <int H, int AP>
 __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
@@ -158,117 +253,96 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
     const int unit = blockIdx.y;
     const int net = (unit / a.unitDiv) % a.nNets;
     const int pc = H * nIn + H + H * H + H + A * H + A;
-    const float *w = a.weights + (size_t)net * pc;
-    // smem layout: W1t [nIn][H] | b1 [H] | W2t [H][H] | b2 [H] | W3t [H][Apad] | b3 [Apad]
-    const int Apad = (A + 3) & ~3;
-    float *W1t = sw, *b1 = W1t + nIn * H, *W2t = b1 + H, *b2 = W2t + H * H, *W3t = b2 + H,
-          *b3 = W3t + H * Apad;
-    // stage the weights transposed ([in][out]); a warp reads one weight row (contiguous) at a time.
-    // The last layer is scaled by log2(e): base-2 logits for the epilogue
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float *w2 = w + H * nIn + H, *w3 = w2 + H * H + H;
-    for (int o = warp; o < H; o += 4)
-        for (int k = lane; k < nIn; k += 32) W1t[k * H + o] = w[o * nIn + k];
-    for (int o = warp; o < H; o += 4)
-        for (int k = lane; k < H; k += 32) W2t[k * H + o] = w2[o * H + k];
-    for (int i = threadIdx.x; i < H; i += blockDim.x) { b1[i] = w[H * nIn + i]; b2[i] = w2[H * H + i]; }
-    for (int i = threadIdx.x; i < H * Apad; i += blockDim.x) W3t[i] = 0.f;
+    SimtNet<H> n1;
+    n1.carve(sw, nIn, A);
+    n1.zero_pad();
     __syncthreads();
-    for (int o = warp; o < A; o += 4)
-        for (int k = lane; k < H; k += 32) W3t[k * Apad + o] = w3[o * H + k] * kLog2e;
-    for (int i = threadIdx.x; i < Apad; i += blockDim.x) b3[i] = i < A ? w3[A * H + i] * kLog2e : -INFINITY;
+    n1.stage(a.weights + (size_t)net * pc);
     __syncthreads();
 
     // persistent: this CTA's share of the unit's 128-environment tiles
     const int nTiles = (a.nEnvs + 127) / 128;
     for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-    const int env = tile * 128 + threadIdx.x;
-    if (env >= a.nEnvs) continue;
-    const int16_t *xr = a.x + (size_t)env * a.envStride + (size_t)unit * a.unitStride;
-    const long long row = (long long)env * a.units + unit;
+        const int env = tile * 128 + threadIdx.x;
+        if (env >= a.nEnvs) continue;
+        const int16_t *xr = a.x + (size_t)env * a.envStride + (size_t)unit * a.unitStride;
+        const long long row = (long long)env * a.units + unit;
+        // FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): the price chooser's input is
+        // [core prio, core rem, slot prio, slot rem] of the core the core chooser picked, sliced out
+        // of the offer observation row; core action 0 feeds the dummy [-5,-5,-5,-5] (quirk Q1)
+        int gsel = -1;
+        int16_t g4[4] = {0, 0, 0, 0};
+        if (a.gatherCore) {
+            gsel = a.gatherCore[row];
+            const int c2 = 2 * a.nCores;
+            if (gsel <= 0 || gsel > a.nCores) {
+                g4[0] = g4[1] = g4[2] = g4[3] = (int16_t)-5;
+            } else {
+                g4[0] = xr[2 * gsel]; g4[1] = xr[2 * gsel + 1]; g4[2] = xr[c2]; g4[3] = xr[c2 + 1];
+            }
+        }
+        if (a.xUsed)
+            for (int k = 0; k < nIn; ++k) a.xUsed[(size_t)row * nIn + k] = a.gatherCore ? g4[k & 3] : xr[k];
+        float lg[AP];
+        if (a.gatherCore)
+            n1.template forward<AP>([&](int k) { return (float)g4[k & 3]; }, lg);
+        else
+            n1.template forward<AP>([&](int k) { return (float)xr[k]; }, lg);
+        actor_epilogue(a, lg, A, row, env, unit, gsel);
+    }
+}
 
-    // FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): the price chooser's input is
-    // [core prio, core rem, slot prio, slot rem] of the core the core chooser picked, sliced out
-    // of the offer observation row; core action 0 feeds the dummy [-5,-5,-5,-5] (quirk Q1)
-    int gsel = -1;
-    int16_t g4[4] = {0, 0, 0, 0};
-    if (a.gatherCore) {
-        gsel = a.gatherCore[row];
-        const int c2 = 2 * a.nCores;
-        if (gsel <= 0 || gsel > a.nCores) {
+// ---- one offer unit of the free-price agents in ONE launch --------------------------------------
+// FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): the core chooser samples a core from
+// the slot's offer observation, then the price chooser samples a price from [core prio, core rem,
+// slot prio, slot rem] of that core ([-5]*4 and a reported price of -5 for core action 0, quirk Q1).
+// Both nets of the unit are staged in shared memory and the thread that evaluated the core chooser
+// for its row goes straight on to the price chooser: the observation row is read once, the core
+// action never leaves the registers and the step needs one launch fewer.
+struct OfferUnitArgs {
+    ActorArgs core, price;  // price.x / strides are ignored (the row is the core chooser's)
+};
+
+template <int H, int AP1, int AP2>
+__global__ void __launch_bounds__(128, 6) offer_unit_forward_simt(const OfferUnitArgs q)
+{
+    extern __shared__ __align__(16) float sw[];
+    const ActorArgs &a = q.core, &b = q.price;
+    const int unit = blockIdx.y;
+    const int net1 = (unit / a.unitDiv) % a.nNets, net2 = (unit / b.unitDiv) % b.nNets;
+    const int pc1 = H * a.nIn + H + H * H + H + a.nActions * H + a.nActions;
+    const int pc2 = H * b.nIn + H + H * H + H + b.nActions * H + b.nActions;
+    SimtNet<H> n1, n2;
+    n1.carve(sw, a.nIn, a.nActions);
+    n2.carve(sw + ((SimtNet<H>::floats(a.nIn, a.nActions) + 3) & ~3), b.nIn, b.nActions);
+    n1.zero_pad();
+    n2.zero_pad();
+    __syncthreads();
+    n1.stage(a.weights + (size_t)net1 * pc1);
+    n2.stage(b.weights + (size_t)net2 * pc2);
+    __syncthreads();
+    const int nTiles = (a.nEnvs + 127) / 128;
+    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
+        const int env = tile * 128 + threadIdx.x;
+        if (env >= a.nEnvs) continue;
+        const int16_t *xr = a.x + (size_t)env * a.envStride + (size_t)unit * a.unitStride;
+        const long long row = (long long)env * a.units + unit;
+        if (a.xUsed)
+            for (int k = 0; k < a.nIn; ++k) a.xUsed[(size_t)row * a.nIn + k] = xr[k];
+        float lg1[AP1];
+        n1.template forward<AP1>([&](int k) { return (float)xr[k]; }, lg1);
+        const int gsel = actor_epilogue(a, lg1, a.nActions, row, env, unit, -1);
+        int16_t g4[4];
+        const int c2 = 2 * b.nCores;
+        if (gsel <= 0 || gsel > b.nCores) {
             g4[0] = g4[1] = g4[2] = g4[3] = (int16_t)-5;
         } else {
             g4[0] = xr[2 * gsel]; g4[1] = xr[2 * gsel + 1]; g4[2] = xr[c2]; g4[3] = xr[c2 + 1];
         }
-    }
-    if (a.xUsed)
-        for (int k = 0; k < nIn; ++k) a.xUsed[(size_t)row * nIn + k] = a.gatherCore ? g4[k & 3] : xr[k];
-
-    float h1[H], h2[H];
-#pragma unroll
-    for (int o = 0; o < H; ++o) h1[o] = b1[o];
-    // inputs in batches of 16: the loads of a batch are issued together (one memory round trip
-    // per 16 inputs instead of one per input)
-    for (int k0 = 0; k0 < nIn; k0 += 16) {
-        float xb[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            const int k = k0 + q;
-            xb[q] = k < nIn ? (a.gatherCore ? (float)g4[k & 3] : (float)xr[k]) : 0.f;
-        }
-#pragma unroll
-        for (int q = 0; q < 16; ++q) {
-            if (k0 + q < nIn) {
-                const float xv = xb[q];
-                const float4 *wr = reinterpret_cast<const float4 *>(W1t + (k0 + q) * H);
-#pragma unroll
-                for (int o4 = 0; o4 < H / 4; ++o4) {
-                    const float4 wv = wr[o4];
-                    h1[4 * o4 + 0] = fmaf(wv.x, xv, h1[4 * o4 + 0]);
-                    h1[4 * o4 + 1] = fmaf(wv.y, xv, h1[4 * o4 + 1]);
-                    h1[4 * o4 + 2] = fmaf(wv.z, xv, h1[4 * o4 + 2]);
-                    h1[4 * o4 + 3] = fmaf(wv.w, xv, h1[4 * o4 + 3]);
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 0; o < H; ++o) { h1[o] = fast_tanh(h1[o]); h2[o] = b2[o]; }
-#pragma unroll
-    for (int k = 0; k < H; ++k) {
-        const float xv = h1[k];
-        const float4 *wr = reinterpret_cast<const float4 *>(W2t + k * H);
-#pragma unroll
-        for (int o4 = 0; o4 < H / 4; ++o4) {
-            const float4 wv = wr[o4];
-            h2[4 * o4 + 0] = fmaf(wv.x, xv, h2[4 * o4 + 0]);
-            h2[4 * o4 + 1] = fmaf(wv.y, xv, h2[4 * o4 + 1]);
-            h2[4 * o4 + 2] = fmaf(wv.z, xv, h2[4 * o4 + 2]);
-            h2[4 * o4 + 3] = fmaf(wv.w, xv, h2[4 * o4 + 3]);
-        }
-    }
-#pragma unroll
-    for (int o = 0; o < H; ++o) h2[o] = fast_tanh(h2[o]);
-
-    float lg[AP];
-#pragma unroll
-    for (int o = 0; o < AP; ++o) lg[o] = -INFINITY;
-#pragma unroll
-    for (int o4 = 0; o4 < AP / 4; ++o4) {
-        if (4 * o4 < A) {
-            float4 acc = *reinterpret_cast<const float4 *>(b3 + 4 * o4);
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                const float4 wv = *reinterpret_cast<const float4 *>(W3t + k * Apad + 4 * o4);
-                acc.x = fmaf(wv.x, h2[k], acc.x);
-                acc.y = fmaf(wv.y, h2[k], acc.y);
-                acc.z = fmaf(wv.z, h2[k], acc.z);
-                acc.w = fmaf(wv.w, h2[k], acc.w);
-            }
-            lg[4 * o4 + 0] = acc.x; lg[4 * o4 + 1] = acc.y; lg[4 * o4 + 2] = acc.z; lg[4 * o4 + 3] = acc.w;
-        }
-    }
-    actor_epilogue(a, lg, A, row, env, unit, gsel);
+        if (b.xUsed) *reinterpret_cast<short4 *>(b.xUsed + (size_t)row * 4) = make_short4(g4[0], g4[1], g4[2], g4[3]);
+        float lg2[AP2];
+        n2.template forward<AP2>([&](int k) { return (float)g4[k & 3]; }, lg2);
+        actor_epilogue(b, lg2, b.nActions, row, env, unit, gsel);
     }
 }
 

@@ -4,6 +4,7 @@ and discounted returns.  Mirrors reference src/PPOmodules.py:25-72 (ActorCritic.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -62,6 +63,62 @@ def _stream(device):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+def _make_io(x, x_stride, units, n_envs, env_stride, seed, step, row_offset, u, action, logprob, probs,
+             action_rec, action_rec_stride, gather_core, n_cores, x_used, timeline, step_dev):
+    io = L.MschedActorIO()
+    io.x, io.x_stride, io.units, io.n_envs, io.n_cores = x.data_ptr(), x_stride, units, n_envs, n_cores
+    io.env_stride, io.row_offset, io.seed, io.step = env_stride, row_offset, seed, step
+    io.u_override = None if u is None else u.data_ptr()
+    io.action = None if action is None else action.data_ptr()
+    io.logprob = None if logprob is None else logprob.data_ptr()
+    io.probs = None if probs is None else probs.data_ptr()
+    io.action_rec = None if action_rec is None else action_rec.data_ptr()
+    io.action_rec_stride = action_rec_stride
+    io.gather_core = None if gather_core is None else gather_core.data_ptr()
+    io.x_used = None if x_used is None else x_used.data_ptr()
+    io.timeline = None if timeline is None else timeline.data_ptr()
+    io.step_dev = None if step_dev is None else step_dev.data_ptr()  # int64 device counter (graph replays)
+    return io
+
+
+def offer_unit_fusable(core_group, price_group):
+    """Shapes msched_offer_unit_forward serves: the divided free-price agents' 16-wide nets."""
+    # Opt-in (MSCHED_OFFER_FUSE=1): measured on B200 at 65,536 envs the single launch is SLOWER inside the
+    # rollout step (112.9 us vs 105.5 us per step) -- the two short launches interleave better with the
+    # acceptor units running on the other stream than one launch with twice the serial work per thread.
+    if os.environ.get("MSCHED_OFFER_FUSE", "0") != "1":
+        return False
+    return (core_group.n_hidden == 16 and price_group.n_hidden == 16 and core_group.n_actions <= 16
+            and price_group.n_actions <= 16 and price_group.n_in == 4)
+
+
+def offer_unit_forward(core_group, price_group, x, x_stride, units, n_envs, n_cores, env_stride=0,
+                       seeds=(0, 0), step=0, row_offset=0, u=None, core_out=None, price_out=None,
+                       core_rec=None, price_rec=None, action_rec_stride=0, x_used=None, step_dev=None):
+    """FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332) for every offer unit in ONE launch:
+    core chooser on the offer observation row, then the price chooser on the 4 values of the chosen core.
+    u: optional pair of float32 [M] draw overrides; core_out / price_out: optional (action int32 [M],
+    logprob float32 [M]) tensors; core_rec / price_rec: int16 views into the action record; x_used: int16
+    [M][4] inputs fed to the price chooser.  Returns ((core action, core logprob), (price action, price logprob))."""
+    dev = x.device
+    M = n_envs * units
+    outs = []
+    for o in (core_out, price_out):
+        if o is None:
+            o = (torch.empty(M, dtype=torch.int32, device=dev), torch.empty(M, dtype=torch.float32, device=dev))
+        outs.append(o)
+    uu = [None, None]
+    if u is not None:
+        uu = [torch.as_tensor(v, dtype=torch.float32).to(dev).contiguous() for v in u]
+    ioc = _make_io(x, x_stride, units, n_envs, env_stride, seeds[0], step, row_offset, uu[0], outs[0][0], outs[0][1],
+                   None, core_rec, action_rec_stride, None, n_cores, None, None, step_dev)
+    iop = _make_io(x, x_stride, units, n_envs, env_stride, seeds[1], step, row_offset, uu[1], outs[1][0], outs[1][1],
+                   None, price_rec, action_rec_stride, None, n_cores, x_used, None, step_dev)
+    L.check(L.lib().msched_offer_unit_forward(C.byref(core_group.desc), C.byref(ioc), C.byref(price_group.desc),
+                                              C.byref(iop), _stream(dev)))
+    return outs[0], outs[1]
+
+
 def actor_forward(group, x, x_stride, units, n_envs, env_stride=0, seed=0, step=0, row_offset=0,
                   u=None, want_probs=False, action=None, logprob=None, action_rec=None,
                   action_rec_stride=0, gather_core=None, n_cores=0, x_used=None, timeline=None, step_dev=None):
@@ -80,18 +137,8 @@ def actor_forward(group, x, x_stride, units, n_envs, env_stride=0, seed=0, step=
     probs = torch.empty((M, group.n_actions), dtype=torch.float32, device=dev) if want_probs else None
     if u is not None:
         u = torch.as_tensor(u, dtype=torch.float32).to(dev).contiguous()
-    io = L.MschedActorIO()
-    io.x, io.x_stride, io.units, io.n_envs, io.n_cores = x.data_ptr(), x_stride, units, n_envs, n_cores
-    io.env_stride, io.row_offset, io.seed, io.step = env_stride, row_offset, seed, step
-    io.u_override = None if u is None else u.data_ptr()
-    io.action, io.logprob = action.data_ptr(), logprob.data_ptr()
-    io.probs = None if probs is None else probs.data_ptr()
-    io.action_rec = None if action_rec is None else action_rec.data_ptr()
-    io.action_rec_stride = action_rec_stride
-    io.gather_core = None if gather_core is None else gather_core.data_ptr()
-    io.x_used = None if x_used is None else x_used.data_ptr()
-    io.timeline = None if timeline is None else timeline.data_ptr()
-    io.step_dev = None if step_dev is None else step_dev.data_ptr()  # int64 device counter (graph replays)
+    io = _make_io(x, x_stride, units, n_envs, env_stride, seed, step, row_offset, u, action, logprob, probs,
+                  action_rec, action_rec_stride, gather_core, n_cores, x_used, timeline, step_dev)
     L.check(L.lib().msched_actor_forward(C.byref(group.desc), C.byref(io), _stream(dev)))
     return action, logprob, probs
 

@@ -153,6 +153,48 @@ def test_price_chooser_gather_and_action_record(actor_impl):
     assert np.array_equal(r[:, 10:10 + units], np.where(core == 0, -5, act))
 
 
+def test_offer_unit_single_launch_matches_two_launch_form():
+    """msched_offer_unit_forward (core chooser + price chooser of every offer unit in one launch) gives
+    exactly what two msched_actor_forward calls give (src/PPOmodules.py:312-332), and the core chooser's
+    probabilities behind both agree with the oracle MLP."""
+    import torch
+    from marl_scheduling_b200 import policy
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(21)
+    for n_envs, units, C, P in ((777, 6, 3, 8), (130, 12, 4, 10), (1, 2, 2, 3)):
+        row = 2 * C + 2
+        x_stride = row + (row & 1) + 2
+        env_stride = units * x_stride + 3
+        xs = torch.as_tensor(rng.integers(-1, 9, (n_envs, env_stride)).astype(np.int16)).to(dev)
+        gc = policy.MlpGroup.random(row, 16, C + 1, units, dev, seed=5)
+        gp = policy.MlpGroup.random(4, 16, P + 1, units, dev, seed=6)
+        for u in (None, (rng.random(n_envs * units).astype(np.float32), rng.random(n_envs * units).astype(np.float32))):
+            rec1 = torch.full((n_envs, 40), 77, dtype=torch.int16, device=dev)
+            rec2 = rec1.clone()
+            xu1 = torch.zeros((n_envs * units, 4), dtype=torch.int16, device=dev)
+            xu2 = torch.zeros_like(xu1)
+            ca, clp, _ = policy.actor_forward(gc, xs, x_stride, units, n_envs, env_stride=env_stride, seed=31, step=9,
+                                              u=None if u is None else u[0], action_rec=rec1[:, 3:], action_rec_stride=40)
+            pa, plp, _ = policy.actor_forward(gp, xs, x_stride, units, n_envs, env_stride=env_stride, seed=32, step=9,
+                                              u=None if u is None else u[1], action_rec=rec1[:, 20:], action_rec_stride=40,
+                                              gather_core=ca, n_cores=C, x_used=xu1)
+            (ca2, clp2), (pa2, plp2) = policy.offer_unit_forward(
+                gc, gp, xs, x_stride, units, n_envs, C, env_stride=env_stride, seeds=(31, 32), step=9, u=u,
+                core_rec=rec2[:, 3:], price_rec=rec2[:, 20:], action_rec_stride=40, x_used=xu2)
+            torch.cuda.synchronize()
+            assert torch.equal(ca, ca2) and torch.equal(pa, pa2)
+            assert torch.equal(clp, clp2) and torch.equal(plp, plp2)
+            assert torch.equal(rec1, rec2) and torch.equal(xu1, xu2)
+            r = rec2.cpu().numpy()
+            assert (r[:, 20:20 + units][ca2.view(n_envs, units).cpu().numpy() == 0] == -5).all()
+    # shapes outside the fused kernel are refused, not silently served
+    from marl_scheduling_b200._lib import MschedError
+    g32 = policy.MlpGroup.random(8, 32, 4, 2, dev, seed=1)
+    gp2 = policy.MlpGroup.random(4, 16, 5, 2, dev, seed=1)
+    with pytest.raises(MschedError):
+        policy.offer_unit_forward(g32, gp2, torch.zeros((4, 16), dtype=torch.int16, device=dev), 8, 2, 4, 3)
+
+
 @pytest.mark.parametrize("shape", [(45, 32, 343, 2), (12, 32, 64, 2), (40, 64, 1323, 1), (30, 16, 130, 3)])
 def test_aggregated_head_matches_fp32_reference(shape):
     """Aggregated action heads (src/PPOmodules.py:177-232): the tensor-core kernel tiles the last
