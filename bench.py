@@ -266,6 +266,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--update-T", type=int, default=16, help="buffer length of the PPO.update measurement (0 = skip)")
     ap.add_argument("--rollout-steps", type=int, default=200,
                     help="steps of the secondary metric (env step + actor forward); 0 = skip")
     args = ap.parse_args()
@@ -602,6 +603,68 @@ def main():
                                       "gbs": 12.0 * rew.numel() / ret_us / 1e3,
                                       "algorithmic_bytes_per_element": 12}}
 
+    # ---- PPO.update on the device: one epoch = one forward+backward launch over the
+    # acceptor units' buffer (T x B samples per net) + Adam; the PyTorch autograd version of the same
+    # update is timed beside it on a smaller buffer ----
+    update = None
+    if args.update_T > 0 and dense and world == 1:
+        from marl_scheduling_b200 import policy
+        from marl_scheduling_b200.agents import BatchedPPO
+        Cc, NL = dom["C"], N * dom["L"]
+        U, n_in, A = N * Cc, 3 + 2 * NL, NL + 1
+        kw = dict(lr_actor=3e-4, lr_critic=1e-3, gamma=0.9, eps_clip=0.2, k_epochs=1, device=dev, seed=5)
+        gen_u = torch.Generator(device=dev).manual_seed(7)
+
+        def timed_update(mode, T, Bu, reps):
+            os.environ["MSCHED_PPO_UPDATE"] = mode
+            ppo = BatchedPPO(n_in, A, 16, U, U, 1, **kw)
+            xs = torch.randint(-1, 9, (T, Bu, U, n_in), generator=gen_u, dtype=torch.int16, device=dev)
+            acts = torch.randint(0, A, (T, Bu, U), generator=gen_u, dtype=torch.int32, device=dev)
+            lps = torch.full((T, Bu, U), -1.9459, device=dev)
+            rws = torch.randint(-5, 9, (T, Bu, U), generator=gen_u, device=dev).float()
+            ms = []
+            for _ in range(reps + 1):
+                ppo.buf_x, ppo.buf_a, ppo.buf_lp, ppo.buf_r = list(xs), list(acts), list(lps), list(rws)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ppo.update()
+                e1.record()
+                torch.cuda.synchronize()
+                ms.append(e0.elapsed_time(e1))
+            grad_ms = None
+            if mode == "kernel":  # the gradient launch alone
+                X = xs.view(T * Bu, U, n_in)
+                Gn = policy.returns(rws.view(T, Bu * U), 0.9, True).view(T * Bu, U)
+                ids = torch.arange(U, dtype=torch.int32, device=dev)
+                ga, gc = torch.zeros_like(ppo.actor.data), torch.zeros_like(ppo.critic.data)
+                _, ws = policy.ppo_grad(ppo.actor.data, ppo.critic.data, n_in, A, X, acts.view(T * Bu, U), lps.view(T * Bu, U),
+                                        Gn, ids, ids.view(U, 1), ga, gc)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(reps):
+                    policy.ppo_grad(ppo.actor.data, ppo.critic.data, n_in, A, X, acts.view(T * Bu, U), lps.view(T * Bu, U),
+                                    Gn, ids, ids.view(U, 1), ga, gc, workspace=ws)
+                e1.record()
+                torch.cuda.synchronize()
+                grad_ms = e0.elapsed_time(e1) / reps
+            os.environ.pop("MSCHED_PPO_UPDATE", None)
+            del xs, acts, lps, rws
+            return min(ms[1:]), grad_ms
+
+        Tk = args.update_T
+        k_ms, g_ms = timed_update("kernel", Tk, B, 3)
+        Bs = max(1, B // 16)
+        a_ms, _ = timed_update("autograd", Tk, Bs, 2)
+        k_small_ms, _ = timed_update("kernel", Tk, Bs, 3)
+        rows = Tk * B * U
+        update = {"what": "PPO.update, one epoch, acceptor nets of the workload (one net per unit): returns + forward/backward "
+                          "gradient kernel (msched_ppo_grad) + Adam (msched_adam_step)",
+                  "net": f"{n_in}->16->16->{A} actor + {n_in}->16->16->1 critic, {U} nets", "T": Tk, "envs": B, "samples": rows,
+                  "update_ms": k_ms, "grad_kernel_ms": g_ms, "samples_per_s": rows / (g_ms * 1e-3),
+                  "autograd_baseline": {"envs": Bs, "samples": Tk * Bs * U, "update_ms": a_ms, "kernel_path_update_ms_same_size": k_small_ms,
+                                        "speedup": a_ms / k_small_ms, "what": "the same update through PyTorch autograd + torch.optim.Adam"}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -644,6 +707,7 @@ def main():
                     "observe_algorithmic_bytes_per_env": ab["obs"] + ab["state"]},
         "cpu_baseline": cpu,
         "rollout_with_policy": rollout,
+        "ppo_update": update,
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
         "sticky_flags_after_warm": flags,
     }

@@ -305,6 +305,46 @@ int msched_dqn_select(const MschedMlpGroup *nets, const MschedActorIO *io, float
 int msched_returns(const float *rewards, int T, int M, double gamma, int normalise, float *out,
                    void *stream);
 
+/* ---- PPO.update on the device ----
+ * One epoch's gradient of PPO.update (src/PPOmodules.py:139-174) for a group of identically shaped
+ * ActorCritic nets (src/PPOmodules.py:25-51; 16 hidden neurons, n_in <= 64, n_actions <= 16), forward and
+ * backward in one kernel: evaluate (log-prob of the stored action, entropy, V(s)), ratios, clipped surrogate,
+ * value_coef * MseLoss (0.5) and -entropy_coef * entropy (0.01), mean over the net's samples, gradient with
+ * respect to every actor and critic parameter.  Sample (tb, u), tb in [0, n_tb) (time x environment), unit
+ * u in [0, units): observation int16 at x + tb*x_tb_stride + u*x_unit_stride, stored action / old log-prob /
+ * normalised return at index tb*units + u.  Selected net s (n_sel of them) has id net_ids[s] and learns from
+ * the units unit_ids[s*units_per_net .. +units_per_net) (every net the same number: divided nets have one
+ * unit each, shared nets several, the CENTRALISATION_SAMPLE rule a subset, src/SchedulingEnvironment.py:
+ * 314-329).  Rows net_ids[s] of grad_actor / grad_critic ([n_nets][msched_mlp_param_count], torch layout)
+ * are overwritten; other rows are not touched.  stats (optional) receives per selected net
+ * [mean -min(surr1,surr2), mean (V-G)^2, mean entropy, M].  Gradients are bit-reproducible (fixed-order
+ * reduction, no atomics).  workspace: device scratch of msched_ppo_workspace_bytes(). */
+typedef struct MschedPpoBatch {
+    const float *actor_weights, *critic_weights; /* device [n_nets][param_count(n_in,16,n_actions / 1)] */
+    int32_t n_in, n_hidden, n_actions, n_nets;
+    const int16_t *x;
+    int64_t x_tb_stride, x_unit_stride; /* int16 elements */
+    const int32_t *action;              /* [n_tb][units] */
+    const float *logprob_old, *returns; /* [n_tb][units] */
+    int64_t n_tb;
+    int32_t units, n_sel, units_per_net, reserved;
+    const int32_t *net_ids;  /* device int32 [n_sel] */
+    const int32_t *unit_ids; /* device int32 [n_sel][units_per_net] */
+    float eps_clip, entropy_coef, value_coef, reserved2;
+    float *grad_actor, *grad_critic;
+    float *stats; /* device float32 [n_sel][4] or NULL */
+    void *workspace;
+    uint64_t workspace_bytes;
+} MschedPpoBatch;
+
+int msched_ppo_workspace_bytes(const MschedPpoBatch *b, uint64_t *bytes);
+int msched_ppo_grad(const MschedPpoBatch *b, void *stream);
+
+/* torch.optim.Adam single-tensor step (src/PPOmodules.py:100-105: one learning rate per head; no weight
+ * decay, no amsgrad) over a flat float32 buffer, torch's operation order; step counts from 1. */
+int msched_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, double lr,
+                     double beta1, double beta2, double eps, int64_t step, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,19 @@ class MschedActorIO(C.Structure):
                 ("gather_core", C.c_void_p), ("x_used", C.c_void_p), ("timeline", C.c_void_p), ("step_dev", C.c_void_p)]
 
 
+class MschedPpoBatch(C.Structure):
+    _fields_ = [("actor_weights", C.c_void_p), ("critic_weights", C.c_void_p),
+                ("n_in", C.c_int32), ("n_hidden", C.c_int32), ("n_actions", C.c_int32), ("n_nets", C.c_int32),
+                ("x", C.c_void_p), ("x_tb_stride", C.c_int64), ("x_unit_stride", C.c_int64),
+                ("action", C.c_void_p), ("logprob_old", C.c_void_p), ("returns", C.c_void_p),
+                ("n_tb", C.c_int64),
+                ("units", C.c_int32), ("n_sel", C.c_int32), ("units_per_net", C.c_int32), ("reserved", C.c_int32),
+                ("net_ids", C.c_void_p), ("unit_ids", C.c_void_p),
+                ("eps_clip", C.c_float), ("entropy_coef", C.c_float), ("value_coef", C.c_float), ("reserved2", C.c_float),
+                ("grad_actor", C.c_void_p), ("grad_critic", C.c_void_p), ("stats", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_uint64)]
+
+
 # every symbol include/msched.h declares: name -> (restype, argtypes)
 P = C.c_void_p
 SYMBOLS = {
@@ -101,6 +114,9 @@ SYMBOLS = {
                                             C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),
     "msched_dqn_param_count": (C.c_int, [C.c_int, C.c_int]),
     "msched_dqn_select": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), C.c_float, P, P]),
+    "msched_ppo_workspace_bytes": (C.c_int, [C.POINTER(MschedPpoBatch), C.POINTER(C.c_uint64)]),
+    "msched_ppo_grad": (C.c_int, [C.POINTER(MschedPpoBatch), P]),
+    "msched_adam_step": (C.c_int, [P, P, P, P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, P]),
     "msched_returns": (C.c_int, [P, C.c_int, C.c_int, C.c_double, C.c_int, P, P]),
 }
 

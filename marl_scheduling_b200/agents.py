@@ -5,19 +5,58 @@
 Rollout (the hot path): actor forward + categorical sample + log-prob run in the CUDA actor kernel
 (msched_actor_forward) straight on the observation record; rewards are routed into device
 buffers; returns use msched_returns.  The PPO update itself (clipped surrogate, 0.5*MSE,
--0.01*entropy, two-LR Adam, K epochs, policy_old sync) is SURVEY.md section 8(f) row N1 and is
-implemented here with PyTorch autograd over the batched buffers.
+-0.01*entropy, two-LR Adam, K epochs, policy_old sync) is SURVEY.md section 8(f) row N1: for the
+16-wide nets (divided, locally and globally shared agents) every epoch is ONE forward+backward
+kernel (msched_ppo_grad, tensor-core sample reduction) plus msched_adam_step; the aggregated heads
+(32/64 hidden neurons, thousands of actions) use PyTorch autograd over the batched buffers.
+MSCHED_PPO_UPDATE=autograd forces the autograd path.
 """
 from __future__ import annotations
 
+import os
 import random
 
 import torch
 
 from . import policy as P
-from .distributed import allreduce_gradients
+from .distributed import allreduce_gradients, allreduce_mean_
 
 UPDATE_CHUNK = 1 << 20  # samples per autograd chunk (gradient accumulation bounds memory)
+
+
+class FlatAdam:
+    """torch.optim.Adam semantics (src/PPOmodules.py:100-105: one learning rate per head, defaults
+    otherwise) over stacked per-net parameter rows through msched_adam_step.  Every net keeps its own
+    step count, like the reference's one optimizer per PPO object."""
+
+    def __init__(self, params, lrs):
+        self.params, self.lrs = params, lrs
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+        self.t = [0] * params[0].shape[0]
+
+    def step(self, grads, nets):
+        nets = list(nets)
+        whole = len(nets) == len(self.t) and len(set(self.t)) == 1
+        for n in nets:
+            self.t[n] += 1
+        for p, g, m, v, lr in zip(self.params, grads, self.m, self.v, self.lrs):
+            if whole:
+                P.adam_step(p.view(-1), g.view(-1), m.view(-1), v.view(-1), lr, self.t[0])
+            else:
+                for n in nets:
+                    P.adam_step(p[n], g[n], m[n], v[n], lr, self.t[n])
+
+    def state_dict(self):
+        return {"kind": "FlatAdam", "t": list(self.t), "m": [x.cpu() for x in self.m], "v": [x.cpu() for x in self.v],
+                "lrs": list(self.lrs)}
+
+    def load_state_dict(self, d):
+        if d.get("kind") != "FlatAdam":
+            raise ValueError("optimizer state is not a FlatAdam state")
+        self.t = list(d["t"])
+        for dst, src in zip(self.m + self.v, list(d["m"]) + list(d["v"])):
+            dst.copy_(src.to(dst.device))
 
 
 class BatchedPPO:
@@ -35,8 +74,18 @@ class BatchedPPO:
         crit = P.MlpGroup.random(n_in, n_hidden, 1, n_nets, device, seed=seed + 7919)
         self.actor = torch.nn.Parameter(init.weights.clone())      # [n_nets, pc_actor]
         self.critic = torch.nn.Parameter(crit.weights.clone())     # [n_nets, pc_critic]
-        self.optimizer = torch.optim.Adam([{"params": [self.actor], "lr": lr_actor},
-                                           {"params": [self.critic], "lr": lr_critic}])
+        self.use_kernels = (P.ppo_grad_supported(n_in, n_hidden, n_actions)
+                            and os.environ.get("MSCHED_PPO_UPDATE", "kernel") != "autograd")
+        if self.use_kernels:
+            self.optimizer = FlatAdam([self.actor.data, self.critic.data], [lr_actor, lr_critic])
+            # one flat gradient buffer for both heads: a single all-reduce per epoch under data parallelism
+            self._grad = torch.zeros(self.actor.numel() + self.critic.numel(), device=device)
+            self._ga = self._grad[: self.actor.numel()].view_as(self.actor)
+            self._gc = self._grad[self.actor.numel():].view_as(self.critic)
+            self._ws, self._ids = None, {}
+        else:
+            self.optimizer = torch.optim.Adam([{"params": [self.actor], "lr": lr_actor},
+                                               {"params": [self.critic], "lr": lr_critic}])
         self.policy_old = P.MlpGroup(n_in, n_hidden, n_actions, self.actor.detach().clone(), device,
                                      unit_div=unit_div)
         self.buf_x, self.buf_a, self.buf_lp, self.buf_r = [], [], [], []
@@ -93,15 +142,17 @@ class BatchedPPO:
         U = self.units
         r = torch.stack(self.buf_r).reshape(T, B * U)
         G = P.returns(r, self.gamma, normalise=True).view(T, B, U)
-        X = torch.stack(self.buf_x).float()                       # [T,B,U,in]
-        Aold = torch.stack(self.buf_a).long()
-        LPold = torch.stack(self.buf_lp)
         units = list(range(U)) if unit_subset is None else list(unit_subset)
         nets = sorted({(u // self.unit_div) % self.n_nets for u in units})
         per_net = {n: [u for u in units if (u // self.unit_div) % self.n_nets == n] for n in nets}
         m = max(len(v) for v in per_net.values())
         if any(len(v) != m for v in per_net.values()):
             raise ValueError("unit subset must give every net the same number of units")
+        if self.use_kernels:
+            return self._update_kernels(T, B, U, G, nets, per_net)
+        X = torch.stack(self.buf_x).float()                       # [T,B,U,in]
+        Aold = torch.stack(self.buf_a).long()
+        LPold = torch.stack(self.buf_lp)
         idx = torch.tensor([per_net[n] for n in nets], device=self.device)      # [n, m]
         def gather(t):  # [T,B,U,...] -> [n, T*B*m, ...]
             g = t[:, :, idx]                                          # [T,B,n,m,...]
@@ -138,6 +189,30 @@ class BatchedPPO:
             allreduce_gradients([self.actor, self.critic])
             self.optimizer.step()
         return float(mse.mean())
+
+    def _update_kernels(self, T, B, U, G, nets, per_net):
+        """K epochs of msched_ppo_grad (forward + backward of every selected net in one launch) and
+        msched_adam_step on the stacked buffers; the observations stay int16."""
+        dev = self.device
+        X = torch.stack(self.buf_x).view(T * B, U, self.n_in)       # int16 [TB,U,in]
+        Aold = torch.stack(self.buf_a).view(T * B, U)                 # int32
+        LPold = torch.stack(self.buf_lp).view(T * B, U)
+        key = tuple((n, tuple(per_net[n])) for n in nets)
+        if key not in self._ids:
+            self._ids[key] = (torch.tensor(nets, dtype=torch.int32, device=dev),
+                              torch.tensor([per_net[n] for n in nets], dtype=torch.int32, device=dev))
+        net_ids, unit_ids = self._ids[key]
+        stats = None
+        for _ in range(self.K_epochs):
+            if len(nets) != self.n_nets:
+                self._grad.zero_()
+            stats, self._ws = P.ppo_grad(self.actor.data, self.critic.data, self.n_in, self.A, X, Aold, LPold,
+                                         G.view(T * B, U), net_ids, unit_ids, self._ga, self._gc,
+                                         eps_clip=self.eps_clip, stats=stats, workspace=self._ws)
+            # data-parallel env shards: one flat-bucket all-reduce per epoch (NCCL over NVLink)
+            allreduce_mean_(self._grad)
+            self.optimizer.step([self._ga, self._gc], nets)
+        return float(stats[:, 1].mean())
 
     def sync_old_and_clear(self):
         self.policy_old.weights.copy_(self.actor.detach())

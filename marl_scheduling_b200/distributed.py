@@ -43,6 +43,15 @@ def allreduce_gradients(params):
         o += n
 
 
+def allreduce_mean_(flat):
+    """In-place average of one flat gradient buffer over all ranks (a single all_reduce)."""
+    if not is_distributed():
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+    flat /= dist.get_world_size()
+    return flat
+
+
 def max_over_ranks(value, device="cpu"):
     """Device-timed durations are reported as the max over ranks."""
     t = torch.tensor([float(value)], dtype=torch.float64, device=device)

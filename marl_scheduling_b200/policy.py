@@ -154,6 +154,53 @@ def returns(rewards, gamma, normalise=True, out=None):
     return out
 
 
+def ppo_grad_supported(n_in, n_hidden, n_actions):
+    """Shapes msched_ppo_grad serves (the divided / shared 16-wide nets); others use autograd."""
+    return n_hidden == 16 and 1 <= n_in <= 64 and 1 <= n_actions <= 16
+
+
+def ppo_grad(actor_w, critic_w, n_in, n_actions, x, action, logprob_old, returns, net_ids, unit_ids,
+             grad_actor, grad_critic, eps_clip=0.2, entropy_coef=0.01, value_coef=0.5, stats=None, workspace=None):
+    """One epoch's PPO gradient (src/PPOmodules.py:139-174) for the selected nets, forward + backward in
+    one kernel.  actor_w / critic_w: float32 [n_nets, pc] on the device; x: int16 [TB, U, n_in] view (any
+    tb / unit strides, innermost contiguous); action int32 / logprob_old / returns float32: contiguous
+    [TB, U]; net_ids int32 [n_sel], unit_ids int32 [n_sel, m] on the device.  Rows net_ids of grad_actor /
+    grad_critic are overwritten.  Returns (stats [n_sel, 4], workspace) for reuse."""
+    dev = x.device
+    TB, U = x.shape[0], x.shape[1]
+    assert x.dtype == torch.int16 and x.stride(2) == 1 and x.shape[2] == n_in
+    for t in (action, logprob_old, returns):
+        assert t.is_contiguous() and t.numel() == TB * U
+    assert action.dtype == torch.int32 and net_ids.dtype == torch.int32 and unit_ids.dtype == torch.int32
+    b = L.MschedPpoBatch()
+    b.actor_weights, b.critic_weights = actor_w.data_ptr(), critic_w.data_ptr()
+    b.n_in, b.n_hidden, b.n_actions, b.n_nets = n_in, 16, n_actions, actor_w.shape[0]
+    b.x, b.x_tb_stride, b.x_unit_stride = x.data_ptr(), x.stride(0), x.stride(1)
+    b.action, b.logprob_old, b.returns = action.data_ptr(), logprob_old.data_ptr(), returns.data_ptr()
+    b.n_tb, b.units, b.n_sel, b.units_per_net = TB, U, unit_ids.shape[0], unit_ids.shape[1]
+    b.net_ids, b.unit_ids = net_ids.data_ptr(), unit_ids.data_ptr()
+    b.eps_clip, b.entropy_coef, b.value_coef = eps_clip, entropy_coef, value_coef
+    b.grad_actor, b.grad_critic = grad_actor.data_ptr(), grad_critic.data_ptr()
+    if stats is None:
+        stats = torch.empty((unit_ids.shape[0], 4), dtype=torch.float32, device=dev)
+    b.stats = stats.data_ptr()
+    need = C.c_uint64()
+    L.check(L.lib().msched_ppo_workspace_bytes(C.byref(b), C.byref(need)))
+    if workspace is None or workspace.numel() * 4 < need.value:
+        workspace = torch.empty((need.value + 3) // 4, dtype=torch.float32, device=dev)
+    b.workspace, b.workspace_bytes = workspace.data_ptr(), workspace.numel() * 4
+    L.check(L.lib().msched_ppo_grad(C.byref(b), _stream(dev)))
+    return stats, workspace
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999, eps=1e-8):
+    """torch.optim.Adam's step over a flat float32 device buffer, in place (step counts from 1)."""
+    for t in (param, grad, exp_avg, exp_avg_sq):
+        assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == param.numel()
+    L.check(L.lib().msched_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                     param.numel(), float(lr), beta1, beta2, eps, int(step), _stream(param.device)))
+
+
 def smoke_check(env, obs):
     """One actor forward on the env's acceptor observations and one returns launch, checked
     against the CPU oracle (used by __graft_entry__.smoke)."""

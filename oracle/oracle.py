@@ -236,3 +236,84 @@ def philox(ctr, key):
     o = np.zeros(4, np.uint32)
     lib().msor_philox(_p(c), _p(k), _p(o))
     return o
+
+
+# ---- PPO.update, numpy float64 restatement with a hand-written backward sweep --------
+def _unpack_net(flat, n_in, H, A):
+    o, out = 0, []
+    for shape in ((H, n_in), (H,), (H, H), (H,), (A, H), (A,)):
+        n = int(np.prod(shape))
+        out.append(np.asarray(flat[o:o + n], np.float64).reshape(shape))
+        o += n
+    return out
+
+
+def _mlp_fwd_bwd(flat, x, dout_fn, n_in, H, A):
+    """Linear-Tanh-Linear-Tanh-Linear (src/PPOmodules.py:32-50); dout_fn(z) -> dL/dz; returns (z, flat grad)."""
+    W1, b1, W2, b2, W3, b3 = _unpack_net(flat, n_in, H, A)
+    h1 = np.tanh(x @ W1.T + b1)
+    h2 = np.tanh(h1 @ W2.T + b2)
+    z = h2 @ W3.T + b3
+    dz = dout_fn(z)
+    da2 = (dz @ W3) * (1 - h2 * h2)
+    da1 = (da2 @ W2) * (1 - h1 * h1)
+    g = [da1.T @ x, da1.sum(0), da2.T @ h1, da2.sum(0), dz.T @ h2, dz.sum(0)]
+    return z, np.concatenate([a.reshape(-1) for a in g])
+
+
+def ppo_loss_grads(actor, critic, x, action, logp_old, G, eps_clip, n_hidden=16):
+    """Gradient of loss.mean() of src/PPOmodules.py:139-174 for one ActorCritic over its samples:
+    evaluate (:65-72), ratios, surr1/surr2 with torch.min / torch.clamp subgradients, 0.5*MseLoss (a batch
+    mean), -0.01*entropy.  Returns (grad actor, grad critic, [mean -surr, mean mse, mean entropy])."""
+    x = np.asarray(x, np.float64)
+    M, n_in = x.shape
+    H = n_hidden
+    A = (len(actor) - (H * n_in + H + H * H + H)) // (H + 1)
+    G = np.asarray(G, np.float64)
+    vbox = {}
+
+    def dcritic(z):
+        vbox["v"] = z[:, 0]
+        return ((z[:, 0] - G) / M)[:, None]          # d/dv of 0.5*mean((v-G)^2)
+    _, gc = _mlp_fwd_bwd(critic, x, dcritic, n_in, H, 1)
+    v = vbox["v"]
+    sbox = {}
+
+    def dactor(z):
+        z = z - z.max(1, keepdims=True)
+        logp = z - np.log(np.exp(z).sum(1, keepdims=True))
+        p = np.exp(logp)
+        ent = -(p * logp).sum(1)
+        lpa = logp[np.arange(M), action]
+        ratio = np.exp(lpa - logp_old)
+        adv = G - v
+        s1, s2 = ratio * adv, np.clip(ratio, 1 - eps_clip, 1 + eps_clip) * adv
+        inr = (ratio >= 1 - eps_clip) & (ratio <= 1 + eps_clip)
+        d = np.where((s1 < s2) | inr, adv, 0.0)
+        onehot = np.zeros_like(p)
+        onehot[np.arange(M), action] = 1.0
+        sbox["s"] = [float((-np.minimum(s1, s2)).mean()), float(((v - G) ** 2).mean()), float(ent.mean())]
+        return ((-d * ratio)[:, None] * (onehot - p) + 0.01 * p * (logp + ent[:, None])) / M
+    _, ga = _mlp_fwd_bwd(actor, x, dactor, n_in, H, A)
+    return ga, gc, sbox["s"]
+
+
+def adam_step(p, g, m, v, lr, step, b1=0.9, b2=0.999, eps=1e-8):
+    """torch.optim.Adam (src/PPOmodules.py:100-105), float64."""
+    m[:] = m + (g - m) * (1 - b1)
+    v[:] = v * b2 + (1 - b2) * g * g
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    p -= (lr / bc1) * m / (np.sqrt(v) / np.sqrt(bc2) + eps)
+
+
+def ppo_update(actor0, critic0, states, actions, logp_old, rewards, gamma, eps_clip, K, lr_actor, lr_critic):
+    """PPO.update (src/PPOmodules.py:127-174) for one world: returns, K epochs, two-learning-rate Adam."""
+    T = len(rewards)
+    G = returns(np.asarray(rewards, np.float64).reshape(T, 1), gamma, True)[:, 0].astype(np.float64)
+    a, c = np.asarray(actor0, np.float64).copy(), np.asarray(critic0, np.float64).copy()
+    ma, va, mc, vc = (np.zeros_like(t) for t in (a, a, c, c))
+    for k in range(1, K + 1):
+        ga, gc, _ = ppo_loss_grads(a, c, states, actions, logp_old, G, eps_clip)
+        adam_step(a, ga, ma, va, lr_actor, k)
+        adam_step(c, gc, mc, vc, lr_critic, k)
+    return a, c

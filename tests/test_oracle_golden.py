@@ -155,3 +155,22 @@ def test_oracle_episode_statistics_match_reference_records(name):
     else:
         assert np.array_equal(orc.stats()[0][:, :2].astype(np.int64), exp[:, :2]), name
     assert int(orc.stats()[0][:, 3].sum()) == int(tr["n_term"].sum())
+
+
+def test_ppo_update_oracle_reproduces_the_reference_update():
+    from helpers import GOLDEN
+    """oracle.ppo_update (hand-written float64 backward + Adam) against the weights the unmodified reference
+    PPO.update produced (tests/golden/ppo_update.npz, oracle/gen_ppo_golden.py)."""
+    from oracle import oracle as O
+    z = np.load(__import__("os").path.join(GOLDEN, "ppo_update.npz"))
+    tags = [t[:-len(".states")] for t in z.files if t.endswith(".states")]
+    assert len(tags) == 3
+    for tag in tags:
+        K = int(z[tag + ".K"])
+        a, c = O.ppo_update(z[tag + ".actor0"], z[tag + ".critic0"], z[tag + ".states"], z[tag + ".actions"].astype(np.int64),
+                            z[tag + ".logprobs"].astype(np.float64), z[tag + ".rewards"], float(z[tag + ".gamma"]),
+                            float(z[tag + ".eps_clip"]), K, float(z[tag + ".lr_actor"]), float(z[tag + ".lr_critic"]))
+        for got, ref, lr in ((a, z[tag + ".actor1"], float(z[tag + ".lr_actor"])), (c, z[tag + ".critic1"], float(z[tag + ".lr_critic"]))):
+            diff = np.abs(got - ref.astype(np.float64))
+            assert diff.max() <= 2.0 * lr * K, (tag, diff.max())
+            assert np.mean(diff > 2e-6) < 0.02, (tag, np.mean(diff > 2e-6), diff.max())
