@@ -241,6 +241,22 @@ def smoke_check(env, obs):
             p2, _, _ = O.mlp_forward(xs2[:, n], ws[0].reshape(32, Wd), ws[1], ws[2].reshape(32, 32), ws[3],
                                      ws[4].reshape(A2, 32), ws[5])
             np.testing.assert_allclose(pr2[:, n], p2, rtol=5e-5, atol=1e-7)
+    # PPO.update gradient kernel (forward + backward, tensor-core sample reduction) against the oracle's
+    # float64 backward sweep, on the acceptor observations of unit 0
+    gen = torch.Generator().manual_seed(4)
+    crit = MlpGroup.random(Wd, 16, 1, N * Cc, env.device, seed=5)
+    xu = x.reshape(B, N * Cc, Wd).contiguous()
+    a_old = torch.randint(0, A, (B, N * Cc), generator=gen, dtype=torch.int32).to(env.device)
+    lp_old = (torch.randn(B, N * Cc, generator=gen) * 0.3 - float(np.log(A))).to(env.device)
+    Gr = torch.randn(B, N * Cc, generator=gen).to(env.device)
+    ids = torch.zeros((1, 1), dtype=torch.int32, device=env.device)
+    ga, gc = torch.zeros_like(grp.weights), torch.zeros_like(crit.weights)
+    ppo_grad(grp.weights, crit.weights, Wd, A, xu, a_old, lp_old, Gr, ids.view(-1), ids, ga, gc)
+    oa, oc, _ = O.ppo_loss_grads(grp.weights[0].cpu().numpy(), crit.weights[0].cpu().numpy(), xu[:, 0].cpu().numpy(),
+                                 a_old[:, 0].cpu().numpy().astype(np.int64), lp_old[:, 0].cpu().numpy().astype(np.float64),
+                                 Gr[:, 0].cpu().numpy(), 0.2)
+    np.testing.assert_allclose(ga[0].cpu().numpy(), oa, rtol=1e-4, atol=1e-5 * np.abs(oa).max())
+    np.testing.assert_allclose(gc[0].cpu().numpy(), oc, rtol=1e-4, atol=1e-5 * np.abs(oc).max())
     r = torch.randint(-5, 12, (50, 64)).float().to(env.device)
     g = returns(r, 0.8733, True).cpu().numpy()
     go = O.returns(r.cpu().numpy().astype(np.float64), 0.8733, True)
