@@ -494,7 +494,25 @@ def main():
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * N * nE / float(te[0]), "unit": "agent-steps/s",
+        # what bounds e2e: the PCIe copies of the step's records (measured here, pinned 64 MiB, both directions)
+        hb = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+        db = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+        pcie = {}
+        for name, (dst, src) in (("h2d_gbs", (db, hb)), ("d2h_gbs", (hb, db))):
+            dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(4):
+                dst.copy_(src, non_blocking=True)
+            c1.record()
+            torch.cuda.synchronize()
+            pcie[name] = 4 * (64 << 20) / (c0.elapsed_time(c1) * 1e-3) / 1e9
+        t_bound = max(B * lay.action_halfs * 2 / (pcie["h2d_gbs"] * 1e9), B * lay.result_words * 4 / (pcie["d2h_gbs"] * 1e9))
+        pcie["bound_value"] = world * B * N / t_bound  # copies at the measured rates, both directions fully overlapped
+        pcie["frac_of_bound"] = world * B * N * nE / float(te[0]) / pcie["bound_value"]
+        del hb, db
+        e2e = {"value": world * B * N * nE / float(te[0]), "unit": "agent-steps/s", "pcie": pcie,
                "h2d_bytes_per_step": B * lay.action_halfs * 2, "d2h_bytes_per_step": B * lay.result_words * 4,
                "steps": nE, "api": "msched_step_host (pinned action records -> result records; observations stay on the device)"}
 

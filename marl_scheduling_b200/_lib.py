@@ -10,7 +10,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmsched.so")
+LIB_PATH = os.environ.get("MSCHED_LIB") or os.path.join(HERE, "libmsched.so")  # MSCHED_LIB: A/B builds of the same ABI
 CSRC = os.path.join(HERE, "csrc")
 
 ABI_VERSION = 1

@@ -469,7 +469,10 @@ inline int launch_offer_unit(const MschedMlpGroup &gc, const MschedActorIO &ioc,
     return 0;
 }
 
-// impl: 0 = tensor cores (tcgen05), 1 = fp32 SIMT
+// warp-level tensor-core kernel for the 16-wide nets: actor_mma_kernel.cuh, compiled in msched_actor_mma.cu
+int launch_actor_mma_any(const ActorArgs &a, dim3 grid, cudaStream_t s);
+
+// impl: 0 = tensor cores (tcgen05), 1 = fp32 SIMT, 2 = warp-level tensor cores (16-wide nets)
 inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io, int impl, cudaStream_t s)
 {
     if (g.n_actions > 32767) return -1;  // actions are reported as int16 in the action record
@@ -481,6 +484,10 @@ inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io
         if (g.n_hidden == 32) return launch_actor_wide<32>(a, g, grid, s);
         if (g.n_hidden == 64) return launch_actor_wide<64>(a, g, grid, s);
         return -1;
+    }
+    if (impl == 2) {
+        if (g.n_hidden != 16 || g.n_actions > 16 || g.n_in > 32) return -1;
+        return launch_actor_mma_any(a, grid, s);
     }
     if (g.n_hidden == 16) return launch_actor_h<16>(a, g, grid, impl, s);
     if (g.n_hidden == 32) return launch_actor_h<32>(a, g, grid, impl, s);

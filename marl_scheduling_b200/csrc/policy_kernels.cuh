@@ -6,6 +6,7 @@
 //   src/PPOmodules.py:128-137       PPO.update returns prologue
 #pragma once
 #include "msched_common.cuh"
+#include "policy_common.cuh"
 
 namespace msched {
 
@@ -46,47 +47,6 @@ __global__ void returns_kernel(const float *__restrict__ r, int T, int M, double
 // grid = (ceil(n_envs / 128), units); a CTA evaluates ONE unit (one net) for 128 consecutive
 // environments, so every lane reads the same weight at the same time (shared-memory broadcast,
 // 128-bit) and FFMA is the bound.  Weights are staged transposed ([in][out]) in shared memory.
-struct ActorArgs {
-    const float *weights;  // n_nets * param_count floats, torch layout per net
-    const int16_t *x;
-    long long envStride, unitStride;  // in int16 elements
-    int nIn, nHidden, nActions, nNets, unitDiv, units, nEnvs;
-    unsigned long long seed, step;
-    long long rowOffset;
-    const float *uOverride;  // [M] or null
-    int32_t *action;         // [M] or null
-    float *logprob;          // [M] or null
-    float *probs;            // [M][A] or null
-    int16_t *actionRec;      // reported action also stored at actionRec[env*actionRecStride + unit]
-    long long actionRecStride;
-    const int32_t *gatherCore;  // FreePriceOfferPPO price chooser: gather the 4 inputs by this action
-    int16_t *xUsed;             // [M][nIn] input actually fed, or null
-    int nCores;
-    unsigned long long *timeline;  // diagnostics, or null
-    const unsigned long long *stepDev;  // device-side step counter (CUDA-graph replays), or null -> `step`
-};
-
-constexpr int kActorMaxActions = 64;
-
-// Softmax -> Categorical(probs): sample by inverse CDF, log_prob with torch's renormalisation and
-// clamp to [eps, 1-eps] (src/PPOmodules.py:53-63); one row per thread, logits in registers
-// tanh with 2 MUFU ops: 1 - 2/(e^{2x}+1).  Absolute error < 3e-7 on the whole range (what matters
-// downstream: the activations feed a Linear layer), exact limits for |x| -> inf, tanh(0) = 0
-constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
-__device__ __forceinline__ float ex2_approx(float x)
-{
-    float r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float fast_tanh(float x)
-{
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));  // e^{2x}
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.f));
-    return fmaf(-2.f, r, 1.f);
-}
-
 // lg[] are BASE-2 logits (the callers fold log2(e) into the last layer's weights and bias when they
 // stage them), so the softmax needs one ex2 per action; lg[o] must be -inf for o >= A (padded
 // bias), so every sweep runs unpredicated over the AP registers

@@ -23,7 +23,7 @@
 //   dL/dV   = 2*c_val*(V - G)                                                    (critic, MseLoss is a batch mean)
 #pragma once
 #include "msched_common.cuh"
-#include "policy_kernels.cuh"
+#include "policy_common.cuh"
 
 namespace msched {
 
@@ -67,20 +67,6 @@ struct PpoNet {
         for (int i = threadIdx.x; i < Apad; i += blockDim.x) b3[i] = i < A ? w3[A * H + i] : 0.f;
     }
 };
-
-__device__ __forceinline__ void tf32_split(float v, uint32_t &hi, uint32_t &lo)
-{
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(v));
-    const float r = v - __uint_as_float(hi);
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
-}
-
-__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
-{
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
 
 // acc[nt] (16 x 8 each) += sum over the warp's 32 samples r of Am[m][r] * Bn[nt*8 + n][r]; both buffers are
 // element-major [element][kPpoStride].  Elements of Bn at or beyond nValid are treated as zero (stale data).
@@ -231,8 +217,12 @@ __device__ __forceinline__ void scatter_accumulators(float *red, int nIn, int A,
 }
 
 // NT1 = ceil(nIn / 8) input tiles, NT3 = ceil(A / 8) action tiles
+#ifndef MSCHED_PPO_MINB
+#define MSCHED_PPO_MINB 4
+#endif
+
 template <int NT1, int NT3>
-__global__ void __launch_bounds__(128) ppo_grad_kernel(const PpoArgs a)
+__global__ void __launch_bounds__(128, MSCHED_PPO_MINB) ppo_grad_kernel(const PpoArgs a)
 {
     constexpr int H = kPpoH, AP = NT3 * 8;
     extern __shared__ __align__(16) float sm[];
@@ -280,9 +270,27 @@ __global__ void __launch_bounds__(128) ppo_grad_kernel(const PpoArgs a)
         }
         const long long r = tb * a.U + u;
         const int16_t *xr = a.x + tb * a.xTbStride + (long long)u * a.xUnitStride;
+#ifndef MSCHED_PPO_NO_PREFETCH
+        {   // the next tile's rows start their way from HBM now (strided 2-byte loads are latency-bound)
+            const long long q2 = q + (long long)gridDim.x * 128;
+            if (q2 < total) {
+                const long long tb2 = q2 / a.m;
+                const int u2 = a.unitIds[(size_t)sel * a.m + (int)(q2 - tb2 * a.m)];
+                const int16_t *x2 = a.x + tb2 * a.xTbStride + (long long)u2 * a.xUnitStride;
+                prefetch_l1(x2);
+                prefetch_l1(x2 + nIn - 1);
+                const long long r2 = tb2 * a.U + u2;
+                prefetch_l1(a.ret + r2);
+                prefetch_l1(a.action + r2);
+                prefetch_l1(a.logpOld + r2);
+            }
+        }
+#endif
         __syncwarp();  // last tile's fragment loads of bufX are done
         for (int k = 0; k < NT1 * 8; ++k) bufX[k * kPpoStride + lane] = (live && k < nIn) ? (float)xr[k] : 0.f;
         const float G = live ? a.ret[r] : 0.f;
+        const int aSel = live ? a.action[r] : 0;
+        const float lpOld = live ? a.logpOld[r] : 0.f;
         const float lv = live ? 1.f : 0.f;
 
         // ---- critic: V(s), dL/dV = 2*c_val*(V - G) ----
@@ -335,7 +343,6 @@ __global__ void __launch_bounds__(128) ppo_grad_kernel(const PpoArgs a)
 #pragma unroll
             for (int o = 0; o < AP; ++o) se += __expf(z[o] - mx);
             const float lse = mx + logf(se);
-            const int aSel = live ? a.action[r] : 0;
             float ent = 0.f, lpa = 0.f;
             float pr[AP];
 #pragma unroll
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(128) ppo_grad_kernel(const PpoArgs a)
                 lpa = o == aSel ? lp : lpa;
                 z[o] = lp;
             }
-            const float ratio = __expf(lpa - (live ? a.logpOld[r] : 0.f));
+            const float ratio = __expf(lpa - lpOld);
             const float adv = G - V;
             const float lo = 1.f - a.epsClip, hi = 1.f + a.epsClip;
             const float s1 = ratio * adv, s2 = fminf(fmaxf(ratio, lo), hi) * adv;

@@ -10,9 +10,10 @@ from helpers import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tc", "simt"])
+@pytest.fixture(params=["tc", "simt", "mma"])
 def actor_impl(request, monkeypatch):
-    """Both actor kernels: tcgen05 tensor cores (3xTF32) and fp32 SIMT."""
+    """The actor kernels: tcgen05 tensor cores (3xTF32), fp32 SIMT, and the warp-level tensor-core kernel of
+    the 16-wide nets (shapes it does not serve fall back to the default choice)."""
     monkeypatch.setenv("MSCHED_ACTOR_IMPL", request.param)
     return request.param
 
@@ -72,6 +73,45 @@ def test_actor_forward_grouped_nets_and_strides_match_oracle(actor_impl):
         sure = margin > 1e-5
         assert np.array_equal(act[n::units][sure], a[sure])
         np.testing.assert_allclose(lp[n::units][sure], l[sure], rtol=1e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize("nin,A,units", [(27, 13, 16), (10, 5, 12), (4, 9, 6), (32, 16, 3), (1, 1, 1), (15, 7, 6)])
+def test_warp_mma_actor_agrees_with_the_simt_kernel(monkeypatch, nin, A, units):
+    """The warp-level tensor-core kernel (the default for 16-wide nets) against the fp32 SIMT kernel on the same
+    rows and draws: probabilities to 2e-5, identical actions wherever the draw is not within 1e-5 of a CDF step,
+    ragged row counts (tiles of 128 / 32 / 16 rows only partly filled)."""
+    import torch
+    from marl_scheduling_b200 import policy
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(nin * 31 + A)
+    for n_envs in (1, 17, 133, 4099):
+        stride = nin + 3
+        env_stride = units * stride + 2
+        xs = torch.as_tensor(rng.integers(-3, 40, (n_envs, env_stride)).astype(np.int16)).to(dev)
+        grp = policy.MlpGroup.random(nin, 16, A, units, dev, seed=7)
+        u = rng.random(n_envs * units).astype(np.float32)
+        out = {}
+        for impl in ("simt", "mma"):
+            monkeypatch.setenv("MSCHED_ACTOR_IMPL", impl)
+            rec = torch.full((n_envs, units + 4), 77, dtype=torch.int16, device=dev)
+            act, lp, pr = policy.actor_forward(grp, xs, stride, units, n_envs, env_stride=env_stride, u=u, want_probs=True,
+                                               action_rec=rec[:, 2:], action_rec_stride=units + 4)
+            out[impl] = (act.cpu().numpy(), lp.cpu().numpy(), pr.cpu().numpy(), rec.cpu().numpy())
+        (a1, l1, p1, r1), (a2, l2, p2, r2) = out["simt"], out["mma"]
+        np.testing.assert_allclose(p2, p1, rtol=2e-5, atol=1e-7)
+        cdf = np.cumsum(p1, 1)
+        sure = np.abs(cdf - (u * p1.sum(1))[:, None]).min(1) > 1e-5
+        assert sure.mean() > 0.99
+        assert np.array_equal(a1[sure], a2[sure])
+        np.testing.assert_allclose(l2[sure], l1[sure], rtol=1e-4, atol=2e-5)
+        assert (r2[:, :2] == 77).all() and (r2[:, 2 + units:] == 77).all()
+        assert np.array_equal(r2[:, 2:2 + units].reshape(-1)[sure], a2[sure])
+        # and the device Philox stream is the same one: same actions without the override
+        monkeypatch.setenv("MSCHED_ACTOR_IMPL", "simt")
+        b1, _, _ = policy.actor_forward(grp, xs, stride, units, n_envs, env_stride=env_stride, seed=5, step=2)
+        monkeypatch.setenv("MSCHED_ACTOR_IMPL", "mma")
+        b2, _, _ = policy.actor_forward(grp, xs, stride, units, n_envs, env_stride=env_stride, seed=5, step=2)
+        assert (b1 != b2).float().mean().item() < 1e-3
 
 
 def test_actor_sampling_is_distributionally_correct(actor_impl):
@@ -153,13 +193,14 @@ def test_price_chooser_gather_and_action_record(actor_impl):
     assert np.array_equal(r[:, 10:10 + units], np.where(core == 0, -5, act))
 
 
-def test_offer_unit_single_launch_matches_two_launch_form():
+def test_offer_unit_single_launch_matches_two_launch_form(monkeypatch):
     """msched_offer_unit_forward (core chooser + price chooser of every offer unit in one launch) gives
     exactly what two msched_actor_forward calls give (src/PPOmodules.py:312-332), and the core chooser's
     probabilities behind both agree with the oracle MLP."""
     import torch
     from marl_scheduling_b200 import policy
     dev = torch.device("cuda", 0)
+    monkeypatch.setenv("MSCHED_ACTOR_IMPL", "simt")  # the single launch is the SIMT code: bit-equal to the SIMT two-launch form
     rng = np.random.default_rng(21)
     for n_envs, units, C, P in ((777, 6, 3, 8), (130, 12, 4, 10), (1, 2, 2, 3)):
         row = 2 * C + 2
