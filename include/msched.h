@@ -198,9 +198,12 @@ int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_d
 int msched_step_observe(void *handle, const int16_t *action_dev, const double *spawn_u_dev,
                         uint32_t *result_dev, int16_t *obs_dev, void *stream);
 
-/* same call with HOST buffers (pinned recommended): H2D of the action records, the step, D2H of
- * the result records, then stream synchronise.  The batch is cut into chunks that alternate between
- * two internal streams so the copies of one chunk overlap the kernel of another.  obs_dev (DEVICE,
+/* same call with HOST buffers: the action records go in, the result records come out, then stream
+ * synchronise.  PINNED buffers (cudaHostAlloc / torch pin_memory) of an unpadded batch (B a multiple of 128)
+ * on a domain with a fused kernel are read and written by the kernel's bulk copies directly (zero-copy: one
+ * launch, the PCIe traffic of the tiles pipelines across the resident CTAs).  Otherwise: H2D of the action
+ * records, the step, D2H of the result records, the batch cut into chunks that alternate between two internal
+ * streams so the copies of one chunk overlap the kernel of another.  obs_dev (DEVICE,
  * optional): the dense observations of the new state stay on the device for the policy kernels
  * (written by the same launch when the domain fuses them).  Staging buffers are owned by the handle. */
 int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_host,

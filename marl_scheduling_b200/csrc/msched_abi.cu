@@ -580,6 +580,35 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaSetDevice(h->device));
     const bool fuse = obs_dev && h->useFused && h->fuseObs;
+    // Zero-copy path: when both host buffers are pinned (device-accessible under unified addressing) and the
+    // batch has no padding, the fused kernel's TMA bulk copies read the action tiles from and write the result
+    // tiles to HOST memory directly -- one launch, no staging copies, and the PCIe traffic of the tiles
+    // pipelines across the resident CTAs (reads of late tiles overlap writes of early ones) instead of
+    // running as three serial phases per chunk.  MSCHED_HOST_ZEROCOPY=0 keeps the staged path.
+    if (h->useFused && h->cfg.B == h->lay.padded_envs && aligned16(action_host) && aligned16(result_host)) {
+        static const bool enabled = [] { const char *e = getenv("MSCHED_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
+        cudaPointerAttributes aa{}, ra{};
+        if (enabled && cudaPointerGetAttributes(&aa, action_host) == cudaSuccess && aa.type == cudaMemoryTypeHost && aa.devicePointer &&
+            cudaPointerGetAttributes(&ra, result_host) == cudaSuccess && ra.type == cudaMemoryTypeHost && ra.devicePointer) {
+            DevParams p = h->p;
+            p.action = static_cast<const int16_t *>(aa.devicePointer);
+            p.result = static_cast<uint32_t *>(ra.devicePointer);
+            p.spawnU = nullptr;
+            p.obs = fuse ? obs_dev : nullptr;
+            p.round = (int)h->round;
+            p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
+            launch_step(h, p, s);
+            CUDA_TRY(cudaGetLastError());
+            h->round += 1;
+            if (obs_dev && !fuse) {
+                int rc = msched_observe_dense(handle, obs_dev, nullptr, stream);
+                if (rc) return rc;
+            }
+            CUDA_TRY(cudaStreamSynchronize(s));
+            return MSCHED_OK;
+        }
+        (void)cudaGetLastError();  // pageable memory: not an error, take the staged path
+    }
     // The batch is cut into chunks (multiples of the 128-env padding unit) that alternate between
     // two internal streams, so the H2D copy of one chunk, the kernel of another and the D2H copy of
     // a third overlap (PCIe is full duplex); environments are independent, so any split is exact.

@@ -41,10 +41,12 @@ int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, vo
     // staging and the three MMA round trips per tile: hidden width >= 32 or more than 16 actions
     // (measured on B200, 65,536 envs: 12->32->32->64 net 33.9 us vs 56.8 us SIMT; 15->16->16->7 net
     // 41 us vs 35 us SIMT).  MSCHED_ACTOR_IMPL=tc|simt forces one.
-    // The 16-wide nets with at most 16 actions run on the warp-level tensor-core kernel (m16n8k8 TF32,
-    // weights and activations in registers, no shared memory); MSCHED_ACTOR_IMPL=tc|simt|mma forces one.
+    // MSCHED_ACTOR_IMPL=tc|simt|mma forces one.  "mma" is the warp-level tensor-core kernel for the 16-wide nets
+    // (actor_mma_kernel.cuh): correct and parity-tested, but measured SLOWER than the SIMT kernel on B200
+    // (41 us vs 36 us, 393,216 rows of 15->16->16->7) -- legacy mma.sync TF32 issues one m16n8k8 per 32 cycles
+    // per SM sub-partition (ncu, hmma sub-pipe), i.e. the FFMA rate, and 3xTF32 needs three of them.
     const bool mmaOk = nets->n_hidden == 16 && nets->n_actions <= 16 && nets->n_in <= 32;
-    int impl = (nets->n_hidden >= 32 || nets->n_actions > 16) ? 0 : (mmaOk ? 2 : 1);
+    int impl = (nets->n_hidden >= 32 || nets->n_actions > 16) ? 0 : 1;
     if (const char *e = getenv("MSCHED_ACTOR_IMPL"))
         impl = !strcmp(e, "simt") ? 1 : (!strcmp(e, "tc") ? 0 : ((!strcmp(e, "mma") && mmaOk) ? 2 : impl));
     int rc = launch_actor_forward(*nets, *io, impl, static_cast<cudaStream_t>(stream));

@@ -97,6 +97,42 @@ __device__ __forceinline__ void outer_accumulate(float (&acc)[NT][4], const floa
     }
 }
 
+// The same contraction on the FP32 pipe (same accumulator ownership as the MMA C fragment: lane (g, t) owns
+// rows g, g+8 x columns 2t, 2t+1 of every 8-column block), four samples per 128-bit shared-memory load.
+// Legacy mma.sync TF32 runs at the FFMA rate on sm_100a (one m16n8k8 per 32 cycles per SM sub-partition) and
+// 3xTF32 needs three per product, so plain FFMA does the job in a third of the pipe time, in exact fp32.
+template <int NT>
+__device__ __forceinline__ void outer_accumulate_simt(float (&acc)[NT][4], const float *Am, const float *Bn, int nValid, int lane)
+{
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int r0 = 0; r0 < 32; r0 += 4) {
+        const float4 a0 = *reinterpret_cast<const float4 *>(Am + g * kPpoStride + r0);
+        const float4 a1 = *reinterpret_cast<const float4 *>(Am + (g + 8) * kPpoStride + r0);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+            const int n = nt * 8 + 2 * t;
+            float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+            if (n < nValid) b0 = *reinterpret_cast<const float4 *>(Bn + n * kPpoStride + r0);
+            if (n + 1 < nValid) b1 = *reinterpret_cast<const float4 *>(Bn + (n + 1) * kPpoStride + r0);
+            acc[nt][0] = fmaf(a0.x, b0.x, acc[nt][0]); acc[nt][0] = fmaf(a0.y, b0.y, acc[nt][0]);
+            acc[nt][0] = fmaf(a0.z, b0.z, acc[nt][0]); acc[nt][0] = fmaf(a0.w, b0.w, acc[nt][0]);
+            acc[nt][1] = fmaf(a0.x, b1.x, acc[nt][1]); acc[nt][1] = fmaf(a0.y, b1.y, acc[nt][1]);
+            acc[nt][1] = fmaf(a0.z, b1.z, acc[nt][1]); acc[nt][1] = fmaf(a0.w, b1.w, acc[nt][1]);
+            acc[nt][2] = fmaf(a1.x, b0.x, acc[nt][2]); acc[nt][2] = fmaf(a1.y, b0.y, acc[nt][2]);
+            acc[nt][2] = fmaf(a1.z, b0.z, acc[nt][2]); acc[nt][2] = fmaf(a1.w, b0.w, acc[nt][2]);
+            acc[nt][3] = fmaf(a1.x, b1.x, acc[nt][3]); acc[nt][3] = fmaf(a1.y, b1.y, acc[nt][3]);
+            acc[nt][3] = fmaf(a1.z, b1.z, acc[nt][3]); acc[nt][3] = fmaf(a1.w, b1.w, acc[nt][3]);
+        }
+    }
+}
+
+#ifdef MSCHED_PPO_SIMT_ACC
+#define PPO_OUTER outer_accumulate_simt
+#else
+#define PPO_OUTER outer_accumulate
+#endif
+
 // sum over the warp's samples of one element row: lane l adds 16 samples of element l & 15 (the two
 // halves are combined when the CTA partial is written)
 __device__ __forceinline__ float row_half_sum(const float *buf, int lane)
@@ -120,7 +156,7 @@ __device__ __forceinline__ void backward_hidden(const PpoNet &n, const float (&h
 #pragma unroll
     for (int k = 0; k < H; ++k) { bufD[k * kPpoStride + lane] = da2[k]; bufH[k * kPpoStride + lane] = h1[k]; }
     __syncwarp();
-    outer_accumulate<2>(acc2, bufD, bufH, H, lane);  // dW2[k_out][i_in]
+    PPO_OUTER<2>(acc2, bufD, bufH, H, lane);  // dW2[k_out][i_in]
     db2 += row_half_sum(bufD, lane);
     // dL/dh1_i = sum_k W2[k][i] * da2_k ; da1 = dh1 * (1 - h1^2)
     float da1[H];
@@ -140,7 +176,7 @@ __device__ __forceinline__ void backward_hidden(const PpoNet &n, const float (&h
 #pragma unroll
     for (int k = 0; k < H; ++k) bufD[k * kPpoStride + lane] = da1[k];
     __syncwarp();
-    outer_accumulate<NT1>(acc1, bufD, bufX, nIn, lane);  // dW1[k_out][i_in]
+    PPO_OUTER<NT1>(acc1, bufD, bufX, nIn, lane);  // dW1[k_out][i_in]
     db1 += row_half_sum(bufD, lane);
 }
 
@@ -308,7 +344,7 @@ __global__ void __launch_bounds__(128, MSCHED_PPO_MINB) ppo_grad_kernel(const Pp
             for (int k = 0; k < H; ++k) bufH[k * kPpoStride + lane] = h2[k];
             bufD[lane] = dv;
             __syncwarp();
-            outer_accumulate<1>(c3, bufH, bufD, 1, lane);  // dW3[0][k]: m = k, n = 0
+            PPO_OUTER<1>(c3, bufH, bufD, 1, lane);  // dW3[0][k]: m = k, n = 0
             cdb3 += row_half_sum(bufD, lane);              // only lanes 0 and 16 hold element 0
             float da2[H];
 #pragma unroll
@@ -373,7 +409,7 @@ __global__ void __launch_bounds__(128, MSCHED_PPO_MINB) ppo_grad_kernel(const Pp
 #pragma unroll
             for (int o = 0; o < AP; ++o) bufD[o * kPpoStride + lane] = dz[o];
             __syncwarp();
-            outer_accumulate<NT3>(a3, bufH, bufD, A, lane);  // dW3[j][k]: m = k, n = j
+            PPO_OUTER<NT3>(a3, bufH, bufD, A, lane);  // dW3[j][k]: m = k, n = j
             adb3 += row_half_sum(bufD, lane);
             float da2[H];
 #pragma unroll

@@ -211,16 +211,20 @@ def test_fault_flags():
     env.close()
 
 
-def test_step_host_matches_device_step():
+@pytest.mark.parametrize("B,pinned", [(500, True), (512, True), (1024, False), (384, True)])
+def test_step_host_matches_device_step(B, pinned):
+    """msched_step_host: the staged path (padded batch or pageable host memory: chunked H2D / kernel / D2H) and the
+    zero-copy path (pinned buffers, no padding: the kernel's bulk copies read and write host memory directly)."""
     import torch
     dom, mode = DOMS["cfg3"]
-    B = 500
     a = _env(B, dict(dom, mode=mode), auction="first", spawn="philox", seed=3)
     b = _env(B, dict(dom, mode=mode), auction="first", spawn="philox", seed=3)
     rng = np.random.default_rng(0)
     lay = a.layout
-    ah = torch.zeros((B, lay.action_halfs), dtype=torch.int16).pin_memory()
-    rh = torch.zeros((B, lay.result_words), dtype=torch.int32).pin_memory()
+    ah = torch.zeros((B, lay.action_halfs), dtype=torch.int16)
+    rh = torch.zeros((B, lay.result_words), dtype=torch.int32)
+    if pinned:
+        ah, rh = ah.pin_memory(), rh.pin_memory()
     for t in range(20):
         offc, acc, offp = random_actions(rng, B, dom, True)
         a.step(offc, acc, None, offer_price=offp)
