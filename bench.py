@@ -514,7 +514,8 @@ def main():
         del hb, db
         e2e = {"value": world * B * N * nE / float(te[0]), "unit": "agent-steps/s", "pcie": pcie,
                "h2d_bytes_per_step": B * lay.action_halfs * 2, "d2h_bytes_per_step": B * lay.result_words * 4,
-               "steps": nE, "api": "msched_step_host (pinned action records -> result records; observations stay on the device)"}
+               "steps": nE, "api": "msched_step_host (pinned action records -> result records, read and written by the kernel's bulk "
+                                   "copies over PCIe (zero-copy); observations stay on the device)"}
 
     # ---- secondary metric: the same step INCLUDING the batched actor forward of the
     # divided PPO agents (one net per unit, src/Agent.py:495-619) and, separately, the return scan ----

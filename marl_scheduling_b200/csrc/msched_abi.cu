@@ -586,19 +586,52 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
     // pipelines across the resident CTAs (reads of late tiles overlap writes of early ones) instead of
     // running as three serial phases per chunk.  MSCHED_HOST_ZEROCOPY=0 keeps the staged path.
     if (h->useFused && h->cfg.B == h->lay.padded_envs && aligned16(action_host) && aligned16(result_host)) {
-        static const bool enabled = [] { const char *e = getenv("MSCHED_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
+        // MSCHED_HOST_ZEROCOPY: 1 (default) both directions, 2 results only (actions staged by the copy engine), 0 off
+        static const int mode = [] { const char *e = getenv("MSCHED_HOST_ZEROCOPY"); return e ? atoi(e) : 1; }();
         cudaPointerAttributes aa{}, ra{};
-        if (enabled && cudaPointerGetAttributes(&aa, action_host) == cudaSuccess && aa.type == cudaMemoryTypeHost && aa.devicePointer &&
+        if (mode > 0 && cudaPointerGetAttributes(&aa, action_host) == cudaSuccess && aa.type == cudaMemoryTypeHost && aa.devicePointer &&
             cudaPointerGetAttributes(&ra, result_host) == cudaSuccess && ra.type == cudaMemoryTypeHost && ra.devicePointer) {
-            DevParams p = h->p;
-            p.action = static_cast<const int16_t *>(aa.devicePointer);
-            p.result = static_cast<uint32_t *>(ra.devicePointer);
-            p.spawnU = nullptr;
-            p.obs = fuse ? obs_dev : nullptr;
-            p.round = (int)h->round;
-            p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
-            launch_step(h, p, s);
-            CUDA_TRY(cudaGetLastError());
+            const int B = h->cfg.B, AH = h->lay.action_halfs, RW = h->lay.result_words;
+            int nChunks = 1;
+            if (const char *e = getenv("MSCHED_HOST_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 64) nChunks = v; }
+            const int chunk = ((B + nChunks - 1) / nChunks + MSCHED_TILE_ENVS - 1) / MSCHED_TILE_ENVS * MSCHED_TILE_ENVS;
+            const bool multi = chunk < B || mode == 2;
+            if (multi) {
+                CUDA_TRY(cudaEventRecord(h->evStart, s));
+                for (int k = 0; k < 2; ++k) CUDA_TRY(cudaStreamWaitEvent(h->hostStream[k], h->evStart, 0));
+            }
+            int c = 0;
+            for (int e0 = 0; e0 < B; e0 += chunk, ++c) {
+                const int n = (B - e0 < chunk) ? (B - e0) : chunk;
+                cudaStream_t cs = multi ? h->hostStream[c & 1] : s;
+                DevParams p = h->p;
+                p.B = n;
+                p.Bpad = n;  // n is a multiple of the padding unit here
+                p.state = h->p.state + (size_t)e0 * p.W;
+                p.chain = h->p.chain + (size_t)e0 * h->lay.chain_words;
+                if (mode == 2) {
+                    CUDA_TRY(cudaMemcpyAsync(h->stageAction + (size_t)e0 * AH, action_host + (size_t)e0 * AH, (size_t)n * AH * 2,
+                                             cudaMemcpyHostToDevice, cs));
+                    p.action = h->stageAction + (size_t)e0 * AH;
+                } else {
+                    p.action = static_cast<const int16_t *>(aa.devicePointer) + (size_t)e0 * AH;
+                }
+                p.result = static_cast<uint32_t *>(ra.devicePointer) + (size_t)e0 * RW;
+                p.spawnU = nullptr;
+                p.obs = fuse ? obs_dev + (size_t)e0 * h->lay.obs_halfs : nullptr;
+                p.envOffset = h->p.envOffset + e0;
+                p.round = (int)h->round;
+                p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
+                launch_step(h, p, cs, !multi);
+                CUDA_TRY(cudaGetLastError());
+            }
+            if (multi) {
+                for (int k = 0; k < 2; ++k) {
+                    CUDA_TRY(cudaEventRecord(h->evDone[k], h->hostStream[k]));
+                    CUDA_TRY(cudaStreamWaitEvent(s, h->evDone[k], 0));
+                }
+                if (h->deviceRound) bump_round_kernel<<<1, 1, 0, s>>>(h->roundDev);
+            }
             h->round += 1;
             if (obs_dev && !fuse) {
                 int rc = msched_observe_dense(handle, obs_dev, nullptr, stream);
