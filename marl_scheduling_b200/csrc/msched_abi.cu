@@ -586,7 +586,8 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
     // pipelines across the resident CTAs (reads of late tiles overlap writes of early ones) instead of
     // running as three serial phases per chunk.  MSCHED_HOST_ZEROCOPY=0 keeps the staged path.
     if (h->useFused && h->cfg.B == h->lay.padded_envs && aligned16(action_host) && aligned16(result_host)) {
-        // MSCHED_HOST_ZEROCOPY: 1 (default) both directions, 2 results only (actions staged by the copy engine), 0 off
+        // MSCHED_HOST_ZEROCOPY: 1 both directions, 2 results only (actions staged by the copy engine), 3 actions only
+        // (results staged and copied out by the copy engine, chunked so that copy k overlaps kernel k+1), 0 off
         static const int mode = [] { const char *e = getenv("MSCHED_HOST_ZEROCOPY"); return e ? atoi(e) : 1; }();
         cudaPointerAttributes aa{}, ra{};
         if (mode > 0 && cudaPointerGetAttributes(&aa, action_host) == cudaSuccess && aa.type == cudaMemoryTypeHost && aa.devicePointer &&
@@ -595,7 +596,7 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
             int nChunks = 1;
             if (const char *e = getenv("MSCHED_HOST_CHUNKS")) { const int v = atoi(e); if (v >= 1 && v <= 64) nChunks = v; }
             const int chunk = ((B + nChunks - 1) / nChunks + MSCHED_TILE_ENVS - 1) / MSCHED_TILE_ENVS * MSCHED_TILE_ENVS;
-            const bool multi = chunk < B || mode == 2;
+            const bool multi = chunk < B || mode >= 2;
             if (multi) {
                 CUDA_TRY(cudaEventRecord(h->evStart, s));
                 for (int k = 0; k < 2; ++k) CUDA_TRY(cudaStreamWaitEvent(h->hostStream[k], h->evStart, 0));
@@ -616,7 +617,7 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
                 } else {
                     p.action = static_cast<const int16_t *>(aa.devicePointer) + (size_t)e0 * AH;
                 }
-                p.result = static_cast<uint32_t *>(ra.devicePointer) + (size_t)e0 * RW;
+                p.result = mode == 3 ? h->stageResult + (size_t)e0 * RW : static_cast<uint32_t *>(ra.devicePointer) + (size_t)e0 * RW;
                 p.spawnU = nullptr;
                 p.obs = fuse ? obs_dev + (size_t)e0 * h->lay.obs_halfs : nullptr;
                 p.envOffset = h->p.envOffset + e0;
@@ -624,6 +625,9 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
                 p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
                 launch_step(h, p, cs, !multi);
                 CUDA_TRY(cudaGetLastError());
+                if (mode == 3)
+                    CUDA_TRY(cudaMemcpyAsync(result_host + (size_t)e0 * RW, h->stageResult + (size_t)e0 * RW, (size_t)n * RW * 4,
+                                             cudaMemcpyDeviceToHost, cs));
             }
             if (multi) {
                 for (int k = 0; k < 2; ++k) {
