@@ -78,8 +78,9 @@ int msched_ppo_grad(const MschedPpoBatch *b, void *stream)
     int nt1 = (b->n_in + 7) / 8;  // input tiles, rounded up to an instantiated count (1, 2, 4, 8)
     nt1 = nt1 <= 2 ? nt1 : (nt1 <= 4 ? 4 : 8);
     auto fl = [](int nIn, int A) { const int Ap = (A + 3) & ~3; return (nIn * 16 + 16 + 256 + 16 + 16 * Ap + Ap + 3) & ~3; };
-    const size_t smem = sizeof(float) * ((size_t)fl(b->n_in, b->n_actions) + fl(b->n_in, 1) + ((P + 3) & ~3) +
-                                         (size_t)4 * (nt1 * 8 + 32) * kPpoStride);
+    size_t bufFloats = (size_t)4 * (nt1 * 8 + 48) * kPpoStride;  // four warps' buffers; the CTA sum overlays them
+    if (bufFloats < (size_t)((P + 3) & ~3)) bufFloats = (size_t)((P + 3) & ~3);
+    const size_t smem = sizeof(float) * ((size_t)fl(b->n_in, b->n_actions) + fl(b->n_in, 1) + bufFloats);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     dim3 grid(gx, b->n_sel);
     int rc = -1;

@@ -144,48 +144,21 @@ __device__ __forceinline__ float row_half_sum(const float *buf, int lane)
     return s;
 }
 
-// layers 2 and 1 of the backward sweep, shared by critic and actor.  On entry da2[] holds dL/d(pre-tanh) of
-// layer 2 for this thread's sample, h1[] its first hidden layer, bufX its input (already parked).
-template <int NT1>
-__device__ __forceinline__ void backward_hidden(const PpoNet &n, const float (&h1)[kPpoH], float (&da2)[kPpoH], float *bufX, float *bufH,
-                                                float *bufD, int nIn, int lane, float (&acc1)[NT1][4], float (&acc2)[2][4],
-                                                float &db1, float &db2)
-{
-    constexpr int H = kPpoH;
-    __syncwarp();  // the previous fragment loads of bufH / bufD are done
-#pragma unroll
-    for (int k = 0; k < H; ++k) { bufD[k * kPpoStride + lane] = da2[k]; bufH[k * kPpoStride + lane] = h1[k]; }
-    __syncwarp();
-    PPO_OUTER<2>(acc2, bufD, bufH, H, lane);  // dW2[k_out][i_in]
-    db2 += row_half_sum(bufD, lane);
-    // dL/dh1_i = sum_k W2[k][i] * da2_k ; da1 = dh1 * (1 - h1^2)
-    float da1[H];
-#pragma unroll
-    for (int i = 0; i < H; ++i) {
-        const float4 *wr = reinterpret_cast<const float4 *>(n.W2t + i * H);
-        float s = 0.f;
-#pragma unroll
-        for (int k4 = 0; k4 < H / 4; ++k4) {
-            const float4 wv = wr[k4];
-            s = fmaf(wv.x, da2[4 * k4], s); s = fmaf(wv.y, da2[4 * k4 + 1], s);
-            s = fmaf(wv.z, da2[4 * k4 + 2], s); s = fmaf(wv.w, da2[4 * k4 + 3], s);
-        }
-        da1[i] = s * fmaf(-h1[i], h1[i], 1.f);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int k = 0; k < H; ++k) bufD[k * kPpoStride + lane] = da1[k];
-    __syncwarp();
-    PPO_OUTER<NT1>(acc1, bufD, bufX, nIn, lane);  // dW1[k_out][i_in]
-    db1 += row_half_sum(bufD, lane);
-}
+// The per-sample sweeps are written as RUNTIME loops over activations parked in shared memory (the buffers the
+// tensor-core contraction needs anyway) instead of fully unrolled register arrays: the first version's loop body
+// was 5,400 instructions (86 KB), more than the instruction cache holds for four CTAs in different phases
+// (ncu: no_instruction 1.3 stalls per issue).  Buffers per warp, element-major [element][kPpoStride]:
+// bufX input, bufH1 first hidden layer, bufH second hidden layer, bufD the current dL/d(pre-activation).
 
-// two hidden layers of the forward sweep
-__device__ __forceinline__ void forward_hidden(const PpoNet &n, const float *bufX, int nIn, int lane, float (&h1)[kPpoH], float (&h2)[kPpoH])
+// forward: h1 -> bufH1, h2 -> bufH (and returned in registers for the head)
+__device__ __forceinline__ void forward_hidden(const PpoNet &n, const float *bufX, float *bufH1, float *bufH, int nIn, int lane,
+                                               float (&h2)[kPpoH])
 {
     constexpr int H = kPpoH;
+    float h1[H];
 #pragma unroll
     for (int o = 0; o < H; ++o) h1[o] = n.b1[o];
+#pragma unroll 2
     for (int k = 0; k < nIn; ++k) {
         const float xv = bufX[k * kPpoStride + lane];
         const float4 *wr = reinterpret_cast<const float4 *>(n.W1t + k * H);
@@ -196,20 +169,74 @@ __device__ __forceinline__ void forward_hidden(const PpoNet &n, const float *buf
             h1[4 * o4 + 2] = fmaf(wv.z, xv, h1[4 * o4 + 2]); h1[4 * o4 + 3] = fmaf(wv.w, xv, h1[4 * o4 + 3]);
         }
     }
+    __syncwarp();  // the previous head's fragment loads of bufH1 / bufH are done
 #pragma unroll
-    for (int o = 0; o < H; ++o) { h1[o] = fast_tanh(h1[o]); h2[o] = n.b2[o]; }
-#pragma unroll
+    for (int o = 0; o < H; ++o) { bufH1[o * kPpoStride + lane] = fast_tanh(h1[o]); h2[o] = n.b2[o]; }
+#pragma unroll 2
     for (int k = 0; k < H; ++k) {
+        const float xv = bufH1[k * kPpoStride + lane];  // own column: no synchronisation needed
         const float4 *wr = reinterpret_cast<const float4 *>(n.W2t + k * H);
 #pragma unroll
         for (int o4 = 0; o4 < H / 4; ++o4) {
             const float4 wv = wr[o4];
-            h2[4 * o4] = fmaf(wv.x, h1[k], h2[4 * o4]); h2[4 * o4 + 1] = fmaf(wv.y, h1[k], h2[4 * o4 + 1]);
-            h2[4 * o4 + 2] = fmaf(wv.z, h1[k], h2[4 * o4 + 2]); h2[4 * o4 + 3] = fmaf(wv.w, h1[k], h2[4 * o4 + 3]);
+            h2[4 * o4] = fmaf(wv.x, xv, h2[4 * o4]); h2[4 * o4 + 1] = fmaf(wv.y, xv, h2[4 * o4 + 1]);
+            h2[4 * o4 + 2] = fmaf(wv.z, xv, h2[4 * o4 + 2]); h2[4 * o4 + 3] = fmaf(wv.w, xv, h2[4 * o4 + 3]);
         }
     }
 #pragma unroll
-    for (int o = 0; o < H; ++o) h2[o] = fast_tanh(h2[o]);
+    for (int o = 0; o < H; ++o) { h2[o] = fast_tanh(h2[o]); bufH[o * kPpoStride + lane] = h2[o]; }
+}
+
+// backward from the head's dL/dz (dz[0..AZ), already parked in bufD rows 0..AZ and contracted with bufH for dW3):
+// da2 = (W3^T dz) * (1 - h2^2) -> bufD, dW2 += da2 (x) h1, da1 = (W2^T da2) * (1 - h1^2) -> bufD, dW1 += da1 (x) x
+template <int NT1, int AZ>
+__device__ __forceinline__ void backward_hidden(const PpoNet &n, const float (&dz)[AZ], float *bufX, float *bufH1, float *bufH, float *bufD,
+                                                int nIn, int lane, float (&acc1)[NT1][4], float (&acc2)[2][4], float &db1, float &db2)
+{
+    constexpr int H = kPpoH;
+    __syncwarp();  // the dW3 fragment loads of bufD (dz) are done
+#pragma unroll 2
+    for (int k = 0; k < H; ++k) {
+        float s = 0.f;
+        if (AZ == 1) {
+            s = n.W3t[k * n.Apad] * dz[0];
+        } else {
+            const float4 *wr = reinterpret_cast<const float4 *>(n.W3t + k * n.Apad);
+#pragma unroll
+            for (int o4 = 0; o4 < AZ / 4; ++o4) {
+                if (4 * o4 < n.Apad) {
+                    const float4 wv = wr[o4];
+                    s = fmaf(wv.x, dz[4 * o4], s); s = fmaf(wv.y, dz[4 * o4 + 1], s);
+                    s = fmaf(wv.z, dz[4 * o4 + 2], s); s = fmaf(wv.w, dz[4 * o4 + 3], s);
+                }
+            }
+        }
+        const float h = bufH[k * kPpoStride + lane];
+        bufD[k * kPpoStride + lane] = s * fmaf(-h, h, 1.f);
+    }
+    __syncwarp();
+    PPO_OUTER<2>(acc2, bufD, bufH1, H, lane);  // dW2[k_out][i_in]
+    db2 += row_half_sum(bufD, lane);
+    float da2[H];
+#pragma unroll
+    for (int k = 0; k < H; ++k) da2[k] = bufD[k * kPpoStride + lane];
+    __syncwarp();  // the dW2 fragment loads of bufD are done
+#pragma unroll 2
+    for (int i = 0; i < H; ++i) {
+        const float4 *wr = reinterpret_cast<const float4 *>(n.W2t + i * H);
+        float s = 0.f;
+#pragma unroll
+        for (int k4 = 0; k4 < H / 4; ++k4) {
+            const float4 wv = wr[k4];
+            s = fmaf(wv.x, da2[4 * k4], s); s = fmaf(wv.y, da2[4 * k4 + 1], s);
+            s = fmaf(wv.z, da2[4 * k4 + 2], s); s = fmaf(wv.w, da2[4 * k4 + 3], s);
+        }
+        const float h = bufH1[i * kPpoStride + lane];
+        bufD[i * kPpoStride + lane] = s * fmaf(-h, h, 1.f);
+    }
+    __syncwarp();
+    PPO_OUTER<NT1>(acc1, bufD, bufX, nIn, lane);  // dW1[k_out][i_in]
+    db1 += row_half_sum(bufD, lane);
 }
 
 // write one net's accumulators of this warp into the CTA sum (shared memory, torch parameter order)
@@ -273,12 +300,11 @@ __global__ void __launch_bounds__(128, MSCHED_PPO_MINB) ppo_grad_kernel(const Pp
     float *p = sm;
     act.carve(p, nIn, A); p += (PpoNet::floats(nIn, A) + 3) & ~3;
     cri.carve(p, nIn, 1); p += (PpoNet::floats(nIn, 1) + 3) & ~3;
-    float *red = p; p += (P + 3) & ~3;
-    float *bufX = p + warp * (NT1 * 8 + 2 * H) * kPpoStride;
-    float *bufH = bufX + NT1 * 8 * kPpoStride, *bufD = bufH + H * kPpoStride;
+    float *red = p;  // the CTA sum aliases the warps' buffers: it is only used after the sample loop
+    float *bufX = p + warp * (NT1 * 8 + 3 * H) * kPpoStride;
+    float *bufH1 = bufX + NT1 * 8 * kPpoStride, *bufH = bufH1 + H * kPpoStride, *bufD = bufH + H * kPpoStride;
     act.stage(a.actorW + (size_t)net * pcA, nIn, A);
     cri.stage(a.criticW + (size_t)net * pcC, nIn, 1);
-    for (int i = threadIdx.x; i < P; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
 
     float a1[NT1][4], a2[2][4], a3[NT3][4], c1[NT1][4], c2[2][4], c3[1][4];
@@ -332,29 +358,23 @@ __global__ void __launch_bounds__(128, MSCHED_PPO_MINB) ppo_grad_kernel(const Pp
         // ---- critic: V(s), dL/dV = 2*c_val*(V - G) ----
         float V;
         {
-            float h1[H], h2[H];
-            forward_hidden(cri, bufX, nIn, lane, h1, h2);
+            float h2[H];
+            forward_hidden(cri, bufX, bufH1, bufH, nIn, lane, h2);
             V = cri.b3[0];
 #pragma unroll
             for (int k = 0; k < H; ++k) V = fmaf(cri.W3t[k * cri.Apad], h2[k], V);
-            const float dv = 2.f * a.valCoef * (V - G) * lv;
+            float dv[1] = {2.f * a.valCoef * (V - G) * lv};
             sMse += (V - G) * (V - G) * lv;
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < H; ++k) bufH[k * kPpoStride + lane] = h2[k];
-            bufD[lane] = dv;
+            bufD[lane] = dv[0];  // (the forward's barrier already separates this from the previous fragment loads)
             __syncwarp();
             PPO_OUTER<1>(c3, bufH, bufD, 1, lane);  // dW3[0][k]: m = k, n = 0
-            cdb3 += row_half_sum(bufD, lane);              // only lanes 0 and 16 hold element 0
-            float da2[H];
-#pragma unroll
-            for (int k = 0; k < H; ++k) da2[k] = cri.W3t[k * cri.Apad] * dv * fmaf(-h2[k], h2[k], 1.f);
-            backward_hidden<NT1>(cri, h1, da2, bufX, bufH, bufD, nIn, lane, c1, c2, cdb1, cdb2);
+            cdb3 += row_half_sum(bufD, lane);       // only lanes 0 and 16 hold element 0
+            backward_hidden<NT1, 1>(cri, dv, bufX, bufH1, bufH, bufD, nIn, lane, c1, c2, cdb1, cdb2);
         }
         // ---- actor: log-softmax, clipped surrogate and entropy gradients ----
         {
-            float h1[H], h2[H], z[AP];
-            forward_hidden(act, bufX, nIn, lane, h1, h2);
+            float h2[H], z[AP];
+            forward_hidden(act, bufX, bufH1, bufH, nIn, lane, h2);
 #pragma unroll
             for (int o4 = 0; o4 < AP / 4; ++o4) {
                 if (4 * o4 < act.Apad) {
@@ -403,34 +423,19 @@ __global__ void __launch_bounds__(128, MSCHED_PPO_MINB) ppo_grad_kernel(const Pp
                 const float ind = o == aSel ? 1.f : 0.f;
                 dz[o] = o < A ? (cr * (ind - pr[o]) + a.entCoef * pr[o] * (z[o] + ent)) * lv : 0.f;
             }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < H; ++k) bufH[k * kPpoStride + lane] = h2[k];
 #pragma unroll
             for (int o = 0; o < AP; ++o) bufD[o * kPpoStride + lane] = dz[o];
             __syncwarp();
             PPO_OUTER<NT3>(a3, bufH, bufD, A, lane);  // dW3[j][k]: m = k, n = j
             adb3 += row_half_sum(bufD, lane);
-            float da2[H];
-#pragma unroll
-            for (int k = 0; k < H; ++k) {
-                const float4 *wr = reinterpret_cast<const float4 *>(act.W3t + k * act.Apad);
-                float s = 0.f;
-#pragma unroll
-                for (int o4 = 0; o4 < AP / 4; ++o4) {
-                    if (4 * o4 < act.Apad) {
-                        const float4 wv = wr[o4];
-                        s = fmaf(wv.x, dz[4 * o4], s); s = fmaf(wv.y, dz[4 * o4 + 1], s);
-                        s = fmaf(wv.z, dz[4 * o4 + 2], s); s = fmaf(wv.w, dz[4 * o4 + 3], s);
-                    }
-                }
-                da2[k] = s * fmaf(-h2[k], h2[k], 1.f);
-            }
-            backward_hidden<NT1>(act, h1, da2, bufX, bufH, bufD, nIn, lane, a1, a2, adb1, adb2);
+            backward_hidden<NT1, AP>(act, dz, bufX, bufH1, bufH, bufD, nIn, lane, a1, a2, adb1, adb2);
         }
     }
 
     // ---- CTA partial: the four warps add their accumulators in turn (fixed order) ----
+    __syncthreads();  // every warp is done with its buffers, which `red` overlays
+    for (int i = threadIdx.x; i < P; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
     for (int w = 0; w < 4; ++w) {
         if (warp == w) {
             scatter_accumulators<NT1, NT3>(red, nIn, A, lane, a1, a2, a3, adb1, adb2, adb3);
