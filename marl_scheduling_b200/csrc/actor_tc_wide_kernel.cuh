@@ -367,6 +367,9 @@ inline int launch_actor_shape(const ActorArgs &a, const MschedMlpGroup &g, dim3 
         actor_forward_tc<H, AP><<<dim3(gx, grid.y), 128, smem, s>>>(a);
         return 0;
     }
+    if constexpr (H > 32) {
+        return -1;  // the fp32 SIMT kernel is built for the 16- and 32-wide nets only (64 accumulators per layer spill)
+    } else {
     const int Apad = (g.n_actions + 3) & ~3;
     const size_t smem = sizeof(float) * ((size_t)g.n_in * H + H + (size_t)H * H + H + (size_t)H * Apad + Apad);
     constexpr int APS = AP <= 16 ? 16 : 64;  // the SIMT kernel is built for two action buckets only
@@ -384,6 +387,7 @@ inline int launch_actor_shape(const ActorArgs &a, const MschedMlpGroup &g, dim3 
     if (gx < 1) gx = 1;
     actor_forward_simt<H, APS><<<dim3(gx, grid.y), 128, smem, s>>>(a);
     return 0;
+    }
 }
 
 template <int H>
