@@ -335,6 +335,25 @@ inline int resident_ctas(const void *fn, size_t dynSmem, int tmemCols)
     return r < 1 ? 1 : r;
 }
 
+template <int H, int APS>
+inline int launch_actor_simt(const ActorArgs &a, size_t smem, dim3 grid, cudaStream_t s)
+{
+    static int nSm = 0, perSm = 0;
+    static size_t cachedSmem = ~(size_t)0;
+    if (!nSm || cachedSmem != smem) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev);
+        perSm = resident_ctas(reinterpret_cast<const void *>(actor_forward_simt<H, APS>), smem, 1);
+        cachedSmem = smem;
+    }
+    int gx = (nSm * perSm) / (int)grid.y;  // persistent: one resident wave, weights staged once per CTA
+    if (gx > (int)grid.x) gx = (int)grid.x;
+    if (gx < 1) gx = 1;
+    actor_forward_simt<H, APS><<<dim3(gx, grid.y), 128, smem, s>>>(a);
+    return 0;
+}
+
 template <int H, int AP>
 inline int launch_actor_shape(const ActorArgs &a, const MschedMlpGroup &g, dim3 grid, int impl, cudaStream_t s)
 {
@@ -372,21 +391,10 @@ inline int launch_actor_shape(const ActorArgs &a, const MschedMlpGroup &g, dim3 
     } else {
     const int Apad = (g.n_actions + 3) & ~3;
     const size_t smem = sizeof(float) * ((size_t)g.n_in * H + H + (size_t)H * H + H + (size_t)H * Apad + Apad);
-    constexpr int APS = AP <= 16 ? 16 : 64;  // the SIMT kernel is built for two action buckets only
-    static int nSm = 0, perSm = 0;
-    static size_t cachedSmem = ~(size_t)0;
-    if (!nSm || cachedSmem != smem) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev);
-        perSm = resident_ctas(reinterpret_cast<const void *>(actor_forward_simt<H, APS>), smem, 1);
-        cachedSmem = smem;
-    }
-    int gx = (nSm * perSm) / (int)grid.y;  // persistent: one resident wave, weights staged once per CTA
-    if (gx > (int)grid.x) gx = (int)grid.x;
-    if (gx < 1) gx = 1;
-    actor_forward_simt<H, APS><<<dim3(gx, grid.y), 128, smem, s>>>(a);
-    return 0;
+    // action buckets of the SIMT kernel: 8 (16-wide nets with up to 8 actions: half the softmax / sampling sweep
+    // of the cfg3 acceptor and core chooser), 16, 64
+    if (H == 16 && g.n_actions <= 8) return launch_actor_simt<H, 8>(a, smem, grid, s);
+    return launch_actor_simt<H, (AP <= 16 ? 16 : 64)>(a, smem, grid, s);
     }
 }
 
