@@ -49,6 +49,7 @@ int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, vo
     int impl = (nets->n_hidden >= 32 || nets->n_actions > 16) ? 0 : 1;
     if (const char *e = getenv("MSCHED_ACTOR_IMPL"))
         impl = !strcmp(e, "simt") ? 1 : (!strcmp(e, "tc") ? 0 : ((!strcmp(e, "mma") && mmaOk) ? 2 : impl));
+    if (impl == 1 && nets->n_hidden > 32) impl = 0;  // the SIMT kernel is built for the 16- and 32-wide nets
     int rc = launch_actor_forward(*nets, *io, impl, static_cast<cudaStream_t>(stream));
     if (rc == -1) return fail(MSCHED_E_ARG, "unsupported MLP shape for the actor kernel");
     if (rc == -2) return fail(MSCHED_E_CUDA, "actor kernel: shared-memory attribute rejected");
