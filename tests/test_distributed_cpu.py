@@ -30,6 +30,10 @@ def _worker(rank, world, port, q):
         b.grad = torch.arange(11.0) * (rank + 1)
         D.allreduce_gradients([a, b])
         mx = D.max_over_ranks(10.0 + rank)
+        # the PPO update kernels keep both heads' gradients in ONE flat buffer: a single all-reduce per epoch
+        flat = torch.arange(9.0) * (rank + 1)
+        D.allreduce_mean_(flat)
+        assert torch.allclose(flat, torch.arange(9.0) * 1.5)
         q.put((rank, off, n, a.grad.clone(), b.grad.clone(), mx))
         dist.barrier()
     finally:
