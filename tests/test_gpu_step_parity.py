@@ -345,3 +345,56 @@ def test_edge_domains_match_oracle(key):
             assert np.array_equal(o["offer"][B - 1], oo["obs_off"])
         env.close()
     assert ran >= 1
+
+
+@pytest.mark.parametrize("key,B", [("cfg3", 65536), ("cfg2", 65536)])
+def test_full_size_batch_windows_match_oracle_and_jobs_are_conserved(key, B):
+    """BASELINE sizes (65,536 envs per GPU, the kernels the bench launches): (1) because every device draw is
+    keyed on the GLOBAL env index, any window of the big batch must equal an oracle instance started at that env
+    offset -- three 64-env windows (first tile, middle, last tile) are compared bit-exactly every step;
+    (2) size-independent invariants over ALL envs: jobs spawned = jobs terminated + jobs present, at most C
+    acceptances per step, no sticky fault flags."""
+    import torch
+    from oracle import oracle as O
+    dom, mode = DOMS[key]
+    free = mode.startswith("free")
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    T, W, seed, base = 48, 64, 99, 1 << 20
+    env = _env(B, dict(dom, mode=mode), auction="random", spawn="philox", seed=seed, env_offset=base)
+    assert env.info()["step_impl"] == "fused"
+    wins = [0, 30016, B - W]
+    orcs = [O.Oracle(W, dom, mode, tie_mode=O.TIE_PHILOX, seed=seed, env_offset=base + w0) for w0 in wins]
+    rng = np.random.default_rng(17)
+    terminated = torch.zeros(B, dtype=torch.int64, device=env.device)
+    for t in range(T):
+        offc, acc, offp = random_actions(rng, B, dom, free)
+        r = env.step(offc, acc, None, offer_price=offp, observe=True)
+        terminated += r["n_terminated"].long()
+        assert int(r["n_accepted"].max()) <= C and int(r["flags"].max()) == 0, t
+        for w0, orc in zip(wins, orcs):
+            sl = slice(w0, w0 + W)
+            orc.step(offc[sl], acc[sl], None, offp=None if offp is None else offp[sl])
+            assert np.array_equal(r["auctioneer_idx"][sl].cpu().numpy(), orc.auc_out), (t, w0)
+            assert np.array_equal(r["agent"][sl].cpu().numpy(), orc.r_agent), (t, w0)
+            assert np.array_equal(r["acceptor"][sl].cpu().numpy(), orc.r_acceptor), (t, w0)
+            assert np.array_equal(r["auctioneer"][sl].cpu().numpy(), orc.r_auctioneer), (t, w0)
+            assert np.array_equal(r["offer"][sl].cpu().numpy().astype(np.float64), orc.r_offer), (t, w0)
+    e = env.export_state()
+    obs = {k: v.cpu().numpy() for k, v in env.obs_views().items()}
+    for w0, orc in zip(wins, orcs):
+        for b in (0, W // 2, W - 1):
+            ob = orc.export(b)
+            for k in STATE_KEYS:
+                assert np.array_equal(np.asarray(e[k][w0 + b]), np.asarray(ob[k])), (w0, b, k)
+            assert np.array_equal(e["chain"][w0 + b], ob["chain"]), (w0, b)
+            oo = orc.observe(b)
+            assert np.array_equal(obs["acceptor"][w0 + b], oo["obs_acc"])
+            assert np.array_equal(obs["offer"][w0 + b], oo["obs_off"])
+            assert np.array_equal(obs["auctioneer"][w0 + b], oo["obs_auc"])
+    # conservation over all 65,536 envs: every job ever created (IDs 1 .. counter-1) is on a core, in a slot, or done
+    present = ((np.asarray(e["core_jobid"]).reshape(B, -1) > 0).sum(1)
+               + (np.asarray(e["slot_jobid"]).reshape(B, -1) > 0).sum(1))
+    spawned = np.asarray(e["job_counter"]).astype(np.int64) - 1
+    assert np.array_equal(spawned, terminated.cpu().numpy() + present)
+    assert spawned.min() > 0 and len(np.unique(spawned)) > 3      # the envs really diverged
+    env.close()
