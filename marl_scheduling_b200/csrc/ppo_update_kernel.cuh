@@ -25,6 +25,11 @@
 #include "msched_common.cuh"
 #include "policy_common.cuh"
 
+#ifndef MSCHED_PPO_UNROLL
+#define MSCHED_PPO_UNROLL 2  // unroll factor of the per-sample runtime sweeps (code size against loop overhead)
+#endif
+constexpr int kPpoUnroll = MSCHED_PPO_UNROLL;
+
 namespace msched {
 
 struct PpoArgs {
@@ -158,7 +163,7 @@ __device__ __forceinline__ void forward_hidden(const PpoNet &n, const float *buf
     float h1[H];
 #pragma unroll
     for (int o = 0; o < H; ++o) h1[o] = n.b1[o];
-#pragma unroll 2
+#pragma unroll kPpoUnroll
     for (int k = 0; k < nIn; ++k) {
         const float xv = bufX[k * kPpoStride + lane];
         const float4 *wr = reinterpret_cast<const float4 *>(n.W1t + k * H);
@@ -172,7 +177,7 @@ __device__ __forceinline__ void forward_hidden(const PpoNet &n, const float *buf
     __syncwarp();  // the previous head's fragment loads of bufH1 / bufH are done
 #pragma unroll
     for (int o = 0; o < H; ++o) { bufH1[o * kPpoStride + lane] = fast_tanh(h1[o]); h2[o] = n.b2[o]; }
-#pragma unroll 2
+#pragma unroll kPpoUnroll
     for (int k = 0; k < H; ++k) {
         const float xv = bufH1[k * kPpoStride + lane];  // own column: no synchronisation needed
         const float4 *wr = reinterpret_cast<const float4 *>(n.W2t + k * H);
@@ -195,7 +200,7 @@ __device__ __forceinline__ void backward_hidden(const PpoNet &n, const float (&d
 {
     constexpr int H = kPpoH;
     __syncwarp();  // the dW3 fragment loads of bufD (dz) are done
-#pragma unroll 2
+#pragma unroll kPpoUnroll
     for (int k = 0; k < H; ++k) {
         float s = 0.f;
         if (AZ == 1) {
@@ -221,7 +226,7 @@ __device__ __forceinline__ void backward_hidden(const PpoNet &n, const float (&d
 #pragma unroll
     for (int k = 0; k < H; ++k) da2[k] = bufD[k * kPpoStride + lane];
     __syncwarp();  // the dW2 fragment loads of bufD are done
-#pragma unroll 2
+#pragma unroll kPpoUnroll
     for (int i = 0; i < H; ++i) {
         const float4 *wr = reinterpret_cast<const float4 *>(n.W2t + i * H);
         float s = 0.f;
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(128, MSCHED_PPO_MINB) ppo_grad_kernel(const Pp
         }
         const long long r = tb * a.U + u;
         const int16_t *xr = a.x + tb * a.xTbStride + (long long)u * a.xUnitStride;
-#ifndef MSCHED_PPO_NO_PREFETCH
+#ifdef MSCHED_PPO_PREFETCH  // measured: no gain once four CTAs per SM hide the latency (1.47 ms with, 1.43 ms without)
         {   // the next tile's rows start their way from HBM now (strided 2-byte loads are latency-bound)
             const long long q2 = q + (long long)gridDim.x * 128;
             if (q2 < total) {
