@@ -18,7 +18,7 @@ int ppo_grid_x(const MschedPpoBatch *b)
 {
     const long long total = (long long)b->n_tb * b->units_per_net;
     long long tiles = (total + 127) / 128;
-    long long gx = 592 / b->n_sel;
+    long long gx = (148 * MSCHED_PPO_MINB) / b->n_sel;  // one resident wave: MSCHED_PPO_MINB CTAs per SM
     if (gx < 1) gx = 1;
     if (gx > tiles) gx = tiles;
     if (gx < 1) gx = 1;
