@@ -216,27 +216,109 @@ def cpu_baseline_sample(cfg, seconds=12.0, threads=1, envs=2048):
                 steps=steps_done)
 
 
+def python_reference_sample(cfg, envs=64, steps=20, warm_steps=200, seconds=None, seed=0):
+    """Times the UNMODIFIED Python reference (oracle/_ref, or /root/reference in the build container):
+    `envs` independent reference worlds, each advanced by SchedulingEnv.step
+    (src/SchedulingEnvironment.py:32-83) + Auctioneer.getAuctioneerAction (src/Auctioneer.py:95-102) per
+    step, one process, one thread -- the reference has no batched or multi-core mode.  Actions are the
+    bench workload's (uniform random indices, drawn untimed).  `warm_steps` untimed steps bring every
+    world to steady state; then `steps` timed steps (or, with `seconds`, whole steps until that much
+    time has passed).  Returns None when the reference files are absent."""
+    from oracle import ref_harness as RH
+    if not RH.reference_available():
+        return None
+    import numpy as np
+    import torch
+    torch.set_num_threads(1)
+    dom, mode = cfg["dom"], cfg["mode"]
+    free = mode.startswith("free")
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    NL, P = N * L, max(dom["prios"])
+    rng = np.random.default_rng(seed)
+    worlds = [RH.make_env(dom, mode) for _ in range(envs)]
+    obs = [env.reset() for _, env in worlds]
+
+    def draw():
+        acc = rng.integers(0, NL + 1, (envs, N, C)).tolist()
+        offc = rng.integers(0, C + 1, (envs, N, L)).tolist()
+        if free:
+            offp = rng.integers(0, P + 1, (envs, N, L)).tolist()
+            off = [[[(offc[e][i][q], offp[e][i][q]) for q in range(L)] for i in range(N)] for e in range(envs)]
+        else:
+            off = offc
+        return acc, off
+
+    def one_step(acts):
+        acc, off = acts
+        for e, (world, env) in enumerate(worlds):
+            auc = world.auctioneer.getAuctioneerAction(obs[e][2])
+            out = env.step(off[e], acc[e], auc)
+            obs[e] = out[:3]
+
+    for _ in range(warm_steps):
+        one_step(draw())
+    done, el = 0, 0.0
+    while True:
+        acts = draw()
+        t0 = time.perf_counter()
+        one_step(acts)
+        el += time.perf_counter() - t0
+        done += 1
+        if (seconds is None and done >= steps) or (seconds is not None and el >= seconds):
+            break
+    return dict(value=envs * N * done / el, env_steps=envs * done, seconds=el, envs=envs, steps=done,
+                warm_steps=warm_steps, source=RH.REFERENCE_SRC)
+
+
+def workload_config(args, cfg, B):
+    """The workload description both arms print (same keys and values, so the two lines name the same work)."""
+    return {"workload": args.config, "domain": cfg["desc"], "envs_per_gpu": B,
+            "observations": "none" if cfg.get("obs") == "none" else args.obs,
+            "auctioneer": "hard-coded auction rule, random arg-max tie-break",
+            "spawn": "typed spawn distribution, one draw per agent and round",
+            "actions": "uniform random indices, fresh draws every step (untimed)"}
+
+
 def run_reference(args, cfg):
-    """--impl reference: the CPU port of the reference's path on all host cores (the Python
-    reference itself cannot travel to the GPU box)."""
+    """--impl reference: the reference's own CPU implementation of the path -- the unmodified Python
+    SchedulingEnv.step + getAuctioneerAction from oracle/_ref (one process, one thread: all the host
+    threads it can use) -- on a bounded sample of the workload per step.  The C port of the same path on
+    every host core at the full 65,536 envs per step is reported beside it as `cpu_baseline_port`."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    B = args.envs or cfg["envs"]
+    K, W = max(1, args.steps), max(0, args.warmup)
+    N = cfg["dom"]["N"]
     threads = os.cpu_count() or 1
-    K = max(1, args.steps)
-    res = cpu_baseline_sample(cfg, seconds=min(60.0, max(5.0, 0.01 * K)), threads=threads, envs=1024)
-    dom = cfg["dom"]
+    # per step: a sample of `envs` reference worlds (the reference advances ~1.8 k env-steps/s per core)
+    envs = 128 if N * cfg["dom"]["L"] <= 16 else 2
+    warm = max(W, 200 if envs > 2 else 5)
+    ref = python_reference_sample(cfg, envs=envs, steps=K, warm_steps=warm)
+    port = cpu_baseline_sample(cfg, seconds=5.0, threads=threads, envs=max(64, B // threads)) \
+        if cfg["dom"]["N"] * cfg["dom"]["L"] <= 64 else None
+    if ref is not None:
+        res, kind, cores = ref, "reference", 1
+        sample = (f"{ref['envs']} independent reference worlds x {ref['steps']} timed steps after {ref['warm_steps']} "
+                  f"untimed, SchedulingEnv.step + Auctioneer.getAuctioneerAction of the unmodified Python reference "
+                  f"({os.path.relpath(ref['source'], ROOT) if ref['source'].startswith(ROOT) else ref['source']}), 1 process, 1 thread of {threads} host cores (the reference is single-threaded)")
+    else:  # the reference files did not travel: the C port stands in
+        res, kind, cores = port, "port", threads
+        sample = f"{port['envs']} envs x {port['steps']} steps, {threads} threads, oracle/msched_oracle.c"
     line = {
         "impl": "reference", "metric": "agent-steps/sec, batched env step+auction @65,536 envs",
         "value": res["value"], "unit": "agent-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * res["seconds"] / res["steps"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
         "data": "synthetic",
-        "config": {"workload": args.config, "domain": cfg["desc"], "envs_per_step": res["envs"],
-                   "note": "CPU port (oracle/msched_oracle.c) of the reference path; each step is a "
-                           "bounded sample of the 65,536-env workload"},
-        "cpu_baseline": {"value": res["value"], "unit": "agent-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"{res['envs']} envs x {res['steps']} steps, {threads} threads"},
+        "config": workload_config(args, cfg, B),
+        "sample_envs_per_step": res["envs"],
+        "cpu_baseline": {"value": res["value"], "unit": "agent-steps/s", "cores": cores, "kind": kind,
+                         "sample": sample},
+        "cpu_baseline_port": None if port is None else {
+            "value": port["value"], "unit": "agent-steps/s", "cores": threads, "kind": "port",
+            "sample": f"{port['envs']} envs per step x {port['steps']} steps, {threads} threads, "
+                      "oracle/msched_oracle.c (C restatement of the same path)"},
         "e2e": {"value": res["value"], "unit": "agent-steps/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -696,24 +778,31 @@ def main():
     # the fused launch also writes the dense observation record: SURVEY 8(d) bytes = 2S + a + r + o
     alg_bytes = ab["step"] + (ab["obs"] if fused else 0)
     achieved = alg_bytes * B / step_launch_s / 1e9
-    cpu = None
+    cpu = cpu_port = None
     if not args.no_cpu_baseline and world == 1:
-        c = cpu_baseline_sample(cfg, seconds=args.cpu_seconds, threads=1, envs=2048)
-        cpu = {"value": c["value"], "unit": "agent-steps/s", "cores": 1, "kind": "port",
-               "sample": f"{c['envs']} envs x {c['steps']} steps of the same workload, 1 thread of "
-                         f"{os.cpu_count()} host cores, oracle/msched_oracle.c"}
+        small = N * dom["L"] <= 64
+        if small:
+            c = cpu_baseline_sample(cfg, seconds=args.cpu_seconds / 2, threads=1, envs=2048)
+            cpu_port = {"value": c["value"], "unit": "agent-steps/s", "cores": 1, "kind": "port",
+                        "sample": f"{c['envs']} envs x {c['steps']} steps of the same workload, 1 thread of "
+                                  f"{os.cpu_count()} host cores, oracle/msched_oracle.c"}
+        r = python_reference_sample(cfg, envs=64 if small else 1, warm_steps=200 if small else 3, seconds=args.cpu_seconds)
+        if r is not None:
+            cpu = {"value": r["value"], "unit": "agent-steps/s", "cores": 1, "kind": "reference",
+                   "sample": f"{r['envs']} independent worlds x {r['steps']} steps ({r['seconds']:.1f} s) after {r['warm_steps']} untimed, "
+                             f"unmodified Python reference SchedulingEnv.step + getAuctioneerAction, 1 thread of {os.cpu_count()} host cores"}
+        else:
+            cpu = cpu_port
     line = {
         "metric": "agent-steps/sec, batched env step+auction @65,536 envs",
         "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.config, "domain": cfg["desc"], "envs_per_gpu": B,
-                   "observations": args.obs, "auctioneer": "in-kernel, random arg-max (Philox)",
-                   "spawn": "device Philox", "actions": "uniform random, fresh draws every step (untimed)",
-                   "l2": l2_note,
-                   "state_warm_steps": args.state_warm, "step_impl": info["step_impl"],
-                   "observations_fused_into_step_launch": bool(fused),
-                   "envs_per_cta": info["envs_per_cta"], "smem_bytes_per_cta": info["smem_bytes_per_cta"]},
+        "config": dict(workload_config(args, cfg, B), l2=l2_note),
+        "kernel_config": {"auctioneer": "in-kernel, random arg-max (Philox)", "spawn": "device Philox",
+                          "state_warm_steps": args.state_warm, "step_impl": info["step_impl"],
+                          "observations_fused_into_step_launch": bool(fused),
+                          "envs_per_cta": info["envs_per_cta"], "smem_bytes_per_cta": info["smem_bytes_per_cta"]},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": n_launch,
@@ -725,6 +814,7 @@ def main():
         "kernels": {"step_us": 1e3 * stepk_ms / K, "observe_us": obs_us,
                     "observe_algorithmic_bytes_per_env": ab["obs"] + ab["state"]},
         "cpu_baseline": cpu,
+        "cpu_baseline_port": cpu_port,
         "rollout_with_policy": rollout,
         "ppo_update": update,
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,

@@ -224,6 +224,20 @@ int msched_observe_dense(void *handle, int16_t *obs_dev, int16_t *ids_dev, void 
  * callers that want to see / override the auctioneer's action like the reference scripts do. */
 int msched_auctioneer_action(void *handle, int random_ties, int16_t *out_dev, void *stream);
 
+/* DividedHardcodedAgent.getActions of every agent (src/Agent.py:622-641) = SchedulingEnv.getActionForAllAgents
+ * of HardcodedFixPriceEnvironment (src/SchedulingEnvironment.py:150-172, 439-456; BASELINE config 1): per
+ * (agent, core) HardcodedAcceptor.selectAction (src/HardcodedModules.py:16-45: accept the best
+ * offeredReward/necessaryTime if it beats the own job's priority/remainingLength, else reject) and per
+ * (agent, slot) HardcodedOfferer.selectAction (src/HardcodedModules.py:81-109: offer to a core with the lowest
+ * priority/remainingLength, never abstain), read from the dense observation record obs_dev (as written by
+ * msched_observe_dense / msched_step_observe) and written into the acceptor idx and offer core fields of the
+ * action record action_dev.  Ties: candidate floor(u * #candidates) in index order, u from Philox (counter =
+ * global env, round, stream 3, unit) when random_ties != 0, the first candidate otherwise, or from
+ * u_override_dev float32 [B][N*C + N*L] (parity tests).  ncand_dev (optional) int32 [B][N*C + N*L]: number of tie
+ * candidates of each unit (0 where no choice was made). */
+int msched_hardcoded_actions(void *handle, const int16_t *obs_dev, int random_ties, const float *u_override_dev,
+                             int16_t *action_dev, int32_t *ncand_dev, void *stream);
+
 /* debug / parity: reference-shaped int32 dump of envs [env0, env0+count):
  * core [C][7] owner,prio,rem,jobid,kind,birth,init ; slot [N*L][7] prio,rem,jobid,kind,wait,
  * birth,init ; offer [N*L][5] core(0 none),recipient,price,time,offerID ;

@@ -107,6 +107,7 @@ SYMBOLS = {
     "msched_step_host": (C.c_int, [P, P, P, P, P]),
     "msched_observe_dense": (C.c_int, [P, P, P, P]),
     "msched_auctioneer_action": (C.c_int, [P, C.c_int, P, P]),
+    "msched_hardcoded_actions": (C.c_int, [P, P, C.c_int, P, P, P, P]),
     "msched_export_state": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, P]),
     "msched_mlp_param_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "msched_actor_forward": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),

@@ -93,16 +93,19 @@ class BatchedPPO:
 
     # -- rollout ---------------------------------------------------------------------------------
     def selectAction(self, x, x_stride, env_stride, n_envs, seed, action_rec=None, action_rec_stride=0,
-                     gather_core=None, n_cores=0):
+                     gather_core=None, n_cores=0, env_offset=0):
         """PPO.selectAction for every (env, unit): x is an int16 view whose rows are the units'
         observations.  Returns actions int32 [n_envs, units]; stores state/action/logprob.
         action_rec: int16 view into the environment's action record that the kernel fills
-        directly; gather_core: core chooser actions (price chooser launch, see policy.actor_forward)."""
+        directly; gather_core: core chooser actions (price chooser launch, see policy.actor_forward);
+        env_offset: global index of this shard's env 0 (the sampling draws are keyed on the GLOBAL row, so a
+        sharded rollout draws what the unsharded one would)."""
         x_used = None
         if gather_core is not None:
             x_used = torch.empty((n_envs, self.units, self.n_in), dtype=torch.int16, device=x.device)
         act, lp, _ = P.actor_forward(self.policy_old, x, x_stride, self.units, n_envs,
                                      env_stride=env_stride, seed=seed, step=self.step_no,
+                                     row_offset=env_offset * self.units,
                                      action_rec=action_rec, action_rec_stride=action_rec_stride,
                                      gather_core=gather_core, n_cores=n_cores, x_used=x_used)
         self.step_no += 1
@@ -239,16 +242,20 @@ class DividedFixedPricePPOAgents:
         self.offer = BatchedPPO(2 * C + 2, C + 1, 16, no, N * L, do, env.LR_ACTOR, env.LR_CRITIC,
                                 env.OFFER_GAMMA, env.EPS_CLIP, env.OFFER_K_EPOCHS, dev, seed=2)
         self.CENTRALISATION_SAMPLE = env.CENTRALISATION_SAMPLE
+        # which units a shared net learns from (src/SchedulingEnvironment.py:314-329, src/Agent.py:708-728): a
+        # private generator seeded like the world, so every data-parallel rank samples the same units
+        self._rng = random.Random(world.seed)
 
     def getActions(self, offerObs, acceptorObs):
         c, lay = self.env.core, self.env.core.layout
         B, N, C, L = c.B, c.N, c.C, c.Lc
         seed = self.world.seed
         # the kernels write the chosen actions straight into the env's action record
+        eo = self.world.envOffset
         self.offer.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 2 + 1,
-                                action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs)
+                                action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs, env_offset=eo)
         self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 2,
-                                   action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs)
+                                   action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs, env_offset=eo)
         # SchedulingEnv.getActionForAllAgents returns (acceptorActions, offerActions)
         return c.acceptor_actions, c.offer_core_actions
 
@@ -262,12 +269,11 @@ class DividedFixedPricePPOAgents:
                 ppo.update()
             elif self.sharing == "global":   # src/SchedulingEnvironment.py:314-329
                 for _ in range(self.CENTRALISATION_SAMPLE):
-                    ppo.update([random.randint(0, ppo.units - 1)])
-            else:                            # src/Agent.py:708-728
+                    ppo.update([self._rng.randint(0, ppo.units - 1)])
+            else:                            # src/Agent.py:708-728: every agent draws its own sub-unit
                 N = self.world.numberOfAgents
                 for _ in range(self.CENTRALISATION_SAMPLE):
-                    j = random.randint(0, sub - 1)
-                    ppo.update([a * sub + j for a in range(N)])
+                    ppo.update([a * sub + self._rng.randint(0, sub - 1) for a in range(N)])
             ppo.sync_old_and_clear()
 
 
@@ -302,7 +308,7 @@ class DividedFreePricePPOAgents:
             (ca, clp), (pa, plp) = P.offer_unit_forward(
                 self.core.policy_old, self.price.policy_old, offerObs, lay.o_off_row, NL, B, C,
                 env_stride=lay.obs_halfs, seeds=(seed * 3 + 1, seed * 3 + 2), step=self.core.step_no,
-                core_rec=c.offer_core_actions, price_rec=c.offer_price_actions,
+                row_offset=self.world.envOffset * NL, core_rec=c.offer_core_actions, price_rec=c.offer_price_actions,
                 action_rec_stride=lay.action_halfs, x_used=x_used)
             for ppo, xs, a_, lp_ in ((self.core, offerObs.reshape(B, NL, 2 * C + 2).clone(), ca, clp),
                                      (self.price, x_used, pa, plp)):
@@ -311,17 +317,19 @@ class DividedFreePricePPOAgents:
                 ppo.buf_a.append(a_.view(B, NL))
                 ppo.buf_lp.append(lp_.view(B, NL))
             self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 3,
-                                       action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs)
+                                       action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs,
+                                       env_offset=self.world.envOffset)
             return c.acceptor_actions, (c.offer_core_actions, c.offer_price_actions)
+        eo = self.world.envOffset
         core = self.core.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 3 + 1,
-                                      action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs)
+                                      action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs, env_offset=eo)
         # price chooser: the kernel slices [core prio, core rem, slot prio, slot rem] of the chosen
         # core out of the offer observation row ([-5]*4 and reported price -5 for core action 0)
         self.price.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 3 + 2,
                                 action_rec=c.offer_price_actions, action_rec_stride=lay.action_halfs,
-                                gather_core=core.reshape(-1), n_cores=C)
+                                gather_core=core.reshape(-1), n_cores=C, env_offset=eo)
         self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 3,
-                                   action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs)
+                                   action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs, env_offset=eo)
         return c.acceptor_actions, (c.offer_core_actions, c.offer_price_actions)
 
     def saveRewards(self, offerRewards, acceptorRewards, agentReward):
@@ -367,8 +375,9 @@ class AggregatedFixPricePPOAgents:
         c = self.env.core
         B, N, C, L = c.B, c.N, c.C, c.Lc
         seed = self.world.seed
-        acc = self.acceptor.selectAction(acceptorObs.contiguous(), acceptorObs.shape[-1], 0, B, seed * 2)
-        off = self.offer.selectAction(offerObs.contiguous(), offerObs.shape[-1], 0, B, seed * 2 + 1)
+        eo = self.world.envOffset
+        acc = self.acceptor.selectAction(acceptorObs.contiguous(), acceptorObs.shape[-1], 0, B, seed * 2, env_offset=eo)
+        off = self.offer.selectAction(offerObs.contiguous(), offerObs.shape[-1], 0, B, seed * 2 + 1, env_offset=eo)
         nd_acc = _digits(acc.long(), c.NL + 1, C)      # [B,N,C]
         nd_off = _digits(off.long(), C + 1, L)         # [B,N,L]
         return nd_acc, nd_off
@@ -403,7 +412,7 @@ class FullyAggregatedFixPricePPOAgents:
     def getActions(self, offerObs, acceptorObs):
         c = self.env.core
         x = torch.cat([offerObs, acceptorObs], dim=-1).contiguous()   # src/Agent.py:463-467
-        n = self.unit.selectAction(x, x.shape[-1], 0, c.B, self.world.seed).long()
+        n = self.unit.selectAction(x, x.shape[-1], 0, c.B, self.world.seed, env_offset=self.world.envOffset).long()
         nd_acc = _digits(n // self.divisor, c.NL + 1, c.C)
         nd_off = _digits(n % self.divisor, c.C + 1, c.Lc)
         return nd_acc, nd_off

@@ -50,6 +50,12 @@ class BatchedSchedulingEnv:
         self.chain = torch.zeros((Bp, lay.chain_words), dtype=torch.int32, device=dev)
         self.action = torch.zeros((Bp, lay.action_halfs), dtype=torch.int16, device=dev)
         self.result = torch.zeros((Bp, lay.result_words), dtype=torch.int32, device=dev)
+        # step() alternates between two result records and two observation records: what one step returned
+        # (views into them) stays valid until the SECOND-next step, so the reference's `old = new` idiom
+        # around env.step (src/trainDQN.py:171-186) sees two different tensors
+        self._result_ring = [self.result, None]
+        self._obs_ring = [None, None]
+        self._flip = 0
         self._obs = None
         self._ids = None
         L.check(self.lib.msched_bind_state(self.handle, self.state.data_ptr(), self.chain.data_ptr()))
@@ -171,7 +177,16 @@ class BatchedSchedulingEnv:
         """SchedulingEnv.step(offerActions, acceptorActions, auctioneer_action) over B envs.
         observe=True also refreshes the observation record (see obs_views)."""
         self.set_actions(offer_core, acceptor, auctioneer, offer_price, spawn_kind)
+        self._flip ^= 1
+        k = self._flip
+        if self._result_ring[k] is None:
+            self._result_ring[k] = torch.zeros_like(self.result)
+        self.result = self._result_ring[k]
         if observe:
+            if self._obs_ring[k] is None:
+                self._obs_ring[k] = torch.zeros((self.layout.padded_envs, self.layout.obs_halfs), dtype=torch.int16,
+                                                device=self.device)
+            self._obs = self._obs_ring[k]
             self.step_observe_records(spawn_u=spawn_u)
         else:
             self.step_records(spawn_u=spawn_u)
@@ -214,6 +229,7 @@ class BatchedSchedulingEnv:
         if self._obs is None:
             self._obs = torch.zeros((self.layout.padded_envs, self.layout.obs_halfs), dtype=torch.int16,
                                     device=self.device)
+            self._obs_ring[self._flip] = self._obs
         return self._obs
 
     def obs_views(self, obs=None):

@@ -104,9 +104,16 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     uint32_t *sState = sm, *sAct = sState + 32 * W, *sRes = sAct + 32 * AW, *sScr = sRes + 32 * RW;
     uint32_t *sObs = sm;  // overlays the work tiles in P6
 
+    // per-CTA phase stamps (tools/timeline.py): compiled in only with -DMSCHED_TIMELINE, the shipped kernel
+    // carries no diagnostic branches
+#ifdef MSCHED_TIMELINE
     unsigned long long *tl = p.timeline ? p.timeline + (size_t)blockIdx.x * 8 : nullptr;
+#define MSCHED_TL(stmt) do { if (tl && threadIdx.x == 0) { stmt; } } while (0)
+#else
+#define MSCHED_TL(stmt) do { } while (0)
+#endif
     if (threadIdx.x == 0) {
-        if (tl) { tl[0] = smid(); tl[1] = globaltimer(); tl[2] = clock64(); }
+        MSCHED_TL((tl[0] = smid(), tl[1] = globaltimer(), tl[2] = clock64()));
         mbar_init(&bar, 1);
         mbar_expect_tx(&bar, 32u * (uint32_t)(W + AW) * 4u);
         bulk_g2s(sState, p.state + (size_t)env0 * W, 32u * W * 4u, &bar);
@@ -154,9 +161,9 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
         scr[D::X_NSPAWN] = 0u;
     }
     __syncthreads();  // barrier initialisation and the P0 products visible to every warp
-    if (tl && threadIdx.x == 0) tl[3] = clock64();
+    MSCHED_TL(tl[3] = clock64());
     mbar_wait(&bar, 0);
-    if (tl && threadIdx.x == 0) tl[4] = clock64();
+    MSCHED_TL(tl[4] = clock64());
 
     // ---- P1: per core, who acts on it and which pending offer is selected.  Offers addressed to
     // (owner, core) are ranked in creation order (agent asc, slot asc); agents (and an external
@@ -515,7 +522,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     fence_async_smem();
     __syncthreads();
     if (threadIdx.x == 0) {
-        if (tl) tl[5] = clock64();
+        MSCHED_TL(tl[5] = clock64());
         bulk_s2g(p.state + (size_t)env0 * W, sState, 32u * W * 4u);
         bulk_s2g(p.result + (size_t)env0 * RW, sRes, 32u * (uint32_t)RW * 4u);
         bulk_commit();
@@ -523,7 +530,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     }
     if (!withObs) {
         if (threadIdx.x == 0) {
-            if (tl) { tl[6] = clock64(); tl[7] = globaltimer(); }
+            MSCHED_TL((tl[6] = clock64(), tl[7] = globaltimer()));
             finish_round(p);
         }
         return;
@@ -587,9 +594,10 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
         bulk_s2g(reinterpret_cast<uint32_t *>(p.obs) + (size_t)env0 * OW, sObs, 32u * (uint32_t)OW * 4u);
         bulk_commit();
         bulk_wait_read();
-        if (tl) { tl[6] = clock64(); tl[7] = globaltimer(); }
+        MSCHED_TL((tl[6] = clock64(), tl[7] = globaltimer()));
         finish_round(p);
     }
+#undef MSCHED_TL
 }
 
 }  // namespace msched

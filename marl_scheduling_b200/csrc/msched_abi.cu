@@ -15,6 +15,7 @@
 #include "step_kernel.cuh"
 #include "coop_step_kernel.cuh"
 #include "fused_step_kernel.cuh"
+#include "hardcoded_kernel.cuh"
 
 using namespace msched;
 
@@ -125,6 +126,26 @@ struct Handle {
     bool deviceRound;
     cudaStream_t hostStream[2];  // msched_step_host pipelines its chunks over these
     cudaEvent_t evStart, evDone[2];
+};
+
+void free_handle(Handle *h)
+{
+    if (!h) return;
+    cudaFree(h->stageAction);
+    cudaFree(h->stageResult);
+    cudaFree(h->roundDev);
+    for (int k = 0; k < 2; ++k) {
+        if (h->hostStream[k]) cudaStreamDestroy(h->hostStream[k]);
+        if (h->evDone[k]) cudaEventDestroy(h->evDone[k]);
+    }
+    if (h->evStart) cudaEventDestroy(h->evStart);
+    delete h;
+}
+// msched_create returns early on any CUDA error: the guard releases what was acquired so far
+struct HandleGuard {
+    Handle *h;
+    ~HandleGuard() { free_handle(h); }
+    Handle *release() { Handle *r = h; h = nullptr; return r; }
 };
 
 StepKernel pick_step_kernel(int N, int C, int L)
@@ -261,7 +282,8 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
         CUDA_TRY(cudaMemcpyToSymbol(c_rcp, rcp, sizeof(rcp)));
         CUDA_TRY(cudaMemcpyToSymbol(c_oddpart, odd, sizeof(odd)));
     }
-    Handle *h = new Handle();
+    HandleGuard guard{new Handle()};
+    Handle *h = guard.h;
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
     h->lay = lay;
@@ -299,7 +321,6 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
         }
     }
     if (!h->stepTile && !h->coopFn) {
-        delete h;
         return fail(MSCHED_E_ARG, "domain too large: the records of 4 environments must fit in shared memory");
     }
     // small batches are latency-bound: the cooperative kernel's shorter per-env critical path wins
@@ -337,7 +358,6 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     if (const char *e = getenv("MSCHED_STEP_IMPL")) {
         const bool wantFused = !strcmp(e, "fused"), wantCoop = !strcmp(e, "coop"), wantLane = !strcmp(e, "lane");
         if ((wantFused && !h->fusedFn) || (wantCoop && !h->coopFn) || (wantLane && !h->stepTile)) {
-            delete h;
             return fail(MSCHED_E_ARG, "MSCHED_STEP_IMPL: that kernel is not available for this domain");
         }
         if (wantFused || wantCoop || wantLane) {
@@ -361,7 +381,7 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
         CUDA_TRY(cudaEventCreateWithFlags(&h->evDone[k], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaEventCreateWithFlags(&h->evStart, cudaEventDisableTiming));
-    *handle = h;
+    *handle = guard.release();
     return MSCHED_OK;
 }
 
@@ -370,15 +390,7 @@ int msched_destroy(void *handle)
     Handle *h = static_cast<Handle *>(handle);
     if (!h) return MSCHED_OK;
     cudaSetDevice(h->device);
-    cudaFree(h->stageAction);
-    cudaFree(h->stageResult);
-    cudaFree(h->roundDev);
-    for (int k = 0; k < 2; ++k) {
-        if (h->hostStream[k]) cudaStreamDestroy(h->hostStream[k]);
-        if (h->evDone[k]) cudaEventDestroy(h->evDone[k]);
-    }
-    if (h->evStart) cudaEventDestroy(h->evStart);
-    delete h;
+    free_handle(h);
     return MSCHED_OK;
 }
 
@@ -411,8 +423,13 @@ int msched_debug_timeline(void *handle, uint64_t *timeline_dev)
 {
     Handle *h = static_cast<Handle *>(handle);
     if (!h) return fail(MSCHED_E_ARG, "null handle");
+#ifdef MSCHED_TIMELINE
     h->p.timeline = reinterpret_cast<unsigned long long *>(timeline_dev);
     return MSCHED_OK;
+#else
+    if (timeline_dev) return fail(MSCHED_E_ARG, "the phase stamps are compiled out: rebuild with make NVEXTRA=-DMSCHED_TIMELINE");
+    return MSCHED_OK;
+#endif
 }
 
 int msched_bind_state(void *handle, void *state_dev, void *chain_dev)
@@ -610,6 +627,7 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
                 p.Bpad = n;  // n is a multiple of the padding unit here
                 p.state = h->p.state + (size_t)e0 * p.W;
                 p.chain = h->p.chain + (size_t)e0 * h->lay.chain_words;
+                p.stats = h->p.stats ? h->p.stats + (size_t)e0 * h->cfg.J * 4 : nullptr;
                 if (mode == 2) {
                     CUDA_TRY(cudaMemcpyAsync(h->stageAction + (size_t)e0 * AH, action_host + (size_t)e0 * AH, (size_t)n * AH * 2,
                                              cudaMemcpyHostToDevice, cs));
@@ -666,6 +684,7 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
         p.Bpad = msched_padded_envs(n);
         p.state = h->p.state + (size_t)e0 * p.W;
         p.chain = h->p.chain + (size_t)e0 * h->lay.chain_words;
+        p.stats = h->p.stats ? h->p.stats + (size_t)e0 * h->cfg.J * 4 : nullptr;
         p.action = h->stageAction + (size_t)e0 * AH;
         p.result = h->stageResult + (size_t)e0 * RW;
         p.spawnU = nullptr;
@@ -722,6 +741,24 @@ int msched_auctioneer_action(void *handle, int random_ties, int16_t *out_dev, vo
     p.round = (int)h->round;
     p.roundDev = h->deviceRound ? h->roundDev : nullptr;
     auctioneer_kernel<<<(p.B + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(p, random_ties, out_dev);
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+int msched_hardcoded_actions(void *handle, const int16_t *obs_dev, int random_ties, const float *u_override_dev,
+                             int16_t *action_dev, int32_t *ncand_dev, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !obs_dev || !action_dev) return fail(MSCHED_E_ARG, "null handle/obs/action");
+    DevParams p = h->p;
+    p.round = (int)h->round;
+    p.roundDev = h->deviceRound ? h->roundDev : nullptr;
+    HardcodedArgs a;
+    a.obs = obs_dev; a.action = action_dev; a.uOverride = u_override_dev; a.ncand = ncand_dev;
+    a.oAcc = h->lay.o_acceptor; a.oOff = h->lay.o_offer; a.accRow = h->lay.o_acc_row; a.offRow = h->lay.o_off_row;
+    a.randomTies = random_ties;
+    const long long M = (long long)p.B * (p.N * p.C + p.NL);
+    hardcoded_policy_kernel<<<(unsigned)((M + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(p, a);
     CUDA_TRY(cudaGetLastError());
     return MSCHED_OK;
 }

@@ -37,11 +37,20 @@ class ReplayMemory:
     def push(self, state, action, next_state, reward):
         """state / next_state int16 [B, units, n_in]; action [B, units]; reward [B, units]."""
         B = state.shape[0]
-        idx = (torch.arange(B, device=state.device) + self.next) % self.capacity
-        self.state[idx] = state
-        self.next_state[idx] = next_state
-        self.action[idx] = action.long()
-        self.reward[idx] = reward.float()
+        if B > self.capacity:
+            # more transitions than the ring holds: only the last `capacity` survive a sequential push, and
+            # keeping exactly those leaves no duplicate indices (index_put with duplicates is unordered)
+            self.next = (self.next + B - self.capacity) % self.capacity
+            state, next_state = state[-self.capacity:], next_state[-self.capacity:]
+            action, reward = action[-self.capacity:], reward[-self.capacity:]
+            B = self.capacity
+        # at most two wrap-free contiguous slice copies
+        first = min(B, self.capacity - self.next)
+        for dst, src in ((self.state, state), (self.next_state, next_state), (self.action, action.long()),
+                         (self.reward, reward.float())):
+            dst[self.next: self.next + first] = src[:first]
+            if first < B:
+                dst[: B - first] = src[first:]
         self.next = (self.next + B) % self.capacity
         self.size = min(self.capacity, self.size + B)
 
@@ -83,7 +92,7 @@ class BatchedDQN:
         return self.RUN_END + (self.RUN_START - self.RUN_END) * math.exp(-1.0 * round_ / self.RUN_DECAY)
 
     def selectAction(self, x, x_stride, env_stride, n_envs, round_, seed, action_rec=None, action_rec_stride=0,
-                     u=None, want_q=False, random_policy=False):
+                     u=None, want_q=False, random_policy=False, row_offset=0):
         """DQNEntity.selectAction for every (env, unit).  Returns int32 actions [n_envs, units]."""
         dev = x.device
         M = n_envs * self.units
@@ -94,6 +103,7 @@ class BatchedDQN:
         io = L.MschedActorIO()
         io.x, io.x_stride, io.units, io.n_envs = x.data_ptr(), x_stride, self.units, n_envs
         io.env_stride, io.seed, io.step = env_stride, seed, self.step_no
+        io.row_offset = row_offset  # global row index of (env 0, unit 0): draws do not depend on the env sharding
         if u is not None:
             u = torch.as_tensor(u, dtype=torch.float32).to(dev).contiguous()
             io.u_override = u.data_ptr()
@@ -159,10 +169,13 @@ class DividedFixPriceDQNAgents:
         c, lay = self.env.core, self.env.core.layout
         rnd, seed = self.world.round, self.world.seed
         rp = bool(self.world.randomPolicy)
+        off = self.world.envOffset
         self.offer.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, c.B, rnd, seed * 2 + 1,
-                                action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs, random_policy=rp)
+                                action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs, random_policy=rp,
+                                row_offset=off * self.offer.units)
         self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, c.B, rnd, seed * 2,
-                                   action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs, random_policy=rp)
+                                   action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs, random_policy=rp,
+                                   row_offset=off * self.acceptor.units)
         return c.acceptor_actions, c.offer_core_actions
 
     def updateTargetNets(self):

@@ -199,65 +199,3 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
         assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == param.numel()
     L.check(L.lib().msched_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                      param.numel(), float(lr), beta1, beta2, eps, int(step), _stream(param.device)))
-
-
-def smoke_check(env, obs):
-    """One actor forward on the env's acceptor observations and one returns launch, checked
-    against the CPU oracle (used by __graft_entry__.smoke)."""
-    import numpy as np
-    from oracle import oracle as O
-    N, Cc, NL = env.N, env.C, env.NL
-    Wd = 3 + 2 * NL
-    grp = MlpGroup.random(Wd, 16, NL + 1, N * Cc, env.device, seed=1)
-    x = obs["acceptor"]  # [B,N,C,Wd] view into the obs record
-    B = x.shape[0]
-    uu = torch.rand(B * N * Cc, generator=torch.Generator().manual_seed(2))
-    act, lp, pr = actor_forward(grp, x, env.layout.o_acc_row, N * Cc, B,
-                                env_stride=env.layout.obs_halfs, u=uu, want_probs=True)
-    xs = x.cpu().numpy().reshape(B, N * Cc, Wd).astype(np.float32)
-    w = grp.weights.cpu().numpy()
-    H, A = 16, NL + 1
-    pr = pr.cpu().numpy().reshape(B, N * Cc, A)
-    for n in range(N * Cc):
-        o = 0
-        ws = []
-        for sz in (H * Wd, H, H * H, H, A * H, A):
-            ws.append(w[n, o:o + sz]); o += sz
-        p, _, _ = O.mlp_forward(xs[:, n], ws[0].reshape(H, Wd), ws[1], ws[2].reshape(H, H), ws[3],
-                                ws[4].reshape(A, H), ws[5])
-        np.testing.assert_allclose(pr[:, n], p, rtol=2e-5, atol=1e-6)
-    # tensor-core kernels: a 32-wide net (tcgen05, 3xTF32) and an aggregated head (200 actions, tiled)
-    for A2 in (40, 200):
-        g2 = MlpGroup.random(Wd, 32, A2, 2, env.device, seed=3)
-        x2 = x[:, 0, :2].contiguous()  # [B,2,Wd]: two units per env
-        _, lp2, pr2 = actor_forward(g2, x2, Wd, 2, B, u=uu[: 2 * B], want_probs=True)
-        w2 = g2.weights.cpu().numpy()
-        xs2 = x2.cpu().numpy().astype(np.float32)
-        pr2 = pr2.cpu().numpy().reshape(B, 2, A2)
-        for n in range(2):
-            o, ws = 0, []
-            for sz in (32 * Wd, 32, 32 * 32, 32, A2 * 32, A2):
-                ws.append(w2[n, o:o + sz]); o += sz
-            p2, _, _ = O.mlp_forward(xs2[:, n], ws[0].reshape(32, Wd), ws[1], ws[2].reshape(32, 32), ws[3],
-                                     ws[4].reshape(A2, 32), ws[5])
-            np.testing.assert_allclose(pr2[:, n], p2, rtol=5e-5, atol=1e-7)
-    # PPO.update gradient kernel (forward + backward, tensor-core sample reduction) against the oracle's
-    # float64 backward sweep, on the acceptor observations of unit 0
-    gen = torch.Generator().manual_seed(4)
-    crit = MlpGroup.random(Wd, 16, 1, N * Cc, env.device, seed=5)
-    xu = x.reshape(B, N * Cc, Wd).contiguous()
-    a_old = torch.randint(0, A, (B, N * Cc), generator=gen, dtype=torch.int32).to(env.device)
-    lp_old = (torch.randn(B, N * Cc, generator=gen) * 0.3 - float(np.log(A))).to(env.device)
-    Gr = torch.randn(B, N * Cc, generator=gen).to(env.device)
-    ids = torch.zeros((1, 1), dtype=torch.int32, device=env.device)
-    ga, gc = torch.zeros_like(grp.weights), torch.zeros_like(crit.weights)
-    ppo_grad(grp.weights, crit.weights, Wd, A, xu, a_old, lp_old, Gr, ids.view(-1), ids, ga, gc)
-    oa, oc, _ = O.ppo_loss_grads(grp.weights[0].cpu().numpy(), crit.weights[0].cpu().numpy(), xu[:, 0].cpu().numpy(),
-                                 a_old[:, 0].cpu().numpy().astype(np.int64), lp_old[:, 0].cpu().numpy().astype(np.float64),
-                                 Gr[:, 0].cpu().numpy(), 0.2)
-    np.testing.assert_allclose(ga[0].cpu().numpy(), oa, rtol=1e-4, atol=1e-5 * np.abs(oa).max())
-    np.testing.assert_allclose(gc[0].cpu().numpy(), oc, rtol=1e-4, atol=1e-5 * np.abs(oc).max())
-    r = torch.randint(-5, 12, (50, 64)).float().to(env.device)
-    g = returns(r, 0.8733, True).cpu().numpy()
-    go = O.returns(r.cpu().numpy().astype(np.float64), 0.8733, True)
-    np.testing.assert_allclose(g, go, rtol=1e-5, atol=1e-5)

@@ -55,13 +55,14 @@ def save_checkpoint(path, world):
         top["agentNets " + name] = {
             "actor": ppo.actor.detach().cpu(), "critic": ppo.critic.detach().cpu(),
             "policy_old": ppo.policy_old.weights.detach().cpu(),
-            name + " optim": ppo.optimizer.state_dict(), "step_no": ppo.step_no,
+            name + " optim": ppo.optimizer.state_dict(), "optim kind": type(ppo.optimizer).__name__,
+            "step_no": ppo.step_no,
             "shape": (ppo.n_in, ppo.H, ppo.A, ppo.n_nets)}
     torch.save(top, path)
 
 
 def load_checkpoint(path, world):
-    top = torch.load(path, map_location="cpu", weights_only=False)
+    top = torch.load(path, map_location="cpu", weights_only=True)  # tensors, lists and scalars only
     for name, ppo in _units(world.agents).items():
         d = top["agentNets " + name]
         if tuple(d["shape"]) != (ppo.n_in, ppo.H, ppo.A, ppo.n_nets):
@@ -70,5 +71,9 @@ def load_checkpoint(path, world):
             ppo.actor.copy_(d["actor"].to(ppo.actor.device))
             ppo.critic.copy_(d["critic"].to(ppo.critic.device))
             ppo.policy_old.weights.copy_(d["policy_old"].to(ppo.policy_old.weights.device))
+        kind = d.get("optim kind", "FlatAdam" if d[name + " optim"].get("kind") == "FlatAdam" else "Adam")
+        if kind != type(ppo.optimizer).__name__:
+            raise ValueError(f"checkpoint of {name} holds a {kind} optimizer state but the agents use "
+                             f"{type(ppo.optimizer).__name__} (MSCHED_PPO_UPDATE selects the kernel or the autograd path)")
         ppo.optimizer.load_state_dict(d[name + " optim"])
         ppo.step_no = int(d["step_no"])

@@ -115,9 +115,32 @@ def pack(tr, dom, mode, agent_kind="divided"):
     return out
 
 
+CHECK_ONLY = False
+MISMATCHES = []
+
+
 def save(name, tr):
-    os.makedirs(GOLDEN, exist_ok=True)
-    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **tr)
+    """Write the fixture; with --check-only compare it (NaN-aware, dtype-aware) with the committed file
+    instead and leave the file alone."""
+    path = os.path.join(GOLDEN, name + ".npz")
+    if not CHECK_ONLY:
+        os.makedirs(GOLDEN, exist_ok=True)
+        np.savez_compressed(path, **tr)
+        return
+    if not os.path.exists(path):
+        MISMATCHES.append(f"{name}: no committed fixture")
+        return
+    z = np.load(path)
+    if sorted(z.files) != sorted(tr):
+        MISMATCHES.append(f"{name}: array names differ")
+        return
+    for k in z.files:
+        a, b = z[k], np.asarray(tr[k])
+        same = a.shape == b.shape and a.dtype == b.dtype and np.array_equal(
+            a, b, equal_nan=a.dtype.kind == "f")
+        if not same:
+            MISMATCHES.append(f"{name}: {k} differs")
+    print(f"  check {name}: {'ok' if not any(m.startswith(name + ':') for m in MISMATCHES) else 'DIFFERS'}")
 
 
 def gen_kats():
@@ -242,12 +265,13 @@ def gen_torch_vectors():
         out[f"{tag}.gamma"] = np.float64(gamma)
         out[f"{tag}.raw"] = raw
         out[f"{tag}.norm"] = t.numpy()
-    os.makedirs(GOLDEN, exist_ok=True)
-    np.savez_compressed(os.path.join(GOLDEN, "torch_vectors.npz"), **out)
+    save("torch_vectors", out)
     print("torch vectors:", len(out), "arrays")
 
 
 def main():
+    global CHECK_ONLY
+    CHECK_ONLY = "--check-only" in sys.argv[1:]
     if not os.path.isdir(H.REFERENCE_SRC):
         raise SystemExit("reference not present; golden fixtures can only be regenerated in "
                          "the build container")
@@ -259,7 +283,9 @@ def main():
     print("KAT table check:", "OK" if ok else "MISMATCH")
     sz = sum(os.path.getsize(os.path.join(GOLDEN, f)) for f in os.listdir(GOLDEN))
     print("golden size: %.1f KiB" % (sz / 1024))
-    if not ok:
+    if CHECK_ONLY:
+        print("committed fixtures:", "all reproduce" if not MISMATCHES else MISMATCHES)
+    if not ok or MISMATCHES:
         raise SystemExit(1)
 
 

@@ -13,13 +13,22 @@ monkey-patched to script / record the spawn draws.
 """
 from __future__ import annotations
 
+import os
 import random
 import sys
 import types
 
 import numpy as np
 
+# the read-only mount in the build container, else the byte-for-byte copy oracle/make_ref.py left in
+# oracle/_ref (git-ignored; ships with the snapshot so that bench.py can time the reference on the GPU box)
 REFERENCE_SRC = "/root/reference/src"
+if not os.path.isdir(REFERENCE_SRC):
+    REFERENCE_SRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "src")
+
+
+def reference_available():
+    return os.path.isfile(os.path.join(REFERENCE_SRC, "SchedulingEnvironment.py"))
 
 _mods = None
 
