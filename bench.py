@@ -326,6 +326,110 @@ def run_reference(args, cfg):
     print(json.dumps(line))
 
 
+def ppo_update_dp_leg(torch, dist, dev, world, rank, T=8, B=65536, epochs=3, reps=3):
+    """BASELINE configs[3] ("cfg4"): PPO with globally shared parameters, env shards on every GPU, NCCL gradient
+    all-reduce (GloballySharedPPO.update, src/PPOmodules.py:395-449; sampling rule src/SchedulingEnvironment.py:
+    314-329).  The cfg2/cfg4 domain's shared acceptor net (27->16->16->13 + critic) learns from one sampled unit's
+    buffer of T steps x B envs PER RANK: every epoch = msched_ppo_grad on the rank's shard -> ONE flat all_reduce
+    (both heads) -> msched_adam_step, through agents.BatchedPPO.update (the product path).  Timed on the device with
+    CUDA events, max over ranks.  The in-bench check (the driver's pytest box has one GPU): on a small buffer every
+    rank computes the gradient of its shard, the all-reduced mean must equal the single-rank gradient of the WHOLE
+    buffer, and after the K Adam steps all ranks must hold bit-identical weights."""
+    from marl_scheduling_b200 import policy
+    from marl_scheduling_b200.agents import BatchedPPO
+    N, C, L = 4, 4, 3
+    NL, U = N * L, N * C
+    n_in, A = 3 + 2 * NL, NL + 1
+    kw = dict(lr_actor=3e-3, lr_critic=1e-2, gamma=0.8733, eps_clip=0.2, k_epochs=epochs, device=dev, seed=5)
+
+    def fill(ppo, T_, B_, gen, lo=0, hi=None):
+        xs = torch.randint(-1, 11, (T_, B_, U, n_in), generator=gen, dtype=torch.int16, device=dev)
+        acts = torch.randint(0, A, (T_, B_, U), generator=gen, dtype=torch.int32, device=dev)
+        lps = torch.rand((T_, B_, U), generator=gen, device=dev) * 0.5 - 2.8
+        rws = torch.randint(-5, 11, (T_, B_, U), generator=gen, device=dev).float()
+        hi = B_ if hi is None else hi
+        ppo.buf_x = [t[lo:hi].contiguous() for t in xs]
+        ppo.buf_a = [t[lo:hi].contiguous() for t in acts]
+        ppo.buf_lp = [t[lo:hi].contiguous() for t in lps]
+        ppo.buf_r = [t[lo:hi].contiguous() for t in rws]
+
+    # ---- check: sharded + all-reduced == whole buffer on one rank; weights bit-identical across ranks ----
+    Bc = 512
+    gen = torch.Generator(device=dev).manual_seed(1234)  # the same whole buffer on every rank
+    ppo_s = BatchedPPO(n_in, A, 16, 1, U, 1, **kw)
+    fill(ppo_s, 4, Bc * world, gen, rank * Bc, (rank + 1) * Bc)
+    gen = torch.Generator(device=dev).manual_seed(1234)
+    ppo_w = BatchedPPO(n_in, A, 16, 1, U, 1, **dict(kw, k_epochs=1))
+    fill(ppo_w, 4, Bc * world, gen)
+    unit = [5]
+    # one epoch on each: gradient buffers (the whole-buffer instance must not all-reduce: call the kernel directly)
+    Tn = 4
+    Gs = policy.returns(torch.stack(ppo_s.buf_r).reshape(Tn, -1), kw["gamma"], True).view(Tn * Bc, U)
+    Gw = policy.returns(torch.stack(ppo_w.buf_r).reshape(Tn, -1), kw["gamma"], True).view(Tn * Bc * world, U)
+    ids = torch.zeros(1, dtype=torch.int32, device=dev)
+    uid = torch.tensor([unit], dtype=torch.int32, device=dev)
+
+    def grad_of(ppo, Gn, TB):
+        flat = torch.zeros(ppo.actor.numel() + ppo.critic.numel(), device=dev)
+        ga, gc = flat[: ppo.actor.numel()].view_as(ppo.actor), flat[ppo.actor.numel():].view_as(ppo.critic)
+        policy.ppo_grad(ppo.actor.data, ppo.critic.data, n_in, A, torch.stack(ppo.buf_x).view(TB, U, n_in),
+                        torch.stack(ppo.buf_a).view(TB, U), torch.stack(ppo.buf_lp).view(TB, U), Gn, ids, uid, ga, gc)
+        return flat
+    g_shard = grad_of(ppo_s, Gs, Tn * Bc)
+    if world > 1:
+        dist.all_reduce(g_shard)
+        g_shard /= world
+    g_whole = grad_of(ppo_w, Gw, Tn * Bc * world)
+    rel = float((g_shard - g_whole).abs().max() / g_whole.abs().max())
+    ppo_s.update(unit)  # K epochs with the all-reduce inside
+    w = torch.cat([ppo_s.actor.data.view(-1), ppo_s.critic.data.view(-1)])
+    wmax, wmin = w.clone(), w.clone()
+    if world > 1:
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(wmin, op=dist.ReduceOp.MIN)
+    identical = bool(torch.equal(wmax.view(torch.int32), wmin.view(torch.int32)))
+    moved = float((w - torch.cat([ppo_w.actor.data.view(-1), ppo_w.critic.data.view(-1)])).abs().max())
+    del ppo_s, ppo_w
+
+    # ---- timing at the full per-rank size ----
+    ppo = BatchedPPO(n_in, A, 16, 1, U, 1, **kw)
+    gen = torch.Generator(device=dev).manual_seed(99 + rank)
+    fill(ppo, T, B, gen)
+    keep = (ppo.buf_x, ppo.buf_a, ppo.buf_lp, ppo.buf_r)
+    ms = []
+    for r in range(reps + 1):
+        ppo.buf_x, ppo.buf_a, ppo.buf_lp, ppo.buf_r = keep
+        ppo.profile = []
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ppo.update([3])
+        e1.record()
+        torch.cuda.synchronize()
+        ep = [(a.elapsed_time(b), b.elapsed_time(c), c.elapsed_time(d)) for a, b, c, d in ppo.profile]
+        ms.append((e0.elapsed_time(e1), sum(x[0] for x in ep) / len(ep), sum(x[1] for x in ep) / len(ep),
+                   sum(x[2] for x in ep) / len(ep)))
+    best = min(ms[1:], key=lambda t: t[0])
+    t = torch.tensor(best, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    upd_ms, grad_ms, ar_ms, adam_ms = (float(v) for v in t)
+    samples = T * B
+    return {"what": "cfg4: globally shared acceptor net, one sampled unit per update (src/SchedulingEnvironment.py:314-329); "
+                    "update = returns kernel + K x (msched_ppo_grad on the rank's env shard -> one flat all_reduce of both "
+                    "heads' gradients -> msched_adam_step), through agents.BatchedPPO.update; device-timed, max over ranks",
+            "net": f"{n_in}->16->16->{A} actor + {n_in}->16->16->1 critic, shared by {U} units",
+            "ranks": world, "T": T, "envs_per_rank": B, "samples_per_rank_per_epoch": samples, "epochs": epochs,
+            "update_ms": upd_ms, "epoch_grad_kernel_ms": grad_ms, "epoch_allreduce_us": 1e3 * ar_ms,
+            "epoch_adam_us": 1e3 * adam_ms, "allreduce_bytes": 4 * (ppo.actor.numel() + ppo.critic.numel()),
+            "samples_per_s_all_ranks": world * samples * epochs / (upd_ms * 1e-3),
+            "check": {"buffer": f"T=4 x {Bc} envs per rank", "sharded_allreduced_vs_whole_buffer_grad_max_rel_err": rel,
+                      "weights_bit_identical_across_ranks": identical, "weights_moved_by": moved,
+                      "ok": bool(identical and rel < 1e-4 and moved > 0)}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -349,6 +453,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--update-T", type=int, default=16, help="buffer length of the PPO.update measurement (0 = skip)")
+    ap.add_argument("--update-dp", type=int, default=1, help="the cfg4 data-parallel PPO update leg (0 = skip)")
+    ap.add_argument("--update-dp-T", type=int, default=8, help="buffer length (steps) of that leg")
     ap.add_argument("--rollout-steps", type=int, default=200,
                     help="steps of the secondary metric (env step + actor forward); 0 = skip")
     args = ap.parse_args()
@@ -766,6 +872,11 @@ def main():
                   "autograd_baseline": {"envs": Bs, "samples": Tk * Bs * U, "update_ms": a_ms, "kernel_path_update_ms_same_size": k_small_ms,
                                         "speedup": a_ms / k_small_ms, "what": "the same update through PyTorch autograd + torch.optim.Adam"}}
 
+    # ---- config 4: data-parallel PPO update (kernel gradient + NCCL all-reduce + Adam), every rank ----
+    update_dp = None
+    if args.update_dp and dense:
+        update_dp = ppo_update_dp_leg(torch, dist, dev, world, rank, T=args.update_dp_T)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -817,6 +928,7 @@ def main():
         "cpu_baseline_port": cpu_port,
         "rollout_with_policy": rollout,
         "ppo_update": update,
+        "ppo_update_dp": update_dp,
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
         "sticky_flags_after_warm": flags,
     }

@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define MSCHED_ABI_VERSION 1
+#define MSCHED_ABI_VERSION 2
 #define MSCHED_MAX_KINDS 16
 #define MSCHED_TILE_ENVS 128 /* record buffers are padded to a multiple of this */
 
@@ -123,6 +123,12 @@ typedef struct MschedLayout {
      * rows carry one leading pad so that (price,time) pairs are aligned words); auctioneer [C]
      * rows, same stride; offer [N][L] rows of 2C+2 values, stride o_off_row */
     int32_t o_acceptor, o_offer, o_auctioneer, o_acc_row, o_off_row;
+    /* compact observation record (msched_observe_compact / msched_step_compact), int16 per env:
+     * core [C][4] ownerID (0 = auctioneer), priority, remainingLength, jobKind (-1 = idle) at c_core;
+     * slot [N*L][2] priority, remainingLength (-1 = empty) at c_slot;
+     * offer [N*L][2] coreID (0 = no pending offer), offeredReward at c_offer -- the recipient of an offer is the
+     * owner of its core and its necessaryTime the slot's remainingLength (src/world.py:406-478) */
+    int32_t cobs_halfs, c_core, c_slot, c_offer;
 } MschedLayout;
 
 int msched_abi_version(void);
@@ -137,7 +143,7 @@ int msched_destroy(void *handle);
 /* which kernels this handle launches (diagnostics; bench.py reports it) */
 typedef struct MschedInfo {
     int32_t step_impl;        /* 0 one lane per env (any domain), 1 cooperative G lanes per env,
-                                 2 register-resident compile-time-domain kernel */
+                                 2 register-resident compile-time-domain kernel, 3 one warp per env (large domains) */
     int32_t fuses_observations; /* msched_step_observe is ONE launch */
     int32_t envs_per_cta, threads_per_cta;
     int32_t smem_bytes_per_cta; /* dynamic shared memory of the step launch (with observations if fused) */
@@ -214,6 +220,18 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
  * NULL) receives the offer-ID tables env.correspondingOfferIDs /
  * auctioneer_correspondingOfferIDs (src/SchedulingEnvironment.py:26-29, B*ids_halfs int16) */
 int msched_observe_dense(void *handle, int16_t *obs_dev, int16_t *ids_dev, void *stream);
+
+/* Compact observations: the information of Agent.gatherObservations / gatherDividedAuctioneerObservation
+ * (src/Agent.py:148-300, src/Auctioneer.py:20-77) without the per-(agent, core) replication of the dense rows --
+ * cores, job slots and pending offers once each (layout: MschedLayout.cobs_halfs / c_core / c_slot / c_offer).
+ * The dense record of BASELINE config 5 (N32 C64 L8) is 2.2 MB per environment, the compact one 2.5 KB; a policy
+ * kernel builds an acceptor row from (core j, the offers whose coreID is j+1 in slot order) and an offer row from
+ * (all cores, slot q).  cobs_dev: padded_envs * cobs_halfs int16. */
+int msched_observe_compact(void *handle, int16_t *cobs_dev, void *stream);
+
+/* msched_step followed by msched_observe_compact; ONE launch on the warp-per-environment kernel (large domains) */
+int msched_step_compact(void *handle, const int16_t *action_dev, const double *spawn_u_dev, uint32_t *result_dev,
+                        int16_t *cobs_dev, void *stream);
 
 /* Auctioneer.getAuctioneerAction (src/Auctioneer.py:95-102) = HardcodedAuctioneerAcceptor
  * .selectAction per core (src/HardcodedModules.py:48-78) on the CURRENT state: the table index of

@@ -80,7 +80,7 @@ class SchedulingEnv(object):
         mean = torch.where(cnt > 0, r["quality_sum"] / cnt.clamp(min=1).double(),
                            torch.full_like(r["quality_sum"], float("nan")))
         done = (c.round % self.world.episodeLength) == 0
-        if self.reward == "fix":  # src/Reward.py:193
+        if self.reward == "fix":  # src/Reward.py:193: env.terminationRevenues += generatedReward
             self.terminationRevenues = self.terminationRevenues + self._termination_revenue(r)
         return (*self._format_obs(o), offerRewards, acceptorRewards,
                 auctioneerReward, agentReward, (mean, cnt), done)
@@ -95,9 +95,13 @@ class SchedulingEnv(object):
         return off, r["acceptor"].unsqueeze(-1), r["auctioneer"], r["agent"]
 
     def _termination_revenue(self, r):
-        # sum of generatedReward over this step's terminations = agent reward credited by
-        # terminations; only tracked as a scalar total like env.terminationRevenues
-        return 0
+        """Sum of generatedReward over this step's terminations, per environment (int64 [B]).  In
+        getDividedFixedPricesReward (src/Reward.py:186-208) every termination credits generatedReward to its
+        owner's agentReward; every liability-chain entry then moves tradedReward from the offerer's agentReward
+        to the recipient's, or -- for the one entry the auctioneer accepted -- to auctioneerReward[core] (a core
+        terminates at most once per step, so that "=" never overwrites).  Trades between agents cancel, hence
+        sum(agentReward) + sum(auctioneerReward) = sum(generatedReward), exactly."""
+        return r["agent"].sum(dim=1, dtype=torch.int64) + r["auctioneer"].sum(dim=1, dtype=torch.int64)
 
     def render(self, mode="human"):
         e = self.core.export_state(0, 1)
@@ -115,9 +119,35 @@ class SchedulingEnv(object):
         return r["quality_sum"] / r["quality_cnt"].clamp(min=1).double(), r["quality_cnt"]
 
 
+class DividedHardcodedAgents(object):
+    """All N DividedHardcodedAgent objects of a world (src/Agent.py:622-641): per (agent, core) a
+    HardcodedAcceptor, per (agent, slot) a HardcodedOfferer (src/HardcodedModules.py:16-45, 81-109), evaluated
+    for every environment by ONE launch (msched_hardcoded_actions) that writes the env's action record."""
+
+    def __init__(self, world, env):
+        self.world, self.env = world, env
+
+    def getActions(self, offerObs=None, acceptorObs=None):
+        """The observations are accepted for signature compatibility; the kernel reads the observation
+        record the last reset()/step() wrote (the tensors handed in are views into it)."""
+        acc, off = self.env.core.hardcoded_actions(random_ties=self.world.randomAuctioneerTies)
+        return off, acc  # (offerNetActions, acceptorNetActions), src/Agent.py:641
+
+
 class HardcodedFixPriceEnvironment(SchedulingEnv):
-    """src/SchedulingEnvironment.py:439-456 (getDividedFixedPricesReward)."""
+    """src/SchedulingEnvironment.py:439-456 (getDividedFixedPricesReward): BASELINE config 1, the
+    heuristic agents of src/trainHC.py."""
     REWARD = "fix"
+
+    def __init__(self, world, params):
+        super().__init__(world, params)
+        self.agents = DividedHardcodedAgents(world, self)
+        self.world.agents = self.agents
+
+    def getActionForAllAgents(self, acceptorObs=None, offerObs=None):
+        """src/SchedulingEnvironment.py:150-172; returns (acceptorActions [B,N,C], offerActions [B,N,L])."""
+        off, acc = self.agents.getActions(offerObs, acceptorObs)
+        return acc, off
 
     def saveRewards(self, offerNetRewards, acceptorNetRewards, agentReward):
         ...

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("MSCHED_LIB") or os.path.join(HERE, "libmsched.so")  # MSCHED_LIB: A/B builds of the same ABI
 CSRC = os.path.join(HERE, "csrc")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_KINDS = 16
 TILE_ENVS = 128
 
@@ -46,7 +46,8 @@ class MschedLayout(C.Structure):
         "a_acceptor", "a_offer_core", "a_offer_price", "a_auctioneer", "a_spawn_kind",
         "r_offer", "r_price", "r_acceptor", "r_auctioneer", "r_agent", "r_quality", "r_counts",
         "r_flags", "r_auctioneer_idx", "RL", "RC",
-        "o_acceptor", "o_offer", "o_auctioneer", "o_acc_row", "o_off_row")]
+        "o_acceptor", "o_offer", "o_auctioneer", "o_acc_row", "o_off_row",
+        "cobs_halfs", "c_core", "c_slot", "c_offer")]
 
 
 class MschedInfo(C.Structure):
@@ -106,6 +107,8 @@ SYMBOLS = {
     "msched_step_observe": (C.c_int, [P, P, P, P, P, P]),
     "msched_step_host": (C.c_int, [P, P, P, P, P]),
     "msched_observe_dense": (C.c_int, [P, P, P, P]),
+    "msched_observe_compact": (C.c_int, [P, P, P]),
+    "msched_step_compact": (C.c_int, [P, P, P, P, P, P]),
     "msched_auctioneer_action": (C.c_int, [P, C.c_int, P, P]),
     "msched_hardcoded_actions": (C.c_int, [P, P, C.c_int, P, P, P, P]),
     "msched_export_state": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, P]),

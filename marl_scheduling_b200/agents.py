@@ -90,6 +90,7 @@ class BatchedPPO:
                                      unit_div=unit_div)
         self.buf_x, self.buf_a, self.buf_lp, self.buf_r = [], [], [], []
         self.step_no = 0
+        self.profile = None  # a list: every kernel-path epoch appends its (start, grad, all-reduce, Adam) CUDA events
 
     # -- rollout ---------------------------------------------------------------------------------
     def selectAction(self, x, x_stride, env_stride, n_envs, seed, action_rec=None, action_rec_stride=0,
@@ -116,7 +117,9 @@ class BatchedPPO:
         return act.view(n_envs, self.units)
 
     def saveReward(self, r):
-        self.buf_r.append(r.reshape(r.shape[0], self.units).float())
+        # a COPY: the reward tensors env.step returns are views into the result record, which a later step
+        # overwrites (float32 planes would otherwise be stored by reference)
+        self.buf_r.append(r.reshape(r.shape[0], self.units).to(torch.float32, copy=True))
 
     # -- update (N1) -------------------------------------------------------------------------------
     def _forward(self, flat, x, A):
@@ -206,16 +209,27 @@ class BatchedPPO:
                               torch.tensor([per_net[n] for n in nets], dtype=torch.int32, device=dev))
         net_ids, unit_ids = self._ids[key]
         stats = None
+        ev = None
         for _ in range(self.K_epochs):
+            if self.profile is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                ev[0].record()
             if len(nets) != self.n_nets:
                 self._grad.zero_()
             stats, self._ws = P.ppo_grad(self.actor.data, self.critic.data, self.n_in, self.A, X, Aold, LPold,
                                          G.view(T * B, U), net_ids, unit_ids, self._ga, self._gc,
                                          eps_clip=self.eps_clip, stats=stats, workspace=self._ws)
+            if ev:
+                ev[1].record()
             # data-parallel env shards: one flat-bucket all-reduce per epoch (NCCL over NVLink)
             allreduce_mean_(self._grad)
+            if ev:
+                ev[2].record()
             self.optimizer.step([self._ga, self._gc], nets)
-        return float(stats[:, 1].mean())
+            if ev:
+                ev[3].record()
+                self.profile.append(ev)
+        return stats[:, 1].mean()
 
     def sync_old_and_clear(self):
         self.policy_old.weights.copy_(self.actor.detach())

@@ -80,7 +80,7 @@ class BatchedSchedulingEnv:
         """Which kernels the handle launches: dict(step_impl, fuses_observations, ...)."""
         i = L.MschedInfo()
         L.check(self.lib.msched_get_info(self.handle, C.byref(i)))
-        return dict(step_impl=("lane", "coop", "fused")[i.step_impl],
+        return dict(step_impl=("lane", "coop", "fused", "warp")[i.step_impl],
                     fuses_observations=bool(i.fuses_observations), envs_per_cta=i.envs_per_cta,
                     threads_per_cta=i.threads_per_cta, smem_bytes_per_cta=i.smem_bytes_per_cta)
 
@@ -171,6 +171,21 @@ class BatchedSchedulingEnv:
                                              None if su is None else su.data_ptr(), result.data_ptr(),
                                              obs.data_ptr(), self._stream()))
         return result, obs
+
+    def step_compact_records(self, action=None, result=None, spawn_u=None, cobs=None):
+        """step_records + the COMPACT observations of the new state (msched_step_compact: one launch on the
+        warp-per-environment kernel of the large domains).  Asynchronous."""
+        action = self.action if action is None else action
+        result = self.result if result is None else result
+        cobs = self._cobs_buffer() if cobs is None else cobs
+        su = None
+        if spawn_u is not None:
+            su = torch.as_tensor(spawn_u, dtype=torch.float64).to(self.device).contiguous()
+            self._keep_su = su
+        L.check(self.lib.msched_step_compact(self.handle, action.data_ptr(),
+                                             None if su is None else su.data_ptr(), result.data_ptr(),
+                                             cobs.data_ptr(), self._stream()))
+        return result, cobs
 
     def step(self, offer_core, acceptor, auctioneer=None, offer_price=None, spawn_kind=None,
              spawn_u=None, observe=False):
@@ -265,6 +280,29 @@ class BatchedSchedulingEnv:
             out["auctioneer_ids"] = ids[:, N * Cc * NL:].view(B, Cc, NL)
         return out
 
+    def _cobs_buffer(self):
+        if getattr(self, "_cobs", None) is None:
+            self._cobs = torch.zeros((self.layout.padded_envs, self.layout.cobs_halfs), dtype=torch.int16,
+                                     device=self.device)
+        return self._cobs
+
+    def compact_views(self, cobs=None):
+        """int16 views into a compact observation record buffer: core [B,C,4] (ownerID, priority,
+        remainingLength, jobKind; -1 = idle), slot [B,N,L,2] (priority, remainingLength; -1 = empty), offer
+        [B,N,L,2] (coreID, 0 = none; offeredReward)."""
+        lay = self.layout
+        c = (self._cobs_buffer() if cobs is None else cobs)[: self.B]
+        return dict(core=c[:, lay.c_core: lay.c_core + 4 * self.C].view(self.B, self.C, 4),
+                    slot=c[:, lay.c_slot: lay.c_slot + 2 * self.NL].view(self.B, self.N, self.Lc, 2),
+                    offer=c[:, lay.c_offer: lay.c_offer + 2 * self.NL].view(self.B, self.N, self.Lc, 2))
+
+    def observe_compact(self):
+        """Compact observations of the current state (msched_observe_compact): the content of the dense
+        reference rows (src/Agent.py:148-300, src/Auctioneer.py:20-77) with every core, slot and pending
+        offer stored once -- what the large domains (config 5) use instead of the 2.2 MB dense record."""
+        L.check(self.lib.msched_observe_compact(self.handle, self._cobs_buffer().data_ptr(), self._stream()))
+        return self.compact_views()
+
     def auctioneer_action(self, random_ties=True):
         """Auctioneer.getAuctioneerAction (reference src/Auctioneer.py:95-102) on the current
         state: int16 [B,C] table indices (N*L = reject)."""
@@ -272,6 +310,24 @@ class BatchedSchedulingEnv:
         L.check(self.lib.msched_auctioneer_action(self.handle, int(random_ties), out.data_ptr(),
                                                   self._stream()))
         return out
+
+    def hardcoded_actions(self, obs=None, random_ties=True, u=None, want_ncand=False):
+        """DividedHardcodedAgent.getActions of every agent (reference src/Agent.py:622-641,
+        src/HardcodedModules.py:16-45,81-109) on an observation record (default: the env's current one):
+        fills the acceptor idx and offer core fields of the env's action record and returns those views
+        ([B,N,C], [B,N,L]).  u: float32 [B, N*C+N*L] tie draws (parity tests); want_ncand adds the number of
+        tie candidates per unit, int32 [B, N*C+N*L]."""
+        obs = self._obs_buffer() if obs is None else obs
+        U = self.N * self.C + self.NL
+        if u is not None:
+            u = torch.as_tensor(u, dtype=torch.float32).to(self.device).contiguous().view(self.B, U)
+        nc = torch.zeros((self.B, U), dtype=torch.int32, device=self.device) if want_ncand else None
+        L.check(self.lib.msched_hardcoded_actions(self.handle, obs.data_ptr(), int(bool(random_ties)),
+                                                  None if u is None else u.data_ptr(), self.action.data_ptr(),
+                                                  None if nc is None else nc.data_ptr(), self._stream()))
+        self._keep_u = u
+        out = (self.acceptor_actions, self.offer_core_actions)
+        return out + (nc,) if want_ncand else out
 
     # ------------------------------------------------------------------ debug / parity
     def export_state(self, env0=0, count=None):

@@ -16,6 +16,7 @@
 #include "coop_step_kernel.cuh"
 #include "fused_step_kernel.cuh"
 #include "hardcoded_kernel.cuh"
+#include "warp_step.h"
 
 using namespace msched;
 
@@ -95,6 +96,10 @@ int compute_layout(const MschedConfig *c, MschedLayout *o)
     o->o_off_row = RO;
     o->obs_halfs = even_odd_half((int)oh);
     o->ids_halfs = (N * C + C) * NL;
+    o->cobs_halfs = compact_obs_halfs(C, NL);
+    o->c_core = 0;
+    o->c_slot = 4 * C;
+    o->c_offer = 4 * C + 2 * NL;
     o->chain_words = C * c->chainCapacity * 2;
     return MSCHED_OK;
 }
@@ -115,6 +120,8 @@ struct Handle {
     int coopG, coopThreads;
     size_t coopSmem;
     bool useCoop;
+    size_t warpSmem;  // warp-per-environment kernel (msched_warp.cu): shared memory per CTA, 0 = not available
+    bool useWarp;
     StepKernel fusedFn;  // compile-time-domain register-resident kernel (step + observations), or null
     size_t fusedSmem, fusedSmemObs;  // dynamic shared memory without / with the observation tile
     int fusedRoles;                  // warps per 32-env tile
@@ -211,6 +218,7 @@ void fill_params(Handle *h)
     p.netZero = (float)c.netZeroOfferReward;
     p.seed = c.seed;
     p.envOffset = c.envOffset;
+    p.COH = l.cobs_halfs;
 }
 
 int pick_tile(size_t bytesPerEnv, int smemOptin, const char *envName)
@@ -236,6 +244,8 @@ void launch_step(const Handle *h, const DevParams &p0, cudaStream_t s, bool self
     p.roundTicket = (h->deviceRound && selfAdvance) ? reinterpret_cast<unsigned *>(h->roundDev + 1) : nullptr;
     if (h->useFused) {
         h->fusedFn<<<p.Bpad / 32, 32 * h->fusedRoles, p.obs ? h->fusedSmemObs : h->fusedSmem, s>>>(p);
+    } else if (h->useWarp) {
+        launch_warp_step(p, h->warpSmem, s);
     } else if (h->useCoop) {
         const int E = h->coopThreads / h->coopG;
         h->coopFn<<<p.Bpad / E, h->coopThreads, h->coopSmem, s>>>(p);
@@ -320,7 +330,15 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
             CUDA_TRY(cudaFuncSetAttribute(h->coopFn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->coopSmem));
         }
     }
-    if (!h->stepTile && !h->coopFn) {
+    // warp-per-environment kernel: the large domains (BASELINE config 5).  Default for more than 8 cores or more
+    // than 64 job slots per environment, where the lane / group kernels' serial offer sweep dominates
+    {
+        CUDA_TRY(warp_step_init());
+        h->warpSmem = warp_step_smem_bytes(h->p, h->smemOptin);
+        if (h->warpSmem) CUDA_TRY(warp_step_prepare(h->warpSmem));
+        h->useWarp = h->warpSmem && (cfg->C > 8 || cfg->N * cfg->L > 64);
+    }
+    if (!h->stepTile && !h->coopFn && !h->warpSmem) {
         return fail(MSCHED_E_ARG, "domain too large: the records of 4 environments must fit in shared memory");
     }
     // small batches are latency-bound: the cooperative kernel's shorter per-env critical path wins
@@ -353,16 +371,19 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
         CUDA_TRY(cudaFuncSetAttribute(h->fusedFn, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(h->fuseObs ? h->fusedSmemObs : h->fusedSmem)));
         h->useFused = true;
+        h->useWarp = false;
     }
     // MSCHED_STEP_IMPL=fused|lane|coop forces one implementation (tests run all of them)
     if (const char *e = getenv("MSCHED_STEP_IMPL")) {
-        const bool wantFused = !strcmp(e, "fused"), wantCoop = !strcmp(e, "coop"), wantLane = !strcmp(e, "lane");
-        if ((wantFused && !h->fusedFn) || (wantCoop && !h->coopFn) || (wantLane && !h->stepTile)) {
+        const bool wantFused = !strcmp(e, "fused"), wantCoop = !strcmp(e, "coop"), wantLane = !strcmp(e, "lane"),
+                   wantWarp = !strcmp(e, "warp");
+        if ((wantFused && !h->fusedFn) || (wantCoop && !h->coopFn) || (wantLane && !h->stepTile) || (wantWarp && !h->warpSmem)) {
             return fail(MSCHED_E_ARG, "MSCHED_STEP_IMPL: that kernel is not available for this domain");
         }
-        if (wantFused || wantCoop || wantLane) {
+        if (wantFused || wantCoop || wantLane || wantWarp) {
             h->useFused = wantFused;
             h->useCoop = wantCoop;
+            h->useWarp = wantWarp;
         }
     }
     h->obsFn = pick_obs_kernel(cfg->N, cfg->C, cfg->L);
@@ -405,6 +426,11 @@ int msched_get_info(void *handle, MschedInfo *out)
         out->envs_per_cta = 32;
         out->threads_per_cta = 32 * h->fusedRoles;
         out->smem_bytes_per_cta = (int)(h->fuseObs ? h->fusedSmemObs : h->fusedSmem);
+    } else if (h->useWarp) {
+        out->step_impl = 3;
+        out->envs_per_cta = 4;
+        out->threads_per_cta = 128;
+        out->smem_bytes_per_cta = (int)h->warpSmem;
     } else if (h->useCoop) {
         out->step_impl = 1;
         out->envs_per_cta = h->coopThreads / h->coopG;
@@ -579,6 +605,46 @@ int msched_step_observe(void *handle, const int16_t *action_dev, const double *s
     p.spawnU = spawn_u_dev;
     p.result = result_dev;
     p.obs = obs_dev;
+    p.round = (int)h->round;
+    p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
+    launch_step(h, p, static_cast<cudaStream_t>(stream));
+    CUDA_TRY(cudaGetLastError());
+    h->round += 1;
+    return MSCHED_OK;
+}
+
+int msched_observe_compact(void *handle, int16_t *cobs_dev, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !cobs_dev) return fail(MSCHED_E_ARG, "null handle/cobs");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    DevParams p = h->p;
+    p.cobs = cobs_dev;
+    launch_observe_compact(p, static_cast<cudaStream_t>(stream));
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}
+
+int msched_step_compact(void *handle, const int16_t *action_dev, const double *spawn_u_dev, uint32_t *result_dev,
+                        int16_t *cobs_dev, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !cobs_dev) return fail(MSCHED_E_ARG, "null handle/cobs");
+    if (!h->useWarp) {
+        int rc = msched_step(handle, action_dev, spawn_u_dev, result_dev, stream);
+        if (rc) return rc;
+        return msched_observe_compact(handle, cobs_dev, stream);
+    }
+    if (!action_dev || !result_dev) return fail(MSCHED_E_ARG, "null action/result");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    if (!aligned16(action_dev) || !aligned16(result_dev)) return fail(MSCHED_E_ARG, "buffers must be 16-byte aligned");
+    if (h->cfg.spawnMode == MSCHED_SPAWN_U64 && !spawn_u_dev) return fail(MSCHED_E_ARG, "spawn_u required");
+    DevParams p = h->p;
+    p.action = action_dev;
+    p.spawnU = spawn_u_dev;
+    p.result = result_dev;
+    p.obs = nullptr;
+    p.cobs = cobs_dev;
     p.round = (int)h->round;
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     launch_step(h, p, static_cast<cudaStream_t>(stream));

@@ -60,6 +60,8 @@ struct DevParams {
     int *roundDev;                 // device-side round counter (CUDA-graph replays), or null -> `round`
     unsigned *roundTicket;         // CTA exit tickets: the last CTA of a launch advances roundDev (or null)
     int *stats;                    // episode statistics int32 [Bpad][J][4], or null (msched_bind_stats)
+    int16_t *cobs;                 // compact observation records (warp kernel / msched_observe_compact), or null
+    int COH;                       // compact observation halfs per env
 };
 
 // ---- host+device layout arithmetic ------------------------------------------------------

@@ -317,3 +317,83 @@ def ppo_update(actor0, critic0, states, actions, logp_old, rewards, gamma, eps_c
         adam_step(a, ga, ma, va, lr_actor, k)
         adam_step(c, gc, mc, vc, lr_critic, k)
     return a, c
+
+
+# ---- hard-coded agents (BASELINE config 1), restated from the reference ---------------------------------------
+def _hc_ratio(a, b):
+    """calculateRewardRatio, src/HardcodedModules.py:5-13, as an exact Fraction."""
+    from fractions import Fraction
+    if a in (-1, -2) or b in (-1, -2):
+        return Fraction(-1)
+    return Fraction(int(a), int(b))
+
+
+def hardcoded_actions(obs_acc, obs_off, u_acc=None, u_off=None, cands_out=None):
+    """DividedHardcodedAgent.getActions for all agents of ONE world (src/Agent.py:622-641):
+    HardcodedAcceptor.selectAction per (agent, core) (src/HardcodedModules.py:16-45) and
+    HardcodedOfferer.selectAction per (agent, slot) (:81-109) on the dense observations
+    obs_acc [N,C,3+2NL], obs_off [N,L,2C+2].  The reference breaks ties with random.sample; here candidate
+    floor(u * #candidates) in index order is taken (u = 0 -> the first), the contract of the CUDA kernel.
+    Returns (acc [N,C], off [N,L], ncand_acc [N,C], ncand_off [N,L]); cands_out (a dict) receives the candidate
+    index lists under ("acc", i, j) / ("off", i, q)."""
+    obs_acc, obs_off = np.asarray(obs_acc), np.asarray(obs_off)
+    N, Cc, W = obs_acc.shape
+    L = obs_off.shape[1]
+    NL = (W - 3) // 2
+    acc = np.full((N, Cc), NL, np.int32)
+    off = np.zeros((N, L), np.int32)
+    nca = np.zeros((N, Cc), np.int32)
+    nco = np.zeros((N, L), np.int32)
+
+    def pick(cands, u):
+        k = int(np.float32(u) * np.float32(len(cands)))
+        return cands[min(k, len(cands) - 1)]
+    for i in range(N):
+        for j in range(Cc):
+            row = obs_acc[i, j].tolist()
+            if row[0] == 0:
+                continue
+            own = _hc_ratio(row[1], row[2])
+            ratios = [_hc_ratio(p, t) for p, t in zip(row[3::2], row[4::2])]
+            mx = max(ratios)
+            if mx > own:
+                cands = [k for k, r in enumerate(ratios) if r == mx]
+                nca[i, j] = len(cands)
+                if cands_out is not None:
+                    cands_out[("acc", i, j)] = cands
+                acc[i, j] = pick(cands, 0.0 if u_acc is None else u_acc[i][j])
+        for q in range(L):
+            row = obs_off[i, q].tolist()
+            ratios = [_hc_ratio(p, t) for p, t in zip(row[:-2:2], row[1:-2:2])]
+            mn = min(ratios)
+            cands = [k for k, r in enumerate(ratios) if r == mn]
+            nco[i, q] = len(cands)
+            if cands_out is not None:
+                cands_out[("off", i, q)] = cands
+            off[i, q] = pick(cands, 0.0 if u_off is None else u_off[i][q])
+    return acc, off, nca, nco
+
+
+def hardcoded_draws(seed, env, round_, n_units):
+    """The u of every unit of one env and round as the CUDA kernel draws them: Philox counter (env lo, env hi,
+    round, 3 << 28 | call << 12), key = seed; unit n uses word n % 4 of call n // 4, u = (x >> 8) * 2^-24."""
+    out = np.zeros(n_units, np.float32)
+    for call in range((n_units + 3) // 4):
+        x = philox([env & 0xFFFFFFFF, (env >> 32) & 0xFFFFFFFF, round_ & 0xFFFFFFFF, (3 << 28) | (call << 12)],
+                   [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF])
+        for w in range(4):
+            if 4 * call + w < n_units:
+                out[4 * call + w] = np.float32(int(x[w]) >> 8) * np.float32(1.0 / 16777216.0)
+    return out
+
+
+def compact_observation(e):
+    """The compact observation record (include/msched.h: MschedLayout.c_core / c_slot / c_offer) of one world from
+    its exported state `e` (Oracle.export): core [C,4] = ownerID, priority, remainingLength, jobKind; slot [N,L,2] =
+    priority, remainingLength; offer [N,L,2] = coreID (0 = none), offeredReward.  The same fields the dense rows of
+    src/Agent.py:167-300 and src/Auctioneer.py:34-77 are built from."""
+    core = np.stack([e["core_owner"], e["core_prio"], e["core_rem"], e["core_kind"]], -1).astype(np.int32)
+    slot = np.stack([e["slot_prio"], e["slot_rem"]], -1).astype(np.int32)
+    has = np.asarray(e["off_core"]) > 0
+    offer = np.stack([np.where(has, e["off_core"], 0), np.where(has, e["off_price"], 0)], -1).astype(np.int32)
+    return dict(core=core, slot=slot, offer=offer)

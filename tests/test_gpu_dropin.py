@@ -205,3 +205,66 @@ def test_ppo_checkpoint_roundtrip(tmp_path):
     assert torch.equal(world.agents.acceptor.actor.detach(), saved)
     assert torch.equal(world.agents.acceptor.policy_old.weights, saved)
     env.close()
+
+
+@pytest.mark.parametrize("arch", ["divided", "free", "semi", "fully"])
+def test_save_rewards_routes_like_the_reference(arch):
+    """Row a13: what env.saveRewards leaves in every unit's reward buffer, per architecture, against the oracle's
+    rewards for the same actions routed by the reference's rules -- divided: unit (i,k) gets [i][k][0]
+    (src/Agent.py:531-536); free prices: core chooser / price chooser / acceptor planes (:610-619); semi-aggregated:
+    the acceptor unit gets agentReward[i], the offer unit offerRewards[i][0] (:388-390,
+    src/SchedulingEnvironment.py:223-225); fully aggregated: agentReward[i] + offerRewards[i][0] (:490-492,
+    src/SchedulingEnvironment.py:243-247)."""
+    import torch
+    from marl_scheduling_b200 import SchedulingEnvironment as SE
+    from marl_scheduling_b200.world import World
+    from oracle import oracle as O
+    B, T = 48, 14
+    if arch == "free":
+        dom = dict(N=2, C=3, L=3, prios=[2, 4, 8], lens=[5, 5, 5], probs=[1 / 3] * 3, fix=[1], episodeLength=10)
+        wp = dict(WP, freePrices=True, numberOfAgents=2, numberOfCores=3, collectionLength=3,
+                  possibleJobPriorities=[2, 4, 8], possibleJobLengths=[5, 5, 5], probabilities=[1 / 3] * 3)
+        mode = "free_comm"
+    elif arch == "divided":
+        dom, wp, mode = DOM, WP, "fix"
+    else:
+        dom = dict(N=2, C=2, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7], episodeLength=10)
+        wp = dict(WP, numberOfAgents=2, numberOfCores=2)
+        mode = "agg"
+    world = World(dict(wp, numberOfEnvironments=B, seed=6))
+    env = {"divided": lambda: SE.PPODividedFixedPriceEnv(world, RL), "free": lambda: SE.PPODividedFreePriceEnv(world, RL, True),
+           "semi": lambda: SE.PPOAggregatedFixPriceEnv(world, RL), "fully": lambda: SE.PPOFullyAggregatedFixPriceEnv(world, RL)}[arch]()
+    orc = O.Oracle(B, dom, mode, tie_mode=O.TIE_PHILOX, seed=6)
+    accO, offO, aucO = env.reset()
+    exp = {}
+    for t in range(T):
+        acceptorActions, offerActions = env.getActionForAllAgents(accO, offO)
+        if arch == "free":
+            offc, offp = (x.cpu().numpy() for x in offerActions)
+        else:
+            offc, offp = offerActions.cpu().numpy(), None
+        acc = acceptorActions.cpu().numpy()
+        aa = world.auctioneer.getAuctioneerAction(aucO)
+        accO, offO, aucO, offR, accR, aucR, agR, q, done = env.step(offerActions, acceptorActions, aa)
+        env.saveRewards(offR, accR, agR)
+        orc.step(offc, acc, None, offp=offp)
+        if arch == "divided":
+            cur = dict(acceptor=orc.r_acceptor.reshape(B, -1), offer=orc.r_offer.reshape(B, -1))
+        elif arch == "free":
+            cur = dict(acceptor=orc.r_acceptor.reshape(B, -1), core=orc.r_offer.reshape(B, -1), price=orc.r_price.reshape(B, -1))
+        elif arch == "semi":
+            cur = dict(acceptor=orc.r_agent, offer=orc.r_offer[..., 0])
+        else:
+            cur = dict(unit=orc.r_agent + orc.r_offer[..., 0])
+        for k, v in cur.items():
+            exp.setdefault(k, []).append(np.asarray(v, np.float64).copy())
+    n_nonzero = 0
+    for name, rows in exp.items():
+        ppo = getattr(env.agents, name)
+        got = torch.stack(ppo.buf_r).cpu().numpy().astype(np.float64)
+        want = np.stack(rows)
+        assert got.shape == want.shape == (T, B, ppo.units), (name, got.shape, want.shape)
+        assert np.array_equal(got, want), name
+        n_nonzero += int((want != 0).sum())
+    assert n_nonzero > 20
+    env.close()

@@ -7,7 +7,7 @@ from test_gpu_step_parity import DOMS, _env, _has_fused, random_actions
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("impl", ["lane", "coop", "fused1", "fused4"])
+@pytest.mark.parametrize("impl", ["lane", "coop", "warp", "fused1", "fused4"])
 @pytest.mark.parametrize("key", ["cfg3", "cfg2", "agg", "odd"])
 def test_episode_statistics_and_sums(key, impl):
     from marl_scheduling_b200.metrics import EpisodeMetrics

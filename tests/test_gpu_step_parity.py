@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _env(B, meta, impl=None, **kw):
-    """impl: None (library default), "lane" (one lane per env), "coop" (G lanes per env) or
+    """impl: None (library default), "lane" (one lane per env), "coop" (G lanes per env), "warp" (one warp per env) or
     "fusedR" (compile-time-domain kernel with R = 1, 2 or 4 role warps per 32-env tile)."""
     import os
     from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
@@ -46,7 +46,7 @@ def _one(exp, b):
     return {k: (v[b] if isinstance(v, np.ndarray) else v) for k, v in exp.items()}
 
 
-@pytest.mark.parametrize("impl", ["lane", "coop", "fused1", "fused2", "fused4"])
+@pytest.mark.parametrize("impl", ["lane", "coop", "warp", "fused1", "fused2", "fused4"])
 @pytest.mark.parametrize("name", golden_names())
 def test_cuda_replays_reference_trace(name, impl):
     """Recorded reference trace, replicated into B envs that straddle two tiles."""
@@ -130,7 +130,7 @@ def random_actions(rng, B, dom, free, p_valid_hint=None):
 DOMS["cfg5"] = (dict(N=32, C=64, L=8, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7]), "fix")
 
 
-@pytest.mark.parametrize("impl", ["lane", "coop", "fused1", "fused2", "fused4"])
+@pytest.mark.parametrize("impl", ["lane", "coop", "warp", "fused1", "fused2", "fused4"])
 @pytest.mark.parametrize("key", list(DOMS))
 @pytest.mark.parametrize("auction", ["first", "random"])
 def test_cuda_matches_oracle_random_batch(key, auction, impl):
@@ -145,7 +145,7 @@ def test_cuda_matches_oracle_random_batch(key, auction, impl):
     if key == "cfg5":
         if impl == "lane":
             pytest.skip("config 5 exceeds the lane-per-env kernel's shared-memory budget")
-        B, T = 96, 25
+        B, T = (500, 40) if impl == "warp" else (96, 25)
     seed = 1234
     env = _env(B, dict(dom, mode=mode), impl=impl, auction=auction, spawn="philox", seed=seed, env_offset=77)
     orc = O.Oracle(B, dom, mode, tie_mode=O.TIE_PHILOX if auction == "random" else O.TIE_FIRST,
@@ -175,8 +175,13 @@ def test_cuda_matches_oracle_random_batch(key, auction, impl):
                     assert np.array_equal(np.asarray(e[k][b]), np.asarray(ob[k])), (key, t, b, k)
                 assert np.array_equal(e["chain"][b], ob["chain"]), (key, t, b, "chain")
                 assert e["job_counter"][b] == ob["job_counter"]
+            co = {k: v.cpu().numpy() for k, v in env.observe_compact().items()}
+            for b in rng.integers(0, B, 10):   # the compact observation record against the oracle's state
+                oc = O.compact_observation(orc.export(int(b)))
+                for k in oc:
+                    assert np.array_equal(co[k][b].reshape(oc[k].shape), oc[k]), (key, t, b, k)
             if key == "cfg5":
-                continue  # dense observations are 2.2 MB per env there; the state record is the compact form
+                continue  # dense observations are 2.2 MB per env there; the compact record is what config 5 uses
             of = {k: v.cpu().numpy() for k, v in env.obs_views().items()} if fused else None
             o = {k: v.cpu().numpy() for k, v in env.observe(with_ids=True).items()}
             if fused:
@@ -302,7 +307,7 @@ def test_edge_domains_match_oracle(key):
     from oracle import oracle as O
     dom, mode, B = EDGE[key]
     free = mode.startswith("free")
-    impls = ["coop"] if key == "cores64" else (["lane", "coop"] + (["fused1", "fused2"] if _has_fused(dom) else []))
+    impls = ["coop", "warp"] if key == "cores64" else (["lane", "coop", "warp"] + (["fused1", "fused2"] if _has_fused(dom) else []))
     from marl_scheduling_b200 import MschedError
     ran = 0
     for impl in impls:
@@ -397,4 +402,70 @@ def test_full_size_batch_windows_match_oracle_and_jobs_are_conserved(key, B):
     spawned = np.asarray(e["job_counter"]).astype(np.int64) - 1
     assert np.array_equal(spawned, terminated.cpu().numpy() + present)
     assert spawned.min() > 0 and len(np.unique(spawned)) > 3      # the envs really diverged
+    env.close()
+
+
+def test_config5_full_size_windows_match_oracle_and_jobs_are_conserved():
+    """BASELINE configs[4] at its full size (N32 C64 L8, 262,144 envs, the kernel the library picks for it): the
+    size-independent properties of test_full_size_batch_windows_... -- (1) three windows of the big batch equal
+    oracle instances started at the same global env offsets, step by step (auction winners, every reward plane,
+    counts) and in their final state (cores, slots, offers, chains); (2) over ALL envs: jobs spawned = jobs
+    terminated + jobs present, at most C acceptances per step, no fault flags.  The action records are drawn on the
+    device (a host copy of one step's actions would be 4 GB)."""
+    import torch
+    from oracle import oracle as O
+    dom, mode = DOMS["cfg5"]
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    NL = N * L
+    B, T, W, seed, base = 262144, 14, 8, 7, 1 << 22
+    env = _env(B, dict(dom, mode=mode), auction="random", spawn="philox", seed=seed, env_offset=base, chain_capacity=16)
+    lay = env.layout
+    wins = [0, 131072 + 40, B - W]
+    orcs = [O.Oracle(W, dom, mode, chain_cap=16, tie_mode=O.TIE_PHILOX, seed=seed, env_offset=base + w0) for w0 in wins]
+    gen = torch.Generator(device=env.device).manual_seed(3)
+    terminated = torch.zeros(B, dtype=torch.int64, device=env.device)
+    acc_v, off_v = env.acceptor_actions, env.offer_core_actions
+    for t in range(T):
+        # acceptor indices biased towards the first table entries so that agents really accept offers
+        acc_v.random_(0, NL + 1, generator=gen)
+        low = torch.rand((B, N, C), device=env.device, generator=gen) < 0.6
+        acc_v[low] = 0
+        off_v.random_(0, C + 1, generator=gen)
+        env.step_compact_records()   # ONE launch: transition + compact observations of the new state
+        r = env.rewards()
+        terminated += r["n_terminated"].long()
+        assert int(r["n_accepted"].max()) <= C and int(r["flags"].max()) == 0, t
+        for w0, orc in zip(wins, orcs):
+            sl = slice(w0, w0 + W)
+            orc.step(off_v[sl].cpu().numpy(), acc_v[sl].cpu().numpy(), None)
+            assert np.array_equal(r["auctioneer_idx"][sl].cpu().numpy(), orc.auc_out), (t, w0)
+            assert np.array_equal(r["agent"][sl].cpu().numpy(), orc.r_agent), (t, w0)
+            assert np.array_equal(r["acceptor"][sl].cpu().numpy(), orc.r_acceptor), (t, w0)
+            assert np.array_equal(r["auctioneer"][sl].cpu().numpy(), orc.r_auctioneer), (t, w0)
+            assert np.array_equal(r["offer"][sl].cpu().numpy().astype(np.float64), orc.r_offer), (t, w0)
+            assert np.array_equal(r["n_accepted"][sl].cpu().numpy(), orc.n_accepted), (t, w0)
+            assert np.array_equal(r["n_terminated"][sl].cpu().numpy(), orc.n_term), (t, w0)
+    assert env.info()["step_impl"] == "warp"
+    n_acc = 0
+    co = {k: v for k, v in env.compact_views().items()}
+    for w0, orc in zip(wins, orcs):
+        e = env.export_state(w0, W)
+        for b in range(W):
+            ob = orc.export(b)
+            oc = O.compact_observation(ob)
+            for k in oc:   # the compact observations the step launch wrote
+                assert np.array_equal(co[k][w0 + b].cpu().numpy().reshape(oc[k].shape), oc[k]), (w0, b, k)
+            for k in STATE_KEYS:
+                assert np.array_equal(np.asarray(e[k][b]), np.asarray(ob[k])), (w0, b, k)
+            assert np.array_equal(e["chain"][b], ob["chain"]), (w0, b)
+            n_acc += int(ob["chain_len"].sum())
+    assert n_acc > 20  # liability chains are in play
+    # conservation over all 262,144 envs, read from the state records (csrc/msched_common.cuh: word 0 = next jobID,
+    # core c jobID at 2+3c+1, slot s jobID at S_SLOT+4s+1; -1 = empty)
+    st = env.state[:B]
+    s_slot = 2 + 3 * C + (C + 3) // 4
+    present = (st[:, 3:2 + 3 * C:3] > 0).sum(1) + (st[:, s_slot + 1::4][:, :NL] > 0).sum(1)
+    spawned = st[:, 0].long() - 1
+    assert torch.equal(spawned, terminated + present)
+    assert int(spawned.min()) > 0 and int(terminated.sum()) > B
     env.close()
