@@ -48,7 +48,7 @@ CONFIGS = {
     # BASELINE.json configs[4]: large domain, cooperative kernel (one warp per env), no dense obs
     "cfg5": dict(dom=dict(N=32, C=64, L=8, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7],
                           mult=1, newJobs=1, episodeLength=100),
-                 mode="fix", envs=262144, obs="none", ring=2,
+                 mode="fix", envs=262144, obs="compact", ring=2,
                  desc="N32 C64 L8, 2 job kinds, fixed prices, 262,144 envs, compact observations (state record)"),
 }
 
@@ -65,7 +65,8 @@ def algorithmic_bytes(dom, mode):
     a = N * C * w + NL * (2 if free else 1) + C * w + N * nj
     r = 4 * N * C + 4 * NL * (2 if free else 1) + 4 * C + 4 * N
     o = 2 * (N * C * (3 + 2 * NL) + NL * (2 * C + 2) + C * (3 + 2 * NL))
-    return dict(step=2 * S + a + r, obs=o, state=S)
+    oc = 2 * (2 * C + 2 * NL + 3 * NL)  # compact observations
+    return dict(step=2 * S + a + r, obs=o, obs_compact=oc, state=S)
 
 
 def measured_peak():
@@ -438,7 +439,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg3", choices=list(CONFIGS))
     ap.add_argument("--envs", type=int, default=0, help="envs per GPU (default: the config's)")
-    ap.add_argument("--obs", default="dense", choices=["dense", "none"])
+    ap.add_argument("--obs", default="dense", choices=["dense", "none", "compact"])
     ap.add_argument("--l2", default="auto", choices=["auto", "rotate", "flush"],
                     help="rotate: shards larger than L2 visited round-robin, back-to-back launches; "
                          "flush: 256 MiB write before every step, per-launch events")
@@ -480,9 +481,10 @@ def main():
     dom, mode = cfg["dom"], cfg["mode"]
     B = args.envs or cfg["envs"]
     N = dom["N"]
-    if cfg.get("obs") == "none":
-        args.obs = "none"
+    if cfg.get("obs") in ("none", "compact"):
+        args.obs = cfg["obs"]
     dense = args.obs == "dense"
+    compact = args.obs == "compact"
 
     def make_env(k):
         return BatchedSchedulingEnv(B, world_params_from_dom(dom, mode.startswith("free")), reward=mode,
@@ -505,6 +507,8 @@ def main():
     def step_on(e, action, result):
         if dense:
             e.step_observe_records(action, result)
+        elif compact:   # transition + compact observations (ONE launch on the warp-per-environment kernel)
+            e.step_compact_records(action, result)
         else:
             e.step_records(action, result)
 
@@ -514,9 +518,10 @@ def main():
         # through the 126 MB L2 since.  Launches are back to back on one stream; each timed block
         # of S*G launches has its own freshly drawn action records (drawn untimed between blocks).
         per_set = B * (lay.state_words * 4 + lay.action_halfs * 2 + lay.result_words * 4 +
-                       (lay.obs_halfs * 2 if dense else 0))
-        S = args.sets or max(3, -(-200_000_000 // per_set) + 1)
-        G = 8
+                       (lay.obs_halfs * 2 if dense else (lay.cobs_halfs * 2 if compact else 0)))
+        big = per_set > 1_000_000_000  # one shard alone is many times the 126 MB L2 (config 5: 5.9 GB)
+        S = args.sets or (2 if big else max(3, -(-200_000_000 // per_set) + 1))
+        G = 2 if big else 8
         envs = [env] + [make_env(k) for k in range(1, S)]
         gen = torch.Generator(device=dev).manual_seed(1 + rank)
         recs = [torch.zeros((lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=dev)
@@ -885,9 +890,12 @@ def main():
     ab = algorithmic_bytes(dom, mode)
     peak, peak_src = measured_peak()
     step_launch_s = stepk_ms * 1e-3 / K
-    kname = {"lane": "step_kernel", "coop": "coop_step_kernel", "fused": "fused_step_kernel"}[info["step_impl"]]
-    # the fused launch also writes the dense observation record: SURVEY 8(d) bytes = 2S + a + r + o
-    alg_bytes = ab["step"] + (ab["obs"] if fused else 0)
+    kname = {"lane": "step_kernel", "coop": "coop_step_kernel", "fused": "fused_step_kernel",
+             "warp": "warp_step_kernel"}[info["step_impl"]]
+    # the fused launch also writes the dense observation record: SURVEY 8(d) bytes = 2S + a + r + o; the warp
+    # kernel's launch the compact one: 2S + a + r + o_c
+    one_launch_compact = compact and info["step_impl"] == "warp"
+    alg_bytes = ab["step"] + (ab["obs"] if fused else (ab["obs_compact"] if one_launch_compact else 0))
     achieved = alg_bytes * B / step_launch_s / 1e9
     cpu = cpu_port = None
     if not args.no_cpu_baseline and world == 1:
@@ -912,7 +920,7 @@ def main():
         "config": dict(workload_config(args, cfg, B), l2=l2_note),
         "kernel_config": {"auctioneer": "in-kernel, random arg-max (Philox)", "spawn": "device Philox",
                           "state_warm_steps": args.state_warm, "step_impl": info["step_impl"],
-                          "observations_fused_into_step_launch": bool(fused),
+                          "observations_fused_into_step_launch": bool(fused or (compact and info["step_impl"] == "warp")),
                           "envs_per_cta": info["envs_per_cta"], "smem_bytes_per_cta": info["smem_bytes_per_cta"]},
         "clocks": clocks,
         "e2e": e2e,
@@ -920,7 +928,8 @@ def main():
         "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": traffic_from_profile(args.config, kname),
                      "peak_source": peak_src, "algorithmic_bytes_per_env_step": alg_bytes,
-                     "algorithmic_bytes_formula": "2S+a+r" + ("+o (dense observations)" if fused else ""),
+                     "algorithmic_bytes_formula": "2S+a+r" + ("+o (dense observations)" if fused else
+                                                              ("+o_c (compact observations)" if one_launch_compact else "")),
                      "units_per_launch": B, "launch_us": step_launch_s * 1e6},
         "kernels": {"step_us": 1e3 * stepk_ms / K, "observe_us": obs_us,
                     "observe_algorithmic_bytes_per_env": ab["obs"] + ab["state"]},

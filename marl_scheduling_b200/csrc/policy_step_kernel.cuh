@@ -1,0 +1,370 @@
+// policy_step_kernel.cuh -- every PPO unit of one rollout step in ONE launch.
+//
+//   src/PPOmodules.py:32-39,53-63    ActorCritic.actor + act(): Linear-Tanh-Linear-Tanh-Linear-Softmax,
+//                                    Categorical.sample, Categorical.log_prob
+//   src/PPOmodules.py:114-125        PPO.selectAction: state / action / log-prob go to the experience buffer
+//   src/PPOmodules.py:312-332        FreePriceOfferPPO.selectAction: core chooser, then the price chooser on
+//                                    [core prio, core rem, slot prio, slot rem] of the chosen core (quirk Q1)
+//   src/Agent.py:504-515, 589-601    the agents' getActions: every acceptor unit and every offer unit of a step
+//
+// The per-group kernels (policy_kernels.cuh, actor_tc_kernel.cuh) cost one launch per net group and an extra
+// pass over the observations per group; at 65,536 environments the three launches of the free-price agents
+// were 80 % of a rollout step.  Here one persistent grid covers all groups: a CTA serves ONE unit (= one net,
+// staged once in shared memory, transposed, the Tanh scale 2*log2(e) and the Softmax scale log2(e) folded into
+// the weights) and walks over 256-environment tiles.  What makes it cheaper per row than the per-group kernel:
+//   * TWO rows (adjacent environments) per thread: every 128-bit weight load feeds 8 FFMAs instead of 4;
+//   * the observation row is read as aligned 32-bit words straight into registers (16 independent loads in
+//     flight per thread), int16 -> float on the integer / FMA pipes (bias trick, no I2F on the XU pipe that
+//     the Tanh / Softmax exponentials keep busy);
+//   * tanh = 1 - 2/(2^z' + 1) with z' already scaled: EX2, FADD, RCP, FFMA;
+//   * one Philox call per environment PAIR and unit serves both rows and both choosers of an offer unit;
+//   * an offer unit's price chooser runs in the thread that sampled the core: its 4 inputs are picked from
+//     the row words already in registers;
+//   * actions go straight into the environment's action record, action / log-prob (and, if asked, the input
+//     rows) into the experience buffer slot of the step.
+// fp32 SIMT: these nets are 16 wide -- a tcgen05 tile would be 87 % padding and its three accumulator round
+// trips per layer cost more issue slots than the 608 FFMAs per row they replace (measured); the
+// wider aggregated heads stay on the tensor-core kernels.
+#pragma once
+#include "msched_common.cuh"
+#include "policy_common.cuh"
+
+namespace msched {
+
+constexpr uint32_t kStreamPolicyStep = 4;
+
+struct PolicyGroupArgs {
+    const float *weights;  // n_nets * param_count, torch layout
+    int nIn, nActions, nNets, unitDiv, units;
+    int xOffset, xStride;  // int16 offsets inside the observation record: row of unit u at xOffset + u * xStride
+    int recOffset;         // int16 offset inside the action record: action of unit u at recOffset + u
+    unsigned long long seed;
+    int32_t *action;       // [nEnvs][units] or null
+    float *logprob;        // [nEnvs][units] or null
+    int16_t *xUsed;        // [nEnvs][units][xUsedStride] or null
+    int xUsedStride;
+    const float *uOverride;  // [nEnvs][units] or null
+    float *probs;            // [nEnvs][units][nActions] or null (tests)
+};
+
+struct PolicyStepArgs {
+    const int16_t *obs;
+    long long obsStride;  // int16 per env
+    int nEnvs, nCores;
+    int16_t *actionRec;
+    long long actionRecStride;
+    long long envOffset;
+    unsigned long long step;
+    const unsigned long long *stepDev;
+    PolicyGroupArgs acc, core, price;  // price.weights == null: fixed prices, the offer unit is the core chooser alone
+    int ctasPerAccUnit, ctasPerOffUnit;
+};
+
+// shared-memory image of one 16-wide net: W1t [KIN][16] | b1 [16] | W2t [16][16] | b2 [16] | W3t [16][AP] | b3 [AP]
+template <int KIN, int AP>
+struct NetImage {
+    static constexpr int kW1 = 0, kB1 = KIN * 16, kW2 = kB1 + 16, kB2 = kW2 + 256, kW3 = kB2 + 16, kB3 = kW3 + 16 * AP;
+    static constexpr int kFloats = kB3 + AP;
+    // all threads of the CTA; `w` = the net's parameters in torch layout [W1 16*nIn | b1 | W2 | b2 | W3 A*16 | b3]
+    __device__ static void stage(float *s, const float *__restrict__ w, int A)
+    {
+        constexpr float s2 = 2.f * kLog2e;
+        const float *w2 = w + 16 * KIN + 16, *w3 = w2 + 256 + 16;
+        for (int i = threadIdx.x; i < KIN * 16; i += blockDim.x) { const int o = i / KIN, k = i - o * KIN; s[kW1 + k * 16 + o] = w[i] * s2; }
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) { const int o = i >> 4, k = i & 15; s[kW2 + k * 16 + o] = w2[i] * s2; }
+        for (int i = threadIdx.x; i < 16; i += blockDim.x) { s[kB1 + i] = w[16 * KIN + i] * s2; s[kB2 + i] = w2[256 + i] * s2; }
+        for (int i = threadIdx.x; i < 16 * AP; i += blockDim.x) {
+            const int k = i / AP, o = i - k * AP;
+            s[kW3 + i] = o < A ? w3[o * 16 + k] * kLog2e : 0.f;
+        }
+        for (int i = threadIdx.x; i < AP; i += blockDim.x) s[kB3 + i] = i < A ? w3[A * 16 + i] * kLog2e : -INFINITY;
+    }
+};
+
+// the two int16 halves of an observation word as floats, on the integer / FMA pipes: flip the sign bits
+// (h + 32768 as unsigned), plant each half in the mantissa of 2^23 * 1.5, subtract 2^23 * 1.5 + 32768
+__device__ __forceinline__ void halves_to_float(uint32_t w, float &lo, float &hi)
+{
+    const uint32_t b = w ^ 0x80008000u;
+    lo = __uint_as_float(__byte_perm(b, 0x4b400000u, 0x7610)) - 12615680.f;
+    hi = __uint_as_float(__byte_perm(b, 0x4b400000u, 0x7632)) - 12615680.f;
+}
+
+__device__ __forceinline__ float tanh_scaled(float z2)  // tanh(z) given z2 = 2 * log2(e) * z
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ex2_approx(z2) + 1.f));
+    return fmaf(-2.f, r, 1.f);
+}
+
+// acc[r][o] += W[k][o] * x[r] for the two rows, one 16-float weight row = four 128-bit broadcast loads
+__device__ __forceinline__ void fma_row16(const float *__restrict__ wrow, float x0, float x1, float (&a0)[16], float (&a1)[16])
+{
+#pragma unroll
+    for (int o4 = 0; o4 < 4; ++o4) {
+        const float4 wv = *reinterpret_cast<const float4 *>(wrow + 4 * o4);
+        a0[4 * o4 + 0] = fmaf(wv.x, x0, a0[4 * o4 + 0]); a1[4 * o4 + 0] = fmaf(wv.x, x1, a1[4 * o4 + 0]);
+        a0[4 * o4 + 1] = fmaf(wv.y, x0, a0[4 * o4 + 1]); a1[4 * o4 + 1] = fmaf(wv.y, x1, a1[4 * o4 + 1]);
+        a0[4 * o4 + 2] = fmaf(wv.z, x0, a0[4 * o4 + 2]); a1[4 * o4 + 2] = fmaf(wv.z, x1, a1[4 * o4 + 2]);
+        a0[4 * o4 + 3] = fmaf(wv.w, x0, a0[4 * o4 + 3]); a1[4 * o4 + 3] = fmaf(wv.w, x1, a1[4 * o4 + 3]);
+    }
+}
+
+// layers 2 and 3 for the two rows: h (after the first Tanh) -> base-2 logits
+template <int KIN, int AP>
+__device__ __forceinline__ void mlp_tail(const float *__restrict__ s, float (&h0)[16], float (&h1)[16], float (&lg0)[AP], float (&lg1)[AP])
+{
+    using NI = NetImage<KIN, AP>;
+    float g0[16], g1[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) { h0[o] = tanh_scaled(h0[o]); h1[o] = tanh_scaled(h1[o]); g0[o] = s[NI::kB2 + o]; g1[o] = g0[o]; }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) fma_row16(s + NI::kW2 + k * 16, h0[k], h1[k], g0, g1);
+#pragma unroll
+    for (int o = 0; o < 16; ++o) { g0[o] = tanh_scaled(g0[o]); g1[o] = tanh_scaled(g1[o]); }
+#pragma unroll
+    for (int o4 = 0; o4 < AP / 4; ++o4) {
+        const float4 b4 = *reinterpret_cast<const float4 *>(s + NI::kB3 + 4 * o4);
+        float4 c0 = b4, c1 = b4;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float4 wv = *reinterpret_cast<const float4 *>(s + NI::kW3 + k * AP + 4 * o4);
+            c0.x = fmaf(wv.x, g0[k], c0.x); c0.y = fmaf(wv.y, g0[k], c0.y); c0.z = fmaf(wv.z, g0[k], c0.z); c0.w = fmaf(wv.w, g0[k], c0.w);
+            c1.x = fmaf(wv.x, g1[k], c1.x); c1.y = fmaf(wv.y, g1[k], c1.y); c1.z = fmaf(wv.z, g1[k], c1.z); c1.w = fmaf(wv.w, g1[k], c1.w);
+        }
+        lg0[4 * o4] = c0.x; lg0[4 * o4 + 1] = c0.y; lg0[4 * o4 + 2] = c0.z; lg0[4 * o4 + 3] = c0.w;
+        lg1[4 * o4] = c1.x; lg1[4 * o4 + 1] = c1.y; lg1[4 * o4 + 2] = c1.z; lg1[4 * o4 + 3] = c1.w;
+    }
+}
+
+// layer 1 from the row words: inputs are the halves LEAD .. LEAD+KIN-1 of the KW words of each row
+template <int KW, int LEAD, int KIN, int AP>
+__device__ __forceinline__ void mlp_pair(const float *__restrict__ s, const uint32_t (&x0)[KW], const uint32_t (&x1)[KW],
+                                         float (&lg0)[AP], float (&lg1)[AP])
+{
+    using NI = NetImage<KIN, AP>;
+    float h0[16], h1[16];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) { h0[o] = s[NI::kB1 + o]; h1[o] = h0[o]; }
+#pragma unroll
+    for (int w = 0; w < KW; ++w) {
+        float a0, b0, a1, b1;
+        halves_to_float(x0[w], a0, b0);
+        halves_to_float(x1[w], a1, b1);
+        const int k = 2 * w - LEAD;  // input index of the word's low half
+        if (k >= 0 && k < KIN) fma_row16(s + NI::kW1 + k * 16, a0, a1, h0, h1);
+        if (k + 1 >= 0 && k + 1 < KIN) fma_row16(s + NI::kW1 + (k + 1) * 16, b0, b1, h0, h1);
+    }
+    mlp_tail<KIN, AP>(s, h0, h1, lg0, lg1);
+}
+
+// Softmax -> Categorical(probs): inverse-CDF sample with draw u, Categorical.log_prob semantics (renormalised,
+// clamped to [eps, 1-eps]); lg are base-2 logits, -inf beyond the net's A actions
+template <int AP>
+__device__ __forceinline__ int sample_row(float (&lg)[AP], int A, float u, float &logp, float *probsOut)
+{
+    float mx = lg[0];
+#pragma unroll
+    for (int o = 1; o < AP; ++o) mx = fmaxf(mx, lg[o]);
+    float sum = 0.f;
+#pragma unroll
+    for (int o = 0; o < AP; ++o) { lg[o] = ex2_approx(lg[o] - mx); sum += lg[o]; }
+    const float inv = 1.f / sum;
+    float tot = 0.f;
+#pragma unroll
+    for (int o = 0; o < AP; ++o) { lg[o] *= inv; tot += lg[o]; }
+    if (probsOut) {
+#pragma unroll
+        for (int o = 0; o < AP; ++o)
+            if (o < A) probsOut[o] = lg[o];
+    }
+    const float thr = u * tot;
+    float cdf = 0.f, pa = 0.f;
+    int act = -1;
+#pragma unroll
+    for (int o = 0; o < AP; ++o) {
+        cdf += lg[o];
+        const bool hit = act < 0 && cdf > thr;
+        act = hit ? o : act;
+        pa = hit ? lg[o] : pa;
+    }
+    if (act < 0) {
+        act = A - 1;
+#pragma unroll
+        for (int o = 0; o < AP; ++o) pa = (o == A - 1) ? lg[o] : pa;
+    }
+    const float eps = 1.1920928955078125e-07f;
+    float pn = pa / tot;
+    pn = fminf(fmaxf(pn, eps), 1.f - eps);
+    logp = logf(pn);
+    return act;
+}
+
+__device__ __forceinline__ float u24(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// draws of an environment pair for one unit: words 0,1 = the two rows of the acceptor / core chooser, words 2,3 =
+// the two rows of the price chooser.  Counter (pair lo, pair hi, step lo, 4 << 28 | step hi : 12 | unit : 16), key = seed
+__device__ __forceinline__ void pair_draws(const PolicyStepArgs &a, unsigned long long seed, int envLocal, int unit, uint32_t (&x)[4])
+{
+    const unsigned long long pair = (unsigned long long)(a.envOffset + envLocal) >> 1;
+    const unsigned long long stp = a.stepDev ? *a.stepDev : a.step;
+    philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)stp,
+                  (kStreamPolicyStep << 28) | ((uint32_t)((stp >> 32) & 0xfffu) << 16) | (uint32_t)(unit & 0xffff),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), x);
+}
+
+template <int KW>
+__device__ __forceinline__ void load_row(const int16_t *obs, long long obsStride, int env, bool live, int off, uint32_t (&x)[KW])
+{
+    const uint32_t *r = reinterpret_cast<const uint32_t *>(obs + (size_t)(live ? env : 0) * obsStride + off);
+#pragma unroll
+    for (int w = 0; w < KW; ++w) x[w] = r[w];
+}
+
+template <int KW>
+__device__ __forceinline__ void store_row(int16_t *dst, const uint32_t (&x)[KW])
+{
+    uint32_t *d = reinterpret_cast<uint32_t *>(dst);
+#pragma unroll
+    for (int w = 0; w < KW; ++w) d[w] = x[w];
+}
+
+// outputs of one row
+__device__ __forceinline__ void emit_row(const PolicyStepArgs &a, const PolicyGroupArgs &g, int env, int unit, int act, float logp,
+                                         int reported)
+{
+    const size_t row = (size_t)env * g.units + unit;
+    if (g.action) g.action[row] = act;
+    if (g.logprob) g.logprob[row] = logp;
+    if (a.actionRec) a.actionRec[(size_t)env * a.actionRecStride + g.recOffset + unit] = (int16_t)reported;
+}
+
+// KW_A/LEAD_A/KIN_A/AP_A: acceptor rows; KW_O/KIN_O/AP_O: offer rows (core chooser); AP_P: price chooser (0 = none)
+template <int KW_A, int LEAD_A, int KIN_A, int AP_A, int KW_O, int KIN_O, int AP_O, int AP_P>
+__global__ void __launch_bounds__(128, 4) policy_step_kernel(const __grid_constant__ PolicyStepArgs a)
+{
+    extern __shared__ __align__(16) float sw[];
+    const int nAccCtas = a.acc.units * a.ctasPerAccUnit;
+    const bool isAcc = (int)blockIdx.x < nAccCtas;
+    const int nTiles = (a.nEnvs + 255) / 256;
+    if (isAcc) {
+        const int unit = blockIdx.x / a.ctasPerAccUnit, slice = blockIdx.x - unit * a.ctasPerAccUnit;
+        const PolicyGroupArgs &g = a.acc;
+        const int net = (unit / g.unitDiv) % g.nNets;
+        const int pc = 16 * KIN_A + 16 + 256 + 16 + 16 * g.nActions + g.nActions;
+        NetImage<KIN_A, AP_A>::stage(sw, g.weights + (size_t)net * pc, g.nActions);
+        __syncthreads();
+        const int off = g.xOffset + unit * g.xStride - LEAD_A;
+        for (int tile = slice; tile < nTiles; tile += a.ctasPerAccUnit) {
+            const int e0 = tile * 256 + 2 * threadIdx.x, e1 = e0 + 1;
+            const bool l0 = e0 < a.nEnvs, l1 = e1 < a.nEnvs;
+            uint32_t x0[KW_A], x1[KW_A];
+            load_row<KW_A>(a.obs, a.obsStride, e0, l0, off, x0);
+            load_row<KW_A>(a.obs, a.obsStride, e1, l1, off, x1);
+            float u0, u1;
+            if (g.uOverride) {
+                u0 = l0 ? g.uOverride[(size_t)e0 * g.units + unit] : 0.f;
+                u1 = l1 ? g.uOverride[(size_t)e1 * g.units + unit] : 0.f;
+            } else {
+                uint32_t r[4];
+                pair_draws(a, g.seed, e0, unit, r);
+                u0 = u24(r[0]); u1 = u24(r[1]);
+            }
+            float lg0[AP_A], lg1[AP_A];
+            mlp_pair<KW_A, LEAD_A, KIN_A, AP_A>(sw, x0, x1, lg0, lg1);
+            float lp0, lp1;
+            const int a0 = sample_row<AP_A>(lg0, g.nActions, u0, lp0, (g.probs && l0) ? g.probs + ((size_t)e0 * g.units + unit) * g.nActions : nullptr);
+            const int a1 = sample_row<AP_A>(lg1, g.nActions, u1, lp1, (g.probs && l1) ? g.probs + ((size_t)e1 * g.units + unit) * g.nActions : nullptr);
+            if (l0) {
+                emit_row(a, g, e0, unit, a0, lp0, a0);
+                if (g.xUsed) store_row<KW_A>(g.xUsed + ((size_t)e0 * g.units + unit) * g.xUsedStride, x0);
+            }
+            if (l1) {
+                emit_row(a, g, e1, unit, a1, lp1, a1);
+                if (g.xUsed) store_row<KW_A>(g.xUsed + ((size_t)e1 * g.units + unit) * g.xUsedStride, x1);
+            }
+        }
+    } else {
+        const int id = blockIdx.x - nAccCtas;
+        const int unit = id / a.ctasPerOffUnit, slice = id - unit * a.ctasPerOffUnit;
+        const PolicyGroupArgs &g = a.core, &gp = a.price;
+        constexpr int APP = AP_P > 0 ? AP_P : 4;
+        float *swp = sw + ((NetImage<KIN_O, AP_O>::kFloats + 3) & ~3);
+        {
+            const int net = (unit / g.unitDiv) % g.nNets;
+            const int pc = 16 * KIN_O + 16 + 256 + 16 + 16 * g.nActions + g.nActions;
+            NetImage<KIN_O, AP_O>::stage(sw, g.weights + (size_t)net * pc, g.nActions);
+            if (AP_P > 0) {
+                const int netp = (unit / gp.unitDiv) % gp.nNets;
+                const int pcp = 16 * 4 + 16 + 256 + 16 + 16 * gp.nActions + gp.nActions;
+                NetImage<4, APP>::stage(swp, gp.weights + (size_t)netp * pcp, gp.nActions);
+            }
+        }
+        __syncthreads();
+        const int off = g.xOffset + unit * g.xStride;
+        for (int tile = slice; tile < nTiles; tile += a.ctasPerOffUnit) {
+            const int e0 = tile * 256 + 2 * threadIdx.x, e1 = e0 + 1;
+            const bool l0 = e0 < a.nEnvs, l1 = e1 < a.nEnvs;
+            uint32_t x0[KW_O], x1[KW_O];
+            load_row<KW_O>(a.obs, a.obsStride, e0, l0, off, x0);
+            load_row<KW_O>(a.obs, a.obsStride, e1, l1, off, x1);
+            float u0, u1, v0 = 0.f, v1 = 0.f;
+            if (g.uOverride) {
+                u0 = l0 ? g.uOverride[(size_t)e0 * g.units + unit] : 0.f;
+                u1 = l1 ? g.uOverride[(size_t)e1 * g.units + unit] : 0.f;
+                if (AP_P > 0 && gp.uOverride) {
+                    v0 = l0 ? gp.uOverride[(size_t)e0 * gp.units + unit] : 0.f;
+                    v1 = l1 ? gp.uOverride[(size_t)e1 * gp.units + unit] : 0.f;
+                }
+            } else {
+                uint32_t r[4];
+                pair_draws(a, g.seed, e0, unit, r);
+                u0 = u24(r[0]); u1 = u24(r[1]); v0 = u24(r[2]); v1 = u24(r[3]);
+            }
+            float lg0[AP_O], lg1[AP_O];
+            mlp_pair<KW_O, 0, KIN_O, AP_O>(sw, x0, x1, lg0, lg1);
+            float lp0, lp1;
+            const int c0 = sample_row<AP_O>(lg0, g.nActions, u0, lp0, (g.probs && l0) ? g.probs + ((size_t)e0 * g.units + unit) * g.nActions : nullptr);
+            const int c1 = sample_row<AP_O>(lg1, g.nActions, u1, lp1, (g.probs && l1) ? g.probs + ((size_t)e1 * g.units + unit) * g.nActions : nullptr);
+            if (l0) {
+                emit_row(a, g, e0, unit, c0, lp0, c0);
+                if (g.xUsed) store_row<KW_O>(g.xUsed + ((size_t)e0 * g.units + unit) * g.xUsedStride, x0);
+            }
+            if (l1) {
+                emit_row(a, g, e1, unit, c1, lp1, c1);
+                if (g.xUsed) store_row<KW_O>(g.xUsed + ((size_t)e1 * g.units + unit) * g.xUsedStride, x1);
+            }
+            if (AP_P > 0) {
+                // FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): the price net sees [core prio, core rem,
+                // slot prio, slot rem] of the chosen core = row words c and nCores; core action 0 feeds the dummy
+                // [-5,-5,-5,-5] and reports price -5 (quirk Q1)
+                uint32_t p0[2], p1[2];
+                const uint32_t dummy = 0xfffbfffbu;
+                uint32_t s0 = x0[0], s1 = x1[0];
+#pragma unroll
+                for (int w = 1; w < KW_O; ++w) { s0 = (w == c0) ? x0[w] : s0; s1 = (w == c1) ? x1[w] : s1; }
+                uint32_t t0 = x0[0], t1 = x1[0];
+#pragma unroll
+                for (int w = 1; w < KW_O; ++w) { t0 = (w == a.nCores) ? x0[w] : t0; t1 = (w == a.nCores) ? x1[w] : t1; }
+                const bool d0 = c0 <= 0 || c0 > a.nCores, d1 = c1 <= 0 || c1 > a.nCores;
+                p0[0] = d0 ? dummy : s0; p0[1] = d0 ? dummy : t0;
+                p1[0] = d1 ? dummy : s1; p1[1] = d1 ? dummy : t1;
+                float q0[APP], q1[APP];
+                mlp_pair<2, 0, 4, APP>(swp, p0, p1, q0, q1);
+                float lq0, lq1;
+                const int b0 = sample_row<APP>(q0, gp.nActions, v0, lq0, (gp.probs && l0) ? gp.probs + ((size_t)e0 * gp.units + unit) * gp.nActions : nullptr);
+                const int b1 = sample_row<APP>(q1, gp.nActions, v1, lq1, (gp.probs && l1) ? gp.probs + ((size_t)e1 * gp.units + unit) * gp.nActions : nullptr);
+                if (l0) {
+                    emit_row(a, gp, e0, unit, b0, lq0, c0 == 0 ? -5 : b0);
+                    if (gp.xUsed) store_row<2>(gp.xUsed + ((size_t)e0 * gp.units + unit) * gp.xUsedStride, p0);
+                }
+                if (l1) {
+                    emit_row(a, gp, e1, unit, b1, lq1, c1 == 0 ? -5 : b1);
+                    if (gp.xUsed) store_row<2>(gp.xUsed + ((size_t)e1 * gp.units + unit) * gp.xUsedStride, p1);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace msched
