@@ -312,6 +312,46 @@ typedef struct MschedActorIO {
 
 int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, void *stream);
 
+/* ---- every PPO unit of a rollout step in ONE launch ----
+ * The agents' getActions of one step (src/Agent.py:504-515 divided / shared fixed-price agents, :589-601 free-price
+ * agents): PPO.selectAction (src/PPOmodules.py:114-125) of every acceptor unit and every offer unit -- for free
+ * prices FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332), core chooser then price chooser -- straight on
+ * the dense observation record.  16-wide nets (the divided, locally and globally shared agents).  Per group: the
+ * nets, where unit u's row sits in the observation record (x_offset + u * x_stride, int16 elements, the row's first
+ * logical value), where its action goes in the action record (rec_offset + u), and the experience-buffer slot of
+ * this step (any of action / logprob / x_used may be NULL; x_used rows are x_used_stride int16 apart and hold the
+ * observation row word-aligned: one leading pad value when x_offset is odd).  price.nets.weights == NULL: fixed
+ * prices (the offer unit is OfferPPO alone).  Sampling draws: Philox4x32-10, key = the group's seed (the core
+ * chooser's for both choosers), counter = (global env >> 1 lo, hi, step lo, 4 << 28 | step hi : 12 | unit : 16);
+ * words 0,1 serve the even / odd environment's acceptor or core-chooser row, words 2,3 their price-chooser rows;
+ * u = (x >> 8) * 2^-24.  env_offset (global index of env 0) must be even.  u_override float32 [n_envs][units]
+ * replaces the draws (parity tests).  Unsupported net shapes return MSCHED_E_ARG: use msched_actor_forward. */
+typedef struct MschedPolicyGroup {
+    MschedMlpGroup nets;
+    int32_t units, x_offset, x_stride, rec_offset;
+    uint64_t seed;
+    int32_t *action;        /* int32 [n_envs][units] */
+    float *logprob;         /* float32 [n_envs][units] */
+    int16_t *x_used;        /* int16 [n_envs][units][x_used_stride] */
+    int32_t x_used_stride, reserved;
+    const float *u_override;
+    float *probs;           /* float32 [n_envs][units][n_actions], tests only */
+} MschedPolicyGroup;
+
+typedef struct MschedPolicyStep {
+    const int16_t *obs;     /* dense observation record */
+    int64_t obs_stride;     /* int16 per env */
+    int32_t n_envs, n_cores;
+    int16_t *action_rec;    /* the env's action record (or NULL) */
+    int64_t action_rec_stride;
+    int64_t env_offset;
+    uint64_t step;
+    const uint64_t *step_dev; /* optional device step counter (CUDA-graph replays) */
+    MschedPolicyGroup acceptor, core, price;
+} MschedPolicyStep;
+
+int msched_policy_step(const MschedPolicyStep *ps, void *stream);
+
 /* FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332) for every offer unit in ONE launch: the
  * core chooser samples a core from the unit's offer observation row (core_io->x, n_cores set), then the
  * same thread feeds [core prio, core rem, slot prio, slot rem] of that core to the price chooser

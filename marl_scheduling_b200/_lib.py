@@ -71,6 +71,20 @@ class MschedActorIO(C.Structure):
                 ("gather_core", C.c_void_p), ("x_used", C.c_void_p), ("timeline", C.c_void_p), ("step_dev", C.c_void_p)]
 
 
+class MschedPolicyGroup(C.Structure):
+    _fields_ = [("nets", MschedMlpGroup), ("units", C.c_int32), ("x_offset", C.c_int32), ("x_stride", C.c_int32),
+                ("rec_offset", C.c_int32), ("seed", C.c_uint64), ("action", C.c_void_p), ("logprob", C.c_void_p),
+                ("x_used", C.c_void_p), ("x_used_stride", C.c_int32), ("reserved", C.c_int32),
+                ("u_override", C.c_void_p), ("probs", C.c_void_p)]
+
+
+class MschedPolicyStep(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("obs_stride", C.c_int64), ("n_envs", C.c_int32), ("n_cores", C.c_int32),
+                ("action_rec", C.c_void_p), ("action_rec_stride", C.c_int64), ("env_offset", C.c_int64),
+                ("step", C.c_uint64), ("step_dev", C.c_void_p),
+                ("acceptor", MschedPolicyGroup), ("core", MschedPolicyGroup), ("price", MschedPolicyGroup)]
+
+
 class MschedPpoBatch(C.Structure):
     _fields_ = [("actor_weights", C.c_void_p), ("critic_weights", C.c_void_p),
                 ("n_in", C.c_int32), ("n_hidden", C.c_int32), ("n_actions", C.c_int32), ("n_nets", C.c_int32),
@@ -114,6 +128,7 @@ SYMBOLS = {
     "msched_export_state": (C.c_int, [P, C.c_int, C.c_int, P, P, P, P, P, P, P]),
     "msched_mlp_param_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "msched_actor_forward": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),
+    "msched_policy_step": (C.c_int, [C.POINTER(MschedPolicyStep), P]),
     "msched_offer_unit_forward": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO),
                                             C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),
     "msched_dqn_param_count": (C.c_int, [C.c_int, C.c_int]),

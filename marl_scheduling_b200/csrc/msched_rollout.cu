@@ -1,0 +1,104 @@
+// msched_rollout.cu -- msched_policy_step (include/msched.h): every PPO unit of a rollout step in one launch.
+#include <cstring>
+
+#include "abi_common.h"
+#include "policy_step_kernel.cuh"
+
+using namespace msched;
+
+namespace {
+
+PolicyGroupArgs group_args(const MschedPolicyGroup &g)
+{
+    PolicyGroupArgs a;
+    memset(&a, 0, sizeof(a));
+    a.weights = g.nets.weights;
+    a.nIn = g.nets.n_in; a.nActions = g.nets.n_actions; a.nNets = g.nets.n_nets;
+    a.unitDiv = g.nets.unit_div > 0 ? g.nets.unit_div : 1;
+    a.units = g.units; a.xOffset = g.x_offset; a.xStride = g.x_stride; a.recOffset = g.rec_offset;
+    a.seed = g.seed; a.action = g.action; a.logprob = g.logprob; a.xUsed = g.x_used; a.xUsedStride = g.x_used_stride;
+    a.uOverride = g.u_override; a.probs = g.probs;
+    return a;
+}
+
+int g_sms = 0;
+
+// KW = words of an observation row incl. the leading pad value; LEAD = 1 if the row starts on an odd int16
+template <int KW_A, int LEAD_A, int KIN_A, int AP_A, int KW_O, int KIN_O, int AP_O, int AP_P>
+int launch(PolicyStepArgs &a, cudaStream_t s)
+{
+    auto fn = policy_step_kernel<KW_A, LEAD_A, KIN_A, AP_A, KW_O, KIN_O, AP_O, AP_P>;
+    constexpr int APP = AP_P > 0 ? AP_P : 4;
+    constexpr int fa = NetImage<KIN_A, AP_A>::kFloats;
+    constexpr int fo = ((NetImage<KIN_O, AP_O>::kFloats + 3) & ~3) + (AP_P > 0 ? NetImage<4, APP>::kFloats : 0);
+    const size_t smem = sizeof(float) * (size_t)(fa > fo ? fa : fo);
+    static int perSm = 0;
+    if (!perSm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 128, smem) != cudaSuccess || perSm < 1) perSm = 1;
+    }
+    // one resident wave, split between the acceptor units and the (heavier) offer units by their multiply-adds
+    const int nTiles = (a.nEnvs + 255) / 256;
+    const double ca = (double)a.acc.units * (16.0 * KIN_A + 256 + 16.0 * a.acc.nActions);
+    const double co = (double)a.core.units * ((16.0 * KIN_O + 256 + 16.0 * a.core.nActions) +
+                                               (AP_P > 0 ? (64.0 + 256 + 16.0 * a.price.nActions) : 0.0));
+    const int total = g_sms * perSm;
+    int na = (int)(total * ca / (ca + co) / a.acc.units), no = (int)(total * co / (ca + co) / a.core.units);
+    na = na < 1 ? 1 : (na > nTiles ? nTiles : na);
+    no = no < 1 ? 1 : (no > nTiles ? nTiles : no);
+    a.ctasPerAccUnit = na;
+    a.ctasPerOffUnit = no;
+    fn<<<a.acc.units * na + a.core.units * no, 128, smem, s>>>(a);
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int msched_policy_step(const MschedPolicyStep *ps, void *stream)
+{
+    if (!ps || !ps->obs) return fail(MSCHED_E_ARG, "null policy step / observations");
+    const MschedPolicyGroup &A = ps->acceptor, &O = ps->core, &P = ps->price;
+    if (!A.nets.weights || !O.nets.weights) return fail(MSCHED_E_ARG, "acceptor and core / offer nets are required");
+    const bool free = P.nets.weights != nullptr;
+    if (A.nets.n_hidden != 16 || O.nets.n_hidden != 16 || (free && P.nets.n_hidden != 16))
+        return fail(MSCHED_E_ARG, "msched_policy_step serves the 16-wide nets (use msched_actor_forward)");
+    if (ps->n_envs < 0 || A.units < 1 || O.units < 1 || A.nets.n_nets < 1 || O.nets.n_nets < 1 || (free && (P.units != O.units || P.nets.n_nets < 1)))
+        return fail(MSCHED_E_ARG, "bad n_envs/units/n_nets");
+    if ((ps->env_offset & 1) || (ps->obs_stride & 1)) return fail(MSCHED_E_ARG, "env_offset and obs_stride must be even");
+    const int lead = A.x_offset & 1;
+    if (((A.x_offset - lead) & 1) || (A.x_stride & 1) || (O.x_offset & 1) || (O.x_stride & 1))
+        return fail(MSCHED_E_ARG, "observation rows must be word aligned (msched_get_layout offsets)");
+    if (ps->n_cores < 1 || O.nets.n_in != 2 * ps->n_cores + 2 || O.nets.n_actions != ps->n_cores + 1)
+        return fail(MSCHED_E_ARG, "offer rows are [2*n_cores+2] with n_cores+1 actions");
+    if (free && P.nets.n_in != 4) return fail(MSCHED_E_ARG, "price chooser: n_in == 4");
+    if ((A.x_used && (A.x_used_stride & 1)) || (O.x_used && (O.x_used_stride & 1)) || (free && P.x_used && P.x_used_stride < 4))
+        return fail(MSCHED_E_ARG, "x_used_stride must be even (whole words)");
+    if (ps->n_envs == 0) return MSCHED_OK;
+    PolicyStepArgs a;
+    memset(&a, 0, sizeof(a));
+    a.obs = ps->obs; a.obsStride = ps->obs_stride; a.nEnvs = ps->n_envs; a.nCores = ps->n_cores;
+    a.actionRec = ps->action_rec; a.actionRecStride = ps->action_rec_stride; a.envOffset = ps->env_offset;
+    a.step = ps->step; a.stepDev = reinterpret_cast<const unsigned long long *>(ps->step_dev);
+    a.acc = group_args(A); a.core = group_args(O);
+    if (free) a.price = group_args(P);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int ka = A.nets.n_in, aa = A.nets.n_actions, ko = O.nets.n_in, ao = O.nets.n_actions, ap = free ? P.nets.n_actions : 0;
+    int rc = -1;
+    // BASELINE cfg3 (N2 C3 L3, free prices): acceptor 15 -> 7, core chooser 8 -> 4, price chooser 4 -> <= 16
+    if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && free && ap <= 16 && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
+        rc = launch<8, 1, 15, 8, 4, 8, 8, 16>(a, s);
+    // BASELINE cfg2 / cfg4 (N4 C4 L3, fixed prices): acceptor 27 -> 13, offer 10 -> 5
+    else if (lead == 1 && ka == 27 && aa <= 16 && ko == 10 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 28) && (!O.x_used || O.x_used_stride >= 10))
+        rc = launch<14, 1, 27, 16, 5, 10, 8, 0>(a, s);
+    // cfg3 domain with fixed prices
+    else if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
+        rc = launch<8, 1, 15, 8, 4, 8, 8, 0>(a, s);
+    // BASELINE cfg1 domain (N2 C3 L2): acceptor 11 -> 5, offer 8 -> 4
+    else if (lead == 1 && ka == 11 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 12) && (!O.x_used || O.x_used_stride >= 8))
+        rc = launch<6, 1, 11, 8, 4, 8, 8, 0>(a, s);
+    if (rc) return fail(MSCHED_E_ARG, "msched_policy_step: no kernel for these net shapes (use msched_actor_forward per group)");
+    CUDA_TRY(cudaGetLastError());
+    return MSCHED_OK;
+}

@@ -199,3 +199,48 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, beta1=0.9, beta2=0.999
         assert t.is_contiguous() and t.dtype == torch.float32 and t.numel() == param.numel()
     L.check(L.lib().msched_adam_step(param.data_ptr(), grad.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
                                      param.numel(), float(lr), beta1, beta2, eps, int(step), _stream(param.device)))
+
+
+def policy_step_group(group, units, x_offset, x_stride, rec_offset, seed, action=None, logprob=None, x_used=None,
+                      u=None, probs=None):
+    """One MschedPolicyGroup of msched_policy_step: `group` (MlpGroup) serves `units` rows per environment whose
+    observation rows start at x_offset + u * x_stride (int16 elements inside the observation record) and whose
+    actions go to rec_offset + u of the action record.  action int32 / logprob float32 [B, units]; x_used int16
+    [B, units, stride] (the row as read: word aligned, one leading pad when x_offset is odd); u float32 [B, units]
+    draw overrides; probs float32 [B, units, A]."""
+    g = L.MschedPolicyGroup()
+    g.nets = group.desc
+    g.units, g.x_offset, g.x_stride, g.rec_offset, g.seed = units, x_offset, x_stride, rec_offset, seed
+    g.action = None if action is None else action.data_ptr()
+    g.logprob = None if logprob is None else logprob.data_ptr()
+    if x_used is not None:
+        assert x_used.dtype == torch.int16 and x_used.stride(-1) == 1
+        g.x_used, g.x_used_stride = x_used.data_ptr(), x_used.stride(-2)
+    g.u_override = None if u is None else u.data_ptr()
+    g.probs = None if probs is None else probs.data_ptr()
+    g._keep = (group, action, logprob, x_used, u, probs)
+    return g
+
+
+def policy_step_supported(acceptor, core, price=None):
+    """Net shapes msched_policy_step has kernels for (the BASELINE domains' 16-wide nets)."""
+    if acceptor.n_hidden != 16 or core.n_hidden != 16 or (price is not None and price.n_hidden != 16):
+        return False
+    shapes = {(15, 8, True), (27, 10, False), (15, 8, False), (11, 8, False)}
+    return ((acceptor.n_in, core.n_in, price is not None) in shapes and acceptor.n_actions <= (16 if acceptor.n_in == 27 else 8)
+            and core.n_actions <= 8 and (price is None or (price.n_in == 4 and price.n_actions <= 16)))
+
+
+def policy_step(obs, obs_stride, n_envs, n_cores, acceptor, core, price=None, action_rec=None, action_rec_stride=0,
+                env_offset=0, step=0, step_dev=None):
+    """Every PPO unit of a rollout step in ONE launch (msched_policy_step): acceptor / core / price are
+    MschedPolicyGroup objects from policy_step_group (price None = fixed prices)."""
+    ps = L.MschedPolicyStep()
+    ps.obs, ps.obs_stride, ps.n_envs, ps.n_cores = obs.data_ptr(), obs_stride, n_envs, n_cores
+    ps.action_rec = None if action_rec is None else action_rec.data_ptr()
+    ps.action_rec_stride, ps.env_offset, ps.step = action_rec_stride, env_offset, step
+    ps.step_dev = None if step_dev is None else step_dev.data_ptr()
+    ps.acceptor, ps.core = acceptor, core
+    if price is not None:
+        ps.price = price
+    L.check(L.lib().msched_policy_step(C.byref(ps), _stream(obs.device)))
