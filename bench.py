@@ -729,70 +729,80 @@ def main():
         p_act, p_lp = torch.empty_like(o_act), torch.empty_like(o_lp)
         res_r = torch.zeros_like(env.result)
 
-        # the acceptor units and the offer units are independent: they run on two side streams and
-        # join before the env step (the price chooser follows the core chooser on its stream).  The
-        # whole step is captured ONCE in a CUDA graph and replayed: world.round and the policy's
-        # Philox step live in device counters (msched_set_round_mode, MschedActorIO.step_dev)
-        side = [torch.cuda.Stream(device=dev) for _ in range(2)]
+        # ONE launch for every PPO unit of the step (msched_policy_step: acceptor units, core chooser and price
+        # chooser of every offer unit; actions straight into the action record; state / action / log-prob into the
+        # experience-buffer slot of the step), then the fused env step + observations.  EIGHT consecutive steps --
+        # eight different buffer slots, 250 MB of experience written -- are captured in one CUDA graph and replayed:
+        # world.round and the policy's Philox step live in device counters.
+        SLOTS = 8
         step_t = torch.zeros(1, dtype=torch.int64, device=dev)
         env.set_device_round(True)
+        one_launch = policy.policy_step_supported(acc_net, off_net, price_net)
+        ring = dict(xa=torch.zeros((SLOTS, B, N * Cc, lay.o_acc_row), dtype=torch.int16, device=dev),
+                    xo=torch.zeros((SLOTS, B, NL, lay.o_off_row), dtype=torch.int16, device=dev),
+                    xp=torch.zeros((SLOTS, B, NL, 4), dtype=torch.int16, device=dev),
+                    a=torch.zeros((SLOTS, 3, B, max(N * Cc, NL)), dtype=torch.int32, device=dev),
+                    lp=torch.zeros((SLOTS, 3, B, max(N * Cc, NL)), dtype=torch.float32, device=dev))
 
-        def rollout_step():
-            cur = torch.cuda.current_stream(dev)
-            fork = torch.cuda.Event()
-            fork.record(cur)
-            with torch.cuda.stream(side[0]):
-                side[0].wait_event(fork)
-                if free and policy.offer_unit_fusable(off_net, price_net):
-                    # core chooser + price chooser of every offer unit in ONE launch
-                    policy.offer_unit_forward(off_net, price_net, ov["offer"], lay.o_off_row, NL, B, Cc,
-                                              env_stride=lay.obs_halfs, seeds=(2, 3), step_dev=step_t,
-                                              core_out=(o_act, o_lp), price_out=(p_act, p_lp),
-                                              core_rec=env.offer_core_actions, price_rec=env.offer_price_actions,
-                                              action_rec_stride=lay.action_halfs)
-                else:
-                    policy.actor_forward(off_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=2,
-                                         step_dev=step_t, action=o_act, logprob=o_lp, action_rec=env.offer_core_actions,
-                                         action_rec_stride=lay.action_halfs)
-                    if free:
-                        policy.actor_forward(price_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs,
-                                             seed=3, step_dev=step_t, action=p_act, logprob=p_lp,
-                                             action_rec=env.offer_price_actions, action_rec_stride=lay.action_halfs,
-                                             gather_core=o_act, n_cores=Cc)
-                j0 = torch.cuda.Event()
-                j0.record(side[0])
-            with torch.cuda.stream(side[1]):
-                side[1].wait_event(fork)
+        def rollout_step(k=0):
+            if one_launch:
+                ga = policy.policy_step_group(acc_net, N * Cc, lay.o_acceptor, lay.o_acc_row, lay.a_acceptor, 1,
+                                              ring["a"][k, 0, :, :N * Cc], ring["lp"][k, 0, :, :N * Cc], x_used=ring["xa"][k])
+                go = policy.policy_step_group(off_net, NL, lay.o_offer, lay.o_off_row, lay.a_offer_core, 2,
+                                              ring["a"][k, 1, :, :NL], ring["lp"][k, 1, :, :NL], x_used=ring["xo"][k])
+                gp = policy.policy_step_group(price_net, NL, lay.o_offer, lay.o_off_row, lay.a_offer_price, 3,
+                                              ring["a"][k, 2, :, :NL], ring["lp"][k, 2, :, :NL], x_used=ring["xp"][k]) if free else None
+                policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, Cc, ga, go, gp, action_rec=env.action,
+                                   action_rec_stride=lay.action_halfs, env_offset=0, step_dev=step_t)
+            else:  # shapes without a one-launch kernel: one launch per net group
+                policy.actor_forward(off_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=2,
+                                     step_dev=step_t, action=o_act, logprob=o_lp, action_rec=env.offer_core_actions,
+                                     action_rec_stride=lay.action_halfs)
+                if free:
+                    policy.actor_forward(price_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs,
+                                         seed=3, step_dev=step_t, action=p_act, logprob=p_lp,
+                                         action_rec=env.offer_price_actions, action_rec_stride=lay.action_halfs,
+                                         gather_core=o_act, n_cores=Cc)
                 policy.actor_forward(acc_net, ov["acceptor"], lay.o_acc_row, N * Cc, B, env_stride=lay.obs_halfs,
                                      seed=1, step_dev=step_t, action=a_act, logprob=a_lp,
                                      action_rec=env.acceptor_actions, action_rec_stride=lay.action_halfs)
-                j1 = torch.cuda.Event()
-                j1.record(side[1])
-            cur.wait_event(j0)
-            cur.wait_event(j1)
             env.step_observe_records(env.action, res_r)
             step_t.add_(1)
 
         for i in range(5):
-            rollout_step()
+            rollout_step(i % SLOTS)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(cap):
             with torch.cuda.graph(graph, stream=cap):
-                rollout_step()
+                for k in range(SLOTS):
+                    rollout_step(k)
         torch.cuda.current_stream(dev).wait_stream(cap)
-        for i in range(20):
+        for i in range(3):
             graph.replay()
         torch.cuda.synchronize()
+        n_rep = max(1, args.rollout_steps // SLOTS)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for i in range(args.rollout_steps):
+        for i in range(n_rep):
             graph.replay()
         e1.record()
         torch.cuda.synchronize()
-        r_ms = e0.elapsed_time(e1) / args.rollout_steps
+        r_ms = e0.elapsed_time(e1) / (n_rep * SLOTS)
+        # the policy launch alone (same graph-free launch, L2 warm), for the split of the step
+        e0.record()
+        for i in range(20):
+            if one_launch:
+                policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, Cc, *[g for g in (
+                    policy.policy_step_group(acc_net, N * Cc, lay.o_acceptor, lay.o_acc_row, lay.a_acceptor, 1, ring["a"][0, 0, :, :N * Cc], ring["lp"][0, 0, :, :N * Cc], x_used=ring["xa"][0]),
+                    policy.policy_step_group(off_net, NL, lay.o_offer, lay.o_off_row, lay.a_offer_core, 2, ring["a"][0, 1, :, :NL], ring["lp"][0, 1, :, :NL], x_used=ring["xo"][0]),
+                    policy.policy_step_group(price_net, NL, lay.o_offer, lay.o_off_row, lay.a_offer_price, 3, ring["a"][0, 2, :, :NL], ring["lp"][0, 2, :, :NL], x_used=ring["xp"][0]) if free else None)],
+                    action_rec=env.action, action_rec_stride=lay.action_halfs, env_offset=0, step_dev=step_t)
+        e1.record()
+        torch.cuda.synchronize()
+        pol_us = e0.elapsed_time(e1) * 1e3 / 20 if one_launch else None
         rflags = int(res_r[:B, lay.r_flags].max().item())
         env.set_device_round(False)
         T = 200
@@ -805,11 +815,18 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         ret_us = e0.elapsed_time(e1) * 1e3 / 5
+        macs = N * Cc * (16 * (3 + 2 * NL) + 256 + 16 * (NL + 1)) + NL * (16 * (2 * Cc + 2) + 256 + 16 * (Cc + 1)) + \
+            (NL * (64 + 256 + 16 * (P + 1)) if free else 0)
         rollout = {"value": B * N / (r_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": r_ms,
-                   "steps": args.rollout_steps, "launches_per_step": 3 if (free and policy.offer_unit_fusable(off_net, price_net)) or not free else 4,
-                   "what": "actor forward of every divided PPO unit (offer/core chooser"
-                           + (", price chooser" if free else "") + ", acceptor: sample + log-prob, actions "
-                           "written into the action record; acceptor and offer units on two streams) + fused env step + observations; one shard, L2 warm, the step captured in a CUDA graph and replayed",
+                   "steps": n_rep * SLOTS, "launches_per_step": 2 if one_launch else (4 if free else 3),
+                   "policy_launch_us": pol_us, "policy_macs_per_env": macs,
+                   "policy_tflops": None if not pol_us else 2.0 * macs * B / pol_us / 1e6,
+                   "experience_bytes_per_step": int(B * (2 * (N * Cc * lay.o_acc_row + NL * lay.o_off_row + (4 * NL if free else 0))
+                                                          + 8 * (N * Cc + NL * (2 if free else 1)))),
+                   "what": "PPO.selectAction of every divided PPO unit (acceptor, offer/core chooser"
+                           + (", price chooser" if free else "") + ") in ONE launch (msched_policy_step: sample + log-prob, actions "
+                           "into the action record, state / action / log-prob into the experience-buffer slot of the step) + the fused "
+                           "env step + observations; 8 consecutive steps (8 buffer slots) captured in a CUDA graph and replayed",
                    "sticky_flags": rflags,
                    "returns_kernel": {"T": T, "units": B * N * Cc, "us": ret_us,
                                       "gbs": 12.0 * rew.numel() / ret_us / 1e3,

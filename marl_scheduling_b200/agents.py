@@ -92,6 +92,28 @@ class BatchedPPO:
         self.step_no = 0
         self.profile = None  # a list: every kernel-path epoch appends its (start, grad, all-reduce, Adam) CUDA events
 
+    # -- experience buffer slots (the one-launch policy step writes state / action / log-prob in place) --------
+    def slot(self, n_envs, x_stride):
+        """Views of the next experience-buffer slot for msched_policy_step: (x int16 [B,U,x_stride], action int32
+        [B,U], logprob float32 [B,U]).  The buffer is a ring of whole steps that doubles when it is full."""
+        t = len(self.buf_a)
+        ring = getattr(self, "_ring", None)
+        if ring is None or ring["x"].shape[1] != n_envs or ring["x"].shape[3] != x_stride or t >= ring["x"].shape[0]:
+            cap = 32 if ring is None else 2 * ring["x"].shape[0]
+            dev = self.device
+            new = dict(x=torch.zeros((cap, n_envs, self.units, x_stride), dtype=torch.int16, device=dev),
+                       a=torch.zeros((cap, n_envs, self.units), dtype=torch.int32, device=dev),
+                       lp=torch.zeros((cap, n_envs, self.units), dtype=torch.float32, device=dev))
+            self._ring = ring = new  # earlier steps keep referring to the old ring's tensors
+        return ring["x"][t], ring["a"][t], ring["lp"][t]
+
+    def commit_slot(self, x_slot, a_slot, lp_slot, lead):
+        """Record a slot the kernel has filled: buffer.states / actions / logprobs of src/PPOmodules.py:114-125."""
+        self.buf_x.append(x_slot[:, :, lead: lead + self.n_in])
+        self.buf_a.append(a_slot)
+        self.buf_lp.append(lp_slot)
+        self.step_no += 1
+
     # -- rollout ---------------------------------------------------------------------------------
     def selectAction(self, x, x_stride, env_stride, n_envs, seed, action_rec=None, action_rec_stride=0,
                      gather_core=None, n_cores=0, env_offset=0):
@@ -236,6 +258,17 @@ class BatchedPPO:
         self.buf_x, self.buf_a, self.buf_lp, self.buf_r = [], [], [], []
 
 
+def _one_launch_ok(core, acceptorObs, offerObs, env_offset, acceptor, offer, price=None):
+    """msched_policy_step applies when the nets have one of its shapes, the shard starts on an even global env
+    and the observations handed in are the views of the env's current observation record (not copies)."""
+    if os.environ.get("MSCHED_POLICY_STEP", "1") == "0" or (env_offset & 1):
+        return False
+    if not P.policy_step_supported(acceptor.policy_old, offer.policy_old, None if price is None else price.policy_old):
+        return False
+    base, lay = core._obs_buffer().data_ptr(), core.layout
+    return (acceptorObs.data_ptr() == base + 2 * lay.o_acceptor and offerObs.data_ptr() == base + 2 * lay.o_offer)
+
+
 class DividedFixedPricePPOAgents:
     """All N agents of src/Agent.py:495-536 (divided), :539-576 (globally shared) or :669-735
     (locally shared) at once: N*C acceptor units and N*L offer units."""
@@ -266,6 +299,18 @@ class DividedFixedPricePPOAgents:
         seed = self.world.seed
         # the kernels write the chosen actions straight into the env's action record
         eo = self.world.envOffset
+        if _one_launch_ok(c, acceptorObs, offerObs, eo, self.acceptor, self.offer):
+            # every unit of the step in ONE launch (msched_policy_step); state / action / log-prob written in place
+            sa, so = self.acceptor.slot(B, lay.o_acc_row), self.offer.slot(B, lay.o_off_row)
+            ga = P.policy_step_group(self.acceptor.policy_old, N * C, lay.o_acceptor, lay.o_acc_row, lay.a_acceptor,
+                                     seed * 2, sa[1], sa[2], x_used=sa[0])
+            go = P.policy_step_group(self.offer.policy_old, N * L, lay.o_offer, lay.o_off_row, lay.a_offer_core,
+                                     seed * 2 + 1, so[1], so[2], x_used=so[0])
+            P.policy_step(c._obs_buffer(), lay.obs_halfs, B, C, ga, go, None, action_rec=c.action,
+                          action_rec_stride=lay.action_halfs, env_offset=eo, step=self.acceptor.step_no)
+            self.acceptor.commit_slot(*sa, lay.o_acceptor & 1)
+            self.offer.commit_slot(*so, 0)
+            return c.acceptor_actions, c.offer_core_actions
         self.offer.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 2 + 1,
                                 action_rec=c.offer_core_actions, action_rec_stride=lay.action_halfs, env_offset=eo)
         self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 2,
@@ -315,6 +360,23 @@ class DividedFreePricePPOAgents:
         c, lay = self.env.core, self.env.core.layout
         B, N, C, L = c.B, c.N, c.C, c.Lc
         seed = self.world.seed
+        if (_one_launch_ok(c, acceptorObs, offerObs, self.world.envOffset, self.acceptor, self.core, self.price)
+                and self.core.step_no == self.price.step_no == self.acceptor.step_no):
+            # acceptor units + core chooser + price chooser of every offer unit in ONE launch (msched_policy_step)
+            NL = N * L
+            sa, sc, sp = self.acceptor.slot(B, lay.o_acc_row), self.core.slot(B, lay.o_off_row), self.price.slot(B, 4)
+            ga = P.policy_step_group(self.acceptor.policy_old, N * C, lay.o_acceptor, lay.o_acc_row, lay.a_acceptor,
+                                     seed * 3, sa[1], sa[2], x_used=sa[0])
+            gc = P.policy_step_group(self.core.policy_old, NL, lay.o_offer, lay.o_off_row, lay.a_offer_core,
+                                     seed * 3 + 1, sc[1], sc[2], x_used=sc[0])
+            gp = P.policy_step_group(self.price.policy_old, NL, lay.o_offer, lay.o_off_row, lay.a_offer_price,
+                                     seed * 3 + 2, sp[1], sp[2], x_used=sp[0])
+            P.policy_step(c._obs_buffer(), lay.obs_halfs, B, C, ga, gc, gp, action_rec=c.action,
+                          action_rec_stride=lay.action_halfs, env_offset=self.world.envOffset, step=self.acceptor.step_no)
+            self.acceptor.commit_slot(*sa, lay.o_acceptor & 1)
+            self.core.commit_slot(*sc, 0)
+            self.price.commit_slot(*sp, 0)
+            return c.acceptor_actions, (c.offer_core_actions, c.offer_price_actions)
         if P.offer_unit_fusable(self.core.policy_old, self.price.policy_old) and self.core.step_no == self.price.step_no:
             # both choosers of every offer unit in one launch (msched_offer_unit_forward)
             NL = N * L
