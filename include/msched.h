@@ -59,6 +59,7 @@ extern "C" {
 #define MSCHED_FLAG_COLLECTION_FULL 2u /* reference: raise in JobCollection.insertJob, src/world.py:133 */
 #define MSCHED_FLAG_ACTION_RANGE 4u    /* reference: assert in src/world.py:389,404 */
 #define MSCHED_FLAG_SPAWN_RANGE 8u     /* reference: UnboundLocalError in src/Agent.py:52-57 (Q13) */
+#define MSCHED_FLAG_COMPACT_RANGE 16u  /* compact result record only: an integer reward did not fit int16 (saturated) */
 
 /* reward variants: src/Reward.py:146-212, :6-89 (commercial / non-commercial), :92-143 */
 enum {
@@ -214,6 +215,25 @@ int msched_step_observe(void *handle, const int16_t *action_dev, const double *s
  * (written by the same launch when the domain fuses them).  Staging buffers are owned by the handle. */
 int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_host,
                      int16_t *obs_dev, void *stream);
+
+/* msched_step_host with a COMPACT result record: what SchedulingEnv.step returns besides the observations
+ * (src/SchedulingEnvironment.py:60-83: the four reward arrays of src/Reward.py, the acception quality, done) in
+ * half the bytes, for callers on the far side of PCIe.  Per env `words` uint32: int16-sized planes first (offsets in
+ * 16-bit units) -- offer reward and price reward as IEEE half (prio1, prio1 - price and netZeroOfferReward: exact
+ * for |value| <= 2048 and a half-representable netZeroOfferReward, which msched_get_compact_result_layout checks),
+ * acceptor / auctioneer / agent reward as int16 (saturated with MSCHED_FLAG_COMPACT_RANGE if one does not fit) --
+ * then three words: quality_sum as float32, counts (as in the full record), flags.  BASELINE config 3: 60 bytes
+ * instead of 116.  Needs a domain with a fused kernel, PINNED host buffers and B a multiple of 128 (else
+ * MSCHED_E_ARG: use msched_step_host); the kernel's bulk copies read the actions from and write the compact
+ * records to host memory directly. */
+typedef struct MschedCompactResultLayout {
+    int32_t words;                                             /* uint32 per env (odd) */
+    int32_t c_offer, c_price, c_acceptor, c_auctioneer, c_agent; /* 16-bit element offsets (-1 = absent) */
+    int32_t c_quality, c_counts, c_flags;                      /* word offsets */
+} MschedCompactResultLayout;
+int msched_get_compact_result_layout(const MschedConfig *cfg, MschedCompactResultLayout *out);
+int msched_step_host_compact(void *handle, const int16_t *action_host, uint32_t *cresult_host, int16_t *obs_dev,
+                             void *stream);
 
 /* Agent.gatherObservations + gatherDividedAuctioneerObservation (src/Agent.py:148-300,
  * src/Auctioneer.py:20-77): dense reference-layout observations; ids_dev (optional, may be

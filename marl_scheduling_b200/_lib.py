@@ -18,7 +18,7 @@ MAX_KINDS = 16
 TILE_ENVS = 128
 
 OK, E_ARG, E_CUDA, E_NODEVICE, E_STATE = 0, -1, -2, -3, -4
-FLAG_CHAIN_OVERFLOW, FLAG_COLLECTION_FULL, FLAG_ACTION_RANGE, FLAG_SPAWN_RANGE = 1, 2, 4, 8
+FLAG_CHAIN_OVERFLOW, FLAG_COLLECTION_FULL, FLAG_ACTION_RANGE, FLAG_SPAWN_RANGE, FLAG_COMPACT_RANGE = 1, 2, 4, 8, 16
 
 REWARD = {"fix": 0, "divided_fixed": 0, "free_comm": 1, "divided_free_commercial": 1,
           "free_ncomm": 2, "divided_free_noncommercial": 2, "agg": 3, "aggregated_fixed": 3}
@@ -48,6 +48,11 @@ class MschedLayout(C.Structure):
         "r_flags", "r_auctioneer_idx", "RL", "RC",
         "o_acceptor", "o_offer", "o_auctioneer", "o_acc_row", "o_off_row",
         "cobs_halfs", "c_core", "c_slot", "c_offer")]
+
+
+class MschedCompactResultLayout(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("words", "c_offer", "c_price", "c_acceptor", "c_auctioneer", "c_agent",
+                                         "c_quality", "c_counts", "c_flags")]
 
 
 class MschedInfo(C.Structure):
@@ -120,6 +125,8 @@ SYMBOLS = {
     "msched_step": (C.c_int, [P, P, P, P, P]),
     "msched_step_observe": (C.c_int, [P, P, P, P, P, P]),
     "msched_step_host": (C.c_int, [P, P, P, P, P]),
+    "msched_get_compact_result_layout": (C.c_int, [C.POINTER(MschedConfig), C.POINTER(MschedCompactResultLayout)]),
+    "msched_step_host_compact": (C.c_int, [P, P, P, P, P]),
     "msched_observe_dense": (C.c_int, [P, P, P, P]),
     "msched_observe_compact": (C.c_int, [P, P, P]),
     "msched_step_compact": (C.c_int, [P, P, P, P, P, P]),

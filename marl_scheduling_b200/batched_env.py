@@ -214,6 +214,40 @@ class BatchedSchedulingEnv:
                                           self._obs_buffer().data_ptr() if observe else None, self._stream()))
         return result_host
 
+    def compact_result_layout(self):
+        """MschedCompactResultLayout of this configuration (raises MschedError if its rewards are not half-exact)."""
+        cl = L.MschedCompactResultLayout()
+        L.check(self.lib.msched_get_compact_result_layout(C.byref(self.cfg), C.byref(cl)))
+        return cl
+
+    def step_host_compact(self, action_host, cresult_host, observe=False):
+        """msched_step_host_compact: pinned int16 action records in, COMPACT result records out (pinned int32
+        [B, words]); decode with compact_rewards()."""
+        L.check(self.lib.msched_step_host_compact(self.handle, action_host.data_ptr(), cresult_host.data_ptr(),
+                                                  self._obs_buffer().data_ptr() if observe else None, self._stream()))
+        return cresult_host
+
+    def compact_rewards(self, cresult):
+        """Decode compact result records (any device) into the dict rewards() returns (float32 / int16 planes)."""
+        cl, B, N, lay = self.compact_result_layout(), self.B, self.N, self.layout
+        r = cresult[:B]
+        h = r.view(torch.int16)
+        out = {}
+        f = lambda off, n: h[:, off: off + n].contiguous().view(torch.float16).float()
+        out["offer"] = f(cl.c_offer, N * lay.RL).view(B, N, lay.RL)
+        out["price"] = f(cl.c_price, N * lay.RL).view(B, N, lay.RL) if cl.c_price >= 0 else None
+        out["acceptor"] = h[:, cl.c_acceptor: cl.c_acceptor + N * lay.RC].view(B, N, lay.RC)
+        out["auctioneer"] = h[:, cl.c_auctioneer: cl.c_auctioneer + self.C]
+        out["agent"] = h[:, cl.c_agent: cl.c_agent + N]
+        out["quality_sum"] = r[:, cl.c_quality].contiguous().view(torch.float32)
+        counts = r[:, cl.c_counts]
+        out["quality_cnt"] = counts & 0xFF
+        out["n_accepted"] = (counts >> 8) & 0xFF
+        out["n_terminated"] = (counts >> 16) & 0xFF
+        out["done"] = (counts >> 24) & 0x1
+        out["flags"] = r[:, cl.c_flags]
+        return out
+
     # ------------------------------------------------------------------ result record views
     def rewards(self, result=None):
         lay, B, N = self.layout, self.B, self.N

@@ -57,11 +57,21 @@ struct FusedDims {
     static constexpr bool SMALL = OBS_TILE <= 14 * 1024;
 };
 
-inline size_t fused_smem_bytes(int stateWords, int actionHalfs, int resultWords, int obsHalfs, int C)
+inline size_t fused_smem_bytes(int stateWords, int actionHalfs, int resultWords, int obsHalfs, int C, int compactWords = 0)
 {
     const int xw = (3 * C + 4 * ((C + 3) / 4) + 4 + 1 + 2) | 1;
-    const size_t work = (size_t)stateWords + actionHalfs / 2 + resultWords + xw, obs = (size_t)obsHalfs / 2;
+    // the compact result tile (msched_step_host_compact) sits behind the work tiles
+    const size_t work = (size_t)stateWords + actionHalfs / 2 + resultWords + xw + compactWords, obs = (size_t)obsHalfs / 2;
     return (size_t)32 * 4 * (work > obs ? work : obs);  // the observation tile overlays the work tiles
+}
+
+// one value of the compact result record: float planes as IEEE half (exact for the small integers and the 0.5 the
+// reward functions produce; the host checks the domain), integer planes saturated to int16 (flag bit 4 if it bites)
+__device__ __forceinline__ uint16_t compact_f(float v) { return __half_as_ushort(__float2half_rn(v)); }
+__device__ __forceinline__ uint16_t compact_i(int v, uint32_t &flags)
+{
+    if (v > 32767 || v < -32768) { flags |= MSCHED_FLAG_COMPACT_RANGE; v = v > 0 ? 32767 : -32768; }
+    return (uint16_t)(v & 0xffff);
 }
 
 // integer accumulation into the tile: several role warps may touch one word (exact, order-free
@@ -509,6 +519,26 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
             res[p.rFlags] = flags;
         }
     }
+    // compact result record (host-buffer step): int16 / half planes, packed behind the work tiles
+    if (p.cres && w == 0) {
+        uint32_t *cr = sScr + 32 * XW + (size_t)lane * p.CW;
+        uint16_t *ch = reinterpret_cast<uint16_t *>(cr);
+        uint32_t cflags = 0u;
+        const int nOff = N * p.RL, nAccW = N * p.RC;
+        for (int k = 0; k < nOff; ++k) ch[p.cOffer + k] = live ? compact_f(resf[p.rOffer + k]) : (uint16_t)0;
+        if (p.cPrice >= 0)
+            for (int k = 0; k < nOff; ++k) ch[p.cPrice + k] = live ? compact_f(resf[p.rPrice + k]) : (uint16_t)0;
+        for (int k = 0; k < nAccW; ++k) ch[p.cAcc + k] = live ? compact_i(resi[p.rAcc + k], cflags) : (uint16_t)0;
+#pragma unroll
+        for (int k = 0; k < C; ++k) ch[p.cAuc + k] = live ? compact_i(resi[p.rAuc + k], cflags) : (uint16_t)0;
+#pragma unroll
+        for (int k = 0; k < N; ++k) ch[p.cAgent + k] = live ? compact_i(resi[p.rAgent + k], cflags) : (uint16_t)0;
+        for (int k = p.cAgent + N; k < 2 * p.cTail; ++k) ch[k] = 0;
+        cr[p.cTail] = live ? __float_as_uint((float)qualSum) : 0u;
+        cr[p.cTail + 1] = live ? res[p.rCounts] : 0u;
+        cr[p.cTail + 2] = live ? (res[p.rFlags] | cflags) : 0u;
+        for (int k = p.cTail + 3; k < p.CW; ++k) cr[k] = 0u;
+    }
 
     // ---- the new state and the result record leave; the observation rows are then staged in the
     // same shared memory ----
@@ -524,7 +554,8 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     if (threadIdx.x == 0) {
         MSCHED_TL(tl[5] = clock64());
         bulk_s2g(p.state + (size_t)env0 * W, sState, 32u * W * 4u);
-        bulk_s2g(p.result + (size_t)env0 * RW, sRes, 32u * (uint32_t)RW * 4u);
+        if (p.cres) bulk_s2g(p.cres + (size_t)env0 * p.CW, sScr + 32 * XW, 32u * (uint32_t)p.CW * 4u);
+        else bulk_s2g(p.result + (size_t)env0 * RW, sRes, 32u * (uint32_t)RW * 4u);
         bulk_commit();
         bulk_wait_read();
     }

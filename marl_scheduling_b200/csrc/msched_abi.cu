@@ -104,6 +104,29 @@ int compute_layout(const MschedConfig *c, MschedLayout *o)
     return MSCHED_OK;
 }
 
+int compute_compact_layout(const MschedConfig *c, const MschedLayout &l, MschedCompactResultLayout *o)
+{
+    if (!o) return fail(MSCHED_E_ARG, "null layout");
+    for (int k = 0; k < c->J; ++k)
+        if (c->prio[k] < -1024 || c->prio[k] > 1024) return fail(MSCHED_E_ARG, "compact results: priorities beyond the exact half range");
+    {
+        const float z = (float)c->netZeroOfferReward;
+        if (__half2float(__float2half_rn(z)) != z || (double)z != c->netZeroOfferReward)
+            return fail(MSCHED_E_ARG, "compact results: netZeroOfferReward is not representable as IEEE half");
+    }
+    int h = 0;
+    o->c_offer = h; h += c->N * l.RL;
+    o->c_price = -1;
+    if (c->freePrices) { o->c_price = h; h += c->N * l.RL; }
+    o->c_acceptor = h; h += c->N * l.RC;
+    o->c_auctioneer = h; h += c->C;
+    o->c_agent = h; h += c->N;
+    const int w = (h + 1) / 2;
+    o->c_quality = w; o->c_counts = w + 1; o->c_flags = w + 2;
+    o->words = make_odd(w + 3);
+    return MSCHED_OK;
+}
+
 typedef void (*StepKernel)(const DevParams);
 typedef void (*ObsKernel)(const DevParams);
 
@@ -120,6 +143,7 @@ struct Handle {
     int coopG, coopThreads;
     size_t coopSmem;
     bool useCoop;
+    MschedCompactResultLayout clay;  // compact result record (words == 0: not available for this configuration)
     size_t warpSmem;  // warp-per-environment kernel (msched_warp.cu): shared memory per CTA, 0 = not available
     bool useWarp;
     StepKernel fusedFn;  // compile-time-domain register-resident kernel (step + observations), or null
@@ -360,8 +384,9 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     if (const char *e = getenv("MSCHED_ROLES")) { const int r = atoi(e); if (r == 1 || r == 2 || r == 4) h->fusedRoles = r; }
     h->fusedFn = pick_fused_kernel(cfg->N, cfg->C, cfg->L, h->fusedRoles);
     if (h->fusedFn) {
-        h->fusedSmem = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, 0, cfg->C);
-        h->fusedSmemObs = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, lay.obs_halfs, cfg->C);
+        if (compute_compact_layout(cfg, lay, &h->clay) != MSCHED_OK) memset(&h->clay, 0, sizeof(h->clay));
+        h->fusedSmem = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, 0, cfg->C, h->clay.words);
+        h->fusedSmemObs = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, lay.obs_halfs, cfg->C, h->clay.words);
         h->fuseObs = h->fusedSmemObs <= 48 * 1024;  // cfg2 domain: 43.6 KB tile, still one launch fewer
         if (const char *e = getenv("MSCHED_FUSE_OBS"))
             h->fuseObs = atoi(e) != 0 && h->fusedSmemObs + 2048 <= (size_t)h->smemOptin;
@@ -610,6 +635,54 @@ int msched_step_observe(void *handle, const int16_t *action_dev, const double *s
     launch_step(h, p, static_cast<cudaStream_t>(stream));
     CUDA_TRY(cudaGetLastError());
     h->round += 1;
+    return MSCHED_OK;
+}
+
+int msched_get_compact_result_layout(const MschedConfig *cfg, MschedCompactResultLayout *out)
+{
+    MschedLayout lay;
+    int rc = compute_layout(cfg, &lay);
+    if (rc) return rc;
+    return compute_compact_layout(cfg, lay, out);
+}
+
+int msched_step_host_compact(void *handle, const int16_t *action_host, uint32_t *cresult_host, int16_t *obs_dev, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !action_host || !cresult_host) return fail(MSCHED_E_ARG, "null handle/action/result");
+    if (!h->useFused || !h->clay.words) return fail(MSCHED_E_ARG, "compact results need a fused-kernel domain with half-exact rewards (use msched_step_host)");
+    if (h->cfg.spawnMode == MSCHED_SPAWN_U64) return fail(MSCHED_E_ARG, "step_host does not take recorded draws");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    if (h->cfg.B != h->lay.padded_envs || !aligned16(action_host) || !aligned16(cresult_host) || (obs_dev && !aligned16(obs_dev)))
+        return fail(MSCHED_E_ARG, "compact host step: B must be a multiple of 128 and the buffers 16-byte aligned");
+    cudaPointerAttributes aa{}, ra{};
+    if (cudaPointerGetAttributes(&aa, action_host) != cudaSuccess || aa.type != cudaMemoryTypeHost || !aa.devicePointer ||
+        cudaPointerGetAttributes(&ra, cresult_host) != cudaSuccess || ra.type != cudaMemoryTypeHost || !ra.devicePointer) {
+        (void)cudaGetLastError();
+        return fail(MSCHED_E_ARG, "compact host step: the host buffers must be pinned (cudaHostAlloc / pin_memory)");
+    }
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const bool fuse = obs_dev && h->fuseObs;
+    DevParams p = h->p;
+    p.action = static_cast<const int16_t *>(aa.devicePointer);
+    p.result = nullptr;
+    p.cres = static_cast<uint32_t *>(ra.devicePointer);
+    p.CW = h->clay.words;
+    p.cOffer = h->clay.c_offer; p.cPrice = h->clay.c_price; p.cAcc = h->clay.c_acceptor; p.cAuc = h->clay.c_auctioneer;
+    p.cAgent = h->clay.c_agent; p.cTail = h->clay.c_quality;
+    p.spawnU = nullptr;
+    p.obs = fuse ? obs_dev : nullptr;
+    p.round = (int)h->round;
+    p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
+    launch_step(h, p, s);
+    CUDA_TRY(cudaGetLastError());
+    h->round += 1;
+    if (obs_dev && !fuse) {
+        int rc = msched_observe_dense(handle, obs_dev, nullptr, stream);
+        if (rc) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
     return MSCHED_OK;
 }
 

@@ -18,6 +18,7 @@
 // The record length is forced ODD so that lane-per-env accesses to the staged tile in shared
 // memory (address = lane*W + field) are bank-conflict free for any field index.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -62,6 +63,10 @@ struct DevParams {
     int *stats;                    // episode statistics int32 [Bpad][J][4], or null (msched_bind_stats)
     int16_t *cobs;                 // compact observation records (warp kernel / msched_observe_compact), or null
     int COH;                       // compact observation halfs per env
+    // compact result record (msched_step_host_compact): int16 / half planes instead of int32 / float32
+    uint32_t *cres;                // compact result records, or null -> the full record goes to `result`
+    int CW;                        // compact result words per env (odd)
+    int cOffer, cPrice, cAcc, cAuc, cAgent, cTail;  // half offsets of the planes; word offset of [quality f32, counts, flags]
 };
 
 // ---- host+device layout arithmetic ------------------------------------------------------

@@ -5,7 +5,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-CFG3 = dict(N=2, C=3, L=3, prios=[2, 4, 8], lens=[5, 5, 5], probs=[1 / 3] * 3, fix=[1])
+CFG3 = dict(N=2, C=3, L=3, prios=[2, 4, 8], lens=[5, 5, 5], probs=[1 / 3] * 3, fix=[1, 2, 3])
 CFG2 = dict(N=4, C=4, L=3, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7])
 CFG1 = dict(N=2, C=3, L=2, prios=[5], lens=[4], probs=[1], fix=[3], mult=2)
 
