@@ -674,15 +674,33 @@ def main():
             tmp = torch.zeros((lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=dev)
             refresh_actions(env, tmp, gen)
             ah.append(tmp[:B].cpu().pin_memory())
-        rh = torch.zeros((B, lay.result_words), dtype=torch.int32).pin_memory()
+        # the result comes back as the COMPACT record (int16 / half planes) when the domain has one; the full record
+        # is timed beside it
+        try:
+            cwords = env.compact_result_layout().words if info["step_impl"] == "fused" else 0
+        except L.MschedError:
+            cwords = 0
+        rh_full = torch.zeros((B, lay.result_words), dtype=torch.int32).pin_memory()
+        rh = torch.zeros((B, cwords), dtype=torch.int32).pin_memory() if cwords else rh_full
+        host_step = env.step_host_compact if cwords else env.step_host
         for i in range(5):
-            env.step_host(ah[i % 16], rh, observe=dense)
+            env.step_host(ah[i % 16], rh_full, observe=dense)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(nE):
+            env.step_host(ah[i % 16], rh_full, observe=dense)
+        torch.cuda.synchronize()
+        te_full = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te_full, op=dist.ReduceOp.MAX)
+        for i in range(5):
+            host_step(ah[i % 16], rh, observe=dense)
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(nE):
-            env.step_host(ah[i % 16], rh, observe=dense)  # observations stay on the device for the policy kernels
+            host_step(ah[i % 16], rh, observe=dense)  # observations stay on the device for the policy kernels
         torch.cuda.synchronize()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
@@ -701,14 +719,18 @@ def main():
             c1.record()
             torch.cuda.synchronize()
             pcie[name] = 4 * (64 << 20) / (c0.elapsed_time(c1) * 1e-3) / 1e9
-        t_bound = max(B * lay.action_halfs * 2 / (pcie["h2d_gbs"] * 1e9), B * lay.result_words * 4 / (pcie["d2h_gbs"] * 1e9))
+        rwords = cwords or lay.result_words
+        t_bound = max(B * lay.action_halfs * 2 / (pcie["h2d_gbs"] * 1e9), B * rwords * 4 / (pcie["d2h_gbs"] * 1e9))
         pcie["bound_value"] = world * B * N / t_bound  # copies at the measured rates, both directions fully overlapped
         pcie["frac_of_bound"] = world * B * N * nE / float(te[0]) / pcie["bound_value"]
         del hb, db
         e2e = {"value": world * B * N * nE / float(te[0]), "unit": "agent-steps/s", "pcie": pcie,
-               "h2d_bytes_per_step": B * lay.action_halfs * 2, "d2h_bytes_per_step": B * lay.result_words * 4,
-               "steps": nE, "api": "msched_step_host (pinned action records -> result records, read and written by the kernel's bulk "
-                                   "copies over PCIe (zero-copy); observations stay on the device)"}
+               "h2d_bytes_per_step": B * lay.action_halfs * 2, "d2h_bytes_per_step": B * rwords * 4,
+               "full_record": {"value": world * B * N * nE / float(te_full[0]), "d2h_bytes_per_step": B * lay.result_words * 4,
+                               "api": "msched_step_host"},
+               "steps": nE, "api": ("msched_step_host_compact" if cwords else "msched_step_host") +
+                                   " (pinned action records -> " + ("compact " if cwords else "") + "result records, read and written by "
+                                   "the kernel's bulk copies over PCIe (zero-copy); observations stay on the device)"}
 
     # ---- secondary metric: the same step INCLUDING the batched actor forward of the
     # divided PPO agents (one net per unit, src/Agent.py:495-619) and, separately, the return scan ----

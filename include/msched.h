@@ -394,6 +394,23 @@ int msched_dqn_param_count(int n_in, int n_actions);
 int msched_dqn_select(const MschedMlpGroup *nets, const MschedActorIO *io, float epsilon, float *q_out,
                       void *stream);
 
+/* optimize_model (src/DQNmodules.py:97-154) up to the optimizer step, for a group of Q-nets: for every net the gradient
+ * of SmoothL1Loss(Q_policy(s)[a], gamma * max_a' Q_target(s') + r) (beta 1, mean over the batch) over `batch`
+ * transitions, clamped to [-1, 1] like `param.grad.data.clamp_(-1, 1)`.  state / next_state: int16
+ * [batch][n_nets][n_in]; action int32, reward float32: [batch][n_nets]; policy / target / grad: float32
+ * [n_nets][msched_dqn_param_count]; loss (optional): float32 [n_nets].  Follow with msched_adam_step (the reference
+ * uses torch.optim.Adam with its default learning rate, src/Agent.py:313-320).  Bit-reproducible (no atomics). */
+typedef struct MschedDqnBatch {
+    const float *policy, *target;
+    int32_t n_in, n_hidden, n_actions, n_nets, batch, reserved;
+    const int16_t *state, *next_state;
+    const int32_t *action;
+    const float *reward;
+    float gamma, reserved2;
+    float *grad, *loss;
+} MschedDqnBatch;
+int msched_dqn_grad(const MschedDqnBatch *b, void *stream);
+
 /* PPO.update returns prologue (src/PPOmodules.py:128-137): G_t = r_t + gamma*G_{t+1} over
  * the whole buffer in float64, cast to float32, optional (G-mean)/(std_unbiased+1e-7) per
  * unit.  rewards/out: float32 [T][M] time-major. */

@@ -90,6 +90,13 @@ class MschedPolicyStep(C.Structure):
                 ("acceptor", MschedPolicyGroup), ("core", MschedPolicyGroup), ("price", MschedPolicyGroup)]
 
 
+class MschedDqnBatch(C.Structure):
+    _fields_ = [("policy", C.c_void_p), ("target", C.c_void_p), ("n_in", C.c_int32), ("n_hidden", C.c_int32),
+                ("n_actions", C.c_int32), ("n_nets", C.c_int32), ("batch", C.c_int32), ("reserved", C.c_int32),
+                ("state", C.c_void_p), ("next_state", C.c_void_p), ("action", C.c_void_p), ("reward", C.c_void_p),
+                ("gamma", C.c_float), ("reserved2", C.c_float), ("grad", C.c_void_p), ("loss", C.c_void_p)]
+
+
 class MschedPpoBatch(C.Structure):
     _fields_ = [("actor_weights", C.c_void_p), ("critic_weights", C.c_void_p),
                 ("n_in", C.c_int32), ("n_hidden", C.c_int32), ("n_actions", C.c_int32), ("n_nets", C.c_int32),
@@ -140,6 +147,7 @@ SYMBOLS = {
                                             C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),
     "msched_dqn_param_count": (C.c_int, [C.c_int, C.c_int]),
     "msched_dqn_select": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), C.c_float, P, P]),
+    "msched_dqn_grad": (C.c_int, [C.POINTER(MschedDqnBatch), P]),
     "msched_ppo_workspace_bytes": (C.c_int, [C.POINTER(MschedPpoBatch), C.POINTER(C.c_uint64)]),
     "msched_ppo_grad": (C.c_int, [C.POINTER(MschedPpoBatch), P]),
     "msched_adam_step": (C.c_int, [P, P, P, P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int64, P]),

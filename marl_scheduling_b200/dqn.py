@@ -4,8 +4,9 @@
 
 Rollout: the epsilon-greedy Q-forward of every (environment, unit) runs in the CUDA kernel behind
 msched_dqn_select, straight on the observation record, writing the action record.  Learning
-(`optimize_model`: SmoothL1Loss against the target net, gradients clamped to [-1, 1], Adam) uses
-PyTorch autograd over device-resident replay memories, like the PPO update (N1).
+(`optimize_model`: SmoothL1Loss against the target net, gradients clamped to [-1, 1], Adam) runs in
+msched_dqn_grad (forward of both nets + backward of every unit's Q-net in one launch, bit-reproducible) followed
+by msched_adam_step, over device-resident replay memories.
 """
 from __future__ import annotations
 
@@ -82,9 +83,12 @@ class BatchedDQN:
             nets.append(torch.cat(parts))
         w = torch.stack(nets).to(device)
         assert w.shape[1] == L.lib().msched_dqn_param_count(n_in, n_actions)
-        self.policy = torch.nn.Parameter(w.clone())
+        self.policy = torch.nn.Parameter(w.clone(), requires_grad=False)
         self.target = w.clone()
-        self.optimizer = torch.optim.Adam([self.policy])
+        # torch.optim.Adam with its defaults per net (src/Agent.py:313-320), through msched_adam_step
+        self.lr, self.opt_step = 1e-3, 0
+        self._m, self._v, self._grad = torch.zeros_like(w), torch.zeros_like(w), torch.zeros_like(w)
+        self._loss = torch.zeros(units, device=device)
         self.memory = ReplayMemory(memory_size, units, n_in, device)
         self.step_no = 0
 
@@ -118,34 +122,31 @@ class BatchedDQN:
         a = action.view(n_envs, self.units)
         return (a, q.view(n_envs, self.units, self.A)) if want_q else a
 
-    def _forward(self, flat, x):
-        """flat [units, pc], x [units, M, in] float -> Q [units, M, A]."""
-        n, H, nin, A = flat.shape[0], self.H, self.n_in, self.A
-        o = 0
-        W1 = flat[:, o:o + H * nin].view(n, H, nin); o += H * nin
-        b1 = flat[:, o:o + H]; o += H
-        W2 = flat[:, o:o + A * H].view(n, A, H); o += A * H
-        b2 = flat[:, o:o + A]
-        h = torch.tanh(torch.baddbmm(b1.unsqueeze(1), x, W1.transpose(1, 2)))
-        return torch.baddbmm(b2.unsqueeze(1), h, W2.transpose(1, 2))
+    def optimize_batch(self, s, a, s2, r):
+        """One optimize_model step (src/DQNmodules.py:97-154) for every unit on an explicit batch: s / s2 int16
+        [batch, units, n_in], a [batch, units], r [batch, units].  Returns the per-unit loss (device tensor)."""
+        from . import policy as P
+        batch = s.shape[0]
+        s, s2 = s.contiguous(), s2.contiguous()
+        a32, r32 = a.to(torch.int32).contiguous(), r.to(torch.float32).contiguous()
+        b = L.MschedDqnBatch()
+        b.policy, b.target = self.policy.data_ptr(), self.target.data_ptr()
+        b.n_in, b.n_hidden, b.n_actions, b.n_nets, b.batch = self.n_in, self.H, self.A, self.units, batch
+        b.state, b.next_state, b.action, b.reward = s.data_ptr(), s2.data_ptr(), a32.data_ptr(), r32.data_ptr()
+        b.gamma = float(self.gamma)
+        b.grad, b.loss = self._grad.data_ptr(), self._loss.data_ptr()
+        L.check(L.lib().msched_dqn_grad(C.byref(b), _stream(self.device)))
+        self.opt_step += 1
+        P.adam_step(self.policy.data.view(-1), self._grad.view(-1), self._m.view(-1), self._v.view(-1), self.lr, self.opt_step)
+        self._keep_batch = (s, s2, a32, r32)
+        return self._loss
 
     def optimize_model(self, batch_size, generator=None):
-        """optimize_model (src/DQNmodules.py:97-154) for all units at once."""
+        """optimize_model (src/DQNmodules.py:97-154) for all units at once: sample, gradient kernel, Adam."""
         if len(self.memory) < batch_size:
             return None
         s, a, s2, r = self.memory.sample(batch_size, generator)
-        x = s.float().permute(1, 0, 2)                      # [units, batch, in]
-        x2 = s2.float().permute(1, 0, 2)
-        qsa = self._forward(self.policy, x).gather(2, a.t().unsqueeze(-1)).squeeze(-1)
-        with torch.no_grad():
-            nxt = self._forward(self.target, x2).max(2)[0]
-        expected = nxt * self.gamma + r.t()
-        loss = torch.nn.functional.smooth_l1_loss(qsa, expected, reduction="none").mean(1).sum()
-        self.optimizer.zero_grad()
-        loss.backward()
-        self.policy.grad.data.clamp_(-1, 1)
-        self.optimizer.step()
-        return float(loss.detach())
+        return self.optimize_batch(s, a, s2, r)
 
     def update_target(self):
         self.target.copy_(self.policy.detach())

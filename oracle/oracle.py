@@ -397,3 +397,62 @@ def compact_observation(e):
     has = np.asarray(e["off_core"]) > 0
     offer = np.stack([np.where(has, e["off_core"], 0), np.where(has, e["off_price"], 0)], -1).astype(np.int32)
     return dict(core=core, slot=slot, offer=offer)
+
+
+# ---- DQN: numpy float64 restatement of src/DQNmodules.py ---------------------------------------
+def _dqn_unpack(flat, n_in, A, H=16):
+    o, out = 0, []
+    for shape in ((H, n_in), (H,), (A, H), (A,)):
+        n = int(np.prod(shape))
+        out.append(np.asarray(flat[o:o + n], np.float64).reshape(shape))
+        o += n
+    return out
+
+
+def dqn_forward(flat, x, n_actions):
+    """DQNEntity.forward (src/DQNmodules.py:41-54): Linear(in,16)-Tanh-Linear(16,A); returns (Q [M,A], hidden [M,16])."""
+    x = np.asarray(x, np.float64)
+    W1, b1, W2, b2 = _dqn_unpack(flat, x.shape[1], n_actions)
+    h = np.tanh(x @ W1.T + b1)
+    return h @ W2.T + b2, h
+
+
+def dqn_select(flat, x, n_actions, sample, rand_action, eps):
+    """DQNEntity.selectAction (src/DQNmodules.py:56-76): `sample > eps_treshold` exploits (first arg-max of Q), else
+    the given random action."""
+    q, _ = dqn_forward(flat, x, n_actions)
+    return np.where(np.asarray(sample) > eps, q.argmax(1), np.asarray(rand_action)).astype(np.int32)
+
+
+def dqn_grad(policy, target, S, A_, S2, R, gamma, n_actions):
+    """Gradient of optimize_model's loss (src/DQNmodules.py:97-154) w.r.t. the policy net, AFTER the clamp to
+    [-1, 1]: SmoothL1Loss (beta 1, mean over the batch) between Q_policy(s)[a] and gamma * max_a' Q_target(s') + r."""
+    S, S2 = np.asarray(S, np.float64), np.asarray(S2, np.float64)
+    M, n_in = S.shape
+    W1, b1, W2, b2 = _dqn_unpack(policy, n_in, n_actions)
+    q, h = dqn_forward(policy, S, n_actions)
+    qn, _ = dqn_forward(target, S2, n_actions)
+    expected = qn.max(1) * gamma + np.asarray(R, np.float64)
+    A_ = np.asarray(A_).astype(np.int64)
+    d = q[np.arange(M), A_] - expected
+    g = np.clip(d, -1.0, 1.0) / M                       # d/dq of mean Huber
+    dq = np.zeros_like(q)
+    dq[np.arange(M), A_] = g
+    dh = dq @ W2
+    dz = dh * (1 - h * h)
+    grads = [dz.T @ S, dz.sum(0), dq.T @ h, dq.sum(0)]
+    flat = np.concatenate([a.reshape(-1) for a in grads])
+    loss = float(np.where(np.abs(d) < 1, 0.5 * d * d, np.abs(d) - 0.5).mean())
+    return np.clip(flat, -1.0, 1.0), loss
+
+
+def dqn_optimize(policy0, target, S, A_, S2, R, idx_steps, gamma, n_actions, lr=1e-3):
+    """optimize_model for the recorded batches `idx_steps` [steps, batch]; returns the parameters after every step."""
+    w = np.asarray(policy0, np.float64).copy()
+    m, v = np.zeros_like(w), np.zeros_like(w)
+    out = []
+    for k, idx in enumerate(idx_steps, 1):
+        g, _ = dqn_grad(w, target, S[idx], A_[idx], S2[idx], R[idx], gamma, n_actions)
+        adam_step(w, g, m, v, lr, k)
+        out.append(w.copy())
+    return np.stack(out)

@@ -17,7 +17,7 @@ def golden_names(kind="divided"):
     out = []
     for f in sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))):
         n = os.path.basename(f)[:-4]
-        if n in ("torch_vectors", "ppo_update"):
+        if n in ("torch_vectors", "ppo_update", "dqn"):
             continue
         if kind == "divided" and n.startswith("aggobs"):
             continue

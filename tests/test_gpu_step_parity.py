@@ -244,6 +244,54 @@ def test_step_host_matches_device_step(B, pinned):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("key", ["cfg3", "cfg2", "agg", "cfg1"])
+def test_step_host_compact_record_equals_full_record(key):
+    """msched_step_host_compact: the same step, the result in int16 / half planes (60 B instead of 116 B per env in
+    config 3).  Every field decodes to exactly what the full record holds (quality_sum to float32); priorities
+    beyond the exact half range or a netZeroOfferReward that is no half are refused."""
+    import torch
+    from marl_scheduling_b200._lib import MschedError
+    dom, mode = DOMS[key]
+    free = mode.startswith("free")
+    B = 384
+    a = _env(B, dict(dom, mode=mode), auction="random", spawn="philox", seed=3)
+    b = _env(B, dict(dom, mode=mode), auction="random", spawn="philox", seed=3)
+    cl = b.compact_result_layout()
+    lay = a.layout
+    assert cl.words % 2 == 1 and cl.words * 4 < lay.result_words * 4
+    ah = torch.zeros((B, lay.action_halfs), dtype=torch.int16).pin_memory()
+    ch = torch.zeros((B, cl.words), dtype=torch.int32).pin_memory()
+    rng = np.random.default_rng(0)
+    seen = 0
+    for t in range(40):
+        offc, acc, offp = random_actions(rng, B, dom, free)
+        ra = a.step(offc, acc, None, offer_price=offp)
+        ah.copy_(a.action[:B].cpu())
+        b.step_host_compact(ah, ch, observe=(t % 3 == 0))
+        rb = b.compact_rewards(ch)
+        for k in ("offer", "price", "acceptor", "auctioneer", "agent", "quality_cnt", "n_accepted", "n_terminated", "done", "flags"):
+            if ra[k] is None:
+                assert rb[k] is None
+                continue
+            assert torch.equal(ra[k].cpu().to(torch.float64), rb[k].to(torch.float64)), (key, t, k)
+        assert torch.allclose(ra["quality_sum"].cpu().float(), rb["quality_sum"], rtol=1e-6, atol=1e-6)
+        seen += int((ra["acceptor"] != 0).sum()) + int((ra["offer"] != 0).sum())
+        if t % 3 == 0:
+            oa, ob = a.observe(), b.obs_views()
+            for k in oa:
+                assert torch.equal(oa[k], ob[k]), (t, k)
+    assert seen > 100 and a.round == b.round == 40
+    ea, eb = a.export_state(), b.export_state()
+    for k in STATE_KEYS:
+        assert np.array_equal(ea[k], eb[k]), k
+    a.close(); b.close()
+    with pytest.raises(MschedError):
+        _env(128, dict(dom, mode=mode, prios=[5000] * len(dom["prios"]))).compact_result_layout()
+    if free:
+        with pytest.raises(MschedError):
+            _env(128, dict(dom, mode=mode, netZero=0.3)).compact_result_layout()
+
+
 @pytest.mark.parametrize("impl", ["fused1", "fused4", "lane"])
 def test_cuda_graph_replay_matches_eager_steps(impl):
     """Device-side round counter (msched_set_round_mode): a captured step + observations can be

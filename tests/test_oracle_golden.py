@@ -174,3 +174,22 @@ def test_ppo_update_oracle_reproduces_the_reference_update():
             diff = np.abs(got - ref.astype(np.float64))
             assert diff.max() <= 2.0 * lr * K, (tag, diff.max())
             assert np.mean(diff > 2e-6) < 0.02, (tag, np.mean(diff > 2e-6), diff.max())
+
+
+def test_oracle_dqn_matches_reference_fixtures():
+    """tests/golden/dqn.npz comes from the UNMODIFIED src/DQNmodules.py (oracle/gen_dqn_golden.py): Q-values,
+    epsilon-greedy choices with the recorded draws, and the weights after three optimize_model steps."""
+    import os
+    z = np.load(os.path.join(__import__("helpers").GOLDEN, "dqn.npz"))
+    for tag in ("acc_cfg2", "off_cfg2", "acc_cfg3"):
+        A = int(z[tag + ".n_actions"])
+        w0 = z[tag + ".w0"]
+        q, _ = O.dqn_forward(w0, z[tag + ".x"], A)
+        np.testing.assert_allclose(q, z[tag + ".q"], rtol=2e-5, atol=2e-6)
+        act = O.dqn_select(w0, z[tag + ".x"], A, z[tag + ".sample"], z[tag + ".randrange"], float(z[tag + ".eps"]))
+        assert np.array_equal(act, z[tag + ".action"])
+        assert 0.2 < (z[tag + ".sample"] > float(z[tag + ".eps"])).mean() < 0.8   # both branches exercised
+        w = O.dqn_optimize(w0, w0, z[tag + ".S"], z[tag + ".A"], z[tag + ".S2"], z[tag + ".R"], z[tag + ".idx"],
+                           float(z[tag + ".gamma"]), A)
+        np.testing.assert_allclose(w, z[tag + ".w_after"], rtol=2e-4, atol=2e-6)
+        assert np.abs(w[-1] - w0).max() > 1e-3
