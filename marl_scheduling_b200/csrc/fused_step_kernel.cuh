@@ -95,7 +95,14 @@ __device__ __forceinline__ void acc_and(uint32_t *p, uint32_t v)
     else atomicAnd(p, v);
 }
 
-template <int N, int C, int L, int R>
+// SPEC >= 0 fixes the configuration switches at compile time (the instantiations the BASELINE configs run):
+// bits 0-1 reward variant, 2-3 auction mode, 4-5 spawn mode, bit 6 newJobsPerRoundPerAgent == 1
+__host__ __device__ constexpr int fused_spec(int mode, int auction, int spawn, int newJobsIsOne)
+{
+    return mode | (auction << 2) | (spawn << 4) | (newJobsIsOne << 6);
+}
+
+template <int N, int C, int L, int R, int SPEC = -1>
 __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 16 : 8) : 1)
     fused_step_kernel(const __grid_constant__ DevParams p)
 {
@@ -130,9 +137,12 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
         bulk_g2s(sAct, p.action + (size_t)env0 * p.AH, 32u * (uint32_t)AW * 4u, &bar);
     }
 
-    const bool randomTies = p.auctionMode == MSCHED_AUCTION_RANDOM_MAX;
-    const bool external = p.auctionMode == MSCHED_AUCTION_EXTERNAL;
-    const int mode = p.mode;
+    const int auctionMode = SPEC >= 0 ? ((SPEC >> 2) & 3) : p.auctionMode;
+    const int spawnMode = SPEC >= 0 ? ((SPEC >> 4) & 3) : p.spawnMode;
+    const int newJobs = (SPEC >= 0 && (SPEC & 64)) ? 1 : p.newJobs;
+    const bool randomTies = auctionMode == MSCHED_AUCTION_RANDOM_MAX;
+    const bool external = auctionMode == MSCHED_AUCTION_EXTERNAL;
+    const int mode = SPEC >= 0 ? (SPEC & 3) : p.mode;
     const bool agg = mode == MSCHED_REWARD_AGGREGATED_FIXED;
     const bool freeM = mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL || mode == MSCHED_REWARD_DIVIDED_FREE_NONCOMMERCIAL;
     const int round = cur_round(p);
@@ -156,7 +166,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
             scr[D::X_TIE + 4 * c + 2] = x[2]; scr[D::X_TIE + 4 * c + 3] = x[3];
         }
     }
-    if (w == 1 % R && p.spawnMode == MSCHED_SPAWN_PHILOX) {
+    if (w == 1 % R && spawnMode == MSCHED_SPAWN_PHILOX) {
         uint32_t x[4];
         env_draw(p, env, kStreamSpawn, 0u, 0u, x);
         scr[D::X_SPAWN] = x[0]; scr[D::X_SPAWN + 1] = x[1]; scr[D::X_SPAWN + 2] = x[2]; scr[D::X_SPAWN + 3] = x[3];
@@ -438,7 +448,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
                 const bool waitOld = (slot[4 * s + 3] & 0xffu) != 0u;
                 uint32_t w3 = 0u;
                 if (a >= 0 && a < C && !waitOld) {
-                    const int price = p.freePrices ? (int)act[p.aOffp + s] : p.fix[kind];
+                    const int price = freeM ? (int)act[p.aOffp + s] : p.fix[kind];
                     w3 = pack_offer(a + 1, core_owner(core[3 * a]), price);
                 }
                 slot[4 * s + 3] = w3;
@@ -456,27 +466,27 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
                     for (int j = 0; j < C; ++j) owned += (core_owner(core[3 * j]) == a2 + 1) ? 1 : 0;
                     // free slots BEFORE any spawn of this step (another item may be filling some now)
                     nfree = L - __popcll((occ >> (a2 * L)) & ((1ull << L) - 1ull));
-                    const bool sp = owned + p.newJobs <= nfree;
-                    if (a2 < a) before += sp ? (uint32_t)p.newJobs : 0u;
+                    const bool sp = owned + newJobs <= nfree;
+                    if (a2 < a) before += sp ? (uint32_t)newJobs : 0u;
                     else mine = sp;
                 }
             }
             if (!mine) continue;
             uint32_t jobctr = st[0] + before;
-            acc_add<R>(reinterpret_cast<int *>(&scr[D::X_NSPAWN]), p.newJobs);
+            acc_add<R>(reinterpret_cast<int *>(&scr[D::X_NSPAWN]), newJobs);
             uint32_t rnd[4] = {scr[D::X_SPAWN], scr[D::X_SPAWN + 1], scr[D::X_SPAWN + 2], scr[D::X_SPAWN + 3]};
             int rndCall = 0;
-            for (int k = 0; k < p.newJobs; ++k) {
+            for (int k = 0; k < newJobs; ++k) {
                 int kind = -1;
-                if (p.spawnMode == MSCHED_SPAWN_KINDS) {
-                    kind = act[p.aSpawn + a * p.newJobs + k];
+                if (spawnMode == MSCHED_SPAWN_KINDS) {
+                    kind = act[p.aSpawn + a * newJobs + k];
                 } else {
-                    if (p.spawnMode == MSCHED_SPAWN_U64) {
-                        const double u = p.spawnU[((size_t)env * N + a) * p.newJobs + k];
+                    if (spawnMode == MSCHED_SPAWN_U64) {
+                        const double u = p.spawnU[((size_t)env * N + a) * newJobs + k];
                         for (int q = 0; q < p.J; ++q)
                             if (u < p.cum[q]) { kind = q; break; }
                     } else {
-                        const int dnum = a * p.newJobs + k;  // draw d uses word d%4 of Philox call d/4
+                        const int dnum = a * newJobs + k;  // draw d uses word d%4 of Philox call d/4
                         if ((dnum >> 2) != rndCall) {
                             rndCall = dnum >> 2;
                             env_draw(p, env, kStreamSpawn, (uint32_t)rndCall, 0u, rnd);

@@ -198,6 +198,22 @@ StepKernel pick_fused_kernel_r(int N, int C, int L)
     return nullptr;
 }
 
+// compile-time configurations of the BASELINE runs (device Philox spawn, one new job per agent and round, in-kernel
+// auction with random ties): cfg3 = free prices + commercial reward, cfg2 / cfg4 = fixed prices
+StepKernel pick_fused_spec(const MschedConfig &c, int roles)
+{
+    if (c.spawnMode != MSCHED_SPAWN_PHILOX || c.newJobsPerRound != 1 || c.auctionMode != MSCHED_AUCTION_RANDOM_MAX) return nullptr;
+    if (c.N == 2 && c.C == 3 && c.L == 3 && c.rewardVariant == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL) {
+        constexpr int S = fused_spec(MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL, MSCHED_AUCTION_RANDOM_MAX, MSCHED_SPAWN_PHILOX, 1);
+        return roles == 1 ? fused_step_kernel<2, 3, 3, 1, S> : roles == 2 ? fused_step_kernel<2, 3, 3, 2, S> : fused_step_kernel<2, 3, 3, 4, S>;
+    }
+    if (c.N == 4 && c.C == 4 && c.L == 3 && c.rewardVariant == MSCHED_REWARD_DIVIDED_FIXED) {
+        constexpr int S = fused_spec(MSCHED_REWARD_DIVIDED_FIXED, MSCHED_AUCTION_RANDOM_MAX, MSCHED_SPAWN_PHILOX, 1);
+        return roles == 2 ? fused_step_kernel<4, 4, 3, 2, S> : roles == 4 ? fused_step_kernel<4, 4, 3, 4, S> : nullptr;
+    }
+    return nullptr;
+}
+
 StepKernel pick_fused_kernel(int N, int C, int L, int roles)
 {
     return roles == 1 ? pick_fused_kernel_r<1>(N, C, L) : roles == 2 ? pick_fused_kernel_r<2>(N, C, L)
@@ -383,6 +399,8 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
     }
     if (const char *e = getenv("MSCHED_ROLES")) { const int r = atoi(e); if (r == 1 || r == 2 || r == 4) h->fusedRoles = r; }
     h->fusedFn = pick_fused_kernel(cfg->N, cfg->C, cfg->L, h->fusedRoles);
+    if (h->fusedFn && !getenv("MSCHED_NO_SPEC"))
+        if (StepKernel sp = pick_fused_spec(*cfg, h->fusedRoles)) h->fusedFn = sp;
     if (h->fusedFn) {
         if (compute_compact_layout(cfg, lay, &h->clay) != MSCHED_OK) memset(&h->clay, 0, sizeof(h->clay));
         h->fusedSmem = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, 0, cfg->C, h->clay.words);

@@ -23,27 +23,24 @@ PolicyGroupArgs group_args(const MschedPolicyGroup &g)
 
 int g_sms = 0;
 
-// KW = words of an observation row incl. the leading pad value; LEAD = 1 if the row starts on an odd int16
-template <int KW_A, int LEAD_A, int KIN_A, int AP_A, int KW_O, int KIN_O, int AP_O, int AP_P>
+// KW = 32-bit words of an observation row (incl. the leading pad value of the acceptor rows)
+template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P>
 int launch(PolicyStepArgs &a, cudaStream_t s)
 {
-    auto fn = policy_step_kernel<KW_A, LEAD_A, KIN_A, AP_A, KW_O, KIN_O, AP_O, AP_P>;
-    constexpr int APP = AP_P > 0 ? AP_P : 4;
-    constexpr int fa = NetImage<KIN_A, AP_A>::kFloats;
-    constexpr int fo = ((NetImage<KIN_O, AP_O>::kFloats + 3) & ~3) + (AP_P > 0 ? NetImage<4, APP>::kFloats : 0);
-    const size_t smem = sizeof(float) * (size_t)(fa > fo ? fa : fo);
+    auto fn = policy_step_kernel<KW_A, AP_A, KW_O, AP_O, AP_P>;
+    const size_t smem = sizeof(float) * (size_t)PolicyStepSmem<KW_A, AP_A, KW_O, AP_O, AP_P>::kWords;
     static int perSm = 0;
     if (!perSm) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 128, smem) != cudaSuccess || perSm < 1) perSm = 1;
     }
     // one resident wave, split between the acceptor units and the (heavier) offer units by their multiply-adds
     const int nTiles = (a.nEnvs + 255) / 256;
-    const double ca = (double)a.acc.units * (16.0 * KIN_A + 256 + 16.0 * a.acc.nActions);
-    const double co = (double)a.core.units * ((16.0 * KIN_O + 256 + 16.0 * a.core.nActions) +
-                                               (AP_P > 0 ? (64.0 + 256 + 16.0 * a.price.nActions) : 0.0));
+    const double ca = (double)a.acc.units * (32.0 * KW_A + 256 + 16.0 * AP_A);
+    const double co = (double)a.core.units * ((32.0 * KW_O + 256 + 16.0 * AP_O) + (AP_P > 0 ? (64.0 + 256 + 16.0 * AP_P) : 0.0));
     const int total = g_sms * perSm;
     int na = (int)(total * ca / (ca + co) / a.acc.units), no = (int)(total * co / (ca + co) / a.core.units);
     na = na < 1 ? 1 : (na > nTiles ? nTiles : na);
@@ -88,16 +85,17 @@ extern "C" int msched_policy_step(const MschedPolicyStep *ps, void *stream)
     int rc = -1;
     // BASELINE cfg3 (N2 C3 L3, free prices): acceptor 15 -> 7, core chooser 8 -> 4, price chooser 4 -> <= 16
     if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && free && ap <= 16 && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
-        rc = launch<8, 1, 15, 8, 4, 8, 8, 16>(a, s);
+        rc = launch<8, 8, 4, 8, 16>(a, s);
     // BASELINE cfg2 / cfg4 (N4 C4 L3, fixed prices): acceptor 27 -> 13, offer 10 -> 5
     else if (lead == 1 && ka == 27 && aa <= 16 && ko == 10 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 28) && (!O.x_used || O.x_used_stride >= 10))
-        rc = launch<14, 1, 27, 16, 5, 10, 8, 0>(a, s);
+        rc = launch<14, 16, 5, 8, 0>(a, s);
     // cfg3 domain with fixed prices
     else if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
-        rc = launch<8, 1, 15, 8, 4, 8, 8, 0>(a, s);
+        rc = launch<8, 8, 4, 8, 0>(a, s);
     // BASELINE cfg1 domain (N2 C3 L2): acceptor 11 -> 5, offer 8 -> 4
     else if (lead == 1 && ka == 11 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 12) && (!O.x_used || O.x_used_stride >= 8))
-        rc = launch<6, 1, 11, 8, 4, 8, 8, 0>(a, s);
+        rc = launch<6, 8, 4, 8, 0>(a, s);
+    if (rc == -2) return fail(MSCHED_E_CUDA, "msched_policy_step: shared-memory attribute rejected");
     if (rc) return fail(MSCHED_E_ARG, "msched_policy_step: no kernel for these net shapes (use msched_actor_forward per group)");
     CUDA_TRY(cudaGetLastError());
     return MSCHED_OK;

@@ -60,19 +60,24 @@ struct PolicyStepArgs {
     int ctasPerAccUnit, ctasPerOffUnit;
 };
 
-// shared-memory image of one 16-wide net: W1t [KIN][16] | b1 [16] | W2t [16][16] | b2 [16] | W3t [16][AP] | b3 [AP]
-template <int KIN, int AP>
+// shared-memory image of one 16-wide net: W1t [2*KW][16] (one row per int16 position of the observation row words,
+// zero rows for the leading pad / trailing unused positions) | b1 [16] | W2t [16][16] | b2 [16] | W3t [16][AP] | b3 [AP]
+template <int KW, int AP>
 struct NetImage {
-    static constexpr int kW1 = 0, kB1 = KIN * 16, kW2 = kB1 + 16, kB2 = kW2 + 256, kW3 = kB2 + 16, kB3 = kW3 + 16 * AP;
-    static constexpr int kFloats = kB3 + AP;
-    // all threads of the CTA; `w` = the net's parameters in torch layout [W1 16*nIn | b1 | W2 | b2 | W3 A*16 | b3]
-    __device__ static void stage(float *s, const float *__restrict__ w, int A)
+    static constexpr int kW1 = 0, kB1 = 2 * KW * 16, kW2 = kB1 + 16, kB2 = kW2 + 256, kW3 = kB2 + 16, kB3 = kW3 + 16 * AP;
+    static constexpr int kFloats = (kB3 + AP + 3) & ~3;
+    // all threads of the CTA; `w` = the net's parameters in torch layout [W1 16*nIn | b1 | W2 | b2 | W3 A*16 | b3];
+    // input k of the net sits at int16 position lead + k of the row
+    __device__ static void stage(float *s, const float *__restrict__ w, int nIn, int lead, int A)
     {
         constexpr float s2 = 2.f * kLog2e;
-        const float *w2 = w + 16 * KIN + 16, *w3 = w2 + 256 + 16;
-        for (int i = threadIdx.x; i < KIN * 16; i += blockDim.x) { const int o = i / KIN, k = i - o * KIN; s[kW1 + k * 16 + o] = w[i] * s2; }
-        for (int i = threadIdx.x; i < 256; i += blockDim.x) { const int o = i >> 4, k = i & 15; s[kW2 + k * 16 + o] = w2[i] * s2; }
-        for (int i = threadIdx.x; i < 16; i += blockDim.x) { s[kB1 + i] = w[16 * KIN + i] * s2; s[kB2 + i] = w2[256 + i] * s2; }
+        const float *w2 = w + 16 * nIn + 16, *w3 = w2 + 256 + 16;
+        for (int i = threadIdx.x; i < 2 * KW * 16; i += blockDim.x) {
+            const int pos = i >> 4, o = i & 15, k = pos - lead;
+            s[kW1 + i] = (k >= 0 && k < nIn) ? w[o * nIn + k] * s2 : 0.f;
+        }
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) { const int k = i >> 4, o = i & 15; s[kW2 + i] = w2[o * 16 + k] * s2; }
+        for (int i = threadIdx.x; i < 16; i += blockDim.x) { s[kB1 + i] = w[16 * nIn + i] * s2; s[kB2 + i] = w2[256 + i] * s2; }
         for (int i = threadIdx.x; i < 16 * AP; i += blockDim.x) {
             const int k = i / AP, o = i - k * AP;
             s[kW3 + i] = o < A ? w3[o * 16 + k] * kLog2e : 0.f;
@@ -110,52 +115,58 @@ __device__ __forceinline__ void fma_row16(const float *__restrict__ wrow, float 
     }
 }
 
-// layers 2 and 3 for the two rows: h (after the first Tanh) -> base-2 logits
-template <int KIN, int AP>
-__device__ __forceinline__ void mlp_tail(const float *__restrict__ s, float (&h0)[16], float (&h1)[16], float (&lg0)[AP], float (&lg1)[AP])
-{
-    using NI = NetImage<KIN, AP>;
-    float g0[16], g1[16];
-#pragma unroll
-    for (int o = 0; o < 16; ++o) { h0[o] = tanh_scaled(h0[o]); h1[o] = tanh_scaled(h1[o]); g0[o] = s[NI::kB2 + o]; g1[o] = g0[o]; }
-#pragma unroll
-    for (int k = 0; k < 16; ++k) fma_row16(s + NI::kW2 + k * 16, h0[k], h1[k], g0, g1);
-#pragma unroll
-    for (int o = 0; o < 16; ++o) { g0[o] = tanh_scaled(g0[o]); g1[o] = tanh_scaled(g1[o]); }
-#pragma unroll
-    for (int o4 = 0; o4 < AP / 4; ++o4) {
-        const float4 b4 = *reinterpret_cast<const float4 *>(s + NI::kB3 + 4 * o4);
-        float4 c0 = b4, c1 = b4;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float4 wv = *reinterpret_cast<const float4 *>(s + NI::kW3 + k * AP + 4 * o4);
-            c0.x = fmaf(wv.x, g0[k], c0.x); c0.y = fmaf(wv.y, g0[k], c0.y); c0.z = fmaf(wv.z, g0[k], c0.z); c0.w = fmaf(wv.w, g0[k], c0.w);
-            c1.x = fmaf(wv.x, g1[k], c1.x); c1.y = fmaf(wv.y, g1[k], c1.y); c1.z = fmaf(wv.z, g1[k], c1.z); c1.w = fmaf(wv.w, g1[k], c1.w);
-        }
-        lg0[4 * o4] = c0.x; lg0[4 * o4 + 1] = c0.y; lg0[4 * o4 + 2] = c0.z; lg0[4 * o4 + 3] = c0.w;
-        lg1[4 * o4] = c1.x; lg1[4 * o4 + 1] = c1.y; lg1[4 * o4 + 2] = c1.z; lg1[4 * o4 + 3] = c1.w;
-    }
-}
+// Per-thread vectors live in shared memory as planes of kPlane words (one word per thread, conflict free): the
+// row words x [2*KW planes: word w of the even / odd row] and the activations h [32 planes].  That keeps the
+// layer loops ROLLED (a dynamic index into a register array would go to local memory): the whole kernel's inner
+// loops are a few hundred instructions and stay in the instruction cache, and only the 32 accumulators of the
+// layer being computed sit in registers.
+constexpr int kPlane = 129;
 
-// layer 1 from the row words: inputs are the halves LEAD .. LEAD+KIN-1 of the KW words of each row
-template <int KW, int LEAD, int KIN, int AP>
-__device__ __forceinline__ void mlp_pair(const float *__restrict__ s, const uint32_t (&x0)[KW], const uint32_t (&x1)[KW],
-                                         float (&lg0)[AP], float (&lg1)[AP])
+// the three layers for the thread's two rows: row words in planes sx[0 .. 2*nWords), activations through sh
+template <int KW, int AP>
+__device__ __forceinline__ void mlp_pair(const float *__restrict__ s, const uint32_t *__restrict__ sx, float *__restrict__ sh,
+                                         int nWords, float (&lg0)[AP], float (&lg1)[AP])
 {
-    using NI = NetImage<KIN, AP>;
-    float h0[16], h1[16];
+    using NI = NetImage<KW, AP>;
+    const int tid = threadIdx.x;
+    {
+        float h0[16], h1[16];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) { h0[o] = s[NI::kB1 + o]; h1[o] = h0[o]; }
+        for (int o = 0; o < 16; ++o) { h0[o] = s[NI::kB1 + o]; h1[o] = h0[o]; }
+#pragma unroll 2
+        for (int w = 0; w < nWords; ++w) {
+            float a0, b0, a1, b1;
+            halves_to_float(sx[(2 * w) * kPlane + tid], a0, b0);
+            halves_to_float(sx[(2 * w + 1) * kPlane + tid], a1, b1);
+            fma_row16(s + NI::kW1 + (2 * w) * 16, a0, a1, h0, h1);
+            fma_row16(s + NI::kW1 + (2 * w + 1) * 16, b0, b1, h0, h1);
+        }
 #pragma unroll
-    for (int w = 0; w < KW; ++w) {
-        float a0, b0, a1, b1;
-        halves_to_float(x0[w], a0, b0);
-        halves_to_float(x1[w], a1, b1);
-        const int k = 2 * w - LEAD;  // input index of the word's low half
-        if (k >= 0 && k < KIN) fma_row16(s + NI::kW1 + k * 16, a0, a1, h0, h1);
-        if (k + 1 >= 0 && k + 1 < KIN) fma_row16(s + NI::kW1 + (k + 1) * 16, b0, b1, h0, h1);
+        for (int o = 0; o < 16; ++o) { sh[(2 * o) * kPlane + tid] = tanh_scaled(h0[o]); sh[(2 * o + 1) * kPlane + tid] = tanh_scaled(h1[o]); }
     }
-    mlp_tail<KIN, AP>(s, h0, h1, lg0, lg1);
+    {
+        float g0[16], g1[16];
+#pragma unroll
+        for (int o = 0; o < 16; ++o) { g0[o] = s[NI::kB2 + o]; g1[o] = g0[o]; }
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) fma_row16(s + NI::kW2 + k * 16, sh[(2 * k) * kPlane + tid], sh[(2 * k + 1) * kPlane + tid], g0, g1);
+#pragma unroll
+        for (int o = 0; o < 16; ++o) { sh[(2 * o) * kPlane + tid] = tanh_scaled(g0[o]); sh[(2 * o + 1) * kPlane + tid] = tanh_scaled(g1[o]); }
+    }
+#pragma unroll
+    for (int o = 0; o < AP; ++o) { lg0[o] = s[NI::kB3 + o]; lg1[o] = lg0[o]; }
+#pragma unroll 4
+    for (int k = 0; k < 16; ++k) {
+        const float y0 = sh[(2 * k) * kPlane + tid], y1 = sh[(2 * k + 1) * kPlane + tid];
+#pragma unroll
+        for (int o4 = 0; o4 < AP / 4; ++o4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(s + NI::kW3 + k * AP + 4 * o4);
+            lg0[4 * o4] = fmaf(wv.x, y0, lg0[4 * o4]); lg0[4 * o4 + 1] = fmaf(wv.y, y0, lg0[4 * o4 + 1]);
+            lg0[4 * o4 + 2] = fmaf(wv.z, y0, lg0[4 * o4 + 2]); lg0[4 * o4 + 3] = fmaf(wv.w, y0, lg0[4 * o4 + 3]);
+            lg1[4 * o4] = fmaf(wv.x, y1, lg1[4 * o4]); lg1[4 * o4 + 1] = fmaf(wv.y, y1, lg1[4 * o4 + 1]);
+            lg1[4 * o4 + 2] = fmaf(wv.z, y1, lg1[4 * o4 + 2]); lg1[4 * o4 + 3] = fmaf(wv.w, y1, lg1[4 * o4 + 3]);
+        }
+    }
 }
 
 // Softmax -> Categorical(probs): inverse-CDF sample with draw u, Categorical.log_prob semantics (renormalised,
@@ -169,14 +180,17 @@ __device__ __forceinline__ int sample_row(float (&lg)[AP], int A, float u, float
     float sum = 0.f;
 #pragma unroll
     for (int o = 0; o < AP; ++o) { lg[o] = ex2_approx(lg[o] - mx); sum += lg[o]; }
-    const float inv = 1.f / sum;
+    const float inv = __fdividef(1.f, sum);
     float tot = 0.f;
 #pragma unroll
     for (int o = 0; o < AP; ++o) { lg[o] *= inv; tot += lg[o]; }
     if (probsOut) {
+        for (int o = 0; o < A; ++o) {
+            float v = lg[0];
 #pragma unroll
-        for (int o = 0; o < AP; ++o)
-            if (o < A) probsOut[o] = lg[o];
+            for (int q = 1; q < AP; ++q) v = (q == o) ? lg[q] : v;
+            probsOut[o] = v;
+        }
     }
     const float thr = u * tot;
     float cdf = 0.f, pa = 0.f;
@@ -194,9 +208,9 @@ __device__ __forceinline__ int sample_row(float (&lg)[AP], int A, float u, float
         for (int o = 0; o < AP; ++o) pa = (o == A - 1) ? lg[o] : pa;
     }
     const float eps = 1.1920928955078125e-07f;
-    float pn = pa / tot;
+    float pn = __fdividef(pa, tot);
     pn = fminf(fmaxf(pn, eps), 1.f - eps);
-    logp = logf(pn);
+    logp = __logf(pn);
     return act;
 }
 
@@ -213,20 +227,41 @@ __device__ __forceinline__ void pair_draws(const PolicyStepArgs &a, unsigned lon
                   (uint32_t)seed, (uint32_t)(seed >> 32), x);
 }
 
+// The observation rows of the warp's 64 environments -> the x planes, warp-cooperatively: LPR lanes per row read the
+// row's consecutive words (whole 32-byte sectors instead of 32 lanes x 4 bytes of 32 different rows)
 template <int KW>
-__device__ __forceinline__ void load_row(const int16_t *obs, long long obsStride, int env, bool live, int off, uint32_t (&x)[KW])
+__device__ __forceinline__ void coop_load_rows(const PolicyStepArgs &a, int envBase, int offWords, uint32_t *sx)
 {
-    const uint32_t *r = reinterpret_cast<const uint32_t *>(obs + (size_t)(live ? env : 0) * obsStride + off);
-#pragma unroll
-    for (int w = 0; w < KW; ++w) x[w] = r[w];
+    constexpr int LPR = KW <= 2 ? 2 : KW <= 4 ? 4 : KW <= 8 ? 8 : KW <= 16 ? 16 : 32, RPI = 32 / LPR;
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    const int w = lane % LPR, rs = lane / LPR;
+    const uint32_t *ob = reinterpret_cast<const uint32_t *>(a.obs);
+    const long long strideW = a.obsStride >> 1;
+#pragma unroll 4
+    for (int r0 = 0; r0 < 64; r0 += RPI) {
+        const int r = r0 + rs, env = envBase + r;
+        if (w < KW) {
+            const uint32_t v = env < a.nEnvs ? ob[(size_t)env * strideW + offWords + w] : 0u;
+            sx[(2 * w + (r & 1)) * kPlane + wbase + (r >> 1)] = v;
+        }
+    }
 }
 
+// the x planes -> the experience buffer rows [env][unit][strideW words], the same lane mapping (full sectors)
 template <int KW>
-__device__ __forceinline__ void store_row(int16_t *dst, const uint32_t (&x)[KW])
+__device__ __forceinline__ void coop_store_rows(const PolicyStepArgs &a, const PolicyGroupArgs &g, int envBase, int unit, const uint32_t *sx)
 {
-    uint32_t *d = reinterpret_cast<uint32_t *>(dst);
-#pragma unroll
-    for (int w = 0; w < KW; ++w) d[w] = x[w];
+    constexpr int LPR = KW <= 2 ? 2 : KW <= 4 ? 4 : KW <= 8 ? 8 : KW <= 16 ? 16 : 32, RPI = 32 / LPR;
+    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
+    const int w = lane % LPR, rs = lane / LPR;
+    uint32_t *dst = reinterpret_cast<uint32_t *>(g.xUsed);
+    const int strideW = g.xUsedStride >> 1;
+#pragma unroll 4
+    for (int r0 = 0; r0 < 64; r0 += RPI) {
+        const int r = r0 + rs, env = envBase + r;
+        if (w < KW && env < a.nEnvs)
+            dst[((size_t)env * g.units + unit) * strideW + w] = sx[(2 * w + (r & 1)) * kPlane + wbase + (r >> 1)];
+    }
 }
 
 // outputs of one row
@@ -239,11 +274,26 @@ __device__ __forceinline__ void emit_row(const PolicyStepArgs &a, const PolicyGr
     if (a.actionRec) a.actionRec[(size_t)env * a.actionRecStride + g.recOffset + unit] = (int16_t)reported;
 }
 
-// KW_A/LEAD_A/KIN_A/AP_A: acceptor rows; KW_O/KIN_O/AP_O: offer rows (core chooser); AP_P: price chooser (0 = none)
-template <int KW_A, int LEAD_A, int KIN_A, int AP_A, int KW_O, int KIN_O, int AP_O, int AP_P>
-__global__ void __launch_bounds__(128, 4) policy_step_kernel(const __grid_constant__ PolicyStepArgs a)
+// KW_A / AP_A: words per acceptor row, padded action count; KW_O / AP_O: offer rows (core chooser); AP_P: price
+// chooser (0 = none).  Shared memory: the unit's net image(s) | x planes | h planes.
+template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P>
+struct PolicyStepSmem {
+    static constexpr int APP = AP_P > 0 ? AP_P : 4;
+    static constexpr int kImgA = NetImage<KW_A, AP_A>::kFloats;
+    static constexpr int kImgO = NetImage<KW_O, AP_O>::kFloats + (AP_P > 0 ? NetImage<2, APP>::kFloats : 0);
+    static constexpr int kImg = kImgA > kImgO ? kImgA : kImgO;
+    static constexpr int kXPlanes = 2 * (KW_A > KW_O + 2 ? KW_A : KW_O + 2);  // the price chooser's 2 words sit behind the offer row
+    static constexpr int kWords = kImg + (kXPlanes + 32) * kPlane;
+};
+
+template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P>
+__global__ void __launch_bounds__(128, 5) policy_step_kernel(const __grid_constant__ PolicyStepArgs a)
 {
+    using SM = PolicyStepSmem<KW_A, AP_A, KW_O, AP_O, AP_P>;
     extern __shared__ __align__(16) float sw[];
+    uint32_t *sx = reinterpret_cast<uint32_t *>(sw + SM::kImg);
+    float *sh = sw + SM::kImg + SM::kXPlanes * kPlane;
+    const int tid = threadIdx.x, wbase = tid & ~31;
     const int nAccCtas = a.acc.units * a.ctasPerAccUnit;
     const bool isAcc = (int)blockIdx.x < nAccCtas;
     const int nTiles = (a.nEnvs + 255) / 256;
@@ -251,16 +301,17 @@ __global__ void __launch_bounds__(128, 4) policy_step_kernel(const __grid_consta
         const int unit = blockIdx.x / a.ctasPerAccUnit, slice = blockIdx.x - unit * a.ctasPerAccUnit;
         const PolicyGroupArgs &g = a.acc;
         const int net = (unit / g.unitDiv) % g.nNets;
-        const int pc = 16 * KIN_A + 16 + 256 + 16 + 16 * g.nActions + g.nActions;
-        NetImage<KIN_A, AP_A>::stage(sw, g.weights + (size_t)net * pc, g.nActions);
+        const int pc = 16 * g.nIn + 16 + 256 + 16 + 16 * g.nActions + g.nActions;
+        const int lead = g.xOffset & 1;
+        NetImage<KW_A, AP_A>::stage(sw, g.weights + (size_t)net * pc, g.nIn, lead, g.nActions);
         __syncthreads();
-        const int off = g.xOffset + unit * g.xStride - LEAD_A;
+        const int offW = (g.xOffset - lead + unit * g.xStride) >> 1;
         for (int tile = slice; tile < nTiles; tile += a.ctasPerAccUnit) {
-            const int e0 = tile * 256 + 2 * threadIdx.x, e1 = e0 + 1;
+            const int envW = tile * 256 + 2 * wbase;  // first environment of this warp
+            const int e0 = tile * 256 + 2 * tid, e1 = e0 + 1;
             const bool l0 = e0 < a.nEnvs, l1 = e1 < a.nEnvs;
-            uint32_t x0[KW_A], x1[KW_A];
-            load_row<KW_A>(a.obs, a.obsStride, e0, l0, off, x0);
-            load_row<KW_A>(a.obs, a.obsStride, e1, l1, off, x1);
+            __syncwarp();
+            coop_load_rows<KW_A>(a, envW, offW, sx);
             float u0, u1;
             if (g.uOverride) {
                 u0 = l0 ? g.uOverride[(size_t)e0 * g.units + unit] : 0.f;
@@ -270,44 +321,41 @@ __global__ void __launch_bounds__(128, 4) policy_step_kernel(const __grid_consta
                 pair_draws(a, g.seed, e0, unit, r);
                 u0 = u24(r[0]); u1 = u24(r[1]);
             }
+            __syncwarp();
             float lg0[AP_A], lg1[AP_A];
-            mlp_pair<KW_A, LEAD_A, KIN_A, AP_A>(sw, x0, x1, lg0, lg1);
+            mlp_pair<KW_A, AP_A>(sw, sx, sh, KW_A, lg0, lg1);
             float lp0, lp1;
             const int a0 = sample_row<AP_A>(lg0, g.nActions, u0, lp0, (g.probs && l0) ? g.probs + ((size_t)e0 * g.units + unit) * g.nActions : nullptr);
             const int a1 = sample_row<AP_A>(lg1, g.nActions, u1, lp1, (g.probs && l1) ? g.probs + ((size_t)e1 * g.units + unit) * g.nActions : nullptr);
-            if (l0) {
-                emit_row(a, g, e0, unit, a0, lp0, a0);
-                if (g.xUsed) store_row<KW_A>(g.xUsed + ((size_t)e0 * g.units + unit) * g.xUsedStride, x0);
-            }
-            if (l1) {
-                emit_row(a, g, e1, unit, a1, lp1, a1);
-                if (g.xUsed) store_row<KW_A>(g.xUsed + ((size_t)e1 * g.units + unit) * g.xUsedStride, x1);
-            }
+            if (l0) emit_row(a, g, e0, unit, a0, lp0, a0);
+            if (l1) emit_row(a, g, e1, unit, a1, lp1, a1);
+            if (g.xUsed) coop_store_rows<KW_A>(a, g, envW, unit, sx);
         }
     } else {
         const int id = blockIdx.x - nAccCtas;
         const int unit = id / a.ctasPerOffUnit, slice = id - unit * a.ctasPerOffUnit;
         const PolicyGroupArgs &g = a.core, &gp = a.price;
-        constexpr int APP = AP_P > 0 ? AP_P : 4;
-        float *swp = sw + ((NetImage<KIN_O, AP_O>::kFloats + 3) & ~3);
+        constexpr int APP = SM::APP;
+        float *swp = sw + NetImage<KW_O, AP_O>::kFloats;
         {
             const int net = (unit / g.unitDiv) % g.nNets;
-            const int pc = 16 * KIN_O + 16 + 256 + 16 + 16 * g.nActions + g.nActions;
-            NetImage<KIN_O, AP_O>::stage(sw, g.weights + (size_t)net * pc, g.nActions);
+            const int pc = 16 * g.nIn + 16 + 256 + 16 + 16 * g.nActions + g.nActions;
+            NetImage<KW_O, AP_O>::stage(sw, g.weights + (size_t)net * pc, g.nIn, 0, g.nActions);
             if (AP_P > 0) {
                 const int netp = (unit / gp.unitDiv) % gp.nNets;
                 const int pcp = 16 * 4 + 16 + 256 + 16 + 16 * gp.nActions + gp.nActions;
-                NetImage<4, APP>::stage(swp, gp.weights + (size_t)netp * pcp, gp.nActions);
+                NetImage<2, APP>::stage(swp, gp.weights + (size_t)netp * pcp, 4, 0, gp.nActions);
             }
         }
         __syncthreads();
-        const int off = g.xOffset + unit * g.xStride;
+        const int offW = (g.xOffset + unit * g.xStride) >> 1;
+        uint32_t *sxp = sx + 2 * KW_O * kPlane;  // the price chooser's two input words per row
         for (int tile = slice; tile < nTiles; tile += a.ctasPerOffUnit) {
-            const int e0 = tile * 256 + 2 * threadIdx.x, e1 = e0 + 1;
+            const int envW = tile * 256 + 2 * wbase;
+            const int e0 = tile * 256 + 2 * tid, e1 = e0 + 1;
             const bool l0 = e0 < a.nEnvs, l1 = e1 < a.nEnvs;
-            uint32_t x0[KW_O], x1[KW_O];
-            load_row<KW_O>(a.obs, a.obsStride, e0, l0, off, x0);
-            load_row<KW_O>(a.obs, a.obsStride, e1, l1, off, x1);
+            __syncwarp();
+            coop_load_rows<KW_O>(a, envW, offW, sx);
             float u0, u1, v0 = 0.f, v1 = 0.f;
             if (g.uOverride) {
                 u0 = l0 ? g.uOverride[(size_t)e0 * g.units + unit] : 0.f;
@@ -321,47 +369,37 @@ __global__ void __launch_bounds__(128, 4) policy_step_kernel(const __grid_consta
                 pair_draws(a, g.seed, e0, unit, r);
                 u0 = u24(r[0]); u1 = u24(r[1]); v0 = u24(r[2]); v1 = u24(r[3]);
             }
-            float lg0[AP_O], lg1[AP_O];
-            mlp_pair<KW_O, 0, KIN_O, AP_O>(sw, x0, x1, lg0, lg1);
-            float lp0, lp1;
-            const int c0 = sample_row<AP_O>(lg0, g.nActions, u0, lp0, (g.probs && l0) ? g.probs + ((size_t)e0 * g.units + unit) * g.nActions : nullptr);
-            const int c1 = sample_row<AP_O>(lg1, g.nActions, u1, lp1, (g.probs && l1) ? g.probs + ((size_t)e1 * g.units + unit) * g.nActions : nullptr);
-            if (l0) {
-                emit_row(a, g, e0, unit, c0, lp0, c0);
-                if (g.xUsed) store_row<KW_O>(g.xUsed + ((size_t)e0 * g.units + unit) * g.xUsedStride, x0);
+            __syncwarp();
+            int c0, c1;
+            {
+                float lg0[AP_O], lg1[AP_O];
+                mlp_pair<KW_O, AP_O>(sw, sx, sh, KW_O, lg0, lg1);
+                float lp0, lp1;
+                c0 = sample_row<AP_O>(lg0, g.nActions, u0, lp0, (g.probs && l0) ? g.probs + ((size_t)e0 * g.units + unit) * g.nActions : nullptr);
+                c1 = sample_row<AP_O>(lg1, g.nActions, u1, lp1, (g.probs && l1) ? g.probs + ((size_t)e1 * g.units + unit) * g.nActions : nullptr);
+                if (l0) emit_row(a, g, e0, unit, c0, lp0, c0);
+                if (l1) emit_row(a, g, e1, unit, c1, lp1, c1);
             }
-            if (l1) {
-                emit_row(a, g, e1, unit, c1, lp1, c1);
-                if (g.xUsed) store_row<KW_O>(g.xUsed + ((size_t)e1 * g.units + unit) * g.xUsedStride, x1);
-            }
+            if (g.xUsed) coop_store_rows<KW_O>(a, g, envW, unit, sx);
             if (AP_P > 0) {
                 // FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): the price net sees [core prio, core rem,
                 // slot prio, slot rem] of the chosen core = row words c and nCores; core action 0 feeds the dummy
                 // [-5,-5,-5,-5] and reports price -5 (quirk Q1)
-                uint32_t p0[2], p1[2];
                 const uint32_t dummy = 0xfffbfffbu;
-                uint32_t s0 = x0[0], s1 = x1[0];
-#pragma unroll
-                for (int w = 1; w < KW_O; ++w) { s0 = (w == c0) ? x0[w] : s0; s1 = (w == c1) ? x1[w] : s1; }
-                uint32_t t0 = x0[0], t1 = x1[0];
-#pragma unroll
-                for (int w = 1; w < KW_O; ++w) { t0 = (w == a.nCores) ? x0[w] : t0; t1 = (w == a.nCores) ? x1[w] : t1; }
                 const bool d0 = c0 <= 0 || c0 > a.nCores, d1 = c1 <= 0 || c1 > a.nCores;
-                p0[0] = d0 ? dummy : s0; p0[1] = d0 ? dummy : t0;
-                p1[0] = d1 ? dummy : s1; p1[1] = d1 ? dummy : t1;
+                sxp[0 * kPlane + tid] = d0 ? dummy : sx[(2 * c0) * kPlane + tid];
+                sxp[1 * kPlane + tid] = d1 ? dummy : sx[(2 * c1 + 1) * kPlane + tid];
+                sxp[2 * kPlane + tid] = d0 ? dummy : sx[(2 * a.nCores) * kPlane + tid];
+                sxp[3 * kPlane + tid] = d1 ? dummy : sx[(2 * a.nCores + 1) * kPlane + tid];
                 float q0[APP], q1[APP];
-                mlp_pair<2, 0, 4, APP>(swp, p0, p1, q0, q1);
+                mlp_pair<2, APP>(swp, sxp, sh, 2, q0, q1);
                 float lq0, lq1;
                 const int b0 = sample_row<APP>(q0, gp.nActions, v0, lq0, (gp.probs && l0) ? gp.probs + ((size_t)e0 * gp.units + unit) * gp.nActions : nullptr);
                 const int b1 = sample_row<APP>(q1, gp.nActions, v1, lq1, (gp.probs && l1) ? gp.probs + ((size_t)e1 * gp.units + unit) * gp.nActions : nullptr);
-                if (l0) {
-                    emit_row(a, gp, e0, unit, b0, lq0, c0 == 0 ? -5 : b0);
-                    if (gp.xUsed) store_row<2>(gp.xUsed + ((size_t)e0 * gp.units + unit) * gp.xUsedStride, p0);
-                }
-                if (l1) {
-                    emit_row(a, gp, e1, unit, b1, lq1, c1 == 0 ? -5 : b1);
-                    if (gp.xUsed) store_row<2>(gp.xUsed + ((size_t)e1 * gp.units + unit) * gp.xUsedStride, p1);
-                }
+                if (l0) emit_row(a, gp, e0, unit, b0, lq0, c0 == 0 ? -5 : b0);
+                if (l1) emit_row(a, gp, e1, unit, b1, lq1, c1 == 0 ? -5 : b1);
+                __syncwarp();
+                if (gp.xUsed) coop_store_rows<2>(a, gp, envW, unit, sxp);
             }
         }
     }
