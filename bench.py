@@ -45,6 +45,10 @@ CONFIGS = {
                           mult=1, newJobs=1, episodeLength=100),
                  mode="fix", envs=65536,
                  desc="N4 C4 L3 (cfg2 domain) at 65,536 envs per GPU"),
+    # BASELINE.json configs[0]: src/trainHC.py:19-30 domain, hard-coded agents (the reference's own CPU-runnable case)
+    "cfg1": dict(dom=dict(N=2, C=3, L=2, prios=[5], lens=[4], probs=[1], fix=[3], mult=2, newJobs=1, episodeLength=50),
+                 mode="fix", envs=65536, policy="hardcoded",
+                 desc="N2 C3 L2, 1 job kind, fixed prices, hard-coded agents (trainHC)"),
     # BASELINE.json configs[4]: large domain, cooperative kernel (one warp per env), no dense obs
     "cfg5": dict(dom=dict(N=32, C=64, L=8, prios=[3, 10], lens=[6, 3], probs=[0.8, 0.2], fix=[2, 7],
                           mult=1, newJobs=1, episodeLength=100),
@@ -735,7 +739,41 @@ def main():
     # ---- secondary metric: the same step INCLUDING the batched actor forward of the
     # divided PPO agents (one net per unit, src/Agent.py:495-619) and, separately, the return scan ----
     rollout = None
-    if args.rollout_steps > 0 and dense and world == 1:
+    if args.rollout_steps > 0 and dense and world == 1 and cfg.get("policy") == "hardcoded":
+        # config 1: the reference's heuristic agents (msched_hardcoded_actions) + the fused env step, from a CUDA graph
+        env.set_device_round(True)
+        res_r = torch.zeros_like(env.result)
+
+        def hc_step():
+            env.hardcoded_actions(random_ties=True)
+            env.step_observe_records(env.action, res_r)
+        for i in range(5):
+            hc_step()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        cap = torch.cuda.Stream(device=dev)
+        cap.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(cap):
+            with torch.cuda.graph(graph, stream=cap):
+                for k in range(8):
+                    hc_step()
+        torch.cuda.current_stream(dev).wait_stream(cap)
+        graph.replay()
+        torch.cuda.synchronize()
+        n_rep = max(1, args.rollout_steps // 8)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n_rep):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        r_ms = e0.elapsed_time(e1) / (n_rep * 8)
+        env.set_device_round(False)
+        rollout = {"value": B * N / (r_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": r_ms, "steps": n_rep * 8,
+                   "launches_per_step": 2, "sticky_flags": int(res_r[:B, lay.r_flags].max().item()),
+                   "what": "DividedHardcodedAgent.getActions of every agent (msched_hardcoded_actions, Philox ties) + the fused env "
+                           "step + observations, 8 steps per CUDA-graph replay"}
+    elif args.rollout_steps > 0 and dense and world == 1:
         from marl_scheduling_b200 import policy
         free = mode.startswith("free")
         Cc, Lc, NL = dom["C"], dom["L"], N * dom["L"]
@@ -775,7 +813,7 @@ def main():
                 gp = policy.policy_step_group(price_net, NL, lay.o_offer, lay.o_off_row, lay.a_offer_price, 3,
                                               ring["a"][k, 2, :, :NL], ring["lp"][k, 2, :, :NL], x_used=ring["xp"][k]) if free else None
                 policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, Cc, ga, go, gp, action_rec=env.action,
-                                   action_rec_stride=lay.action_halfs, env_offset=0, step_dev=step_t)
+                                   action_rec_stride=lay.action_halfs, env_offset=0, step_dev=step_t, input_bound=max(max(dom['prios']), max(dom['lens']), 8))
             else:  # shapes without a one-launch kernel: one launch per net group
                 policy.actor_forward(off_net, ov["offer"], lay.o_off_row, NL, B, env_stride=lay.obs_halfs, seed=2,
                                      step_dev=step_t, action=o_act, logprob=o_lp, action_rec=env.offer_core_actions,
@@ -821,7 +859,7 @@ def main():
                     policy.policy_step_group(acc_net, N * Cc, lay.o_acceptor, lay.o_acc_row, lay.a_acceptor, 1, ring["a"][0, 0, :, :N * Cc], ring["lp"][0, 0, :, :N * Cc], x_used=ring["xa"][0]),
                     policy.policy_step_group(off_net, NL, lay.o_offer, lay.o_off_row, lay.a_offer_core, 2, ring["a"][0, 1, :, :NL], ring["lp"][0, 1, :, :NL], x_used=ring["xo"][0]),
                     policy.policy_step_group(price_net, NL, lay.o_offer, lay.o_off_row, lay.a_offer_price, 3, ring["a"][0, 2, :, :NL], ring["lp"][0, 2, :, :NL], x_used=ring["xp"][0]) if free else None)],
-                    action_rec=env.action, action_rec_stride=lay.action_halfs, env_offset=0, step_dev=step_t)
+                    action_rec=env.action, action_rec_stride=lay.action_halfs, env_offset=0, step_dev=step_t, input_bound=max(max(dom['prios']), max(dom['lens']), 8))
         e1.record()
         torch.cuda.synchronize()
         pol_us = e0.elapsed_time(e1) * 1e3 / 20 if one_launch else None

@@ -345,7 +345,9 @@ int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, vo
  * chooser's for both choosers), counter = (global env >> 1 lo, hi, step lo, 4 << 28 | step hi : 12 | unit : 16);
  * words 0,1 serve the even / odd environment's acceptor or core-chooser row, words 2,3 their price-chooser rows;
  * u = (x >> 8) * 2^-24.  env_offset (global index of env 0) must be even.  u_override float32 [n_envs][units]
- * replaces the draws (parity tests).  Unsupported net shapes return MSCHED_E_ARG: use msched_actor_forward. */
+ * replaces the draws (parity tests).  Unsupported net shapes return MSCHED_E_ARG: use msched_actor_forward.
+ * Two kernels serve the call with the same contract: tcgen05 tensor cores (3xTF32; needs input_bound <= 2047) and
+ * fp32 SIMT; MSCHED_POLICY_STEP_IMPL=tc|simt forces one. */
 typedef struct MschedPolicyGroup {
     MschedMlpGroup nets;
     int32_t units, x_offset, x_stride, rec_offset;
@@ -368,21 +370,12 @@ typedef struct MschedPolicyStep {
     uint64_t step;
     const uint64_t *step_dev; /* optional device step counter (CUDA-graph replays) */
     MschedPolicyGroup acceptor, core, price;
+    int32_t input_bound;      /* the caller's bound on |observation value| (priorities, prices, lengths); 1..2047 lets the
+                                 tensor-core kernel take the inputs as exact TF32 operands, 0 = unknown (fp32 SIMT kernel) */
+    int32_t reserved;
 } MschedPolicyStep;
 
 int msched_policy_step(const MschedPolicyStep *ps, void *stream);
-
-/* FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332) for every offer unit in ONE launch: the
- * core chooser samples a core from the unit's offer observation row (core_io->x, n_cores set), then the
- * same thread feeds [core prio, core rem, slot prio, slot rem] of that core to the price chooser
- * ([-5]*4 and a reported price of -5 for core action 0, quirk Q1).  Equivalent to msched_actor_forward
- * (core_nets, core_io) followed by msched_actor_forward(price_nets, price_io with gather_core =
- * core_io->action), without re-reading the row and without the second launch.  price_io's x / strides /
- * gather_core are ignored; its seed / step / u_override / outputs are the price chooser's own.  16-wide
- * nets with at most 16 actions each (the divided free-price agents); other shapes: MSCHED_E_ARG, use
- * the two-call form. */
-int msched_offer_unit_forward(const MschedMlpGroup *core_nets, const MschedActorIO *core_io,
-                              const MschedMlpGroup *price_nets, const MschedActorIO *price_io, void *stream);
 
 /* DQNEntity.selectAction (src/DQNmodules.py:34-76) for a group of Q-nets Linear(in,16)-Tanh-Linear(16,A)
  * (weights per net [W1 16*in | b1 16 | W2 A*16 | b2 A], torch layout): epsilon-greedy action per

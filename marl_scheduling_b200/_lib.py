@@ -87,7 +87,8 @@ class MschedPolicyStep(C.Structure):
     _fields_ = [("obs", C.c_void_p), ("obs_stride", C.c_int64), ("n_envs", C.c_int32), ("n_cores", C.c_int32),
                 ("action_rec", C.c_void_p), ("action_rec_stride", C.c_int64), ("env_offset", C.c_int64),
                 ("step", C.c_uint64), ("step_dev", C.c_void_p),
-                ("acceptor", MschedPolicyGroup), ("core", MschedPolicyGroup), ("price", MschedPolicyGroup)]
+                ("acceptor", MschedPolicyGroup), ("core", MschedPolicyGroup), ("price", MschedPolicyGroup),
+                ("input_bound", C.c_int32), ("reserved", C.c_int32)]
 
 
 class MschedDqnBatch(C.Structure):
@@ -143,8 +144,6 @@ SYMBOLS = {
     "msched_mlp_param_count": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "msched_actor_forward": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),
     "msched_policy_step": (C.c_int, [C.POINTER(MschedPolicyStep), P]),
-    "msched_offer_unit_forward": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO),
-                                            C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), P]),
     "msched_dqn_param_count": (C.c_int, [C.c_int, C.c_int]),
     "msched_dqn_select": (C.c_int, [C.POINTER(MschedMlpGroup), C.POINTER(MschedActorIO), C.c_float, P, P]),
     "msched_dqn_grad": (C.c_int, [C.POINTER(MschedDqnBatch), P]),

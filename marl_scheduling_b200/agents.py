@@ -258,6 +258,15 @@ class BatchedPPO:
         self.buf_x, self.buf_a, self.buf_lp, self.buf_r = [], [], [], []
 
 
+def _input_bound(world):
+    """Largest |value| an observation can hold (priorities, remaining lengths, prices, the -1/-2/-5 markers): lets
+    msched_policy_step take the inputs as exact TF32 operands when it is at most 2047."""
+    vals = [5] + [abs(int(v)) for v in world.possibleJobPriorities] + [abs(int(v)) for v in world.possibleJobLengths]
+    if not world.freePrices:
+        vals += [abs(int(v)) for v in world.listOfFixPrices]
+    return max(vals)
+
+
 def _one_launch_ok(core, acceptorObs, offerObs, env_offset, acceptor, offer, price=None):
     """msched_policy_step applies when the nets have one of its shapes, the shard starts on an even global env
     and the observations handed in are the views of the env's current observation record (not copies)."""
@@ -307,7 +316,8 @@ class DividedFixedPricePPOAgents:
             go = P.policy_step_group(self.offer.policy_old, N * L, lay.o_offer, lay.o_off_row, lay.a_offer_core,
                                      seed * 2 + 1, so[1], so[2], x_used=so[0])
             P.policy_step(c._obs_buffer(), lay.obs_halfs, B, C, ga, go, None, action_rec=c.action,
-                          action_rec_stride=lay.action_halfs, env_offset=eo, step=self.acceptor.step_no)
+                          action_rec_stride=lay.action_halfs, env_offset=eo, step=self.acceptor.step_no,
+                          input_bound=_input_bound(self.world))
             self.acceptor.commit_slot(*sa, lay.o_acceptor & 1)
             self.offer.commit_slot(*so, 0)
             return c.acceptor_actions, c.offer_core_actions
@@ -372,29 +382,11 @@ class DividedFreePricePPOAgents:
             gp = P.policy_step_group(self.price.policy_old, NL, lay.o_offer, lay.o_off_row, lay.a_offer_price,
                                      seed * 3 + 2, sp[1], sp[2], x_used=sp[0])
             P.policy_step(c._obs_buffer(), lay.obs_halfs, B, C, ga, gc, gp, action_rec=c.action,
-                          action_rec_stride=lay.action_halfs, env_offset=self.world.envOffset, step=self.acceptor.step_no)
+                          action_rec_stride=lay.action_halfs, env_offset=self.world.envOffset, step=self.acceptor.step_no,
+                          input_bound=_input_bound(self.world))
             self.acceptor.commit_slot(*sa, lay.o_acceptor & 1)
             self.core.commit_slot(*sc, 0)
             self.price.commit_slot(*sp, 0)
-            return c.acceptor_actions, (c.offer_core_actions, c.offer_price_actions)
-        if P.offer_unit_fusable(self.core.policy_old, self.price.policy_old) and self.core.step_no == self.price.step_no:
-            # both choosers of every offer unit in one launch (msched_offer_unit_forward)
-            NL = N * L
-            x_used = torch.empty((B, NL, 4), dtype=torch.int16, device=offerObs.device)
-            (ca, clp), (pa, plp) = P.offer_unit_forward(
-                self.core.policy_old, self.price.policy_old, offerObs, lay.o_off_row, NL, B, C,
-                env_stride=lay.obs_halfs, seeds=(seed * 3 + 1, seed * 3 + 2), step=self.core.step_no,
-                row_offset=self.world.envOffset * NL, core_rec=c.offer_core_actions, price_rec=c.offer_price_actions,
-                action_rec_stride=lay.action_halfs, x_used=x_used)
-            for ppo, xs, a_, lp_ in ((self.core, offerObs.reshape(B, NL, 2 * C + 2).clone(), ca, clp),
-                                     (self.price, x_used, pa, plp)):
-                ppo.step_no += 1
-                ppo.buf_x.append(xs)
-                ppo.buf_a.append(a_.view(B, NL))
-                ppo.buf_lp.append(lp_.view(B, NL))
-            self.acceptor.selectAction(acceptorObs, lay.o_acc_row, lay.obs_halfs, B, seed * 3,
-                                       action_rec=c.acceptor_actions, action_rec_stride=lay.action_halfs,
-                                       env_offset=self.world.envOffset)
             return c.acceptor_actions, (c.offer_core_actions, c.offer_price_actions)
         eo = self.world.envOffset
         core = self.core.selectAction(offerObs, lay.o_off_row, lay.obs_halfs, B, seed * 3 + 1,

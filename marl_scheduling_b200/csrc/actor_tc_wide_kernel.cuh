@@ -453,38 +453,6 @@ inline ActorArgs make_actor_args(const MschedMlpGroup &g, const MschedActorIO &i
     return a;
 }
 
-// FreePriceOfferPPO.selectAction in one launch (fp32 SIMT, 16-wide nets, <= 16 actions each): the
-// core chooser and the price chooser of every offer unit
-inline int launch_offer_unit(const MschedMlpGroup &gc, const MschedActorIO &ioc, const MschedMlpGroup &gp,
-                             const MschedActorIO &iop, cudaStream_t s)
-{
-    OfferUnitArgs q;
-    q.core = make_actor_args(gc, ioc);
-    q.price = make_actor_args(gp, iop);
-    q.price.nCores = ioc.n_cores;
-    auto fl = [](int nIn, int A) { const int Ap = (A + 3) & ~3; return nIn * 16 + 16 + 256 + 16 + 16 * Ap + Ap; };
-    const size_t smem = sizeof(float) * (size_t)(((fl(gc.n_in, gc.n_actions) + 3) & ~3) + fl(gp.n_in, gp.n_actions));
-    static int nSm = 0, perSm = 0;
-    static size_t cachedSmem = ~(size_t)0;
-    if (!nSm || cachedSmem != smem) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&nSm, cudaDevAttrMultiProcessorCount, dev);
-        perSm = resident_ctas(reinterpret_cast<const void *>(offer_unit_forward_simt<16, 16, 16>), smem, 1);
-        cachedSmem = smem;
-    }
-    const int tiles = (ioc.n_envs + 127) / 128;
-    int gx = (nSm * perSm) / ioc.units;
-    if (gx > tiles) gx = tiles;
-    if (gx < 1) gx = 1;
-    offer_unit_forward_simt<16, 16, 16><<<dim3(gx, ioc.units), 128, smem, s>>>(q);
-    return 0;
-}
-
-// warp-level tensor-core kernel for the 16-wide nets: actor_mma_kernel.cuh, compiled in msched_actor_mma.cu
-int launch_actor_mma_any(const ActorArgs &a, dim3 grid, cudaStream_t s);
-
-// impl: 0 = tensor cores (tcgen05), 1 = fp32 SIMT, 2 = warp-level tensor cores (16-wide nets)
 inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io, int impl, cudaStream_t s)
 {
     if (g.n_actions > 32767) return -1;  // actions are reported as int16 in the action record
@@ -496,10 +464,6 @@ inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io
         if (g.n_hidden == 32) return launch_actor_wide<32>(a, g, grid, s);
         if (g.n_hidden == 64) return launch_actor_wide<64>(a, g, grid, s);
         return -1;
-    }
-    if (impl == 2) {
-        if (g.n_hidden != 16 || g.n_actions > 16 || g.n_in > 32) return -1;
-        return launch_actor_mma_any(a, grid, s);
     }
     if (g.n_hidden == 16) return launch_actor_h<16>(a, g, grid, impl, s);
     if (g.n_hidden == 32) return launch_actor_h<32>(a, g, grid, impl, s);

@@ -37,48 +37,17 @@ int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, vo
     if (io->action_rec && io->action_rec_stride < io->units)
         return fail(MSCHED_E_ARG, "action_rec_stride smaller than units");
     if (io->n_envs == 0) return MSCHED_OK;
-    // Tensor cores (tcgen05, 3xTF32) where the contraction is wide enough to pay for the operand
-    // staging and the three MMA round trips per tile: hidden width >= 32 or more than 16 actions
-    // (measured on B200, 65,536 envs: 12->32->32->64 net 33.9 us vs 56.8 us SIMT; 15->16->16->7 net
-    // 41 us vs 35 us SIMT).  MSCHED_ACTOR_IMPL=tc|simt forces one.
-    // MSCHED_ACTOR_IMPL=tc|simt|mma forces one.  "mma" is the warp-level tensor-core kernel for the 16-wide nets
-    // (actor_mma_kernel.cuh): correct and parity-tested, but measured SLOWER than the SIMT kernel on B200
-    // (41 us vs 36 us, 393,216 rows of 15->16->16->7) -- legacy mma.sync TF32 issues one m16n8k8 per 32 cycles
-    // per SM sub-partition (ncu, hmma sub-pipe), i.e. the FFMA rate, and 3xTF32 needs three of them.
-    const bool mmaOk = nets->n_hidden == 16 && nets->n_actions <= 16 && nets->n_in <= 32;
+    // Tensor cores (tcgen05, 3xTF32) where the contraction is wide enough to pay for the operand staging and the
+    // three MMA round trips per tile: hidden width >= 32 or more than 16 actions (measured on B200, 65,536 envs:
+    // 12->32->32->64 net 33.9 us vs 56.8 us SIMT; 15->16->16->7 net 41 us vs 35 us SIMT).  The 16-wide nets of a
+    // whole rollout step are served by msched_policy_step; this entry point is the per-group form (aggregated
+    // heads, shapes without a one-launch kernel, tests).  MSCHED_ACTOR_IMPL=tc|simt forces one.
     int impl = (nets->n_hidden >= 32 || nets->n_actions > 16) ? 0 : 1;
-    if (const char *e = getenv("MSCHED_ACTOR_IMPL"))
-        impl = !strcmp(e, "simt") ? 1 : (!strcmp(e, "tc") ? 0 : ((!strcmp(e, "mma") && mmaOk) ? 2 : impl));
+    if (const char *e = getenv("MSCHED_ACTOR_IMPL")) impl = !strcmp(e, "simt") ? 1 : (!strcmp(e, "tc") ? 0 : impl);
     if (impl == 1 && nets->n_hidden > 32) impl = 0;  // the SIMT kernel is built for the 16- and 32-wide nets
     int rc = launch_actor_forward(*nets, *io, impl, static_cast<cudaStream_t>(stream));
     if (rc == -1) return fail(MSCHED_E_ARG, "unsupported MLP shape for the actor kernel");
     if (rc == -2) return fail(MSCHED_E_CUDA, "actor kernel: shared-memory attribute rejected");
-    CUDA_TRY(cudaGetLastError());
-    return MSCHED_OK;
-}
-
-int msched_offer_unit_forward(const MschedMlpGroup *core_nets, const MschedActorIO *core_io,
-                              const MschedMlpGroup *price_nets, const MschedActorIO *price_io, void *stream)
-{
-    if (!core_nets || !core_io || !price_nets || !price_io || !core_io->x || !core_nets->weights || !price_nets->weights)
-        return fail(MSCHED_E_ARG, "null nets/io/x/weights");
-    if (core_io->n_envs < 0 || core_io->units < 1 || core_nets->n_nets < 1 || price_nets->n_nets < 1)
-        return fail(MSCHED_E_ARG, "bad n_envs/units/n_nets");
-    if (price_io->units != core_io->units || price_io->n_envs != core_io->n_envs)
-        return fail(MSCHED_E_ARG, "the price chooser serves the core chooser's rows (same units and n_envs)");
-    const int nc = core_io->n_cores;
-    if (nc < 1 || core_nets->n_in != 2 * nc + 2 || core_io->x_stride < 2 * nc + 2 || core_nets->n_actions != nc + 1)
-        return fail(MSCHED_E_ARG, "core chooser: n_in == 2*n_cores+2 offer rows and n_cores+1 actions");
-    if (price_nets->n_in != 4) return fail(MSCHED_E_ARG, "price chooser: n_in == 4");
-    if (core_nets->n_hidden != 16 || price_nets->n_hidden != 16 || core_nets->n_actions > 16 || price_nets->n_actions > 16 ||
-        price_nets->n_actions < 1)
-        return fail(MSCHED_E_ARG, "fused offer unit: 16-wide nets with at most 16 actions (use two msched_actor_forward calls)");
-    if ((core_io->action_rec && core_io->action_rec_stride < core_io->units) ||
-        (price_io->action_rec && price_io->action_rec_stride < price_io->units))
-        return fail(MSCHED_E_ARG, "action_rec_stride smaller than units");
-    if (core_io->probs || price_io->probs) return fail(MSCHED_E_ARG, "probs output: use msched_actor_forward");
-    if (core_io->n_envs == 0) return MSCHED_OK;
-    launch_offer_unit(*core_nets, *core_io, *price_nets, *price_io, static_cast<cudaStream_t>(stream));
     CUDA_TRY(cudaGetLastError());
     return MSCHED_OK;
 }
@@ -88,6 +57,20 @@ int msched_returns(const float *rewards, int T, int M, double gamma, int normali
     if (!rewards || !out || T < 1 || M < 0) return fail(MSCHED_E_ARG, "bad rewards/out/T/M");
     if (normalise && T < 2) return fail(MSCHED_E_ARG, "normalisation needs T >= 2");
     if (M == 0) return MSCHED_OK;
+    // TMA-tiled kernel (every reward read once) when the rows are 16-byte aligned and a [T][128] tile fits in
+    // shared memory; the streaming kernel otherwise
+    const size_t tileBytes = (size_t)T * 128 * sizeof(float);
+    if ((M & 3) == 0 && tileBytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(rewards) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        static size_t attr = 0;
+        if (tileBytes > attr) {
+            CUDA_TRY(cudaFuncSetAttribute(returns_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+            attr = 200 * 1024;
+        }
+        returns_tile_kernel<<<(M + 127) / 128, 128, tileBytes, static_cast<cudaStream_t>(stream)>>>(rewards, T, M, gamma, normalise, out);
+        CUDA_TRY(cudaGetLastError());
+        return MSCHED_OK;
+    }
     returns_kernel<<<(M + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(rewards, T, M, gamma,
                                                                                    normalise, out);
     CUDA_TRY(cudaGetLastError());

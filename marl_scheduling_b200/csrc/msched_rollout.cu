@@ -2,7 +2,10 @@
 #include <cstring>
 
 #include "abi_common.h"
+#include <cstdlib>
+
 #include "policy_step_kernel.cuh"
+#include "policy_step_tc_kernel.cuh"
 
 using namespace msched;
 
@@ -51,6 +54,34 @@ int launch(PolicyStepArgs &a, cudaStream_t s)
     return 0;
 }
 
+// the tensor-core kernel: one row per thread, 128-environment tiles
+template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P>
+int launch_tc(PolicyStepArgs &a, cudaStream_t s)
+{
+    auto fn = policy_step_tc_kernel<KW_A, AP_A, KW_O, AP_O, AP_P>;
+    const size_t smem = (size_t)PolicyStepTcSmem<KW_A, AP_A, KW_O, AP_O, AP_P>::kBytes;
+    static int perSm = 0;
+    if (!perSm) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 128, smem) != cudaSuccess || perSm < 1) perSm = 1;
+        if (perSm > 16) perSm = 16;  // 32 tensor-memory columns per CTA, 512 per SM
+    }
+    const int nTiles = (a.nEnvs + 127) / 128;
+    // per-tile cost of a unit ~ its number of nets (the per-row epilogues dominate, not the MMAs)
+    const double ca = (double)a.acc.units, co = (double)a.core.units * (AP_P > 0 ? 2.0 : 1.0);
+    const int total = g_sms * perSm;
+    int na = (int)(total * ca / (ca + co) / a.acc.units), no = (int)(total * co / (ca + co) / a.core.units);
+    na = na < 1 ? 1 : (na > nTiles ? nTiles : na);
+    no = no < 1 ? 1 : (no > nTiles ? nTiles : no);
+    a.ctasPerAccUnit = na;
+    a.ctasPerOffUnit = no;
+    fn<<<a.acc.units * na + a.core.units * no, 128, smem, s>>>(a);
+    return 0;
+}
+
 }  // namespace
 
 extern "C" int msched_policy_step(const MschedPolicyStep *ps, void *stream)
@@ -83,6 +114,23 @@ extern "C" int msched_policy_step(const MschedPolicyStep *ps, void *stream)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int ka = A.nets.n_in, aa = A.nets.n_actions, ko = O.nets.n_in, ao = O.nets.n_actions, ap = free ? P.nets.n_actions : 0;
     int rc = -1;
+    // tensor cores when the inputs are exact TF32 operands (|x| <= 2047); MSCHED_POLICY_STEP_IMPL=tc|simt forces one
+    bool tc = ps->input_bound > 0 && ps->input_bound <= 2047;
+    if (const char *e = getenv("MSCHED_POLICY_STEP_IMPL")) tc = !strcmp(e, "tc") ? true : (!strcmp(e, "simt") ? false : tc);
+    if (tc) {
+        if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && free && ap <= 16 && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
+            rc = launch_tc<8, 8, 4, 8, 16>(a, s);
+        else if (lead == 1 && ka == 27 && aa <= 16 && ko == 10 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 28) && (!O.x_used || O.x_used_stride >= 10))
+            rc = launch_tc<14, 16, 5, 8, 0>(a, s);
+        else if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
+            rc = launch_tc<8, 8, 4, 8, 0>(a, s);
+        else if (lead == 1 && ka == 11 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 12) && (!O.x_used || O.x_used_stride >= 8))
+            rc = launch_tc<6, 8, 4, 8, 0>(a, s);
+        if (rc == -2) return fail(MSCHED_E_CUDA, "msched_policy_step: shared-memory attribute rejected");
+        if (rc) return fail(MSCHED_E_ARG, "msched_policy_step: no kernel for these net shapes (use msched_actor_forward per group)");
+        CUDA_TRY(cudaGetLastError());
+        return MSCHED_OK;
+    }
     // BASELINE cfg3 (N2 C3 L3, free prices): acceptor 15 -> 7, core chooser 8 -> 4, price chooser 4 -> <= 16
     if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && free && ap <= 16 && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
         rc = launch<8, 8, 4, 8, 16>(a, s);

@@ -43,6 +43,55 @@ __global__ void returns_kernel(const float *__restrict__ r, int T, int M, double
     }
 }
 
+// ---- discounted returns, TMA-tiled -----------------------------------------------------------------
+// The same computation with every reward read from HBM ONCE: a CTA owns 128 consecutive units; one thread issues a
+// 512-byte bulk copy (cp.async.bulk, 1-D TMA) per time step, all T of them in flight at once on one mbarrier, so
+// the whole [T][128] reward tile (100 KB at T = 200) lands in shared memory at full memory-level parallelism.
+// Each thread then scans its column backwards in float64 like the Python loop, keeps G in place of r, forms the
+// moments, normalises in place, and the tile leaves with T bulk stores.  8 B/element of HBM traffic instead of 12
+// and no second float64 chain.  Needs M % 4 == 0 (16-byte rows) and T * 512 B of shared memory.
+__global__ void __launch_bounds__(128) returns_tile_kernel(const float *__restrict__ r, int T, int M, double gamma, int normalise,
+                                                           float *__restrict__ out)
+{
+    extern __shared__ __align__(128) float tile[];  // [T][128]
+    __shared__ __align__(8) uint64_t bar;
+    const int m0 = blockIdx.x * 128, tid = threadIdx.x;
+    const int cols = min(128, M - m0);  // a multiple of 4
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, (uint32_t)T * (uint32_t)cols * 4u);
+        for (int t = 0; t < T; ++t) bulk_g2s(tile + t * 128, r + (size_t)t * M + m0, (uint32_t)cols * 4u, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    if (tid < cols) {
+        double disc = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int t = T - 1; t >= 0; --t) {
+            disc = __dadd_rn((double)tile[t * 128 + tid], __dmul_rn(gamma, disc));
+            const float g = (float)disc;
+            tile[t * 128 + tid] = g;
+            s1 += (double)g;
+            s2 += (double)g * (double)g;
+        }
+        if (normalise) {
+            const float mean = (float)(s1 / T);
+            const double dm = (double)mean;
+            double var = (s2 - 2.0 * dm * s1 + (double)T * dm * dm) / (double)(T - 1);
+            if (var < 0.0) var = 0.0;
+            const float denom = (float)sqrt(var) + 1e-7f;
+#pragma unroll 8
+            for (int t = 0; t < T; ++t) tile[t * 128 + tid] = (tile[t * 128 + tid] - mean) / denom;
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        for (int t = 0; t < T; ++t) bulk_s2g(out + (size_t)t * M + m0, tile + t * 128, (uint32_t)cols * 4u);
+        bulk_commit();
+        bulk_wait_read();
+    }
+}
+
 // ---- actor forward, fp32 SIMT version --------------------------------------------------------
 // grid = (ceil(n_envs / 128), units); a CTA evaluates ONE unit (one net) for 128 consecutive
 // environments, so every lane reads the same weight at the same time (shared-memory broadcast,
@@ -249,60 +298,6 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
         else
             n1.template forward<AP>([&](int k) { return (float)xr[k]; }, lg);
         actor_epilogue(a, lg, A, row, env, unit, gsel);
-    }
-}
-
-// ---- one offer unit of the free-price agents in ONE launch --------------------------------------
-// FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): the core chooser samples a core from
-// the slot's offer observation, then the price chooser samples a price from [core prio, core rem,
-// slot prio, slot rem] of that core ([-5]*4 and a reported price of -5 for core action 0, quirk Q1).
-// Both nets of the unit are staged in shared memory and the thread that evaluated the core chooser
-// for its row goes straight on to the price chooser: the observation row is read once, the core
-// action never leaves the registers and the step needs one launch fewer.
-struct OfferUnitArgs {
-    ActorArgs core, price;  // price.x / strides are ignored (the row is the core chooser's)
-};
-
-template <int H, int AP1, int AP2>
-__global__ void __launch_bounds__(128, 6) offer_unit_forward_simt(const OfferUnitArgs q)
-{
-    extern __shared__ __align__(16) float sw[];
-    const ActorArgs &a = q.core, &b = q.price;
-    const int unit = blockIdx.y;
-    const int net1 = (unit / a.unitDiv) % a.nNets, net2 = (unit / b.unitDiv) % b.nNets;
-    const int pc1 = H * a.nIn + H + H * H + H + a.nActions * H + a.nActions;
-    const int pc2 = H * b.nIn + H + H * H + H + b.nActions * H + b.nActions;
-    SimtNet<H> n1, n2;
-    n1.carve(sw, a.nIn, a.nActions);
-    n2.carve(sw + ((SimtNet<H>::floats(a.nIn, a.nActions) + 3) & ~3), b.nIn, b.nActions);
-    n1.zero_pad();
-    n2.zero_pad();
-    __syncthreads();
-    n1.stage(a.weights + (size_t)net1 * pc1);
-    n2.stage(b.weights + (size_t)net2 * pc2);
-    __syncthreads();
-    const int nTiles = (a.nEnvs + 127) / 128;
-    for (int tile = blockIdx.x; tile < nTiles; tile += gridDim.x) {
-        const int env = tile * 128 + threadIdx.x;
-        if (env >= a.nEnvs) continue;
-        const int16_t *xr = a.x + (size_t)env * a.envStride + (size_t)unit * a.unitStride;
-        const long long row = (long long)env * a.units + unit;
-        if (a.xUsed)
-            for (int k = 0; k < a.nIn; ++k) a.xUsed[(size_t)row * a.nIn + k] = xr[k];
-        float lg1[AP1];
-        n1.template forward<AP1>([&](int k) { return (float)xr[k]; }, lg1);
-        const int gsel = actor_epilogue(a, lg1, a.nActions, row, env, unit, -1);
-        int16_t g4[4];
-        const int c2 = 2 * b.nCores;
-        if (gsel <= 0 || gsel > b.nCores) {
-            g4[0] = g4[1] = g4[2] = g4[3] = (int16_t)-5;
-        } else {
-            g4[0] = xr[2 * gsel]; g4[1] = xr[2 * gsel + 1]; g4[2] = xr[c2]; g4[3] = xr[c2 + 1];
-        }
-        if (b.xUsed) *reinterpret_cast<short4 *>(b.xUsed + (size_t)row * 4) = make_short4(g4[0], g4[1], g4[2], g4[3]);
-        float lg2[AP2];
-        n2.template forward<AP2>([&](int k) { return (float)g4[k & 3]; }, lg2);
-        actor_epilogue(b, lg2, b.nActions, row, env, unit, gsel);
     }
 }
 

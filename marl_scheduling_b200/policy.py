@@ -81,44 +81,6 @@ def _make_io(x, x_stride, units, n_envs, env_stride, seed, step, row_offset, u, 
     return io
 
 
-def offer_unit_fusable(core_group, price_group):
-    """Shapes msched_offer_unit_forward serves: the divided free-price agents' 16-wide nets."""
-    # Opt-in (MSCHED_OFFER_FUSE=1): measured on B200 at 65,536 envs the single launch is SLOWER inside the
-    # rollout step (112.9 us vs 105.5 us per step) -- the two short launches interleave better with the
-    # acceptor units running on the other stream than one launch with twice the serial work per thread.
-    if os.environ.get("MSCHED_OFFER_FUSE", "0") != "1":
-        return False
-    return (core_group.n_hidden == 16 and price_group.n_hidden == 16 and core_group.n_actions <= 16
-            and price_group.n_actions <= 16 and price_group.n_in == 4)
-
-
-def offer_unit_forward(core_group, price_group, x, x_stride, units, n_envs, n_cores, env_stride=0,
-                       seeds=(0, 0), step=0, row_offset=0, u=None, core_out=None, price_out=None,
-                       core_rec=None, price_rec=None, action_rec_stride=0, x_used=None, step_dev=None):
-    """FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332) for every offer unit in ONE launch:
-    core chooser on the offer observation row, then the price chooser on the 4 values of the chosen core.
-    u: optional pair of float32 [M] draw overrides; core_out / price_out: optional (action int32 [M],
-    logprob float32 [M]) tensors; core_rec / price_rec: int16 views into the action record; x_used: int16
-    [M][4] inputs fed to the price chooser.  Returns ((core action, core logprob), (price action, price logprob))."""
-    dev = x.device
-    M = n_envs * units
-    outs = []
-    for o in (core_out, price_out):
-        if o is None:
-            o = (torch.empty(M, dtype=torch.int32, device=dev), torch.empty(M, dtype=torch.float32, device=dev))
-        outs.append(o)
-    uu = [None, None]
-    if u is not None:
-        uu = [torch.as_tensor(v, dtype=torch.float32).to(dev).contiguous() for v in u]
-    ioc = _make_io(x, x_stride, units, n_envs, env_stride, seeds[0], step, row_offset, uu[0], outs[0][0], outs[0][1],
-                   None, core_rec, action_rec_stride, None, n_cores, None, None, step_dev)
-    iop = _make_io(x, x_stride, units, n_envs, env_stride, seeds[1], step, row_offset, uu[1], outs[1][0], outs[1][1],
-                   None, price_rec, action_rec_stride, None, n_cores, x_used, None, step_dev)
-    L.check(L.lib().msched_offer_unit_forward(C.byref(core_group.desc), C.byref(ioc), C.byref(price_group.desc),
-                                              C.byref(iop), _stream(dev)))
-    return outs[0], outs[1]
-
-
 def actor_forward(group, x, x_stride, units, n_envs, env_stride=0, seed=0, step=0, row_offset=0,
                   u=None, want_probs=False, action=None, logprob=None, action_rec=None,
                   action_rec_stride=0, gather_core=None, n_cores=0, x_used=None, timeline=None, step_dev=None):
@@ -232,7 +194,7 @@ def policy_step_supported(acceptor, core, price=None):
 
 
 def policy_step(obs, obs_stride, n_envs, n_cores, acceptor, core, price=None, action_rec=None, action_rec_stride=0,
-                env_offset=0, step=0, step_dev=None):
+                env_offset=0, step=0, step_dev=None, input_bound=0):
     """Every PPO unit of a rollout step in ONE launch (msched_policy_step): acceptor / core / price are
     MschedPolicyGroup objects from policy_step_group (price None = fixed prices)."""
     ps = L.MschedPolicyStep()
@@ -240,6 +202,7 @@ def policy_step(obs, obs_stride, n_envs, n_cores, acceptor, core, price=None, ac
     ps.action_rec = None if action_rec is None else action_rec.data_ptr()
     ps.action_rec_stride, ps.env_offset, ps.step = action_rec_stride, env_offset, step
     ps.step_dev = None if step_dev is None else step_dev.data_ptr()
+    ps.input_bound = int(input_bound)  # max |observation value| (0 = unknown): <= 2047 allows the tensor-core kernel
     ps.acceptor, ps.core = acceptor, core
     if price is not None:
         ps.price = price

@@ -10,10 +10,10 @@ from helpers import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["tc", "simt", "mma"])
+@pytest.fixture(params=["tc", "simt"])
 def actor_impl(request, monkeypatch):
-    """The actor kernels: tcgen05 tensor cores (3xTF32), fp32 SIMT, and the warp-level tensor-core kernel of
-    the 16-wide nets (shapes it does not serve fall back to the default choice)."""
+    """The per-group actor kernels: tcgen05 tensor cores (3xTF32) and fp32 SIMT (shapes one does not serve fall back
+    to the default choice)."""
     monkeypatch.setenv("MSCHED_ACTOR_IMPL", request.param)
     return request.param
 
@@ -75,45 +75,6 @@ def test_actor_forward_grouped_nets_and_strides_match_oracle(actor_impl):
         np.testing.assert_allclose(lp[n::units][sure], l[sure], rtol=1e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize("nin,A,units", [(27, 13, 16), (10, 5, 12), (4, 9, 6), (32, 16, 3), (1, 1, 1), (15, 7, 6)])
-def test_warp_mma_actor_agrees_with_the_simt_kernel(monkeypatch, nin, A, units):
-    """The warp-level tensor-core kernel (the default for 16-wide nets) against the fp32 SIMT kernel on the same
-    rows and draws: probabilities to 2e-5, identical actions wherever the draw is not within 1e-5 of a CDF step,
-    ragged row counts (tiles of 128 / 32 / 16 rows only partly filled)."""
-    import torch
-    from marl_scheduling_b200 import policy
-    dev = torch.device("cuda", 0)
-    rng = np.random.default_rng(nin * 31 + A)
-    for n_envs in (1, 17, 133, 4099):
-        stride = nin + 3
-        env_stride = units * stride + 2
-        xs = torch.as_tensor(rng.integers(-3, 40, (n_envs, env_stride)).astype(np.int16)).to(dev)
-        grp = policy.MlpGroup.random(nin, 16, A, units, dev, seed=7)
-        u = rng.random(n_envs * units).astype(np.float32)
-        out = {}
-        for impl in ("simt", "mma"):
-            monkeypatch.setenv("MSCHED_ACTOR_IMPL", impl)
-            rec = torch.full((n_envs, units + 4), 77, dtype=torch.int16, device=dev)
-            act, lp, pr = policy.actor_forward(grp, xs, stride, units, n_envs, env_stride=env_stride, u=u, want_probs=True,
-                                               action_rec=rec[:, 2:], action_rec_stride=units + 4)
-            out[impl] = (act.cpu().numpy(), lp.cpu().numpy(), pr.cpu().numpy(), rec.cpu().numpy())
-        (a1, l1, p1, r1), (a2, l2, p2, r2) = out["simt"], out["mma"]
-        np.testing.assert_allclose(p2, p1, rtol=2e-5, atol=1e-7)
-        cdf = np.cumsum(p1, 1)
-        sure = np.abs(cdf - (u * p1.sum(1))[:, None]).min(1) > 1e-5
-        assert sure.mean() > 0.99
-        assert np.array_equal(a1[sure], a2[sure])
-        np.testing.assert_allclose(l2[sure], l1[sure], rtol=1e-4, atol=2e-5)
-        assert (r2[:, :2] == 77).all() and (r2[:, 2 + units:] == 77).all()
-        assert np.array_equal(r2[:, 2:2 + units].reshape(-1)[sure], a2[sure])
-        # and the device Philox stream is the same one: same actions without the override
-        monkeypatch.setenv("MSCHED_ACTOR_IMPL", "simt")
-        b1, _, _ = policy.actor_forward(grp, xs, stride, units, n_envs, env_stride=env_stride, seed=5, step=2)
-        monkeypatch.setenv("MSCHED_ACTOR_IMPL", "mma")
-        b2, _, _ = policy.actor_forward(grp, xs, stride, units, n_envs, env_stride=env_stride, seed=5, step=2)
-        assert (b1 != b2).float().mean().item() < 1e-3
-
-
 def test_actor_sampling_is_distributionally_correct(actor_impl):
     import torch
     from marl_scheduling_b200 import policy
@@ -148,6 +109,17 @@ def test_returns_match_reference_and_oracle():
     # scan property: raw returns satisfy G_t - gamma*G_{t+1} = r_t
     raw = policy.returns(torch.as_tensor(r).to(dev), 0.5, normalise=False).cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(raw[:-1] - 0.5 * raw[1:], r[:-1], rtol=0, atol=2e-5)
+    # the TMA-tiled kernel (16-byte aligned rows, tile in shared memory) and the streaming kernel (any M, any T)
+    # do the same arithmetic: bit-equal results
+    for T, M in ((200, 5000), (57, 4096), (3, 132)):
+        r = rng.integers(-9, 15, (T, M + 1)).astype(np.float32)
+        for norm in (True, False):
+            a = policy.returns(torch.as_tensor(np.ascontiguousarray(r[:, :M])).to(dev), 0.9, normalise=norm)   # tiled
+            b = policy.returns(torch.as_tensor(r).to(dev), 0.9, normalise=norm)[:, :M]                         # M + 1: streaming
+            assert torch.equal(a, b), (T, M, norm)
+    big = rng.integers(-9, 15, (600, 256)).astype(np.float32)   # tile larger than shared memory: streaming kernel
+    np.testing.assert_allclose(policy.returns(torch.as_tensor(big).to(dev), 0.95).cpu().numpy(),
+                               O.returns(big.astype(np.float64), 0.95), rtol=1e-5, atol=1e-5)
 
 
 def test_price_chooser_gather_and_action_record(actor_impl):
@@ -191,49 +163,6 @@ def test_price_chooser_gather_and_action_record(actor_impl):
     r = rec.cpu().numpy()
     assert (r[:, :10] == 77).all() and (r[:, 10 + units:] == 77).all()
     assert np.array_equal(r[:, 10:10 + units], np.where(core == 0, -5, act))
-
-
-def test_offer_unit_single_launch_matches_two_launch_form(monkeypatch):
-    """msched_offer_unit_forward (core chooser + price chooser of every offer unit in one launch) gives
-    exactly what two msched_actor_forward calls give (src/PPOmodules.py:312-332), and the core chooser's
-    probabilities behind both agree with the oracle MLP."""
-    import torch
-    from marl_scheduling_b200 import policy
-    dev = torch.device("cuda", 0)
-    monkeypatch.setenv("MSCHED_ACTOR_IMPL", "simt")  # the single launch is the SIMT code: bit-equal to the SIMT two-launch form
-    rng = np.random.default_rng(21)
-    for n_envs, units, C, P in ((777, 6, 3, 8), (130, 12, 4, 10), (1, 2, 2, 3)):
-        row = 2 * C + 2
-        x_stride = row + (row & 1) + 2
-        env_stride = units * x_stride + 3
-        xs = torch.as_tensor(rng.integers(-1, 9, (n_envs, env_stride)).astype(np.int16)).to(dev)
-        gc = policy.MlpGroup.random(row, 16, C + 1, units, dev, seed=5)
-        gp = policy.MlpGroup.random(4, 16, P + 1, units, dev, seed=6)
-        for u in (None, (rng.random(n_envs * units).astype(np.float32), rng.random(n_envs * units).astype(np.float32))):
-            rec1 = torch.full((n_envs, 40), 77, dtype=torch.int16, device=dev)
-            rec2 = rec1.clone()
-            xu1 = torch.zeros((n_envs * units, 4), dtype=torch.int16, device=dev)
-            xu2 = torch.zeros_like(xu1)
-            ca, clp, _ = policy.actor_forward(gc, xs, x_stride, units, n_envs, env_stride=env_stride, seed=31, step=9,
-                                              u=None if u is None else u[0], action_rec=rec1[:, 3:], action_rec_stride=40)
-            pa, plp, _ = policy.actor_forward(gp, xs, x_stride, units, n_envs, env_stride=env_stride, seed=32, step=9,
-                                              u=None if u is None else u[1], action_rec=rec1[:, 20:], action_rec_stride=40,
-                                              gather_core=ca, n_cores=C, x_used=xu1)
-            (ca2, clp2), (pa2, plp2) = policy.offer_unit_forward(
-                gc, gp, xs, x_stride, units, n_envs, C, env_stride=env_stride, seeds=(31, 32), step=9, u=u,
-                core_rec=rec2[:, 3:], price_rec=rec2[:, 20:], action_rec_stride=40, x_used=xu2)
-            torch.cuda.synchronize()
-            assert torch.equal(ca, ca2) and torch.equal(pa, pa2)
-            assert torch.equal(clp, clp2) and torch.equal(plp, plp2)
-            assert torch.equal(rec1, rec2) and torch.equal(xu1, xu2)
-            r = rec2.cpu().numpy()
-            assert (r[:, 20:20 + units][ca2.view(n_envs, units).cpu().numpy() == 0] == -5).all()
-    # shapes outside the fused kernel are refused, not silently served
-    from marl_scheduling_b200._lib import MschedError
-    g32 = policy.MlpGroup.random(8, 32, 4, 2, dev, seed=1)
-    gp2 = policy.MlpGroup.random(4, 16, 5, 2, dev, seed=1)
-    with pytest.raises(MschedError):
-        policy.offer_unit_forward(g32, gp2, torch.zeros((4, 16), dtype=torch.int16, device=dev), 8, 2, 4, 3)
 
 
 @pytest.mark.parametrize("shape", [(45, 32, 343, 2), (12, 32, 64, 2), (40, 64, 1323, 1), (30, 16, 130, 3)])

@@ -31,8 +31,11 @@ def _check_group(O, w, x, u, act, lp, pr, nin, A, nets_of_unit):
         np.testing.assert_allclose(lp[:, n][sure], l[sure], rtol=1e-4, atol=2e-5)
 
 
+@pytest.mark.parametrize("impl", ["simt", "tc"])
 @pytest.mark.parametrize("key", ["cfg3_free", "cfg2_fix", "cfg2_shared", "cfg3_fix", "cfg1_fix"])
-def test_policy_step_matches_oracle_mlp(key):
+def test_policy_step_matches_oracle_mlp(key, impl, monkeypatch):
+    """Both kernels behind msched_policy_step -- fp32 SIMT and tcgen05 tensor cores (3xTF32) -- against the oracle."""
+    monkeypatch.setenv("MSCHED_POLICY_STEP_IMPL", impl)
     import torch
     from marl_scheduling_b200 import policy
     from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
@@ -77,7 +80,7 @@ def test_policy_step_matches_oracle_mlp(key):
         return A_, O_, P_
     A_, O_, P_ = groups(True)
     policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, action_rec=env.action,
-                       action_rec_stride=lay.action_halfs, env_offset=0, step=5)
+                       action_rec_stride=lay.action_halfs, env_offset=0, step=5, input_bound=16)
     torch.cuda.synchronize()
     acc_x = obs["acceptor"].reshape(B, Ua, nin_a).cpu().numpy()
     off_x = obs["offer"].reshape(B, Uo, nin_o).cpu().numpy()
@@ -105,7 +108,7 @@ def test_policy_step_matches_oracle_mlp(key):
     keep = {k: tuple(t.clone() for t in v[:2]) for k, v in out.items()}
     A_, O_, P_ = groups(False)
     off_env = 4242
-    policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, env_offset=off_env, step=9)
+    policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, env_offset=off_env, step=9, input_bound=16)
     torch.cuda.synchronize()
     drawn = {k: tuple(t.clone() for t in v[:2]) for k, v in out.items()}
     for b in (0, 1, 2, 333, 776):
@@ -119,7 +122,7 @@ def test_policy_step_matches_oracle_mlp(key):
                 if seed == 102 and free:
                     up[b, unit] = float(np.float32(int(x[2 + (b & 1)]) >> 8) * np.float32(2.0 ** -24))
     A_, O_, P_ = groups(True)
-    policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, env_offset=off_env, step=9)
+    policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, env_offset=off_env, step=9, input_bound=16)
     torch.cuda.synchronize()
     for b in (0, 1, 2, 333, 776):
         for unit in (0, Uo - 1):

@@ -14,14 +14,12 @@ shapes = [("acceptor cfg3", 15, 16, 7, 6), ("core chooser cfg3", 8, 16, 4, 6), (
           ("agg acceptor cfg3 343", 45, 32, 343, 2), ("fully agg cfg3 21952", 57, 64, 21952, 2),
           ("agg acceptor cfg2 28561", 108, 32, 28561, 4)]
 only = sys.argv[1] if len(sys.argv) > 1 else None   # e.g. "tc:acceptor cfg3"
-for impl in ("tc", "simt", "mma"):
+for impl in ("tc", "simt"):
     os.environ["MSCHED_ACTOR_IMPL"] = impl
     for name, nin, h, A, units in shapes:
         if only and only != f"{impl}:{name}":
             continue
         if A > 64 and impl == "simt":
-            continue
-        if impl == "mma" and (h != 16 or A > 16 or nin > 32):
             continue
         grp = policy.MlpGroup.random(nin, h, A, units, dev, seed=1)
         x = torch.randint(-2, 11, (B, units * nin), dtype=torch.int16, device=dev)

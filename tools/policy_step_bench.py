@@ -44,17 +44,17 @@ def run(variant, reps=30):
     O_ = policy.policy_step_group(go, Uo, lay.o_offer, lay.o_off_row, lay.a_offer_core, 2, buf["a"][1] if o else None, buf["lp"][1] if o else None, x_used=buf["xo"] if x else None)
     P_ = policy.policy_step_group(gp, Uo, lay.o_offer, lay.o_off_row, lay.a_offer_price, 3, buf["a"][2] if o else None, buf["lp"][2] if o else None, x_used=buf["xp"] if x else None) if free else None
     for i in range(3):
-        policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, action_rec=env.action, action_rec_stride=lay.action_halfs, step=i)
+        policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, action_rec=env.action, action_rec_stride=lay.action_halfs, step=i, input_bound=16)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(reps):
-        policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, action_rec=env.action, action_rec_stride=lay.action_halfs, step=i)
+        policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, action_rec=env.action, action_rec_stride=lay.action_halfs, step=i, input_bound=16)
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
     macs = Ua * (16 * (3 + 2 * NL) + 256 + 16 * (NL + 1)) + Uo * (16 * (2 * C + 2) + 256 + 16 * (C + 1)) + (Uo * (64 + 256 + 16 * (P + 1)) if free else 0)
-    print(f"{which} {variant:8s} B={B}: {us:8.1f} us  {2 * macs * B / us / 1e6:6.2f} TFLOP/s  rows/us {B * (Ua + Uo * (2 if free else 1)) / us:8.1f}", flush=True)
+    print(f"{os.environ.get('MSCHED_POLICY_STEP_IMPL', 'default'):7s} {which} {variant:8s} B={B}: {us:8.1f} us  {2 * macs * B / us / 1e6:6.2f} TFLOP/s  rows/us {B * (Ua + Uo * (2 if free else 1)) / us:8.1f}", flush=True)
 
 
 for v in ("full", "noxused", "actiononly"):
