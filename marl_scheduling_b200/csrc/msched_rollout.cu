@@ -54,31 +54,43 @@ int launch(PolicyStepArgs &a, cudaStream_t s)
     return 0;
 }
 
-// the tensor-core kernel: one row per thread, 128-environment tiles
-template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P>
+// the tensor-core kernel: one row per thread, SLOTS 128-environment tiles in flight per CTA, MINB CTAs per SM
+template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P, int SLOTS, int MINB>
 int launch_tc(PolicyStepArgs &a, cudaStream_t s)
 {
-    auto fn = policy_step_tc_kernel<KW_A, AP_A, KW_O, AP_O, AP_P>;
-    const size_t smem = (size_t)PolicyStepTcSmem<KW_A, AP_A, KW_O, AP_O, AP_P>::kBytes;
+    auto fn = policy_step_tc_kernel<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS, MINB>;
+    using SM = PolicyStepTcSmem<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS>;
+    const size_t smem = (size_t)SM::kBytes;
+    constexpr int threads = SLOTS * 128 + 32;
     static int perSm = 0;
     if (!perSm) {
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
         if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 128, smem) != cudaSuccess || perSm < 1) perSm = 1;
-        if (perSm > 16) perSm = 16;  // 32 tensor-memory columns per CTA, 512 per SM
+        // resident CTAs per SM: the launch bounds hold the registers to MINB CTAs; shared memory (dynamic + static
+        // barriers + 1 KB the system reserves per CTA) and the 512 tensor-memory columns are counted here (the
+        // occupancy API answered 1 for these kernels where ncu reports 2 or 3 resident CTAs)
+        int smemSm = 0;
+        cudaDeviceGetAttribute(&smemSm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        perSm = MINB;
+        const int bySmem = smemSm / ((int)smem + 1024 + 256);
+        if (perSm > bySmem) perSm = bySmem;
+        if (perSm > 512 / (int)SM::kTmemCols) perSm = 512 / (int)SM::kTmemCols;
+        if (perSm < 1) perSm = 1;
     }
     const int nTiles = (a.nEnvs + 127) / 128;
-    // per-tile cost of a unit ~ its number of nets (the per-row epilogues dominate, not the MMAs)
-    const double ca = (double)a.acc.units, co = (double)a.core.units * (AP_P > 0 ? 2.0 : 1.0);
+    // per-tile cost of a unit in thread instructions (the per-row epilogues dominate, not the MMAs): row load +
+    // draws + two Tanh epilogues + the sampling epilogue per net
+    const double ca = (double)a.acc.units * (14.0 * TcRows<KW_A>::NI + 70 + 300 + 110 + 6.0 * AP_A);
+    const double co = (double)a.core.units * (14.0 * TcRows<KW_O>::NI + 70 + 300 + 110 + 6.0 * AP_O + (AP_P > 0 ? 30 + 300 + 110 + 6.0 * AP_P : 0.0));
     const int total = g_sms * perSm;
     int na = (int)(total * ca / (ca + co) / a.acc.units), no = (int)(total * co / (ca + co) / a.core.units);
     na = na < 1 ? 1 : (na > nTiles ? nTiles : na);
     no = no < 1 ? 1 : (no > nTiles ? nTiles : no);
     a.ctasPerAccUnit = na;
     a.ctasPerOffUnit = no;
-    fn<<<a.acc.units * na + a.core.units * no, 128, smem, s>>>(a);
+    fn<<<a.acc.units * na + a.core.units * no, threads, smem, s>>>(a);
     return 0;
 }
 
@@ -114,18 +126,29 @@ extern "C" int msched_policy_step(const MschedPolicyStep *ps, void *stream)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int ka = A.nets.n_in, aa = A.nets.n_actions, ko = O.nets.n_in, ao = O.nets.n_actions, ap = free ? P.nets.n_actions : 0;
     int rc = -1;
-    // tensor cores when the inputs are exact TF32 operands (|x| <= 2047); MSCHED_POLICY_STEP_IMPL=tc|simt forces one
-    bool tc = ps->input_bound > 0 && ps->input_bound <= 2047;
-    if (const char *e = getenv("MSCHED_POLICY_STEP_IMPL")) tc = !strcmp(e, "tc") ? true : (!strcmp(e, "simt") ? false : tc);
+    // The tensor-core kernel needs exact TF32 inputs (|x| <= 2047).  Measured (gpurun_out/r2g_ps.log) its serial
+    // issue -> commit -> epilogue chain per layer loses to the SIMT kernel (248 vs 78 us at 65,536 envs), so it only
+    // runs when asked for: MSCHED_POLICY_STEP_IMPL=tc
+    bool tc = false;
+    if (const char *e = getenv("MSCHED_POLICY_STEP_IMPL")) tc = !strcmp(e, "tc") && ps->input_bound > 0 && ps->input_bound <= 2047;
     if (tc) {
         if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && free && ap <= 16 && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
-            rc = launch_tc<8, 8, 4, 8, 16>(a, s);
+            {
+                // tuning variants of the slot / occupancy split (MSCHED_POLICY_TC_VARIANT), cfg3 shape only
+                const char *v = getenv("MSCHED_POLICY_TC_VARIANT");
+                const int var = v ? atoi(v) : 0;
+                if (var == 1) rc = launch_tc<8, 8, 4, 8, 16, 2, 2>(a, s);
+                else if (var == 2) rc = launch_tc<8, 8, 4, 8, 16, 3, 2>(a, s);
+                else if (var == 3) rc = launch_tc<8, 8, 4, 8, 16, 4, 1>(a, s);
+                else if (var == 4) rc = launch_tc<8, 8, 4, 8, 16, 1, 4>(a, s);
+                else rc = launch_tc<8, 8, 4, 8, 16, 2, 3>(a, s);
+            }
         else if (lead == 1 && ka == 27 && aa <= 16 && ko == 10 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 28) && (!O.x_used || O.x_used_stride >= 10))
-            rc = launch_tc<14, 16, 5, 8, 0>(a, s);
+            rc = launch_tc<14, 16, 5, 8, 0, 2, 2>(a, s);
         else if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
-            rc = launch_tc<8, 8, 4, 8, 0>(a, s);
+            rc = launch_tc<8, 8, 4, 8, 0, 2, 3>(a, s);
         else if (lead == 1 && ka == 11 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 12) && (!O.x_used || O.x_used_stride >= 8))
-            rc = launch_tc<6, 8, 4, 8, 0>(a, s);
+            rc = launch_tc<6, 8, 4, 8, 0, 2, 3>(a, s);
         if (rc == -2) return fail(MSCHED_E_CUDA, "msched_policy_step: shared-memory attribute rejected");
         if (rc) return fail(MSCHED_E_ARG, "msched_policy_step: no kernel for these net shapes (use msched_actor_forward per group)");
         CUDA_TRY(cudaGetLastError());

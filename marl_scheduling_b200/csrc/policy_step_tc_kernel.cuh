@@ -1,41 +1,57 @@
-// policy_step_tc_kernel.cuh -- msched_policy_step on the 5th-generation tensor cores.
+// policy_step_tc_kernel.cuh -- msched_policy_step on the 5th-generation tensor cores, warp specialised.
 //
 // Same work and same contract as policy_step_kernel.cuh (every PPO unit of a rollout step in one launch:
-// src/PPOmodules.py:32-39,53-63,114-125,312-332), but the three Linear layers of a 128-row tile are
-// tcgen05.mma instructions with the accumulator in tensor memory; the threads only do what a matrix unit cannot:
-// int16 -> float, bias + Tanh, the hi/lo operand split, Softmax / Categorical.sample / log_prob.
+// src/PPOmodules.py:32-39,53-63,114-125,312-332).  The three Linear layers of a 128-row tile are tcgen05.mma
+// instructions with the accumulator in tensor memory; the threads only do what a matrix unit cannot:
+// int16 -> float, Tanh, the hi/lo operand split, Softmax / Categorical.sample / log_prob.
 //
-//   rows      a CTA of 128 threads serves ONE unit (an acceptor unit, or an offer unit = core chooser followed by
-//             the price chooser) and walks over 128-environment tiles; thread r = row r of the tile
+//   CTA       serves ONE unit (an acceptor unit, or an offer unit = core chooser followed by the price chooser),
+//             nets staged once as B operands; SLOTS tile slots of 128 environments are in flight at once
+//   warps     4 epilogue warps per slot (thread = row of the slot's tile = one environment) + ONE issuer warp.
+//             There is no CTA barrier in the loop: an epilogue warp that has written its rows of the next A operand
+//             arrives on the slot's `ready` mbarrier (count 4); the issuer waits for it, issues the layer's MMAs and
+//             commits them to the slot's `done` mbarrier, on which the slot's 128 threads sleep.  While one slot
+//             waits for its MMAs the other slots' warps run their epilogues: the SM's issue slots and its
+//             transcendental unit stay busy, and the MMA round trip (the whole cost of the first, serial version
+//             of this kernel: 248 us) is hidden
 //   operands  shared memory, canonical no-swizzle K-major layout (8-row x 16-byte core matrices; a K chunk of 4
 //             floats of all 128 rows is one 2 KB panel, thread r owns 16 bytes of it: conflict-free 128-bit stores)
 //   layer 1   the inputs are small integers (|x| <= 2047: exactly representable in TF32), so A needs no split:
 //             D = X * W1hi^T + X * W1lo^T, two MMAs per K step of 8
 //   layers 2,3  "3xTF32": h = hi + lo, D = Hhi*Whi^T + Hhi*Wlo^T + Hlo*Whi^T (about 2^-21 relative per product,
 //             the order of the fp32 accumulation itself)
-//   scales    2*log2(e) folded into W1, b1, W2, b2 (tanh = 1 - 2/(2^z' + 1): EX2, FADD, RCP, FFMA) and log2(e)
-//             into W3, b3 (base-2 logits for the softmax)
+//   bias      one more MMA per layer: a constant A panel [1 1 0 0 0 0 0 0] against a B chunk [b_hi b_lo 0 ...]
+//             (accumulate = 0: it also initialises the accumulator), so the epilogues neither load nor add biases
+//   scales    2*log2(e) folded into W1, b1, W2, b2 and log2(e) into W3, b3 (base-2 logits for the softmax)
+//   tanh      1 - 2/(2^z' + 1); the reciprocals of FOUR values come from ONE rcp (1/a = b*c*d / (a*b*c*d), z'
+//             clamped to 30 so that the product stays finite; tanh is 1.0f there anyway): 20 instead of 32
+//             transcendental-unit operations per row and layer -- that unit (16 lanes per clock and SM) is the
+//             bound of this kernel, not the tensor pipe
 //   loads     the observation rows of a warp's 32 environments are read warp-cooperatively (8 lanes per 32-byte
-//             row: whole sectors), converted and written straight into the layer-1 A panels; the same lanes
-//             write the experience-buffer copy of the row
+//             row: whole sectors) one tile AHEAD into registers, converted and written straight into the layer-1
+//             A panels; the same lanes write the experience-buffer copy of the row
 //   price chooser  its four inputs are picked out of the layer-1 A panels (already floats) by the sampled core
-// One elected thread issues the MMAs of a layer and commits them to an mbarrier; the CTA meets at a barrier before
-// every issue (operands written, previous accumulator read).  Several CTAs per SM (30 KB of shared memory, 32
-// tensor-memory columns each) keep the SM busy while a CTA waits for its MMAs.
 #pragma once
 #include "policy_step_kernel.cuh"
 #include "tc_primitives.cuh"
 
 namespace msched {
 
-// B operands (hi then lo) of one 16-wide net + its scaled biases, bytes
+// B operands of one 16-wide net.  Per layer: hi chunks | lo chunks | 2 bias chunks; a chunk = 4 K values of the
+// 16 output rows = 256 bytes
 template <int KC1>  // K chunks (4 floats) of layer 1; even (UMMA K = 8 for tf32)
 struct TcNetImage {
-    static constexpr int kW1 = 0, kW1Half = KC1 * 256;       // [KC1 chunks][16 rows][16 B]
-    static constexpr int kW2 = kW1 + 2 * kW1Half, kWHalf = 4 * 256;
-    static constexpr int kW3 = kW2 + 2 * kWHalf;
-    static constexpr int kBias = kW3 + 2 * kWHalf;            // b1 | b2 | b3, 16 floats each
-    static constexpr int kBytes = kBias + 48 * 4;
+    static constexpr int kL1 = 0, kL1Lo = KC1 * 256, kL1Bias = 2 * KC1 * 256;
+    static constexpr int kL2 = kL1Bias + 512, kL2Lo = kL2 + 1024, kL2Bias = kL2 + 2048;
+    static constexpr int kL3 = kL2Bias + 512, kL3Lo = kL3 + 1024, kL3Bias = kL3 + 2048;
+    static constexpr int kBytes = kL3Bias + 512;
+    __device__ static void put(unsigned char *hi, unsigned char *lo, int n, int k, float v)
+    {
+        const float h = tf32_hi(v);
+        const int off = (k >> 2) * 256 + n * 16 + (k & 3) * 4;
+        *reinterpret_cast<float *>(hi + off) = h;
+        *reinterpret_cast<float *>(lo + off) = tf32_hi(v - h);
+    }
     // all threads; W1 row position = lead + input index (the int16 position inside the row words)
     __device__ static void stage(unsigned char *s, const float *__restrict__ w, int nIn, int lead, int A)
     {
@@ -43,270 +59,368 @@ struct TcNetImage {
         const float *w2 = w + 16 * nIn + 16, *w3 = w2 + 256 + 16;
         for (int i = threadIdx.x; i < 16 * KC1 * 4; i += blockDim.x) {
             const int n = i / (KC1 * 4), pos = i - n * (KC1 * 4), k = pos - lead;
-            const float v = (k >= 0 && k < nIn) ? w[n * nIn + k] * s2 : 0.f;
-            const float hi = tf32_hi(v);
-            const int off = (pos >> 2) * 256 + n * 16 + (pos & 3) * 4;
-            *reinterpret_cast<float *>(s + kW1 + off) = hi;
-            *reinterpret_cast<float *>(s + kW1 + kW1Half + off) = tf32_hi(v - hi);
+            put(s + kL1, s + kL1Lo, n, pos, (k >= 0 && k < nIn) ? w[n * nIn + k] * s2 : 0.f);
         }
         for (int i = threadIdx.x; i < 256; i += blockDim.x) {
             const int n = i >> 4, k = i & 15;
-            const int off = (k >> 2) * 256 + n * 16 + (k & 3) * 4;
-            const float v2 = w2[n * 16 + k] * s2, h2 = tf32_hi(v2);
-            *reinterpret_cast<float *>(s + kW2 + off) = h2;
-            *reinterpret_cast<float *>(s + kW2 + kWHalf + off) = tf32_hi(v2 - h2);
-            const float v3 = n < A ? w3[n * 16 + k] * kLog2e : 0.f, h3 = tf32_hi(v3);
-            *reinterpret_cast<float *>(s + kW3 + off) = h3;
-            *reinterpret_cast<float *>(s + kW3 + kWHalf + off) = tf32_hi(v3 - h3);
+            put(s + kL2, s + kL2Lo, n, k, w2[n * 16 + k] * s2);
+            put(s + kL3, s + kL3Lo, n, k, n < A ? w3[n * 16 + k] * kLog2e : 0.f);
         }
-        float *b = reinterpret_cast<float *>(s + kBias);
-        for (int i = threadIdx.x; i < 16; i += blockDim.x) {
-            b[i] = w[16 * nIn + i] * s2;
-            b[16 + i] = w2[256 + i] * s2;
-            b[32 + i] = i < A ? w3[A * 16 + i] * kLog2e : -INFINITY;
+        // bias chunks: K position 0 = hi, 1 = lo, 2..7 = 0; logits beyond the net's A actions get -1e30 (2^x = 0)
+        for (int i = threadIdx.x; i < 16 * 8; i += blockDim.x) {
+            const int n = i >> 3, k = i & 7;
+            const float b1 = w[16 * nIn + n] * s2, b2 = w2[256 + n] * s2, b3 = n < A ? w3[A * 16 + n] * kLog2e : -1e30f;
+            const int off = (k >> 2) * 256 + n * 16 + (k & 3) * 4;
+            const float h1 = tf32_hi(b1), h2 = tf32_hi(b2), h3 = tf32_hi(b3);
+            *reinterpret_cast<float *>(s + kL1Bias + off) = k == 0 ? h1 : (k == 1 ? tf32_hi(b1 - h1) : 0.f);
+            *reinterpret_cast<float *>(s + kL2Bias + off) = k == 0 ? h2 : (k == 1 ? tf32_hi(b2 - h2) : 0.f);
+            *reinterpret_cast<float *>(s + kL3Bias + off) = k == 0 ? h3 : (k == 1 ? tf32_hi(b3 - h3) : 0.f);
         }
     }
 };
 
-// issue one layer: D[128 x 16] = A[128 x 4*KC] * W^T; aLo == 0: exact A (two MMAs per K step), else 3xTF32
-__device__ __forceinline__ void tc_issue_layer(uint32_t tmemD, uint32_t aHi, uint32_t aLo, uint32_t bHi, uint32_t bLo, int KC,
-                                               uint64_t *bar)
+// one layer of one slot: D[128 x 16] = ONES * BIAS + A[128 x 4*KC] * W^T; aLo == 0: exact A (two MMAs per K step of
+// 8), else 3xTF32.  Issued by one thread, committed to the slot's `done` barrier
+__device__ __forceinline__ void tc_issue_layer(uint32_t tmemD, uint32_t ones, uint32_t aHi, uint32_t aLo, uint32_t bHi, uint32_t bLo,
+                                               uint32_t bBias, int KC, uint64_t *bar)
 {
     constexpr uint32_t idesc = umma_idesc_tf32(128, 16);
-    uint32_t acc = 0u;
+    umma_tf32(tmemD, umma_smem_desc(ones, 2048u, 128u), umma_smem_desc(bBias, 256u, 128u), idesc, 0u);
     for (int ks = 0; ks < KC / 2; ++ks) {
         const uint64_t ah = umma_smem_desc(aHi + ks * 4096, 2048u, 128u);
         const uint64_t bh = umma_smem_desc(bHi + ks * 512, 256u, 128u);
         const uint64_t bl = umma_smem_desc(bLo + ks * 512, 256u, 128u);
-        umma_tf32(tmemD, ah, bh, idesc, acc);
+        umma_tf32(tmemD, ah, bh, idesc, 1u);
         umma_tf32(tmemD, ah, bl, idesc, 1u);
         if (aLo) umma_tf32(tmemD, umma_smem_desc(aLo + ks * 4096, 2048u, 128u), bh, idesc, 1u);
-        acc = 1u;
     }
     umma_commit(bar);
 }
 
-// accumulator row + bias -> Tanh -> hi / lo A panels of the next layer (K = 16: 4 + 4 panels of 2 KB)
-__device__ __forceinline__ void tc_hidden_epilogue(uint32_t trow, const float *__restrict__ bias, unsigned char *aH, int tid)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// an epilogue warp hands its rows of the slot to the issuer: operand stores visible to the async proxy,
+// accumulator reads done, then one arrival per warp
+__device__ __forceinline__ void tc_slot_arrive(uint64_t *ready)
+{
+    fence_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(ready);
+}
+
+__device__ __forceinline__ void tc_slot_wait(uint64_t *done, uint32_t &k)
+{
+    mbar_wait_bounded(done, k & 1u);
+    ++k;
+    tc_fence_after();
+}
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// tanh of four pre-scaled values (z2 = 2*log2(e)*z) with one reciprocal
+__device__ __forceinline__ void tanh4_scaled(float &x0, float &x1, float &x2, float &x3)
+{
+    const float e0 = ex2_approx(fminf(x0, 30.f)) + 1.f, e1 = ex2_approx(fminf(x1, 30.f)) + 1.f;
+    const float e2 = ex2_approx(fminf(x2, 30.f)) + 1.f, e3 = ex2_approx(fminf(x3, 30.f)) + 1.f;
+    const float p = e0 * e1, q = e2 * e3;
+    const float r = rcp_approx(p * q);
+    const float qr = q * r, pr = p * r;
+    x0 = fmaf(-2.f, e1 * qr, 1.f);
+    x1 = fmaf(-2.f, e0 * qr, 1.f);
+    x2 = fmaf(-2.f, e3 * pr, 1.f);
+    x3 = fmaf(-2.f, e2 * pr, 1.f);
+}
+
+// accumulator row (bias included) -> Tanh -> hi / lo A panels of the next layer (K = 16: 4 + 4 panels of 2 KB)
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t trow, unsigned char *aH, int row)
 {
     float v[16];
     tmem_ld16(trow, v);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const float4 b4 = *reinterpret_cast<const float4 *>(bias + 4 * c);
-        const float h0 = tanh_scaled(v[4 * c] + b4.x), h1 = tanh_scaled(v[4 * c + 1] + b4.y);
-        const float h2 = tanh_scaled(v[4 * c + 2] + b4.z), h3 = tanh_scaled(v[4 * c + 3] + b4.w);
+        float h0 = v[4 * c], h1 = v[4 * c + 1], h2 = v[4 * c + 2], h3 = v[4 * c + 3];
+        tanh4_scaled(h0, h1, h2, h3);
         const float i0 = tf32_hi(h0), i1 = tf32_hi(h1), i2 = tf32_hi(h2), i3 = tf32_hi(h3);
-        *reinterpret_cast<float4 *>(aH + c * 2048 + tid * 16) = make_float4(i0, i1, i2, i3);
-        *reinterpret_cast<float4 *>(aH + (4 + c) * 2048 + tid * 16) = make_float4(h0 - i0, h1 - i1, h2 - i2, h3 - i3);
+        *reinterpret_cast<float4 *>(aH + c * 2048 + row * 16) = make_float4(i0, i1, i2, i3);
+        *reinterpret_cast<float4 *>(aH + (4 + c) * 2048 + row * 16) = make_float4(h0 - i0, h1 - i1, h2 - i2, h3 - i3);
     }
 }
 
-// the barrier every MMA issue sits behind: operand stores visible to the async proxy, accumulator reads done
-__device__ __forceinline__ void tc_cta_sync()
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
 {
-    fence_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// logits of the thread's row -> sample; AP = 8 or 16 columns are read
+// logits of the thread's row (bias included, base 2) -> sample; AP = 8 or 16 columns are read
 template <int AP>
-__device__ __forceinline__ int tc_sample(uint32_t trow, const float *__restrict__ b3, int A, float u, float &logp, float *probsOut)
+__device__ __forceinline__ int tc_sample(uint32_t trow, int A, float u, float &logp, float *probsOut)
 {
-    float v[16];
-    tmem_ld16(trow, v);
     float lg[AP];
-#pragma unroll
-    for (int o = 0; o < AP; ++o) lg[o] = v[o] + b3[o];
+    if constexpr (AP == 8) tmem_ld8(trow, lg);
+    else tmem_ld16(trow, lg);
     return sample_row<AP>(lg, A, u, logp, probsOut);
 }
 
-// observation rows of the warp's 32 environments -> layer-1 A panels (floats, exact) and the experience buffer.
-// LPR lanes per row read consecutive words; the word's two values land at K positions 2w, 2w+1 of the row
+// Observation rows of a warp's 32 environments.  LPR lanes per row read consecutive words: lane = (row slot rs, word w),
+// iteration i covers rows i*RPI + rs.  fetch: global -> registers (one tile ahead); put: registers -> layer-1 A panels
+// (floats, exact; the word's two values land at K positions 2w, 2w+1 of the row) and the experience buffer
 template <int KW>
-__device__ __forceinline__ void tc_load_rows(const PolicyStepArgs &a, const PolicyGroupArgs &g, int tileEnv0, int unit, int offWords,
-                                             unsigned char *aX)
-{
-    constexpr int LPR = KW <= 2 ? 2 : KW <= 4 ? 4 : KW <= 8 ? 8 : KW <= 16 ? 16 : 32, RPI = 32 / LPR;
-    const int lane = threadIdx.x & 31, wbase = threadIdx.x & ~31;
-    const int w = lane % LPR, rs = lane / LPR;
-    const uint32_t *ob = reinterpret_cast<const uint32_t *>(a.obs);
-    const long long strideW = a.obsStride >> 1;
-    uint32_t *xu = reinterpret_cast<uint32_t *>(g.xUsed);
-    const int xuW = g.xUsedStride >> 1;
-#pragma unroll 4
-    for (int r0 = 0; r0 < 32; r0 += RPI) {
-        const int r = wbase + r0 + rs, env = tileEnv0 + r;
-        if (w < KW) {
-            const bool live = env < a.nEnvs;
-            const uint32_t v = live ? ob[(size_t)env * strideW + offWords + w] : 0u;
-            float lo, hi;
-            halves_to_float(v, lo, hi);
-            // K position 2w -> chunk w/2, element 2*(w&1); the pair is 8 aligned bytes of the row's 16-byte slot
-            *reinterpret_cast<float2 *>(aX + (w >> 1) * 2048 + r * 16 + (w & 1) * 8) = make_float2(lo, hi);
-            if (xu && live) xu[((size_t)env * g.units + unit) * xuW + w] = v;
+struct TcRows {
+    static constexpr int LPR = KW <= 2 ? 2 : KW <= 4 ? 4 : KW <= 8 ? 8 : KW <= 16 ? 16 : 32, RPI = 32 / LPR, NI = LPR;
+    __device__ static __forceinline__ void fetch(const PolicyStepArgs &a, int env0, int offWords, uint32_t (&v)[NI])
+    {
+        const int lane = threadIdx.x & 31, w = lane % LPR, rs = lane / LPR;
+        const uint32_t *ob = reinterpret_cast<const uint32_t *>(a.obs);
+        const long long strideW = a.obsStride >> 1;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+            const int env = env0 + i * RPI + rs;
+            v[i] = (w < KW && env < a.nEnvs) ? __ldg(ob + (size_t)env * strideW + offWords + w) : 0u;
         }
     }
-}
+    __device__ static __forceinline__ void put(const PolicyStepArgs &a, const PolicyGroupArgs &g, int env0, int unit, const uint32_t (&v)[NI],
+                                               unsigned char *aX, int row0)
+    {
+        const int lane = threadIdx.x & 31, w = lane % LPR, rs = lane / LPR;
+        uint32_t *xu = reinterpret_cast<uint32_t *>(g.xUsed);
+        const int xuW = g.xUsedStride >> 1;
+        if (w < KW) {
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int r = i * RPI + rs, env = env0 + r;
+                float lo, hi;
+                halves_to_float(v[i], lo, hi);
+                *reinterpret_cast<float2 *>(aX + (w >> 1) * 2048 + (row0 + r) * 16 + (w & 1) * 8) = make_float2(lo, hi);
+                if (xu && env < a.nEnvs) xu[((size_t)env * g.units + unit) * xuW + w] = v[i];
+            }
+        }
+    }
+};
 
 // KW_A / KW_O: words per acceptor / offer row (even number of K chunks after padding); AP_*: logits columns read
-template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P>
+template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P, int SLOTS>
 struct PolicyStepTcSmem {
     static constexpr int KC_A = ((2 * KW_A + 7) / 8) * 2, KC_O = ((2 * KW_O + 7) / 8) * 2;  // layer-1 K chunks, even
     static constexpr int kNetA = TcNetImage<KC_A>::kBytes;
     static constexpr int kNetO = TcNetImage<KC_O>::kBytes + (AP_P > 0 ? TcNetImage<2>::kBytes : 0);
     static constexpr int kNet = ((kNetA > kNetO ? kNetA : kNetO) + 127) & ~127;
     static constexpr int KCX = KC_A > KC_O ? KC_A : KC_O;
-    static constexpr int kAX = kNet, kAH = kAX + KCX * 2048;
-    static constexpr int kBytes = kAH + 8 * 2048;
+    static constexpr int kOnes = kNet;                     // 2 chunks: [1 1 0 0] per row, zeros
+    static constexpr int kSlot0 = kOnes + 4096;
+    static constexpr int kAH = KCX * 2048;                 // inside a slot: layer-1 panels | hidden hi (4) | hidden lo (4)
+    static constexpr int kSlotBytes = kAH + 8 * 2048;
+    static constexpr int kBytes = kSlot0 + SLOTS * kSlotBytes;
+    static constexpr uint32_t kTmemCols = SLOTS * 16 <= 32 ? 32u : (SLOTS * 16 <= 64 ? 64u : 128u);
 };
 
-template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P>
-__global__ void __launch_bounds__(128, 5) policy_step_tc_kernel(const __grid_constant__ PolicyStepArgs a)
+// the three layers of one net for the thread's row, given that the layer-1 operand has been handed over; returns the action
+template <int AP>
+__device__ __forceinline__ int tc_run_net(uint32_t trow, unsigned char *aH, int row, uint64_t *ready, uint64_t *done, uint32_t &k, int A,
+                                          float u, float &logp, float *probsOut)
 {
-    using SM = PolicyStepTcSmem<KW_A, AP_A, KW_O, AP_O, AP_P>;
+    tc_slot_wait(done, k);
+    tc_hidden_epilogue(trow, aH, row);
+    tc_slot_arrive(ready);
+    tc_slot_wait(done, k);
+    tc_hidden_epilogue(trow, aH, row);
+    tc_slot_arrive(ready);
+    tc_slot_wait(done, k);
+    return tc_sample<AP>(trow, A, u, logp, probsOut);
+}
+
+template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P, int SLOTS, int MINB>
+__global__ void __launch_bounds__(SLOTS * 128 + 32, MINB) policy_step_tc_kernel(const __grid_constant__ PolicyStepArgs a)
+{
+    using SM = PolicyStepTcSmem<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS>;
+    using NA = TcNetImage<SM::KC_A>;
+    using NO = TcNetImage<SM::KC_O>;
+    using NP = TcNetImage<2>;
     extern __shared__ __align__(128) unsigned char smc[];
-    __shared__ __align__(8) uint64_t bar;
+    __shared__ __align__(8) uint64_t barReady[SLOTS], barDone[SLOTS];
     __shared__ uint32_t tmemBase;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    unsigned char *aX = smc + SM::kAX, *aH = smc + SM::kAH;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int kIssuer = SLOTS * 4;
     const int nAccCtas = a.acc.units * a.ctasPerAccUnit;
     const bool isAcc = (int)blockIdx.x < nAccCtas;
     const int nTiles = (a.nEnvs + 127) / 128;
 
-    if (warp == 0) tmem_alloc(&tmemBase, 32u);
-    if (tid == 32) mbar_init(&bar, 1);
     int unit, slice, stride;
     if (isAcc) {
         unit = blockIdx.x / a.ctasPerAccUnit; slice = blockIdx.x - unit * a.ctasPerAccUnit; stride = a.ctasPerAccUnit;
         const PolicyGroupArgs &g = a.acc;
         const int net = (unit / g.unitDiv) % g.nNets;
         const int pc = 16 * g.nIn + 16 + 256 + 16 + 16 * g.nActions + g.nActions;
-        TcNetImage<SM::KC_A>::stage(smc, g.weights + (size_t)net * pc, g.nIn, g.xOffset & 1, g.nActions);
+        NA::stage(smc, g.weights + (size_t)net * pc, g.nIn, g.xOffset & 1, g.nActions);
     } else {
         const int id = blockIdx.x - nAccCtas;
         unit = id / a.ctasPerOffUnit; slice = id - unit * a.ctasPerOffUnit; stride = a.ctasPerOffUnit;
         const PolicyGroupArgs &g = a.core, &gp = a.price;
         const int net = (unit / g.unitDiv) % g.nNets;
         const int pc = 16 * g.nIn + 16 + 256 + 16 + 16 * g.nActions + g.nActions;
-        TcNetImage<SM::KC_O>::stage(smc, g.weights + (size_t)net * pc, g.nIn, 0, g.nActions);
+        NO::stage(smc, g.weights + (size_t)net * pc, g.nIn, 0, g.nActions);
         if constexpr (AP_P > 0) {
             const int netp = (unit / gp.unitDiv) % gp.nNets;
             const int pcp = 16 * 4 + 16 + 256 + 16 + 16 * gp.nActions + gp.nActions;
-            TcNetImage<2>::stage(smc + TcNetImage<SM::KC_O>::kBytes, gp.weights + (size_t)netp * pcp, 4, 0, gp.nActions);
+            NP::stage(smc + NO::kBytes, gp.weights + (size_t)netp * pcp, 4, 0, gp.nActions);
         }
     }
-    // zero the A panels once: K positions beyond a row's words stay zero for the whole kernel
-    for (int i = tid; i < (SM::KCX + 8) * 2048 / 16; i += 128) reinterpret_cast<uint4 *>(aX)[i] = make_uint4(0u, 0u, 0u, 0u);
-    tc_cta_sync();
+    // the constant bias operand, and zeroed A panels: K positions beyond a row's words stay zero for the whole kernel
+    for (int i = tid; i < 256; i += blockDim.x)
+        reinterpret_cast<float4 *>(smc + SM::kOnes)[i] = i < 128 ? make_float4(1.f, 1.f, 0.f, 0.f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < SLOTS * SM::kSlotBytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smc + SM::kSlot0)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == kIssuer) tmem_alloc(&tmemBase, SM::kTmemCols);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) { mbar_init(&barReady[s], 4); mbar_init(&barDone[s], 1); }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     const uint32_t tbase = tmemBase;
-    const uint32_t trow = tbase + ((uint32_t)(warp * 32) << 16);
-    const uint32_t sNet = smem_u32(smc), sAX = smem_u32(aX), sAH = smem_u32(aH);
-    uint32_t ph = 0u;
+    const int myTiles = slice < nTiles ? (nTiles - slice + stride - 1) / stride : 0;  // tiles slice, slice+stride, ...: slot s takes every SLOTS-th
+    const int lpt = (!isAcc && AP_P > 0) ? 6 : 3;                                     // layers per tile
 
-    for (int tile = slice; tile < nTiles; tile += stride) {
-        const int env = tile * 128 + tid;
-        const bool live = env < a.nEnvs;
+    if (warp == kIssuer) {
+        const uint32_t sNet = smem_u32(smc), sOnes = sNet + SM::kOnes, sSlot0 = sNet + SM::kSlot0;
+        const int maxSteps = ((myTiles + SLOTS - 1) / SLOTS) * lpt;
+        int li = 0, j = 0;
+        for (int it = 0; it < maxSteps; ++it) {
+            // operands of layer li (0..2 the unit's first net, 3..5 the price chooser)
+            uint32_t aOff, aLo, b, bLo, bBias;
+            int kc;
+            if (li == 0 || li == 3) {
+                aOff = 0u; aLo = 0u;
+                if (isAcc) { b = NA::kL1; bLo = NA::kL1Lo; bBias = NA::kL1Bias; kc = SM::KC_A; }
+                else if (li == 0) { b = NO::kL1; bLo = NO::kL1Lo; bBias = NO::kL1Bias; kc = SM::KC_O; }
+                else { b = NO::kBytes + NP::kL1; bLo = NO::kBytes + NP::kL1Lo; bBias = NO::kBytes + NP::kL1Bias; kc = 2; }
+            } else {
+                aOff = SM::kAH; aLo = SM::kAH + 4 * 2048;
+                const uint32_t base = isAcc ? 0u : (li < 3 ? 0u : (uint32_t)NO::kBytes);
+                // kL2 / kL3 offsets depend on the net's KC1
+                const bool second = (li == 1 || li == 4);
+                if (isAcc) { b = second ? NA::kL2 : NA::kL3; bLo = second ? NA::kL2Lo : NA::kL3Lo; bBias = second ? NA::kL2Bias : NA::kL3Bias; }
+                else if (li < 3) { b = second ? NO::kL2 : NO::kL3; bLo = second ? NO::kL2Lo : NO::kL3Lo; bBias = second ? NO::kL2Bias : NO::kL3Bias; }
+                else { b = second ? NP::kL2 : NP::kL3; bLo = second ? NP::kL2Lo : NP::kL3Lo; bBias = second ? NP::kL2Bias : NP::kL3Bias; }
+                b += base; bLo += base; bBias += base;
+                kc = 4;
+            }
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                if (j * SLOTS + s < myTiles) {
+                    mbar_wait_bounded(&barReady[s], (uint32_t)it & 1u);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sl = sSlot0 + s * SM::kSlotBytes;
+                        tc_issue_layer(tbase + s * 16, sOnes, sl + aOff, aLo ? sl + aLo : 0u, sNet + b, sNet + bLo, sNet + bBias, kc, &barDone[s]);
+                    }
+                    __syncwarp();
+                }
+            }
+            if (++li == lpt) { li = 0; ++j; }
+        }
+    } else {
+        const int slot = warp >> 2, wq = warp & 3, row = tid & 127;
+        unsigned char *aX = smc + SM::kSlot0 + slot * SM::kSlotBytes, *aH = aX + SM::kAH;
+        const uint32_t trow = tbase + slot * 16 + ((uint32_t)(wq * 32) << 16);
+        uint64_t *ready = &barReady[slot], *done = &barDone[slot];
+        uint32_t k = 0u;
         if (isAcc) {
-            using NI = TcNetImage<SM::KC_A>;
+            using RL = TcRows<KW_A>;
             const PolicyGroupArgs &g = a.acc;
-            const float *bias = reinterpret_cast<const float *>(smc + NI::kBias);
-            tc_load_rows<KW_A>(a, g, tile * 128, unit, (g.xOffset - (g.xOffset & 1) + unit * g.xStride) >> 1, aX);
-            tc_cta_sync();
-            if (tid == 0) tc_issue_layer(tbase, sAX, 0u, sNet + NI::kW1, sNet + NI::kW1 + NI::kW1Half, SM::KC_A, &bar);
-            float u;
-            if (g.uOverride) {
-                u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
-            } else {
-                uint32_t r[4];
-                pair_draws(a, g.seed, env, unit, r);
-                u = u24((env & 1) ? r[1] : r[0]);
+            const int offW = (g.xOffset - (g.xOffset & 1) + unit * g.xStride) >> 1;
+            uint32_t rows[RL::NI];
+            if (slot < myTiles) RL::fetch(a, (slice + slot * stride) * 128 + wq * 32, offW, rows);
+            for (int j = 0; j * SLOTS + slot < myTiles; ++j) {
+                const int tile = slice + (j * SLOTS + slot) * stride;
+                const int env = tile * 128 + row;
+                const bool live = env < a.nEnvs;
+                RL::put(a, g, tile * 128 + wq * 32, unit, rows, aX, wq * 32);
+                tc_slot_arrive(ready);
+                if ((j + 1) * SLOTS + slot < myTiles) RL::fetch(a, (tile + SLOTS * stride) * 128 + wq * 32, offW, rows);
+                float u;
+                if (g.uOverride) {
+                    u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
+                } else {
+                    uint32_t r[4];
+                    pair_draws(a, g.seed, env, unit, r);
+                    u = u24((env & 1) ? r[1] : r[0]);
+                }
+                float lp;
+                const int act = tc_run_net<AP_A>(trow, aH, row, ready, done, k, g.nActions, u, lp,
+                                                 (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
+                if (live) emit_row(a, g, env, unit, act, lp, act);
             }
-            mbar_wait_bounded(&bar, ph); ph ^= 1u; tc_fence_after();
-            tc_hidden_epilogue(trow, bias, aH, tid);
-            tc_cta_sync();
-            if (tid == 0) tc_issue_layer(tbase, sAH, sAH + 4 * 2048, sNet + NI::kW2, sNet + NI::kW2 + NI::kWHalf, 4, &bar);
-            mbar_wait_bounded(&bar, ph); ph ^= 1u; tc_fence_after();
-            tc_hidden_epilogue(trow, bias + 16, aH, tid);
-            tc_cta_sync();
-            if (tid == 0) tc_issue_layer(tbase, sAH, sAH + 4 * 2048, sNet + NI::kW3, sNet + NI::kW3 + NI::kWHalf, 4, &bar);
-            mbar_wait_bounded(&bar, ph); ph ^= 1u; tc_fence_after();
-            float lp;
-            const int act = tc_sample<AP_A>(trow, bias + 32, g.nActions, u, lp,
-                                            (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
-            if (live) emit_row(a, g, env, unit, act, lp, act);
         } else {
-            using NI = TcNetImage<SM::KC_O>;
+            using RL = TcRows<KW_O>;
             const PolicyGroupArgs &g = a.core, &gp = a.price;
-            const float *bias = reinterpret_cast<const float *>(smc + NI::kBias);
-            tc_load_rows<KW_O>(a, g, tile * 128, unit, (g.xOffset + unit * g.xStride) >> 1, aX);
-            tc_cta_sync();
-            if (tid == 0) tc_issue_layer(tbase, sAX, 0u, sNet + NI::kW1, sNet + NI::kW1 + NI::kW1Half, SM::KC_O, &bar);
-            float u, v = 0.f;
-            if (g.uOverride) {
-                u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
-                if (AP_P > 0 && gp.uOverride) v = live ? gp.uOverride[(size_t)env * gp.units + unit] : 0.f;
-            } else {
-                uint32_t r[4];
-                pair_draws(a, g.seed, env, unit, r);
-                u = u24((env & 1) ? r[1] : r[0]);
-                v = u24((env & 1) ? r[3] : r[2]);
-            }
-            mbar_wait_bounded(&bar, ph); ph ^= 1u; tc_fence_after();
-            tc_hidden_epilogue(trow, bias, aH, tid);
-            tc_cta_sync();
-            if (tid == 0) tc_issue_layer(tbase, sAH, sAH + 4 * 2048, sNet + NI::kW2, sNet + NI::kW2 + NI::kWHalf, 4, &bar);
-            mbar_wait_bounded(&bar, ph); ph ^= 1u; tc_fence_after();
-            tc_hidden_epilogue(trow, bias + 16, aH, tid);
-            tc_cta_sync();
-            if (tid == 0) tc_issue_layer(tbase, sAH, sAH + 4 * 2048, sNet + NI::kW3, sNet + NI::kW3 + NI::kWHalf, 4, &bar);
-            mbar_wait_bounded(&bar, ph); ph ^= 1u; tc_fence_after();
-            float lp;
-            const int c = tc_sample<AP_O>(trow, bias + 32, g.nActions, u, lp,
-                                          (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
-            if (live) emit_row(a, g, env, unit, c, lp, c);
-            if constexpr (AP_P > 0) {
-                // FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): [core prio, core rem, slot prio, slot rem] of
-                // the chosen core = K positions 2c, 2c+1, 2*nCores, 2*nCores+1 of the thread's own layer-1 row (floats);
-                // core action 0 feeds the dummy [-5,-5,-5,-5] and reports price -5 (quirk Q1)
-                using NP = TcNetImage<2>;
-                const unsigned char *netP = smc + NI::kBytes;
-                const float *biasP = reinterpret_cast<const float *>(netP + NP::kBias);
-                const bool dummy = c <= 0 || c > a.nCores;
-                const int cc = dummy ? 0 : c;
-                const float2 pc2 = *reinterpret_cast<const float2 *>(aX + (cc >> 1) * 2048 + tid * 16 + (cc & 1) * 8);
-                const float2 ps2 = *reinterpret_cast<const float2 *>(aX + (a.nCores >> 1) * 2048 + tid * 16 + (a.nCores & 1) * 8);
-                const float4 in = dummy ? make_float4(-5.f, -5.f, -5.f, -5.f) : make_float4(pc2.x, pc2.y, ps2.x, ps2.y);
-                if (gp.xUsed && live)
-                    *reinterpret_cast<short4 *>(gp.xUsed + ((size_t)env * gp.units + unit) * gp.xUsedStride) =
-                        make_short4((short)in.x, (short)in.y, (short)in.z, (short)in.w);
-                // (a thread only ever reads and rewrites its OWN 16-byte slots of the panels: no barrier needed here)
-                *reinterpret_cast<float4 *>(aX + tid * 16) = in;
-                *reinterpret_cast<float4 *>(aX + 2048 + tid * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
-                tc_cta_sync();
-                const uint32_t sNetP = sNet + NI::kBytes;
-                if (tid == 0) tc_issue_layer(tbase, sAX, 0u, sNetP + NP::kW1, sNetP + NP::kW1 + NP::kW1Half, 2, &bar);
-                mbar_wait_bounded(&bar, ph); ph ^= 1u; tc_fence_after();
-                tc_hidden_epilogue(trow, biasP, aH, tid);
-                tc_cta_sync();
-                if (tid == 0) tc_issue_layer(tbase, sAH, sAH + 4 * 2048, sNetP + NP::kW2, sNetP + NP::kW2 + NP::kWHalf, 4, &bar);
-                mbar_wait_bounded(&bar, ph); ph ^= 1u; tc_fence_after();
-                tc_hidden_epilogue(trow, biasP + 16, aH, tid);
-                tc_cta_sync();
-                if (tid == 0) tc_issue_layer(tbase, sAH, sAH + 4 * 2048, sNetP + NP::kW3, sNetP + NP::kW3 + NP::kWHalf, 4, &bar);
-                mbar_wait_bounded(&bar, ph); ph ^= 1u; tc_fence_after();
-                float lq;
-                const int b = tc_sample<AP_P>(trow, biasP + 32, gp.nActions, v, lq,
-                                              (gp.probs && live) ? gp.probs + ((size_t)env * gp.units + unit) * gp.nActions : nullptr);
-                if (live) emit_row(a, gp, env, unit, b, lq, c == 0 ? -5 : b);
+            const int offW = (g.xOffset + unit * g.xStride) >> 1;
+            uint32_t rows[RL::NI];
+            if (slot < myTiles) RL::fetch(a, (slice + slot * stride) * 128 + wq * 32, offW, rows);
+            for (int j = 0; j * SLOTS + slot < myTiles; ++j) {
+                const int tile = slice + (j * SLOTS + slot) * stride;
+                const int env = tile * 128 + row;
+                const bool live = env < a.nEnvs;
+                RL::put(a, g, tile * 128 + wq * 32, unit, rows, aX, wq * 32);
+                tc_slot_arrive(ready);
+                if ((j + 1) * SLOTS + slot < myTiles) RL::fetch(a, (tile + SLOTS * stride) * 128 + wq * 32, offW, rows);
+                float u, v = 0.f;
+                if (g.uOverride) {
+                    u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
+                    if (AP_P > 0 && gp.uOverride) v = live ? gp.uOverride[(size_t)env * gp.units + unit] : 0.f;
+                } else {
+                    uint32_t r[4];
+                    pair_draws(a, g.seed, env, unit, r);
+                    u = u24((env & 1) ? r[1] : r[0]);
+                    v = u24((env & 1) ? r[3] : r[2]);
+                }
+                float lp;
+                const int c = tc_run_net<AP_O>(trow, aH, row, ready, done, k, g.nActions, u, lp,
+                                               (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
+                if (live) emit_row(a, g, env, unit, c, lp, c);
+                if constexpr (AP_P > 0) {
+                    // FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): [core prio, core rem, slot prio, slot rem] of
+                    // the chosen core = K positions 2c, 2c+1, 2*nCores, 2*nCores+1 of the thread's own layer-1 row (floats);
+                    // core action 0 feeds the dummy [-5,-5,-5,-5] and reports price -5 (quirk Q1)
+                    const bool dummy = c <= 0 || c > a.nCores;
+                    const int cc = dummy ? 0 : c;
+                    const float2 pc2 = *reinterpret_cast<const float2 *>(aX + (cc >> 1) * 2048 + row * 16 + (cc & 1) * 8);
+                    const float2 ps2 = *reinterpret_cast<const float2 *>(aX + (a.nCores >> 1) * 2048 + row * 16 + (a.nCores & 1) * 8);
+                    const float4 in = dummy ? make_float4(-5.f, -5.f, -5.f, -5.f) : make_float4(pc2.x, pc2.y, ps2.x, ps2.y);
+                    if (gp.xUsed && live)
+                        *reinterpret_cast<short4 *>(gp.xUsed + ((size_t)env * gp.units + unit) * gp.xUsedStride) =
+                            make_short4((short)in.x, (short)in.y, (short)in.z, (short)in.w);
+                    // (the layer-1 MMAs of the core chooser completed long ago; a thread rewrites only its OWN 16-byte slots)
+                    *reinterpret_cast<float4 *>(aX + row * 16) = in;
+                    *reinterpret_cast<float4 *>(aX + 2048 + row * 16) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    tc_slot_arrive(ready);
+                    float lq;
+                    const int b = tc_run_net<AP_P>(trow, aH, row, ready, done, k, gp.nActions, v, lq,
+                                                   (gp.probs && live) ? gp.probs + ((size_t)env * gp.units + unit) * gp.nActions : nullptr);
+                    if (live) emit_row(a, gp, env, unit, b, lq, c == 0 ? -5 : b);
+                    __syncwarp();  // every lane has read its price inputs before the next tile's rows land in the panels
+                }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tbase, 32u);
+    if (warp == kIssuer) tmem_dealloc(tbase, SM::kTmemCols);
 }
 
 }  // namespace msched
