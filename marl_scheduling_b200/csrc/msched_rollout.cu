@@ -130,17 +130,18 @@ extern "C" int msched_policy_step(const MschedPolicyStep *ps, void *stream)
     // issue -> commit -> epilogue chain per layer loses to the SIMT kernel (248 vs 78 us at 65,536 envs), so it only
     // runs when asked for: MSCHED_POLICY_STEP_IMPL=tc
     bool tc = false;
-    if (const char *e = getenv("MSCHED_POLICY_STEP_IMPL")) tc = !strcmp(e, "tc") && ps->input_bound > 0 && ps->input_bound <= 2047;
+    if (const char *e = getenv("MSCHED_POLICY_STEP_IMPL")) tc = !strcmp(e, "tc") && ps->input_bound > 0 && ps->input_bound <= 511;
     if (tc) {
         if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && free && ap <= 16 && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
             {
                 // tuning variants of the slot / occupancy split (MSCHED_POLICY_TC_VARIANT), cfg3 shape only
                 const char *v = getenv("MSCHED_POLICY_TC_VARIANT");
                 const int var = v ? atoi(v) : 0;
-                if (var == 1) rc = launch_tc<8, 8, 4, 8, 16, 2, 2>(a, s);
+                if (var == 1) rc = launch_tc<8, 8, 4, 8, 16, 2, 4>(a, s);
                 else if (var == 2) rc = launch_tc<8, 8, 4, 8, 16, 3, 2>(a, s);
-                else if (var == 3) rc = launch_tc<8, 8, 4, 8, 16, 4, 1>(a, s);
-                else if (var == 4) rc = launch_tc<8, 8, 4, 8, 16, 1, 4>(a, s);
+                else if (var == 3) rc = launch_tc<8, 8, 4, 8, 16, 4, 2>(a, s);
+                else if (var == 4) rc = launch_tc<8, 8, 4, 8, 16, 4, 1>(a, s);
+                else if (var == 5) rc = launch_tc<8, 8, 4, 8, 16, 3, 3>(a, s);
                 else rc = launch_tc<8, 8, 4, 8, 16, 2, 3>(a, s);
             }
         else if (lead == 1 && ka == 27 && aa <= 16 && ko == 10 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 28) && (!O.x_used || O.x_used_stride >= 10))
