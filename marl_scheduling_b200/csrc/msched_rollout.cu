@@ -61,7 +61,7 @@ int launch_tc(PolicyStepArgs &a, cudaStream_t s)
     auto fn = policy_step_tc_kernel<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS, MINB>;
     using SM = PolicyStepTcSmem<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS>;
     const size_t smem = (size_t)SM::kBytes;
-    constexpr int threads = SLOTS * 128 + 32;
+    constexpr int threads = SLOTS * 128;
     static int perSm = 0;
     if (!perSm) {
         int dev = 0;
@@ -82,8 +82,8 @@ int launch_tc(PolicyStepArgs &a, cudaStream_t s)
     const int nTiles = (a.nEnvs + 127) / 128;
     // per-tile cost of a unit in thread instructions (the per-row epilogues dominate, not the MMAs): row load +
     // draws + two Tanh epilogues + the sampling epilogue per net
-    const double ca = (double)a.acc.units * (14.0 * TcRows<KW_A>::NI + 70 + 300 + 110 + 6.0 * AP_A);
-    const double co = (double)a.core.units * (14.0 * TcRows<KW_O>::NI + 70 + 300 + 110 + 6.0 * AP_O + (AP_P > 0 ? 30 + 300 + 110 + 6.0 * AP_P : 0.0));
+    const double ca = (double)a.acc.units * (14.0 * (KW_A <= 4 ? 4 : KW_A <= 8 ? 8 : 16) + 70 + 300 + 110 + 6.0 * AP_A);
+    const double co = (double)a.core.units * (14.0 * (KW_O <= 4 ? 4 : KW_O <= 8 ? 8 : 16) + 70 + 300 + 110 + 6.0 * AP_O + (AP_P > 0 ? 30 + 300 + 110 + 6.0 * AP_P : 0.0));
     const int total = g_sms * perSm;
     int na = (int)(total * ca / (ca + co) / a.acc.units), no = (int)(total * co / (ca + co) / a.core.units);
     na = na < 1 ? 1 : (na > nTiles ? nTiles : na);

@@ -1,40 +1,41 @@
-// policy_step_tc_kernel.cuh -- msched_policy_step on the 5th-generation tensor cores, warp specialised.
+// policy_step_tc_kernel.cuh -- msched_policy_step on the 5th-generation tensor cores.
 //
 // Same work and same contract as policy_step_kernel.cuh (every PPO unit of a rollout step in one launch:
 // src/PPOmodules.py:32-39,53-63,114-125,312-332).  The three Linear layers of a 128-row tile are tcgen05.mma
-// instructions with the accumulator in tensor memory; the threads only do what a matrix unit cannot:
-// int16 -> float, Tanh, the hi/lo operand split, Softmax / Categorical.sample / log_prob.
+// instructions; the threads only do what a matrix unit cannot: int16 -> fp16, Tanh, the hi/lo operand split,
+// Softmax / Categorical.sample / log_prob.
 //
 //   CTA       serves ONE unit (an acceptor unit, or an offer unit = core chooser followed by the price chooser),
-//             nets staged once as B operands; SLOTS tile slots of 128 environments are in flight at once
-//   warps     4 epilogue warps per slot (thread = row of the slot's tile = one environment) + ONE issuer warp.
-//             There is no CTA barrier in the loop: an epilogue warp that has written its rows of the next A operand
-//             arrives on the slot's `ready` mbarrier (count 4); the issuer waits for it, issues the layer's MMAs and
-//             commits them to the slot's `done` mbarrier, on which the slot's 128 threads sleep.  While one slot
-//             waits for its MMAs the other slots' warps run their epilogues: the SM's issue slots and its
-//             transcendental unit stay busy, and the MMA round trip (the whole cost of the first, serial version
-//             of this kernel: 248 us) is hidden
-//   operands  fp16 PAIRS in shared memory (kind::f16, fp32 accumulate), canonical no-swizzle K-major layout (8-row x
-//             16-byte core matrices; a K chunk of 8 halves of all 128 rows is one 2 KB panel, thread r owns 16 bytes
-//             of it: conflict-free 128-bit stores).  Every fp32 value is split v = hi + lo with hi = v cut to 11
+//             nets staged once as B operands in shared memory; SLOTS tile slots of 128 environments are in flight
+//   warps     4 warps per slot (thread = row of the slot's tile = one environment); the slots of a CTA never meet.
+//             There is no CTA barrier in the loop: a slot's 128 threads meet at the slot's NAMED barrier once their
+//             rows of the next A operand are written, one elected thread of the slot issues the layer's MMAs and
+//             commits them to the slot's `done` mbarrier, on which the slot's threads sleep.  While one slot waits
+//             for its MMAs the other slots' warps run their epilogues
+//   operands  BOTH the accumulator and the A operand live in TENSOR MEMORY (tcgen05.mma with A from tensor memory):
+//             thread r owns lane r -- it reads its accumulator row with tcgen05.ld and writes its row of the next
+//             layer's A operand with tcgen05.st, two fp16 per 32-bit column.  Nothing of the activation path goes
+//             through shared memory, so the loop has no generic -> async proxy fence (the fence is a MEMBAR that
+//             also waits for the thread's global loads and stores: with A panels in shared memory every layer of
+//             every tile stalled on the tile's row loads / experience stores -- measured 59 us, and 54 us with the
+//             MMAs taken out entirely), and an MMA no longer spends ~58 cycles reading a 4 KB A panel
+//   numerics  fp16 PAIRS (kind::f16, fp32 accumulate): every fp32 value is split v = hi + lo with hi = v cut to 11
 //             significant bits (exact in fp16) and lo = v - hi rounded to fp16: 22 bits, the products of the parts
-//             are exact in the fp32 accumulator.  One MMA covers K = 16, i.e. a whole hidden layer: the first
-//             version of this kernel used kind::tf32 (K = 8, 32-bit operands) and needed 19 MMAs per acceptor
-//             tile; ncu showed the tensor pipe 38 % busy at one CTA per SM -- each of these tiny MMAs holds it for
-//             ~58 cycles, the time to read the 4 KB A panel from shared memory -- so the MMA COUNT was the bound
+//             are exact in the fp32 accumulator.  One MMA covers K = 16, i.e. a whole hidden layer
 //   layer 1   the inputs are small integers (|x| <= 511: int16 -> fp16 exactly, by a mantissa trick on the integer
 //             pipe), so A needs no split: D = X * W1hi^T + X * W1lo^T, two MMAs per 16 inputs
 //   layers 2,3  h = hi + lo, D = Hhi*Whi^T + Hhi*Wlo^T + Hlo*Whi^T: three MMAs (about 2^-21 relative per product,
 //             the order of the fp32 accumulation itself)
-//   scales    2*log2(e) folded into W1, b1, W2, b2 and log2(e) into W3, b3 (base-2 logits for the softmax); the
-//             biases are added by the epilogues (one more MMA per layer costs more than 16 FADDs)
+//   bias      one more MMA per layer: a constant A operand [1 1 0 ...] against a B chunk [b_hi b_lo 0 ...]
+//             (accumulate = 0: it also initialises the accumulator), so the epilogues neither load nor add biases
+//   scales    2*log2(e) folded into W1, b1, W2, b2 and log2(e) into W3, b3 (base-2 logits for the softmax)
 //   tanh      1 - 2/(2^z' + 1); the reciprocals of FOUR values come from ONE rcp (1/a = b*c*d / (a*b*c*d), z'
 //             clamped to 30 so that the product stays finite; tanh is 1.0f there anyway): 20 instead of 32
 //             transcendental-unit operations per row and layer (that unit does 16 lanes per clock and SM)
 //   loads     the observation rows of a warp's 32 environments are read warp-cooperatively (8 lanes per 32-byte
-//             row: whole sectors) one tile AHEAD into registers, converted and written straight into the layer-1
-//             A panels; the same lanes write the experience-buffer copy of the row
-//   price chooser  its four inputs are picked out of the layer-1 A panels (already fp16) by the sampled core
+//             row: whole sectors) one tile AHEAD into registers, converted and transposed through a warp-private
+//             staging tile to the row's owner; the same lanes write the experience-buffer copy of the row
+//   price chooser  its four inputs are picked out of the owner's staged row (already fp16) by the sampled core
 #pragma once
 #include "policy_step_kernel.cuh"
 #include "tc_primitives.cuh"
@@ -46,17 +47,25 @@ __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N)
 {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+// D[tmem] (+)= A[tmem] * B[smem]^T: the A operand is read from tensor memory (lane = row, two fp16 per column)
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n"
         "}\n" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // two floats -> one word of two fp16 (round to nearest), `even` in the low half (the lower K index)
 __device__ __forceinline__ uint32_t pack_f16x2(float even, float odd)
 {
@@ -87,15 +96,14 @@ __device__ __forceinline__ float f16hi_to_float(uint32_t w)
     return r;
 }
 
-// B operands of one 16-wide net: per layer hi chunks | lo chunks (a chunk = 8 K values of the 16 output rows = 256
-// bytes of fp16), then the scaled biases b1 | b2 | b3 as floats (b3 = -inf beyond the net's A actions)
+// B operands of one 16-wide net: per layer hi chunks | lo chunks | 2 bias chunks (a chunk = 8 K values of the 16
+// output rows = 256 bytes of fp16; the bias chunks hold b_hi, b_lo at K positions 0, 1)
 template <int KC1>  // K chunks (8 halves) of layer 1; even (UMMA K = 16 for fp16)
 struct TcNetImage {
-    static constexpr int kL1 = 0, kL1Lo = KC1 * 256;
-    static constexpr int kL2 = 2 * KC1 * 256, kL2Lo = kL2 + 512;
-    static constexpr int kL3 = kL2 + 1024, kL3Lo = kL3 + 512;
-    static constexpr int kBias = kL3 + 1024;
-    static constexpr int kBytes = kBias + 48 * 4;
+    static constexpr int kL1 = 0, kL1Lo = KC1 * 256, kL1Bias = 2 * KC1 * 256;
+    static constexpr int kL2 = kL1Bias + 512, kL2Lo = kL2 + 512, kL2Bias = kL2 + 1024;
+    static constexpr int kL3 = kL2Bias + 512, kL3Lo = kL3 + 512, kL3Bias = kL3 + 1024;
+    static constexpr int kBytes = kL3Bias + 512;
     __device__ static void put(unsigned char *hi, unsigned char *lo, int n, int k, float v)
     {
         const float h = tf32_hi(v);  // 13 low mantissa bits cleared: 11 significant bits, exact in fp16
@@ -117,52 +125,70 @@ struct TcNetImage {
             put(s + kL2, s + kL2Lo, n, k, w2[n * 16 + k] * s2);
             put(s + kL3, s + kL3Lo, n, k, n < A ? w3[n * 16 + k] * kLog2e : 0.f);
         }
-        float *b = reinterpret_cast<float *>(s + kBias);
-        for (int i = threadIdx.x; i < 16; i += blockDim.x) {
-            b[i] = w[16 * nIn + i] * s2;
-            b[16 + i] = w2[256 + i] * s2;
-            b[32 + i] = i < A ? w3[A * 16 + i] * kLog2e : -INFINITY;
+        // bias chunks: K position 0 = hi, 1 = lo, 2..15 = 0; logits beyond the net's A actions get -60000 (2^x = 0)
+        for (int i = threadIdx.x; i < 16 * 16; i += blockDim.x) {
+            const int n = i >> 4, k = i & 15;
+            const float b1 = w[16 * nIn + n] * s2, b2 = w2[256 + n] * s2, b3 = n < A ? w3[A * 16 + n] * kLog2e : -60000.f;
+            const int off = (k >> 3) * 256 + n * 16 + (k & 7) * 2;
+            const float h1 = tf32_hi(b1), h2 = tf32_hi(b2), h3 = tf32_hi(b3);
+            *reinterpret_cast<unsigned short *>(s + kL1Bias + off) = k == 0 ? f16_bits(h1) : (k == 1 ? f16_bits(b1 - h1) : (unsigned short)0);
+            *reinterpret_cast<unsigned short *>(s + kL2Bias + off) = k == 0 ? f16_bits(h2) : (k == 1 ? f16_bits(b2 - h2) : (unsigned short)0);
+            *reinterpret_cast<unsigned short *>(s + kL3Bias + off) = k == 0 ? f16_bits(h3) : (k == 1 ? f16_bits(b3 - h3) : (unsigned short)0);
         }
     }
 };
 
-// one layer of one slot: D[128 x 16] = A[128 x 8*KC] * W^T with W = hi + lo; aLo == 0: exact A (two MMAs per K step
-// of 16), else A = hi + lo as well (three).  Issued by one thread, committed to the slot's `done` barrier
-__device__ __forceinline__ void tc_issue_layer(uint32_t tmemD, uint32_t aHi, uint32_t aLo, uint32_t bHi, uint32_t bLo, int KC, uint64_t *bar)
+// one layer of one slot: D[128 x 16] = ONES * BIAS + A[128 x 16*KS] * W^T with W = hi + lo; aLo == 0: exact A (two
+// MMAs per K step of 16), else A = hi + lo as well (three).  A operands are tensor-memory columns (8 per K step).
+// Issued by one thread, committed to the slot's `done` barrier
+__device__ __forceinline__ void tc_issue_layer(uint32_t tmemD, uint32_t ones, uint32_t aHi, uint32_t aLo, uint32_t bHi, uint32_t bLo,
+                                               uint32_t bBias, int KS, uint64_t *bar)
 {
     constexpr uint32_t idesc = umma_idesc_f16(128, 16);
-    uint32_t acc = 0u;
-    for (int ks = 0; ks < KC / 2; ++ks) {
-        const uint64_t ah = umma_smem_desc(aHi + ks * 4096, 2048u, 128u);
+    umma_f16_ts(tmemD, ones, umma_smem_desc(bBias, 256u, 128u), idesc, 0u);
+    for (int ks = 0; ks < KS; ++ks) {
         const uint64_t bh = umma_smem_desc(bHi + ks * 512, 256u, 128u);
         const uint64_t bl = umma_smem_desc(bLo + ks * 512, 256u, 128u);
-        umma_f16(tmemD, ah, bh, idesc, acc);
-        umma_f16(tmemD, ah, bl, idesc, 1u);
-        if (aLo) umma_f16(tmemD, umma_smem_desc(aLo + ks * 4096, 2048u, 128u), bh, idesc, 1u);
-        acc = 1u;
+        umma_f16_ts(tmemD, aHi + ks * 8, bh, idesc, 1u);
+        umma_f16_ts(tmemD, aHi + ks * 8, bl, idesc, 1u);
+        if (aLo) umma_f16_ts(tmemD, aLo + ks * 8, bh, idesc, 1u);
     }
     umma_commit(bar);
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+// the slot's 128 threads have written their rows of the next A operand into tensor memory and read the accumulator:
+// they meet at the slot's named barrier, then one thread of the slot's first warp issues
+__device__ __forceinline__ void tc_slot_issue(int slot, uint32_t tmemD, uint32_t ones, uint32_t aHi, uint32_t aLo, uint32_t bHi, uint32_t bLo,
+                                              uint32_t bBias, int KS, uint64_t *done)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-// an epilogue warp hands its rows of the slot to the issuer: operand stores visible to the async proxy,
-// accumulator reads done, then one arrival per warp
-__device__ __forceinline__ void tc_slot_arrive(uint64_t *ready)
-{
-    fence_async_smem();
+    tmem_st_wait();
     tc_fence_before();
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbar_arrive(ready);
+    asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory");
+    if ((threadIdx.x & 127) < 32) {
+        tc_fence_after();
+        if ((threadIdx.x & 31) == 0) tc_issue_layer(tmemD, ones, aHi, aLo, bHi, bLo, bBias, KS, done);
+        __syncwarp();
+    }
 }
 
+// sleep on the slot's `done` barrier (the hardware suspends the thread up to the hint); a lost completion traps
 __device__ __forceinline__ void tc_slot_wait(uint64_t *done, uint32_t &k)
 {
-    mbar_wait_bounded(done, k & 1u);
+    const uint32_t addr = smem_u32(done), parity = k & 1u;
     ++k;
+    uint32_t ok = 0u;
+#pragma unroll 1
+    for (int it = 0; it < (1 << 16) && !ok; ++it)
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity), "r"(20000u)
+            : "memory");
+    if (!ok) __trap();
     tc_fence_after();
 }
 
@@ -187,25 +213,22 @@ __device__ __forceinline__ void tanh4_scaled(float &x0, float &x1, float &x2, fl
     x3 = fmaf(-2.f, e2 * pr, 1.f);
 }
 
-// accumulator row + bias -> Tanh -> hi / lo A panels of the next layer (K = 16 halves: 2 + 2 panels of 2 KB)
-__device__ __forceinline__ void tc_hidden_epilogue(uint32_t trow, const float *__restrict__ bias, unsigned char *aH, int row)
+// accumulator row (bias included) -> Tanh -> the thread's row of the next layer's hi / lo operands (8 + 8 columns)
+__device__ __forceinline__ void tc_hidden_epilogue(uint32_t trow, uint32_t aHrow)
 {
     float v[16];
     tmem_ld16(trow, v);
     uint32_t hi[8], lo[8];
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        const float4 b4 = *reinterpret_cast<const float4 *>(bias + 4 * c);
-        float h0 = v[4 * c] + b4.x, h1 = v[4 * c + 1] + b4.y, h2 = v[4 * c + 2] + b4.z, h3 = v[4 * c + 3] + b4.w;
+        float h0 = v[4 * c], h1 = v[4 * c + 1], h2 = v[4 * c + 2], h3 = v[4 * c + 3];
         tanh4_scaled(h0, h1, h2, h3);
         const float i0 = tf32_hi(h0), i1 = tf32_hi(h1), i2 = tf32_hi(h2), i3 = tf32_hi(h3);
         hi[2 * c] = pack_f16x2(i0, i1); hi[2 * c + 1] = pack_f16x2(i2, i3);
         lo[2 * c] = pack_f16x2(h0 - i0, h1 - i1); lo[2 * c + 1] = pack_f16x2(h2 - i2, h3 - i3);
     }
-    *reinterpret_cast<uint4 *>(aH + row * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4 *>(aH + 2048 + row * 16) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
-    *reinterpret_cast<uint4 *>(aH + 4096 + row * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-    *reinterpret_cast<uint4 *>(aH + 6144 + row * 16) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    tmem_st8(aHrow, hi);
+    tmem_st8(aHrow + 8, lo);
 }
 
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
@@ -219,94 +242,146 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// logits of the thread's row (base 2) -> sample; AP = 8 or 16 columns are read
+// logits of the thread's row (bias included, base 2) -> sample; AP = 8 or 16 columns are read
 template <int AP>
-__device__ __forceinline__ int tc_sample(uint32_t trow, const float *__restrict__ b3, int A, float u, float &logp, float *probsOut)
+__device__ __forceinline__ int tc_sample(uint32_t trow, int A, float u, float &logp, float *probsOut)
 {
     float lg[AP];
     if constexpr (AP == 8) tmem_ld8(trow, lg);
     else tmem_ld16(trow, lg);
-#pragma unroll
-    for (int o = 0; o < AP; ++o) lg[o] += b3[o];
     return sample_row<AP>(lg, A, u, logp, probsOut);
 }
 
 // Observation rows of a warp's 32 environments.  LPR lanes per row read consecutive words: lane = (row slot rs, word w),
-// iteration i covers rows i*RPI + rs.  fetch: global -> registers (one tile ahead); put: registers -> layer-1 A panels
-// (fp16, exact; the word's two values land at K positions 2w, 2w+1 of the row) and the experience buffer
-template <int KW>
+// iteration i covers rows i*RPI + rs.  fetch: global -> registers (one tile ahead); put: registers -> fp16 pairs (exact;
+// the word's two values are K positions 2w, 2w+1 of the row) into the warp's staging tile [32 rows][SW words] and the
+// experience buffer; the row's owner then moves its row into tensor memory.  The per-lane parts of the addresses
+// are formed once per kernel, a tile adds its base and a row step per iteration
+template <int KW, int SW>
 struct TcRows {
     static constexpr int LPR = KW <= 2 ? 2 : KW <= 4 ? 4 : KW <= 8 ? 8 : KW <= 16 ? 16 : 32, RPI = 32 / LPR, NI = LPR;
-    __device__ static __forceinline__ void fetch(const PolicyStepArgs &a, int env0, int offWords, uint32_t (&v)[NI])
+    const uint32_t *src;   // obs + rs * strideW + offWords + w
+    uint32_t *dst;         // xUsed + (rs * units + unit) * xuW + w, or null
+    size_t srcEnv, dstEnv;  // words per environment
+    int w, rs;
+    __device__ __forceinline__ TcRows(const PolicyStepArgs &a, const PolicyGroupArgs &g, int unit, int offWords)
     {
-        const int lane = threadIdx.x & 31, w = lane % LPR, rs = lane / LPR;
-        const uint32_t *ob = reinterpret_cast<const uint32_t *>(a.obs);
-        const long long strideW = a.obsStride >> 1;
+        const int lane = threadIdx.x & 31;
+        w = lane % LPR; rs = lane / LPR;
+        srcEnv = (size_t)(a.obsStride >> 1);
+        src = reinterpret_cast<const uint32_t *>(a.obs) + (size_t)rs * srcEnv + offWords + w;
+        dstEnv = (size_t)g.units * (size_t)(g.xUsedStride >> 1);
+        dst = g.xUsed ? reinterpret_cast<uint32_t *>(g.xUsed) + (size_t)rs * dstEnv + (size_t)unit * (g.xUsedStride >> 1) + w : nullptr;
+    }
+    __device__ __forceinline__ void fetch(int nEnvs, int env0, uint32_t (&v)[NI]) const
+    {
+        const uint32_t *p = src + (size_t)env0 * srcEnv;
+        const size_t step = (size_t)RPI * srcEnv;
+        if (w < KW) {
+            if (env0 + 32 <= nEnvs) {
 #pragma unroll
-        for (int i = 0; i < NI; ++i) {
-            const int env = env0 + i * RPI + rs;
-            v[i] = (w < KW && env < a.nEnvs) ? __ldg(ob + (size_t)env * strideW + offWords + w) : 0u;
+                for (int i = 0; i < NI; ++i) v[i] = __ldg(p + i * step);
+            } else {
+#pragma unroll
+                for (int i = 0; i < NI; ++i) v[i] = (env0 + i * RPI + rs < nEnvs) ? __ldg(p + i * step) : 0u;
+            }
         }
     }
-    __device__ static __forceinline__ void put(const PolicyStepArgs &a, const PolicyGroupArgs &g, int env0, int unit, const uint32_t (&v)[NI],
-                                               unsigned char *aX, int row0)
+    // stage: this warp's [32][SW] words
+    __device__ __forceinline__ void put(int nEnvs, int env0, const uint32_t (&v)[NI], uint32_t *stage) const
     {
-        const int lane = threadIdx.x & 31, w = lane % LPR, rs = lane / LPR;
-        uint32_t *xu = reinterpret_cast<uint32_t *>(g.xUsed);
-        const int xuW = g.xUsedStride >> 1;
         if (w < KW) {
+            uint32_t *sp = stage + rs * SW + w;
 #pragma unroll
-            for (int i = 0; i < NI; ++i) {
-                const int r = i * RPI + rs, env = env0 + r;
-                *reinterpret_cast<uint32_t *>(aX + (w >> 2) * 2048 + (row0 + r) * 16 + (w & 3) * 4) = halves_to_f16x2(v[i]);
-                if (xu && env < a.nEnvs) xu[((size_t)env * g.units + unit) * xuW + w] = v[i];
+            for (int i = 0; i < NI; ++i) sp[i * RPI * SW] = halves_to_f16x2(v[i]);
+            if (dst) {
+                uint32_t *q = dst + (size_t)env0 * dstEnv;
+                const size_t step = (size_t)RPI * dstEnv;
+                if (env0 + 32 <= nEnvs) {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) q[i * step] = v[i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < NI; ++i)
+                        if (env0 + i * RPI + rs < nEnvs) q[i * step] = v[i];
+                }
             }
         }
     }
 };
 
+// the owner's staged row -> its lane of the layer-1 operand columns (SW words = SW / 8 K steps)
+template <int SW>
+__device__ __forceinline__ void tc_row_to_tmem(const uint32_t *stageRow, uint32_t aXrow)
+{
+#pragma unroll
+    for (int q = 0; q < SW / 8; ++q) {
+        const uint4 x0 = *reinterpret_cast<const uint4 *>(stageRow + 8 * q), x1 = *reinterpret_cast<const uint4 *>(stageRow + 8 * q + 4);
+        const uint32_t r[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        tmem_st8(aXrow + 8 * q, r);
+    }
+}
+
 // KW_A / KW_O: words per acceptor / offer row; AP_*: logits columns read
 template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P, int SLOTS>
 struct PolicyStepTcSmem {
-    static constexpr int KC_A = ((2 * KW_A + 15) / 16) * 2, KC_O = ((2 * KW_O + 15) / 16) * 2;  // layer-1 K chunks of 8, even
-    static constexpr int kNetA = TcNetImage<KC_A>::kBytes;
-    static constexpr int kNetO = TcNetImage<KC_O>::kBytes + (AP_P > 0 ? TcNetImage<2>::kBytes : 0);
+    static constexpr int KS_A = (2 * KW_A + 15) / 16, KS_O = (2 * KW_O + 15) / 16;  // layer-1 K steps of 16
+    static constexpr int kNetA = TcNetImage<2 * KS_A>::kBytes;
+    static constexpr int kNetO = TcNetImage<2 * KS_O>::kBytes + (AP_P > 0 ? TcNetImage<2>::kBytes : 0);
     static constexpr int kNet = ((kNetA > kNetO ? kNetA : kNetO) + 127) & ~127;
-    static constexpr int KCX = KC_A > KC_O ? KC_A : KC_O;
-    static constexpr int kSlot0 = kNet;
-    static constexpr int kAH = KCX * 2048;                 // inside a slot: layer-1 panels | hidden hi (2) | hidden lo (2)
-    static constexpr int kSlotBytes = kAH + 4 * 2048;
-    static constexpr int kBytes = kSlot0 + SLOTS * kSlotBytes;
-    static constexpr uint32_t kTmemCols = SLOTS * 16 <= 32 ? 32u : (SLOTS * 16 <= 64 ? 64u : 128u);
+    static constexpr int KSX = KS_A > KS_O ? KS_A : KS_O;
+    static constexpr int SW = 8 * KSX;                      // staged words per row
+    static constexpr int kStage = kNet;                     // [SLOTS * 4 warps][32 rows][SW] words
+    static constexpr int kBytes = kStage + SLOTS * 128 * SW * 4;
+    // tensor-memory columns of a slot: accumulator 16 | hidden hi 8 | hidden lo 8 | layer-1 operand 8 per K step
+    static constexpr int kColsH = 16, kColsX = 32, kSlotCols = 32 + 8 * KSX;
+    static constexpr int kColsOnes = SLOTS * kSlotCols;     // 8 columns [1 1 0 ...] shared by the slots
+    static constexpr int kColsUsed = kColsOnes + 8;
+    static constexpr uint32_t kTmemCols = kColsUsed <= 32 ? 32u : (kColsUsed <= 64 ? 64u : (kColsUsed <= 128 ? 128u : 256u));
 };
 
-// the three layers of one net for the thread's row, given that the layer-1 operand has been handed over; returns the action
-template <int AP>
-__device__ __forceinline__ int tc_run_net(uint32_t trow, const float *__restrict__ bias, unsigned char *aH, int row, uint64_t *ready,
-                                          uint64_t *done, uint32_t &k, int A, float u, float &logp, float *probsOut)
+// what one slot needs to run a net: its accumulator and operand columns, the CTA's constant operand
+struct TcSlot {
+    int slot;
+    uint32_t tmemD, tOnes;  // lane 0 addresses (the issuing thread's view)
+    uint32_t trow;          // the thread's lane of the slot's columns
+    uint64_t *done;
+    uint32_t k;
+};
+
+// layer 1 of a net (B image NI at shared address sNet): the operand is in the slot's layer-1 columns (ks1 K steps)
+template <class NI, int COLS_X>
+__device__ __forceinline__ void tc_issue_l1(TcSlot &t, uint32_t sNet, int ks1)
 {
-    tc_slot_wait(done, k);
-    tc_hidden_epilogue(trow, bias, aH, row);
-    tc_slot_arrive(ready);
-    tc_slot_wait(done, k);
-    tc_hidden_epilogue(trow, bias + 16, aH, row);
-    tc_slot_arrive(ready);
-    tc_slot_wait(done, k);
-    return tc_sample<AP>(trow, bias + 32, A, u, logp, probsOut);
+    tc_slot_issue(t.slot, t.tmemD, t.tOnes, t.tmemD + COLS_X, 0u, sNet + NI::kL1, sNet + NI::kL1Lo, sNet + NI::kL1Bias, ks1, t.done);
+}
+
+// the rest of the net for the thread's row, layer 1 being under way; returns the action
+template <int AP, class NI>
+__device__ __forceinline__ int tc_run_net(TcSlot &t, uint32_t sNet, int A, float u, float &logp, float *probsOut)
+{
+    tc_slot_wait(t.done, t.k);
+    tc_hidden_epilogue(t.trow, t.trow + 16);
+    tc_slot_issue(t.slot, t.tmemD, t.tOnes, t.tmemD + 16, t.tmemD + 24, sNet + NI::kL2, sNet + NI::kL2Lo, sNet + NI::kL2Bias, 1, t.done);
+    tc_slot_wait(t.done, t.k);
+    tc_hidden_epilogue(t.trow, t.trow + 16);
+    tc_slot_issue(t.slot, t.tmemD, t.tOnes, t.tmemD + 16, t.tmemD + 24, sNet + NI::kL3, sNet + NI::kL3Lo, sNet + NI::kL3Bias, 1, t.done);
+    tc_slot_wait(t.done, t.k);
+    return tc_sample<AP>(t.trow, A, u, logp, probsOut);
 }
 
 template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P, int SLOTS, int MINB>
-__global__ void __launch_bounds__(SLOTS * 128 + 32, MINB) policy_step_tc_kernel(const __grid_constant__ PolicyStepArgs a)
+__global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const __grid_constant__ PolicyStepArgs a)
 {
     using SM = PolicyStepTcSmem<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS>;
-    using NA = TcNetImage<SM::KC_A>;
-    using NO = TcNetImage<SM::KC_O>;
+    using NA = TcNetImage<2 * SM::KS_A>;
+    using NO = TcNetImage<2 * SM::KS_O>;
     using NP = TcNetImage<2>;
+    constexpr int SW = SM::SW;
     extern __shared__ __align__(128) unsigned char smc[];
-    __shared__ __align__(8) uint64_t barReady[SLOTS], barDone[SLOTS];
+    __shared__ __align__(8) uint64_t barDone[SLOTS];
     __shared__ uint32_t tmemBase;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int kIssuer = SLOTS * 4;
     const int nAccCtas = a.acc.units * a.ctasPerAccUnit;
     const bool isAcc = (int)blockIdx.x < nAccCtas;
     const int nTiles = (a.nEnvs + 127) / 128;
@@ -331,145 +406,121 @@ __global__ void __launch_bounds__(SLOTS * 128 + 32, MINB) policy_step_tc_kernel(
             NP::stage(smc + NO::kBytes, gp.weights + (size_t)netp * pcp, 4, 0, gp.nActions);
         }
     }
-    // zeroed A panels: K positions beyond a row's words stay zero for the whole kernel
-    for (int i = tid; i < SLOTS * SM::kSlotBytes / 16; i += blockDim.x) reinterpret_cast<uint4 *>(smc + SM::kSlot0)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (warp == kIssuer) tmem_alloc(&tmemBase, SM::kTmemCols);
-    if (tid == 0) {
+    // zeroed staging tiles: words beyond a row's KW stay zero for the whole kernel
+    for (int i = tid; i < SLOTS * 128 * SW / 4; i += blockDim.x) reinterpret_cast<uint4 *>(smc + SM::kStage)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (warp == 0) tmem_alloc(&tmemBase, SM::kTmemCols);
+    if (tid == 32) {
 #pragma unroll
-        for (int s = 0; s < SLOTS; ++s) { mbar_init(&barReady[s], 4); mbar_init(&barDone[s], 1); }
+        for (int s = 0; s < SLOTS; ++s) mbar_init(&barDone[s], 1);
     }
-    fence_async_smem();
+    fence_async_smem();  // the B images are read by the MMAs (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tbase = tmemBase;
+    const int wq = warp & 3;
+    const uint32_t laneSel = (uint32_t)(wq * 32) << 16;
+    if (warp < 4) {  // the constant bias operand: fp16 1.0 (0x3c00) at K positions 0, 1 of every row
+        const uint32_t ones[8] = {0x3c003c00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st8(tmemBase + SM::kColsOnes + laneSel, ones);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
     const int myTiles = slice < nTiles ? (nTiles - slice + stride - 1) / stride : 0;  // tiles slice, slice+stride, ...: slot s takes every SLOTS-th
-    const int lpt = (!isAcc && AP_P > 0) ? 6 : 3;                                     // layers per tile
 
-    if (warp == kIssuer) {
-        const uint32_t sNet = smem_u32(smc), sSlot0 = sNet + SM::kSlot0;
-        const int maxSteps = ((myTiles + SLOTS - 1) / SLOTS) * lpt;
-        int li = 0, j = 0;
-        for (int it = 0; it < maxSteps; ++it) {
-            // operands of layer li (0..2 the unit's first net, 3..5 the price chooser)
-            uint32_t aOff, aLo, b, bLo;
-            int kc;
-            if (li == 0 || li == 3) {
-                aOff = 0u; aLo = 0u;
-                if (isAcc) { b = NA::kL1; bLo = NA::kL1Lo; kc = SM::KC_A; }
-                else if (li == 0) { b = NO::kL1; bLo = NO::kL1Lo; kc = SM::KC_O; }
-                else { b = NO::kBytes + NP::kL1; bLo = NO::kBytes + NP::kL1Lo; kc = 2; }
+    TcSlot t;
+    t.slot = warp >> 2;
+    const int row = tid & 127;
+    const uint32_t sNet = smem_u32(smc);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(smc + SM::kStage) + warp * 32 * SW;  // this warp's rows
+    const uint32_t *stageRow = stage + lane * SW;
+    t.tmemD = tmemBase + t.slot * SM::kSlotCols;
+    t.tOnes = tmemBase + SM::kColsOnes;
+    t.trow = t.tmemD + laneSel;
+    t.done = &barDone[t.slot];
+    t.k = 0u;
+    if (isAcc) {
+        const PolicyGroupArgs &g = a.acc;
+        const TcRows<KW_A, SW> rl(a, g, unit, (g.xOffset - (g.xOffset & 1) + unit * g.xStride) >> 1);
+        uint32_t rows[TcRows<KW_A, SW>::NI];
+        if (t.slot < myTiles) rl.fetch(a.nEnvs, (slice + t.slot * stride) * 128 + wq * 32, rows);
+        for (int j = 0; j * SLOTS + t.slot < myTiles; ++j) {
+            const int tile = slice + (j * SLOTS + t.slot) * stride;
+            const int env = tile * 128 + row;
+            const bool live = env < a.nEnvs;
+            __syncwarp();
+            rl.put(a.nEnvs, tile * 128 + wq * 32, rows, stage);
+            __syncwarp();
+            tc_row_to_tmem<8 * SM::KS_A>(stageRow, t.trow + SM::kColsX);
+            tc_issue_l1<NA, SM::kColsX>(t, sNet, SM::KS_A);
+            if ((j + 1) * SLOTS + t.slot < myTiles) rl.fetch(a.nEnvs, (tile + SLOTS * stride) * 128 + wq * 32, rows);
+            float u;
+            if (g.uOverride) {
+                u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
             } else {
-                aOff = SM::kAH; aLo = SM::kAH + 2 * 2048;
-                const bool second = (li == 1 || li == 4);
-                if (isAcc) { b = second ? NA::kL2 : NA::kL3; bLo = second ? NA::kL2Lo : NA::kL3Lo; }
-                else if (li < 3) { b = second ? NO::kL2 : NO::kL3; bLo = second ? NO::kL2Lo : NO::kL3Lo; }
-                else { b = NO::kBytes + (second ? NP::kL2 : NP::kL3); bLo = NO::kBytes + (second ? NP::kL2Lo : NP::kL3Lo); }
-                kc = 2;
+                uint32_t r[4];
+                pair_draws(a, g.seed, env, unit, r);
+                u = u24((env & 1) ? r[1] : r[0]);
             }
-#pragma unroll
-            for (int s = 0; s < SLOTS; ++s) {
-                if (j * SLOTS + s < myTiles) {
-                    mbar_wait_bounded(&barReady[s], (uint32_t)it & 1u);
-                    tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t sl = sSlot0 + s * SM::kSlotBytes;
-                        tc_issue_layer(tbase + s * 16, sl + aOff, aLo ? sl + aLo : 0u, sNet + b, sNet + bLo, kc, &barDone[s]);
-                    }
-                    __syncwarp();
-                }
-            }
-            if (++li == lpt) { li = 0; ++j; }
+            float lp;
+            const int act = tc_run_net<AP_A, NA>(t, sNet, g.nActions, u, lp,
+                                                 (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
+            if (live) emit_row(a, g, env, unit, act, lp, act);
         }
     } else {
-        const int slot = warp >> 2, wq = warp & 3, row = tid & 127;
-        unsigned char *aX = smc + SM::kSlot0 + slot * SM::kSlotBytes, *aH = aX + SM::kAH;
-        const uint32_t trow = tbase + slot * 16 + ((uint32_t)(wq * 32) << 16);
-        uint64_t *ready = &barReady[slot], *done = &barDone[slot];
-        uint32_t k = 0u;
-        if (isAcc) {
-            using RL = TcRows<KW_A>;
-            const PolicyGroupArgs &g = a.acc;
-            const float *bias = reinterpret_cast<const float *>(smc + NA::kBias);
-            const int offW = (g.xOffset - (g.xOffset & 1) + unit * g.xStride) >> 1;
-            uint32_t rows[RL::NI];
-            if (slot < myTiles) RL::fetch(a, (slice + slot * stride) * 128 + wq * 32, offW, rows);
-            for (int j = 0; j * SLOTS + slot < myTiles; ++j) {
-                const int tile = slice + (j * SLOTS + slot) * stride;
-                const int env = tile * 128 + row;
-                const bool live = env < a.nEnvs;
-                RL::put(a, g, tile * 128 + wq * 32, unit, rows, aX, wq * 32);
-                tc_slot_arrive(ready);
-                if ((j + 1) * SLOTS + slot < myTiles) RL::fetch(a, (tile + SLOTS * stride) * 128 + wq * 32, offW, rows);
-                float u;
-                if (g.uOverride) {
-                    u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
-                } else {
-                    uint32_t r[4];
-                    pair_draws(a, g.seed, env, unit, r);
-                    u = u24((env & 1) ? r[1] : r[0]);
-                }
-                float lp;
-                const int act = tc_run_net<AP_A>(trow, bias, aH, row, ready, done, k, g.nActions, u, lp,
-                                                 (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
-                if (live) emit_row(a, g, env, unit, act, lp, act);
+        const PolicyGroupArgs &g = a.core, &gp = a.price;
+        const TcRows<KW_O, SW> rl(a, g, unit, (g.xOffset + unit * g.xStride) >> 1);
+        uint32_t rows[TcRows<KW_O, SW>::NI];
+        if (t.slot < myTiles) rl.fetch(a.nEnvs, (slice + t.slot * stride) * 128 + wq * 32, rows);
+        for (int j = 0; j * SLOTS + t.slot < myTiles; ++j) {
+            const int tile = slice + (j * SLOTS + t.slot) * stride;
+            const int env = tile * 128 + row;
+            const bool live = env < a.nEnvs;
+            __syncwarp();  // (every lane has read its price inputs from the staging tile)
+            rl.put(a.nEnvs, tile * 128 + wq * 32, rows, stage);
+            __syncwarp();
+            tc_row_to_tmem<8 * SM::KS_O>(stageRow, t.trow + SM::kColsX);
+            tc_issue_l1<NO, SM::kColsX>(t, sNet, SM::KS_O);
+            if ((j + 1) * SLOTS + t.slot < myTiles) rl.fetch(a.nEnvs, (tile + SLOTS * stride) * 128 + wq * 32, rows);
+            float u, v = 0.f;
+            if (g.uOverride) {
+                u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
+                if (AP_P > 0 && gp.uOverride) v = live ? gp.uOverride[(size_t)env * gp.units + unit] : 0.f;
+            } else {
+                uint32_t r[4];
+                pair_draws(a, g.seed, env, unit, r);
+                u = u24((env & 1) ? r[1] : r[0]);
+                v = u24((env & 1) ? r[3] : r[2]);
             }
-        } else {
-            using RL = TcRows<KW_O>;
-            const PolicyGroupArgs &g = a.core, &gp = a.price;
-            const float *bias = reinterpret_cast<const float *>(smc + NO::kBias);
-            const int offW = (g.xOffset + unit * g.xStride) >> 1;
-            uint32_t rows[RL::NI];
-            if (slot < myTiles) RL::fetch(a, (slice + slot * stride) * 128 + wq * 32, offW, rows);
-            for (int j = 0; j * SLOTS + slot < myTiles; ++j) {
-                const int tile = slice + (j * SLOTS + slot) * stride;
-                const int env = tile * 128 + row;
-                const bool live = env < a.nEnvs;
-                RL::put(a, g, tile * 128 + wq * 32, unit, rows, aX, wq * 32);
-                tc_slot_arrive(ready);
-                if ((j + 1) * SLOTS + slot < myTiles) RL::fetch(a, (tile + SLOTS * stride) * 128 + wq * 32, offW, rows);
-                float u, v = 0.f;
-                if (g.uOverride) {
-                    u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
-                    if (AP_P > 0 && gp.uOverride) v = live ? gp.uOverride[(size_t)env * gp.units + unit] : 0.f;
-                } else {
-                    uint32_t r[4];
-                    pair_draws(a, g.seed, env, unit, r);
-                    u = u24((env & 1) ? r[1] : r[0]);
-                    v = u24((env & 1) ? r[3] : r[2]);
-                }
-                float lp;
-                const int c = tc_run_net<AP_O>(trow, bias, aH, row, ready, done, k, g.nActions, u, lp,
+            float lp;
+            const int c = tc_run_net<AP_O, NO>(t, sNet, g.nActions, u, lp,
                                                (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
-                if (live) emit_row(a, g, env, unit, c, lp, c);
-                if constexpr (AP_P > 0) {
-                    // FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): [core prio, core rem, slot prio, slot rem] of
-                    // the chosen core = row words c and nCores of the thread's own layer-1 row (fp16 pairs); core action 0
-                    // feeds the dummy [-5,-5,-5,-5] and reports price -5 (quirk Q1)
-                    const float *biasP = reinterpret_cast<const float *>(smc + NO::kBytes + NP::kBias);
-                    const bool dummy = c <= 0 || c > a.nCores;
-                    const int cc = dummy ? 0 : c;
-                    const uint32_t wc = *reinterpret_cast<const uint32_t *>(aX + (cc >> 2) * 2048 + row * 16 + (cc & 3) * 4);
-                    const uint32_t ws = *reinterpret_cast<const uint32_t *>(aX + (a.nCores >> 2) * 2048 + row * 16 + (a.nCores & 3) * 4);
-                    const uint32_t in0 = dummy ? 0xc500c500u : wc, in1 = dummy ? 0xc500c500u : ws;  // fp16 -5
-                    if (gp.xUsed && live)
-                        *reinterpret_cast<short4 *>(gp.xUsed + ((size_t)env * gp.units + unit) * gp.xUsedStride) =
-                            make_short4((short)f16lo_to_float(in0), (short)f16hi_to_float(in0), (short)f16lo_to_float(in1), (short)f16hi_to_float(in1));
-                    // (the layer-1 MMAs of the core chooser completed long ago; a thread rewrites only its OWN 16-byte slots)
-                    *reinterpret_cast<uint4 *>(aX + row * 16) = make_uint4(in0, in1, 0u, 0u);
-                    *reinterpret_cast<uint4 *>(aX + 2048 + row * 16) = make_uint4(0u, 0u, 0u, 0u);
-                    tc_slot_arrive(ready);
-                    float lq;
-                    const int b = tc_run_net<AP_P>(trow, biasP, aH, row, ready, done, k, gp.nActions, v, lq,
+            if (live) emit_row(a, g, env, unit, c, lp, c);
+            if constexpr (AP_P > 0) {
+                // FreePriceOfferPPO.selectAction (src/PPOmodules.py:312-332): [core prio, core rem, slot prio, slot rem] of
+                // the chosen core = words c and nCores of the thread's own staged row (fp16 pairs); core action 0 feeds
+                // the dummy [-5,-5,-5,-5] and reports price -5 (quirk Q1)
+                const bool dummy = c <= 0 || c > a.nCores;
+                const uint32_t wc = stageRow[dummy ? 0 : c], ws = stageRow[a.nCores];
+                const uint32_t in0 = dummy ? 0xc500c500u : wc, in1 = dummy ? 0xc500c500u : ws;  // fp16 -5
+                if (gp.xUsed && live)
+                    *reinterpret_cast<short4 *>(gp.xUsed + ((size_t)env * gp.units + unit) * gp.xUsedStride) =
+                        make_short4((short)f16lo_to_float(in0), (short)f16hi_to_float(in0), (short)f16lo_to_float(in1), (short)f16hi_to_float(in1));
+                // (the layer-1 MMAs of the core chooser completed long ago)
+                const uint32_t px[8] = {in0, in1, 0u, 0u, 0u, 0u, 0u, 0u};
+                tmem_st8(t.trow + SM::kColsX, px);
+                tc_issue_l1<NP, SM::kColsX>(t, sNet + NO::kBytes, 1);
+                float lq;
+                const int b = tc_run_net<AP_P, NP>(t, sNet + NO::kBytes, gp.nActions, v, lq,
                                                    (gp.probs && live) ? gp.probs + ((size_t)env * gp.units + unit) * gp.nActions : nullptr);
-                    if (live) emit_row(a, gp, env, unit, b, lq, c == 0 ? -5 : b);
-                }
+                if (live) emit_row(a, gp, env, unit, b, lq, c == 0 ? -5 : b);
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kIssuer) tmem_dealloc(tbase, SM::kTmemCols);
+    if (warp == 0) tmem_dealloc(tmemBase, SM::kTmemCols);
 }
 
 }  // namespace msched
