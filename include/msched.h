@@ -346,8 +346,8 @@ int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, vo
  * words 0,1 serve the even / odd environment's acceptor or core-chooser row, words 2,3 their price-chooser rows;
  * u = (x >> 8) * 2^-24.  env_offset (global index of env 0) must be even.  u_override float32 [n_envs][units]
  * replaces the draws (parity tests).  Unsupported net shapes return MSCHED_E_ARG: use msched_actor_forward.
- * Two kernels serve the call with the same contract: tcgen05 tensor cores (3xTF32; needs input_bound <= 2047) and
- * fp32 SIMT; MSCHED_POLICY_STEP_IMPL=tc|simt forces one. */
+ * Two kernels serve the call with the same contract: tcgen05 tensor cores (fp16 hi/lo operand pairs, fp32
+ * accumulate; needs 0 < input_bound <= 511) and fp32 SIMT; MSCHED_POLICY_STEP_IMPL=tc|simt forces one. */
 typedef struct MschedPolicyGroup {
     MschedMlpGroup nets;
     int32_t units, x_offset, x_stride, rec_offset;
@@ -370,8 +370,8 @@ typedef struct MschedPolicyStep {
     uint64_t step;
     const uint64_t *step_dev; /* optional device step counter (CUDA-graph replays) */
     MschedPolicyGroup acceptor, core, price;
-    int32_t input_bound;      /* the caller's bound on |observation value| (priorities, prices, lengths); 1..2047 lets the
-                                 tensor-core kernel take the inputs as exact TF32 operands, 0 = unknown (fp32 SIMT kernel) */
+    int32_t input_bound;      /* the caller's bound on |observation value| (priorities, prices, lengths); 1..511 lets the
+                                 tensor-core kernel take the inputs as exact fp16 operands, 0 = unknown (fp32 SIMT kernel) */
     int32_t reserved;
 } MschedPolicyStep;
 

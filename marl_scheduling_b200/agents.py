@@ -260,7 +260,7 @@ class BatchedPPO:
 
 def _input_bound(world):
     """Largest |value| an observation can hold (priorities, remaining lengths, prices, the -1/-2/-5 markers): lets
-    msched_policy_step take the inputs as exact TF32 operands when it is at most 2047."""
+    msched_policy_step take the inputs as exact fp16 operands (tensor-core kernel) when it is at most 511."""
     vals = [5] + [abs(int(v)) for v in world.possibleJobPriorities] + [abs(int(v)) for v in world.possibleJobLengths]
     if not world.freePrices:
         vals += [abs(int(v)) for v in world.listOfFixPrices]

@@ -80,10 +80,12 @@ int launch_tc(PolicyStepArgs &a, cudaStream_t s)
         if (perSm < 1) perSm = 1;
     }
     const int nTiles = (a.nEnvs + 127) / 128;
-    // per-tile cost of a unit in thread instructions (the per-row epilogues dominate, not the MMAs): row load +
-    // draws + two Tanh epilogues + the sampling epilogue per net
-    const double ca = (double)a.acc.units * (14.0 * (KW_A <= 4 ? 4 : KW_A <= 8 ? 8 : 16) + 70 + 300 + 110 + 6.0 * AP_A);
-    const double co = (double)a.core.units * (14.0 * (KW_O <= 4 ? 4 : KW_O <= 8 ? 8 : 16) + 70 + 300 + 110 + 6.0 * AP_O + (AP_P > 0 ? 30 + 300 + 110 + 6.0 * AP_P : 0.0));
+    // per-tile cost of a unit in thread instructions, from the ncu instruction counts (profiles/r02_policy_step_tc*):
+    // row load + draws + emit, and per net two Tanh epilogues (175 each), the sampling epilogue, three issue / wait rounds
+    constexpr double kNet8 = 350 + 130 + 36, kNet16 = 350 + 190 + 36;
+    const double ca = (double)a.acc.units * (8.0 * (KW_A <= 4 ? 4 : KW_A <= 8 ? 8 : 16) + 85 + (AP_A > 8 ? kNet16 : kNet8));
+    const double co = (double)a.core.units * (8.0 * (KW_O <= 4 ? 4 : KW_O <= 8 ? 8 : 16) + 85 + (AP_O > 8 ? kNet16 : kNet8) +
+                                              (AP_P > 0 ? 35 + (AP_P > 8 ? kNet16 : kNet8) : 0.0));
     const int total = g_sms * perSm;
     int na = (int)(total * ca / (ca + co) / a.acc.units), no = (int)(total * co / (ca + co) / a.core.units);
     na = na < 1 ? 1 : (na > nTiles ? nTiles : na);
@@ -126,30 +128,23 @@ extern "C" int msched_policy_step(const MschedPolicyStep *ps, void *stream)
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int ka = A.nets.n_in, aa = A.nets.n_actions, ko = O.nets.n_in, ao = O.nets.n_actions, ap = free ? P.nets.n_actions : 0;
     int rc = -1;
-    // The tensor-core kernel needs exact TF32 inputs (|x| <= 2047).  Measured (gpurun_out/r2g_ps.log) its serial
-    // issue -> commit -> epilogue chain per layer loses to the SIMT kernel (248 vs 78 us at 65,536 envs), so it only
-    // runs when asked for: MSCHED_POLICY_STEP_IMPL=tc
-    bool tc = false;
-    if (const char *e = getenv("MSCHED_POLICY_STEP_IMPL")) tc = !strcmp(e, "tc") && ps->input_bound > 0 && ps->input_bound <= 511;
+    // The tensor-core kernel takes the observations as exact fp16 operands (|x| <= 511: the caller states its bound in
+    // input_bound); anything else runs the fp32 SIMT kernel.  MSCHED_POLICY_STEP_IMPL=tc|simt forces one (the parity
+    // tests run both).  Measured at 65,536 envs, cfg3 / cfg2 shapes: 57 / 109 us tensor cores, 86 / 225 us SIMT
+    bool tc = ps->input_bound > 0 && ps->input_bound <= 511;
+    if (const char *e = getenv("MSCHED_POLICY_STEP_IMPL")) {
+        if (!strcmp(e, "simt")) tc = false;
+        else if (!strcmp(e, "tc") && !tc) return fail(MSCHED_E_ARG, "MSCHED_POLICY_STEP_IMPL=tc needs 0 < input_bound <= 511");
+    }
     if (tc) {
         if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && free && ap <= 16 && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
-            {
-                // tuning variants of the slot / occupancy split (MSCHED_POLICY_TC_VARIANT), cfg3 shape only
-                const char *v = getenv("MSCHED_POLICY_TC_VARIANT");
-                const int var = v ? atoi(v) : 0;
-                if (var == 1) rc = launch_tc<8, 8, 4, 8, 16, 2, 4>(a, s);
-                else if (var == 2) rc = launch_tc<8, 8, 4, 8, 16, 3, 2>(a, s);
-                else if (var == 3) rc = launch_tc<8, 8, 4, 8, 16, 4, 2>(a, s);
-                else if (var == 4) rc = launch_tc<8, 8, 4, 8, 16, 4, 1>(a, s);
-                else if (var == 5) rc = launch_tc<8, 8, 4, 8, 16, 3, 3>(a, s);
-                else rc = launch_tc<8, 8, 4, 8, 16, 2, 3>(a, s);
-            }
+            rc = launch_tc<8, 8, 4, 8, 16, 4, 2>(a, s);
         else if (lead == 1 && ka == 27 && aa <= 16 && ko == 10 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 28) && (!O.x_used || O.x_used_stride >= 10))
-            rc = launch_tc<14, 16, 5, 8, 0, 2, 2>(a, s);
+            rc = launch_tc<14, 16, 5, 8, 0, 4, 2>(a, s);
         else if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
-            rc = launch_tc<8, 8, 4, 8, 0, 2, 3>(a, s);
+            rc = launch_tc<8, 8, 4, 8, 0, 4, 2>(a, s);
         else if (lead == 1 && ka == 11 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 12) && (!O.x_used || O.x_used_stride >= 8))
-            rc = launch_tc<6, 8, 4, 8, 0, 2, 3>(a, s);
+            rc = launch_tc<6, 8, 4, 8, 0, 4, 2>(a, s);
         if (rc == -2) return fail(MSCHED_E_CUDA, "msched_policy_step: shared-memory attribute rejected");
         if (rc) return fail(MSCHED_E_ARG, "msched_policy_step: no kernel for these net shapes (use msched_actor_forward per group)");
         CUDA_TRY(cudaGetLastError());

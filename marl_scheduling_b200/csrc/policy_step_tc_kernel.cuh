@@ -171,23 +171,29 @@ __device__ __forceinline__ void tc_slot_issue(int slot, uint32_t tmemD, uint32_t
     }
 }
 
-// sleep on the slot's `done` barrier (the hardware suspends the thread up to the hint); a lost completion traps
-__device__ __forceinline__ void tc_slot_wait(uint64_t *done, uint32_t &k)
+// sleep on the slot's `done` barrier: one try_wait (the hardware suspends the thread up to the hint) almost always
+// suffices; the retry loop is bounded and traps on a lost completion instead of hanging the device
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint32_t addr, uint32_t parity, uint32_t ns)
 {
-    const uint32_t addr = smem_u32(done), parity = k & 1u;
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity), "r"(ns)
+        : "memory");
+    return ok;
+}
+__device__ __forceinline__ void tc_slot_wait(uint32_t doneAddr, uint32_t &k)
+{
+    const uint32_t parity = k & 1u;
     ++k;
     uint32_t ok = 0u;
 #pragma unroll 1
-    for (int it = 0; it < (1 << 16) && !ok; ++it)
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity), "r"(20000u)
-            : "memory");
+    for (int it = 0; it < (1 << 16) && !ok; ++it) ok = mbar_try_wait_hint(doneAddr, parity, 20000u);
     if (!ok) __trap();
     tc_fence_after();
 }
@@ -346,7 +352,7 @@ struct TcSlot {
     uint32_t tmemD, tOnes;  // lane 0 addresses (the issuing thread's view)
     uint32_t trow;          // the thread's lane of the slot's columns
     uint64_t *done;
-    uint32_t k;
+    uint32_t doneAddr, k;
 };
 
 // layer 1 of a net (B image NI at shared address sNet): the operand is in the slot's layer-1 columns (ks1 K steps)
@@ -360,13 +366,13 @@ __device__ __forceinline__ void tc_issue_l1(TcSlot &t, uint32_t sNet, int ks1)
 template <int AP, class NI>
 __device__ __forceinline__ int tc_run_net(TcSlot &t, uint32_t sNet, int A, float u, float &logp, float *probsOut)
 {
-    tc_slot_wait(t.done, t.k);
+    tc_slot_wait(t.doneAddr, t.k);
     tc_hidden_epilogue(t.trow, t.trow + 16);
     tc_slot_issue(t.slot, t.tmemD, t.tOnes, t.tmemD + 16, t.tmemD + 24, sNet + NI::kL2, sNet + NI::kL2Lo, sNet + NI::kL2Bias, 1, t.done);
-    tc_slot_wait(t.done, t.k);
+    tc_slot_wait(t.doneAddr, t.k);
     tc_hidden_epilogue(t.trow, t.trow + 16);
     tc_slot_issue(t.slot, t.tmemD, t.tOnes, t.tmemD + 16, t.tmemD + 24, sNet + NI::kL3, sNet + NI::kL3Lo, sNet + NI::kL3Bias, 1, t.done);
-    tc_slot_wait(t.done, t.k);
+    tc_slot_wait(t.doneAddr, t.k);
     return tc_sample<AP>(t.trow, A, u, logp, probsOut);
 }
 
@@ -439,6 +445,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
     t.tOnes = tmemBase + SM::kColsOnes;
     t.trow = t.tmemD + laneSel;
     t.done = &barDone[t.slot];
+    t.doneAddr = smem_u32(t.done);
     t.k = 0u;
     if (isAcc) {
         const PolicyGroupArgs &g = a.acc;

@@ -202,7 +202,7 @@ def policy_step(obs, obs_stride, n_envs, n_cores, acceptor, core, price=None, ac
     ps.action_rec = None if action_rec is None else action_rec.data_ptr()
     ps.action_rec_stride, ps.env_offset, ps.step = action_rec_stride, env_offset, step
     ps.step_dev = None if step_dev is None else step_dev.data_ptr()
-    ps.input_bound = int(input_bound)  # max |observation value| (0 = unknown): <= 2047 allows the tensor-core kernel
+    ps.input_bound = int(input_bound)  # max |observation value| (0 = unknown): 1..511 allows the tensor-core kernel
     ps.acceptor, ps.core = acceptor, core
     if price is not None:
         ps.price = price

@@ -126,6 +126,7 @@ def test_dqn_env_loop_learns_something():
     env = SE.DQNDividedFixedPricesEnv(world, params)
     accO, offO, aucO = env.reset()
     before = env.agents.acceptor.policy.detach().clone()
+    changed = 0
     for t in range(12):
         oldA, oldO = accO, offO   # the reference's `old = new` idiom: step() returns views that stay valid one more step
         acceptorActions, offerActions = env.getActionForAllAgents(accO, offO)
@@ -137,7 +138,9 @@ def test_dqn_env_loop_learns_something():
         l2 = env.updateAcceptorMemoriesAndOptimize(oldA, actA, accO, accR[..., 0])
         assert l1 is not None and l2 is not None
         assert bool(torch.isfinite(l1).all()) and bool(torch.isfinite(l2).all())
-        assert oldA.data_ptr() != accO.data_ptr() and not torch.equal(oldA, accO)
+        assert oldA.data_ptr() != accO.data_ptr() and oldO.data_ptr() != offO.data_ptr()   # no aliasing of old and new
+        changed += int(not torch.equal(oldA, accO)) + int(not torch.equal(oldO, offO))
+    assert changed > 6   # (the first acceptor observations are all "empty core, no offers": equal but distinct buffers)
     env.agents.updateTargetNets()
     assert not torch.equal(before, env.agents.acceptor.policy.detach())
     assert torch.equal(env.agents.acceptor.target, env.agents.acceptor.policy.detach())
