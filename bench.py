@@ -480,7 +480,19 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout on the first communicator: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
 
     dom, mode = cfg["dom"], cfg["mode"]
     B = args.envs or cfg["envs"]
@@ -489,6 +501,7 @@ def main():
         args.obs = cfg["obs"]
     dense = args.obs == "dense"
     compact = args.obs == "compact"
+    serial_us = None
 
     def make_env(k):
         return BatchedSchedulingEnv(B, world_params_from_dom(dom, mode.startswith("free")), reward=mode,
@@ -542,16 +555,17 @@ def main():
             for e in envs:
                 e.set_device_round(True)  # world.round in a device counter: a block can be replayed from a graph
 
-        def launch_block(n):
+        def launch_block(n, strs=None):
+            strs = strs or streams
             cur = torch.cuda.current_stream(dev)
             fork = torch.cuda.Event()
             fork.record(cur)
-            for st in streams:
+            for st in strs:
                 st.wait_event(fork)
             for i in range(n):
-                with torch.cuda.stream(streams[(i % S) % len(streams)]):
+                with torch.cuda.stream(strs[(i % S) % len(strs)]):
                     step_on(envs[i % S], recs[i], results[i % S])
-            for st in streams:
+            for st in strs:
                 join = torch.cuda.Event()
                 join.record(st)
                 cur.wait_event(join)
@@ -560,22 +574,23 @@ def main():
         # captured ONCE in a CUDA graph (its action records are refreshed in place between replays)
         graphs = {}
 
-        def block_graph(n):
-            if n not in graphs:
-                launch_block(n)  # warm-up outside the capture
+        def block_graph(n, strs=None):
+            key = (n, len(strs or streams))
+            if key not in graphs:
+                launch_block(n, strs)  # warm-up outside the capture
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 cap = torch.cuda.Stream(device=dev)
                 cap.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(cap):
                     with torch.cuda.graph(g, stream=cap):
-                        launch_block(n)
+                        launch_block(n, strs)
                 torch.cuda.current_stream(dev).wait_stream(cap)
-                graphs[n] = g
-            return graphs[n]
+                graphs[key] = g
+            return graphs[key]
 
-        def run_block(n, timed):
-            g = block_graph(n) if use_graph else None
+        def run_block(n, timed, strs=None):
+            g = block_graph(n, strs) if use_graph else None
             for r in recs[:n]:
                 refresh_actions(env, r, gen)
             if timed is not None:
@@ -583,7 +598,7 @@ def main():
             if g is not None:
                 g.replay()
             else:
-                launch_block(n)
+                launch_block(n, strs)
             if timed is not None:
                 timed[1].record()
 
@@ -613,6 +628,16 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         tot_ms = stepk_ms = float(t[0])
         obs_us = None
+        # the same launches strictly one after the other on ONE stream (what a single dependent rollout sees)
+        if len(streams) > 1 and rank == 0:
+            one = streams[:1]
+            run_block(S * G, None, one)
+            evs = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(6)]
+            torch.cuda.synchronize()
+            for e in evs:
+                run_block(S * G, e, one)
+            torch.cuda.synchronize()
+            serial_us = 1e3 * sum(e[0].elapsed_time(e[1]) for e in evs) / (len(evs) * S * G)
         l2_note = (f"inputs larger than L2: {S} shards x {per_set / 1e6:.0f} MB visited round-robin, launches "
                    f"in blocks of {S * G} on {len(streams)} stream(s)" + (", each block one CUDA-graph replay" if use_graph else ""))
         n_launch = K
@@ -1007,7 +1032,9 @@ def main():
                      "peak_source": peak_src, "algorithmic_bytes_per_env_step": alg_bytes,
                      "algorithmic_bytes_formula": "2S+a+r" + ("+o (dense observations)" if fused else
                                                               ("+o_c (compact observations)" if one_launch_compact else "")),
-                     "units_per_launch": B, "launch_us": step_launch_s * 1e6},
+                     "units_per_launch": B, "launch_us": step_launch_s * 1e6,
+                     "serial_launch_us": serial_us,
+                     "serial_frac": (alg_bytes * B / (serial_us * 1e-6) / 1e9 / peak) if serial_us else None},
         "kernels": {"step_us": 1e3 * stepk_ms / K, "observe_us": obs_us,
                     "observe_algorithmic_bytes_per_env": ab["obs"] + ab["state"]},
         "cpu_baseline": cpu,

@@ -161,14 +161,14 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
             uint32_t x[4];
-            env_draw(p, env, kStreamTie, (uint32_t)c, 0u, x);
+            env_draw_at(p, round, env, kStreamTie, (uint32_t)c, 0u, x);
             scr[D::X_TIE + 4 * c] = x[0]; scr[D::X_TIE + 4 * c + 1] = x[1];
             scr[D::X_TIE + 4 * c + 2] = x[2]; scr[D::X_TIE + 4 * c + 3] = x[3];
         }
     }
     if (w == 1 % R && spawnMode == MSCHED_SPAWN_PHILOX) {
         uint32_t x[4];
-        env_draw(p, env, kStreamSpawn, 0u, 0u, x);
+        env_draw_at(p, round, env, kStreamSpawn, 0u, 0u, x);
         scr[D::X_SPAWN] = x[0]; scr[D::X_SPAWN + 1] = x[1]; scr[D::X_SPAWN + 2] = x[2]; scr[D::X_SPAWN + 3] = x[3];
     }
     if (w == 2 % R) {
@@ -180,7 +180,9 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
         for (int j = 0; j < C; ++j) scr[D::X_TERM + j] = 0u;
         scr[D::X_NSPAWN] = 0u;
     }
+    if (round < 0) __trap();  // (never: makes every thread HOLD the round before the barrier, see take_round_ticket)
     __syncthreads();  // barrier initialisation and the P0 products visible to every warp
+    const unsigned ticket = threadIdx.x == 0 ? take_round_ticket(p) : 0u;
     MSCHED_TL(tl[3] = clock64());
     mbar_wait(&bar, 0);
     MSCHED_TL(tl[4] = clock64());
@@ -489,7 +491,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
                         const int dnum = a * newJobs + k;  // draw d uses word d%4 of Philox call d/4
                         if ((dnum >> 2) != rndCall) {
                             rndCall = dnum >> 2;
-                            env_draw(p, env, kStreamSpawn, (uint32_t)rndCall, 0u, rnd);
+                            env_draw_at(p, round, env, kStreamSpawn, (uint32_t)rndCall, 0u, rnd);
                         }
                         const uint32_t xr = (dnum & 3) == 0 ? rnd[0] : (dnum & 3) == 1 ? rnd[1] : (dnum & 3) == 2 ? rnd[2] : rnd[3];
                         // first kind with u = xr * 2^-32 < cum[kind], decided exactly in integers
@@ -572,7 +574,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     if (!withObs) {
         if (threadIdx.x == 0) {
             MSCHED_TL((tl[6] = clock64(), tl[7] = globaltimer()));
-            finish_round(p);
+            redeem_round_ticket(p, ticket);
         }
         return;
     }
@@ -636,7 +638,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
         bulk_commit();
         bulk_wait_read();
         MSCHED_TL((tl[6] = clock64(), tl[7] = globaltimer()));
-        finish_round(p);
+        redeem_round_ticket(p, ticket);
     }
 #undef MSCHED_TL
 }

@@ -125,12 +125,17 @@ __device__ __forceinline__ int cur_done(const DevParams &p, int round)
     return p.roundDev ? (((round + 1) % p.episodeLength) == 0 ? 1 : 0) : p.doneFlag;
 }
 
+__device__ __forceinline__ void env_draw_at(const DevParams &p, int round, int env, uint32_t stream, uint32_t a,
+                                            uint32_t b, uint32_t out[4])
+{
+    const unsigned long long g = (unsigned long long)(p.envOffset + env);
+    philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)round, (stream << 28) | (a << 12) | b,
+                  (uint32_t)p.seed, (uint32_t)(p.seed >> 32), out);
+}
 __device__ __forceinline__ void env_draw(const DevParams &p, int env, uint32_t stream, uint32_t a,
                                          uint32_t b, uint32_t out[4])
 {
-    const unsigned long long g = (unsigned long long)(p.envOffset + env);
-    philox4x32_10((uint32_t)g, (uint32_t)(g >> 32), (uint32_t)cur_round(p), (stream << 28) | (a << 12) | b,
-                  (uint32_t)p.seed, (uint32_t)(p.seed >> 32), out);
+    env_draw_at(p, cur_round(p), env, stream, a, b, out);
 }
 __device__ __forceinline__ double u53(const uint32_t x[4])
 {
@@ -202,6 +207,22 @@ __device__ __forceinline__ unsigned long long globaltimer()
 // Called by one thread of every CTA after its last use of the round: the CTA that draws the last
 // ticket knows that every other CTA of the launch is past its reads and advances the counter, so a
 // step needs no separate "round += 1" launch (graph-replay mode only)
+// The same in two halves for a kernel whose threads ALL hold the round in a register before a CTA barrier: the
+// ticket is drawn right after that barrier (its latency hides behind the step) and only redeemed at the end
+__device__ __forceinline__ unsigned take_round_ticket(const DevParams &p)
+{
+    if (!p.roundTicket) return 0u;
+    __threadfence();
+    return atomicAdd(p.roundTicket, 1u);
+}
+__device__ __forceinline__ void redeem_round_ticket(const DevParams &p, unsigned t)
+{
+    if (p.roundTicket && t == gridDim.x - 1) {  // every CTA of the launch has read the round
+        *p.roundTicket = 0u;
+        *p.roundDev += 1;
+        __threadfence();
+    }
+}
 __device__ __forceinline__ void finish_round(const DevParams &p)
 {
     if (p.roundTicket) {
