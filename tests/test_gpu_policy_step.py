@@ -147,3 +147,105 @@ def test_policy_step_refuses_other_shapes():
     O_ = policy.policy_step_group(go, 2, 64, 6, 4, 2)
     with pytest.raises(MschedError):
         policy.policy_step(obs, 128, 8, 2, A_, O_)
+
+
+def test_policy_step_full_size_windows_match_oracle_and_simt(monkeypatch):
+    """BASELINE size (65,536 envs, the grid the bench launches): three 128-env windows of the big batch against the
+    oracle MLP (probabilities, sampled actions, log-probs, experience rows), and over ALL rows the tensor-core kernel
+    against the fp32 SIMT kernel run with the same draws (same actions wherever the draw is not within 1e-5 of a CDF
+    step, log-probs within 1e-4)."""
+    import torch
+    from marl_scheduling_b200 import policy
+    from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
+    from oracle import oracle as O
+    dom = CFG3
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    NL, P, B = N * L, max(dom["prios"]), 65536
+    env = BatchedSchedulingEnv(B, world_params_from_dom(dom, True), reward="free_comm", auction="random", spawn="philox", seed=4)
+    dev, lay = env.device, env.layout
+    g = torch.Generator(device=dev).manual_seed(2)
+    for t in range(15):
+        env.acceptor_actions.random_(0, 2, generator=g)
+        env.offer_core_actions.random_(0, C + 1, generator=g)
+        env.offer_price_actions.random_(0, P + 1, generator=g)
+        env.step_observe_records()
+    obs = env.obs_views()
+    Ua, Uo = N * C, NL
+    nin_a, A_a, nin_o, A_o = 3 + 2 * NL, NL + 1, 2 * C + 2, C + 1
+    ga = policy.MlpGroup.random(nin_a, 16, A_a, Ua, dev, seed=31)
+    go = policy.MlpGroup.random(nin_o, 16, A_o, Uo, dev, seed=32)
+    gp = policy.MlpGroup.random(4, 16, P + 1, Uo, dev, seed=33)
+    res = {}
+    for impl in ("tc", "simt"):
+        monkeypatch.setenv("MSCHED_POLICY_STEP_IMPL", impl)
+        out = [(torch.zeros((B, n), dtype=torch.int32, device=dev), torch.zeros((B, n), device=dev),
+                torch.zeros((B, n, A), device=dev)) for n, A in ((Ua, A_a), (Uo, A_o), (Uo, P + 1))]
+        xs = [torch.zeros((B, Ua, lay.o_acc_row), dtype=torch.int16, device=dev), torch.zeros((B, Uo, lay.o_off_row), dtype=torch.int16, device=dev),
+              torch.zeros((B, Uo, 4), dtype=torch.int16, device=dev)]
+        A_ = policy.policy_step_group(ga, Ua, lay.o_acceptor, lay.o_acc_row, lay.a_acceptor, 7, *out[0][:2], x_used=xs[0], probs=out[0][2])
+        O_ = policy.policy_step_group(go, Uo, lay.o_offer, lay.o_off_row, lay.a_offer_core, 8, *out[1][:2], x_used=xs[1], probs=out[1][2])
+        P_ = policy.policy_step_group(gp, Uo, lay.o_offer, lay.o_off_row, lay.a_offer_price, 9, *out[2][:2], x_used=xs[2], probs=out[2][2])
+        policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, env_offset=0, step=3, input_bound=16)
+        torch.cuda.synchronize()
+        res[impl] = (out, xs)
+    (to, tx), (so, sx) = res["tc"], res["simt"]
+    for k in range(3):
+        assert torch.equal(tx[k], sx[k])                               # experience rows: bit-identical
+        pt, ps = to[k][2], so[k][2]
+        if k < 2:                                                      # (the price chooser's input depends on the sampled core)
+            assert float((pt - ps).abs().max()) < 2e-5
+        same = to[k][0] == so[k][0]
+        assert float(same.float().mean()) > 0.9995
+        if k < 2:
+            assert float((to[k][1] - so[k][1])[same].abs().max()) < 1e-4
+    acc_x = obs["acceptor"].reshape(B, Ua, nin_a)
+    off_x = obs["offer"].reshape(B, Uo, nin_o)
+    for w0 in (0, 31872, B - 128):                                     # windows: first, an odd tile in the middle, last
+        sl = slice(w0, w0 + 128)
+        for (x, grp, out, nin, A) in ((acc_x, ga, to[0], nin_a, A_a), (off_x, go, to[1], nin_o, A_o)):
+            wts = grp.weights.cpu().numpy()
+            xw = x[sl].cpu().numpy().astype(np.float32)
+            for n in range(x.shape[1]):
+                p, _, _ = O.mlp_forward(xw[:, n], *_unpack(wts, n, nin, A))
+                np.testing.assert_allclose(out[2][sl, n].cpu().numpy(), p, rtol=2e-5, atol=1e-7)
+                pa = np.take_along_axis(p / p.sum(1, keepdims=True), out[0][sl, n].cpu().numpy()[:, None].astype(np.int64), 1)[:, 0]
+                np.testing.assert_allclose(out[1][sl, n].cpu().numpy(), np.log(np.clip(pa, 1.1920929e-07, 1 - 1.1920929e-07)), rtol=1e-4, atol=2e-5)
+    env.close()
+
+
+def test_policy_step_large_inputs_take_the_simt_kernel(monkeypatch):
+    """input_bound > 511 (or unknown) must not reach the fp16 operand path: forcing `tc` is an error, the default call
+    falls back to the fp32 SIMT kernel and agrees with the oracle on rows holding values beyond +-511."""
+    import torch
+    from marl_scheduling_b200 import policy
+    from marl_scheduling_b200._lib import MschedError
+    from oracle import oracle as O
+    dev = torch.device("cuda", 0)
+    B, N, C, L = 300, 2, 3, 3
+    NL, Ua, Uo = N * L, N * C, N * L
+    nin_a, A_a, nin_o, A_o = 3 + 2 * NL, NL + 1, 2 * C + 2, C + 1
+    RA, RO = nin_a + 1, nin_o
+    OH = Ua * RA + Uo * RO + 2
+    rng = np.random.default_rng(3)
+    obs = torch.as_tensor(rng.integers(-900, 900, (B, OH)).astype(np.int16)).to(dev)
+    ga = policy.MlpGroup.random(nin_a, 16, A_a, Ua, dev, seed=41)
+    go = policy.MlpGroup.random(nin_o, 16, A_o, Uo, dev, seed=42)
+    ga.weights.mul_(0.02); go.weights.mul_(0.02)   # keep the pre-activations of 900-sized inputs in range
+    out = [(torch.zeros((B, n), dtype=torch.int32, device=dev), torch.zeros((B, n), device=dev), torch.zeros((B, n, A), device=dev))
+           for n, A in ((Ua, A_a), (Uo, A_o))]
+    A_ = policy.policy_step_group(ga, Ua, 1, RA, 0, 1, *out[0][:2], probs=out[0][2])
+    O_ = policy.policy_step_group(go, Uo, Ua * RA, RO, Ua, 2, *out[1][:2], probs=out[1][2])
+    monkeypatch.setenv("MSCHED_POLICY_STEP_IMPL", "tc")
+    with pytest.raises(MschedError):
+        policy.policy_step(obs, OH, B, C, A_, O_, input_bound=900)
+    monkeypatch.delenv("MSCHED_POLICY_STEP_IMPL")
+    policy.policy_step(obs, OH, B, C, A_, O_, input_bound=900)
+    torch.cuda.synchronize()
+    x = obs.cpu().numpy()
+    acc_x = x[:, :Ua * RA].reshape(B, Ua, RA)[:, :, 1:].astype(np.float32)
+    off_x = x[:, Ua * RA:Ua * RA + Uo * RO].reshape(B, Uo, RO).astype(np.float32)
+    for (xw, grp, o, nin, A) in ((acc_x, ga, out[0], nin_a, A_a), (off_x, go, out[1], nin_o, A_o)):
+        wts = grp.weights.cpu().numpy()
+        for n in (0, xw.shape[1] - 1):
+            p, _, _ = O.mlp_forward(xw[:, n], *_unpack(wts, n, nin, A))
+            np.testing.assert_allclose(o[2][:, n].cpu().numpy(), p, rtol=5e-5, atol=1e-7)
