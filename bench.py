@@ -452,6 +452,7 @@ def main():
     ap.add_argument("--device-round", action="store_true", help="device-side round counter without graphs")
     ap.add_argument("--streams", type=int, default=3,
                     help="streams the independent shards alternate between in --l2 rotate (1 = strictly serial launches)")
+    ap.add_argument("--no-multi", action="store_true", help="skip the msched_step_multi (T steps per launch) measurement")
     ap.add_argument("--no-flush", action="store_true", help="keep L2 warm between steps (diagnostic)")
     ap.add_argument("--state-warm", type=int, default=1000, help="untimed steps to reach steady state")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
@@ -479,6 +480,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from marl_scheduling_b200.distributed import pin_host_to_gpu
+    host_pin = pin_host_to_gpu(local)  # before any pinned host buffer is allocated
     if world > 1:
         # NCCL prints its version banner to stdout on the first communicator: keep stdout for the ONE JSON line
         sys.stdout.flush()
@@ -502,6 +505,7 @@ def main():
     dense = args.obs == "dense"
     compact = args.obs == "compact"
     serial_us = None
+    multi = None
 
     def make_env(k):
         return BatchedSchedulingEnv(B, world_params_from_dom(dom, mode.startswith("free")), reward=mode,
@@ -638,6 +642,47 @@ def main():
                 run_block(S * G, e, one)
             torch.cuda.synchronize()
             serial_us = 1e3 * sum(e[0].elapsed_time(e[1]) for e in evs) / (len(evs) * S * G)
+        # msched_step_multi: T steps per launch (a CTA keeps its 32 environments; observations after EVERY step, so each
+        # step does the work of the headline step; the state is re-read from L2 instead of HBM between a launch's steps)
+        if rank == 0 and fused and not args.no_multi:
+            try:
+                Tm = 8
+                m_acts = [torch.zeros((Tm, lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=dev) for _ in range(S)]
+                m_res = [torch.zeros((Tm, lay.padded_envs, lay.result_words), dtype=torch.int32, device=dev) for _ in range(S)]
+                m_obs = [torch.zeros((Tm, lay.padded_envs, lay.obs_halfs), dtype=torch.int16, device=dev) for _ in range(S)]
+
+                def multi_block():
+                    for k in range(S):
+                        envs[k].step_multi_records(m_acts[k], m_res[k], m_obs[k], obs_every=True)
+
+                def multi_refresh():
+                    for k in range(S):
+                        for t_ in range(Tm):
+                            refresh_actions(env, m_acts[k][t_], gen)
+                multi_refresh()
+                multi_block()
+                torch.cuda.synchronize()
+                gm = torch.cuda.CUDAGraph()
+                cap = torch.cuda.Stream(device=dev)
+                cap.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(cap):
+                    with torch.cuda.graph(gm, stream=cap):
+                        multi_block()
+                torch.cuda.current_stream(dev).wait_stream(cap)
+                evm = [[torch.cuda.Event(enable_timing=True) for _ in range(2)] for _ in range(6)]
+                for e in evm:
+                    multi_refresh()
+                    e[0].record()
+                    gm.replay()
+                    e[1].record()
+                torch.cuda.synchronize()
+                multi_us = 1e3 * sum(e[0].elapsed_time(e[1]) for e in evm) / (len(evm) * S * Tm)
+                multi = {"steps_per_launch": Tm, "us_per_step": multi_us,
+                         "what": "msched_step_multi: %d dependent steps per launch, observations after every step, launches of %d "
+                                 "shards one after the other on ONE stream (graph replay)" % (Tm, S)}
+                del m_acts, m_res, m_obs
+            except L.MschedError as e:
+                multi = {"unavailable": str(e)}
         l2_note = (f"inputs larger than L2: {S} shards x {per_set / 1e6:.0f} MB visited round-robin, launches "
                    f"in blocks of {S * G} on {len(streams)} stream(s)" + (", each block one CUDA-graph replay" if use_graph else ""))
         n_launch = K
@@ -738,6 +783,8 @@ def main():
         hb = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
         db = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
         pcie = {}
+        if world > 1:
+            dist.barrier()  # every rank copies at the same time: the rates include the contention on the host side
         for name, (dst, src) in (("h2d_gbs", (db, hb)), ("d2h_gbs", (hb, db))):
             dst.copy_(src, non_blocking=True)
             torch.cuda.synchronize()
@@ -752,6 +799,15 @@ def main():
         t_bound = max(B * lay.action_halfs * 2 / (pcie["h2d_gbs"] * 1e9), B * rwords * 4 / (pcie["d2h_gbs"] * 1e9))
         pcie["bound_value"] = world * B * N / t_bound  # copies at the measured rates, both directions fully overlapped
         pcie["frac_of_bound"] = world * B * N * nE / float(te[0]) / pcie["bound_value"]
+        if world > 1:  # the slowest rank's copy rates (all ranks copying concurrently) bound the job
+            tr = torch.tensor([pcie["h2d_gbs"], pcie["d2h_gbs"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(tr, op=dist.ReduceOp.MIN)
+            pcie["h2d_gbs_min_rank"], pcie["d2h_gbs_min_rank"] = float(tr[0]), float(tr[1])
+        pcie["host_pinning"] = host_pin
+        pcie["limiter"] = ("PCIe / host memory: the records of a step cross the bus once in each direction; %d rank(s) copying "
+                           "concurrently reach %.0f / %.0f GB/s per GPU (H2D / D2H, copy engine), the kernel's SM-originated "
+                           "zero-copy traffic runs at %.2f of the bound those rates set" %
+                           (world, pcie["h2d_gbs"], pcie["d2h_gbs"], pcie["frac_of_bound"]))
         del hb, db
         e2e = {"value": world * B * N * nE / float(te[0]), "unit": "agent-steps/s", "pcie": pcie,
                "h2d_bytes_per_step": B * lay.action_halfs * 2, "d2h_bytes_per_step": B * rwords * 4,
@@ -1034,7 +1090,9 @@ def main():
                                                               ("+o_c (compact observations)" if one_launch_compact else "")),
                      "units_per_launch": B, "launch_us": step_launch_s * 1e6,
                      "serial_launch_us": serial_us,
-                     "serial_frac": (alg_bytes * B / (serial_us * 1e-6) / 1e9 / peak) if serial_us else None},
+                     "serial_frac": (alg_bytes * B / (serial_us * 1e-6) / 1e9 / peak) if serial_us else None,
+                     "multi_step": (dict(multi, frac=alg_bytes * B / (multi["us_per_step"] * 1e-6) / 1e9 / peak)
+                                    if multi and "us_per_step" in multi else multi)},
         "kernels": {"step_us": 1e3 * stepk_ms / K, "observe_us": obs_us,
                     "observe_algorithmic_bytes_per_env": ab["obs"] + ab["state"]},
         "cpu_baseline": cpu,

@@ -205,6 +205,18 @@ int msched_step(void *handle, const int16_t *action_dev, const double *spawn_u_d
 int msched_step_observe(void *handle, const int16_t *action_dev, const double *spawn_u_dev,
                         uint32_t *result_dev, int16_t *obs_dev, void *stream);
 
+/* n_steps consecutive SchedulingEnv.steps in ONE launch for scripted / pre-drawn actions (rollouts of the hard-coded
+ * agents' action traces, random-policy warm-up, evaluation): step t reads the action record action_dev + t *
+ * padded_envs * action_halfs and writes the result record result_dev + t * padded_envs * result_words.  A CTA keeps
+ * its 32 environments for all steps: no launch gap, ramp or tail between the steps of a dependent chain, and --
+ * without obs_every -- the state tile stays in shared memory between steps (only the last step's observations are
+ * written to obs_dev [padded_envs][obs_halfs], which may be NULL).  obs_every != 0: every step writes its
+ * observations to obs_dev + t * padded_envs * obs_halfs.  Same results, bit for bit, as n_steps calls of
+ * msched_step_observe; the round advances by n_steps.  Domains with a multi-step instantiation of the fused kernel
+ * only (the BASELINE configurations; MSCHED_E_ARG otherwise), device Philox or recorded-kind spawn. */
+int msched_step_multi(void *handle, const int16_t *action_dev, int n_steps, uint32_t *result_dev, int16_t *obs_dev,
+                      int obs_every, void *stream);
+
 /* same call with HOST buffers: the action records go in, the result records come out, then stream
  * synchronise.  PINNED buffers (cudaHostAlloc / torch pin_memory) of an unpadded batch (B a multiple of 128)
  * on a domain with a fused kernel are read and written by the kernel's bulk copies directly (zero-copy: one

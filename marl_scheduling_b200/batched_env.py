@@ -172,6 +172,18 @@ class BatchedSchedulingEnv:
                                              obs.data_ptr(), self._stream()))
         return result, obs
 
+    def step_multi_records(self, actions, results, obs=None, obs_every=False):
+        """msched_step_multi: T = actions.shape[0] consecutive steps in ONE launch (fused-kernel domains).  actions int16
+        [T, padded_envs, action_halfs], results int32 [T, padded_envs, result_words]; obs: the env's observation
+        record (last step) by default, or int16 [T, padded_envs, obs_halfs] with obs_every.  Asynchronous."""
+        T = int(actions.shape[0])
+        assert actions.is_contiguous() and results.is_contiguous() and results.shape[0] == T
+        if obs is None and not obs_every:
+            obs = self._obs_buffer()
+        L.check(self.lib.msched_step_multi(self.handle, actions.data_ptr(), T, results.data_ptr(),
+                                           None if obs is None else obs.data_ptr(), 1 if obs_every else 0, self._stream()))
+        return results, obs
+
     def step_compact_records(self, action=None, result=None, spawn_u=None, cobs=None):
         """step_records + the COMPACT observations of the new state (msched_step_compact: one launch on the
         warp-per-environment kernel of the large domains).  Asynchronous."""

@@ -102,7 +102,7 @@ __host__ __device__ constexpr int fused_spec(int mode, int auction, int spawn, i
     return mode | (auction << 2) | (spawn << 4) | (newJobsIsOne << 6);
 }
 
-template <int N, int C, int L, int R, int SPEC = -1>
+template <int N, int C, int L, int R, int SPEC = -1, bool MULTI = false>
 __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 16 : 8) : 1)
     fused_step_kernel(const __grid_constant__ DevParams p)
 {
@@ -132,9 +132,6 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     if (threadIdx.x == 0) {
         MSCHED_TL((tl[0] = smid(), tl[1] = globaltimer(), tl[2] = clock64()));
         mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, 32u * (uint32_t)(W + AW) * 4u);
-        bulk_g2s(sState, p.state + (size_t)env0 * W, 32u * W * 4u, &bar);
-        bulk_g2s(sAct, p.action + (size_t)env0 * p.AH, 32u * (uint32_t)AW * 4u, &bar);
     }
 
     const int auctionMode = SPEC >= 0 ? ((SPEC >> 2) & 3) : p.auctionMode;
@@ -145,8 +142,24 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     const int mode = SPEC >= 0 ? (SPEC & 3) : p.mode;
     const bool agg = mode == MSCHED_REWARD_AGGREGATED_FIXED;
     const bool freeM = mode == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL || mode == MSCHED_REWARD_DIVIDED_FREE_NONCOMMERCIAL;
-    const int round = cur_round(p);
+    const int round0 = cur_round(p);
     const bool live = env < p.B;
+    // msched_step_multi: nSteps consecutive steps in this launch.  With observations after every step the tile is
+    // re-read each step (the observation tile overlays it); without, the state tile stays in shared memory and only
+    // the action tile of the next step is fetched
+    const int nSteps = MULTI ? (p.nSteps > 1 ? p.nSteps : 1) : 1;  // (the one-step instantiation folds the loop away)
+    unsigned ticket = 0u;
+    bool stateResident = false;
+#pragma unroll 1
+    for (int tStep = 0; tStep < nSteps; ++tStep) {
+    const int round = round0 + tStep;
+    const bool lastStep = tStep == nSteps - 1;
+    const bool obsThis = withObs && (lastStep || p.obsEvery != 0);
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, 32u * (uint32_t)((stateResident ? 0 : W) + AW) * 4u);
+        if (!stateResident) bulk_g2s(sState, p.state + (size_t)env0 * W, 32u * W * 4u, &bar);
+        bulk_g2s(sAct, p.action + (size_t)tStep * p.actStep + (size_t)env0 * p.AH, 32u * (uint32_t)AW * 4u, &bar);
+    }
 
     uint32_t *st = sState + (size_t)lane * W;
     const int16_t *act = reinterpret_cast<const int16_t *>(sAct + (size_t)lane * AW);
@@ -182,9 +195,9 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     }
     if (round < 0) __trap();  // (never: makes every thread HOLD the round before the barrier, see take_round_ticket)
     __syncthreads();  // barrier initialisation and the P0 products visible to every warp
-    const unsigned ticket = threadIdx.x == 0 ? take_round_ticket(p) : 0u;
+    if (tStep == 0 && threadIdx.x == 0) ticket = take_round_ticket(p);
     MSCHED_TL(tl[3] = clock64());
-    mbar_wait(&bar, 0);
+    mbar_wait(&bar, (uint32_t)tStep & 1u);
     MSCHED_TL(tl[4] = clock64());
 
     // ---- P1: per core, who acts on it and which pending offer is selected.  Offers addressed to
@@ -527,7 +540,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
             const unsigned long long qb = (unsigned long long)__double_as_longlong(qualSum);
             res[p.rQual] = (uint32_t)qb;
             res[p.rQual + 1] = (uint32_t)(qb >> 32);
-            res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nAcc << 8) | ((uint32_t)nTerm << 16) | ((uint32_t)cur_done(p, round) << 24);
+            res[p.rCounts] = (uint32_t)qualCnt | ((uint32_t)nAcc << 8) | ((uint32_t)nTerm << 16) | ((uint32_t)(nSteps > 1 ? ((((round + 1) % p.episodeLength) == 0) ? 1 : 0) : cur_done(p, round)) << 24);
             res[p.rFlags] = flags;
         }
     }
@@ -555,7 +568,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     // ---- the new state and the result record leave; the observation rows are then staged in the
     // same shared memory ----
     uint32_t cw0[C], sw0[NL], sw3[NL];
-    if (withObs) {
+    if (obsThis) {
 #pragma unroll
         for (int j = 0; j < C; ++j) cw0[j] = core[3 * j];
 #pragma unroll
@@ -565,19 +578,17 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     __syncthreads();
     if (threadIdx.x == 0) {
         MSCHED_TL(tl[5] = clock64());
-        bulk_s2g(p.state + (size_t)env0 * W, sState, 32u * W * 4u);
+        // the state leaves when the observation tile is about to overlay it, and after the last step
+        if (obsThis || lastStep) bulk_s2g(p.state + (size_t)env0 * W, sState, 32u * W * 4u);
         if (p.cres) bulk_s2g(p.cres + (size_t)env0 * p.CW, sScr + 32 * XW, 32u * (uint32_t)p.CW * 4u);
-        else bulk_s2g(p.result + (size_t)env0 * RW, sRes, 32u * (uint32_t)RW * 4u);
+        else bulk_s2g(p.result + (size_t)tStep * p.resStep + (size_t)env0 * RW, sRes, 32u * (uint32_t)RW * 4u);
         bulk_commit();
-        bulk_wait_read();
+        // the next step re-reads what this one wrote (state) only after the store has COMPLETED
+        if (obsThis && !lastStep) bulk_wait_all();
+        else bulk_wait_read();
     }
-    if (!withObs) {
-        if (threadIdx.x == 0) {
-            MSCHED_TL((tl[6] = clock64(), tl[7] = globaltimer()));
-            redeem_round_ticket(p, ticket);
-        }
-        return;
-    }
+    stateResident = !obsThis;
+    if (obsThis) {
     __syncthreads();  // the bulk stores have read the work tiles: the memory is free
 
     // ---- P6: observations of the new state (src/Agent.py:148-300, src/Auctioneer.py:20-77).  A core
@@ -634,11 +645,17 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     fence_async_smem();
     __syncthreads();
     if (threadIdx.x == 0) {
-        bulk_s2g(reinterpret_cast<uint32_t *>(p.obs) + (size_t)env0 * OW, sObs, 32u * (uint32_t)OW * 4u);
+        bulk_s2g(reinterpret_cast<uint32_t *>(p.obs + (p.obsEvery ? (size_t)tStep * p.obsStep : 0)) + (size_t)env0 * OW, sObs,
+                 32u * (uint32_t)OW * 4u);
         bulk_commit();
         bulk_wait_read();
+    }
+    }  // obsThis
+    if (!lastStep) __syncthreads();  // the stores have read the tiles: the next step may overwrite them
+    }  // steps of the launch
+    if (threadIdx.x == 0) {
         MSCHED_TL((tl[6] = clock64(), tl[7] = globaltimer()));
-        redeem_round_ticket(p, ticket);
+        redeem_round_ticket(p, ticket, nSteps);
     }
 #undef MSCHED_TL
 }

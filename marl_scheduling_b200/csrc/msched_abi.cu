@@ -147,6 +147,7 @@ struct Handle {
     size_t warpSmem;  // warp-per-environment kernel (msched_warp.cu): shared memory per CTA, 0 = not available
     bool useWarp;
     StepKernel fusedFn;  // compile-time-domain register-resident kernel (step + observations), or null
+    StepKernel multiFn = nullptr;  // its multi-step instantiation (msched_step_multi), or null
     size_t fusedSmem, fusedSmemObs;  // dynamic shared memory without / with the observation tile
     int fusedRoles;                  // warps per 32-env tile
     bool useFused, fuseObs;
@@ -211,6 +212,27 @@ StepKernel pick_fused_spec(const MschedConfig &c, int roles)
         constexpr int S = fused_spec(MSCHED_REWARD_DIVIDED_FIXED, MSCHED_AUCTION_RANDOM_MAX, MSCHED_SPAWN_PHILOX, 1);
         return roles == 2 ? fused_step_kernel<4, 4, 3, 2, S> : roles == 4 ? fused_step_kernel<4, 4, 3, 4, S> : nullptr;
     }
+    return nullptr;
+}
+
+// the multi-step instantiations (msched_step_multi): the BASELINE configurations and the generic 2-role kernels of
+// their domains
+StepKernel pick_fused_multi(const MschedConfig &c, int roles, bool spec)
+{
+    const bool baseline = spec && c.spawnMode == MSCHED_SPAWN_PHILOX && c.newJobsPerRound == 1 && c.auctionMode == MSCHED_AUCTION_RANDOM_MAX;
+    if (c.N == 2 && c.C == 3 && c.L == 3 && (roles == 2 || roles == 4)) {
+        constexpr int S = fused_spec(MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL, MSCHED_AUCTION_RANDOM_MAX, MSCHED_SPAWN_PHILOX, 1);
+        if (baseline && c.rewardVariant == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL)
+            return roles == 2 ? fused_step_kernel<2, 3, 3, 2, S, true> : fused_step_kernel<2, 3, 3, 4, S, true>;
+        return roles == 2 ? fused_step_kernel<2, 3, 3, 2, -1, true> : fused_step_kernel<2, 3, 3, 4, -1, true>;
+    }
+    if (c.N == 4 && c.C == 4 && c.L == 3 && roles == 4) {
+        constexpr int S = fused_spec(MSCHED_REWARD_DIVIDED_FIXED, MSCHED_AUCTION_RANDOM_MAX, MSCHED_SPAWN_PHILOX, 1);
+        if (baseline && c.rewardVariant == MSCHED_REWARD_DIVIDED_FIXED) return fused_step_kernel<4, 4, 3, 4, S, true>;
+        return fused_step_kernel<4, 4, 3, 4, -1, true>;
+    }
+    if (c.N == 2 && c.C == 3 && c.L == 2 && (roles == 2 || roles == 4))
+        return roles == 2 ? fused_step_kernel<2, 3, 2, 2, -1, true> : fused_step_kernel<2, 3, 2, 4, -1, true>;
     return nullptr;
 }
 
@@ -415,6 +437,9 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
                                       (int)(h->fuseObs ? h->fusedSmemObs : h->fusedSmem)));
         h->useFused = true;
         h->useWarp = false;
+        h->multiFn = h->fuseObs ? pick_fused_multi(*cfg, h->fusedRoles, !getenv("MSCHED_NO_SPEC")) : nullptr;
+        if (h->multiFn)
+            CUDA_TRY(cudaFuncSetAttribute(h->multiFn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fusedSmemObs));
     }
     // MSCHED_STEP_IMPL=fused|lane|coop forces one implementation (tests run all of them)
     if (const char *e = getenv("MSCHED_STEP_IMPL")) {
@@ -653,6 +678,31 @@ int msched_step_observe(void *handle, const int16_t *action_dev, const double *s
     launch_step(h, p, static_cast<cudaStream_t>(stream));
     CUDA_TRY(cudaGetLastError());
     h->round += 1;
+    return MSCHED_OK;
+}
+
+int msched_step_multi(void *handle, const int16_t *action_dev, int n_steps, uint32_t *result_dev, int16_t *obs_dev, int obs_every,
+                      void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !action_dev || !result_dev) return fail(MSCHED_E_ARG, "null handle/action/result");
+    if (n_steps < 1 || n_steps > 4096) return fail(MSCHED_E_ARG, "n_steps out of range");
+    if (!h->useFused || !h->multiFn) return fail(MSCHED_E_ARG, "msched_step_multi: no multi-step kernel for this domain / role count (use msched_step_observe per step)");
+    if (h->cfg.spawnMode == MSCHED_SPAWN_U64) return fail(MSCHED_E_ARG, "msched_step_multi: recorded float64 spawn draws are per step (use msched_step)");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    if (!aligned16(action_dev) || !aligned16(result_dev) || (obs_dev && !aligned16(obs_dev))) return fail(MSCHED_E_ARG, "buffers must be 16-byte aligned");
+    if (obs_every && !obs_dev) return fail(MSCHED_E_ARG, "obs_every needs an observation buffer");
+    DevParams p = h->p;
+    p.action = action_dev; p.spawnU = nullptr; p.result = result_dev; p.obs = obs_dev; p.cres = nullptr;
+    p.nSteps = n_steps; p.obsEvery = obs_every ? 1 : 0;
+    p.actStep = (long long)p.Bpad * p.AH; p.resStep = (long long)p.Bpad * p.RW; p.obsStep = (long long)p.Bpad * p.OH;
+    p.round = (int)h->round;
+    p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
+    p.roundDev = h->deviceRound ? h->roundDev : nullptr;
+    p.roundTicket = h->deviceRound ? reinterpret_cast<unsigned *>(h->roundDev + 1) : nullptr;
+    h->multiFn<<<p.Bpad / 32, 32 * h->fusedRoles, obs_dev ? h->fusedSmemObs : h->fusedSmem, static_cast<cudaStream_t>(stream)>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    h->round += n_steps;
     return MSCHED_OK;
 }
 

@@ -67,6 +67,11 @@ struct DevParams {
     uint32_t *cres;                // compact result records, or null -> the full record goes to `result`
     int CW;                        // compact result words per env (odd)
     int cOffer, cPrice, cAcc, cAuc, cAgent, cTail;  // half offsets of the planes; word offset of [quality f32, counts, flags]
+    // multi-step launches of the fused kernel (msched_step_multi): nSteps consecutive steps per launch, step t reads
+    // action + t * actStep (int16), writes result + t * resStep (uint32) and, if obsEvery, obs + t * obsStep (int16);
+    // without obsEvery only the last step builds observations and the state tile stays in shared memory in between
+    int nSteps, obsEvery;
+    long long actStep, resStep, obsStep;
 };
 
 // ---- host+device layout arithmetic ------------------------------------------------------
@@ -215,11 +220,11 @@ __device__ __forceinline__ unsigned take_round_ticket(const DevParams &p)
     __threadfence();
     return atomicAdd(p.roundTicket, 1u);
 }
-__device__ __forceinline__ void redeem_round_ticket(const DevParams &p, unsigned t)
+__device__ __forceinline__ void redeem_round_ticket(const DevParams &p, unsigned t, int steps = 1)
 {
     if (p.roundTicket && t == gridDim.x - 1) {  // every CTA of the launch has read the round
         *p.roundTicket = 0u;
-        *p.roundDev += 1;
+        *p.roundDev += steps;
         __threadfence();
     }
 }

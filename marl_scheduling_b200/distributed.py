@@ -22,6 +22,35 @@ def shard_envs(total_envs, world_size, rank):
     return off, n
 
 
+def pin_host_to_gpu(gpu_index):
+    """Best effort: bind this process (and therefore the pinned host buffers it allocates afterwards, first touch) to
+    the CPUs of the NUMA node the GPU hangs off (NVML's ideal CPU affinity).  The host-buffer step writes results
+    from the SMs straight into host memory; with all ranks' buffers on one node the far GPUs cross the socket link.
+    Returns a short description (what was set, or why nothing was)."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        try:
+            node = pynvml.nvmlDeviceGetNumaNodeId(h)
+        except Exception:
+            node = None
+        if not cpus:
+            return f"numa node {node}: no usable CPUs in the GPU's affinity mask"
+        if cpus == allowed:
+            return f"numa node {node}: the GPU's affinity mask is every allowed CPU ({len(allowed)}): nothing to pin"
+        os.sched_setaffinity(0, cpus)
+        return f"numa node {node}: bound to {len(cpus)} of {len(allowed)} CPUs"
+    except Exception as e:  # no NVML, no permission: run unpinned
+        return f"unpinned ({type(e).__name__})"
+
+
 def is_distributed():
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 

@@ -517,3 +517,45 @@ def test_config5_full_size_windows_match_oracle_and_jobs_are_conserved():
     assert torch.equal(spawned, terminated + present)
     assert int(spawned.min()) > 0 and int(terminated.sum()) > B
     env.close()
+
+
+@pytest.mark.parametrize("key,auction,obs_every,dev_round", [
+    ("cfg3", "random", False, False), ("cfg3", "random", True, True), ("cfg3", "first", True, False),
+    ("cfg2", "random", True, False), ("cfg2", "random", False, True), ("cfg1", "random", False, False)])
+def test_step_multi_matches_single_steps(key, auction, obs_every, dev_round):
+    """msched_step_multi (T steps per launch, a CTA keeps its 32 environments; without obs_every the state tile stays
+    in shared memory between steps) walks bit for bit through the states, result records and observations of T
+    msched_step_observe calls -- host round and device round counter, two launches in a row."""
+    import torch
+    dom, mode = DOMS[key]
+    free = mode.startswith("free")
+    B, T = 1000, 9
+    a = _env(B, dict(dom, mode=mode), auction=auction, spawn="philox", seed=21)
+    b = _env(B, dict(dom, mode=mode), auction=auction, spawn="philox", seed=21)
+    if dev_round:
+        a.set_device_round(True); b.set_device_round(True)
+    lay, dev = a.layout, a.device
+    rng = np.random.default_rng(6)
+    for launch in range(2):
+        acts = torch.zeros((T, lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=dev)
+        for t in range(T):
+            offc, acc, offp = random_actions(rng, B, dom, free)
+            a.set_actions(offc, acc, None, offer_price=offp)
+            acts[t].copy_(a.action)
+        res1 = torch.zeros((T, lay.padded_envs, lay.result_words), dtype=torch.int32, device=dev)
+        obs1 = torch.zeros((T, lay.padded_envs, lay.obs_halfs), dtype=torch.int16, device=dev)
+        for t in range(T):
+            a.step_observe_records(acts[t], res1[t], obs=obs1[t])
+        res2 = torch.zeros_like(res1)
+        obs2 = torch.zeros_like(obs1) if obs_every else torch.zeros_like(obs1[0])
+        b.step_multi_records(acts, res2, obs2, obs_every=obs_every)
+        torch.cuda.synchronize()
+        assert torch.equal(res1[:, :B], res2[:, :B]), (key, launch)
+        assert torch.equal(a.state[:B], b.state[:B]) and torch.equal(a.chain[:B], b.chain[:B])
+        if obs_every:
+            assert torch.equal(obs1[:, :B], obs2[:, :B])
+        else:
+            assert torch.equal(obs1[T - 1, :B], obs2[:B])
+        assert a.round == b.round == (launch + 1) * T
+    assert int(res2[:, :B, lay.r_flags].max()) == 0
+    a.close(); b.close()
