@@ -494,6 +494,11 @@ def main():
             torch.cuda.synchronize()
         finally:
             sys.stdout.flush()
+            try:  # NCCL writes through C stdio: flush ITS buffer while fd 1 still points at stderr
+                import ctypes
+                ctypes.CDLL(None).fflush(None)
+            except Exception:
+                pass
             os.dup2(keep, 1)
             os.close(keep)
 
@@ -849,11 +854,35 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         r_ms = e0.elapsed_time(e1) / (n_rep * 8)
+        # the same loop inside ONE launch (msched_rollout_hardcoded: the agents read the observation tile in shared
+        # memory, their actions become the next step's action tile), observations written after every step
+        one = None
+        try:
+            Tm = 8
+            res_m = torch.zeros((Tm, lay.padded_envs, lay.result_words), dtype=torch.int32, device=dev)
+            obs_m = torch.zeros((Tm, lay.padded_envs, lay.obs_halfs), dtype=torch.int16, device=dev)
+            env.hardcoded_actions(random_ties=True)
+            for i in range(3):
+                env.rollout_hardcoded(res_m, obs_m, obs_every=True, random_ties=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(n_rep):
+                env.rollout_hardcoded(res_m, obs_m, obs_every=True, random_ties=True)
+            e1.record()
+            torch.cuda.synchronize()
+            m_ms = e0.elapsed_time(e1) / (n_rep * Tm)
+            one = {"value": B * N / (m_ms * 1e-3), "ms_per_step": m_ms, "steps_per_launch": Tm,
+                   "sticky_flags": int(res_m[:, :B, lay.r_flags].max().item()),
+                   "what": "msched_rollout_hardcoded: %d x (step ; hard-coded agents on the new observations) per launch, "
+                           "observations written after every step" % Tm}
+        except L.MschedError as e:
+            one = {"unavailable": str(e)}
         env.set_device_round(False)
         rollout = {"value": B * N / (r_ms * 1e-3), "unit": "agent-steps/s", "ms_per_step": r_ms, "steps": n_rep * 8,
                    "launches_per_step": 2, "sticky_flags": int(res_r[:B, lay.r_flags].max().item()),
                    "what": "DividedHardcodedAgent.getActions of every agent (msched_hardcoded_actions, Philox ties) + the fused env "
-                           "step + observations, 8 steps per CUDA-graph replay"}
+                           "step + observations, 8 steps per CUDA-graph replay",
+                   "one_launch": one}
     elif args.rollout_steps > 0 and dense and world == 1:
         from marl_scheduling_b200 import policy
         free = mode.startswith("free")

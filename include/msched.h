@@ -288,6 +288,18 @@ int msched_auctioneer_action(void *handle, int random_ties, int16_t *out_dev, vo
 int msched_hardcoded_actions(void *handle, const int16_t *obs_dev, int random_ties, const float *u_override_dev,
                              int16_t *action_dev, int32_t *ncand_dev, void *stream);
 
+/* The rollout loop of BASELINE config 1 (src/trainHC.py:60-95: getActionForAllAgents -> step, hard-coded agents and
+ * auctioneer) on the device: n_steps x ( SchedulingEnv.step ; DividedHardcodedAgent.getActions on the NEW
+ * observations ) in ONE launch of the multi-step fused kernel -- the agents' units of an environment are evaluated on
+ * the observation tile in shared memory and their actions become the next step's action tile without leaving the SM.
+ * action_dev: IN the action record of the first step (msched_hardcoded_actions on the current observations), OUT the
+ * agents' actions for the step after the last (so launches chain).  result_dev [n_steps][padded_envs][result_words];
+ * obs_dev as in msched_step_multi (every step with obs_every, else the last step's).  Tie draws as in
+ * msched_hardcoded_actions (Philox at the round of the observations; random_ties == 0: first candidate).  Same
+ * results, bit for bit, as the two-launch loop.  Fixed prices, in-kernel auction, device spawn draws. */
+int msched_rollout_hardcoded(void *handle, int16_t *action_dev, int n_steps, uint32_t *result_dev, int16_t *obs_dev,
+                             int obs_every, int random_ties, void *stream);
+
 /* debug / parity: reference-shaped int32 dump of envs [env0, env0+count):
  * core [C][7] owner,prio,rem,jobid,kind,birth,init ; slot [N*L][7] prio,rem,jobid,kind,wait,
  * birth,init ; offer [N*L][5] core(0 none),recipient,price,time,offerID ;

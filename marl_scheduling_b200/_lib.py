@@ -133,6 +133,7 @@ SYMBOLS = {
     "msched_step": (C.c_int, [P, P, P, P, P]),
     "msched_step_observe": (C.c_int, [P, P, P, P, P, P]),
     "msched_step_multi": (C.c_int, [P, P, C.c_int, P, P, C.c_int, P]),
+    "msched_rollout_hardcoded": (C.c_int, [P, P, C.c_int, P, P, C.c_int, C.c_int, P]),
     "msched_step_host": (C.c_int, [P, P, P, P, P]),
     "msched_get_compact_result_layout": (C.c_int, [C.POINTER(MschedConfig), C.POINTER(MschedCompactResultLayout)]),
     "msched_step_host_compact": (C.c_int, [P, P, P, P, P]),

@@ -375,6 +375,20 @@ class BatchedSchedulingEnv:
         out = (self.acceptor_actions, self.offer_core_actions)
         return out + (nc,) if want_ncand else out
 
+    def rollout_hardcoded(self, results, obs=None, obs_every=False, random_ties=True):
+        """msched_rollout_hardcoded: T = results.shape[0] x (step ; hard-coded agents on the new observations) in ONE
+        launch.  The env's action record must hold the first step's actions (hardcoded_actions()); afterwards it holds
+        the agents' actions for the step after the last.  results int32 [T, padded_envs, result_words]; obs: the env's
+        observation record (last step) or int16 [T, padded_envs, obs_halfs] with obs_every.  Asynchronous."""
+        T = int(results.shape[0])
+        assert results.is_contiguous()
+        if obs is None:
+            assert not obs_every
+            obs = self._obs_buffer()
+        L.check(self.lib.msched_rollout_hardcoded(self.handle, self.action.data_ptr(), T, results.data_ptr(), obs.data_ptr(),
+                                                  1 if obs_every else 0, int(bool(random_ties)), self._stream()))
+        return results, obs
+
     # ------------------------------------------------------------------ debug / parity
     def export_state(self, env0=0, count=None):
         """Reference-shaped dump (numpy) of envs [env0, env0+count), see include/msched.h."""

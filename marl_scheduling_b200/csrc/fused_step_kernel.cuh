@@ -35,6 +35,7 @@
 #pragma once
 #include "msched_common.cuh"
 #include "observe_kernel.cuh"
+#include "hardcoded_kernel.cuh"
 #include "step_kernel.cuh"
 
 namespace msched {
@@ -148,17 +149,20 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     // re-read each step (the observation tile overlays it); without, the state tile stays in shared memory and only
     // the action tile of the next step is fetched
     const int nSteps = MULTI ? (p.nSteps > 1 ? p.nSteps : 1) : 1;  // (the one-step instantiation folds the loop away)
+    const bool hc = MULTI && p.hcPolicy != 0;  // the hard-coded agents act inside the loop (msched_rollout_hardcoded)
+    constexpr int HCU = (N * C + NL + R - 1) / R;  // their units per thread
     unsigned ticket = 0u;
-    bool stateResident = false;
+    bool stateResident = false, actResident = false;
 #pragma unroll 1
     for (int tStep = 0; tStep < nSteps; ++tStep) {
     const int round = round0 + tStep;
     const bool lastStep = tStep == nSteps - 1;
-    const bool obsThis = withObs && (lastStep || p.obsEvery != 0);
+    const bool obsStore = withObs && (lastStep || p.obsEvery != 0);
+    const bool obsThis = obsStore || (withObs && hc);  // (the agents read the observation tile of every step)
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&bar, 32u * (uint32_t)((stateResident ? 0 : W) + AW) * 4u);
+        mbar_expect_tx(&bar, 32u * (uint32_t)((stateResident ? 0 : W) + (actResident ? 0 : AW)) * 4u);
         if (!stateResident) bulk_g2s(sState, p.state + (size_t)env0 * W, 32u * W * 4u, &bar);
-        bulk_g2s(sAct, p.action + (size_t)tStep * p.actStep + (size_t)env0 * p.AH, 32u * (uint32_t)AW * 4u, &bar);
+        if (!actResident) bulk_g2s(sAct, p.action + (size_t)tStep * p.actStep + (size_t)env0 * p.AH, 32u * (uint32_t)AW * 4u, &bar);
     }
 
     uint32_t *st = sState + (size_t)lane * W;
@@ -644,11 +648,40 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     }
     fence_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) {
+    // DividedHardcodedAgent.getActions on the observation tile (src/Agent.py:622-641, src/HardcodedModules.py:16-45,
+    // 81-109): the units of the lane's environment are dealt to the role warps
+    int16_t hcAct[HCU];
+    if (hc) {
+        const int16_t *ob16 = reinterpret_cast<const int16_t *>(sObs + (size_t)lane * OW);
+#pragma unroll
+        for (int i = 0; i < HCU; ++i) {
+            const int unit = w + i * R;
+            hcAct[i] = 0;
+            if (unit < N * C + NL) {
+                const float u = p.hcRandomTies ? hc_unit_draw(p, round + 1, env, unit) : 0.f;
+                int nc;
+                hcAct[i] = (int16_t)hc_unit_action(p, ob16, p.hcOAcc, p.hcOOff, p.hcAccRow, p.hcOffRow, unit, u, nc);
+            }
+        }
+    }
+    if (threadIdx.x == 0 && obsStore) {
         bulk_s2g(reinterpret_cast<uint32_t *>(p.obs + (p.obsEvery ? (size_t)tStep * p.obsStep : 0)) + (size_t)env0 * OW, sObs,
                  32u * (uint32_t)OW * 4u);
         bulk_commit();
         bulk_wait_read();
+    }
+    if (hc) {
+        __syncthreads();  // the rows have been read (and the observation store has read the tile)
+        // the next step's action tile, or, after the last step, the action record in global memory
+        int16_t *dstA = lastStep ? p.actionOut + (size_t)env * p.AH : reinterpret_cast<int16_t *>(sAct + (size_t)lane * AW);
+        if (!lastStep || live) {
+#pragma unroll
+            for (int i = 0; i < HCU; ++i) {
+                const int unit = w + i * R;
+                if (unit < N * C + NL) dstA[unit < N * C ? p.aAcc + unit : p.aOffc + unit - N * C] = hcAct[i];
+            }
+        }
+        actResident = !lastStep;
     }
     }  // obsThis
     if (!lastStep) __syncthreads();  // the stores have read the tiles: the next step may overwrite them

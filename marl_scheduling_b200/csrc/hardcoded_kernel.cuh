@@ -37,27 +37,17 @@ __device__ __forceinline__ void hc_ratio(int a, int b, int &num, int &den)
     else { num = a; den = b; }
 }
 
-__global__ void __launch_bounds__(128) hardcoded_policy_kernel(const __grid_constant__ DevParams p, const HardcodedArgs a)
+// the action of one unit (acceptors 0 .. N*C-1, offerers N*C ..) from the environment's dense observation record `ob`
+// (global memory or the shared-memory tile of the fused kernel); nc = number of tie candidates (0: no choice made)
+__device__ __forceinline__ int hc_unit_action(const DevParams &p, const int16_t *ob, int oAcc, int oOff, int accRow, int offRow, int unit,
+                                              float u, int &nc)
 {
-    const int U = p.N * p.C + p.NL;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (long long)p.B * U) return;
-    const int env = (int)(gid / U), unit = (int)(gid % U);
-    const int16_t *ob = a.obs + (size_t)env * p.OH;
-    float u = 0.f;
-    if (a.uOverride) {
-        u = a.uOverride[gid];
-    } else if (a.randomTies) {
-        uint32_t x[4];
-        env_draw(p, env, kStreamHardcoded, (uint32_t)(unit >> 2), 0u, x);
-        const uint32_t xv = (unit & 3) == 0 ? x[0] : (unit & 3) == 1 ? x[1] : (unit & 3) == 2 ? x[2] : x[3];
-        u = (float)(xv >> 8) * (1.0f / 16777216.0f);
-    }
-    int act, nc = 0;
+    nc = 0;
+    int act;
     if (unit < p.N * p.C) {
         // ---- HardcodedAcceptor: accept the best offeredReward/necessaryTime if it beats the own job's
         // priority/remainingLength, else reject (index NL); not the owner -> reject ----
-        const int16_t *row = ob + a.oAcc + (size_t)unit * a.accRow;
+        const int16_t *row = ob + oAcc + (size_t)unit * accRow;
         act = p.NL;
         if (row[0] != 0) {
             int on, od;
@@ -89,12 +79,11 @@ __global__ void __launch_bounds__(128) hardcoded_policy_kernel(const __grid_cons
                 nc = 0;
             }
         }
-        a.action[(size_t)env * p.AH + p.aAcc + unit] = (int16_t)act;
     } else {
         // ---- HardcodedOfferer: offer to a (random) core with the LOWEST priority/remainingLength, an
         // idle core rating -1; never abstains ----
         const int s = unit - p.N * p.C;
-        const int16_t *row = ob + a.oOff + (size_t)s * a.offRow;
+        const int16_t *row = ob + oOff + (size_t)s * offRow;
         int bn = 0, bd = 0;
         for (int j = 0; j < p.C; ++j) {
             int n, d;
@@ -116,8 +105,34 @@ __global__ void __launch_bounds__(128) hardcoded_policy_kernel(const __grid_cons
                 ++t;
             }
         }
-        a.action[(size_t)env * p.AH + p.aOffc + s] = (int16_t)act;
     }
+    return act;
+}
+
+// the unit's tie draw: word unit % 4 of Philox call unit / 4 of the hard-coded-agents stream, at the round the
+// observations belong to
+__device__ __forceinline__ float hc_unit_draw(const DevParams &p, int round, int env, int unit)
+{
+    uint32_t x[4];
+    env_draw_at(p, round, env, kStreamHardcoded, (uint32_t)(unit >> 2), 0u, x);
+    const uint32_t xv = (unit & 3) == 0 ? x[0] : (unit & 3) == 1 ? x[1] : (unit & 3) == 2 ? x[2] : x[3];
+    return (float)(xv >> 8) * (1.0f / 16777216.0f);
+}
+
+__global__ void __launch_bounds__(128) hardcoded_policy_kernel(const __grid_constant__ DevParams p, const HardcodedArgs a)
+{
+    const int U = p.N * p.C + p.NL;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)p.B * U) return;
+    const int env = (int)(gid / U), unit = (int)(gid % U);
+    const int16_t *ob = a.obs + (size_t)env * p.OH;
+    float u = 0.f;
+    if (a.uOverride) u = a.uOverride[gid];
+    else if (a.randomTies) u = hc_unit_draw(p, cur_round(p), env, unit);
+    int nc;
+    const int act = hc_unit_action(p, ob, a.oAcc, a.oOff, a.accRow, a.offRow, unit, u, nc);
+    if (unit < p.N * p.C) a.action[(size_t)env * p.AH + p.aAcc + unit] = (int16_t)act;
+    else a.action[(size_t)env * p.AH + p.aOffc + unit - p.N * p.C] = (int16_t)act;
     if (a.ncand) a.ncand[gid] = nc;
 }
 

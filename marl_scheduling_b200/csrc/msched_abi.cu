@@ -706,6 +706,34 @@ int msched_step_multi(void *handle, const int16_t *action_dev, int n_steps, uint
     return MSCHED_OK;
 }
 
+int msched_rollout_hardcoded(void *handle, int16_t *action_dev, int n_steps, uint32_t *result_dev, int16_t *obs_dev, int obs_every,
+                             int random_ties, void *stream)
+{
+    Handle *h = static_cast<Handle *>(handle);
+    if (!h || !action_dev || !result_dev || !obs_dev) return fail(MSCHED_E_ARG, "null handle/action/result/obs");
+    if (n_steps < 1 || n_steps > 4096) return fail(MSCHED_E_ARG, "n_steps out of range");
+    if (!h->useFused || !h->multiFn) return fail(MSCHED_E_ARG, "msched_rollout_hardcoded: no multi-step kernel for this domain / role count");
+    if (h->cfg.freePrices || h->cfg.auctionMode == MSCHED_AUCTION_EXTERNAL || h->cfg.spawnMode != MSCHED_SPAWN_PHILOX)
+        return fail(MSCHED_E_ARG, "msched_rollout_hardcoded: fixed prices, in-kernel auction and device spawn draws only (the agents fill "
+                                  "the acceptor and offer-core fields of the action record, nothing else)");
+    if (!h->p.state) return fail(MSCHED_E_STATE, "state not bound");
+    if (!aligned16(action_dev) || !aligned16(result_dev) || !aligned16(obs_dev)) return fail(MSCHED_E_ARG, "buffers must be 16-byte aligned");
+    DevParams p = h->p;
+    p.action = action_dev; p.actionOut = action_dev; p.spawnU = nullptr; p.result = result_dev; p.obs = obs_dev; p.cres = nullptr;
+    p.nSteps = n_steps; p.obsEvery = obs_every ? 1 : 0;
+    p.actStep = 0; p.resStep = (long long)p.Bpad * p.RW; p.obsStep = (long long)p.Bpad * p.OH;
+    p.hcPolicy = 1; p.hcRandomTies = random_ties ? 1 : 0;
+    p.hcOAcc = h->lay.o_acceptor; p.hcOOff = h->lay.o_offer; p.hcAccRow = h->lay.o_acc_row; p.hcOffRow = h->lay.o_off_row;
+    p.round = (int)h->round;
+    p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
+    p.roundDev = h->deviceRound ? h->roundDev : nullptr;
+    p.roundTicket = h->deviceRound ? reinterpret_cast<unsigned *>(h->roundDev + 1) : nullptr;
+    h->multiFn<<<p.Bpad / 32, 32 * h->fusedRoles, h->fusedSmemObs, static_cast<cudaStream_t>(stream)>>>(p);
+    CUDA_TRY(cudaGetLastError());
+    h->round += n_steps;
+    return MSCHED_OK;
+}
+
 int msched_get_compact_result_layout(const MschedConfig *cfg, MschedCompactResultLayout *out)
 {
     MschedLayout lay;

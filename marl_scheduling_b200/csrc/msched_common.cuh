@@ -72,6 +72,10 @@ struct DevParams {
     // without obsEvery only the last step builds observations and the state tile stays in shared memory in between
     int nSteps, obsEvery;
     long long actStep, resStep, obsStep;
+    // ... with the hard-coded agents in the loop (msched_rollout_hardcoded): the actions of step t+1 are computed from
+    // the observation tile of step t inside the kernel; the actions after the last step go to actionOut
+    int hcPolicy, hcRandomTies, hcOAcc, hcOOff, hcAccRow, hcOffRow;
+    int16_t *actionOut;
 };
 
 // ---- host+device layout arithmetic ------------------------------------------------------

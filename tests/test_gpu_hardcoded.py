@@ -90,3 +90,41 @@ def test_hardcoded_env_closed_loop_matches_oracle():
         for k in ("core_owner", "core_rem", "core_jobid", "slot_rem", "slot_jobid", "off_core", "chain_len"):
             assert np.array_equal(np.asarray(e[k][b]), np.asarray(ob[k])), (b, k)
     env.close()
+
+
+@pytest.mark.parametrize("obs_every,ties,dev_round", [(False, True, False), (True, True, True), (True, False, False)])
+def test_rollout_hardcoded_one_launch_matches_two_launch_loop(obs_every, ties, dev_round):
+    """msched_rollout_hardcoded (config 1: T x (step ; hard-coded agents) inside ONE launch, the agents reading the
+    observation tile in shared memory) against the loop of msched_step_observe + msched_hardcoded_actions: result
+    records of every step, final state, chains, observations and the next action record, bit for bit; two launches."""
+    import torch
+    from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
+    dom = dict(N=2, C=3, L=2, prios=[5], lens=[4], probs=[1], fix=[3], mult=2)
+    B, T = 900, 11
+    mk = lambda: BatchedSchedulingEnv(B, world_params_from_dom(dom, False), reward="fix", auction="random", spawn="philox", seed=5)
+    a, b = mk(), mk()
+    if dev_round:
+        a.set_device_round(True); b.set_device_round(True)
+    lay, dev = a.layout, a.device
+    for e in (a, b):
+        e.observe()
+        e.hardcoded_actions(random_ties=ties)
+    for launch in range(2):
+        res1 = torch.zeros((T, lay.padded_envs, lay.result_words), dtype=torch.int32, device=dev)
+        obs1 = torch.zeros((T, lay.padded_envs, lay.obs_halfs), dtype=torch.int16, device=dev)
+        for t in range(T):
+            a.step_observe_records(a.action, res1[t], obs=obs1[t])
+            a.hardcoded_actions(obs=obs1[t], random_ties=ties)
+        res2 = torch.zeros_like(res1)
+        obs2 = torch.zeros_like(obs1) if obs_every else torch.zeros_like(obs1[0])
+        b.rollout_hardcoded(res2, obs2, obs_every=obs_every, random_ties=ties)
+        torch.cuda.synchronize()
+        assert torch.equal(res1[:, :B], res2[:, :B]), launch
+        assert torch.equal(a.state[:B], b.state[:B]) and torch.equal(a.chain[:B], b.chain[:B])
+        assert torch.equal(obs1[:, :B], obs2[:, :B]) if obs_every else torch.equal(obs1[T - 1, :B], obs2[:B])
+        NC, NL = a.N * a.C, a.NL
+        assert torch.equal(a.action[:B, lay.a_acceptor:lay.a_acceptor + NC], b.action[:B, lay.a_acceptor:lay.a_acceptor + NC])
+        assert torch.equal(a.action[:B, lay.a_offer_core:lay.a_offer_core + NL], b.action[:B, lay.a_offer_core:lay.a_offer_core + NL])
+        assert a.round == b.round == (launch + 1) * T
+    assert int(res2[:, :B, lay.r_agent:lay.r_agent + a.N].sum()) > 0     # jobs terminate, agents earn
+    a.close(); b.close()
