@@ -103,7 +103,7 @@ __host__ __device__ constexpr int fused_spec(int mode, int auction, int spawn, i
     return mode | (auction << 2) | (spawn << 4) | (newJobsIsOne << 6);
 }
 
-template <int N, int C, int L, int R, int SPEC = -1, bool MULTI = false>
+template <int N, int C, int L, int R, int SPEC = -1, bool MULTI = false, bool HC = false>
 __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 16 : 8) : 1)
     fused_step_kernel(const __grid_constant__ DevParams p)
 {
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     // re-read each step (the observation tile overlays it); without, the state tile stays in shared memory and only
     // the action tile of the next step is fetched
     const int nSteps = MULTI ? (p.nSteps > 1 ? p.nSteps : 1) : 1;  // (the one-step instantiation folds the loop away)
-    const bool hc = MULTI && p.hcPolicy != 0;  // the hard-coded agents act inside the loop (msched_rollout_hardcoded)
+    constexpr bool hc = MULTI && HC;  // the hard-coded agents act inside the loop (msched_rollout_hardcoded): own instantiation
     constexpr int HCU = (N * C + NL + R - 1) / R;  // their units per thread
     unsigned ticket = 0u;
     bool stateResident = false, actResident = false;
@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
     // DividedHardcodedAgent.getActions on the observation tile (src/Agent.py:622-641, src/HardcodedModules.py:16-45,
     // 81-109): the units of the lane's environment are dealt to the role warps
     int16_t hcAct[HCU];
-    if (hc) {
+    if constexpr (hc) {
         const int16_t *ob16 = reinterpret_cast<const int16_t *>(sObs + (size_t)lane * OW);
 #pragma unroll
         for (int i = 0; i < HCU; ++i) {
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
         bulk_commit();
         bulk_wait_read();
     }
-    if (hc) {
+    if constexpr (hc) {
         __syncthreads();  // the rows have been read (and the observation store has read the tile)
         // the next step's action tile, or, after the last step, the action record in global memory
         int16_t *dstA = lastStep ? p.actionOut + (size_t)env * p.AH : reinterpret_cast<int16_t *>(sAct + (size_t)lane * AW);

@@ -148,6 +148,7 @@ struct Handle {
     bool useWarp;
     StepKernel fusedFn;  // compile-time-domain register-resident kernel (step + observations), or null
     StepKernel multiFn = nullptr;  // its multi-step instantiation (msched_step_multi), or null
+    StepKernel hcFn = nullptr;     // ... with the hard-coded agents in the loop (msched_rollout_hardcoded), or null
     size_t fusedSmem, fusedSmemObs;  // dynamic shared memory without / with the observation tile
     int fusedRoles;                  // warps per 32-env tile
     bool useFused, fuseObs;
@@ -217,24 +218,28 @@ StepKernel pick_fused_spec(const MschedConfig &c, int roles)
 
 // the multi-step instantiations (msched_step_multi): the BASELINE configurations and the generic 2-role kernels of
 // their domains
-StepKernel pick_fused_multi(const MschedConfig &c, int roles, bool spec)
+template <bool HC>
+StepKernel pick_fused_multi_t(const MschedConfig &c, int roles, bool spec)
 {
     const bool baseline = spec && c.spawnMode == MSCHED_SPAWN_PHILOX && c.newJobsPerRound == 1 && c.auctionMode == MSCHED_AUCTION_RANDOM_MAX;
     if (c.N == 2 && c.C == 3 && c.L == 3 && (roles == 2 || roles == 4)) {
         constexpr int S = fused_spec(MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL, MSCHED_AUCTION_RANDOM_MAX, MSCHED_SPAWN_PHILOX, 1);
-        if (baseline && c.rewardVariant == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL)
-            return roles == 2 ? fused_step_kernel<2, 3, 3, 2, S, true> : fused_step_kernel<2, 3, 3, 4, S, true>;
-        return roles == 2 ? fused_step_kernel<2, 3, 3, 2, -1, true> : fused_step_kernel<2, 3, 3, 4, -1, true>;
+        if constexpr (!HC)  // (the hard-coded agents play fixed prices)
+            if (baseline && c.rewardVariant == MSCHED_REWARD_DIVIDED_FREE_COMMERCIAL)
+                return roles == 2 ? fused_step_kernel<2, 3, 3, 2, S, true> : fused_step_kernel<2, 3, 3, 4, S, true>;
+        return roles == 2 ? fused_step_kernel<2, 3, 3, 2, -1, true, HC> : fused_step_kernel<2, 3, 3, 4, -1, true, HC>;
     }
     if (c.N == 4 && c.C == 4 && c.L == 3 && roles == 4) {
         constexpr int S = fused_spec(MSCHED_REWARD_DIVIDED_FIXED, MSCHED_AUCTION_RANDOM_MAX, MSCHED_SPAWN_PHILOX, 1);
-        if (baseline && c.rewardVariant == MSCHED_REWARD_DIVIDED_FIXED) return fused_step_kernel<4, 4, 3, 4, S, true>;
-        return fused_step_kernel<4, 4, 3, 4, -1, true>;
+        if (baseline && c.rewardVariant == MSCHED_REWARD_DIVIDED_FIXED) return fused_step_kernel<4, 4, 3, 4, S, true, HC>;
+        return fused_step_kernel<4, 4, 3, 4, -1, true, HC>;
     }
     if (c.N == 2 && c.C == 3 && c.L == 2 && (roles == 2 || roles == 4))
-        return roles == 2 ? fused_step_kernel<2, 3, 2, 2, -1, true> : fused_step_kernel<2, 3, 2, 4, -1, true>;
+        return roles == 2 ? fused_step_kernel<2, 3, 2, 2, -1, true, HC> : fused_step_kernel<2, 3, 2, 4, -1, true, HC>;
     return nullptr;
 }
+StepKernel pick_fused_multi(const MschedConfig &c, int roles, bool spec) { return pick_fused_multi_t<false>(c, roles, spec); }
+StepKernel pick_fused_hc(const MschedConfig &c, int roles, bool spec) { return pick_fused_multi_t<true>(c, roles, spec); }
 
 StepKernel pick_fused_kernel(int N, int C, int L, int roles)
 {
@@ -440,6 +445,9 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
         h->multiFn = h->fuseObs ? pick_fused_multi(*cfg, h->fusedRoles, !getenv("MSCHED_NO_SPEC")) : nullptr;
         if (h->multiFn)
             CUDA_TRY(cudaFuncSetAttribute(h->multiFn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fusedSmemObs));
+        h->hcFn = (h->fuseObs && !cfg->freePrices) ? pick_fused_hc(*cfg, h->fusedRoles, !getenv("MSCHED_NO_SPEC")) : nullptr;
+        if (h->hcFn)
+            CUDA_TRY(cudaFuncSetAttribute(h->hcFn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->fusedSmemObs));
     }
     // MSCHED_STEP_IMPL=fused|lane|coop forces one implementation (tests run all of them)
     if (const char *e = getenv("MSCHED_STEP_IMPL")) {
@@ -712,7 +720,7 @@ int msched_rollout_hardcoded(void *handle, int16_t *action_dev, int n_steps, uin
     Handle *h = static_cast<Handle *>(handle);
     if (!h || !action_dev || !result_dev || !obs_dev) return fail(MSCHED_E_ARG, "null handle/action/result/obs");
     if (n_steps < 1 || n_steps > 4096) return fail(MSCHED_E_ARG, "n_steps out of range");
-    if (!h->useFused || !h->multiFn) return fail(MSCHED_E_ARG, "msched_rollout_hardcoded: no multi-step kernel for this domain / role count");
+    if (!h->useFused || !h->hcFn) return fail(MSCHED_E_ARG, "msched_rollout_hardcoded: no multi-step kernel for this domain / role count");
     if (h->cfg.freePrices || h->cfg.auctionMode == MSCHED_AUCTION_EXTERNAL || h->cfg.spawnMode != MSCHED_SPAWN_PHILOX)
         return fail(MSCHED_E_ARG, "msched_rollout_hardcoded: fixed prices, in-kernel auction and device spawn draws only (the agents fill "
                                   "the acceptor and offer-core fields of the action record, nothing else)");
@@ -728,7 +736,7 @@ int msched_rollout_hardcoded(void *handle, int16_t *action_dev, int n_steps, uin
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     p.roundDev = h->deviceRound ? h->roundDev : nullptr;
     p.roundTicket = h->deviceRound ? reinterpret_cast<unsigned *>(h->roundDev + 1) : nullptr;
-    h->multiFn<<<p.Bpad / 32, 32 * h->fusedRoles, h->fusedSmemObs, static_cast<cudaStream_t>(stream)>>>(p);
+    h->hcFn<<<p.Bpad / 32, 32 * h->fusedRoles, h->fusedSmemObs, static_cast<cudaStream_t>(stream)>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->round += n_steps;
     return MSCHED_OK;
