@@ -86,10 +86,26 @@ int launch_tc(PolicyStepArgs &a, cudaStream_t s)
     const double ca = (double)a.acc.units * (8.0 * (KW_A <= 4 ? 4 : KW_A <= 8 ? 8 : 16) + 85 + (AP_A > 8 ? kNet16 : kNet8));
     const double co = (double)a.core.units * (8.0 * (KW_O <= 4 ? 4 : KW_O <= 8 ? 8 : 16) + 85 + (AP_O > 8 ? kNet16 : kNet8) +
                                               (AP_P > 0 ? 35 + (AP_P > 8 ? kNet16 : kNet8) : 0.0));
+    // CTAs per acceptor unit (na) and per offer unit (no): a slot walks ceil(tiles / (CTAs * SLOTS)) tiles of its unit, and
+    // the launch lasts as long as its slowest slot -- so the split is chosen on the WHOLE-TILE counts (at 512 tiles, 18 / 31
+    // CTAs per unit mean 8 and 5 tiles per slot, 16 / 32 mean 8 and 4: a fifth less for the offer units' six-layer tiles)
     const int total = g_sms * perSm;
-    int na = (int)(total * ca / (ca + co) / a.acc.units), no = (int)(total * co / (ca + co) / a.core.units);
-    na = na < 1 ? 1 : (na > nTiles ? nTiles : na);
-    no = no < 1 ? 1 : (no > nTiles ? nTiles : no);
+    const double tca = ca / a.acc.units, tco = co / a.core.units;  // cost of one tile of an acceptor / offer unit
+    int na = 1, no = 1;
+    double best = 1e300;
+    for (int x = 1; x <= nTiles && x * a.acc.units < total; ++x) {
+        int y = (total - x * a.acc.units) / a.core.units;
+        if (y < 1) break;
+        if (y > nTiles) y = nTiles;
+        const int ta = (nTiles + x * SLOTS - 1) / (x * SLOTS), to = (nTiles + y * SLOTS - 1) / (y * SLOTS);
+        const double cost = ta * tca > to * tco ? ta * tca : to * tco;
+        if (cost < best - 1e-9) { best = cost; na = x; no = y; }
+    }
+    {   // the fewest CTAs that still give these tile counts (less staging, fewer resident warps for the same work)
+        const int ta = (nTiles + na * SLOTS - 1) / (na * SLOTS), to = (nTiles + no * SLOTS - 1) / (no * SLOTS);
+        while (na > 1 && (nTiles + (na - 1) * SLOTS - 1) / ((na - 1) * SLOTS) == ta) --na;
+        while (no > 1 && (nTiles + (no - 1) * SLOTS - 1) / ((no - 1) * SLOTS) == to) --no;
+    }
     a.ctasPerAccUnit = na;
     a.ctasPerOffUnit = no;
     fn<<<a.acc.units * na + a.core.units * no, threads, smem, s>>>(a);
