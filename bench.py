@@ -603,6 +603,10 @@ def main():
             for r in recs[:n]:
                 refresh_actions(env, r, gen)
             if timed is not None:
+                # the block is enqueued BEHIND a ~150 us spin kernel: by the time the first event is stamped the graph
+                # launch is already in the queue, so the host's enqueue latency (13-15 us, as much as a step) is not
+                # inside the timed window -- the events bracket the device's execution of exactly n steps
+                torch.cuda._sleep(300000)
                 timed[0].record()
             if g is not None:
                 g.replay()
@@ -689,7 +693,8 @@ def main():
             except L.MschedError as e:
                 multi = {"unavailable": str(e)}
         l2_note = (f"inputs larger than L2: {S} shards x {per_set / 1e6:.0f} MB visited round-robin, launches "
-                   f"in blocks of {S * G} on {len(streams)} stream(s)" + (", each block one CUDA-graph replay" if use_graph else ""))
+                   f"in blocks of {S * G} on {len(streams)} stream(s)" + (", each block one CUDA-graph replay" if use_graph else "") +
+                   ", every timed block enqueued behind a 150 us spin kernel (host enqueue latency outside the events)")
         n_launch = K
     else:
         ring, gen = make_actions(torch, env, cfg.get("ring", 8), seed=1 + rank)
