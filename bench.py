@@ -275,13 +275,27 @@ def python_reference_sample(cfg, envs=64, steps=20, warm_steps=200, seconds=None
                 warm_steps=warm_steps, source=RH.REFERENCE_SRC)
 
 
+def l2_rule(args):
+    """How the GPU arm keeps its inputs out of L2 between timed iterations -- a function of the arguments alone, so
+    that both arms print the same `config` (the reference arm runs on the GPU arm's config; it has no L2 to flush)."""
+    if args.no_flush:
+        return "warm (no flush)"
+    if args.l2 == "flush":
+        return "flushed before every timed step (256 MiB write), per-launch events"
+    return ("inputs larger than L2: independent shards of the batch (>= 200 MB of records in flight) visited round-robin, "
+            f"launches in blocks on {args.streams} stream(s)" + (", each block one CUDA-graph replay" if args.graph == 1 else "") +
+            ", every timed block enqueued behind a 150 us spin kernel (host enqueue latency outside the events); "
+            "`--l2 auto` falls back to the flush protocol for domains whose step is two launches")
+
+
 def workload_config(args, cfg, B):
     """The workload description both arms print (same keys and values, so the two lines name the same work)."""
     return {"workload": args.config, "domain": cfg["desc"], "envs_per_gpu": B,
             "observations": "none" if cfg.get("obs") == "none" else args.obs,
             "auctioneer": "hard-coded auction rule, random arg-max tie-break",
             "spawn": "typed spawn distribution, one draw per agent and round",
-            "actions": "uniform random indices, fresh draws every step (untimed)"}
+            "actions": "uniform random indices, fresh draws every step (untimed)",
+            "l2": l2_rule(args)}
 
 
 def run_reference(args, cfg):
@@ -1109,7 +1123,8 @@ def main():
         "value": value, "unit": "agent-steps/s", "n_gpus": world, "steps": K, "warmup": args.warmup,
         "ms_per_step": tot_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": dict(workload_config(args, cfg, B), l2=l2_note),
+        "config": workload_config(args, cfg, B),
+        "l2_detail": l2_note,
         "kernel_config": {"auctioneer": "in-kernel, random arg-max (Philox)", "spawn": "device Philox",
                           "state_warm_steps": args.state_warm, "step_impl": info["step_impl"],
                           "observations_fused_into_step_launch": bool(fused or (compact and info["step_impl"] == "warp")),
