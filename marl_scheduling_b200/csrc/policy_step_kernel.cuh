@@ -22,9 +22,9 @@
 //     the row words already in registers;
 //   * actions go straight into the environment's action record, action / log-prob (and, if asked, the input
 //     rows) into the experience buffer slot of the step.
-// fp32 SIMT: these nets are 16 wide -- a tcgen05 tile would be 87 % padding and its three accumulator round
-// trips per layer cost more issue slots than the 608 FFMAs per row they replace (measured); the
-// wider aggregated heads stay on the tensor-core kernels.
+// This is the fp32 SIMT form.  It serves observations beyond +-511 (msched_policy_step's input_bound); within that
+// bound the tensor-core kernel of policy_step_tc_kernel.cuh (same contract, same draws) runs instead: 51 us against 78 us
+// at 65,536 environments of the config-3 shape.  Shared by both: the argument structs, sample_row, pair_draws, emit_row.
 #pragma once
 #include "msched_common.cuh"
 #include "policy_common.cuh"

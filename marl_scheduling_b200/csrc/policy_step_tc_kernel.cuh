@@ -36,6 +36,10 @@
 //             row: whole sectors) one tile AHEAD into registers, converted and transposed through a warp-private
 //             staging tile to the row's owner; the same lanes write the experience-buffer copy of the row
 //   price chooser  its four inputs are picked out of the owner's staged row (already fp16) by the sampled core
+//   bound     instruction issue: ~17,000 thread instructions per environment (36 Tanh layers x ~175, 18 sampling rows x
+//             ~130) at 60 % of the issue slots; tensor pipe 22 %.  The launch lasts as long as its slowest slot, so the
+//             host splits the CTAs between the unit kinds on whole-tile counts (msched_rollout.cu); DESIGN.md 5.0 has
+//             the measured history, including the variants that lost (work queue, two tiles per slot, issuer warp)
 #pragma once
 #include "policy_step_kernel.cuh"
 #include "tc_primitives.cuh"
