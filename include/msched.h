@@ -234,14 +234,15 @@ int msched_step_host(void *handle, const int16_t *action_host, uint32_t *result_
  * 16-bit units) -- offer reward and price reward as IEEE half (prio1, prio1 - price and netZeroOfferReward: exact
  * for |value| <= 2048 and a half-representable netZeroOfferReward, which msched_get_compact_result_layout checks),
  * acceptor / auctioneer / agent reward as int16 (saturated with MSCHED_FLAG_COMPACT_RANGE if one does not fit) --
- * then three words: quality_sum as float32, counts (as in the full record), flags.  BASELINE config 3: 60 bytes
- * instead of 116.  Needs a domain with a fused kernel, PINNED host buffers and B a multiple of 128 (else
+ * then two words: quality_sum as float32, and counts (bits 0..24, as in the full record) with the sticky flags in
+ * bits 25..31 (c_flags == c_counts).  BASELINE config 3: 56 bytes instead of 116, and a 32-env tile of 1,792 bytes
+ * = 7 x 256, so every tile written over PCIe starts on a 256-byte boundary.  Needs a domain with a fused kernel, PINNED host buffers and B a multiple of 128 (else
  * MSCHED_E_ARG: use msched_step_host); the kernel's bulk copies read the actions from and write the compact
  * records to host memory directly. */
 typedef struct MschedCompactResultLayout {
-    int32_t words;                                             /* uint32 per env (odd) */
+    int32_t words;                                             /* uint32 per env */
     int32_t c_offer, c_price, c_acceptor, c_auctioneer, c_agent; /* 16-bit element offsets (-1 = absent) */
-    int32_t c_quality, c_counts, c_flags;                      /* word offsets */
+    int32_t c_quality, c_counts, c_flags;                      /* word offsets; flags = bits 25..31 of the counts word */
 } MschedCompactResultLayout;
 int msched_get_compact_result_layout(const MschedConfig *cfg, MschedCompactResultLayout *out);
 int msched_step_host_compact(void *handle, const int16_t *action_host, uint32_t *cresult_host, int16_t *obs_dev,

@@ -257,7 +257,7 @@ class BatchedSchedulingEnv:
         out["n_accepted"] = (counts >> 8) & 0xFF
         out["n_terminated"] = (counts >> 16) & 0xFF
         out["done"] = (counts >> 24) & 0x1
-        out["flags"] = r[:, cl.c_flags]
+        out["flags"] = (r[:, cl.c_flags] >> 25) & 0x7F   # the sticky flags share the counts word (bits 25..31)
         return out
 
     # ------------------------------------------------------------------ result record views

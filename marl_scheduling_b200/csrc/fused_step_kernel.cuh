@@ -564,9 +564,8 @@ __global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 
         for (int k = 0; k < N; ++k) ch[p.cAgent + k] = live ? compact_i(resi[p.rAgent + k], cflags) : (uint16_t)0;
         for (int k = p.cAgent + N; k < 2 * p.cTail; ++k) ch[k] = 0;
         cr[p.cTail] = live ? __float_as_uint((float)qualSum) : 0u;
-        cr[p.cTail + 1] = live ? res[p.rCounts] : 0u;
-        cr[p.cTail + 2] = live ? (res[p.rFlags] | cflags) : 0u;
-        for (int k = p.cTail + 3; k < p.CW; ++k) cr[k] = 0u;
+        cr[p.cTail + 1] = live ? ((res[p.rCounts] & 0x01ffffffu) | ((res[p.rFlags] | cflags) << 25)) : 0u;  // flags: bits 25..31
+        for (int k = p.cTail + 2; k < p.CW; ++k) cr[k] = 0u;
     }
 
     // ---- the new state and the result record leave; the observation rows are then staged in the

@@ -122,8 +122,12 @@ int compute_compact_layout(const MschedConfig *c, const MschedLayout &l, MschedC
     o->c_auctioneer = h; h += c->C;
     o->c_agent = h; h += c->N;
     const int w = (h + 1) / 2;
-    o->c_quality = w; o->c_counts = w + 1; o->c_flags = w + 2;
-    o->words = make_odd(w + 3);
+    // tail: quality_sum (float32), then ONE word: counts in bits 0..24 as in the full record, the sticky flags in bits
+    // 25..31.  The word count is not forced odd: config 3's 14 words make a 32-env tile 1,792 bytes = 7 x 256, so every
+    // tile the kernel writes over PCIe starts on a 256-byte boundary (the 2-way bank conflict of an even stride costs
+    // a few dozen shared-memory stores per tile)
+    o->c_quality = w; o->c_counts = w + 1; o->c_flags = w + 1;
+    o->words = w + 2;
     return MSCHED_OK;
 }
 

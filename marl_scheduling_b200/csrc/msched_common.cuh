@@ -65,7 +65,7 @@ struct DevParams {
     int COH;                       // compact observation halfs per env
     // compact result record (msched_step_host_compact): int16 / half planes instead of int32 / float32
     uint32_t *cres;                // compact result records, or null -> the full record goes to `result`
-    int CW;                        // compact result words per env (odd)
+    int CW;                        // compact result words per env
     int cOffer, cPrice, cAcc, cAuc, cAgent, cTail;  // half offsets of the planes; word offset of [quality f32, counts, flags]
     // multi-step launches of the fused kernel (msched_step_multi): nSteps consecutive steps per launch, step t reads
     // action + t * actStep (int16), writes result + t * resStep (uint32) and, if obsEvery, obs + t * obsStep (int16);
