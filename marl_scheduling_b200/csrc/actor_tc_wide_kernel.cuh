@@ -386,8 +386,8 @@ inline int launch_actor_shape(const ActorArgs &a, const MschedMlpGroup &g, dim3 
         actor_forward_tc<H, AP><<<dim3(gx, grid.y), 128, smem, s>>>(a);
         return 0;
     }
-    if constexpr (H > 32) {
-        return -1;  // the fp32 SIMT kernel is built for the 16- and 32-wide nets only (64 accumulators per layer spill)
+    if constexpr (H > 16) {
+        return -1;  // the fp32 SIMT kernel is built for the 16-wide nets only (the wider nets run on the tensor cores)
     } else {
     const int Apad = (g.n_actions + 3) & ~3;
     const size_t smem = sizeof(float) * ((size_t)g.n_in * H + H + (size_t)H * H + H + (size_t)H * Apad + Apad);
@@ -399,7 +399,7 @@ inline int launch_actor_shape(const ActorArgs &a, const MschedMlpGroup &g, dim3 
 }
 
 template <int H>
-inline int launch_actor_h(const ActorArgs &a, const MschedMlpGroup &g, dim3 grid, int impl, cudaStream_t s)
+int launch_actor_h(const ActorArgs &a, const MschedMlpGroup &g, dim3 grid, int impl, cudaStream_t s)
 {
     const int ap = (g.n_actions + 15) / 16 * 16;
     if (ap == 16) return launch_actor_shape<H, 16>(a, g, grid, impl, s);
@@ -411,7 +411,7 @@ inline int launch_actor_h(const ActorArgs &a, const MschedMlpGroup &g, dim3 grid
 
 // aggregated heads (more than 64 actions): tensor cores only, last layer tiled over the actions
 template <int H>
-inline int launch_actor_wide(const ActorArgs &a, const MschedMlpGroup &g, dim3 grid, cudaStream_t s)
+int launch_actor_wide(const ActorArgs &a, const MschedMlpGroup &g, dim3 grid, cudaStream_t s)
 {
     const size_t smem = (size_t)actor_wide_smem(g.n_in, H).total;
     if (smem > 220 * 1024) return -1;
@@ -435,6 +435,16 @@ inline int launch_actor_wide(const ActorArgs &a, const MschedMlpGroup &g, dim3 g
     actor_forward_tc_wide<H><<<dim3(gx, grid.y), 128, smem, s>>>(a);
     return 0;
 }
+
+// The kernel families are compiled in separate translation units (the build is as long as its slowest unit):
+// msched_policy.cu holds the dispatcher and the 16-wide nets, msched_actor_h32.cu / _h64.cu the 32- / 64-wide nets,
+// msched_actor_wide.cu the aggregated heads.  The dispatcher's unit sees the others as explicit instantiations
+#ifdef MSCHED_ACTOR_DISPATCH_TU
+extern template int launch_actor_h<32>(const ActorArgs &, const MschedMlpGroup &, dim3, int, cudaStream_t);
+extern template int launch_actor_h<64>(const ActorArgs &, const MschedMlpGroup &, dim3, int, cudaStream_t);
+extern template int launch_actor_wide<16>(const ActorArgs &, const MschedMlpGroup &, dim3, cudaStream_t);
+extern template int launch_actor_wide<32>(const ActorArgs &, const MschedMlpGroup &, dim3, cudaStream_t);
+extern template int launch_actor_wide<64>(const ActorArgs &, const MschedMlpGroup &, dim3, cudaStream_t);
 
 inline ActorArgs make_actor_args(const MschedMlpGroup &g, const MschedActorIO &io)
 {
@@ -470,5 +480,7 @@ inline int launch_actor_forward(const MschedMlpGroup &g, const MschedActorIO &io
     if (g.n_hidden == 64) return launch_actor_h<64>(a, g, grid, impl, s);
     return -1;
 }
+#endif  // MSCHED_ACTOR_DISPATCH_TU (the dispatcher exists in that unit only: an inline function that names every
+        // instantiation makes the front end instantiate all of them in every unit that sees it)
 
 }  // namespace msched

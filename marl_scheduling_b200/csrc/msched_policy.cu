@@ -4,6 +4,7 @@
 #include <cstring>
 #include <cmath>
 
+#define MSCHED_ACTOR_DISPATCH_TU  // the 32- / 64-wide nets and the aggregated heads are compiled in their own units
 #include "abi_common.h"
 #include "msched_common.cuh"
 #include "policy_kernels.cuh"
@@ -44,7 +45,8 @@ int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, vo
     // heads, shapes without a one-launch kernel, tests).  MSCHED_ACTOR_IMPL=tc|simt forces one.
     int impl = (nets->n_hidden >= 32 || nets->n_actions > 16) ? 0 : 1;
     if (const char *e = getenv("MSCHED_ACTOR_IMPL")) impl = !strcmp(e, "simt") ? 1 : (!strcmp(e, "tc") ? 0 : impl);
-    if (impl == 1 && nets->n_hidden > 32) impl = 0;  // the SIMT kernel is built for the 16- and 32-wide nets
+    if (impl == 1 && nets->n_hidden > 16) impl = 0;  // the SIMT kernel is built for the 16-wide nets (the wider ones always run
+                                                     // on the tensor cores; their SIMT instantiations were 3.5 minutes of build)
     int rc = launch_actor_forward(*nets, *io, impl, static_cast<cudaStream_t>(stream));
     if (rc == -1) return fail(MSCHED_E_ARG, "unsupported MLP shape for the actor kernel");
     if (rc == -2) return fail(MSCHED_E_CUDA, "actor kernel: shared-memory attribute rejected");

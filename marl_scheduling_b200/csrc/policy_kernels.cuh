@@ -10,6 +10,7 @@
 
 namespace msched {
 
+#ifdef MSCHED_ACTOR_DISPATCH_TU  // (plain kernels: defined once, in the unit that launches them)
 // ---- discounted returns --------------------------------------------------------------------
 // One lane per unit m; rewards/out are [T][M] so that a warp touches 128 contiguous bytes per
 // time step.  G_t = r_t + gamma*G_{t+1} in float64 like the Python loop, cast to float32; the
@@ -91,6 +92,8 @@ __global__ void __launch_bounds__(128) returns_tile_kernel(const float *__restri
         bulk_wait_read();
     }
 }
+
+#endif  // MSCHED_ACTOR_DISPATCH_TU
 
 // ---- actor forward, fp32 SIMT version --------------------------------------------------------
 // grid = (ceil(n_envs / 128), units); a CTA evaluates ONE unit (one net) for 128 consecutive
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(128) actor_forward_simt(const ActorArgs a)
     }
 }
 
+#ifdef MSCHED_ACTOR_DISPATCH_TU  // (plain kernels: defined once, in the unit that launches them)
 // ---- DQNEntity.selectAction (src/DQNmodules.py:34-76), batched ------------------------------------
 // Q-net Linear(in,16)-Tanh-Linear(16,A); epsilon-greedy: with probability epsilon (the caller's
 // RUN_END + (RUN_START-RUN_END)*exp(-round/RUN_DECAY)) a uniformly random action, else arg-max Q
@@ -390,5 +394,7 @@ __global__ void __launch_bounds__(128) dqn_select_kernel(const QArgs q)
         if (a.actionRec) a.actionRec[(size_t)env * a.actionRecStride + unit] = (int16_t)act;
     }
 }
+
+#endif  // MSCHED_ACTOR_DISPATCH_TU
 
 }  // namespace msched
