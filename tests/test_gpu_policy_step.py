@@ -249,3 +249,47 @@ def test_policy_step_large_inputs_take_the_simt_kernel(monkeypatch):
         for n in (0, xw.shape[1] - 1):
             p, _, _ = O.mlp_forward(xw[:, n], *_unpack(wts, n, nin, A))
             np.testing.assert_allclose(o[2][:, n].cpu().numpy(), p, rtol=5e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("impl", ["tc", "simt"])
+def test_policy_step_two_env_shards_reproduce_the_single_shard_actions(impl, monkeypatch):
+    """Sampling draws are keyed on the GLOBAL environment index (env_offset): the policy step of two env shards, each
+    launched with its own offset as under data parallelism, gives the same actions, log-probs and experience rows as the
+    single launch over the whole batch (exploration noise must not repeat across ranks, results must
+    not depend on the number of GPUs)."""
+    monkeypatch.setenv("MSCHED_POLICY_STEP_IMPL", impl)
+    import torch
+    from marl_scheduling_b200 import policy
+    from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
+    dom = CFG3
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    NL, P, B = N * L, max(dom["prios"]), 512
+    env = BatchedSchedulingEnv(B, world_params_from_dom(dom, True), reward="free_comm", auction="random", spawn="philox", seed=8)
+    dev, lay = env.device, env.layout
+    g = torch.Generator(device=dev).manual_seed(3)
+    for t in range(10):
+        env.acceptor_actions.random_(0, 2, generator=g)
+        env.offer_core_actions.random_(0, C + 1, generator=g)
+        env.offer_price_actions.random_(0, P + 1, generator=g)
+        env.step_observe_records()
+    Ua, Uo = N * C, NL
+    ga = policy.MlpGroup.random(3 + 2 * NL, 16, NL + 1, Ua, dev, seed=51)
+    go = policy.MlpGroup.random(2 * C + 2, 16, C + 1, Uo, dev, seed=52)
+    gp = policy.MlpGroup.random(4, 16, P + 1, Uo, dev, seed=53)
+    obs = env._obs_buffer()
+
+    def run(obs_part, n, off):
+        out = [(torch.zeros((n, u), dtype=torch.int32, device=dev), torch.zeros((n, u), device=dev)) for u in (Ua, Uo, Uo)]
+        A_ = policy.policy_step_group(ga, Ua, lay.o_acceptor, lay.o_acc_row, lay.a_acceptor, 11, *out[0])
+        O_ = policy.policy_step_group(go, Uo, lay.o_offer, lay.o_off_row, lay.a_offer_core, 12, *out[1])
+        P_ = policy.policy_step_group(gp, Uo, lay.o_offer, lay.o_off_row, lay.a_offer_price, 13, *out[2])
+        policy.policy_step(obs_part, lay.obs_halfs, n, C, A_, O_, P_, env_offset=off, step=4, input_bound=16)
+        torch.cuda.synchronize()
+        return out
+    whole = run(obs, B, 1000)
+    lo, hi = run(obs[:256], 256, 1000), run(obs[256:], 256, 1256)
+    for k in range(3):
+        assert torch.equal(whole[k][0], torch.cat([lo[k][0], hi[k][0]]))
+        assert torch.equal(whole[k][1], torch.cat([lo[k][1], hi[k][1]]))
+    assert not torch.equal(lo[0][0], hi[0][0])   # (different environments, different draws)
+    env.close()
