@@ -92,15 +92,16 @@ def test_hardcoded_env_closed_loop_matches_oracle():
     env.close()
 
 
-@pytest.mark.parametrize("obs_every,ties,dev_round", [(False, True, False), (True, True, True), (True, False, False)])
-def test_rollout_hardcoded_one_launch_matches_two_launch_loop(obs_every, ties, dev_round):
+@pytest.mark.parametrize("obs_every,ties,dev_round,B", [(False, True, False, 900), (True, True, True, 900), (True, False, False, 900),
+                                                        (True, True, True, 65536)])  # the last: BASELINE configs[0]'s domain at the full batch
+def test_rollout_hardcoded_one_launch_matches_two_launch_loop(obs_every, ties, dev_round, B):
     """msched_rollout_hardcoded (config 1: T x (step ; hard-coded agents) inside ONE launch, the agents reading the
     observation tile in shared memory) against the loop of msched_step_observe + msched_hardcoded_actions: result
     records of every step, final state, chains, observations and the next action record, bit for bit; two launches."""
     import torch
     from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
     dom = dict(N=2, C=3, L=2, prios=[5], lens=[4], probs=[1], fix=[3], mult=2)
-    B, T = 900, 11
+    T = 11
     mk = lambda: BatchedSchedulingEnv(B, world_params_from_dom(dom, False), reward="fix", auction="random", spawn="philox", seed=5)
     a, b = mk(), mk()
     if dev_round:

@@ -519,17 +519,18 @@ def test_config5_full_size_windows_match_oracle_and_jobs_are_conserved():
     env.close()
 
 
-@pytest.mark.parametrize("key,auction,obs_every,dev_round", [
-    ("cfg3", "random", False, False), ("cfg3", "random", True, True), ("cfg3", "first", True, False),
-    ("cfg2", "random", True, False), ("cfg2", "random", False, True), ("cfg1", "random", False, False)])
-def test_step_multi_matches_single_steps(key, auction, obs_every, dev_round):
+@pytest.mark.parametrize("key,auction,obs_every,dev_round,B", [
+    ("cfg3", "random", False, False, 1000), ("cfg3", "random", True, True, 1000), ("cfg3", "first", True, False, 1000),
+    ("cfg2", "random", True, False, 1000), ("cfg2", "random", False, True, 1000), ("cfg1", "random", False, False, 1000),
+    ("cfg3", "random", True, True, 65536), ("cfg3", "random", False, False, 65536)])  # BASELINE's full batch
+def test_step_multi_matches_single_steps(key, auction, obs_every, dev_round, B):
     """msched_step_multi (T steps per launch, a CTA keeps its 32 environments; without obs_every the state tile stays
     in shared memory between steps) walks bit for bit through the states, result records and observations of T
     msched_step_observe calls -- host round and device round counter, two launches in a row."""
     import torch
     dom, mode = DOMS[key]
     free = mode.startswith("free")
-    B, T = 1000, 9
+    T = 9
     a = _env(B, dict(dom, mode=mode), auction=auction, spawn="philox", seed=21)
     b = _env(B, dict(dom, mode=mode), auction=auction, spawn="philox", seed=21)
     if dev_round:
