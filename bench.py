@@ -449,6 +449,33 @@ def ppo_update_dp_leg(torch, dist, dev, world, rank, T=8, B=65536, epochs=3, rep
                       "ok": bool(identical and rel < 1e-4 and moved > 0)}}
 
 
+def other_configs(args):
+    """The step leg of BASELINE.json's other configurations, each in its own process after this one's measurement is
+    over (same timing rules, same K / W; parity of every one of them is the GPU test suite's job): not bench lines
+    of their own, a record that the kernels those configurations select were run by this command."""
+    import subprocess
+    out = {}
+    for key in ("cfg1", "cfg2", "cfg4", "cfg5"):
+        cmd = [sys.executable, os.path.abspath(__file__), "--config", key, "--gpus", "1", "--steps", str(args.steps),
+               "--warmup", str(args.warmup), "--no-cpu-baseline", "--e2e-steps", "0",
+               "--rollout-steps", "200" if key == "cfg1" else "0",  # cfg1 = the hard-coded agents' rollout
+               "--update-T", "0", "--update-dp", "0", "--other-configs", "0"]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            out[key] = {"workload": d["config"].get("domain"), "envs": d["config"].get("envs_per_gpu"),
+                        "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
+                        "kernel": d["roofline"]["kernel"], "launches_per_step": d["gpu_launches"] / max(1, d["steps"]),
+                        "roofline_frac": d["roofline"]["frac"],
+                        "algorithmic_bytes_per_env_step": d["roofline"]["algorithmic_bytes_per_env_step"],
+                        "l2": d.get("l2_detail"), "sticky_flags": d.get("sticky_flags_after_warm")}
+            if d.get("rollout_with_policy"):
+                out[key]["rollout"] = d["rollout_with_policy"]
+        except Exception as e:  # a side leg must never take the bench line down
+            out[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -477,6 +504,10 @@ def main():
     ap.add_argument("--update-dp-T", type=int, default=8, help="buffer length (steps) of that leg")
     ap.add_argument("--rollout-steps", type=int, default=200,
                     help="steps of the secondary metric (env step + actor forward); 0 = skip")
+    ap.add_argument("--other-configs", type=int, default=1,
+                    help="N=1, default workload only: after the measurement, run the step leg of BASELINE's other "
+                         "configurations (each its own process, one after the other) and report them under "
+                         "`other_configs`; 0 = skip")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -1152,6 +1183,8 @@ def main():
         "wall_ms_per_step_incl_flush": 1e3 * t_wall / K,
         "sticky_flags_after_warm": flags,
     }
+    if world == 1 and args.config == "cfg3" and args.other_configs and not args.envs:
+        line["other_configs"] = other_configs(args)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
