@@ -153,7 +153,9 @@ struct Handle {
     StepKernel fusedFn;  // compile-time-domain register-resident kernel (step + observations), or null
     StepKernel multiFn = nullptr;  // its multi-step instantiation (msched_step_multi), or null
     StepKernel hcFn = nullptr;     // ... with the hard-coded agents in the loop (msched_rollout_hardcoded), or null
-    size_t fusedSmem, fusedSmemObs;  // dynamic shared memory without / with the observation tile
+    size_t fusedSmem, fusedSmemObs;  // dynamic shared memory without / with the observation tile (compact result tile included)
+    size_t fusedSmemNC, fusedSmemObsNC;  // the same for launches without the compact result tile (p.cres null): cfg3 13.6 KB
+                                         // with the reserve instead of 15.2 KB, i.e. 16 resident CTAs per SM instead of 15
     int fusedRoles;                  // warps per 32-env tile
     bool useFused, fuseObs;
     ObsKernel obsFn;  // compile-time-domain observation kernel, or null -> direct kernel
@@ -314,7 +316,8 @@ void launch_step(const Handle *h, const DevParams &p0, cudaStream_t s, bool self
     p.roundDev = h->deviceRound ? h->roundDev : nullptr;
     p.roundTicket = (h->deviceRound && selfAdvance) ? reinterpret_cast<unsigned *>(h->roundDev + 1) : nullptr;
     if (h->useFused) {
-        h->fusedFn<<<p.Bpad / 32, 32 * h->fusedRoles, p.obs ? h->fusedSmemObs : h->fusedSmem, s>>>(p);
+        const size_t smem = p.cres ? (p.obs ? h->fusedSmemObs : h->fusedSmem) : (p.obs ? h->fusedSmemObsNC : h->fusedSmemNC);
+        h->fusedFn<<<p.Bpad / 32, 32 * h->fusedRoles, smem, s>>>(p);
     } else if (h->useWarp) {
         launch_warp_step(p, h->warpSmem, s);
     } else if (h->useCoop) {
@@ -436,6 +439,8 @@ int msched_create(const MschedConfig *cfg, int device, void **handle)
         if (compute_compact_layout(cfg, lay, &h->clay) != MSCHED_OK) memset(&h->clay, 0, sizeof(h->clay));
         h->fusedSmem = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, 0, cfg->C, h->clay.words);
         h->fusedSmemObs = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, lay.obs_halfs, cfg->C, h->clay.words);
+        h->fusedSmemNC = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, 0, cfg->C, 0);
+        h->fusedSmemObsNC = fused_smem_bytes(lay.state_words, lay.action_halfs, lay.result_words, lay.obs_halfs, cfg->C, 0);
         h->fuseObs = h->fusedSmemObs <= 48 * 1024;  // cfg2 domain: 43.6 KB tile, still one launch fewer
         if (const char *e = getenv("MSCHED_FUSE_OBS"))
             h->fuseObs = atoi(e) != 0 && h->fusedSmemObs + 2048 <= (size_t)h->smemOptin;
@@ -505,7 +510,7 @@ int msched_get_info(void *handle, MschedInfo *out)
         out->fuses_observations = h->fuseObs ? 1 : 0;
         out->envs_per_cta = 32;
         out->threads_per_cta = 32 * h->fusedRoles;
-        out->smem_bytes_per_cta = (int)(h->fuseObs ? h->fusedSmemObs : h->fusedSmem);
+        out->smem_bytes_per_cta = (int)(h->fuseObs ? h->fusedSmemObsNC : h->fusedSmemNC);
     } else if (h->useWarp) {
         out->step_impl = 3;
         out->envs_per_cta = 4;
@@ -712,7 +717,7 @@ int msched_step_multi(void *handle, const int16_t *action_dev, int n_steps, uint
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     p.roundDev = h->deviceRound ? h->roundDev : nullptr;
     p.roundTicket = h->deviceRound ? reinterpret_cast<unsigned *>(h->roundDev + 1) : nullptr;
-    h->multiFn<<<p.Bpad / 32, 32 * h->fusedRoles, obs_dev ? h->fusedSmemObs : h->fusedSmem, static_cast<cudaStream_t>(stream)>>>(p);
+    h->multiFn<<<p.Bpad / 32, 32 * h->fusedRoles, obs_dev ? h->fusedSmemObsNC : h->fusedSmemNC, static_cast<cudaStream_t>(stream)>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->round += n_steps;
     return MSCHED_OK;
@@ -740,7 +745,7 @@ int msched_rollout_hardcoded(void *handle, int16_t *action_dev, int n_steps, uin
     p.doneFlag = ((h->round + 1) % h->cfg.episodeLength) == 0 ? 1 : 0;
     p.roundDev = h->deviceRound ? h->roundDev : nullptr;
     p.roundTicket = h->deviceRound ? reinterpret_cast<unsigned *>(h->roundDev + 1) : nullptr;
-    h->hcFn<<<p.Bpad / 32, 32 * h->fusedRoles, h->fusedSmemObs, static_cast<cudaStream_t>(stream)>>>(p);
+    h->hcFn<<<p.Bpad / 32, 32 * h->fusedRoles, h->fusedSmemObsNC, static_cast<cudaStream_t>(stream)>>>(p);
     CUDA_TRY(cudaGetLastError());
     h->round += n_steps;
     return MSCHED_OK;
