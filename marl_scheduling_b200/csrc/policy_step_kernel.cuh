@@ -192,21 +192,20 @@ __device__ __forceinline__ int sample_row(float (&lg)[AP], int A, float u, float
             probsOut[o] = v;
         }
     }
+    // first action whose running sum exceeds u * tot, the last action if none does: the sums never decrease
+    // (probabilities >= 0), so that index = the number of sums that do NOT exceed the threshold
     const float thr = u * tot;
-    float cdf = 0.f, pa = 0.f;
-    int act = -1;
+    float cdf = 0.f;
+    int act = 0;
 #pragma unroll
     for (int o = 0; o < AP; ++o) {
         cdf += lg[o];
-        const bool hit = act < 0 && cdf > thr;
-        act = hit ? o : act;
-        pa = hit ? lg[o] : pa;
+        act += (cdf > thr) ? 0 : 1;
     }
-    if (act < 0) {
-        act = A - 1;
+    act = min(act, A - 1);
+    float pa = lg[0];
 #pragma unroll
-        for (int o = 0; o < AP; ++o) pa = (o == A - 1) ? lg[o] : pa;
-    }
+    for (int o = 1; o < AP; ++o) pa = (o == act) ? lg[o] : pa;
     const float eps = 1.1920928955078125e-07f;
     float pn = __fdividef(pa, tot);
     pn = fminf(fmaxf(pn, eps), 1.f - eps);

@@ -209,18 +209,20 @@ __device__ __forceinline__ float rcp_approx(float x)
     return r;
 }
 
-// tanh of four pre-scaled values (z2 = 2*log2(e)*z) with one reciprocal
+// tanh of four pre-scaled values (z2 = 2*log2(e)*z) with one reciprocal: tanh z = 1 - 2 / (2^z2 + 1).  The factors
+// carry -1/2 each (folded into the "+1" as one FMA), so that the product's reciprocal comes out scaled by the -2 of
+// the formula: with e_i = -(2^z2_i + 1)/2, p = e0 e1, q = e2 e3, r = 1/(p q):  1 + e1 (q r) = 1 - 2 / (2^z2_0 + 1)
 __device__ __forceinline__ void tanh4_scaled(float &x0, float &x1, float &x2, float &x3)
 {
-    const float e0 = ex2_approx(fminf(x0, 30.f)) + 1.f, e1 = ex2_approx(fminf(x1, 30.f)) + 1.f;
-    const float e2 = ex2_approx(fminf(x2, 30.f)) + 1.f, e3 = ex2_approx(fminf(x3, 30.f)) + 1.f;
+    const float e0 = fmaf(ex2_approx(fminf(x0, 30.f)), -0.5f, -0.5f), e1 = fmaf(ex2_approx(fminf(x1, 30.f)), -0.5f, -0.5f);
+    const float e2 = fmaf(ex2_approx(fminf(x2, 30.f)), -0.5f, -0.5f), e3 = fmaf(ex2_approx(fminf(x3, 30.f)), -0.5f, -0.5f);
     const float p = e0 * e1, q = e2 * e3;
     const float r = rcp_approx(p * q);
     const float qr = q * r, pr = p * r;
-    x0 = fmaf(-2.f, e1 * qr, 1.f);
-    x1 = fmaf(-2.f, e0 * qr, 1.f);
-    x2 = fmaf(-2.f, e3 * pr, 1.f);
-    x3 = fmaf(-2.f, e2 * pr, 1.f);
+    x0 = fmaf(e1, qr, 1.f);
+    x1 = fmaf(e0, qr, 1.f);
+    x2 = fmaf(e3, pr, 1.f);
+    x3 = fmaf(e2, pr, 1.f);
 }
 
 // accumulator row (bias included) -> Tanh -> the thread's row of the next layer's hi / lo operands (8 + 8 columns)
@@ -260,6 +262,36 @@ __device__ __forceinline__ int tc_sample(uint32_t trow, int A, float u, float &l
     if constexpr (AP == 8) tmem_ld8(trow, lg);
     else tmem_ld16(trow, lg);
     return sample_row<AP>(lg, A, u, logp, probsOut);
+}
+
+// The Philox draw of the thread's row.  One Philox call serves an environment PAIR (pair_draws: words 0, 1 = the two
+// rows of the acceptor / core chooser, words 2, 3 = those of the price chooser), so the two lanes of a pair would
+// compute the same ten rounds: instead, on an even iteration j of the slot's tile loop the even lane computes the
+// call of THIS tile and the odd lane that of the slot's NEXT tile (tile + tileStep), and the two swap words with one
+// shuffle per draw -- one Philox call per thread and TWO tiles, the draws themselves unchanged.  dr = the call the
+// thread holds (kept across iterations).  Returns the row's word, the price chooser's word in vWord (WITH_V)
+// SHARE false = every thread computes its own call (the 27-input acceptor shape has no registers to keep one across
+// iterations: sharing measured 102.6 us against 97.5 us there, 48.9 against 51.4 us on the config-3 shape)
+template <bool WITH_V, bool SHARE>
+__device__ __forceinline__ uint32_t tc_pair_draw(const PolicyStepArgs &a, unsigned long long seed, int tile, int tileStep, int row,
+                                                 int unit, int j, uint32_t (&dr)[4], uint32_t &vWord)
+{
+    const int par = row & 1;  // = the lane's parity = the environment's parity (tiles start on even environments)
+    if constexpr (!SHARE) {
+        uint32_t r[4];
+        pair_draws(a, seed, tile * 128 + row, unit, r);
+        if constexpr (WITH_V) vWord = par ? r[3] : r[2];
+        return par ? r[1] : r[0];
+    }
+    if ((j & 1) == 0) pair_draws(a, seed, (tile + par * tileStep) * 128 + row, unit, dr);
+    const bool holder = par == (j & 1);  // this thread's call is the one of the current tile
+    const uint32_t got = __shfl_xor_sync(0xffffffffu, par ? dr[0] : dr[1], 1);  // what the neighbour needs of mine
+    const uint32_t u = holder ? (par ? dr[1] : dr[0]) : got;
+    if constexpr (WITH_V) {
+        const uint32_t gotV = __shfl_xor_sync(0xffffffffu, par ? dr[2] : dr[3], 1);
+        vWord = holder ? (par ? dr[3] : dr[2]) : gotV;
+    }
+    return u;
 }
 
 // Observation rows of a warp's 32 environments.  LPR lanes per row read consecutive words: lane = (row slot rs, word w),
@@ -455,6 +487,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
         const PolicyGroupArgs &g = a.acc;
         const TcRows<KW_A, SW> rl(a, g, unit, (g.xOffset - (g.xOffset & 1) + unit * g.xStride) >> 1);
         uint32_t rows[TcRows<KW_A, SW>::NI];
+        uint32_t dr[4] = {0u, 0u, 0u, 0u}, dummyV;
         if (t.slot < myTiles) rl.fetch(a.nEnvs, (slice + t.slot * stride) * 128 + wq * 32, rows);
         for (int j = 0; j * SLOTS + t.slot < myTiles; ++j) {
             const int tile = slice + (j * SLOTS + t.slot) * stride;
@@ -470,9 +503,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
             if (g.uOverride) {
                 u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
             } else {
-                uint32_t r[4];
-                pair_draws(a, g.seed, env, unit, r);
-                u = u24((env & 1) ? r[1] : r[0]);
+                u = u24(tc_pair_draw<false, (KW_A <= 8)>(a, g.seed, tile, SLOTS * stride, row, unit, j, dr, dummyV));
             }
             float lp;
             const int act = tc_run_net<AP_A, NA>(t, sNet, g.nActions, u, lp,
@@ -483,6 +514,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
         const PolicyGroupArgs &g = a.core, &gp = a.price;
         const TcRows<KW_O, SW> rl(a, g, unit, (g.xOffset + unit * g.xStride) >> 1);
         uint32_t rows[TcRows<KW_O, SW>::NI];
+        uint32_t dr[4] = {0u, 0u, 0u, 0u};
         if (t.slot < myTiles) rl.fetch(a.nEnvs, (slice + t.slot * stride) * 128 + wq * 32, rows);
         for (int j = 0; j * SLOTS + t.slot < myTiles; ++j) {
             const int tile = slice + (j * SLOTS + t.slot) * stride;
@@ -499,10 +531,9 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
                 u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
                 if (AP_P > 0 && gp.uOverride) v = live ? gp.uOverride[(size_t)env * gp.units + unit] : 0.f;
             } else {
-                uint32_t r[4];
-                pair_draws(a, g.seed, env, unit, r);
-                u = u24((env & 1) ? r[1] : r[0]);
-                v = u24((env & 1) ? r[3] : r[2]);
+                uint32_t vw;
+                u = u24(tc_pair_draw<(AP_P > 0), (KW_A <= 8)>(a, g.seed, tile, SLOTS * stride, row, unit, j, dr, vw));
+                v = u24(vw);
             }
             float lp;
             const int c = tc_run_net<AP_O, NO>(t, sNet, g.nActions, u, lp,
