@@ -217,10 +217,11 @@ __device__ __forceinline__ float u24(uint32_t x) { return (float)(x >> 8) * (1.0
 
 // draws of an environment pair for one unit: words 0,1 = the two rows of the acceptor / core chooser, words 2,3 =
 // the two rows of the price chooser.  Counter (pair lo, pair hi, step lo, 4 << 28 | step hi : 12 | unit : 16), key = seed
-__device__ __forceinline__ void pair_draws(const PolicyStepArgs &a, unsigned long long seed, int envLocal, int unit, uint32_t (&x)[4])
+__device__ __forceinline__ unsigned long long policy_step_now(const PolicyStepArgs &a) { return a.stepDev ? *a.stepDev : a.step; }
+__device__ __forceinline__ void pair_draws(const PolicyStepArgs &a, unsigned long long seed, int envLocal, int unit, uint32_t (&x)[4],
+                                           unsigned long long stp)
 {
     const unsigned long long pair = (unsigned long long)(a.envOffset + envLocal) >> 1;
-    const unsigned long long stp = a.stepDev ? *a.stepDev : a.step;
     philox4x32_10((uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)stp,
                   (kStreamPolicyStep << 28) | ((uint32_t)((stp >> 32) & 0xfffu) << 16) | (uint32_t)(unit & 0xffff),
                   (uint32_t)seed, (uint32_t)(seed >> 32), x);
@@ -317,7 +318,7 @@ __global__ void __launch_bounds__(128, 5) policy_step_kernel(const __grid_consta
                 u1 = l1 ? g.uOverride[(size_t)e1 * g.units + unit] : 0.f;
             } else {
                 uint32_t r[4];
-                pair_draws(a, g.seed, e0, unit, r);
+                pair_draws(a, g.seed, e0, unit, r, policy_step_now(a));
                 u0 = u24(r[0]); u1 = u24(r[1]);
             }
             __syncwarp();
@@ -365,7 +366,7 @@ __global__ void __launch_bounds__(128, 5) policy_step_kernel(const __grid_consta
                 }
             } else {
                 uint32_t r[4];
-                pair_draws(a, g.seed, e0, unit, r);
+                pair_draws(a, g.seed, e0, unit, r, policy_step_now(a));
                 u0 = u24(r[0]); u1 = u24(r[1]); v0 = u24(r[2]); v1 = u24(r[3]);
             }
             __syncwarp();

@@ -209,23 +209,46 @@ __device__ __forceinline__ float rcp_approx(float x)
     return r;
 }
 
-// tanh of four pre-scaled values (z2 = 2*log2(e)*z) with one reciprocal: tanh z = 1 - 2 / (2^z2 + 1).  The factors
-// carry -1/2 each (folded into the "+1" as one FMA), so that the product's reciprocal comes out scaled by the -2 of
-// the formula: with e_i = -(2^z2_i + 1)/2, p = e0 e1, q = e2 e3, r = 1/(p q):  1 + e1 (q r) = 1 - 2 / (2^z2_0 + 1)
+// tanh of four pre-scaled values (z2 = 2*log2(e)*z): tanh z = 1 - 2 / (2^z2 + 1).
+// MODE 0: one reciprocal per value -- four instructions and TWO special-function operations per value (2^z2 = inf
+//   gives 1/inf = 0 -> +1, 2^z2 = 0 gives -1: no clamp).
+// MODE 4: one reciprocal per four values -- 5.5 instructions and 1.25 special-function operations per value.  The
+//   factors carry -1/2 each (folded into the "+1" as one FMA), so that the product's reciprocal comes out scaled by
+//   the -2 of the formula: with e_i = -(2^z2_i + 1)/2, p = e0 e1, q = e2 e3, r = 1/(p q): 1 + e1 (q r) = 1 - 2/(2^z2_0 + 1).
+// Which one is faster depends on how busy the special-function pipe already is: measured at 65,536 environments,
+// the config-3 shape (price chooser: a third more softmax rows) 47.5 us with MODE 4 against 49.3 us with MODE 0, the
+// config-2 shape 97.8 us against 93.5 us.
+template <int MODE>
 __device__ __forceinline__ void tanh4_scaled(float &x0, float &x1, float &x2, float &x3)
 {
-    const float e0 = fmaf(ex2_approx(fminf(x0, 30.f)), -0.5f, -0.5f), e1 = fmaf(ex2_approx(fminf(x1, 30.f)), -0.5f, -0.5f);
-    const float e2 = fmaf(ex2_approx(fminf(x2, 30.f)), -0.5f, -0.5f), e3 = fmaf(ex2_approx(fminf(x3, 30.f)), -0.5f, -0.5f);
-    const float p = e0 * e1, q = e2 * e3;
-    const float r = rcp_approx(p * q);
-    const float qr = q * r, pr = p * r;
-    x0 = fmaf(e1, qr, 1.f);
-    x1 = fmaf(e0, qr, 1.f);
-    x2 = fmaf(e3, pr, 1.f);
-    x3 = fmaf(e2, pr, 1.f);
+    if constexpr (MODE == 4) {
+        const float e0 = fmaf(ex2_approx(fminf(x0, 30.f)), -0.5f, -0.5f), e1 = fmaf(ex2_approx(fminf(x1, 30.f)), -0.5f, -0.5f);
+        const float e2 = fmaf(ex2_approx(fminf(x2, 30.f)), -0.5f, -0.5f), e3 = fmaf(ex2_approx(fminf(x3, 30.f)), -0.5f, -0.5f);
+        const float p = e0 * e1, q = e2 * e3;
+        const float r = rcp_approx(p * q);
+        const float qr = q * r, pr = p * r;
+        x0 = fmaf(e1, qr, 1.f);
+        x1 = fmaf(e0, qr, 1.f);
+        x2 = fmaf(e3, pr, 1.f);
+        x3 = fmaf(e2, pr, 1.f);
+    } else if constexpr (MODE == 2) {
+        const float e0 = fmaf(ex2_approx(fminf(x0, 60.f)), -0.5f, -0.5f), e1 = fmaf(ex2_approx(fminf(x1, 60.f)), -0.5f, -0.5f);
+        const float e2 = fmaf(ex2_approx(fminf(x2, 60.f)), -0.5f, -0.5f), e3 = fmaf(ex2_approx(fminf(x3, 60.f)), -0.5f, -0.5f);
+        const float r = rcp_approx(e0 * e1), t = rcp_approx(e2 * e3);
+        x0 = fmaf(e1, r, 1.f);
+        x1 = fmaf(e0, r, 1.f);
+        x2 = fmaf(e3, t, 1.f);
+        x3 = fmaf(e2, t, 1.f);
+    } else {
+        x0 = fmaf(rcp_approx(ex2_approx(x0) + 1.f), -2.f, 1.f);
+        x1 = fmaf(rcp_approx(ex2_approx(x1) + 1.f), -2.f, 1.f);
+        x2 = fmaf(rcp_approx(ex2_approx(x2) + 1.f), -2.f, 1.f);
+        x3 = fmaf(rcp_approx(ex2_approx(x3) + 1.f), -2.f, 1.f);
+    }
 }
 
 // accumulator row (bias included) -> Tanh -> the thread's row of the next layer's hi / lo operands (8 + 8 columns)
+template <int TANH>
 __device__ __forceinline__ void tc_hidden_epilogue(uint32_t trow, uint32_t aHrow)
 {
     float v[16];
@@ -234,7 +257,7 @@ __device__ __forceinline__ void tc_hidden_epilogue(uint32_t trow, uint32_t aHrow
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
         float h0 = v[4 * c], h1 = v[4 * c + 1], h2 = v[4 * c + 2], h3 = v[4 * c + 3];
-        tanh4_scaled(h0, h1, h2, h3);
+        tanh4_scaled<TANH>(h0, h1, h2, h3);
         const float i0 = tf32_hi(h0), i1 = tf32_hi(h1), i2 = tf32_hi(h2), i3 = tf32_hi(h3);
         hi[2 * c] = pack_f16x2(i0, i1); hi[2 * c + 1] = pack_f16x2(i2, i3);
         lo[2 * c] = pack_f16x2(h0 - i0, h1 - i1); lo[2 * c + 1] = pack_f16x2(h2 - i2, h3 - i3);
@@ -274,16 +297,16 @@ __device__ __forceinline__ int tc_sample(uint32_t trow, int A, float u, float &l
 // iterations: sharing measured 102.6 us against 97.5 us there, 48.9 against 51.4 us on the config-3 shape)
 template <bool WITH_V, bool SHARE>
 __device__ __forceinline__ uint32_t tc_pair_draw(const PolicyStepArgs &a, unsigned long long seed, int tile, int tileStep, int row,
-                                                 int unit, int j, uint32_t (&dr)[4], uint32_t &vWord)
+                                                 int unit, int j, uint32_t (&dr)[4], uint32_t &vWord, unsigned long long stp)
 {
     const int par = row & 1;  // = the lane's parity = the environment's parity (tiles start on even environments)
     if constexpr (!SHARE) {
         uint32_t r[4];
-        pair_draws(a, seed, tile * 128 + row, unit, r);
+        pair_draws(a, seed, tile * 128 + row, unit, r, stp);
         if constexpr (WITH_V) vWord = par ? r[3] : r[2];
         return par ? r[1] : r[0];
     }
-    if ((j & 1) == 0) pair_draws(a, seed, (tile + par * tileStep) * 128 + row, unit, dr);
+    if ((j & 1) == 0) pair_draws(a, seed, (tile + par * tileStep) * 128 + row, unit, dr, stp);
     const bool holder = par == (j & 1);  // this thread's call is the one of the current tile
     const uint32_t got = __shfl_xor_sync(0xffffffffu, par ? dr[0] : dr[1], 1);  // what the neighbour needs of mine
     const uint32_t u = holder ? (par ? dr[1] : dr[0]) : got;
@@ -399,14 +422,14 @@ __device__ __forceinline__ void tc_issue_l1(TcSlot &t, uint32_t sNet, int ks1)
 }
 
 // the rest of the net for the thread's row, layer 1 being under way; returns the action
-template <int AP, class NI>
+template <int AP, class NI, int TANH>
 __device__ __forceinline__ int tc_run_net(TcSlot &t, uint32_t sNet, int A, float u, float &logp, float *probsOut)
 {
     tc_slot_wait(t.doneAddr, t.k);
-    tc_hidden_epilogue(t.trow, t.trow + 16);
+    tc_hidden_epilogue<TANH>(t.trow, t.trow + 16);
     tc_slot_issue(t.slot, t.tmemD, t.tOnes, t.tmemD + 16, t.tmemD + 24, sNet + NI::kL2, sNet + NI::kL2Lo, sNet + NI::kL2Bias, 1, t.done);
     tc_slot_wait(t.doneAddr, t.k);
-    tc_hidden_epilogue(t.trow, t.trow + 16);
+    tc_hidden_epilogue<TANH>(t.trow, t.trow + 16);
     tc_slot_issue(t.slot, t.tmemD, t.tOnes, t.tmemD + 16, t.tmemD + 24, sNet + NI::kL3, sNet + NI::kL3Lo, sNet + NI::kL3Bias, 1, t.done);
     tc_slot_wait(t.doneAddr, t.k);
     return tc_sample<AP>(t.trow, A, u, logp, probsOut);
@@ -419,6 +442,10 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
     using NA = TcNetImage<2 * SM::KS_A>;
     using NO = TcNetImage<2 * SM::KS_O>;
     using NP = TcNetImage<2>;
+#ifndef MSCHED_TANH_PRICE_MODE
+#define MSCHED_TANH_PRICE_MODE 4
+#endif
+    constexpr int kTanh = AP_P > 0 ? MSCHED_TANH_PRICE_MODE : 0;  // tanh4_scaled: by the load of the special-function pipe
     constexpr int SW = SM::SW;
     extern __shared__ __align__(128) unsigned char smc[];
     __shared__ __align__(8) uint64_t barDone[SLOTS];
@@ -471,6 +498,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
     tc_fence_after();
     const int myTiles = slice < nTiles ? (nTiles - slice + stride - 1) / stride : 0;  // tiles slice, slice+stride, ...: slot s takes every SLOTS-th
 
+    const unsigned long long stepNow = policy_step_now(a);  // read once: the counter only moves between launches
     TcSlot t;
     t.slot = warp >> 2;
     const int row = tid & 127;
@@ -503,10 +531,10 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
             if (g.uOverride) {
                 u = live ? g.uOverride[(size_t)env * g.units + unit] : 0.f;
             } else {
-                u = u24(tc_pair_draw<false, (KW_A <= 8)>(a, g.seed, tile, SLOTS * stride, row, unit, j, dr, dummyV));
+                u = u24(tc_pair_draw<false, (KW_A <= 8)>(a, g.seed, tile, SLOTS * stride, row, unit, j, dr, dummyV, stepNow));
             }
             float lp;
-            const int act = tc_run_net<AP_A, NA>(t, sNet, g.nActions, u, lp,
+            const int act = tc_run_net<AP_A, NA, kTanh>(t, sNet, g.nActions, u, lp,
                                                  (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
             if (live) emit_row(a, g, env, unit, act, lp, act);
         }
@@ -532,11 +560,11 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
                 if (AP_P > 0 && gp.uOverride) v = live ? gp.uOverride[(size_t)env * gp.units + unit] : 0.f;
             } else {
                 uint32_t vw;
-                u = u24(tc_pair_draw<(AP_P > 0), (KW_A <= 8)>(a, g.seed, tile, SLOTS * stride, row, unit, j, dr, vw));
+                u = u24(tc_pair_draw<(AP_P > 0), (KW_A <= 8)>(a, g.seed, tile, SLOTS * stride, row, unit, j, dr, vw, stepNow));
                 v = u24(vw);
             }
             float lp;
-            const int c = tc_run_net<AP_O, NO>(t, sNet, g.nActions, u, lp,
+            const int c = tc_run_net<AP_O, NO, kTanh>(t, sNet, g.nActions, u, lp,
                                                (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
             if (live) emit_row(a, g, env, unit, c, lp, c);
             if constexpr (AP_P > 0) {
@@ -554,7 +582,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
                 tmem_st8(t.trow + SM::kColsX, px);
                 tc_issue_l1<NP, SM::kColsX>(t, sNet + NO::kBytes, 1);
                 float lq;
-                const int b = tc_run_net<AP_P, NP>(t, sNet + NO::kBytes, gp.nActions, v, lq,
+                const int b = tc_run_net<AP_P, NP, kTanh>(t, sNet + NO::kBytes, gp.nActions, v, lq,
                                                    (gp.probs && live) ? gp.probs + ((size_t)env * gp.units + unit) * gp.nActions : nullptr);
                 if (live) emit_row(a, gp, env, unit, b, lq, c == 0 ? -5 : b);
             }
