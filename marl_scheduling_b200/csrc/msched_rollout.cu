@@ -55,10 +55,11 @@ int launch(PolicyStepArgs &a, cudaStream_t s)
 }
 
 // the tensor-core kernel: one row per thread, SLOTS 128-environment tiles in flight per CTA, MINB CTAs per SM
-template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P, int SLOTS, int MINB>
+// EXACT: the action counts the instantiation is built for (acceptor | core << 8 | price << 16), 0 = any up to AP_*
+template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P, int SLOTS, int MINB, int EXACT = 0>
 int launch_tc(PolicyStepArgs &a, cudaStream_t s)
 {
-    auto fn = policy_step_tc_kernel<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS, MINB>;
+    auto fn = policy_step_tc_kernel<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS, MINB, EXACT>;
     using SM = PolicyStepTcSmem<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS>;
     const size_t smem = (size_t)SM::kBytes;
     constexpr int threads = SLOTS * 128;
@@ -153,10 +154,13 @@ extern "C" int msched_policy_step(const MschedPolicyStep *ps, void *stream)
         else if (!strcmp(e, "tc") && !tc) return fail(MSCHED_E_ARG, "MSCHED_POLICY_STEP_IMPL=tc needs 0 < input_bound <= 511");
     }
     if (tc) {
+        // the BASELINE shapes have instantiations built for their exact action counts (config 3: 7 / 4 / 9 actions, configs
+        // 2 and 4: 13 / 5), whose sampling epilogues skip the padding columns
         if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && free && ap <= 16 && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
-            rc = launch_tc<8, 8, 4, 8, 16, 4, 2>(a, s);
+            rc = (aa == 7 && ao == 4 && ap == 9) ? launch_tc<8, 8, 4, 8, 16, 4, 2, (7 | (4 << 8) | (9 << 16))>(a, s)
+                                                 : launch_tc<8, 8, 4, 8, 16, 4, 2>(a, s);
         else if (lead == 1 && ka == 27 && aa <= 16 && ko == 10 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 28) && (!O.x_used || O.x_used_stride >= 10))
-            rc = launch_tc<14, 16, 5, 8, 0, 4, 2>(a, s);
+            rc = (aa == 13 && ao == 5) ? launch_tc<14, 16, 5, 8, 0, 4, 2, (13 | (5 << 8))>(a, s) : launch_tc<14, 16, 5, 8, 0, 4, 2>(a, s);
         else if (lead == 1 && ka == 15 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 16) && (!O.x_used || O.x_used_stride >= 8))
             rc = launch_tc<8, 8, 4, 8, 0, 4, 2>(a, s);
         else if (lead == 1 && ka == 11 && aa <= 8 && ko == 8 && ao <= 8 && !free && (!A.x_used || A.x_used_stride >= 12) && (!O.x_used || O.x_used_stride >= 8))

@@ -171,24 +171,26 @@ __device__ __forceinline__ void mlp_pair(const float *__restrict__ s, const uint
 
 // Softmax -> Categorical(probs): inverse-CDF sample with draw u, Categorical.log_prob semantics (renormalised,
 // clamped to [eps, 1-eps]); lg are base-2 logits, -inf beyond the net's A actions
-template <int AP>
+// AE = the number of columns that can hold an action (A <= AE <= AP; a kernel built for one net shape passes its exact
+// action count and skips the padding columns' exponentials and sums)
+template <int AP, int AE = AP>
 __device__ __forceinline__ int sample_row(float (&lg)[AP], int A, float u, float &logp, float *probsOut)
 {
     float mx = lg[0];
 #pragma unroll
-    for (int o = 1; o < AP; ++o) mx = fmaxf(mx, lg[o]);
+    for (int o = 1; o < AE; ++o) mx = fmaxf(mx, lg[o]);
     float sum = 0.f;
 #pragma unroll
-    for (int o = 0; o < AP; ++o) { lg[o] = ex2_approx(lg[o] - mx); sum += lg[o]; }
+    for (int o = 0; o < AE; ++o) { lg[o] = ex2_approx(lg[o] - mx); sum += lg[o]; }
     const float inv = __fdividef(1.f, sum);
     float tot = 0.f;
 #pragma unroll
-    for (int o = 0; o < AP; ++o) { lg[o] *= inv; tot += lg[o]; }
+    for (int o = 0; o < AE; ++o) { lg[o] *= inv; tot += lg[o]; }
     if (probsOut) {
         for (int o = 0; o < A; ++o) {
             float v = lg[0];
 #pragma unroll
-            for (int q = 1; q < AP; ++q) v = (q == o) ? lg[q] : v;
+            for (int q = 1; q < AE; ++q) v = (q == o) ? lg[q] : v;
             probsOut[o] = v;
         }
     }
@@ -198,14 +200,14 @@ __device__ __forceinline__ int sample_row(float (&lg)[AP], int A, float u, float
     float cdf = 0.f;
     int act = 0;
 #pragma unroll
-    for (int o = 0; o < AP; ++o) {
+    for (int o = 0; o < AE; ++o) {
         cdf += lg[o];
         act += (cdf > thr) ? 0 : 1;
     }
     act = min(act, A - 1);
     float pa = lg[0];
 #pragma unroll
-    for (int o = 1; o < AP; ++o) pa = (o == act) ? lg[o] : pa;
+    for (int o = 1; o < AE; ++o) pa = (o == act) ? lg[o] : pa;
     const float eps = 1.1920928955078125e-07f;
     float pn = __fdividef(pa, tot);
     pn = fminf(fmaxf(pn, eps), 1.f - eps);

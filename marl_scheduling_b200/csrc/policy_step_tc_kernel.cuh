@@ -278,13 +278,13 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8])
 }
 
 // logits of the thread's row (bias included, base 2) -> sample; AP = 8 or 16 columns are read
-template <int AP>
+template <int AP, int AE>
 __device__ __forceinline__ int tc_sample(uint32_t trow, int A, float u, float &logp, float *probsOut)
 {
     float lg[AP];
     if constexpr (AP == 8) tmem_ld8(trow, lg);
     else tmem_ld16(trow, lg);
-    return sample_row<AP>(lg, A, u, logp, probsOut);
+    return sample_row<AP, AE>(lg, A, u, logp, probsOut);
 }
 
 // The Philox draw of the thread's row.  One Philox call serves an environment PAIR (pair_draws: words 0, 1 = the two
@@ -422,7 +422,7 @@ __device__ __forceinline__ void tc_issue_l1(TcSlot &t, uint32_t sNet, int ks1)
 }
 
 // the rest of the net for the thread's row, layer 1 being under way; returns the action
-template <int AP, class NI, int TANH>
+template <int AP, class NI, int TANH, int AE>
 __device__ __forceinline__ int tc_run_net(TcSlot &t, uint32_t sNet, int A, float u, float &logp, float *probsOut)
 {
     tc_slot_wait(t.doneAddr, t.k);
@@ -432,10 +432,12 @@ __device__ __forceinline__ int tc_run_net(TcSlot &t, uint32_t sNet, int A, float
     tc_hidden_epilogue<TANH>(t.trow, t.trow + 16);
     tc_slot_issue(t.slot, t.tmemD, t.tOnes, t.tmemD + 16, t.tmemD + 24, sNet + NI::kL3, sNet + NI::kL3Lo, sNet + NI::kL3Bias, 1, t.done);
     tc_slot_wait(t.doneAddr, t.k);
-    return tc_sample<AP>(t.trow, A, u, logp, probsOut);
+    return tc_sample<AP, AE>(t.trow, A, u, logp, probsOut);
 }
 
-template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P, int SLOTS, int MINB>
+// EXACT != 0: the kernel is built for one set of action counts (acceptor | core << 8 | price << 16) and its sampling
+// epilogues skip the padding columns; 0: any counts up to the padded AP_*
+template <int KW_A, int AP_A, int KW_O, int AP_O, int AP_P, int SLOTS, int MINB, int EXACT = 0>
 __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const __grid_constant__ PolicyStepArgs a)
 {
     using SM = PolicyStepTcSmem<KW_A, AP_A, KW_O, AP_O, AP_P, SLOTS>;
@@ -445,6 +447,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
 #ifndef MSCHED_TANH_PRICE_MODE
 #define MSCHED_TANH_PRICE_MODE 4
 #endif
+    constexpr int AE_A = EXACT ? (EXACT & 0xff) : AP_A, AE_O = EXACT ? ((EXACT >> 8) & 0xff) : AP_O, AE_P = EXACT ? ((EXACT >> 16) & 0xff) : AP_P;
     constexpr int kTanh = AP_P > 0 ? MSCHED_TANH_PRICE_MODE : 0;  // tanh4_scaled: by the load of the special-function pipe
     constexpr int SW = SM::SW;
     extern __shared__ __align__(128) unsigned char smc[];
@@ -534,7 +537,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
                 u = u24(tc_pair_draw<false, (KW_A <= 8)>(a, g.seed, tile, SLOTS * stride, row, unit, j, dr, dummyV, stepNow));
             }
             float lp;
-            const int act = tc_run_net<AP_A, NA, kTanh>(t, sNet, g.nActions, u, lp,
+            const int act = tc_run_net<AP_A, NA, kTanh, AE_A>(t, sNet, g.nActions, u, lp,
                                                  (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
             if (live) emit_row(a, g, env, unit, act, lp, act);
         }
@@ -564,7 +567,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
                 v = u24(vw);
             }
             float lp;
-            const int c = tc_run_net<AP_O, NO, kTanh>(t, sNet, g.nActions, u, lp,
+            const int c = tc_run_net<AP_O, NO, kTanh, AE_O>(t, sNet, g.nActions, u, lp,
                                                (g.probs && live) ? g.probs + ((size_t)env * g.units + unit) * g.nActions : nullptr);
             if (live) emit_row(a, g, env, unit, c, lp, c);
             if constexpr (AP_P > 0) {
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(SLOTS * 128, MINB) policy_step_tc_kernel(const
                 tmem_st8(t.trow + SM::kColsX, px);
                 tc_issue_l1<NP, SM::kColsX>(t, sNet + NO::kBytes, 1);
                 float lq;
-                const int b = tc_run_net<AP_P, NP, kTanh>(t, sNet + NO::kBytes, gp.nActions, v, lq,
+                const int b = tc_run_net<AP_P, NP, kTanh, (AE_P > 0 ? AE_P : 1)>(t, sNet + NO::kBytes, gp.nActions, v, lq,
                                                    (gp.probs && live) ? gp.probs + ((size_t)env * gp.units + unit) * gp.nActions : nullptr);
                 if (live) emit_row(a, gp, env, unit, b, lq, c == 0 ? -5 : b);
             }

@@ -32,9 +32,11 @@ def _check_group(O, w, x, u, act, lp, pr, nin, A, nets_of_unit):
 
 
 @pytest.mark.parametrize("impl", ["simt", "tc"])
-@pytest.mark.parametrize("key", ["cfg3_free", "cfg2_fix", "cfg2_shared", "cfg3_fix", "cfg1_fix"])
+@pytest.mark.parametrize("key", ["cfg3_free", "cfg2_fix", "cfg2_shared", "cfg3_fix", "cfg1_fix", "cfg3_narrow_free", "cfg2_narrow_fix"])
 def test_policy_step_matches_oracle_mlp(key, impl, monkeypatch):
-    """Both kernels behind msched_policy_step -- fp32 SIMT and tcgen05 tensor cores (3xTF32) -- against the oracle."""
+    """Both kernels behind msched_policy_step -- fp32 SIMT and tcgen05 tensor cores (3xTF32) -- against the oracle.
+    The "narrow" keys shrink the action counts below the BASELINE shapes' (one acceptor / core / price action fewer):
+    the tensor-core instantiations built for the exact BASELINE counts do not apply and the padded ones run."""
     monkeypatch.setenv("MSCHED_POLICY_STEP_IMPL", impl)
     import torch
     from marl_scheduling_b200 import policy
@@ -43,6 +45,7 @@ def test_policy_step_matches_oracle_mlp(key, impl, monkeypatch):
     dom = {"cfg3": CFG3, "cfg2": CFG2, "cfg1": CFG1}[key[:4]]
     free = key.endswith("free")
     shared = key.endswith("shared")
+    narrow = 1 if "narrow" in key else 0
     N, C, L = dom["N"], dom["C"], dom["L"]
     NL, P = N * L, max(dom["prios"])
     B = 777
@@ -55,7 +58,8 @@ def test_policy_step_matches_oracle_mlp(key, impl, monkeypatch):
                  offer_price=rng.integers(0, P + 1, (B, N, L)) if free else None, observe=True)
     obs = env.obs_views()
     Ua, Uo = N * C, NL
-    nin_a, A_a, nin_o, A_o = 3 + 2 * NL, NL + 1, 2 * C + 2, C + 1
+    nin_a, A_a, nin_o, A_o = 3 + 2 * NL, NL + 1 - narrow, 2 * C + 2, C + 1
+    P -= narrow
     na, no = (1, 1) if shared else (Ua, Uo)
     ga = policy.MlpGroup.random(nin_a, 16, A_a, na, dev, seed=11)
     go = policy.MlpGroup.random(nin_o, 16, A_o, no, dev, seed=12)
