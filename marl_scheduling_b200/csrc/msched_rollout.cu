@@ -147,7 +147,7 @@ extern "C" int msched_policy_step(const MschedPolicyStep *ps, void *stream)
     int rc = -1;
     // The tensor-core kernel takes the observations as exact fp16 operands (|x| <= 511: the caller states its bound in
     // input_bound); anything else runs the fp32 SIMT kernel.  MSCHED_POLICY_STEP_IMPL=tc|simt forces one (the parity
-    // tests run both).  Measured at 65,536 envs, cfg3 / cfg2 shapes: 57 / 109 us tensor cores, 86 / 225 us SIMT
+    // tests run both).  Measured at 65,536 envs, cfg3 / cfg2 shapes: 47 / 94 us tensor cores, 78 / 225 us SIMT
     bool tc = ps->input_bound > 0 && ps->input_bound <= 511;
     if (const char *e = getenv("MSCHED_POLICY_STEP_IMPL")) {
         if (!strcmp(e, "simt")) tc = false;

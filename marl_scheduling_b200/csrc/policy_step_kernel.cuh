@@ -23,7 +23,7 @@
 //   * actions go straight into the environment's action record, action / log-prob (and, if asked, the input
 //     rows) into the experience buffer slot of the step.
 // This is the fp32 SIMT form.  It serves observations beyond +-511 (msched_policy_step's input_bound); within that
-// bound the tensor-core kernel of policy_step_tc_kernel.cuh (same contract, same draws) runs instead: 51 us against 78 us
+// bound the tensor-core kernel of policy_step_tc_kernel.cuh (same contract, same draws) runs instead: 47 us against 78 us
 // at 65,536 environments of the config-3 shape.  Shared by both: the argument structs, sample_row, pair_draws, emit_row.
 #pragma once
 #include "msched_common.cuh"

@@ -29,15 +29,18 @@
 //   bias      one more MMA per layer: a constant A operand [1 1 0 ...] against a B chunk [b_hi b_lo 0 ...]
 //             (accumulate = 0: it also initialises the accumulator), so the epilogues neither load nor add biases
 //   scales    2*log2(e) folded into W1, b1, W2, b2 and log2(e) into W3, b3 (base-2 logits for the softmax)
-//   tanh      1 - 2/(2^z' + 1); the reciprocals of FOUR values come from ONE rcp (1/a = b*c*d / (a*b*c*d), z'
-//             clamped to 30 so that the product stays finite; tanh is 1.0f there anyway): 20 instead of 32
-//             transcendental-unit operations per row and layer (that unit does 16 lanes per clock and SM)
+//   tanh      1 - 2/(2^z' + 1); with a price chooser in the launch the reciprocals of FOUR values come from ONE rcp
+//             (1/a = b*c*d / (a*b*c*d), z' clamped to 30 so that the product stays finite; tanh is 1.0f there
+//             anyway): 20 instead of 32 transcendental-unit operations per row and layer (that unit does 16 lanes
+//             per clock and SM); the other shapes take one rcp per value (fewer instructions), see tanh4_scaled
+//   draws     one Philox call serves an environment pair: the two lanes of a pair compute the calls of two
+//             consecutive tiles of the slot and swap words (tc_pair_draw)
 //   loads     the observation rows of a warp's 32 environments are read warp-cooperatively (8 lanes per 32-byte
 //             row: whole sectors) one tile AHEAD into registers, converted and transposed through a warp-private
 //             staging tile to the row's owner; the same lanes write the experience-buffer copy of the row
 //   price chooser  its four inputs are picked out of the owner's staged row (already fp16) by the sampled core
-//   bound     instruction issue: ~17,000 thread instructions per environment (36 Tanh layers x ~175, 18 sampling rows x
-//             ~130) at 60 % of the issue slots; tensor pipe 22 %.  The launch lasts as long as its slowest slot, so the
+//   bound     instruction issue: ~15,500 thread instructions per environment (36 Tanh layers x ~165, 18 sampling rows x
+//             ~115) at 60 % of the issue slots; tensor pipe 22 %.  The launch lasts as long as its slowest slot, so the
 //             host splits the CTAs between the unit kinds on whole-tile counts (msched_rollout.cu); DESIGN.md 5.0 has
 //             the measured history, including the variants that lost (work queue, two tiles per slot, issuer warp)
 #pragma once
