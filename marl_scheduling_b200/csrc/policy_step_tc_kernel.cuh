@@ -405,7 +405,8 @@ struct PolicyStepTcSmem {
     static constexpr int kColsH = 16, kColsX = 32, kSlotCols = 32 + 8 * KSX;
     static constexpr int kColsOnes = SLOTS * kSlotCols;     // 8 columns [1 1 0 ...] shared by the slots
     static constexpr int kColsUsed = kColsOnes + 8;
-    static constexpr uint32_t kTmemCols = kColsUsed <= 32 ? 32u : (kColsUsed <= 64 ? 64u : (kColsUsed <= 128 ? 128u : 256u));
+    static constexpr uint32_t kTmemCols = kColsUsed <= 32 ? 32u : (kColsUsed <= 64 ? 64u : (kColsUsed <= 128 ? 128u : (kColsUsed <= 256 ? 256u : 512u)));
+    static_assert(kColsUsed <= 512, "tensor memory has 512 columns");
 };
 
 // what one slot needs to run a net: its accumulator and operand columns, the CTA's constant operand
