@@ -986,19 +986,30 @@ def main():
                 policy.actor_forward(acc_net, ov["acceptor"], lay.o_acc_row, N * Cc, B, env_stride=lay.obs_halfs,
                                      seed=1, step_dev=step_t, action=a_act, logprob=a_lp,
                                      action_rec=env.acceptor_actions, action_rec_stride=lay.action_halfs)
-            env.step_observe_records(env.action, res_r)
-            step_t.add_(1)
+            if side is not None:  # graph capture: the policy's step counter moves on a branch beside the env step
+                cur = torch.cuda.current_stream(dev)
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    step_t.add_(1)
+                env.step_observe_records(env.action, res_r)
+                cur.wait_stream(side)
+            else:
+                env.step_observe_records(env.action, res_r)
+                step_t.add_(1)
 
+        side = None
         for i in range(5):
             rollout_step(i % SLOTS)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         cap = torch.cuda.Stream(device=dev)
         cap.wait_stream(torch.cuda.current_stream(dev))
+        side = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(cap):
             with torch.cuda.graph(graph, stream=cap):
                 for k in range(SLOTS):
                     rollout_step(k)
+        side = None
         torch.cuda.current_stream(dev).wait_stream(cap)
         for i in range(3):
             graph.replay()
@@ -1046,7 +1057,7 @@ def main():
                    "what": "PPO.selectAction of every divided PPO unit (acceptor, offer/core chooser"
                            + (", price chooser" if free else "") + ") in ONE launch (msched_policy_step: sample + log-prob, actions "
                            "into the action record, state / action / log-prob into the experience-buffer slot of the step) + the fused "
-                           "env step + observations; 8 consecutive steps (8 buffer slots) captured in a CUDA graph and replayed",
+                           "env step + observations; 8 consecutive steps (8 buffer slots) captured in a CUDA graph and replayed (the one-thread increment of the policy's step counter sits on a graph branch beside the env step)",
                    "sticky_flags": rflags,
                    "returns_kernel": {"T": T, "units": B * N * Cc, "us": ret_us,
                                       "gbs": 12.0 * rew.numel() / ret_us / 1e3,
