@@ -104,7 +104,11 @@ __host__ __device__ constexpr int fused_spec(int mode, int auction, int spawn, i
 }
 
 template <int N, int C, int L, int R, int SPEC = -1, bool MULTI = false, bool HC = false>
-__global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? 16 : 8) : 1)
+// Resident CTAs per SM the registers are held to (small domains): 16 of 64 threads for the one-step kernel -- its
+// launches overlap with their neighbours' and every resident tile counts (64 registers) -- and 14 for the multi-step
+// kernel, whose one wave of 13.8 tiles per SM at 65,536 environments stays for the whole launch: 72 registers measured
+// 15.2 us per step against 16.05 us (and the one-step kernel 16.5 against 15.9 us with them)
+__global__ void __launch_bounds__(32 * R, FusedDims<N, C, L>::SMALL ? (R <= 2 ? (MULTI ? 14 : 16) : (MULTI ? 7 : 8)) : 1)
     fused_step_kernel(const __grid_constant__ DevParams p)
 {
     using D = FusedDims<N, C, L>;
