@@ -461,7 +461,7 @@ def other_configs(args):
                "--rollout-steps", "200" if key == "cfg1" else "0",  # cfg1 = the hard-coded agents' rollout
                "--update-T", "0", "--update-dp", "0", "--other-configs", "0"]
         try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
             d = json.loads(r.stdout.strip().splitlines()[-1])
             out[key] = {"workload": d["config"].get("domain"), "envs": d["config"].get("envs_per_gpu"),
                         "value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"],
