@@ -96,7 +96,7 @@ def traffic_from_profile(cfg_name, kernel="step_kernel"):
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through NVML while the timed region runs."""
 
-    def __init__(self, index, period=0.02):
+    def __init__(self, index, period=0.002):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons = [], set()
@@ -150,7 +150,7 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(s)}
+                "samples": len(s), "window": "state warm-up + warm-up + timed steps (the same launches throughout)"}
 
 
 def refresh_actions(env, rec, gen):
@@ -660,11 +660,13 @@ def main():
             if timed is not None:
                 timed[1].record()
 
+        # the clocks are sampled from here on: the state warm-up runs the same launches as the timed region, which at
+        # the default step count is too short (a fraction of a millisecond) for more than one NVML reading
+        sampler.start()
         for _ in range(-(-args.state_warm * S // (S * G))):
             run_block(S * G, None)
         torch.cuda.synchronize()
         flags = max(int(r[:B, lay.r_flags].max().item()) for r in results) if args.state_warm else 0
-        sampler.start()
         for _ in range(-(-max(args.warmup, 3) // (S * G))):
             run_block(S * G, None)
         blocks = [min(S * G, K - b0) for b0 in range(0, K, S * G)]
@@ -750,11 +752,11 @@ def main():
             refresh_actions(env, ring[i % len(ring)], gen)
             step_on(env, ring[i % len(ring)], results[i & 1])
 
+        sampler.start()  # from the state warm-up on (the same launches as the timed region)
         for i in range(args.state_warm):
             one_step(i)
         torch.cuda.synchronize()
         flags = int(results[(args.state_warm - 1) & 1][:B, lay.r_flags].max().item()) if args.state_warm else 0
-        sampler.start()
         for i in range(max(args.warmup, 3)):
             if flush is not None:
                 flush.fill_(i & 0xFF)
