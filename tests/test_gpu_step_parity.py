@@ -292,6 +292,40 @@ def test_step_host_compact_record_equals_full_record(key):
             _env(128, dict(dom, mode=mode, netZero=0.3)).compact_result_layout()
 
 
+@pytest.mark.parametrize("full_record", [False, True])
+def test_step_host_full_batch_in_waves_matches_device_step(full_record):
+    """The host-buffer step at BASELINE's 65,536 environments: the zero-copy launch is held to a few resident CTAs per SM
+    and runs its 2,048 tiles in waves (csrc/msched_abi.cu launch_step) -- results, states and observations equal the
+    device step's, for the compact and for the full result record."""
+    import torch
+    dom, mode = DOMS["cfg3"]
+    B = 65536
+    a = _env(B, dict(dom, mode=mode), auction="random", spawn="philox", seed=8)
+    b = _env(B, dict(dom, mode=mode), auction="random", spawn="philox", seed=8)
+    lay = a.layout
+    cl = b.compact_result_layout()
+    ah = torch.zeros((B, lay.action_halfs), dtype=torch.int16).pin_memory()
+    rh = torch.zeros((B, lay.result_words if full_record else cl.words), dtype=torch.int32).pin_memory()
+    rng = np.random.default_rng(4)
+    for t in range(6):
+        offc, acc, offp = random_actions(rng, B, dom, True)
+        ra = a.step(offc, acc, None, offer_price=offp)
+        ah.copy_(a.action[:B].cpu())
+        if full_record:
+            b.step_host(ah, rh, observe=True)
+            assert torch.equal(rh.to(a.result.device), a.result[:B]), t
+        else:
+            b.step_host_compact(ah, rh, observe=True)
+            rb = b.compact_rewards(rh)
+            for k in ("offer", "price", "acceptor", "auctioneer", "agent", "n_accepted", "n_terminated", "done", "flags"):
+                assert torch.equal(ra[k].cpu().to(torch.float64), rb[k].to(torch.float64)), (t, k)
+        oa, ob = a.observe(), b.obs_views()
+        for k in oa:
+            assert torch.equal(oa[k], ob[k]), (t, k)
+    assert torch.equal(a.state[:B], b.state[:B]) and torch.equal(a.chain[:B], b.chain[:B])
+    a.close(); b.close()
+
+
 @pytest.mark.parametrize("impl", ["fused1", "fused4", "lane"])
 def test_cuda_graph_replay_matches_eager_steps(impl):
     """Device-side round counter (msched_set_round_mode): a captured step + observations can be
