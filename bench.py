@@ -469,6 +469,11 @@ def other_configs(args):
                         "roofline_frac": d["roofline"]["frac"],
                         "algorithmic_bytes_per_env_step": d["roofline"]["algorithmic_bytes_per_env_step"],
                         "l2": d.get("l2_detail"), "sticky_flags": d.get("sticky_flags_after_warm")}
+            ms = d["roofline"].get("multi_step") or {}
+            if "us_per_step" in ms:  # the dependent chain through msched_step_multi (T steps per launch)
+                out[key]["multi_step"] = {"us_per_step": ms["us_per_step"], "frac": ms.get("frac"),
+                                          "steps_per_launch": ms.get("steps_per_launch")}
+            out[key]["serial_frac"] = d["roofline"].get("serial_frac")
             if d.get("rollout_with_policy"):
                 out[key]["rollout"] = d["rollout_with_policy"]
         except Exception as e:  # a side leg must never take the bench line down
