@@ -56,9 +56,10 @@ int msched_actor_forward(const MschedMlpGroup *nets, const MschedActorIO *io, vo
 
 int msched_returns(const float *rewards, int T, int M, double gamma, int normalise, float *out, void *stream)
 {
-    if (!rewards || !out || T < 1 || M < 0) return fail(MSCHED_E_ARG, "bad rewards/out/T/M");
+    if (T < 1 || M < 0) return fail(MSCHED_E_ARG, "bad T/M");
     if (normalise && T < 2) return fail(MSCHED_E_ARG, "normalisation needs T >= 2");
-    if (M == 0) return MSCHED_OK;
+    if (M == 0) return MSCHED_OK;  // an empty buffer has no address to check
+    if (!rewards || !out) return fail(MSCHED_E_ARG, "null rewards/out");
     // TMA-tiled kernel (every reward read once) when the rows are 16-byte aligned and a [T][128] tile fits in
     // shared memory; the streaming kernel otherwise
     const size_t tileBytes = (size_t)T * 128 * sizeof(float);

@@ -1,0 +1,61 @@
+"""GPU: the ends of the size range -- a batch of ONE environment against a recorded reference trace, and calls over
+nothing (zero environments / zero units), which must succeed, launch nothing and leave their outputs alone."""
+import numpy as np
+import pytest
+
+from helpers import assert_state_equal, golden_names, load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _one(exp, b):
+    return {k: (v[b] if isinstance(v, np.ndarray) else v) for k, v in exp.items()}
+
+
+@pytest.mark.parametrize("name", golden_names()[:4])
+def test_single_environment_batch_replays_reference_trace(name):
+    """B = 1: one live lane in a 128-environment padding unit (the reference's own shape: one World per process,
+    src/world.py:210-254)."""
+    from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
+    tr, meta = load_golden(name)
+    free = meta["mode"].startswith("free")
+    env = BatchedSchedulingEnv(1, world_params_from_dom(meta, free), reward=meta["mode"],
+                               net_zero_offer_reward=meta.get("netZero", 0.5), auction="external", spawn="u64")
+    one = lambda a: np.asarray(a)[None].copy()
+    for t in range(tr["done"].shape[0]):
+        r = env.step(one(tr["in_offc"][t]), one(tr["in_acc"][t]), one(tr["in_auc"][t]),
+                     offer_price=one(tr["in_offp"][t]) if free else None, spawn_u=one(tr["in_spawn_u"][t]))
+        e = env.export_state()
+        assert (e["flags"] == 0).all(), (name, t)
+        assert_state_equal(_one(e, 0), tr, t, prefix=name)
+        assert np.array_equal(r["agent"].cpu().numpy()[0], tr["r_agent"][t]), (name, t)
+        assert np.array_equal(r["acceptor"].cpu().numpy()[0], tr["r_acceptor"][t]), (name, t)
+        assert int(r["n_accepted"][0]) == tr["n_accepted"][t] and int(r["n_terminated"][0]) == tr["n_term"][t]
+    env.close()
+
+
+def test_calls_over_nothing_succeed_and_write_nothing():
+    """n_envs == 0 / M == 0: MSCHED_OK without a launch (include/msched.h); the output buffers keep their contents."""
+    import torch
+    from marl_scheduling_b200 import policy
+    from marl_scheduling_b200._lib import MschedError
+    dev = torch.device("cuda", 0)
+    net = policy.MlpGroup.random(15, 16, 7, 6, dev, seed=1)
+    x = torch.zeros((128, 6, 16), dtype=torch.int16, device=dev)
+    act = torch.full((6,), -7, dtype=torch.int32, device=dev)
+    lp = torch.full((6,), -7.0, dtype=torch.float32, device=dev)
+    policy.actor_forward(net, x, 16, 6, 0, seed=1, action=act, logprob=lp)
+    # the whole-step launch over zero environments
+    core = policy.MlpGroup.random(8, 16, 4, 6, dev, seed=2)
+    ga = policy.policy_step_group(net, 6, 0, 16, 0, 1, act, lp)
+    go = policy.policy_step_group(core, 6, 96, 8, 6, 2, act, lp)
+    policy.policy_step(x, 6 * 16 + 6 * 8, 0, 3, ga, go, None, input_bound=8)
+    # returns over zero columns; one time step cannot be normalised (std over one value)
+    r0 = torch.zeros((5, 0), dtype=torch.float32, device=dev)
+    assert policy.returns(r0, 0.9, True).shape == (5, 0)
+    r1 = torch.ones((1, 8), dtype=torch.float32, device=dev)
+    assert torch.equal(policy.returns(r1, 0.9, False), r1)
+    with pytest.raises(MschedError):
+        policy.returns(r1, 0.9, True)
+    torch.cuda.synchronize()
+    assert int(act.min()) == -7 and float(lp.max()) == -7.0
