@@ -59,3 +59,45 @@ def test_calls_over_nothing_succeed_and_write_nothing():
         policy.returns(r1, 0.9, True)
     torch.cuda.synchronize()
     assert int(act.min()) == -7 and float(lp.max()) == -7.0
+
+
+def test_multi_step_entry_points_at_one_and_zero_steps():
+    """msched_step_multi / msched_rollout_hardcoded with T = 1 are one msched_step_observe (+ one hard-coded agents
+    launch); T = 0 is refused (n_steps out of range), nothing is launched and the round does not move."""
+    import torch
+    from marl_scheduling_b200._lib import MschedError
+    from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
+    dom = dict(N=2, C=3, L=2, prios=[5], lens=[4], probs=[1], fix=[3], mult=2)
+    B = 333  # ragged: 11 tiles of 32, the last one with 13 live lanes
+    mk = lambda: BatchedSchedulingEnv(B, world_params_from_dom(dom, False), reward="fix", auction="random", spawn="philox", seed=9)
+    a, b, c = mk(), mk(), mk()
+    lay, dev = a.layout, a.device
+    for e in (a, b, c):
+        e.observe()
+        e.hardcoded_actions(random_ties=True)
+    for t in range(5):
+        res1 = torch.zeros((1, lay.padded_envs, lay.result_words), dtype=torch.int32, device=dev)
+        obs1 = torch.zeros((1, lay.padded_envs, lay.obs_halfs), dtype=torch.int16, device=dev)
+        acts = a.action.clone()[None]
+        a.step_observe_records(a.action, res1[0], obs=obs1[0])
+        a.hardcoded_actions(obs=obs1[0], random_ties=True)
+        res2, obs2 = torch.zeros_like(res1), torch.zeros_like(obs1)
+        b.step_multi_records(acts, res2, obs2, obs_every=True)         # scripted actions, one step per launch
+        b.action.copy_(a.action)                                        # (b's agents are a's)
+        res3, obs3 = torch.zeros_like(res1), torch.zeros_like(obs1)
+        c.rollout_hardcoded(res3, obs3, obs_every=True, random_ties=True)  # step ; agents, one step per launch
+        torch.cuda.synchronize()
+        for r, o, e in ((res2, obs2, b), (res3, obs3, c)):
+            assert torch.equal(res1[:, :B], r[:, :B]) and torch.equal(obs1[:, :B], o[:, :B]), t
+            assert torch.equal(a.state[:B], e.state[:B]) and torch.equal(a.chain[:B], e.chain[:B]), t
+        assert torch.equal(a.action[:B], c.action[:B]), t
+    assert a.round == b.round == c.round == 5
+    empty_a = torch.zeros((0, lay.padded_envs, lay.action_halfs), dtype=torch.int16, device=dev)
+    empty_r = torch.zeros((0, lay.padded_envs, lay.result_words), dtype=torch.int32, device=dev)
+    with pytest.raises(MschedError):
+        b.step_multi_records(empty_a, empty_r, None, obs_every=False)
+    with pytest.raises(MschedError):
+        c.rollout_hardcoded(empty_r, None, obs_every=False, random_ties=True)
+    assert b.round == c.round == 5
+    for e in (a, b, c):
+        e.close()
