@@ -101,3 +101,52 @@ def test_multi_step_entry_points_at_one_and_zero_steps():
     assert b.round == c.round == 5
     for e in (a, b, c):
         e.close()
+
+
+@pytest.mark.parametrize("B", [2, 100, 130, 4098])
+def test_policy_step_small_and_ragged_batches_tc_equals_simt(B, monkeypatch):
+    """msched_policy_step on batches smaller than one tile, straddling two, and with a 2-environment last tile: the
+    tensor-core kernel (slots without a tile, the environment-pair Philox call shared between two tiles of a slot)
+    against the fp32 SIMT kernel with the same draws -- experience rows identical, the same actions up to draws that
+    sit on a CDF step."""
+    import torch
+    from marl_scheduling_b200 import policy
+    from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
+    dom = dict(N=2, C=3, L=3, prios=[2, 4, 8], lens=[5, 5, 5], probs=[1 / 3] * 3, fix=[1, 2, 3])
+    N, C, L = dom["N"], dom["C"], dom["L"]
+    NL, P = N * L, max(dom["prios"])
+    env = BatchedSchedulingEnv(B, world_params_from_dom(dom, True), reward="free_comm", auction="random", spawn="philox", seed=4)
+    dev, lay = env.device, env.layout
+    g = torch.Generator(device=dev).manual_seed(2)
+    for t in range(10):
+        env.acceptor_actions.random_(0, 2, generator=g)
+        env.offer_core_actions.random_(0, C + 1, generator=g)
+        env.offer_price_actions.random_(0, P + 1, generator=g)
+        env.step_observe_records()
+    Ua, Uo = N * C, NL
+    ga = policy.MlpGroup.random(3 + 2 * NL, 16, NL + 1, Ua, dev, seed=31)
+    go = policy.MlpGroup.random(2 * C + 2, 16, C + 1, Uo, dev, seed=32)
+    gp = policy.MlpGroup.random(4, 16, P + 1, Uo, dev, seed=33)
+    res = {}
+    for impl in ("tc", "simt"):
+        monkeypatch.setenv("MSCHED_POLICY_STEP_IMPL", impl)
+        out = [(torch.full((B, n), -1, dtype=torch.int32, device=dev), torch.zeros((B, n), device=dev)) for n in (Ua, Uo, Uo)]
+        xs = [torch.zeros((B, Ua, lay.o_acc_row), dtype=torch.int16, device=dev), torch.zeros((B, Uo, lay.o_off_row), dtype=torch.int16, device=dev),
+              torch.zeros((B, Uo, 4), dtype=torch.int16, device=dev)]
+        A_ = policy.policy_step_group(ga, Ua, lay.o_acceptor, lay.o_acc_row, lay.a_acceptor, 7, *out[0], x_used=xs[0])
+        O_ = policy.policy_step_group(go, Uo, lay.o_offer, lay.o_off_row, lay.a_offer_core, 8, *out[1], x_used=xs[1])
+        P_ = policy.policy_step_group(gp, Uo, lay.o_offer, lay.o_off_row, lay.a_offer_price, 9, *out[2], x_used=xs[2])
+        policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, env_offset=6, step=11, input_bound=16)
+        torch.cuda.synchronize()
+        res[impl] = (out, xs)
+    (to, tx), (so, sx) = res["tc"], res["simt"]
+    for k in range(2):
+        assert torch.equal(tx[k], sx[k])
+        assert int(to[k][0].min()) >= 0                                  # every row was written
+        diff = int((to[k][0] != so[k][0]).sum())
+        assert diff <= max(1, to[k][0].numel() // 1000), (k, diff)
+        same = to[k][0] == so[k][0]
+        assert float((to[k][1] - so[k][1])[same].abs().max()) < 1e-4
+    same_core = (to[1][0] == so[1][0])
+    assert torch.equal(tx[2][same_core], sx[2][same_core])               # the price chooser's inputs follow the sampled core
+    env.close()
