@@ -150,3 +150,16 @@ def test_policy_step_small_and_ragged_batches_tc_equals_simt(B, monkeypatch):
     same_core = (to[1][0] == so[1][0])
     assert torch.equal(tx[2][same_core], sx[2][same_core])               # the price chooser's inputs follow the sampled core
     env.close()
+
+
+def test_two_million_environments_last_window_equals_offset_batch():
+    """32 x BASELINE's batch (2,097,152 environments, 1.5 GB of records): the last 128 environments walk through the
+    states, results and observations of a 128-environment batch created at env_offset = B - 128 (64-bit offsets, draws
+    keyed on the global index), and spawned = terminated + present holds for every environment."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "big_batch_check", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "big_batch_check.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.check(1 << 21, 20) > (1 << 21)
