@@ -163,3 +163,36 @@ def test_two_million_environments_last_window_equals_offset_batch():
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     assert mod.check(1 << 21, 20) > (1 << 21)
+
+
+@pytest.mark.parametrize("base", [(1 << 32) - 40, (1 << 33) + 6, (1 << 40) + 2])
+def test_global_environment_index_beyond_32_bits_matches_oracle(base):
+    """env_offset around and beyond 2^32 (a shard deep inside a very large job): the Philox counters carry the global
+    environment index in two 32-bit words -- the batch straddling the 2^32 boundary included -- and the step walks
+    through the oracle's states, rewards and auction winners."""
+    import torch
+    from marl_scheduling_b200.batched_env import BatchedSchedulingEnv, world_params_from_dom
+    from helpers import STATE_KEYS
+    from oracle import oracle as O
+    dom = dict(N=2, C=3, L=3, prios=[2, 4, 8], lens=[5, 5, 5], probs=[1 / 3] * 3, fix=[1])
+    B, seed = 96, 12
+    env = BatchedSchedulingEnv(B, world_params_from_dom(dom, True), reward="free_comm", auction="random", spawn="philox",
+                               seed=seed, env_offset=base)
+    orc = O.Oracle(B, dom, "free_comm", tie_mode=O.TIE_PHILOX, seed=seed, env_offset=base)
+    rng = np.random.default_rng(2)
+    N, C, L = 2, 3, 3
+    for t in range(25):
+        acc = np.where(rng.random((B, N, C)) < 0.6, rng.integers(0, 2, (B, N, C)), rng.integers(0, N * L + 1, (B, N, C)))
+        offc, offp = rng.integers(0, C + 1, (B, N, L)), rng.integers(0, 9, (B, N, L))
+        r = env.step(offc, acc, None, offer_price=offp)
+        orc.step(offc, acc, None, offp=offp)
+        assert np.array_equal(r["auctioneer_idx"].cpu().numpy(), orc.auc_out), t
+        assert np.array_equal(r["agent"].cpu().numpy(), orc.r_agent), t
+        assert np.array_equal(r["acceptor"].cpu().numpy(), orc.r_acceptor), t
+        assert int(r["flags"].max()) == 0
+    e = env.export_state()
+    for b in (0, 39, 40, 41, B - 1):
+        ob = orc.export(b)
+        for k in STATE_KEYS:
+            assert np.array_equal(np.asarray(e[k][b]), np.asarray(ob[k])), (b, k)
+    env.close()
