@@ -111,7 +111,7 @@ def test_policy_step_matches_oracle_mlp(key, impl, monkeypatch):
     # ---- the Philox draws: feeding the contract's u as overrides reproduces the un-overridden launch ----
     keep = {k: tuple(t.clone() for t in v[:2]) for k, v in out.items()}
     A_, O_, P_ = groups(False)
-    off_env = 4242
+    off_env = (1 << 33) + 4242  # beyond 32 bits: the pair index fills both counter words
     policy.policy_step(env._obs_buffer(), lay.obs_halfs, B, C, A_, O_, P_, env_offset=off_env, step=9, input_bound=16)
     torch.cuda.synchronize()
     drawn = {k: tuple(t.clone() for t in v[:2]) for k, v in out.items()}
