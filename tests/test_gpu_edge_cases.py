@@ -196,3 +196,50 @@ def test_global_environment_index_beyond_32_bits_matches_oracle(base):
         for k in STATE_KEYS:
             assert np.array_equal(np.asarray(e[k][b]), np.asarray(ob[k])), (b, k)
     env.close()
+
+
+def test_policy_step_tensor_core_inputs_at_the_bound():
+    """The tensor-core kernel takes observations up to |x| = 511 as exact fp16 operands (include/msched.h
+    input_bound): an observation record filled with values over the whole range [-511, 511], the extremes included,
+    gives the fp32 SIMT kernel's probabilities and the same experience rows."""
+    import os
+    import torch
+    from marl_scheduling_b200 import policy
+    dev = torch.device("cuda", 0)
+    B, C, N, L = 300, 3, 2, 3
+    NL, Ua, Uo = N * L, N * C, N * L
+    row_a, row_o = 16, 8                      # the config-3 layout: acceptor rows 15 values behind one pad, offer rows 8
+    stride = Ua * row_a + Uo * row_o
+    g = torch.Generator(device=dev).manual_seed(5)
+    obs = torch.randint(-511, 512, (B, stride), dtype=torch.int16, device=dev, generator=g)
+    obs[0, :] = 511
+    obs[1, :] = -511
+    ga = policy.MlpGroup.random(15, 16, 7, Ua, dev, seed=1)
+    go = policy.MlpGroup.random(8, 16, 4, Uo, dev, seed=2)
+    for grp, n_in in ((ga, 15), (go, 8)):     # small first-layer weights keep the Tanh inputs out of saturation
+        grp.weights[:, :16 * n_in].mul_(0.004)
+    res = {}
+    old = os.environ.get("MSCHED_POLICY_STEP_IMPL")
+    try:
+        for impl in ("tc", "simt"):
+            os.environ["MSCHED_POLICY_STEP_IMPL"] = impl
+            pa = torch.zeros((B, Ua, 7), device=dev)
+            po = torch.zeros((B, Uo, 4), device=dev)
+            xa = torch.zeros((B, Ua, row_a), dtype=torch.int16, device=dev)
+            xo = torch.zeros((B, Uo, row_o), dtype=torch.int16, device=dev)
+            A_ = policy.policy_step_group(ga, Ua, 1, row_a, 0, 1, x_used=xa, probs=pa)
+            O_ = policy.policy_step_group(go, Uo, Ua * row_a, row_o, Ua, 2, x_used=xo, probs=po)
+            policy.policy_step(obs, stride, B, C, A_, O_, None, step=1, input_bound=511)
+            torch.cuda.synchronize()
+            res[impl] = (pa, po, xa, xo)
+    finally:
+        os.environ.pop("MSCHED_POLICY_STEP_IMPL", None)
+        if old is not None:
+            os.environ["MSCHED_POLICY_STEP_IMPL"] = old
+    t, s = res["tc"], res["simt"]
+    assert torch.equal(t[2], s[2]) and torch.equal(t[3], s[3])
+    assert torch.equal(t[3][:2].reshape(2, -1), obs[:2, Ua * row_a:].reshape(2, -1))     # the extremes came through
+    for k in (0, 1):
+        assert float((t[k] - s[k]).abs().max()) < 2e-5, k
+        assert float((t[k].sum(-1) - 1).abs().max()) < 1e-5
+    assert float(t[0].std()) > 1e-3                                   # not a saturated / uniform comparison
