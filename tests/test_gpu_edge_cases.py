@@ -243,3 +243,40 @@ def test_policy_step_tensor_core_inputs_at_the_bound():
         assert float((t[k] - s[k]).abs().max()) < 2e-5, k
         assert float((t[k].sum(-1) - 1).abs().max()) < 1e-5
     assert float(t[0].std()) > 1e-3                                   # not a saturated / uniform comparison
+
+
+@pytest.mark.parametrize("B", [None, 1, 3])
+def test_drop_in_loop_at_the_reference_batch_of_one(B):
+    """The reference's own shape: ONE world per process (numberOfEnvironments absent = 1).  The free-price PPO loop of
+    src/trainPPOExperiment4-2.py -- getActionForAllAgents, step, saveRewards, updateAgents -- through the drop-in
+    classes with 1 (and 3) environments: the one-launch policy step on a 1-environment batch, a gradient over T x 1
+    samples per net, returns over a handful of columns."""
+    import torch
+    from marl_scheduling_b200 import SchedulingEnvironment as SE
+    from marl_scheduling_b200.world import World
+    wp = dict(freePrices=True, fixPricesList=[1], numberOfAgents=2, numberOfCores=3, collectionLength=3,
+              possibleJobPriorities=[2, 4, 8], possibleJobLengths=[5, 5, 5], probabilities=[1 / 3] * 3,
+              newJobsPerRoundPerAgent=1, rewardMultiplier=1, episodeLength=10, maxVisibleOffers=4)
+    rl = dict(netZeroOfferReward=0.5, LR_ACTOR=0.003, LR_CRITIC=0.01, OFFER_GAMMA=0.5, ACCEPTOR_GAMMA=0.8733,
+              EPS_CLIP=0.2, RAW_K_EPOCHS=2, ACCEPTOR_K_EPOCHS=2, OFFER_K_EPOCHS=2, CENTRALISATION_SAMPLE=2)
+    if B is not None:
+        wp["numberOfEnvironments"] = B
+    n = 1 if B is None else B
+    world = World(wp)
+    env = SE.PPODividedFreePriceEnv(world, rl, True)
+    accO, offO, aucO = env.reset()
+    total = 0.0
+    for t in range(20):
+        acceptorActions, (core, price) = env.getActionForAllAgents(accO, offO)
+        assert acceptorActions.shape == (n, 2, 3) and core.shape == (n, 2, 3) and price.shape == (n, 2, 3)
+        assert bool(((price == -5) == (core == 0)).all())
+        accO, offO, aucO, offR, accR, aucR, agR, q, done = env.step((core, price), acceptorActions, None)
+        assert bool(done) == ((t + 1) % 10 == 0) if not torch.is_tensor(done) else bool(done.all()) == ((t + 1) % 10 == 0)
+        env.saveRewards(offR, accR, agR)
+        total += float(torch.as_tensor(agR).sum())
+    before = env.agents.acceptor.actor.detach().clone()
+    env.updateAgents()
+    after = env.agents.acceptor.actor.detach()
+    assert torch.isfinite(after).all() and torch.isfinite(env.agents.price.actor).all()
+    assert not torch.equal(before, after)
+    env.close()
