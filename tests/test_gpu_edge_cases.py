@@ -280,3 +280,35 @@ def test_drop_in_loop_at_the_reference_batch_of_one(B):
     assert torch.isfinite(after).all() and torch.isfinite(env.agents.price.actor).all()
     assert not torch.equal(before, after)
     env.close()
+
+
+def test_dqn_drop_in_loop_with_one_world():
+    """The DQN loop of src/trainDQN.py:171-186 with ONE world: optimize_model returns nothing until the replay memory
+    holds a batch (src/DQNmodules.py:98-99), then finite losses; one transition per step and unit is stored."""
+    import torch
+    from marl_scheduling_b200 import SchedulingEnvironment as SE
+    from marl_scheduling_b200.world import World
+    wp = dict(freePrices=False, fixPricesList=[2, 7], numberOfAgents=2, numberOfCores=2, collectionLength=3,
+              possibleJobPriorities=[3, 10], possibleJobLengths=[6, 3], probabilities=[0.8, 0.2],
+              newJobsPerRoundPerAgent=1, rewardMultiplier=1, episodeLength=10, maxVisibleOffers=4, seed=2)
+    params = dict(netZeroOfferReward=0.5, RUN_END=0.05, RUN_START=0.9, RUN_DECAY=200, BATCH_SIZE=8,
+                  OFFER_GAMMA=0.5, ACCEPTOR_GAMMA=0.87, REPLAY_MEMORY_SIZE=64)
+    world = World(wp)
+    env = SE.DQNDividedFixedPricesEnv(world, params)
+    accO, offO, aucO = env.reset()
+    got = []
+    for t in range(20):
+        oldA, oldO = accO, offO
+        acceptorActions, offerActions = env.getActionForAllAgents(accO, offO)
+        assert acceptorActions.shape[0] == 1 and offerActions.shape[0] == 1
+        aa = world.auctioneer.getAuctioneerAction(aucO)
+        actA, actO = acceptorActions.clone(), offerActions.clone()
+        accO, offO, aucO, offR, accR, aucR, agR, q, done = env.step(offerActions, acceptorActions, aa)
+        l1 = env.updateOfferMemoriesAndOptimize(oldO, actO, offO, offR[..., 0])
+        l2 = env.updateAcceptorMemoriesAndOptimize(oldA, actA, accO, accR[..., 0])
+        got.append(l1 is not None and l2 is not None)
+        if got[-1]:
+            assert bool(torch.isfinite(l1).all()) and bool(torch.isfinite(l2).all())
+    assert got[:7] == [False] * 7 and all(got[7:])      # a batch of 8 exists from the 8th transition on
+    assert len(env.agents.acceptor.memory) == 20
+    env.close()
