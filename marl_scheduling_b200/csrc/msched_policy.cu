@@ -60,19 +60,30 @@ int msched_returns(const float *rewards, int T, int M, double gamma, int normali
     if (normalise && T < 2) return fail(MSCHED_E_ARG, "normalisation needs T >= 2");
     if (M == 0) return MSCHED_OK;  // an empty buffer has no address to check
     if (!rewards || !out) return fail(MSCHED_E_ARG, "null rewards/out");
-    // TMA-tiled kernel (every reward read once) when the rows are 16-byte aligned and a [T][128] tile fits in
-    // shared memory; the streaming kernel otherwise
-    const size_t tileBytes = (size_t)T * 128 * sizeof(float);
-    if ((M & 3) == 0 && tileBytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(rewards) & 15) == 0 &&
-        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-        static size_t attr = 0;
-        if (tileBytes > attr) {
-            CUDA_TRY(cudaFuncSetAttribute(returns_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-            attr = 200 * 1024;
+    // TMA-tiled kernel (every reward read once) when the rows are 16-byte aligned and a [T][W] tile fits in shared
+    // memory -- W = 128 columns up to T = 400, 64 up to 800, 32 up to 1,600 (narrower tiles are not faster: 261 / 263 /
+    // 284 us at T = 200, the float64 chain of a column is the bound) -- the streaming kernel otherwise
+    if ((M & 3) == 0 && (reinterpret_cast<uintptr_t>(rewards) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        int W = 0;
+        for (int w = 128; w >= 32 && !W; w >>= 1)
+            if ((size_t)T * w * sizeof(float) <= 200 * 1024) W = w;
+        if (const char *e = getenv("MSCHED_RETURNS_W")) { const int v = atoi(e); if ((v == 32 || v == 64 || v == 128) && (size_t)T * v * sizeof(float) <= 200 * 1024) W = v; }
+        if (W) {
+            const size_t tileBytes = (size_t)T * W * sizeof(float);
+            static bool attr = false;
+            if (!attr) {
+                CUDA_TRY(cudaFuncSetAttribute(returns_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+                CUDA_TRY(cudaFuncSetAttribute(returns_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+                CUDA_TRY(cudaFuncSetAttribute(returns_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+                attr = true;
+            }
+            cudaStream_t s = static_cast<cudaStream_t>(stream);
+            if (W == 128) returns_tile_kernel<128><<<(M + 127) / 128, 128, tileBytes, s>>>(rewards, T, M, gamma, normalise, out);
+            else if (W == 64) returns_tile_kernel<64><<<(M + 63) / 64, 64, tileBytes, s>>>(rewards, T, M, gamma, normalise, out);
+            else returns_tile_kernel<32><<<(M + 31) / 32, 32, tileBytes, s>>>(rewards, T, M, gamma, normalise, out);
+            CUDA_TRY(cudaGetLastError());
+            return MSCHED_OK;
         }
-        returns_tile_kernel<<<(M + 127) / 128, 128, tileBytes, static_cast<cudaStream_t>(stream)>>>(rewards, T, M, gamma, normalise, out);
-        CUDA_TRY(cudaGetLastError());
-        return MSCHED_OK;
     }
     returns_kernel<<<(M + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(rewards, T, M, gamma,
                                                                                    normalise, out);

@@ -45,32 +45,33 @@ __global__ void returns_kernel(const float *__restrict__ r, int T, int M, double
 }
 
 // ---- discounted returns, TMA-tiled -----------------------------------------------------------------
-// The same computation with every reward read from HBM ONCE: a CTA owns 128 consecutive units; one thread issues a
-// 512-byte bulk copy (cp.async.bulk, 1-D TMA) per time step, all T of them in flight at once on one mbarrier, so
+// The same computation with every reward read from HBM ONCE: a CTA owns W consecutive units; one thread issues a
+// 4W-byte bulk copy (cp.async.bulk, 1-D TMA) per time step, all T of them in flight at once on one mbarrier, so
 // the whole [T][128] reward tile (100 KB at T = 200) lands in shared memory at full memory-level parallelism.
 // Each thread then scans its column backwards in float64 like the Python loop, keeps G in place of r, forms the
 // moments, normalises in place, and the tile leaves with T bulk stores.  8 B/element of HBM traffic instead of 12
 // and no second float64 chain.  Needs M % 4 == 0 (16-byte rows) and T * 512 B of shared memory.
-__global__ void __launch_bounds__(128) returns_tile_kernel(const float *__restrict__ r, int T, int M, double gamma, int normalise,
+template <int W>
+__global__ void __launch_bounds__(W) returns_tile_kernel(const float *__restrict__ r, int T, int M, double gamma, int normalise,
                                                            float *__restrict__ out)
 {
-    extern __shared__ __align__(128) float tile[];  // [T][128]
+    extern __shared__ __align__(128) float tile[];  // [T][W]
     __shared__ __align__(8) uint64_t bar;
-    const int m0 = blockIdx.x * 128, tid = threadIdx.x;
-    const int cols = min(128, M - m0);  // a multiple of 4
+    const int m0 = blockIdx.x * W, tid = threadIdx.x;
+    const int cols = min(W, M - m0);  // a multiple of 4
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_expect_tx(&bar, (uint32_t)T * (uint32_t)cols * 4u);
-        for (int t = 0; t < T; ++t) bulk_g2s(tile + t * 128, r + (size_t)t * M + m0, (uint32_t)cols * 4u, &bar);
+        for (int t = 0; t < T; ++t) bulk_g2s(tile + t * W, r + (size_t)t * M + m0, (uint32_t)cols * 4u, &bar);
     }
     __syncthreads();
     mbar_wait(&bar, 0);
     if (tid < cols) {
         double disc = 0.0, s1 = 0.0, s2 = 0.0;
         for (int t = T - 1; t >= 0; --t) {
-            disc = __dadd_rn((double)tile[t * 128 + tid], __dmul_rn(gamma, disc));
+            disc = __dadd_rn((double)tile[t * W + tid], __dmul_rn(gamma, disc));
             const float g = (float)disc;
-            tile[t * 128 + tid] = g;
+            tile[t * W + tid] = g;
             s1 += (double)g;
             s2 += (double)g * (double)g;
         }
@@ -81,13 +82,13 @@ __global__ void __launch_bounds__(128) returns_tile_kernel(const float *__restri
             if (var < 0.0) var = 0.0;
             const float denom = (float)sqrt(var) + 1e-7f;
 #pragma unroll 8
-            for (int t = 0; t < T; ++t) tile[t * 128 + tid] = (tile[t * 128 + tid] - mean) / denom;
+            for (int t = 0; t < T; ++t) tile[t * W + tid] = (tile[t * W + tid] - mean) / denom;
         }
     }
     fence_async_smem();
     __syncthreads();
     if (tid == 0) {
-        for (int t = 0; t < T; ++t) bulk_s2g(out + (size_t)t * M + m0, tile + t * 128, (uint32_t)cols * 4u);
+        for (int t = 0; t < T; ++t) bulk_s2g(out + (size_t)t * M + m0, tile + t * W, (uint32_t)cols * 4u);
         bulk_commit();
         bulk_wait_read();
     }
