@@ -67,18 +67,20 @@ int msched_returns(const float *rewards, int T, int M, double gamma, int normali
         int W = 0;
         for (int w = 128; w >= 32 && !W; w >>= 1)
             if ((size_t)T * w * sizeof(float) <= 200 * 1024) W = w;
-        if (const char *e = getenv("MSCHED_RETURNS_W")) { const int v = atoi(e); if ((v == 32 || v == 64 || v == 128) && (size_t)T * v * sizeof(float) <= 200 * 1024) W = v; }
+        if (const char *e = getenv("MSCHED_RETURNS_W")) { const int v = atoi(e); if ((v == 32 || v == 64 || v == 128 || v == 256) && (size_t)T * v * sizeof(float) <= 200 * 1024) W = v; }
         if (W) {
             const size_t tileBytes = (size_t)T * W * sizeof(float);
             static bool attr = false;
             if (!attr) {
+                CUDA_TRY(cudaFuncSetAttribute(returns_tile_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
                 CUDA_TRY(cudaFuncSetAttribute(returns_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
                 CUDA_TRY(cudaFuncSetAttribute(returns_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
                 CUDA_TRY(cudaFuncSetAttribute(returns_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
                 attr = true;
             }
             cudaStream_t s = static_cast<cudaStream_t>(stream);
-            if (W == 128) returns_tile_kernel<128><<<(M + 127) / 128, 128, tileBytes, s>>>(rewards, T, M, gamma, normalise, out);
+            if (W == 256) returns_tile_kernel<256><<<(M + 255) / 256, 256, tileBytes, s>>>(rewards, T, M, gamma, normalise, out);
+            else if (W == 128) returns_tile_kernel<128><<<(M + 127) / 128, 128, tileBytes, s>>>(rewards, T, M, gamma, normalise, out);
             else if (W == 64) returns_tile_kernel<64><<<(M + 63) / 64, 64, tileBytes, s>>>(rewards, T, M, gamma, normalise, out);
             else returns_tile_kernel<32><<<(M + 31) / 32, 32, tileBytes, s>>>(rewards, T, M, gamma, normalise, out);
             CUDA_TRY(cudaGetLastError());

@@ -62,9 +62,10 @@ __global__ void __launch_bounds__(W) returns_tile_kernel(const float *__restrict
     if (tid == 0) {
         mbar_init(&bar, 1);
         mbar_expect_tx(&bar, (uint32_t)T * (uint32_t)cols * 4u);
-        for (int t = 0; t < T; ++t) bulk_g2s(tile + t * W, r + (size_t)t * M + m0, (uint32_t)cols * 4u, &bar);
     }
     __syncthreads();
+    // every thread issues its share of the T row copies (one thread issuing all of them is a serial chain of T issues)
+    for (int t = tid; t < T; t += W) bulk_g2s(tile + t * W, r + (size_t)t * M + m0, (uint32_t)cols * 4u, &bar);
     mbar_wait(&bar, 0);
     if (tid < cols) {
         double disc = 0.0, s1 = 0.0, s2 = 0.0;
@@ -87,11 +88,9 @@ __global__ void __launch_bounds__(W) returns_tile_kernel(const float *__restrict
     }
     fence_async_smem();
     __syncthreads();
-    if (tid == 0) {
-        for (int t = 0; t < T; ++t) bulk_s2g(out + (size_t)t * M + m0, tile + t * W, (uint32_t)cols * 4u);
-        bulk_commit();
-        bulk_wait_read();
-    }
+    for (int t = tid; t < T; t += W) bulk_s2g(out + (size_t)t * M + m0, tile + t * W, (uint32_t)cols * 4u);
+    bulk_commit();
+    bulk_wait_read();
 }
 
 #endif  // MSCHED_ACTOR_DISPATCH_TU
