@@ -5,6 +5,7 @@
 //   src/PPOmodules.py:114-125       PPO.selectAction (state.float())
 //   src/PPOmodules.py:128-137       PPO.update returns prologue
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
 #include "msched_common.cuh"
 #include "policy_common.cuh"
 
@@ -91,6 +92,62 @@ __global__ void __launch_bounds__(W) returns_tile_kernel(const float *__restrict
     for (int t = tid; t < T; t += W) bulk_s2g(out + (size_t)t * M + m0, tile + t * W, (uint32_t)cols * 4u);
     bulk_commit();
     bulk_wait_read();
+}
+
+// The tile moved by ONE 2-D tensor-map copy each way (cp.async.bulk.tensor.2d, box [T][W], T <= 256): the 1-D version
+// above issues 2 T row copies of 512 bytes per tile, and the copy unit's fixed time per copy -- not the bytes -- is what
+// bounds it (1.2 M copies per call at T = 200, 393,216 units).  Columns beyond M are filled with zeros on the way in and
+// dropped on the way out by the copy unit.  The wait is bounded: a descriptor the hardware rejects traps instead of hanging
+template <int W>
+__global__ void __launch_bounds__(W) returns_tmap_kernel(const __grid_constant__ CUtensorMap tin, const __grid_constant__ CUtensorMap tout,
+                                                           int T, int M, double gamma, int normalise)
+{
+    extern __shared__ __align__(128) float tile[];  // [T][W]
+    __shared__ __align__(8) uint64_t bar;
+    const int m0 = blockIdx.x * W, tid = threadIdx.x;
+    const int cols = min(W, M - m0);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_async_smem();
+        mbar_expect_tx(&bar, (uint32_t)T * (uint32_t)W * 4u);  // the whole box counts, clipped or not
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                     ::"r"(smem_u32(tile)), "l"(&tin), "r"(m0), "r"(0), "r"(smem_u32(&bar)) : "memory");
+    }
+    __syncthreads();
+    {
+        uint32_t ok = 0u;
+        for (int it = 0; it < (1 << 22) && !ok; ++it)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(ok) : "r"(smem_u32(&bar)), "r"(0u) : "memory");
+        if (!ok) __trap();
+    }
+    if (tid < cols) {
+        double disc = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int t = T - 1; t >= 0; --t) {
+            disc = __dadd_rn((double)tile[t * W + tid], __dmul_rn(gamma, disc));
+            const float g = (float)disc;
+            tile[t * W + tid] = g;
+            s1 += (double)g;
+            s2 += (double)g * (double)g;
+        }
+        if (normalise) {
+            const float mean = (float)(s1 / T);
+            const double dm = (double)mean;
+            double var = (s2 - 2.0 * dm * s1 + (double)T * dm * dm) / (double)(T - 1);
+            if (var < 0.0) var = 0.0;
+            const float denom = (float)sqrt(var) + 1e-7f;
+#pragma unroll 8
+            for (int t = 0; t < T; ++t) tile[t * W + tid] = (tile[t * W + tid] - mean) / denom;
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (tid == 0) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                     ::"l"(&tout), "r"(m0), "r"(0), "r"(smem_u32(tile)) : "memory");
+        bulk_commit();
+        bulk_wait_read();
+    }
 }
 
 #endif  // MSCHED_ACTOR_DISPATCH_TU
