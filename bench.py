@@ -1066,9 +1066,12 @@ def main():
                            "into the action record, state / action / log-prob into the experience-buffer slot of the step) + the fused "
                            "env step + observations; 8 consecutive steps (8 buffer slots) captured in a CUDA graph and replayed (the one-thread increment of the policy's step counter sits on a graph branch beside the env step)",
                    "sticky_flags": rflags,
+                   # 8 B/element (read r, write G); the tiled kernels normalise in shared memory, so
+                   # that is also their HBM traffic (rounds 1-2 counted 12 B for a streaming second pass)
                    "returns_kernel": {"T": T, "units": B * N * Cc, "us": ret_us,
-                                      "gbs": 12.0 * rew.numel() / ret_us / 1e3,
-                                      "algorithmic_bytes_per_element": 12}}
+                                      "gbs": 8.0 * rew.numel() / ret_us / 1e3,
+                                      "hbm_frac": 8.0 * rew.numel() / ret_us / 1e3 / measured_peak()[0],
+                                      "algorithmic_bytes_per_element": 8}}
 
     # ---- PPO.update on the device: one epoch = one forward+backward launch over the
     # acceptor units' buffer (T x B samples per net) + Adam; the PyTorch autograd version of the same

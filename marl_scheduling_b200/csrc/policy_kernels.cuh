@@ -17,6 +17,15 @@ namespace msched {
 // time step.  G_t = r_t + gamma*G_{t+1} in float64 like the Python loop, cast to float32; the
 // normalisation statistics are accumulated in float64 over the float32 values in the same sweep
 // and a second sweep recomputes G instead of re-reading it (12 B/element of HBM traffic).
+// x / d for one divisor d and many x: the quotient from the reciprocal (computed once per column) plus one residual
+// correction -- q = x * (1/d); q += (x - q d) * (1/d) -- which is the correctly rounded quotient except in rare last-bit
+// ties (the inline IEEE division is ~14 instructions per element and was 56 % of the tensor-map kernel's instructions)
+__device__ __forceinline__ float div_by(float x, float d, float inv)
+{
+    const float q = x * inv;
+    return fmaf(fmaf(-q, d, x), inv, q);
+}
+
 __global__ void returns_kernel(const float *__restrict__ r, int T, int M, double gamma, int normalise,
                                float *__restrict__ out)
 {
@@ -37,11 +46,11 @@ __global__ void returns_kernel(const float *__restrict__ r, int T, int M, double
     double var = (s2 - 2.0 * dm * s1 + (double)T * dm * dm) / (double)(T - 1);
     if (var < 0.0) var = 0.0;
     const float sd = (float)sqrt(var);
-    const float denom = sd + 1e-7f;
+    const float denom = sd + 1e-7f, inv = 1.0f / denom;
     disc = 0.0;
     for (int t = T - 1; t >= 0; --t) {
         disc = __dadd_rn((double)r[(size_t)t * M + m], __dmul_rn(gamma, disc));
-        out[(size_t)t * M + m] = ((float)disc - mean) / denom;
+        out[(size_t)t * M + m] = div_by((float)disc - mean, denom, inv);
     }
 }
 
@@ -82,9 +91,9 @@ __global__ void __launch_bounds__(W) returns_tile_kernel(const float *__restrict
             const double dm = (double)mean;
             double var = (s2 - 2.0 * dm * s1 + (double)T * dm * dm) / (double)(T - 1);
             if (var < 0.0) var = 0.0;
-            const float denom = (float)sqrt(var) + 1e-7f;
+            const float denom = (float)sqrt(var) + 1e-7f, inv = 1.0f / denom;
 #pragma unroll 8
-            for (int t = 0; t < T; ++t) tile[t * W + tid] = (tile[t * W + tid] - mean) / denom;
+            for (int t = 0; t < T; ++t) tile[t * W + tid] = div_by(tile[t * W + tid] - mean, denom, inv);
         }
     }
     fence_async_smem();
@@ -135,9 +144,9 @@ __global__ void __launch_bounds__(W) returns_tmap_kernel(const __grid_constant__
             const double dm = (double)mean;
             double var = (s2 - 2.0 * dm * s1 + (double)T * dm * dm) / (double)(T - 1);
             if (var < 0.0) var = 0.0;
-            const float denom = (float)sqrt(var) + 1e-7f;
+            const float denom = (float)sqrt(var) + 1e-7f, inv = 1.0f / denom;
 #pragma unroll 8
-            for (int t = 0; t < T; ++t) tile[t * W + tid] = (tile[t * W + tid] - mean) / denom;
+            for (int t = 0; t < T; ++t) tile[t * W + tid] = div_by(tile[t * W + tid] - mean, denom, inv);
         }
     }
     fence_async_smem();

@@ -12,4 +12,4 @@ for T, M in ((200, 393216), (16, 393216), (64, 1 << 20)):
     for _ in range(10): policy.returns(rew, 0.8733, True)
     e1.record(); torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 100
-    print(os.environ.get("MSCHED_RETURNS_W", "auto"), T, M, f"{us:.1f} us", f"{12 * T * M / us / 1e3:.0f} GB/s (12 B/elem)")
+    print(os.environ.get("MSCHED_RETURNS_W", "auto"), T, M, f"{us:.1f} us", f"{8 * T * M / us / 1e3:.0f} GB/s (8 B/elem: read r, write G)")
